@@ -1,0 +1,220 @@
+"""ctypes binding of the CPU ORACLE (oracle/_build/liboracle.so).  TEST INFRASTRUCTURE ONLY.
+
+Only tests/, __graft_entry__.smoke() and bench.py (cpu_baseline / --impl reference) may import
+this module; the product package cube_slam_b200 never does.
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB_PATH = os.path.join(_HERE, "_build", "liboracle.so")
+
+
+def build(force=False):
+    """Compile the oracle with the committed Makefile (g++ -O2 -ffp-contract=off)."""
+    srcs = [os.path.join(_HERE, f) for f in os.listdir(_HERE) if f.endswith((".cpp", ".h"))]
+    if (not force and os.path.exists(_LIB_PATH)
+            and all(os.path.getmtime(_LIB_PATH) >= os.path.getmtime(s) for s in srcs)):
+        return _LIB_PATH
+    subprocess.check_call(["make", "-C", _HERE, "-s"] + (["-B"] if force else []))
+    return _LIB_PATH
+
+
+class Params(C.Structure):
+    _fields_ = [
+        ("consider_config_1", C.c_int), ("consider_config_2", C.c_int),
+        ("whether_sample_cam_roll_pitch", C.c_int), ("whether_sample_bbox_height", C.c_int),
+        ("max_cuboid_num", C.c_int),
+        ("nominal_skew_ratio", C.c_double), ("max_cut_skew", C.c_double),
+        ("vp12_edge_angle_thre", C.c_double), ("vp3_edge_angle_thre", C.c_double),
+        ("shorted_edge_thre", C.c_double), ("reweight_edge_distance", C.c_int),
+        ("whether_normalize_two_errors", C.c_int),
+        ("weight_vp_angle", C.c_double), ("weight_skew_error", C.c_double),
+        ("pre_merge_dist_thre", C.c_double), ("pre_merge_angle_thre", C.c_double),
+        ("edge_length_threshold", C.c_double),
+        ("canny_low", C.c_double), ("canny_high", C.c_double),
+        ("yaw_half_range_deg", C.c_double), ("yaw_step_deg", C.c_double),
+        ("top_sample_count_override", C.c_int),
+    ]
+
+
+class Cuboid(C.Structure):
+    _fields_ = [
+        ("pos", C.c_double * 3), ("scale", C.c_double * 3), ("rotY", C.c_double),
+        ("box_config_type", C.c_double * 2),
+        ("box_corners_2d", C.c_int32 * 16),
+        ("box_corners_3d_world", C.c_double * 24),
+        ("rect_detect_2d", C.c_double * 4),
+        ("edge_distance_error", C.c_double), ("edge_angle_error", C.c_double),
+        ("normalized_error", C.c_double), ("skew_ratio", C.c_double),
+        ("down_expand_height", C.c_double),
+        ("camera_roll_delta", C.c_double), ("camera_pitch_delta", C.c_double),
+        ("combined_score", C.c_double),
+        ("proposal_index", C.c_int32), ("height_sample_id", C.c_int32),
+        ("valid", C.c_int32), ("pad_", C.c_int32),
+    ]
+
+
+CUBOID_DTYPE = np.dtype([
+    ("pos", "f8", 3), ("scale", "f8", 3), ("rotY", "f8"), ("box_config_type", "f8", 2),
+    ("box_corners_2d", "i4", (2, 8)), ("box_corners_3d_world", "f8", (3, 8)),
+    ("rect_detect_2d", "f8", 4), ("edge_distance_error", "f8"), ("edge_angle_error", "f8"),
+    ("normalized_error", "f8"), ("skew_ratio", "f8"), ("down_expand_height", "f8"),
+    ("camera_roll_delta", "f8"), ("camera_pitch_delta", "f8"), ("combined_score", "f8"),
+    ("proposal_index", "i4"), ("height_sample_id", "i4"), ("valid", "i4"), ("pad_", "i4"),
+])
+assert CUBOID_DTYPE.itemsize == C.sizeof(Cuboid)
+
+
+class Trace(C.Structure):
+    _fields_ = [
+        ("want_object", C.c_int), ("want_height_sample", C.c_int),
+        ("roi", C.c_int * 4), ("n_lines_roi", C.c_int), ("n_lines_merged", C.c_int),
+        ("merged_lines", C.POINTER(C.c_double)), ("cap_lines", C.c_int),
+        ("canny", C.POINTER(C.c_uint8)), ("dist", C.POINTER(C.c_float)), ("cap_px", C.c_int),
+        ("n_candidates", C.c_int), ("n_valid", C.c_int),
+        ("rows", C.POINTER(C.c_double)), ("corners", C.POINTER(C.c_double)),
+        ("cand_index", C.POINTER(C.c_int32)), ("cap_valid", C.c_int),
+        ("n_kept", C.c_int), ("kept_ids", C.POINTER(C.c_int32)), ("kept_scores", C.POINTER(C.c_double)),
+    ]
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        build()
+        _lib = C.CDLL(_LIB_PATH)
+        _lib.orc_default_params.argtypes = [C.POINTER(Params)]
+        _lib.orc_detect_cuboid.restype = C.c_int
+        _lib.orc_merge_break_lines.restype = C.c_int
+        for name in ("lsd_orc_detect", "edl_orc_detect"):
+            if hasattr(_lib, name):
+                getattr(_lib, name).restype = C.c_int
+    return _lib
+
+
+def _p(a, t):
+    return a.ctypes.data_as(C.POINTER(t))
+
+
+def default_params(**kw):
+    p = Params()
+    lib().orc_default_params(C.byref(p))
+    for k, v in kw.items():
+        if not hasattr(p, k):
+            raise AttributeError(k)
+        setattr(p, k, v)
+    return p
+
+
+def bgr2gray(bgr, fixed15=True):
+    bgr = np.ascontiguousarray(bgr, np.uint8)
+    h, w = bgr.shape[:2]
+    out = np.empty((h, w), np.uint8)
+    lib().orc_bgr2gray(_p(bgr, C.c_uint8), w, h, w * 3, _p(out, C.c_uint8), w, int(fixed15))
+    return out
+
+
+def canny(gray, low=80.0, high=200.0):
+    gray = np.ascontiguousarray(gray, np.uint8)
+    h, w = gray.shape
+    out = np.empty((h, w), np.uint8)
+    lib().orc_canny(_p(gray, C.c_uint8), w, h, w, C.c_double(low), C.c_double(high), _p(out, C.c_uint8))
+    return out
+
+
+def chamfer_dt(edges):
+    edges = np.ascontiguousarray(edges, np.uint8)
+    h, w = edges.shape
+    out = np.empty((h, w), np.float32)
+    lib().orc_chamfer_dt(_p(edges, C.c_uint8), w, h, _p(out, C.c_float))
+    return out
+
+
+def merge_break_lines(lines, dist_thre=20.0, angle_thre_deg=5.0, len_thre=30.0):
+    lines = np.ascontiguousarray(lines, np.float64).reshape(-1, 4)
+    out = np.empty_like(lines)
+    n = lib().orc_merge_break_lines(_p(lines, C.c_double), len(lines), C.c_double(dist_thre),
+                                    C.c_double(angle_thre_deg), C.c_double(len_thre), _p(out, C.c_double))
+    return out[:n].copy()
+
+
+def cam_pose(K, T):
+    K = np.ascontiguousarray(K, np.float64)
+    T = np.ascontiguousarray(T, np.float64)
+    out = np.empty(13)
+    lib().orc_cam_pose(_p(K, C.c_double), _p(T, C.c_double), _p(out, C.c_double))
+    return {"euler": out[:3].copy(), "KinvR": out[3:12].reshape(3, 3).copy(), "yaw": out[12]}
+
+
+def detect_cuboid(img, K, T_wc, boxes, lines, params=None, topk_cap=None, trace_object=None,
+                  trace_height_sample=0, trace_caps=(4096, 1 << 21, 1 << 16)):
+    """detect_3d_cuboid::detect_cuboid for one frame (box_proposal_detail.cpp:56-557).
+
+    Returns dict(cuboids=[structured array per bbox], n_candidates, n_valid, trace=dict|None)."""
+    L = lib()
+    if params is None:
+        params = default_params()
+    img = np.ascontiguousarray(img, np.uint8)
+    h, w = img.shape[:2]
+    ch = 1 if img.ndim == 2 else img.shape[2]
+    K = np.ascontiguousarray(K, np.float64).reshape(3, 3)
+    T_wc = np.ascontiguousarray(T_wc, np.float64).reshape(4, 4)
+    boxes = np.ascontiguousarray(boxes, np.float64).reshape(-1, 5)
+    lines = np.ascontiguousarray(lines, np.float64).reshape(-1, 4)
+    N = len(boxes)
+    if topk_cap is None:
+        topk_cap = max(int(params.max_cuboid_num), 1)
+    out = np.zeros((max(N, 1), topk_cap), CUBOID_DTYPE)
+    counts = np.zeros(max(N, 1), np.int32)
+    ncand = C.c_int64(0)
+    nvalid = C.c_int64(0)
+    tr = None
+    bufs = None
+    if trace_object is not None:
+        cap_lines, cap_px, cap_valid = trace_caps
+        bufs = dict(
+            merged_lines=np.zeros((cap_lines, 4)), canny=np.zeros(cap_px, np.uint8), dist=np.zeros(cap_px, np.float32),
+            rows=np.zeros((cap_valid, 9)), corners=np.zeros((cap_valid, 16)), cand_index=np.zeros(cap_valid, np.int32),
+            kept_ids=np.zeros(cap_valid, np.int32), kept_scores=np.zeros(cap_valid))
+        tr = Trace()
+        tr.want_object = trace_object
+        tr.want_height_sample = trace_height_sample
+        tr.merged_lines = _p(bufs["merged_lines"], C.c_double)
+        tr.cap_lines = cap_lines
+        tr.canny = _p(bufs["canny"], C.c_uint8)
+        tr.dist = _p(bufs["dist"], C.c_float)
+        tr.cap_px = cap_px
+        tr.rows = _p(bufs["rows"], C.c_double)
+        tr.corners = _p(bufs["corners"], C.c_double)
+        tr.cand_index = _p(bufs["cand_index"], C.c_int32)
+        tr.cap_valid = cap_valid
+        tr.kept_ids = _p(bufs["kept_ids"], C.c_int32)
+        tr.kept_scores = _p(bufs["kept_scores"], C.c_double)
+    rc = L.orc_detect_cuboid(_p(img, C.c_uint8), w, h, img.strides[0], ch, _p(K, C.c_double), _p(T_wc, C.c_double),
+                             _p(boxes, C.c_double), N, _p(lines, C.c_double), len(lines), C.byref(params), topk_cap,
+                             out.ctypes.data_as(C.POINTER(Cuboid)), _p(counts, C.c_int),
+                             C.byref(ncand), C.byref(nvalid), C.byref(tr) if tr is not None else None)
+    if rc != 0:
+        raise RuntimeError("orc_detect_cuboid failed: %d" % rc)
+    res = {"cuboids": [out[i, :counts[i]].copy() for i in range(N)], "n_candidates": ncand.value,
+           "n_valid": nvalid.value, "trace": None}
+    if tr is not None:
+        rw, rh = tr.roi[2], tr.roi[3]
+        npx = max(rw, 0) * max(rh, 0)
+        res["trace"] = dict(
+            roi=tuple(tr.roi), n_lines_roi=tr.n_lines_roi, n_lines_merged=tr.n_lines_merged,
+            merged_lines=bufs["merged_lines"][:tr.n_lines_merged].copy(),
+            canny=bufs["canny"][:npx].reshape(rh, rw).copy() if npx <= trace_caps[1] else None,
+            dist=bufs["dist"][:npx].reshape(rh, rw).copy() if npx <= trace_caps[1] else None,
+            n_candidates=tr.n_candidates, n_valid=tr.n_valid,
+            rows=bufs["rows"][:tr.n_valid].copy(), corners=bufs["corners"][:tr.n_valid].copy(),
+            cand_index=bufs["cand_index"][:tr.n_valid].copy(),
+            n_kept=tr.n_kept, kept_ids=bufs["kept_ids"][:tr.n_kept].copy(), kept_scores=bufs["kept_scores"][:tr.n_kept].copy())
+    return res
