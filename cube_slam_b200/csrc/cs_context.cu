@@ -1,0 +1,724 @@
+/*
+ * cs_context.cu -- the C ABI of libcubeslam_b200.so: context, batch orchestration, host<->device.
+ *
+ * Host work per batch is O(frames + boxes): the camera-pose tables, the sample grids and the
+ * per-box ROI job descriptors of detect_cuboid (box_proposal_detail.cpp:59-60,99-163,215-226);
+ * everything per pixel / per line / per proposal runs in the CUDA kernels.
+ */
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "cs_host_pose.h"
+#include "cs_internal.h"
+#include "cs_kernels.h"
+
+namespace {
+
+struct DevBuf {
+    void *p = nullptr;
+    size_t cap = 0;
+};
+
+enum Stage { ST_GRAY, ST_CANNY, ST_HYST, ST_DT, ST_LINES, ST_SWEEP, ST_FUSE, ST_COUNT };
+const char *kStageNames[ST_COUNT] = {"gray", "canny", "hyst", "dt", "lines", "sweep", "fuse"};
+
+}  // namespace
+
+struct cs_ctx {
+    int device = 0;
+    int max_w = 0, max_h = 0, max_frames = 0, max_boxes = 0, max_lines = 0;
+    cudaStream_t stream = nullptr;
+    std::string err;
+    double K[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
+    double invK[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
+    bool have_K = false;
+
+    /* current batch (host copies of the small inputs) */
+    bool prepared = false;
+    int n_frames = 0, w = 0, h = 0, stride = 0, channels = 0;
+    cs_cuboid_params prm;
+    std::vector<double> h_T, h_boxes, h_lines;
+    std::vector<int32_t> h_box_off, h_line_off;
+    int topk = 1;
+
+    /* host tables built by build_tables() */
+    std::vector<CsFrame> frames;
+    std::vector<CsPose> poses;
+    std::vector<double> yaws;
+    std::vector<CsJob> jobs;
+    std::vector<CsObj> objs;
+    std::vector<CsTile> tiles;
+    std::vector<int2> sweep_blocks;
+    std::vector<int32_t> dt_ids;
+    int dt_class_off[CS_DT_CLASSES + 1] = {0};
+    int64_t total_px = 0, total_cand = 0;
+
+    /* device buffers (grow only) */
+    DevBuf d_img, d_gray, d_lines, d_frames, d_poses, d_yaws, d_jobs, d_objs, d_tiles, d_blocks, d_dtids;
+    DevBuf d_map, d_queue, d_qtail, d_dist, d_mlines, d_lcounts, d_err;
+    DevBuf d_cvalid, d_cdist, d_cangle, d_vlist, d_key, d_idx, d_flag, d_keep, d_norm, d_score, d_jcounts;
+    DevBuf d_out, d_outcnt, d_gather;
+    void *pinned = nullptr;
+    size_t pinned_cap = 0;
+
+    /* profiling */
+    bool profiling = false;
+    cudaEvent_t ev[ST_COUNT + 1] = {nullptr};
+    cudaEvent_t ev_total[2] = {nullptr, nullptr};
+    float stage_ms[ST_COUNT] = {0};
+    float total_ms = 0;
+    bool stage_valid = false;
+    int64_t launches = 0;
+    cs_batch_stats stats;
+
+    /* NCCL (loaded at run time) */
+    void *nccl_lib = nullptr;
+    void *nccl_comm = nullptr;
+    int world = 1, rank = 0;
+};
+
+#include "cs_nccl.h"
+
+namespace {
+
+int fail(cs_ctx *c, int code, const char *fmt, ...)
+{
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    if (c) c->err = buf;
+    return code;
+}
+
+#define CS_CUDA(c, call)                                                                              \
+    do {                                                                                              \
+        cudaError_t e__ = (call);                                                                     \
+        if (e__ != cudaSuccess) return fail((c), CS_ERR_CUDA, "%s: %s", #call, cudaGetErrorString(e__)); \
+    } while (0)
+
+int ensure(cs_ctx *c, DevBuf &b, size_t bytes)
+{
+    if (bytes <= b.cap) return CS_OK;
+    if (b.p) cudaFree(b.p);
+    b.p = nullptr;
+    b.cap = 0;
+    const size_t want = bytes + bytes / 8 + 256;
+    cudaError_t e = cudaMalloc(&b.p, want);
+    if (e != cudaSuccess) return fail(c, CS_ERR_CUDA, "cudaMalloc(%zu): %s", want, cudaGetErrorString(e));
+    b.cap = want;
+    return CS_OK;
+}
+
+template <class T>
+int upload(cs_ctx *c, DevBuf &b, const std::vector<T> &v)
+{
+    const size_t bytes = sizeof(T) * v.size();
+    int rc = ensure(c, b, std::max<size_t>(bytes, 16));
+    if (rc) return rc;
+    if (bytes) CS_CUDA(c, cudaMemcpyAsync(b.p, v.data(), bytes, cudaMemcpyHostToDevice, c->stream));
+    return CS_OK;
+}
+
+/* Host evaluation of box_proposal_detail.cpp:59-60,99-163,215-226 for the whole batch. */
+int build_tables(cs_ctx *c)
+{
+    const cs_cuboid_params &p = c->prm;
+    const int F = c->n_frames;
+    c->frames.assign(F, CsFrame());
+    c->poses.clear();
+    c->yaws.clear();
+    c->jobs.clear();
+    c->objs.clear();
+    c->tiles.clear();
+    c->sweep_blocks.clear();
+    c->total_px = 0;
+    c->total_cand = 0;
+    const int img_width = c->w, img_height = c->h;
+
+    for (int f = 0; f < F; f++) {
+        CsFrame &fr = c->frames[f];
+        std::memcpy(fr.invK, c->invK, sizeof(fr.invK));
+        const double *T = &c->h_T[(size_t)f * 16];
+        CsPose raw;
+        cshost::make_pose(c->K, T, &raw, fr.euler_raw);
+        fr.pose_off = (int32_t)c->poses.size();
+        if (p.whether_sample_cam_roll_pitch) {
+            /* :215-226, :233-239 */
+            std::vector<double> rolls, pitches;
+            cshost::linespace_d(fr.euler_raw[0] - 6.0 / 180.0 * M_PI, fr.euler_raw[0] + 6.0 / 180.0 * M_PI, 3.0 / 180.0 * M_PI, rolls);
+            cshost::linespace_d(fr.euler_raw[1] - 6.0 / 180.0 * M_PI, fr.euler_raw[1] + 6.0 / 180.0 * M_PI, 3.0 / 180.0 * M_PI, pitches);
+            if ((int)(rolls.size() * pitches.size()) > CS_MAX_POSE) return fail(c, CS_ERR_CAPACITY, "too many roll/pitch samples");
+            for (double r : rolls)
+                for (double q : pitches) {
+                    double Tn[16], Rn[9];
+                    std::memcpy(Tn, T, sizeof(Tn));
+                    cshost::euler_to_rot(r, q, fr.euler_raw[2], Rn);
+                    for (int i = 0; i < 3; i++)
+                        for (int j = 0; j < 3; j++) Tn[i * 4 + j] = Rn[i * 3 + j];
+                    CsPose ps;
+                    cshost::make_pose(c->K, Tn, &ps, nullptr);
+                    ps.roll = r; /* the sampled values are what the reference records (:453) */
+                    ps.pitch = q;
+                    c->poses.push_back(ps);
+                }
+        } else {
+            raw.roll = fr.euler_raw[0];
+            raw.pitch = fr.euler_raw[1];
+            c->poses.push_back(raw);
+        }
+        fr.n_pose = (int32_t)c->poses.size() - fr.pose_off;
+        /* :126-128 */
+        const double yaw_init = raw.camera_yaw - 90.0 / 180.0 * M_PI;
+        std::vector<double> ys;
+        cshost::linespace_d(yaw_init - p.yaw_half_range_deg / 180.0 * M_PI, yaw_init + p.yaw_half_range_deg / 180.0 * M_PI,
+                            p.yaw_step_deg / 180.0 * M_PI, ys);
+        if ((int)ys.size() > CS_MAX_YAW) return fail(c, CS_ERR_CAPACITY, "too many yaw samples (%zu)", ys.size());
+        fr.yaw_off = (int32_t)c->yaws.size();
+        fr.n_yaw = (int32_t)ys.size();
+        c->yaws.insert(c->yaws.end(), ys.begin(), ys.end());
+        fr.line_off = c->h_line_off[f];
+        fr.n_lines = c->h_line_off[f + 1] - c->h_line_off[f];
+
+        for (int b = c->h_box_off[f]; b < c->h_box_off[f + 1]; b++) {
+            const double *bb = &c->h_boxes[(size_t)b * 5];
+            /* :107-112 */
+            const int left_x_raw = (int)bb[0], top_y_raw = (int)bb[1];
+            const int obj_width_raw = (int)bb[2], obj_height_raw = (int)bb[3];
+            const int right_x_raw = (int)(left_x_raw + bb[2]);
+            CsObj ob;
+            ob.frame = f;
+            ob.job_off = (int32_t)c->jobs.size();
+            ob.left = left_x_raw;
+            ob.top = top_y_raw;
+            ob.width_raw = obj_width_raw;
+            ob.height_raw = obj_height_raw;
+            /* :114-123 */
+            int hs_list[3], n_hs = 0;
+            hs_list[n_hs++] = 0;
+            if (p.whether_sample_bbox_height) {
+                int r = std::max(std::min(20, obj_height_raw - 90), 20);
+                r = std::min(r, img_height - top_y_raw - obj_height_raw - 1);
+                if (r > 10) hs_list[n_hs++] = (int)std::round(r / 2);
+                hs_list[n_hs++] = r;
+            }
+            for (int hs = 0; hs < n_hs; hs++) {
+                CsJob jb;
+                std::memset(&jb, 0, sizeof(jb));
+                jb.frame = f;
+                jb.obj = b;
+                jb.hs = hs;
+                jb.left = left_x_raw;
+                jb.top = top_y_raw;
+                jb.right = right_x_raw;
+                jb.width_raw = obj_width_raw;
+                jb.height_raw = obj_height_raw;
+                jb.down_expand = hs_list[hs];
+                const int obj_height_expan = obj_height_raw + jb.down_expand;
+                jb.down_y_expan = top_y_raw + obj_height_expan;
+                jb.diag = std::sqrt((double)(obj_width_raw * obj_width_raw + obj_height_expan * obj_height_expan)); /* :141 */
+                /* :144-146 */
+                jb.top_lo = left_x_raw + 5;
+                jb.top_hi = right_x_raw - 5;
+                if (p.top_sample_count_override > 0) {
+                    jb.top_override = 1;
+                    jb.top_step = 1;
+                    jb.n_top = (jb.top_hi >= jb.top_lo) ? p.top_sample_count_override : 0;
+                } else {
+                    jb.top_step = (int)std::round(std::min(20, obj_width_raw / 10));
+                    jb.n_top = cshost::linespace_count_i(jb.top_lo, jb.top_hi, jb.top_step);
+                }
+                /* :155-161 */
+                const int e = std::min(std::max(std::min(20, obj_width_raw - 100), 10), std::max(std::min(20, obj_height_expan - 100), 10));
+                jb.roi_l = std::max(0, left_x_raw - e);
+                jb.roi_r = std::min(img_width - 1, right_x_raw + e);
+                jb.roi_t = std::max(0, top_y_raw - e);
+                jb.roi_b = std::min(img_height - 1, jb.down_y_expan + e);
+                jb.roi_w = jb.roi_r - jb.roi_l;
+                jb.roi_h = jb.roi_b - jb.roi_t;
+                if (jb.roi_w <= 0 || jb.roi_h <= 0 || jb.roi_l + jb.roi_w > img_width || jb.roi_t + jb.roi_h > img_height || jb.roi_l >= img_width ||
+                    jb.roi_t >= img_height)
+                    return fail(c, CS_ERR_INVALID_ARG, "frame %d box %d: empty or out-of-image ROI", f, b - c->h_box_off[f]);
+                if (cs_dt_class_of(jb.roi_w) < 0) return fail(c, CS_ERR_CAPACITY, "ROI wider than %d px", 32 * 64);
+                jb.n_cand = fr.n_pose * fr.n_yaw * jb.n_top * 2;
+                jb.px_off = c->total_px;
+                c->total_px += ((int64_t)jb.roi_w * jb.roi_h + 15) / 16 * 16;
+                jb.cand_off = c->total_cand;
+                c->total_cand += jb.n_cand;
+                jb.tile_off = (int32_t)c->tiles.size();
+                jb.tiles_x = (jb.roi_w + 31) / 32;
+                const int tiles_y = (jb.roi_h + 31) / 32;
+                const int job_id = (int)c->jobs.size();
+                for (int ty = 0; ty < tiles_y; ty++)
+                    for (int tx = 0; tx < jb.tiles_x; tx++) {
+                        CsTile t;
+                        t.job = job_id;
+                        t.tx = (int16_t)tx;
+                        t.ty = (int16_t)ty;
+                        c->tiles.push_back(t);
+                    }
+                for (int ps = 0; ps < fr.n_pose; ps++) c->sweep_blocks.push_back(make_int2(job_id, ps));
+                c->jobs.push_back(jb);
+            }
+            ob.n_jobs = (int32_t)c->jobs.size() - ob.job_off;
+            c->objs.push_back(ob);
+        }
+    }
+    /* distance-transform width classes */
+    c->dt_ids.clear();
+    for (int cls = 0; cls < CS_DT_CLASSES; cls++) {
+        c->dt_class_off[cls] = (int)c->dt_ids.size();
+        for (size_t j = 0; j < c->jobs.size(); j++)
+            if (cs_dt_class_of(c->jobs[j].roi_w) == cls) c->dt_ids.push_back((int32_t)j);
+    }
+    c->dt_class_off[CS_DT_CLASSES] = (int)c->dt_ids.size();
+    return CS_OK;
+}
+
+int alloc_work(cs_cuboid_params &, cs_ctx *c)
+{
+    int rc;
+    const size_t px = (size_t)std::max<int64_t>(c->total_px, 16), cand = (size_t)std::max<int64_t>(c->total_cand, 16);
+    const size_t nj = std::max<size_t>(c->jobs.size(), 1), no = std::max<size_t>(c->objs.size(), 1);
+    if ((rc = ensure(c, c->d_map, px + 16))) return rc;
+    if ((rc = ensure(c, c->d_queue, px * 4))) return rc;
+    if ((rc = ensure(c, c->d_qtail, nj * 4))) return rc;
+    if ((rc = ensure(c, c->d_dist, px * 4))) return rc;
+    if ((rc = ensure(c, c->d_mlines, nj * CS_MAXL_OUT * 7 * sizeof(double)))) return rc;
+    if ((rc = ensure(c, c->d_lcounts, nj * 2 * 4))) return rc;
+    if ((rc = ensure(c, c->d_err, 16))) return rc;
+    if ((rc = ensure(c, c->d_cvalid, cand))) return rc;
+    if ((rc = ensure(c, c->d_cdist, cand * 8))) return rc;
+    if ((rc = ensure(c, c->d_cangle, cand * 8))) return rc;
+    if ((rc = ensure(c, c->d_vlist, cand * 4))) return rc;
+    if ((rc = ensure(c, c->d_key, cand * 2 * 8))) return rc;
+    if ((rc = ensure(c, c->d_idx, cand * 2 * 4))) return rc;
+    if ((rc = ensure(c, c->d_flag, cand))) return rc;
+    if ((rc = ensure(c, c->d_keep, cand * 4))) return rc;
+    if ((rc = ensure(c, c->d_norm, cand * 8))) return rc;
+    if ((rc = ensure(c, c->d_score, cand * 8))) return rc;
+    if ((rc = ensure(c, c->d_jcounts, nj * 2 * 4))) return rc;
+    if ((rc = ensure(c, c->d_out, no * c->topk * sizeof(cs_cuboid_rec)))) return rc;
+    if ((rc = ensure(c, c->d_outcnt, no * 4))) return rc;
+    return CS_OK;
+}
+
+int run_batch(cs_ctx *c, bool sync)
+{
+    if (!c->prepared) return fail(c, CS_ERR_NOT_PREPARED, "no batch uploaded");
+    int rc;
+    cudaStream_t st = c->stream;
+    c->launches = 0;
+    if (c->profiling) cudaEventRecord(c->ev_total[0], st);
+    /* host tables: sample grids + job descriptors, then their (small) upload */
+    if ((rc = build_tables(c))) return rc;
+    if ((rc = alloc_work(c->prm, c))) return rc;
+    if ((rc = upload(c, c->d_frames, c->frames))) return rc;
+    if ((rc = upload(c, c->d_poses, c->poses))) return rc;
+    if ((rc = upload(c, c->d_yaws, c->yaws))) return rc;
+    if ((rc = upload(c, c->d_jobs, c->jobs))) return rc;
+    if ((rc = upload(c, c->d_objs, c->objs))) return rc;
+    if ((rc = upload(c, c->d_tiles, c->tiles))) return rc;
+    if ((rc = upload(c, c->d_blocks, c->sweep_blocks))) return rc;
+    if ((rc = upload(c, c->d_dtids, c->dt_ids))) return rc;
+    CS_CUDA(c, cudaMemsetAsync(c->d_err.p, 0, 16, st));
+
+    const int n_jobs = (int)c->jobs.size(), n_objs = (int)c->objs.size();
+    const uint8_t *gray = (const uint8_t *)c->d_gray.p;
+    auto mark = [&](int s) {
+        if (c->profiling) cudaEventRecord(c->ev[s], st);
+    };
+    mark(ST_GRAY);
+    if (c->channels == 3 || c->stride != c->w)
+        cs_launch_gray((const uint8_t *)c->d_img.p, (uint8_t *)c->d_gray.p, c->n_frames, c->w, c->h, c->stride, c->channels, st, &c->launches);
+    else
+        gray = (const uint8_t *)c->d_img.p;
+    mark(ST_CANNY);
+    int low = (int)std::floor(std::min(c->prm.canny_low, c->prm.canny_high)), high = (int)std::floor(std::max(c->prm.canny_low, c->prm.canny_high));
+    cs_launch_canny(gray, c->w, c->h, (const CsJob *)c->d_jobs.p, n_jobs, (const CsTile *)c->d_tiles.p, (int)c->tiles.size(), (uint8_t *)c->d_map.p,
+                    (int32_t *)c->d_queue.p, (int32_t *)c->d_qtail.p, low, high, st, &c->launches);
+    mark(ST_HYST);
+    cs_launch_hyst((const CsJob *)c->d_jobs.p, n_jobs, (uint8_t *)c->d_map.p, (int32_t *)c->d_queue.p, (int32_t *)c->d_qtail.p, st, &c->launches);
+    mark(ST_DT);
+    cs_launch_dt((const CsJob *)c->d_jobs.p, (const int32_t *)c->d_dtids.p, c->dt_class_off, (const uint8_t *)c->d_map.p, (float *)c->d_dist.p, st,
+                 &c->launches);
+    mark(ST_LINES);
+    cs_launch_roi_lines((const CsJob *)c->d_jobs.p, n_jobs, (const CsFrame *)c->d_frames.p, (const double *)c->d_lines.p, (double *)c->d_mlines.p,
+                        (int32_t *)c->d_lcounts.p, (int32_t *)c->d_err.p, c->prm.pre_merge_dist_thre, c->prm.pre_merge_angle_thre,
+                        c->prm.edge_length_threshold, st, &c->launches);
+    mark(ST_SWEEP);
+    cs_launch_sweep((const CsJob *)c->d_jobs.p, (const CsFrame *)c->d_frames.p, (const CsPose *)c->d_poses.p, (const double *)c->d_yaws.p,
+                    (const int2 *)c->d_blocks.p, (int)c->sweep_blocks.size(), (const double *)c->d_mlines.p, (const int32_t *)c->d_lcounts.p,
+                    (const float *)c->d_dist.p, (uint8_t *)c->d_cvalid.p, (double *)c->d_cdist.p, (double *)c->d_cangle.p, &c->prm, st, &c->launches);
+    mark(ST_FUSE);
+    cs_launch_fuse((const CsObj *)c->d_objs.p, n_objs, (const CsJob *)c->d_jobs.p, (const CsFrame *)c->d_frames.p, (const CsPose *)c->d_poses.p,
+                   (const double *)c->d_yaws.p, (const uint8_t *)c->d_cvalid.p, (const double *)c->d_cdist.p, (const double *)c->d_cangle.p,
+                   (int32_t *)c->d_vlist.p, (uint64_t *)c->d_key.p, (uint32_t *)c->d_idx.p, (uint8_t *)c->d_flag.p, (int32_t *)c->d_keep.p,
+                   (double *)c->d_norm.p, (double *)c->d_score.p, (int32_t *)c->d_jcounts.p, (cs_cuboid_rec *)c->d_out.p, (int32_t *)c->d_outcnt.p,
+                   c->topk, &c->prm, st, &c->launches);
+    mark(ST_COUNT);
+    if (c->profiling) cudaEventRecord(c->ev_total[1], st);
+    CS_CUDA(c, cudaGetLastError());
+    c->stage_valid = false;
+    if (sync) {
+        CS_CUDA(c, cudaStreamSynchronize(st));
+        if (c->profiling) {
+            for (int s = 0; s < ST_COUNT; s++) cudaEventElapsedTime(&c->stage_ms[s], c->ev[s], c->ev[s + 1]);
+            cudaEventElapsedTime(&c->total_ms, c->ev_total[0], c->ev_total[1]);
+            c->stage_valid = true;
+        }
+    }
+    return CS_OK;
+}
+
+int store_batch(cs_ctx *c, const uint8_t *imgs, int n_frames, int width, int height, int stride, int channels, const double *T_wc,
+                const double *boxes, const int32_t *box_offsets, const double *lines, const int32_t *line_offsets,
+                const cs_cuboid_params *params)
+{
+    if (!c) return CS_ERR_INVALID_ARG;
+    if (!imgs || n_frames <= 0 || width <= 0 || height <= 0 || !T_wc || !box_offsets || !line_offsets || !params)
+        return fail(c, CS_ERR_INVALID_ARG, "null or empty argument");
+    if (channels != 1 && channels != 3) return fail(c, CS_ERR_INVALID_ARG, "channels must be 1 or 3");
+    if (stride < width * channels) return fail(c, CS_ERR_INVALID_ARG, "stride smaller than a row");
+    if (!c->have_K) return fail(c, CS_ERR_INVALID_ARG, "cs_set_calibration has not been called");
+    if (params->max_cuboid_num < 1 || params->max_cuboid_num > CS_MAX_TOPK)
+        return fail(c, CS_ERR_CAPACITY, "max_cuboid_num must be in [1,%d]", CS_MAX_TOPK);
+    if (width > c->max_w || height > c->max_h || n_frames > c->max_frames) return fail(c, CS_ERR_CAPACITY, "batch exceeds cs_create capacities");
+    for (int f = 0; f < n_frames; f++) {
+        if (box_offsets[f + 1] < box_offsets[f] || line_offsets[f + 1] < line_offsets[f]) return fail(c, CS_ERR_INVALID_ARG, "offsets must be non-decreasing");
+        if (box_offsets[f + 1] - box_offsets[f] > c->max_boxes) return fail(c, CS_ERR_CAPACITY, "frame %d: more than %d boxes", f, c->max_boxes);
+        if (line_offsets[f + 1] - line_offsets[f] > c->max_lines) return fail(c, CS_ERR_CAPACITY, "frame %d: more than %d lines", f, c->max_lines);
+    }
+    const int nb = box_offsets[n_frames], nl = line_offsets[n_frames];
+    if ((nb > 0 && !boxes) || (nl > 0 && !lines)) return fail(c, CS_ERR_INVALID_ARG, "null boxes/lines");
+    c->prepared = false;
+    c->n_frames = n_frames;
+    c->w = width;
+    c->h = height;
+    c->stride = stride;
+    c->channels = channels;
+    c->prm = *params;
+    c->topk = params->max_cuboid_num;
+    c->h_T.assign(T_wc, T_wc + (size_t)n_frames * 16);
+    c->h_boxes.assign(boxes, boxes + (size_t)nb * 5);
+    c->h_lines.assign(lines, lines + (size_t)nl * 4);
+    c->h_box_off.assign(box_offsets, box_offsets + n_frames + 1);
+    c->h_line_off.assign(line_offsets, line_offsets + n_frames + 1);
+    int rc;
+    const size_t img_bytes = (size_t)n_frames * height * stride;
+    if ((rc = ensure(c, c->d_img, img_bytes + 64))) return rc;
+    if ((rc = ensure(c, c->d_gray, (size_t)n_frames * height * width + 64))) return rc;
+    if ((rc = ensure(c, c->d_lines, std::max<size_t>((size_t)nl * 4 * sizeof(double), 64)))) return rc;
+    CS_CUDA(c, cudaMemcpyAsync(c->d_img.p, imgs, img_bytes, cudaMemcpyHostToDevice, c->stream));
+    if (nl) CS_CUDA(c, cudaMemcpyAsync(c->d_lines.p, lines, (size_t)nl * 4 * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    c->prepared = true;
+    return CS_OK;
+}
+
+int fetch(cs_ctx *c, cs_cuboid_rec *out, int32_t *out_counts)
+{
+    if (!c->prepared) return fail(c, CS_ERR_NOT_PREPARED, "no batch uploaded");
+    const size_t no = c->objs.size();
+    if (no == 0) return CS_OK;
+    if (out) CS_CUDA(c, cudaMemcpyAsync(out, c->d_out.p, no * c->topk * sizeof(cs_cuboid_rec), cudaMemcpyDeviceToHost, c->stream));
+    if (out_counts) CS_CUDA(c, cudaMemcpyAsync(out_counts, c->d_outcnt.p, no * sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream));
+    int32_t err = 0;
+    CS_CUDA(c, cudaMemcpyAsync(&err, c->d_err.p, 4, cudaMemcpyDeviceToHost, c->stream));
+    CS_CUDA(c, cudaStreamSynchronize(c->stream));
+    if (err & 1) return fail(c, CS_ERR_CAPACITY, "more than %d line segments inside one ROI", CS_LINE_CAP);
+    if (err & 2) return fail(c, CS_ERR_CAPACITY, "more than %d merged segments inside one ROI", CS_MAXL_OUT);
+    if (out && out_counts) { /* slots past the count are not cuboids */
+        for (size_t o = 0; o < no; o++)
+            for (int k = out_counts[o]; k < c->topk; k++) std::memset(&out[o * c->topk + k], 0, sizeof(cs_cuboid_rec));
+    }
+    return CS_OK;
+}
+
+}  // namespace
+
+/* ============================================================================================ C ABI */
+extern "C" {
+
+int cs_abi_version(void) { return CS_ABI_VERSION; }
+
+void cs_default_cuboid_params(cs_cuboid_params *p)
+{
+    if (!p) return;
+    std::memset(p, 0, sizeof(*p));
+    p->consider_config_1 = 1;
+    p->consider_config_2 = 1;
+    p->whether_sample_cam_roll_pitch = 0;
+    p->whether_sample_bbox_height = 0;
+    p->max_cuboid_num = 1;
+    p->reweight_edge_distance = 1;
+    p->whether_normalize_two_errors = 1;
+    p->top_sample_count_override = 0;
+    p->nominal_skew_ratio = 1;
+    p->max_cut_skew = 3;
+    p->vp12_edge_angle_thre = 15;
+    p->vp3_edge_angle_thre = 10;
+    p->shorted_edge_thre = 20;
+    p->weight_vp_angle = 0.8;
+    p->weight_skew_error = 1.5;
+    p->pre_merge_dist_thre = 20;
+    p->pre_merge_angle_thre = 5;
+    p->edge_length_threshold = 30;
+    p->canny_low = 80;
+    p->canny_high = 200;
+    p->yaw_half_range_deg = 45;
+    p->yaw_step_deg = 6;
+}
+
+void cs_default_line_params(cs_line_params *p)
+{
+    if (!p) return;
+    p->use_LSD = 0;          /* line_lbd_allclass.cpp:121 */
+    p->numoctaves = 1;       /* line_lbd_allclass.h:25 */
+    p->octaveratio = 1.f;
+    p->line_length_thres = 50; /* line_lbd_allclass.cpp:122 */
+}
+
+cs_ctx *cs_create(int device, int max_width, int max_height, int max_frames, int max_boxes_per_frame, int max_lines_per_frame)
+{
+    if (max_width <= 0 || max_height <= 0 || max_frames <= 0 || max_boxes_per_frame < 0 || max_lines_per_frame < 0) return nullptr;
+    int n_dev = 0;
+    if (cudaGetDeviceCount(&n_dev) != cudaSuccess || device < 0 || device >= n_dev) {
+        fprintf(stderr, "cube_slam_b200: no usable CUDA device %d (found %d); this library has no CPU path\n", device, n_dev);
+        return nullptr;
+    }
+    if (cudaSetDevice(device) != cudaSuccess) return nullptr;
+    cs_ctx *c = new cs_ctx();
+    c->device = device;
+    c->max_w = max_width;
+    c->max_h = max_height;
+    c->max_frames = max_frames;
+    c->max_boxes = max_boxes_per_frame;
+    c->max_lines = max_lines_per_frame;
+    std::memset(&c->stats, 0, sizeof(c->stats));
+    cs_default_cuboid_params(&c->prm);
+    if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) {
+        delete c;
+        return nullptr;
+    }
+    for (int s = 0; s <= ST_COUNT; s++) cudaEventCreate(&c->ev[s]);
+    cudaEventCreate(&c->ev_total[0]);
+    cudaEventCreate(&c->ev_total[1]);
+    return c;
+}
+
+void cs_destroy(cs_ctx *c)
+{
+    if (!c) return;
+    cudaSetDevice(c->device);
+    cudaStreamSynchronize(c->stream);
+    cs_nccl_teardown(c);
+    DevBuf *all[] = {&c->d_img,   &c->d_gray,  &c->d_lines,  &c->d_frames, &c->d_poses,   &c->d_yaws, &c->d_jobs, &c->d_objs,  &c->d_tiles,
+                     &c->d_blocks, &c->d_dtids, &c->d_map,    &c->d_queue,  &c->d_qtail,   &c->d_dist, &c->d_mlines, &c->d_lcounts, &c->d_err,
+                     &c->d_cvalid, &c->d_cdist, &c->d_cangle, &c->d_vlist,  &c->d_key,     &c->d_idx,  &c->d_flag, &c->d_keep,  &c->d_norm,
+                     &c->d_score,  &c->d_jcounts, &c->d_out,  &c->d_outcnt, &c->d_gather};
+    for (DevBuf *b : all)
+        if (b->p) cudaFree(b->p);
+    if (c->pinned) cudaFreeHost(c->pinned);
+    for (int s = 0; s <= ST_COUNT; s++)
+        if (c->ev[s]) cudaEventDestroy(c->ev[s]);
+    cudaEventDestroy(c->ev_total[0]);
+    cudaEventDestroy(c->ev_total[1]);
+    cudaStreamDestroy(c->stream);
+    delete c;
+}
+
+const char *cs_last_error(const cs_ctx *c) { return c ? c->err.c_str() : "null context (cs_create failed: no CUDA device?)"; }
+
+int cs_set_calibration(cs_ctx *c, const double K[9])
+{
+    if (!c || !K) return CS_ERR_INVALID_ARG;
+    std::memcpy(c->K, K, sizeof(c->K));
+    cshost::invert3(c->K, c->invK);
+    c->have_K = true;
+    return CS_OK;
+}
+
+int cs_cam_pose(const double K[9], const double T_wc[16], double euler_zyx[3], double KinvR[9])
+{
+    if (!K || !T_wc) return CS_ERR_INVALID_ARG;
+    CsPose ps;
+    double e[3];
+    cshost::make_pose(K, T_wc, &ps, e);
+    if (euler_zyx) std::memcpy(euler_zyx, e, sizeof(e));
+    if (KinvR) std::memcpy(KinvR, ps.KinvR, sizeof(ps.KinvR));
+    return CS_OK;
+}
+
+int cs_batch_upload(cs_ctx *c, const uint8_t *imgs, int n_frames, int width, int height, int stride, int channels, const double *T_wc,
+                    const double *boxes, const int32_t *box_offsets, const double *lines, const int32_t *line_offsets,
+                    const cs_cuboid_params *params)
+{
+    if (!c) return CS_ERR_INVALID_ARG;
+    cudaSetDevice(c->device);
+    int rc = store_batch(c, imgs, n_frames, width, height, stride, channels, T_wc, boxes, box_offsets, lines, line_offsets, params);
+    if (rc) return rc;
+    CS_CUDA(c, cudaStreamSynchronize(c->stream));
+    return CS_OK;
+}
+
+int cs_batch_run(cs_ctx *c)
+{
+    if (!c) return CS_ERR_INVALID_ARG;
+    cudaSetDevice(c->device);
+    return run_batch(c, true);
+}
+
+int cs_batch_run_async(cs_ctx *c)
+{
+    if (!c) return CS_ERR_INVALID_ARG;
+    cudaSetDevice(c->device);
+    return run_batch(c, false);
+}
+
+int cs_batch_fetch(cs_ctx *c, cs_cuboid_rec *out, int32_t *out_counts)
+{
+    if (!c) return CS_ERR_INVALID_ARG;
+    cudaSetDevice(c->device);
+    return fetch(c, out, out_counts);
+}
+
+int cs_detect_cuboids_batch(cs_ctx *c, const uint8_t *imgs, int n_frames, int width, int height, int stride, int channels, const double *T_wc,
+                            const double *boxes, const int32_t *box_offsets, const double *lines, const int32_t *line_offsets,
+                            const cs_cuboid_params *params, cs_cuboid_rec *out, int32_t *out_counts)
+{
+    if (!c) return CS_ERR_INVALID_ARG;
+    cudaSetDevice(c->device);
+    int rc = store_batch(c, imgs, n_frames, width, height, stride, channels, T_wc, boxes, box_offsets, lines, line_offsets, params);
+    if (rc) return rc;
+    if ((rc = run_batch(c, false))) return rc;
+    return fetch(c, out, out_counts);
+}
+
+int cs_detect_cuboids(cs_ctx *c, const uint8_t *img, int width, int height, int stride, int channels, const double T_wc[16], const double *boxes,
+                      int n_boxes, const double *lines, int n_lines, const cs_cuboid_params *params, cs_cuboid_rec *out, int32_t *out_counts)
+{
+    if (n_boxes < 0 || n_lines < 0) return c ? fail(c, CS_ERR_INVALID_ARG, "negative count") : CS_ERR_INVALID_ARG;
+    const int32_t bo[2] = {0, n_boxes}, lo[2] = {0, n_lines};
+    static const double dummy[5] = {0, 0, 0, 0, 0};
+    if (n_boxes == 0) { /* empty bbox matrix => empty output (box_proposal_detail.cpp:71-72) */
+        return CS_OK;
+    }
+    return cs_detect_cuboids_batch(c, img, 1, width, height, stride, channels, T_wc, boxes, bo, n_lines ? lines : dummy, lo, params, out, out_counts);
+}
+
+int cs_batch_stats_get(cs_ctx *c, cs_batch_stats *s)
+{
+    if (!c || !s) return CS_ERR_INVALID_ARG;
+    if (!c->prepared) return fail(c, CS_ERR_NOT_PREPARED, "no batch uploaded");
+    cudaSetDevice(c->device);
+    std::memset(s, 0, sizeof(*s));
+    s->n_frames = c->n_frames;
+    s->n_objects = (int64_t)c->objs.size();
+    s->n_roi_jobs = (int64_t)c->jobs.size();
+    s->n_candidates = c->total_cand;
+    s->n_kernel_launches = c->launches;
+    s->n_lines_in = c->h_line_off.empty() ? 0 : c->h_line_off.back();
+    for (const CsJob &j : c->jobs) s->roi_pixels += (int64_t)j.roi_w * j.roi_h;
+    if (!c->jobs.empty()) {
+        std::vector<int32_t> jc(c->jobs.size() * 2);
+        CS_CUDA(c, cudaMemcpyAsync(jc.data(), c->d_jcounts.p, jc.size() * 4, cudaMemcpyDeviceToHost, c->stream));
+        CS_CUDA(c, cudaStreamSynchronize(c->stream));
+        for (size_t j = 0; j < c->jobs.size(); j++) s->n_valid += jc[j * 2];
+    }
+    c->stats = *s;
+    return CS_OK;
+}
+
+int cs_batch_device_records(cs_ctx *c, void **dev_ptr, size_t *n_bytes)
+{
+    if (!c || !dev_ptr || !n_bytes) return CS_ERR_INVALID_ARG;
+    if (!c->prepared) return fail(c, CS_ERR_NOT_PREPARED, "no batch uploaded");
+    *dev_ptr = c->d_out.p;
+    *n_bytes = c->objs.size() * c->topk * sizeof(cs_cuboid_rec);
+    return CS_OK;
+}
+
+void *cs_stream(cs_ctx *c) { return c ? (void *)c->stream : nullptr; }
+
+int cs_set_profiling(cs_ctx *c, int enable)
+{
+    if (!c) return CS_ERR_INVALID_ARG;
+    c->profiling = enable != 0;
+    return CS_OK;
+}
+
+int cs_stage_ms(cs_ctx *c, const char *stage, float *ms)
+{
+    if (!c || !stage || !ms) return CS_ERR_INVALID_ARG;
+    if (!c->stage_valid) return fail(c, CS_ERR_NOT_PREPARED, "no profiled synchronous run");
+    if (!strcmp(stage, "total")) {
+        *ms = c->total_ms;
+        return CS_OK;
+    }
+    for (int s = 0; s < ST_COUNT; s++)
+        if (!strcmp(stage, kStageNames[s])) {
+            *ms = c->stage_ms[s];
+            return CS_OK;
+        }
+    return fail(c, CS_ERR_INVALID_ARG, "unknown stage %s", stage);
+}
+
+int cs_debug_roi(cs_ctx *c, int job, int32_t roi_xywh[4], uint8_t *canny, float *dist, int cap_px, double *merged_lines, int cap_lines,
+                 int32_t *n_lines_roi, int32_t *n_lines_merged)
+{
+    if (!c) return CS_ERR_INVALID_ARG;
+    if (!c->prepared || job < 0 || job >= (int)c->jobs.size()) return fail(c, CS_ERR_INVALID_ARG, "bad job index");
+    cudaSetDevice(c->device);
+    const CsJob &jb = c->jobs[job];
+    const int npx = jb.roi_w * jb.roi_h;
+    if (roi_xywh) {
+        roi_xywh[0] = jb.roi_l;
+        roi_xywh[1] = jb.roi_t;
+        roi_xywh[2] = jb.roi_w;
+        roi_xywh[3] = jb.roi_h;
+    }
+    CS_CUDA(c, cudaStreamSynchronize(c->stream));
+    if (canny && cap_px >= npx) {
+        CS_CUDA(c, cudaMemcpy(canny, (uint8_t *)c->d_map.p + jb.px_off, npx, cudaMemcpyDeviceToHost));
+        for (int i = 0; i < npx; i++) canny[i] = (canny[i] & 2) ? 255 : 0;
+    }
+    if (dist && cap_px >= npx) CS_CUDA(c, cudaMemcpy(dist, (float *)c->d_dist.p + jb.px_off, (size_t)npx * 4, cudaMemcpyDeviceToHost));
+    int32_t cnt[2];
+    CS_CUDA(c, cudaMemcpy(cnt, (int32_t *)c->d_lcounts.p + job * 2, 8, cudaMemcpyDeviceToHost));
+    if (n_lines_roi) *n_lines_roi = cnt[0];
+    if (n_lines_merged) *n_lines_merged = cnt[1];
+    if (merged_lines) {
+        std::vector<double> tmp((size_t)CS_MAXL_OUT * 7);
+        CS_CUDA(c, cudaMemcpy(tmp.data(), (double *)c->d_mlines.p + (size_t)job * CS_MAXL_OUT * 7, tmp.size() * 8, cudaMemcpyDeviceToHost));
+        for (int i = 0; i < std::min(cnt[1], cap_lines); i++)
+            for (int k = 0; k < 4; k++) merged_lines[i * 4 + k] = tmp[(size_t)k * CS_MAXL_OUT + i];
+    }
+    return CS_OK;
+}
+
+int cs_debug_candidates(cs_ctx *c, int job, int32_t *n_candidates, uint8_t *valid, double *dist_err, double *angle_err, int cap)
+{
+    if (!c) return CS_ERR_INVALID_ARG;
+    if (!c->prepared || job < 0 || job >= (int)c->jobs.size()) return fail(c, CS_ERR_INVALID_ARG, "bad job index");
+    cudaSetDevice(c->device);
+    const CsJob &jb = c->jobs[job];
+    if (n_candidates) *n_candidates = jb.n_cand;
+    const int n = std::min(cap, jb.n_cand);
+    CS_CUDA(c, cudaStreamSynchronize(c->stream));
+    if (valid && n) CS_CUDA(c, cudaMemcpy(valid, (uint8_t *)c->d_cvalid.p + jb.cand_off, n, cudaMemcpyDeviceToHost));
+    if (dist_err && n) CS_CUDA(c, cudaMemcpy(dist_err, (double *)c->d_cdist.p + jb.cand_off, (size_t)n * 8, cudaMemcpyDeviceToHost));
+    if (angle_err && n) CS_CUDA(c, cudaMemcpy(angle_err, (double *)c->d_cangle.p + jb.cand_off, (size_t)n * 8, cudaMemcpyDeviceToHost));
+    return CS_OK;
+}
+
+} /* extern "C" */
+
+#include "cs_nccl_impl.inc"

@@ -1,0 +1,129 @@
+/*
+ * cs_host_pose.cpp -- host-side camera-pose tables and sample grids of detect_cuboid.
+ *
+ * These are a handful of FP64 values per frame (set_cam_pose, the roll/pitch pose hypotheses, the yaw
+ * sample list).  They are evaluated on the host with libm -- like the reference does -- so that the
+ * sample grids the kernels sweep are the reference's own numbers, and uploaded as small tables.
+ *   set_calibration / set_cam_pose        detect_3d_cuboid/src/box_proposal_detail.cpp:36-54
+ *   quat_to_euler_zyx, euler_zyx_to_rot   detect_3d_cuboid/src/matrix_utils.cpp:36-46,75-89
+ *   linespace                             detect_3d_cuboid/src/matrix_utils.cpp:350-363
+ * Compiled with -ffp-contract=off.
+ */
+#include "cs_host_pose.h"
+
+#include <cmath>
+#include <cstring>
+
+namespace cshost {
+
+static inline double cof(const double *m, int i, int j)
+{
+    const int a = (i + 1) % 3, b = (i + 2) % 3, c = (j + 1) % 3, d = (j + 2) % 3;
+    return m[a * 3 + c] * m[b * 3 + d] - m[a * 3 + d] * m[b * 3 + c];
+}
+
+/* fixed-size 3x3 inverse, cofactor form (the evaluation order of Eigen's 3x3 inverse) */
+void invert3(const double *m, double *out)
+{
+    const double k0 = cof(m, 0, 0), k1 = cof(m, 1, 0), k2 = cof(m, 2, 0);
+    const double det = (k0 * m[0] + k1 * m[3]) + k2 * m[6];
+    const double s = 1.0 / det;
+    out[0] = k0 * s;
+    out[1] = k1 * s;
+    out[2] = k2 * s;
+    for (int r = 1; r < 3; r++)
+        for (int c = 0; c < 3; c++) out[r * 3 + c] = cof(m, c, r) * s;
+}
+
+static void matmul3(const double *a, const double *b, double *c)
+{
+    for (int r = 0; r < 3; r++)
+        for (int k = 0; k < 3; k++) c[r * 3 + k] = (a[r * 3] * b[k] + a[r * 3 + 1] * b[3 + k]) + a[r * 3 + 2] * b[6 + k];
+}
+
+void euler_to_rot(double roll, double pitch, double yaw, double *R)
+{
+    const double cp = std::cos(pitch), sp = std::sin(pitch), sr = std::sin(roll), cr = std::cos(roll), sy = std::sin(yaw), cy = std::cos(yaw);
+    R[0] = cp * cy;
+    R[1] = (sr * sp * cy) - (cr * sy);
+    R[2] = (cr * sp * cy) + (sr * sy);
+    R[3] = cp * sy;
+    R[4] = (sr * sp * sy) + (cr * cy);
+    R[5] = (cr * sp * sy) - (sr * cy);
+    R[6] = -sp;
+    R[7] = sr * cp;
+    R[8] = cr * cp;
+}
+
+/* Eigen::Quaterniond(R) followed by quat_to_euler_zyx */
+static void euler_from_rot(const double *R, double *e)
+{
+    double x, y, z, w;
+    const double tr = R[0] + R[4] + R[8];
+    if (tr > 0.0) {
+        double t = std::sqrt(tr + 1.0);
+        w = 0.5 * t;
+        t = 0.5 / t;
+        x = (R[7] - R[5]) * t;
+        y = (R[2] - R[6]) * t;
+        z = (R[3] - R[1]) * t;
+    } else {
+        int i = 0;
+        if (R[4] > R[0]) i = 1;
+        if (R[8] > R[i * 4]) i = 2;
+        const int j = (i + 1) % 3, k = (j + 1) % 3;
+        double q[3];
+        double t = std::sqrt(R[i * 4] - R[j * 4] - R[k * 4] + 1.0);
+        q[i] = 0.5 * t;
+        t = 0.5 / t;
+        w = (R[k * 3 + j] - R[j * 3 + k]) * t;
+        q[j] = (R[j * 3 + i] + R[i * 3 + j]) * t;
+        q[k] = (R[k * 3 + i] + R[i * 3 + k]) * t;
+        x = q[0];
+        y = q[1];
+        z = q[2];
+    }
+    e[0] = std::atan2(2 * (w * x + y * z), 1 - 2 * (x * x + y * y));
+    e[1] = std::asin(2 * (w * y - z * x));
+    e[2] = std::atan2(2 * (w * z + x * y), 1 - 2 * (y * y + z * z));
+}
+
+void make_pose(const double *K, const double *T, CsPose *pose, double *euler_out)
+{
+    double R[9], invR[9], e[3];
+    for (int r = 0; r < 3; r++)
+        for (int c = 0; c < 3; c++) R[r * 3 + c] = T[r * 4 + c];
+    euler_from_rot(R, e);
+    invert3(R, invR);
+    matmul3(K, invR, pose->KinvR);
+    std::memcpy(pose->T, T, sizeof(double) * 16);
+    /* ground plane (0,0,1,0) seen from the sensor: T^T * plane */
+    const double pw[4] = {0, 0, 1, 0};
+    for (int c = 0; c < 4; c++) pose->ground[c] = ((T[c] * pw[0] + T[4 + c] * pw[1]) + T[8 + c] * pw[2]) + T[12 + c] * pw[3];
+    pose->roll = e[0];
+    pose->pitch = e[1];
+    pose->camera_yaw = e[2];
+    if (euler_out) std::memcpy(euler_out, e, sizeof(e));
+}
+
+void linespace_d(double start, double end, double step, std::vector<double> &out)
+{
+    while (start <= end) {
+        out.push_back(start);
+        start += step;
+        if (out.size() > 1000) break;
+    }
+}
+
+int linespace_count_i(int start, int end, int step)
+{
+    int n = 0;
+    while (start <= end) {
+        n++;
+        start += step;
+        if (n > 1000) break;
+    }
+    return n;
+}
+
+}  // namespace cshost

@@ -1,0 +1,67 @@
+/* cs_internal.h -- structures shared by the host orchestration and the sm_100a kernels. */
+#ifndef CS_INTERNAL_H
+#define CS_INTERNAL_H
+
+#include <stdint.h>
+
+#include "../../include/cube_slam_b200.h"
+
+#define CS_MAX_YAW 512        /* yaw samples per object (reference default 16; dense sweep 181) */
+#define CS_MAX_POSE 32        /* roll x pitch samples (reference 5 x 5) */
+#define CS_MAX_TOPK 32        /* upper bound of max_cuboid_num handled on device */
+#define CS_LINE_CAP 1024      /* lines of one frame that fall inside one ROI (shared-memory resident) */
+#define CS_MAXL_OUT 256       /* merged lines kept per ROI */
+
+/* One camera pose hypothesis: detect_3d_cuboid::cam_pose after set_cam_pose
+ * (box_proposal_detail.cpp:42-54) plus the ground plane in the sensor frame (:100,238). */
+struct CsPose {
+    double KinvR[9];
+    double T[16];
+    double ground[4];
+    double roll, pitch;
+    double camera_yaw; /* cam_pose.camera_yaw re-derived through the quaternion */
+};
+
+/* Per-frame constants */
+struct CsFrame {
+    double invK[9];
+    double euler_raw[3];
+    int32_t pose_off;  /* first CsPose of this frame; pose 0 == raw pose when sampling is off */
+    int32_t n_pose;
+    int32_t yaw_off;   /* first yaw sample of this frame in the yaw table */
+    int32_t n_yaw;
+    int32_t line_off;  /* CSR into the batch line array */
+    int32_t n_lines;
+};
+
+/* One (2D box, height sample) ROI job: box_proposal_detail.cpp:107-163 evaluated on the host. */
+struct CsJob {
+    int32_t frame;
+    int32_t obj;        /* global object index */
+    int32_t hs;         /* height-sample id */
+    int32_t left, top, right;           /* left_x_raw, top_y_raw, right_x_raw */
+    int32_t width_raw, height_raw;
+    int32_t down_expand, down_y_expan;
+    int32_t roi_l, roi_t, roi_r, roi_b; /* dist-map ROI corners (inclusive box test uses these) */
+    int32_t roi_w, roi_h;               /* width_expan_distmap, height_expan_distmap */
+    int32_t n_top, top_lo, top_hi, top_step, top_override;
+    int32_t n_cand;                     /* n_pose * n_yaw * n_top * 2 */
+    int32_t tile_off;                   /* first canny tile of this job */
+    int32_t tiles_x;
+    int64_t px_off;                     /* offset of this ROI in the edge / dist arenas (pixels) */
+    int64_t cand_off;                   /* offset into the candidate record arenas */
+    double diag;                        /* obj_diaglength_expan */
+};
+
+struct CsObj {
+    int32_t frame;
+    int32_t job_off, n_jobs;
+    int32_t left, top, width_raw, height_raw;
+};
+
+struct CsTile {
+    int32_t job;
+    int16_t tx, ty;
+};
+
+#endif

@@ -1,0 +1,32 @@
+/* cs_kernels.h -- launcher prototypes of the sm_100a kernels (one .cu per stage group). */
+#ifndef CS_KERNELS_H
+#define CS_KERNELS_H
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "cs_internal.h"
+
+#define CS_DT_CLASSES 7
+extern const int cs_dt_class_ppl[CS_DT_CLASSES];
+int cs_dt_class_of(int roi_w);
+
+void cs_launch_gray(const uint8_t *d_img, uint8_t *d_gray, int n_frames, int w, int h, int stride, int channels, cudaStream_t st,
+                    int64_t *launches);
+void cs_launch_canny(const uint8_t *d_gray, int img_w, int img_h, const CsJob *d_jobs, int n_jobs, const CsTile *d_tiles, int n_tiles,
+                     uint8_t *d_map, int32_t *d_queue, int32_t *d_qtail, int low, int high, cudaStream_t st, int64_t *launches);
+void cs_launch_hyst(const CsJob *d_jobs, int n_jobs, uint8_t *d_map, int32_t *d_queue, int32_t *d_qtail, cudaStream_t st, int64_t *launches);
+void cs_launch_dt(const CsJob *d_jobs, const int32_t *d_ids, const int *class_off, const uint8_t *d_map, float *d_dist, cudaStream_t st,
+                  int64_t *launches);
+void cs_launch_roi_lines(const CsJob *d_jobs, int n_jobs, const CsFrame *d_frames, const double *d_lines, double *d_out_lines,
+                         int32_t *d_out_counts, int32_t *d_err, double dist_thre, double angle_thre_deg, double len_thre, cudaStream_t st,
+                         int64_t *launches);
+void cs_launch_sweep(const CsJob *d_jobs, const CsFrame *d_frames, const CsPose *d_poses, const double *d_yaw, const int2 *d_blocks,
+                     int n_blocks, const double *d_mlines, const int32_t *d_line_counts, const float *d_dist, uint8_t *c_valid, double *c_dist,
+                     double *c_angle, const cs_cuboid_params *prm, cudaStream_t st, int64_t *launches);
+void cs_launch_fuse(const CsObj *d_objs, int n_objs, const CsJob *d_jobs, const CsFrame *d_frames, const CsPose *d_poses, const double *d_yaw,
+                    const uint8_t *c_valid, const double *c_dist, const double *c_angle, int32_t *w_vlist, uint64_t *w_key, uint32_t *w_idx,
+                    uint8_t *w_flag, int32_t *w_keep, double *w_norm, double *w_score, int32_t *job_counts, cs_cuboid_rec *d_out,
+                    int32_t *d_out_counts, int topk, const cs_cuboid_params *prm, cudaStream_t st, int64_t *launches);
+
+#endif

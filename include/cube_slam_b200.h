@@ -1,0 +1,193 @@
+/*
+ * cube_slam_b200.h -- C ABI of the B200-native cuboid-proposal front end (libcubeslam_b200.so).
+ *
+ * Drop-in boundary for CubeSLAM's per-frame hot path.  Every entry point names the reference
+ * interface it replaces (paths relative to the reference repository root).  Plain pointers and
+ * sizes only; no C++/torch types.  All functions return CS_OK (0) or a negative cs_status; the
+ * text of the last failure is available from cs_last_error().
+ *
+ * Threading contract (as the reference objects): one cs_ctx per host thread;
+ * a context owns one CUDA stream plus its device workspace; calls are synchronous on return unless
+ * the name ends in _async.
+ */
+#ifndef CUBE_SLAM_B200_H
+#define CUBE_SLAM_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CS_ABI_VERSION 1
+
+typedef enum cs_status {
+    CS_OK = 0,
+    CS_ERR_INVALID_ARG = -1,
+    CS_ERR_CUDA = -2,          /* CUDA runtime failure or no usable sm_100 device */
+    CS_ERR_CAPACITY = -3,      /* input exceeds the capacities given to cs_create */
+    CS_ERR_NOT_PREPARED = -4,  /* run/fetch before a batch was uploaded */
+    CS_ERR_NCCL = -5,
+    CS_ERR_UNSUPPORTED = -6
+} cs_status;
+
+typedef struct cs_ctx cs_ctx;
+
+/* Mode members of class detect_3d_cuboid (detect_3d_cuboid/include/detect_3d_cuboid/detect_3d_cuboid.h:65-79)
+ * followed by the hard-coded locals of detect_cuboid() exposed with the reference's literals as
+ * defaults (detect_3d_cuboid/src/box_proposal_detail.cpp:79-87,126-128,144,177-179,197). */
+typedef struct cs_cuboid_params {
+    int32_t consider_config_1;             /* detect_3d_cuboid.h:72, default 1 */
+    int32_t consider_config_2;             /* :73, default 1 */
+    int32_t whether_sample_cam_roll_pitch; /* :74, default 0 */
+    int32_t whether_sample_bbox_height;    /* :75, default 0 */
+    int32_t max_cuboid_num;                /* :77, default 1 */
+    int32_t reweight_edge_distance;        /* box_proposal_detail.cpp:82, default 1 */
+    int32_t whether_normalize_two_errors;  /* :85, default 1 */
+    int32_t top_sample_count_override;     /* 0 = reference rule (:144-146); >0 = fixed count (BASELINE dense sweep) */
+    double nominal_skew_ratio;             /* detect_3d_cuboid.h:78, default 1 */
+    double max_cut_skew;                   /* :79, default 3 */
+    double vp12_edge_angle_thre;           /* box_proposal_detail.cpp:79, default 15 (deg) */
+    double vp3_edge_angle_thre;            /* :80, default 10 (deg) */
+    double shorted_edge_thre;              /* :81, default 20 (px) */
+    double weight_vp_angle;                /* :86, default 0.8 */
+    double weight_skew_error;              /* :87, default 1.5 */
+    double pre_merge_dist_thre;            /* :177, default 20 (px) */
+    double pre_merge_angle_thre;           /* :178, default 5 (deg) */
+    double edge_length_threshold;          /* :179, default 30 (px) */
+    double canny_low;                      /* :197, default 80 */
+    double canny_high;                     /* :197, default 200 */
+    double yaw_half_range_deg;             /* :128, default 45 */
+    double yaw_step_deg;                   /* :128, default 6 */
+} cs_cuboid_params;
+
+/* POD mirror of class cuboid (detect_3d_cuboid.h:15-36); matrices are row-major. */
+typedef struct cs_cuboid_rec {
+    double pos[3];
+    double scale[3];
+    double rotY;
+    double box_config_type[2];
+    int32_t box_corners_2d[16];       /* 2 x 8 */
+    double box_corners_3d_world[24];  /* 3 x 8 */
+    double rect_detect_2d[4];
+    double edge_distance_error;
+    double edge_angle_error;
+    double normalized_error;
+    double skew_ratio;
+    double down_expand_height;
+    double camera_roll_delta;
+    double camera_pitch_delta;
+    double combined_score;            /* normalized_error + skew penalty (box_proposal_detail.cpp:526) */
+    int32_t proposal_index;           /* row in the reference's valid-proposal list of its height sample */
+    int32_t height_sample_id;
+    int32_t valid;                    /* 1 when this slot holds a cuboid */
+    int32_t pad_;
+} cs_cuboid_rec;
+
+/* Members of class line_lbd_detect (line_lbd/include/line_lbd/line_lbd_allclass.h:22-31) and the
+ * constants its two detectors are built with (line_lbd/libs/LSDDetector.cpp:173-183,205;
+ * line_lbd/libs/binary_descriptor.cpp:1511-1522). */
+typedef struct cs_line_params {
+    int32_t use_LSD;            /* line_lbd_allclass.h:29; class default 0, object_slam sets 1 (main_obj.cpp:365) */
+    int32_t numoctaves;         /* :26, default 1 (only octave 0 survives filter_lines) */
+    float octaveratio;          /* :27, default 1 */
+    float line_length_thres;    /* :30, class default 50, object_slam uses 15 */
+} cs_line_params;
+
+/* per-batch work counters (what BASELINE.json's metric counts) */
+typedef struct cs_batch_stats {
+    int64_t n_frames;
+    int64_t n_objects;          /* 2D boxes */
+    int64_t n_roi_jobs;         /* boxes x height samples */
+    int64_t n_candidates;       /* enumerated (pose, yaw, top-x, config) tuples */
+    int64_t n_valid;            /* proposals that reach box_edge_sum_dists == "scored cuboid proposals" */
+    int64_t n_kernel_launches;  /* launches of this library's kernels in the last run */
+    int64_t roi_pixels;         /* sum of dist-map ROI areas */
+    int64_t n_lines_in;         /* input line segments over all frames */
+} cs_batch_stats;
+
+/* ---- life cycle ------------------------------------------------------------------------- */
+int cs_abi_version(void);
+/* Replaces constructing detect_3d_cuboid / line_lbd_detect objects (main_obj.cpp:354-366, Tracking.cc:242-244).
+ * Capacities bound the device workspace; max_frames is the largest batch. */
+cs_ctx *cs_create(int device, int max_width, int max_height, int max_frames, int max_boxes_per_frame,
+                  int max_lines_per_frame);
+void cs_destroy(cs_ctx *ctx);
+const char *cs_last_error(const cs_ctx *ctx);
+void cs_default_cuboid_params(cs_cuboid_params *p);
+void cs_default_line_params(cs_line_params *p);
+
+/* detect_3d_cuboid::set_calibration (box_proposal_detail.cpp:36-40); K row-major 3x3 */
+int cs_set_calibration(cs_ctx *ctx, const double K[9]);
+
+/* detect_3d_cuboid::set_cam_pose (box_proposal_detail.cpp:42-54) as a pure function: the ZYX Euler angles
+ * (roll, pitch, yaw; cam_pose.euler_angle, read by callers as cam_pose_raw.euler_angle, main_obj.cpp:465) and
+ * K*R^-1 of a camera-to-world transform.  Host-only, needs no context. */
+int cs_cam_pose(const double K[9], const double T_wc[16], double euler_zyx[3], double KinvR[9]);
+
+/* ---- cuboid proposals ------------------------------------------------------------------- */
+/* detect_3d_cuboid::detect_cuboid (box_proposal_detail.cpp:56-557; header detect_3d_cuboid.h:62-63)
+ * for ONE frame with HOST buffers.  img: H x stride bytes, channels 3 (BGR) or 1; T_wc row-major 4x4;
+ * boxes N x 5 [x y w h prob] 0-based; lines M x 4 [x1 y1 x2 y2];
+ * out: N x topk records (topk = params->max_cuboid_num); out_counts: N. */
+int cs_detect_cuboids(cs_ctx *ctx, const uint8_t *img, int width, int height, int stride, int channels,
+                      const double T_wc[16], const double *boxes, int n_boxes, const double *lines, int n_lines,
+                      const cs_cuboid_params *params, cs_cuboid_rec *out, int32_t *out_counts);
+
+/* The same call over a batch of frames (host buffers).  Frames are images of identical size laid out
+ * back to back (frame f at imgs + f*height*stride).  box_offsets/line_offsets have n_frames+1 entries
+ * (CSR); out holds box_offsets[n_frames] x topk records. */
+int cs_detect_cuboids_batch(cs_ctx *ctx, const uint8_t *imgs, int n_frames, int width, int height, int stride,
+                            int channels, const double *T_wc /* n_frames x 16 */, const double *boxes,
+                            const int32_t *box_offsets, const double *lines, const int32_t *line_offsets,
+                            const cs_cuboid_params *params, cs_cuboid_rec *out, int32_t *out_counts);
+
+/* Device-resident variant used by the throughput benchmark: upload once, run many times, fetch. */
+int cs_batch_upload(cs_ctx *ctx, const uint8_t *imgs, int n_frames, int width, int height, int stride, int channels,
+                    const double *T_wc, const double *boxes, const int32_t *box_offsets, const double *lines,
+                    const int32_t *line_offsets, const cs_cuboid_params *params);
+int cs_batch_run(cs_ctx *ctx);                       /* host-side sampling tables + every kernel; synchronous */
+int cs_batch_run_async(cs_ctx *ctx);                 /* same, returns after enqueueing on the context stream */
+int cs_batch_fetch(cs_ctx *ctx, cs_cuboid_rec *out, int32_t *out_counts);
+int cs_batch_stats_get(cs_ctx *ctx, cs_batch_stats *stats);
+/* device pointer of the record buffer ([n_objects] x topk cs_cuboid_rec) and its size in bytes */
+int cs_batch_device_records(cs_ctx *ctx, void **dev_ptr, size_t *n_bytes);
+/* raw CUDA stream of the context (cudaStream_t) so callers can time with events on it */
+void *cs_stream(cs_ctx *ctx);
+/* milliseconds spent in the named stage of the last cs_batch_run ("gray","canny","hyst","dt","lines","sweep","fuse","total") */
+int cs_stage_ms(cs_ctx *ctx, const char *stage, float *ms);
+/* enable per-stage CUDA-event timing (adds event records only) */
+int cs_set_profiling(cs_ctx *ctx, int enable);
+
+/* debug/inspection: copy intermediate per-ROI results of the last run back to the host.
+ * job = ROI job index (object-major, height-sample-minor). Any pointer may be NULL. */
+int cs_debug_roi(cs_ctx *ctx, int job, int32_t roi_xywh[4], uint8_t *canny, float *dist, int cap_px,
+                 double *merged_lines, int cap_lines, int32_t *n_lines_roi, int32_t *n_lines_merged);
+int cs_debug_candidates(cs_ctx *ctx, int job, int32_t *n_candidates, uint8_t *valid, double *dist_err,
+                        double *angle_err, int cap);
+
+/* ---- line segments ---------------------------------------------------------------------- */
+/* line_lbd_detect::detect_filter_lines(const cv::Mat&, cv::Mat&) (line_lbd/class/line_lbd_allclass.cpp:216-221):
+ * detect (LSD or EDLines) -> keep octave 0 and length > line_length_thres -> n x 4 float [x1 y1 x2 y2].
+ * lines_xyxy has room for *n_inout segments; on return *n_inout is the number written. */
+int cs_detect_lines(cs_ctx *ctx, const uint8_t *img, int width, int height, int stride, int channels,
+                    const cs_line_params *params, float *lines_xyxy, int32_t *n_inout);
+int cs_detect_lines_batch(cs_ctx *ctx, const uint8_t *imgs, int n_frames, int width, int height, int stride,
+                          int channels, const cs_line_params *params, float *lines_xyxy, int32_t max_lines_per_frame,
+                          int32_t *n_lines /* n_frames */);
+
+/* ---- multi-GPU -------------------------------------------------------------------------- */
+/* Frames shard across ranks; the only exchange is one all-gather of the top-K record buffers.
+ * No reference counterpart (the reference is single process); see BASELINE.json north_star. */
+int cs_comm_unique_id(cs_ctx *ctx, const char *nccl_library_path, uint8_t id_out[128]);
+int cs_comm_init(cs_ctx *ctx, const char *nccl_library_path, const uint8_t id[128], int world_size, int rank);
+/* all-gather recs_per_rank records from every rank's record buffer into gathered (DEVICE pointer owned by the
+ * context, returned through *gathered_dev; world_size x recs_per_rank records). */
+int cs_allgather_topk(cs_ctx *ctx, int recs_per_rank, void **gathered_dev);
+int cs_fetch_gathered(cs_ctx *ctx, cs_cuboid_rec *out, int n_records);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CUBE_SLAM_B200_H */
