@@ -5,6 +5,7 @@ This package holds the CUDA sources (csrc/), the in-tree build (build.py) and a 
 the reference's C++ interface for this path (detect_3d_cuboid.py, line_lbd.py).
 """
 from . import _lib  # noqa: F401
+from ._lib import CUBOID_DTYPE  # noqa: F401
 from .detect_3d_cuboid import Context, CubeSlamError, cuboid, default_params, detect_3d_cuboid  # noqa: F401
 
 __all__ = ["Context", "CubeSlamError", "cuboid", "default_params", "detect_3d_cuboid"]

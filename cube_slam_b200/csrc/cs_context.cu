@@ -54,15 +54,14 @@ struct cs_ctx {
     std::vector<double> yaws;
     std::vector<CsJob> jobs;
     std::vector<CsObj> objs;
-    std::vector<CsTile> tiles;
     std::vector<int2> sweep_blocks;
     std::vector<int32_t> dt_ids;
-    int dt_class_off[CS_DT_CLASSES + 1] = {0};
-    int64_t total_px = 0, total_cand = 0;
+    int64_t total_px = 0, total_cand = 0, total_bits = 0;
+    int n_tiles = 0, max_plane_words = 0, max_dpitch = 0;
 
     /* device buffers (grow only) */
-    DevBuf d_img, d_gray, d_lines, d_frames, d_poses, d_yaws, d_jobs, d_objs, d_tiles, d_blocks, d_dtids;
-    DevBuf d_map, d_queue, d_qtail, d_dist, d_mlines, d_lcounts, d_err;
+    DevBuf d_img, d_gray, d_lines, d_frames, d_poses, d_yaws, d_jobs, d_objs, d_blocks, d_dtids;
+    DevBuf d_bits, d_dist, d_mlines, d_lcounts, d_err;
     DevBuf d_cvalid, d_cdist, d_cangle, d_vlist, d_key, d_idx, d_flag, d_keep, d_norm, d_score, d_jcounts;
     DevBuf d_out, d_outcnt, d_gather;
     void *pinned = nullptr;
@@ -138,10 +137,13 @@ int build_tables(cs_ctx *c)
     c->yaws.clear();
     c->jobs.clear();
     c->objs.clear();
-    c->tiles.clear();
     c->sweep_blocks.clear();
     c->total_px = 0;
     c->total_cand = 0;
+    c->total_bits = 0;
+    c->n_tiles = 0;
+    c->max_plane_words = 0;
+    c->max_dpitch = 0;
     const int img_width = c->w, img_height = c->h;
 
     for (int f = 0; f < F; f++) {
@@ -249,22 +251,21 @@ int build_tables(cs_ctx *c)
                     return fail(c, CS_ERR_INVALID_ARG, "frame %d box %d: empty or out-of-image ROI", f, b - c->h_box_off[f]);
                 if (cs_dt_class_of(jb.roi_w) < 0) return fail(c, CS_ERR_CAPACITY, "ROI wider than %d px", 32 * 64);
                 jb.n_cand = fr.n_pose * fr.n_yaw * jb.n_top * 2;
+                jb.bw = (jb.roi_w + 31) / 32;
+                jb.dpitch = (jb.roi_w + 3) & ~3;
                 jb.px_off = c->total_px;
-                c->total_px += ((int64_t)jb.roi_w * jb.roi_h + 15) / 16 * 16;
+                c->total_px += ((int64_t)jb.dpitch * jb.roi_h + 15) / 16 * 16;
+                jb.bit_off = c->total_bits;
+                const int plane_words = (jb.roi_h + 2) * (jb.bw + 2);
+                c->total_bits += 2 * (int64_t)plane_words;
+                c->max_plane_words = std::max(c->max_plane_words, plane_words);
+                c->max_dpitch = std::max(c->max_dpitch, jb.dpitch);
                 jb.cand_off = c->total_cand;
                 c->total_cand += jb.n_cand;
-                jb.tile_off = (int32_t)c->tiles.size();
+                jb.tile_off = c->n_tiles;
                 jb.tiles_x = (jb.roi_w + 31) / 32;
-                const int tiles_y = (jb.roi_h + 31) / 32;
+                c->n_tiles += jb.tiles_x * ((jb.roi_h + 31) / 32);
                 const int job_id = (int)c->jobs.size();
-                for (int ty = 0; ty < tiles_y; ty++)
-                    for (int tx = 0; tx < jb.tiles_x; tx++) {
-                        CsTile t;
-                        t.job = job_id;
-                        t.tx = (int16_t)tx;
-                        t.ty = (int16_t)ty;
-                        c->tiles.push_back(t);
-                    }
                 for (int ps = 0; ps < fr.n_pose; ps++) c->sweep_blocks.push_back(make_int2(job_id, ps));
                 c->jobs.push_back(jb);
             }
@@ -272,14 +273,11 @@ int build_tables(cs_ctx *c)
             c->objs.push_back(ob);
         }
     }
-    /* distance-transform width classes */
+    /* distance-transform order: jobs grouped by width class so neighbouring CTAs share an instantiation */
     c->dt_ids.clear();
-    for (int cls = 0; cls < CS_DT_CLASSES; cls++) {
-        c->dt_class_off[cls] = (int)c->dt_ids.size();
+    for (int cls = 0; cls < CS_DT_CLASSES; cls++)
         for (size_t j = 0; j < c->jobs.size(); j++)
             if (cs_dt_class_of(c->jobs[j].roi_w) == cls) c->dt_ids.push_back((int32_t)j);
-    }
-    c->dt_class_off[CS_DT_CLASSES] = (int)c->dt_ids.size();
     return CS_OK;
 }
 
@@ -288,9 +286,7 @@ int alloc_work(cs_cuboid_params &, cs_ctx *c)
     int rc;
     const size_t px = (size_t)std::max<int64_t>(c->total_px, 16), cand = (size_t)std::max<int64_t>(c->total_cand, 16);
     const size_t nj = std::max<size_t>(c->jobs.size(), 1), no = std::max<size_t>(c->objs.size(), 1);
-    if ((rc = ensure(c, c->d_map, px + 16))) return rc;
-    if ((rc = ensure(c, c->d_queue, px * 4))) return rc;
-    if ((rc = ensure(c, c->d_qtail, nj * 4))) return rc;
+    if ((rc = ensure(c, c->d_bits, (size_t)std::max<int64_t>(c->total_bits, 16) * 4))) return rc;
     if ((rc = ensure(c, c->d_dist, px * 4))) return rc;
     if ((rc = ensure(c, c->d_mlines, nj * CS_MAXL_OUT * 7 * sizeof(double)))) return rc;
     if ((rc = ensure(c, c->d_lcounts, nj * 2 * 4))) return rc;
@@ -326,7 +322,6 @@ int run_batch(cs_ctx *c, bool sync)
     if ((rc = upload(c, c->d_yaws, c->yaws))) return rc;
     if ((rc = upload(c, c->d_jobs, c->jobs))) return rc;
     if ((rc = upload(c, c->d_objs, c->objs))) return rc;
-    if ((rc = upload(c, c->d_tiles, c->tiles))) return rc;
     if ((rc = upload(c, c->d_blocks, c->sweep_blocks))) return rc;
     if ((rc = upload(c, c->d_dtids, c->dt_ids))) return rc;
     CS_CUDA(c, cudaMemsetAsync(c->d_err.p, 0, 16, st));
@@ -343,13 +338,13 @@ int run_batch(cs_ctx *c, bool sync)
         gray = (const uint8_t *)c->d_img.p;
     mark(ST_CANNY);
     int low = (int)std::floor(std::min(c->prm.canny_low, c->prm.canny_high)), high = (int)std::floor(std::max(c->prm.canny_low, c->prm.canny_high));
-    cs_launch_canny(gray, c->w, c->h, (const CsJob *)c->d_jobs.p, n_jobs, (const CsTile *)c->d_tiles.p, (int)c->tiles.size(), (uint8_t *)c->d_map.p,
-                    (int32_t *)c->d_queue.p, (int32_t *)c->d_qtail.p, low, high, st, &c->launches);
+    cs_launch_canny(gray, c->w, c->h, (const CsJob *)c->d_jobs.p, n_jobs, c->n_tiles, (uint32_t *)c->d_bits.p, (size_t)c->total_bits * 4, low, high,
+                    st, &c->launches);
     mark(ST_HYST);
-    cs_launch_hyst((const CsJob *)c->d_jobs.p, n_jobs, (uint8_t *)c->d_map.p, (int32_t *)c->d_queue.p, (int32_t *)c->d_qtail.p, st, &c->launches);
+    cs_launch_hyst((const CsJob *)c->d_jobs.p, n_jobs, (uint32_t *)c->d_bits.p, c->max_plane_words, st, &c->launches);
     mark(ST_DT);
-    cs_launch_dt((const CsJob *)c->d_jobs.p, (const int32_t *)c->d_dtids.p, c->dt_class_off, (const uint8_t *)c->d_map.p, (float *)c->d_dist.p, st,
-                 &c->launches);
+    cs_launch_dt((const CsJob *)c->d_jobs.p, (const int32_t *)c->d_dtids.p, n_jobs, c->max_dpitch, (const uint32_t *)c->d_bits.p, (float *)c->d_dist.p,
+                 st, &c->launches);
     mark(ST_LINES);
     cs_launch_roi_lines((const CsJob *)c->d_jobs.p, n_jobs, (const CsFrame *)c->d_frames.p, (const double *)c->d_lines.p, (double *)c->d_mlines.p,
                         (int32_t *)c->d_lcounts.p, (int32_t *)c->d_err.p, c->prm.pre_merge_dist_thre, c->prm.pre_merge_angle_thre,
@@ -520,8 +515,8 @@ void cs_destroy(cs_ctx *c)
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
     cs_nccl_teardown(c);
-    DevBuf *all[] = {&c->d_img,   &c->d_gray,  &c->d_lines,  &c->d_frames, &c->d_poses,   &c->d_yaws, &c->d_jobs, &c->d_objs,  &c->d_tiles,
-                     &c->d_blocks, &c->d_dtids, &c->d_map,    &c->d_queue,  &c->d_qtail,   &c->d_dist, &c->d_mlines, &c->d_lcounts, &c->d_err,
+    DevBuf *all[] = {&c->d_img,   &c->d_gray,  &c->d_lines,  &c->d_frames, &c->d_poses,   &c->d_yaws, &c->d_jobs, &c->d_objs,
+                     &c->d_blocks, &c->d_dtids, &c->d_bits, &c->d_dist, &c->d_mlines, &c->d_lcounts, &c->d_err,
                      &c->d_cvalid, &c->d_cdist, &c->d_cangle, &c->d_vlist,  &c->d_key,     &c->d_idx,  &c->d_flag, &c->d_keep,  &c->d_norm,
                      &c->d_score,  &c->d_jcounts, &c->d_out,  &c->d_outcnt, &c->d_gather};
     for (DevBuf *b : all)
@@ -687,10 +682,15 @@ int cs_debug_roi(cs_ctx *c, int job, int32_t roi_xywh[4], uint8_t *canny, float 
     }
     CS_CUDA(c, cudaStreamSynchronize(c->stream));
     if (canny && cap_px >= npx) {
-        CS_CUDA(c, cudaMemcpy(canny, (uint8_t *)c->d_map.p + jb.px_off, npx, cudaMemcpyDeviceToHost));
-        for (int i = 0; i < npx; i++) canny[i] = (canny[i] & 2) ? 255 : 0;
+        const int bwp = jb.bw + 2;
+        std::vector<uint32_t> plane((size_t)(jb.roi_h + 2) * bwp);
+        CS_CUDA(c, cudaMemcpy(plane.data(), (uint32_t *)c->d_bits.p + jb.bit_off, plane.size() * 4, cudaMemcpyDeviceToHost));
+        for (int y = 0; y < jb.roi_h; y++)
+            for (int x = 0; x < jb.roi_w; x++) canny[(size_t)y * jb.roi_w + x] = ((plane[(size_t)(y + 1) * bwp + 1 + (x >> 5)] >> (x & 31)) & 1u) ? 255 : 0;
     }
-    if (dist && cap_px >= npx) CS_CUDA(c, cudaMemcpy(dist, (float *)c->d_dist.p + jb.px_off, (size_t)npx * 4, cudaMemcpyDeviceToHost));
+    if (dist && cap_px >= npx)
+        CS_CUDA(c, cudaMemcpy2D(dist, (size_t)jb.roi_w * 4, (float *)c->d_dist.p + jb.px_off, (size_t)jb.dpitch * 4, (size_t)jb.roi_w * 4, jb.roi_h,
+                                cudaMemcpyDeviceToHost));
     int32_t cnt[2];
     CS_CUDA(c, cudaMemcpy(cnt, (int32_t *)c->d_lcounts.p + job * 2, 8, cudaMemcpyDeviceToHost));
     if (n_lines_roi) *n_lines_roi = cnt[0];

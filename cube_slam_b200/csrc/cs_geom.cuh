@@ -204,7 +204,7 @@ __constant__ int8_t c_vpe2[3][4] = {{0, 1, 2, 3}, {3, 0, 4, 5}, {2, 4, 1, 5}};
 
 /* box_edge_sum_dists (object_3d_util.cpp:427-453): 11 samples per visible edge, float32 running sum in
  * the reference's order.  Out-of-range indices (the reference's latent inclusive-box UB) are clamped. */
-__device__ __forceinline__ double g_edge_sum_dists(const float *__restrict__ dist, int dw, int dh, const D2 *c, double off_x, double off_y,
+__device__ __forceinline__ double g_edge_sum_dists(const float *__restrict__ dist, int pitch, int dw, int dh, const D2 *c, double off_x, double off_y,
                                                    int config_id, bool reweight)
 {
     float sum_dist = 0;
@@ -223,7 +223,7 @@ __device__ __forceinline__ double g_edge_sum_dists(const float *__restrict__ dis
             int ix = (int)px, iy = (int)py;
             ix = min(max(ix, 0), dw - 1);
             iy = min(max(iy, 0), dh - 1);
-            float d1 = __ldg(dist + (size_t)iy * dw + ix);
+            float d1 = __ldg(dist + (size_t)iy * pitch + ix);
             if (rw) {
                 if (4 <= e && e <= 5) d1 = (float)((double)d1 * 3.0 / 2.0);
                 if (6 == e) d1 = (float)((double)d1 * 2.0);

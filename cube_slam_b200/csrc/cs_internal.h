@@ -46,9 +46,12 @@ struct CsJob {
     int32_t roi_w, roi_h;               /* width_expan_distmap, height_expan_distmap */
     int32_t n_top, top_lo, top_hi, top_step, top_override;
     int32_t n_cand;                     /* n_pose * n_yaw * n_top * 2 */
-    int32_t tile_off;                   /* first canny tile of this job */
+    int32_t tile_off;                   /* first canny tile of this job (prefix over jobs) */
     int32_t tiles_x;
-    int64_t px_off;                     /* offset of this ROI in the edge / dist arenas (pixels) */
+    int32_t bw;                         /* 32-bit words per bit-plane row, ceil(roi_w / 32) */
+    int32_t dpitch;                     /* row pitch of the dist map in floats (roi_w rounded up to 4) */
+    int64_t bit_off;                    /* offset (words) of this ROI's two bordered bit planes */
+    int64_t px_off;                     /* offset (floats) of this ROI's dist map, multiple of 16 */
     int64_t cand_off;                   /* offset into the candidate record arenas */
     double diag;                        /* obj_diaglength_expan */
 };
@@ -57,11 +60,6 @@ struct CsObj {
     int32_t frame;
     int32_t job_off, n_jobs;
     int32_t left, top, width_raw, height_raw;
-};
-
-struct CsTile {
-    int32_t job;
-    int16_t tx, ty;
 };
 
 #endif

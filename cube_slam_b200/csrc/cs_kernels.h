@@ -13,11 +13,11 @@ int cs_dt_class_of(int roi_w);
 
 void cs_launch_gray(const uint8_t *d_img, uint8_t *d_gray, int n_frames, int w, int h, int stride, int channels, cudaStream_t st,
                     int64_t *launches);
-void cs_launch_canny(const uint8_t *d_gray, int img_w, int img_h, const CsJob *d_jobs, int n_jobs, const CsTile *d_tiles, int n_tiles,
-                     uint8_t *d_map, int32_t *d_queue, int32_t *d_qtail, int low, int high, cudaStream_t st, int64_t *launches);
-void cs_launch_hyst(const CsJob *d_jobs, int n_jobs, uint8_t *d_map, int32_t *d_queue, int32_t *d_qtail, cudaStream_t st, int64_t *launches);
-void cs_launch_dt(const CsJob *d_jobs, const int32_t *d_ids, const int *class_off, const uint8_t *d_map, float *d_dist, cudaStream_t st,
-                  int64_t *launches);
+void cs_launch_canny(const uint8_t *d_gray, int img_w, int img_h, const CsJob *d_jobs, int n_jobs, int n_tiles, uint32_t *d_bits,
+                     size_t bits_bytes, int low, int high, cudaStream_t st, int64_t *launches);
+void cs_launch_hyst(const CsJob *d_jobs, int n_jobs, uint32_t *d_bits, int max_plane_words, cudaStream_t st, int64_t *launches);
+void cs_launch_dt(const CsJob *d_jobs, const int32_t *d_ids, int n_jobs, int max_dpitch, const uint32_t *d_bits, float *d_dist,
+                  cudaStream_t st, int64_t *launches);
 void cs_launch_roi_lines(const CsJob *d_jobs, int n_jobs, const CsFrame *d_frames, const double *d_lines, double *d_out_lines,
                          int32_t *d_out_counts, int32_t *d_err, double dist_thre, double angle_thre_deg, double len_thre, cudaStream_t st,
                          int64_t *launches);

@@ -8,6 +8,11 @@
  *
  * All stages are integer / fixed-point and therefore bit-exact against the oracle restatements
  * (oracle/cuboid_oracle.cpp: orc_bgr2gray, orc_canny, orc_chamfer_dt).
+ *
+ * Edge maps travel as BIT PLANES (1 bit per pixel): plane S = "edge" (strong, or weak reached by the
+ * hysteresis), plane W = weak candidates.  A ROI of h rows x w columns is stored with a one-word / one-row
+ * zero border: (h+2) rows of (bw+2) 32-bit words, bw = ceil(w/32).  That makes NMS output two ballots per
+ * warp, hysteresis a word-parallel dilation in shared memory, and the distance transform's input 32x smaller.
  */
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -63,65 +68,81 @@ __global__ void __launch_bounds__(256) k_bgr2gray_generic(const uint8_t *__restr
 /* ------------------------------------------------------------------------------------------
  * Canny part 1: Sobel + |dx|+|dy| + non-maximum suppression over 32x32 tiles of each ROI.
  * The gray tile (+2 halo, replicated at the ROI border: OpenCV filters an ROI in isolation) is staged
- * in shared memory; magnitudes of the +1 halo are held there too (zero outside the ROI).
- * Map codes: 0 = not an edge, 1 = weak candidate, 2 = strong.  Strong pixels are appended to the
- * job's hysteresis queue with one atomic per warp.
+ * in shared memory; magnitudes of the +1 halo are held there too (zero outside the ROI).  A warp
+ * owns 32 consecutive pixels of a row, so the strong / weak classification leaves as two ballots.
  * ------------------------------------------------------------------------------------------ */
 #define CT 32 /* tile edge */
 
 __global__ void __launch_bounds__(256) k_canny_nms(const uint8_t *__restrict__ gray, int img_w, int img_h, const CsJob *__restrict__ jobs,
-                                                   const CsTile *__restrict__ tiles, uint8_t *__restrict__ map_arena,
-                                                   int32_t *__restrict__ queue_arena, int32_t *__restrict__ q_tail, int low, int high)
+                                                   int n_jobs, uint32_t *__restrict__ bits_arena, int low, int high)
 {
-    __shared__ uint8_t s_g[CT + 4][CT + 4];
-    __shared__ int16_t s_dx[CT + 2][CT + 2];
-    __shared__ int16_t s_dy[CT + 2][CT + 2];
+    __shared__ uint8_t s_g[CT + 4][CT + 4 + 4];
+    __shared__ int16_t s_dx[CT + 2][CT + 2 + 2];
+    __shared__ int16_t s_dy[CT + 2][CT + 2 + 2];
     __shared__ uint16_t s_m[CT + 2][CT + 2 + 2];
+    __shared__ int s_job;
 
-    const CsTile t = tiles[blockIdx.x];
-    const CsJob jb = jobs[t.job];
-    const int w = jb.roi_w, h = jb.roi_h;
-    const int x0 = t.tx * CT, y0 = t.ty * CT;
-    const uint8_t *src = gray + ((size_t)jb.frame * img_h + jb.roi_t) * img_w + jb.roi_l;
-    const int tid = threadIdx.x;
-
-    for (int i = tid; i < (CT + 4) * (CT + 4); i += 256) {
-        const int ly = i / (CT + 4), lx = i - ly * (CT + 4);
-        int gy = y0 + ly - 2, gx = x0 + lx - 2;
-        gy = min(max(gy, 0), h - 1);
-        gx = min(max(gx, 0), w - 1);
-        s_g[ly][lx] = src[(size_t)gy * img_w + gx];
+    /* tile -> job: binary search in the per-job tile prefix */
+    if (threadIdx.x == 0 && threadIdx.y == 0) {
+        int lo = 0, hi = n_jobs - 1;
+        const int t = blockIdx.x;
+        while (lo < hi) {
+            const int mid = (lo + hi + 1) >> 1;
+            if (jobs[mid].tile_off <= t)
+                lo = mid;
+            else
+                hi = mid - 1;
+        }
+        s_job = lo;
     }
     __syncthreads();
-    for (int i = tid; i < (CT + 2) * (CT + 2); i += 256) {
-        const int ly = i / (CT + 2), lx = i - ly * (CT + 2);
-        const int gy = y0 + ly - 1, gx = x0 + lx - 1; /* ROI coordinates of this magnitude */
-        int dx = 0, dy = 0, m = 0;
-        if (gy >= 0 && gy < h && gx >= 0 && gx < w) {
-            const int cy = ly + 1, cx = lx + 1; /* centre in s_g */
-            const int a = s_g[cy - 1][cx - 1], b = s_g[cy - 1][cx], c = s_g[cy - 1][cx + 1];
-            const int d = s_g[cy][cx - 1], f = s_g[cy][cx + 1];
-            const int g = s_g[cy + 1][cx - 1], hh = s_g[cy + 1][cx], k = s_g[cy + 1][cx + 1];
-            dx = (c + 2 * f + k) - (a + 2 * d + g);
-            dy = (g + 2 * hh + k) - (a + 2 * b + c);
-            m = abs(dx) + abs(dy);
+    const CsJob &jb = jobs[s_job];
+    const int w = jb.roi_w, h = jb.roi_h;
+    const int tl = blockIdx.x - jb.tile_off;
+    const int tile_y = tl / jb.tiles_x, tile_x = tl - tile_y * jb.tiles_x;
+    const int x0 = tile_x * CT, y0 = tile_y * CT;
+    const uint8_t *src = gray + ((size_t)jb.frame * img_h + jb.roi_t) * img_w + jb.roi_l;
+    const int tx = threadIdx.x, ty = threadIdx.y;
+
+    for (int ly = ty; ly < CT + 4; ly += 8) {
+        const int gy = min(max(y0 + ly - 2, 0), h - 1);
+        for (int lx = tx; lx < CT + 4; lx += 32) {
+            const int gx = min(max(x0 + lx - 2, 0), w - 1);
+            s_g[ly][lx] = src[(size_t)gy * img_w + gx];
         }
-        s_dx[ly][lx] = (int16_t)dx;
-        s_dy[ly][lx] = (int16_t)dy;
-        s_m[ly][lx] = (uint16_t)m;
+    }
+    __syncthreads();
+    for (int ly = ty; ly < CT + 2; ly += 8) {
+        const int gy = y0 + ly - 1;
+        for (int lx = tx; lx < CT + 2; lx += 32) {
+            const int gx = x0 + lx - 1; /* ROI coordinates of this magnitude */
+            int dx = 0, dy = 0, m = 0;
+            if (gy >= 0 && gy < h && gx >= 0 && gx < w) {
+                const int cy = ly + 1, cx = lx + 1; /* centre in s_g */
+                const int a = s_g[cy - 1][cx - 1], b = s_g[cy - 1][cx], c = s_g[cy - 1][cx + 1];
+                const int d = s_g[cy][cx - 1], f = s_g[cy][cx + 1];
+                const int g = s_g[cy + 1][cx - 1], hh = s_g[cy + 1][cx], k = s_g[cy + 1][cx + 1];
+                dx = (c + 2 * f + k) - (a + 2 * d + g);
+                dy = (g + 2 * hh + k) - (a + 2 * b + c);
+                m = abs(dx) + abs(dy);
+            }
+            s_dx[ly][lx] = (int16_t)dx;
+            s_dy[ly][lx] = (int16_t)dy;
+            s_m[ly][lx] = (uint16_t)m;
+        }
     }
     __syncthreads();
 
     const int TG22 = 13573; /* (int)(0.4142135623730950488016887242097 * (1 << 15) + 0.5) */
-    uint8_t *map = map_arena + jb.px_off;
-    int32_t *queue = queue_arena + jb.px_off;
-    const int lane = tid & 31;
-    for (int i = tid; i < CT * CT; i += 256) {
-        const int ly = i >> 5, lx = i & 31;
+    const int bwp = jb.bw + 2;
+    uint32_t *planeS = bits_arena + jb.bit_off;
+    uint32_t *planeW = planeS + (size_t)(h + 2) * bwp;
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        const int ly = ty + 8 * k, lx = tx;
         const int gy = y0 + ly, gx = x0 + lx;
-        const bool in = (gy < h && gx < w);
         int code = 0;
-        if (in) {
+        if (gy < h && gx < w) {
             const int my = ly + 1, mx = lx + 1;
             const int m = s_m[my][mx];
             if (m > low) {
@@ -142,65 +163,90 @@ __global__ void __launch_bounds__(256) k_canny_nms(const uint8_t *__restrict__ g
                 }
                 if (is_max) code = (m > high) ? 2 : 1;
             }
-            map[(size_t)gy * w + gx] = (uint8_t)code;
         }
-        /* warp-aggregated append of strong pixels */
         const unsigned strong = __ballot_sync(0xffffffffu, code == 2);
-        if (strong) {
-            int base = 0;
-            if (lane == 0) base = atomicAdd(&q_tail[t.job], __popc(strong));
-            base = __shfl_sync(0xffffffffu, base, 0);
-            if (code == 2) queue[base + __popc(strong & ((1u << lane) - 1u))] = gy * w + gx;
+        const unsigned weak = __ballot_sync(0xffffffffu, code == 1);
+        if (tx == 0 && gy < h) {
+            const size_t wi = (size_t)(gy + 1) * bwp + 1 + tile_x;
+            planeS[wi] = strong;
+            planeW[wi] = weak;
         }
     }
 }
 
 /* ------------------------------------------------------------------------------------------
- * Canny part 2: hysteresis.  One CTA per ROI runs a level-synchronous flood fill from the strong
- * pixels; a weak pixel (1) is claimed exactly once by an atomicOr on its byte's word (1 -> 3).
- * The result (all weak pixels 8-connected to a strong one) does not depend on visiting order, so
- * it equals OpenCV's stack-based flood fill bit for bit.
+ * Canny part 2: hysteresis on the bit planes.  One CTA per ROI; both planes sit in shared memory
+ * (global memory for ROIs too large for it).  A thread owns one word column over a run of rows and
+ * sweeps it down and up: new = dilate3x3(S) & W, closed horizontally inside the word, moved from W
+ * to S.  Sweeps repeat until no thread changed anything.  The fixed point (every weak pixel
+ * 8-connected to a strong one) is unique, hence identical to OpenCV's stack-based flood fill.
  * ------------------------------------------------------------------------------------------ */
-__global__ void __launch_bounds__(256) k_canny_hyst(const CsJob *__restrict__ jobs, uint8_t *__restrict__ map_arena,
-                                                    int32_t *__restrict__ queue_arena, int32_t *__restrict__ q_tail)
+#define HY_THREADS 256
+
+template <class PT>
+__device__ __forceinline__ bool hyst_word(PT S, PT W, int bwp, int r, int c)
 {
-    __shared__ int s_new;
-    const CsJob jb = jobs[blockIdx.x];
-    const int w = jb.roi_w, h = jb.roi_h;
-    uint8_t *map = map_arena + jb.px_off;
-    int32_t *queue = queue_arena + jb.px_off;
-    int head = 0, tail = q_tail[blockIdx.x];
+    const size_t i = (size_t)r * bwp + c;
+    uint32_t m = W[i];
+    if (m == 0) return false;
+    const uint32_t nC = S[i - bwp] | S[i] | S[i + bwp];
+    const uint32_t nL = S[i - bwp - 1] | S[i - 1] | S[i + bwp - 1];
+    const uint32_t nR = S[i - bwp + 1] | S[i + 1] | S[i + bwp + 1];
+    const uint32_t d = nC | (nC << 1) | (nC >> 1) | (nL >> 31) | (nR << 31);
+    uint32_t nw = d & m;
+    if (nw == 0) return false;
+    uint32_t s = S[i] | nw;
+    m &= ~nw;
+    /* close horizontally inside the word */
+    while (true) {
+        const uint32_t t = ((s << 1) | (s >> 1)) & m;
+        if (t == 0) break;
+        s |= t;
+        m &= ~t;
+    }
+    S[i] = s;
+    W[i] = m;
+    return true;
+}
+
+extern __shared__ uint32_t hy_smem[];
+
+__global__ void __launch_bounds__(HY_THREADS) k_canny_hyst(const CsJob *__restrict__ jobs, uint32_t *__restrict__ bits_arena, int smem_words)
+{
+    const CsJob &jb = jobs[blockIdx.x];
+    const int h = jb.roi_h, bw = jb.bw, bwp = bw + 2;
+    const int plane = (h + 2) * bwp;
+    uint32_t *gS = bits_arena + jb.bit_off;
+    const bool in_smem = (2 * plane <= smem_words);
+    uint32_t *S = in_smem ? hy_smem : gS;
+    uint32_t *W = S + plane;
     const int tid = threadIdx.x;
-    while (tail > head) {
-        if (tid == 0) s_new = 0;
+    if (in_smem) {
+        for (int i = tid; i < 2 * plane; i += HY_THREADS) S[i] = gS[i];
         __syncthreads();
-        for (int i = head + tid; i < tail; i += 256) {
-            const int p = queue[i];
-            const int y = p / w, x = p - y * w;
-#pragma unroll
-            for (int dy = -1; dy <= 1; dy++) {
-                const int ny = y + dy;
-                if (ny < 0 || ny >= h) continue;
-#pragma unroll
-                for (int dx = -1; dx <= 1; dx++) {
-                    if (dx == 0 && dy == 0) continue;
-                    const int nx = x + dx;
-                    if (nx < 0 || nx >= w) continue;
-                    const size_t q = (size_t)ny * w + nx;
-                    if (map[q] == 1) {
-                        const uintptr_t addr = (uintptr_t)(map + q);
-                        unsigned *word = (unsigned *)(addr & ~(uintptr_t)3);
-                        const unsigned sh = (unsigned)(addr & 3) * 8u;
-                        const unsigned old = atomicOr(word, 2u << sh);
-                        if (((old >> sh) & 255u) == 1u) queue[tail + atomicAdd(&s_new, 1)] = ny * w + nx;
-                    }
-                }
+    }
+    /* thread -> (word column, row run) */
+    const int n_runs = max(HY_THREADS / bw, 1);
+    const int rows_per = (h + n_runs - 1) / n_runs;
+    const int c = 1 + tid % bw, run = tid / bw;
+    const int r0 = 1 + run * rows_per, r1 = min(r0 + rows_per, h + 1);
+    const bool active = (run < n_runs) && (tid < n_runs * bw);
+    while (true) {
+        bool changed = false;
+        if (active) {
+            if (in_smem) {
+                for (int r = r0; r < r1; r++) changed |= hyst_word<uint32_t *>(S, W, bwp, r, c);
+                for (int r = r1 - 2; r >= r0; r--) changed |= hyst_word<uint32_t *>(S, W, bwp, r, c);
+            } else { /* oversized ROI: iterate in global memory (volatile: neighbours' updates must be re-read) */
+                for (int r = r0; r < r1; r++) changed |= hyst_word<volatile uint32_t *>(S, W, bwp, r, c);
+                for (int r = r1 - 2; r >= r0; r--) changed |= hyst_word<volatile uint32_t *>(S, W, bwp, r, c);
+                __threadfence();
             }
         }
-        __syncthreads();
-        head = tail;
-        tail += s_new;
-        __syncthreads();
+        if (!__syncthreads_or(changed ? 1 : 0)) break;
+    }
+    if (in_smem) {
+        for (int i = tid; i < plane; i += HY_THREADS) gS[i] = S[i];
     }
 }
 
@@ -212,69 +258,145 @@ __global__ void __launch_bounds__(256) k_canny_hyst(const CsJob *__restrict__ jo
  * evaluated as a local scan + a 5-step warp scan, all in exact integer arithmetic, so the result
  * equals the sequential OpenCV loop bit for bit.  "Infinity" is a sentinel BIG (> any reachable
  * distance) that is re-clamped every row; it is emitted as OpenCV's saturated DIST_MAX.
+ * The edge bits of the next rows are prefetched into registers; the backward pass streams the forward
+ * rows back through a cp.async ring in shared memory, so no row waits on an L2 round trip.
  * ------------------------------------------------------------------------------------------ */
 #define DT_HV 62587
 #define DT_DG 89738
 #define DT_BIG (1 << 30)
+#define DT_PF 4   /* prefetch depth (rows) */
+
+/* the PPL edge bits of columns [c0, c0+PPL) of one bit-plane row, as 64-bit mask */
+template <int PPL>
+__device__ __forceinline__ uint64_t dt_row_bits(const uint32_t *__restrict__ row_words /* word 0 = column 0 */, int c0, int bw)
+{
+    const int w0 = c0 >> 5, sh = c0 & 31;
+    /* words beyond the row are the zero border / next row start: mask by bw */
+    const uint32_t a = (w0 < bw) ? __ldg(row_words + w0) : 0u;
+    const uint32_t b = (w0 + 1 < bw) ? __ldg(row_words + w0 + 1) : 0u;
+    uint64_t bits = __funnelshift_r(a, b, sh);
+    if (PPL > 32) {
+        const uint32_t c = (w0 + 2 < bw) ? __ldg(row_words + w0 + 2) : 0u;
+        bits |= (uint64_t)__funnelshift_r(b, c, sh) << 32;
+    }
+    return bits;
+}
+
+__device__ __forceinline__ void cp_async16(void *smem, const void *gmem)
+{
+    const unsigned s = (unsigned)__cvta_generic_to_shared(smem);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(s), "l"(gmem));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait()
+{
+    asm volatile("cp.async.wait_group %0;\n" ::"n"(N));
+}
 
 template <int PPL>
-__device__ __forceinline__ void dt_warp(const uint8_t *__restrict__ map, uint32_t *__restrict__ tmp, int w, int h)
+__device__ __forceinline__ void dt_warp(const uint32_t *__restrict__ planeS, int bwp, uint32_t *__restrict__ tmp, int w, int h, int dpitch,
+                                        uint32_t *ring /* DT_PF rows of dpitch words, shared */)
 {
     const int lane = threadIdx.x & 31;
     const int c0 = lane * PPL;
     const unsigned FULL = 0xffffffffu;
+    const int bw = bwp - 2;
     int up[PPL];
 #pragma unroll
     for (int k = 0; k < PPL; k++) up[k] = DT_BIG;
 
-    /* forward pass */
-    for (int i = 0; i < h; i++) {
-        const uint8_t *mrow = map + (size_t)i * w;
-        int upL = __shfl_up_sync(FULL, up[PPL - 1], 1);
-        int upR = __shfl_down_sync(FULL, up[0], 1);
-        if (lane == 0) upL = DT_BIG;
-        if (lane == 31) upR = DT_BIG;
-        int v[PPL];
+    /* ---- forward pass ---- */
+    uint64_t pf[DT_PF];
 #pragma unroll
-        for (int k = 0; k < PPL; k++) {
-            const int col = c0 + k;
-            const int l = (k == 0) ? upL : up[k - 1];
-            const int r = (k == PPL - 1) ? upR : up[k + 1];
-            int u = min(min(l + DT_DG, up[k] + DT_HV), r + DT_DG);
-            if (col < w) {
-                if (mrow[col] & 2) u = 0;
-            } else
-                u = DT_BIG;
-            v[k] = u - DT_HV * col;
-        }
+    for (int d = 0; d < DT_PF; d++) pf[d] = (d < h) ? dt_row_bits<PPL>(planeS + (size_t)(d + 1) * bwp + 1, c0, bw) : 0ull;
+    for (int i0 = 0; i0 < h; i0 += DT_PF) {
 #pragma unroll
-        for (int k = 1; k < PPL; k++) v[k] = min(v[k], v[k - 1]);
-        int incl = v[PPL - 1];
+        for (int d = 0; d < DT_PF; d++) {
+            const int i = i0 + d;
+            if (i < h) {
+                const uint64_t bits = pf[d];
+                const int nxt = i + DT_PF;
+                pf[d] = (nxt < h) ? dt_row_bits<PPL>(planeS + (size_t)(nxt + 1) * bwp + 1, c0, bw) : 0ull;
+                int upL = __shfl_up_sync(FULL, up[PPL - 1], 1);
+                int upR = __shfl_down_sync(FULL, up[0], 1);
+                if (lane == 0) upL = DT_BIG;
+                if (lane == 31) upR = DT_BIG;
+                int v[PPL];
 #pragma unroll
-        for (int d = 1; d < 32; d <<= 1) {
-            const int o = __shfl_up_sync(FULL, incl, d);
-            if (lane >= d) incl = min(incl, o);
-        }
-        int excl = __shfl_up_sync(FULL, incl, 1);
-        if (lane == 0) excl = INT_MAX;
-        uint32_t *trow = tmp + (size_t)i * w;
+                for (int k = 0; k < PPL; k++) {
+                    const int col = c0 + k;
+                    const int l = (k == 0) ? upL : up[k - 1];
+                    const int r = (k == PPL - 1) ? upR : up[k + 1];
+                    int u = min(min(l + DT_DG, up[k] + DT_HV), r + DT_DG);
+                    if ((bits >> k) & 1ull) u = 0; /* bits beyond column w are zero (NMS writes none) */
+                    if (col >= w) u = DT_BIG;
+                    v[k] = u - DT_HV * col;
+                }
 #pragma unroll
-        for (int k = 0; k < PPL; k++) {
-            const int col = c0 + k;
-            int t = min(v[k], excl) + DT_HV * col;
-            if (t >= DT_BIG || col >= w) t = DT_BIG;
-            up[k] = t;
-            if (col < w) trow[col] = (uint32_t)t;
+                for (int k = 1; k < PPL; k++) v[k] = min(v[k], v[k - 1]);
+                int incl = v[PPL - 1];
+#pragma unroll
+                for (int dd = 1; dd < 32; dd <<= 1) {
+                    const int o = __shfl_up_sync(FULL, incl, dd);
+                    if (lane >= dd) incl = min(incl, o);
+                }
+                int excl = __shfl_up_sync(FULL, incl, 1);
+                if (lane == 0) excl = INT_MAX;
+                uint32_t *trow = tmp + (size_t)i * dpitch;
+#pragma unroll
+                for (int k = 0; k < PPL; k++) {
+                    const int col = c0 + k;
+                    int t = min(v[k], excl) + DT_HV * col;
+                    if (t >= DT_BIG || col >= w) t = DT_BIG;
+                    up[k] = t;
+                }
+#pragma unroll
+                for (int k = 0; k < PPL; k += 4)
+                    if (c0 + k < dpitch) *reinterpret_cast<uint4 *>(trow + c0 + k) = make_uint4(up[k], up[k + 1], up[k + 2], up[k + 3]);
+            }
         }
     }
 
-    /* backward pass: `up` now plays the role of the row below */
+    /* ---- backward pass: `up` now plays the role of the row below ---- */
 #pragma unroll
     for (int k = 0; k < PPL; k++) up[k] = DT_BIG;
     const float scale = 1.f / 65536.f;
     const float dist_max = (float)(0xffffffffu - (uint32_t)DT_DG) * scale;
+    const int chunks = dpitch >> 2; /* 16-byte chunks per row */
+    __syncwarp();
+    /* prime the ring with rows h-1 .. h-DT_PF */
+#pragma unroll
+    for (int d = 0; d < DT_PF; d++) {
+        const int i = h - 1 - d;
+        if (i >= 0)
+            for (int q = lane; q < chunks; q += 32) cp_async16(ring + (size_t)d * dpitch + q * 4, tmp + (size_t)i * dpitch + q * 4);
+        cp_async_commit();
+    }
+    int slot = 0;
     for (int i = h - 1; i >= 0; i--) {
-        uint32_t *trow = tmp + (size_t)i * w;
+        cp_async_wait<DT_PF - 1>();
+        __syncwarp();
+        const uint32_t *srow = ring + (size_t)slot * dpitch;
+        int cur[PPL];
+#pragma unroll
+        for (int k = 0; k < PPL; k += 4) {
+            uint4 q = make_uint4(DT_BIG, DT_BIG, DT_BIG, DT_BIG);
+            if (c0 + k < dpitch) q = *reinterpret_cast<const uint4 *>(srow + c0 + k);
+            cur[k] = (int)q.x;
+            cur[k + 1] = (int)q.y;
+            cur[k + 2] = (int)q.z;
+            cur[k + 3] = (int)q.w;
+        }
+        __syncwarp();
+        /* refill this slot with the row DT_PF above */
+        {
+            const int nxt = i - DT_PF;
+            if (nxt >= 0)
+                for (int q = lane; q < chunks; q += 32) cp_async16(ring + (size_t)slot * dpitch + q * 4, tmp + (size_t)nxt * dpitch + q * 4);
+            cp_async_commit();
+        }
+        slot = (slot + 1 == DT_PF) ? 0 : slot + 1;
         int dnL = __shfl_up_sync(FULL, up[PPL - 1], 1);
         int dnR = __shfl_down_sync(FULL, up[0], 1);
         if (lane == 0) dnL = DT_BIG;
@@ -285,47 +407,74 @@ __device__ __forceinline__ void dt_warp(const uint8_t *__restrict__ map, uint32_
             const int col = c0 + k;
             const int l = (k == 0) ? dnL : up[k - 1];
             const int r = (k == PPL - 1) ? dnR : up[k + 1];
-            int cur = (col < w) ? (int)trow[col] : DT_BIG;
-            cur = min(min(cur, r + DT_DG), min(up[k] + DT_HV, l + DT_DG));
-            if (col >= w) cur = DT_BIG;
-            v[k] = cur + DT_HV * col;
+            int c = min(min(cur[k], r + DT_DG), min(up[k] + DT_HV, l + DT_DG));
+            if (col >= w) c = DT_BIG;
+            v[k] = c + DT_HV * col;
         }
 #pragma unroll
         for (int k = PPL - 2; k >= 0; k--) v[k] = min(v[k], v[k + 1]);
         int incl = v[0];
 #pragma unroll
-        for (int d = 1; d < 32; d <<= 1) {
-            const int o = __shfl_down_sync(FULL, incl, d);
-            if (lane + d < 32) incl = min(incl, o);
+        for (int dd = 1; dd < 32; dd <<= 1) {
+            const int o = __shfl_down_sync(FULL, incl, dd);
+            if (lane + dd < 32) incl = min(incl, o);
         }
         int excl = __shfl_down_sync(FULL, incl, 1);
         if (lane == 31) excl = INT_MAX;
-        float *drow = reinterpret_cast<float *>(trow);
+        float *drow = reinterpret_cast<float *>(tmp + (size_t)i * dpitch);
+        float outv[PPL];
 #pragma unroll
         for (int k = 0; k < PPL; k++) {
             const int col = c0 + k;
             int t = min(v[k], excl) - DT_HV * col;
             if (t >= DT_BIG || col >= w) t = DT_BIG;
             up[k] = t;
-            if (col < w) drow[col] = (t >= DT_BIG) ? dist_max : (float)(uint32_t)t * scale;
+            outv[k] = (t >= DT_BIG) ? dist_max : (float)(uint32_t)t * scale;
         }
+#pragma unroll
+        for (int k = 0; k < PPL; k += 4)
+            if (c0 + k < dpitch) *reinterpret_cast<float4 *>(drow + c0 + k) = make_float4(outv[k], outv[k + 1], outv[k + 2], outv[k + 3]);
     }
+    cp_async_wait<0>();
 }
 
-template <int PPL>
-__global__ void __launch_bounds__(128) k_chamfer_dt(const CsJob *__restrict__ jobs, const int32_t *__restrict__ job_ids, int n_ids,
-                                                    const uint8_t *__restrict__ map_arena, float *__restrict__ dist_arena)
+extern __shared__ uint32_t dt_smem[];
+
+/* one warp per CTA; jobs are ordered by width class so neighbouring CTAs run the same instantiation */
+__global__ void __launch_bounds__(32) k_chamfer_dt(const CsJob *__restrict__ jobs, const int32_t *__restrict__ job_ids,
+                                                   const uint32_t *__restrict__ bits_arena, float *__restrict__ dist_arena)
 {
-    const int slot = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    if (slot >= n_ids) return;
-    const CsJob jb = jobs[job_ids[slot]];
-    const uint8_t *map = map_arena + jb.px_off;
+    const CsJob &jb = jobs[job_ids[blockIdx.x]];
+    const uint32_t *planeS = bits_arena + jb.bit_off;
     uint32_t *tmp = reinterpret_cast<uint32_t *>(dist_arena + jb.px_off);
-    if (jb.roi_w <= 0 || jb.roi_h <= 0) return;
-    dt_warp<PPL>(map, tmp, jb.roi_w, jb.roi_h);
+    const int w = jb.roi_w, h = jb.roi_h, bwp = jb.bw + 2, dp = jb.dpitch;
+    if (w <= 0 || h <= 0) return;
+    if (w <= 32 * 4)
+        dt_warp<4>(planeS, bwp, tmp, w, h, dp, dt_smem);
+    else if (w <= 32 * 8)
+        dt_warp<8>(planeS, bwp, tmp, w, h, dp, dt_smem);
+    else if (w <= 32 * 12)
+        dt_warp<12>(planeS, bwp, tmp, w, h, dp, dt_smem);
+    else if (w <= 32 * 16)
+        dt_warp<16>(planeS, bwp, tmp, w, h, dp, dt_smem);
+    else if (w <= 32 * 24)
+        dt_warp<24>(planeS, bwp, tmp, w, h, dp, dt_smem);
+    else if (w <= 32 * 40)
+        dt_warp<40>(planeS, bwp, tmp, w, h, dp, dt_smem);
+    else
+        dt_warp<64>(planeS, bwp, tmp, w, h, dp, dt_smem);
 }
 
 /* ------------------------------------------------------------------------------------------ launchers */
+const int cs_dt_class_ppl[CS_DT_CLASSES] = {4, 8, 12, 16, 24, 40, 64};
+
+int cs_dt_class_of(int roi_w)
+{
+    for (int c = 0; c < CS_DT_CLASSES; c++)
+        if (roi_w <= 32 * cs_dt_class_ppl[c]) return c;
+    return -1;
+}
+
 void cs_launch_gray(const uint8_t *d_img, uint8_t *d_gray, int n_frames, int w, int h, int stride, int channels, cudaStream_t st,
                     int64_t *launches)
 {
@@ -348,53 +497,44 @@ void cs_launch_gray(const uint8_t *d_img, uint8_t *d_gray, int n_frames, int w, 
     }
 }
 
-void cs_launch_canny(const uint8_t *d_gray, int img_w, int img_h, const CsJob *d_jobs, int n_jobs, const CsTile *d_tiles, int n_tiles,
-                     uint8_t *d_map, int32_t *d_queue, int32_t *d_qtail, int low, int high, cudaStream_t st, int64_t *launches)
+void cs_launch_canny(const uint8_t *d_gray, int img_w, int img_h, const CsJob *d_jobs, int n_jobs, int n_tiles, uint32_t *d_bits,
+                     size_t bits_bytes, int low, int high, cudaStream_t st, int64_t *launches)
 {
     if (n_jobs <= 0) return;
-    cudaMemsetAsync(d_qtail, 0, sizeof(int32_t) * n_jobs, st);
+    cudaMemsetAsync(d_bits, 0, bits_bytes, st); /* zero borders (and stale bits) of every plane */
     if (n_tiles > 0) {
-        k_canny_nms<<<n_tiles, 256, 0, st>>>(d_gray, img_w, img_h, d_jobs, d_tiles, d_map, d_queue, d_qtail, low, high);
+        k_canny_nms<<<n_tiles, dim3(32, 8), 0, st>>>(d_gray, img_w, img_h, d_jobs, n_jobs, d_bits, low, high);
         (*launches)++;
     }
 }
 
-void cs_launch_hyst(const CsJob *d_jobs, int n_jobs, uint8_t *d_map, int32_t *d_queue, int32_t *d_qtail, cudaStream_t st, int64_t *launches)
+void cs_launch_hyst(const CsJob *d_jobs, int n_jobs, uint32_t *d_bits, int max_plane_words, cudaStream_t st, int64_t *launches)
 {
     if (n_jobs <= 0) return;
-    k_canny_hyst<<<n_jobs, 256, 0, st>>>(d_jobs, d_map, d_queue, d_qtail);
+    static int cur_attr = 0;
+    int smem_words = 2 * max_plane_words;
+    const int cap_words = (200 * 1024) / 4;
+    if (smem_words > cap_words) smem_words = cap_words;
+    const int bytes = smem_words * 4;
+    if (bytes > cur_attr) {
+        cudaFuncSetAttribute(k_canny_hyst, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+        cur_attr = bytes;
+    }
+    k_canny_hyst<<<n_jobs, HY_THREADS, bytes, st>>>(d_jobs, d_bits, smem_words);
     (*launches)++;
 }
 
-/* width classes of the distance transform: a lane owns PPL columns */
-const int cs_dt_class_ppl[CS_DT_CLASSES] = {4, 8, 12, 16, 24, 40, 64};
-
-int cs_dt_class_of(int roi_w)
+/* d_ids: all job ids ordered by width class; max_dpitch = widest padded row of the batch */
+void cs_launch_dt(const CsJob *d_jobs, const int32_t *d_ids, int n_jobs, int max_dpitch, const uint32_t *d_bits, float *d_dist,
+                  cudaStream_t st, int64_t *launches)
 {
-    for (int c = 0; c < CS_DT_CLASSES; c++)
-        if (roi_w <= 32 * cs_dt_class_ppl[c]) return c;
-    return -1;
-}
-
-template <int PPL>
-static void launch_dt_class(const CsJob *d_jobs, const int32_t *d_ids, int n, const uint8_t *d_map, float *d_dist, cudaStream_t st,
-                            int64_t *launches)
-{
-    if (n <= 0) return;
-    const int wpb = (PPL >= 24) ? 2 : 4;
-    k_chamfer_dt<PPL><<<(n + wpb - 1) / wpb, wpb * 32, 0, st>>>(d_jobs, d_ids, n, d_map, d_dist);
+    if (n_jobs <= 0) return;
+    static int cur_attr = 0;
+    const int bytes = DT_PF * max_dpitch * 4;
+    if (bytes > cur_attr && bytes > 48 * 1024) {
+        cudaFuncSetAttribute(k_chamfer_dt, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+        cur_attr = bytes;
+    }
+    k_chamfer_dt<<<n_jobs, 32, bytes, st>>>(d_jobs, d_ids, d_bits, d_dist);
     (*launches)++;
-}
-
-/* d_ids: job ids grouped by class; class c occupies [class_off[c], class_off[c+1]) */
-void cs_launch_dt(const CsJob *d_jobs, const int32_t *d_ids, const int *class_off, const uint8_t *d_map, float *d_dist, cudaStream_t st,
-                  int64_t *launches)
-{
-    launch_dt_class<4>(d_jobs, d_ids + class_off[0], class_off[1] - class_off[0], d_map, d_dist, st, launches);
-    launch_dt_class<8>(d_jobs, d_ids + class_off[1], class_off[2] - class_off[1], d_map, d_dist, st, launches);
-    launch_dt_class<12>(d_jobs, d_ids + class_off[2], class_off[3] - class_off[2], d_map, d_dist, st, launches);
-    launch_dt_class<16>(d_jobs, d_ids + class_off[3], class_off[4] - class_off[3], d_map, d_dist, st, launches);
-    launch_dt_class<24>(d_jobs, d_ids + class_off[4], class_off[5] - class_off[4], d_map, d_dist, st, launches);
-    launch_dt_class<40>(d_jobs, d_ids + class_off[5], class_off[6] - class_off[5], d_map, d_dist, st, launches);
-    launch_dt_class<64>(d_jobs, d_ids + class_off[6], class_off[7] - class_off[6], d_map, d_dist, st, launches);
 }

@@ -209,7 +209,7 @@ __global__ void __launch_bounds__(SW_THREADS) k_sweep_score(const CsJob *__restr
                 const int sg = S.slot_cand[tid];
                 const int syi = sg / (n_top * 2);
                 const int scfg = ((sg - syi * (n_top * 2)) & 1) + 1;
-                const double sum_dist = g_edge_sum_dists(dist, jb.roi_w, jb.roi_h, S.corners[tid], (double)jb.roi_l, (double)jb.roi_t, scfg,
+                const double sum_dist = g_edge_sum_dists(dist, jb.dpitch, jb.roi_w, jb.roi_h, S.corners[tid], (double)jb.roi_l, (double)jb.roi_t, scfg,
                                                          prm.reweight_edge_distance != 0);
                 const double ang_err = g_angle_error(S.vp_angles[syi], scfg, S.corners[tid]);
                 const int64_t ci = cbase + (int64_t)y0 * n_top * 2 + sg;
