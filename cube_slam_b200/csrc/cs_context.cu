@@ -57,7 +57,8 @@ struct cs_ctx {
     std::vector<int2> sweep_blocks;
     std::vector<int32_t> dt_ids;
     int64_t total_px = 0, total_cand = 0, total_bits = 0;
-    int n_tiles = 0, max_plane_words = 0, max_dpitch = 0;
+    int n_tiles = 0, max_plane_words = 0, max_dpitch = 0, max_roi_h = 0;
+    int force_split_dt = 0; /* debug: use the two-kernel hysteresis + scan DT path */
 
     /* device buffers (grow only) */
     DevBuf d_img, d_gray, d_lines, d_frames, d_poses, d_yaws, d_jobs, d_objs, d_blocks, d_dtids;
@@ -144,6 +145,7 @@ int build_tables(cs_ctx *c)
     c->n_tiles = 0;
     c->max_plane_words = 0;
     c->max_dpitch = 0;
+    c->max_roi_h = 0;
     const int img_width = c->w, img_height = c->h;
 
     for (int f = 0; f < F; f++) {
@@ -260,6 +262,7 @@ int build_tables(cs_ctx *c)
                 c->total_bits += 2 * (int64_t)plane_words;
                 c->max_plane_words = std::max(c->max_plane_words, plane_words);
                 c->max_dpitch = std::max(c->max_dpitch, jb.dpitch);
+                c->max_roi_h = std::max(c->max_roi_h, jb.roi_h);
                 jb.cand_off = c->total_cand;
                 c->total_cand += jb.n_cand;
                 jb.tile_off = c->n_tiles;
@@ -341,10 +344,15 @@ int run_batch(cs_ctx *c, bool sync)
     cs_launch_canny(gray, c->w, c->h, (const CsJob *)c->d_jobs.p, n_jobs, c->n_tiles, (uint32_t *)c->d_bits.p, (size_t)c->total_bits * 4, low, high,
                     st, &c->launches);
     mark(ST_HYST);
-    cs_launch_hyst((const CsJob *)c->d_jobs.p, n_jobs, (uint32_t *)c->d_bits.p, c->max_plane_words, st, &c->launches);
+    bool fused = false;
+    if (!c->force_split_dt)
+        fused = cs_launch_hyst_dt((const CsJob *)c->d_jobs.p, n_jobs, (uint32_t *)c->d_bits.p, (float *)c->d_dist.p, c->max_plane_words, c->max_dpitch,
+                                  c->max_roi_h, st, &c->launches);
+    if (!fused) cs_launch_hyst((const CsJob *)c->d_jobs.p, n_jobs, (uint32_t *)c->d_bits.p, c->max_plane_words, st, &c->launches);
     mark(ST_DT);
-    cs_launch_dt((const CsJob *)c->d_jobs.p, (const int32_t *)c->d_dtids.p, n_jobs, c->max_dpitch, (const uint32_t *)c->d_bits.p, (float *)c->d_dist.p,
-                 st, &c->launches);
+    if (!fused)
+        cs_launch_dt((const CsJob *)c->d_jobs.p, (const int32_t *)c->d_dtids.p, n_jobs, c->max_dpitch, (const uint32_t *)c->d_bits.p, (float *)c->d_dist.p,
+                     st, &c->launches);
     mark(ST_LINES);
     cs_launch_roi_lines((const CsJob *)c->d_jobs.p, n_jobs, (const CsFrame *)c->d_frames.p, (const double *)c->d_lines.p, (double *)c->d_mlines.p,
                         (int32_t *)c->d_lcounts.p, (int32_t *)c->d_err.p, c->prm.pre_merge_dist_thre, c->prm.pre_merge_angle_thre,
@@ -646,7 +654,8 @@ void *cs_stream(cs_ctx *c) { return c ? (void *)c->stream : nullptr; }
 int cs_set_profiling(cs_ctx *c, int enable)
 {
     if (!c) return CS_ERR_INVALID_ARG;
-    c->profiling = enable != 0;
+    c->profiling = (enable & 1) != 0;
+    c->force_split_dt = (enable & 2) != 0; /* bit 1: take the split hysteresis / scan-DT kernels (fallback path testing) */
     return CS_OK;
 }
 

@@ -18,6 +18,8 @@ void cs_launch_canny(const uint8_t *d_gray, int img_w, int img_h, const CsJob *d
 void cs_launch_hyst(const CsJob *d_jobs, int n_jobs, uint32_t *d_bits, int max_plane_words, cudaStream_t st, int64_t *launches);
 void cs_launch_dt(const CsJob *d_jobs, const int32_t *d_ids, int n_jobs, int max_dpitch, const uint32_t *d_bits, float *d_dist,
                   cudaStream_t st, int64_t *launches);
+bool cs_launch_hyst_dt(const CsJob *d_jobs, int n_jobs, uint32_t *d_bits, float *d_dist, int max_plane_words, int max_dpitch, int max_h,
+                       cudaStream_t st, int64_t *launches);
 void cs_launch_roi_lines(const CsJob *d_jobs, int n_jobs, const CsFrame *d_frames, const double *d_lines, double *d_out_lines,
                          int32_t *d_out_counts, int32_t *d_err, double dist_thre, double angle_thre_deg, double len_thre, cudaStream_t st,
                          int64_t *launches);

@@ -465,6 +465,159 @@ __global__ void __launch_bounds__(32) k_chamfer_dt(const CsJob *__restrict__ job
         dt_warp<64>(planeS, bwp, tmp, w, h, dp, dt_smem);
 }
 
+
+/* ------------------------------------------------------------------------------------------
+ * Fused hysteresis + chamfer distance transform, one CTA per ROI (the default path).
+ *
+ * Hysteresis as in k_canny_hyst, with both bit planes in shared memory.  The distance transform then
+ * runs as a skewed WAVEFRONT instead of a row-by-row scan: warp b owns the 32-row band b, lane l owns
+ * row 32b+l and walks it left to right, two columns behind the lane above it, so that the three
+ * upper neighbours of every cell were produced one, two and three steps earlier:
+ *       t(i,j) = min(t(i-1,j-1)+b, t(i-1,j)+a, t(i-1,j+1)+b, t(i,j-1)+a)        (0 on an edge pixel)
+ * The value a lane just produced reaches the lane below with one __shfl_up; the last row of a band
+ * reaches the next band's warp through a tagged word in shared memory (value | tag << 30), which the
+ * consumer lane polls -- no block-wide barrier inside a pass.  Bands therefore pipeline: a ROI of
+ * H x W finishes in about 2H + W steps while every SM keeps thousands of lanes busy.  Same integer
+ * recurrences as the raster scan, evaluated in another order, hence bit-exact.
+ * ------------------------------------------------------------------------------------------ */
+#define WF_BIG (1 << 29)
+#define WF_MAX_WARPS 16
+
+template <bool BWD>
+__device__ __forceinline__ void wf_pass(const uint32_t *S /* smem edge plane, bordered */, int bwp, uint32_t *__restrict__ tmp, int w, int h,
+                                        int dpitch, volatile uint32_t *rowbuf /* nw x rb_pitch */, int rb_pitch, int nw)
+{
+    const unsigned FULL = 0xffffffffu;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int nbands = (h + 31) >> 5;
+    const float scale = 1.f / 65536.f;
+    const float dist_max = (float)(0xffffffffu - (uint32_t)DT_DG) * scale;
+    for (int band = wid; band < nbands; band += nw) {
+        const int rr = band * 32 + lane; /* row in pass order */
+        const bool row_ok = rr < h;
+        const int r = BWD ? (h - 1 - rr) : rr;
+        const uint32_t tag_out = (uint32_t)(((band / nw) & 1) + 1) << 30;
+        const uint32_t tag_in = (band > 0) ? (uint32_t)((((band - 1) / nw) & 1) + 1) << 30 : 0u;
+        volatile uint32_t *rb_out = rowbuf + (size_t)(band % nw) * rb_pitch;
+        volatile uint32_t *rb_in = rowbuf + (size_t)((band + nw - 1) % nw) * rb_pitch;
+        const bool feeds_next = (band + 1 < nbands);
+        uint32_t *trow = tmp + (size_t)(row_ok ? r : 0) * dpitch;
+        const uint32_t *srow = S + (size_t)((row_ok ? r : 0) + 1) * bwp + 1;
+        int a = WF_BIG, b = WF_BIG, left = WF_BIG, last = WF_BIG;
+        uint32_t bits = 0;
+        uint32_t o0 = 0, o1 = 0, o2 = 0, o3 = 0;     /* forward: last four results of this row */
+        uint4 cg = make_uint4(WF_BIG, WF_BIG, WF_BIG, WF_BIG), ng = cg; /* backward: current / next group of forward values */
+        if (BWD && row_ok) {
+            const int g0 = (w - 1) & ~3;
+            cg = *reinterpret_cast<const uint4 *>(trow + g0);
+            if (g0 >= 4) ng = *reinterpret_cast<const uint4 *>(trow + g0 - 4);
+        }
+        const int n_steps = w + 64;
+        for (int s = 0; s < n_steps; s++) {
+            const int j = s - 2 * lane - 1; /* column in pass order; -1 = priming step */
+            int c = __shfl_up_sync(FULL, last, 1);
+            if (lane == 0) {
+                c = WF_BIG;
+                if (band > 0 && j + 1 >= 0 && j + 1 < w) {
+                    uint32_t v;
+                    do {
+                        v = rb_in[j + 1];
+                    } while ((v & 0xc0000000u) != tag_in);
+                    c = (int)(v & 0x3fffffffu);
+                }
+            }
+            if (j + 1 >= w) c = WF_BIG;
+            if (row_ok && j >= 0 && j < w) {
+                const int col = BWD ? (w - 1 - j) : j;
+                int t = min(min(a + DT_DG, b + DT_HV), min(c + DT_DG, left + DT_HV));
+                if (!BWD) {
+                    if ((col & 31) == 0) bits = srow[col >> 5];
+                    if ((bits >> (col & 31)) & 1u) t = 0;
+                } else {
+                    const int q = col & 3;
+                    const uint32_t cur = (q == 3) ? cg.w : (q == 2) ? cg.z : (q == 1) ? cg.y : cg.x;
+                    t = min(t, (int)cur);
+                }
+                if (t >= WF_BIG) t = WF_BIG;
+                left = t;
+                last = t;
+                if (lane == 31 && feeds_next) rb_out[j] = (uint32_t)t | tag_out;
+                if (!BWD) {
+                    o0 = o1;
+                    o1 = o2;
+                    o2 = o3;
+                    o3 = (uint32_t)t;
+                    if ((col & 3) == 3)
+                        *reinterpret_cast<uint4 *>(trow + col - 3) = make_uint4(o0, o1, o2, o3);
+                    else if (col == w - 1) { /* ragged tail of the row */
+                        trow[col] = o3;
+                        if ((col & 3) >= 1) trow[col - 1] = o2;
+                        if ((col & 3) >= 2) trow[col - 2] = o1;
+                    }
+                } else {
+                    const float f = (t >= WF_BIG) ? dist_max : (float)(uint32_t)t * scale;
+                    const uint32_t fb = __float_as_uint(f);
+                    /* results leave in place of the forward values, a group of four at a time */
+                    const int q = col & 3;
+                    if (q == 3) o3 = fb;
+                    else if (q == 2) o2 = fb;
+                    else if (q == 1) o1 = fb;
+                    else o0 = fb;
+                    if (q == 0) {
+                        *reinterpret_cast<uint4 *>(trow + col) = make_uint4(o0, o1, o2, o3);
+                        cg = ng;
+                        if (col >= 8) ng = *reinterpret_cast<const uint4 *>(trow + col - 8);
+                    }
+                }
+            }
+            a = (j + 1 == 0) ? WF_BIG : b;
+            b = c;
+        }
+    }
+}
+
+extern __shared__ uint32_t hd_smem[];
+
+__global__ void __launch_bounds__(32 * WF_MAX_WARPS) k_hyst_dt(const CsJob *__restrict__ jobs, uint32_t *__restrict__ bits_arena,
+                                                               float *__restrict__ dist_arena, int plane_cap_words, int rb_pitch)
+{
+    const CsJob &jb = jobs[blockIdx.x];
+    const int h = jb.roi_h, w = jb.roi_w, bw = jb.bw, bwp = bw + 2;
+    const int plane = (h + 2) * bwp;
+    uint32_t *gS = bits_arena + jb.bit_off;
+    uint32_t *S = hd_smem;
+    uint32_t *W = S + plane;
+    uint32_t *rowbuf = hd_smem + 2 * plane_cap_words;
+    const int tid = threadIdx.x, nthreads = blockDim.x, nw = nthreads >> 5;
+    for (int i = tid; i < 2 * plane; i += nthreads) S[i] = gS[i];
+    for (int i = tid; i < nw * rb_pitch; i += nthreads) rowbuf[i] = 0;
+    __syncthreads();
+    /* hysteresis */
+    {
+        const int n_runs = max(nthreads / bw, 1);
+        const int rows_per = (h + n_runs - 1) / n_runs;
+        const int c = 1 + tid % bw, run = tid / bw;
+        const int r0 = 1 + run * rows_per, r1 = min(r0 + rows_per, h + 1);
+        const bool active = (run < n_runs) && (tid < n_runs * bw);
+        while (true) {
+            bool changed = false;
+            if (active) {
+                for (int r = r0; r < r1; r++) changed |= hyst_word<uint32_t *>(S, W, bwp, r, c);
+                for (int r = r1 - 2; r >= r0; r--) changed |= hyst_word<uint32_t *>(S, W, bwp, r, c);
+            }
+            if (!__syncthreads_or(changed ? 1 : 0)) break;
+        }
+        for (int i = tid; i < plane; i += nthreads) gS[i] = S[i]; /* final edge map (inspection / reuse) */
+    }
+    uint32_t *tmp = reinterpret_cast<uint32_t *>(dist_arena + jb.px_off);
+    wf_pass<false>(S, bwp, tmp, w, h, jb.dpitch, rowbuf, rb_pitch, nw);
+    __syncthreads(); /* forward values written by other warps' lanes are read back below */
+    for (int i = tid; i < nw * rb_pitch; i += nthreads) rowbuf[i] = 0;
+    __threadfence_block();
+    __syncthreads();
+    wf_pass<true>(S, bwp, tmp, w, h, jb.dpitch, rowbuf, rb_pitch, nw);
+}
+
 /* ------------------------------------------------------------------------------------------ launchers */
 const int cs_dt_class_ppl[CS_DT_CLASSES] = {4, 8, 12, 16, 24, 40, 64};
 
@@ -537,4 +690,26 @@ void cs_launch_dt(const CsJob *d_jobs, const int32_t *d_ids, int n_jobs, int max
     }
     k_chamfer_dt<<<n_jobs, 32, bytes, st>>>(d_jobs, d_ids, d_bits, d_dist);
     (*launches)++;
+}
+
+/* fused hysteresis + wavefront DT; returns false if the batch's largest ROI does not fit shared memory
+ * (the caller then uses cs_launch_hyst + cs_launch_dt) */
+bool cs_launch_hyst_dt(const CsJob *d_jobs, int n_jobs, uint32_t *d_bits, float *d_dist, int max_plane_words, int max_dpitch, int max_h,
+                       cudaStream_t st, int64_t *launches)
+{
+    if (n_jobs <= 0) return true;
+    int nw = (max_h + 31) / 32;
+    if (nw > WF_MAX_WARPS) nw = WF_MAX_WARPS;
+    if (nw < 2) nw = 2;
+    const int rb_pitch = (max_dpitch + 3) & ~3;
+    const size_t bytes = ((size_t)2 * max_plane_words + (size_t)nw * rb_pitch) * 4;
+    if (bytes > 200 * 1024) return false;
+    static size_t cur_attr = 0;
+    if (bytes > cur_attr) {
+        cudaFuncSetAttribute(k_hyst_dt, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+        cur_attr = bytes;
+    }
+    k_hyst_dt<<<n_jobs, 32 * nw, bytes, st>>>(d_jobs, d_bits, d_dist, max_plane_words, rb_pitch);
+    (*launches)++;
+    return true;
 }

@@ -78,10 +78,14 @@ def test_fixture_a_modes(cs, oracle, fixture_a, mode):
     ctx.close()
 
 
-def test_fixture_a_stages(cs, oracle, fixture_a):
-    """Stage by stage: gray/Canny/DT bit-exact, merged lines bit-exact, valid set + per-proposal errors."""
+@pytest.mark.parametrize("split_kernels", [0, 2])
+def test_fixture_a_stages(cs, oracle, fixture_a, split_kernels):
+    """Stage by stage: gray/Canny/DT bit-exact, merged lines bit-exact, valid set + per-proposal errors.
+    split_kernels=2 forces the fallback path (separate hysteresis kernel + row-scan DT) used for ROIs too
+    large for the fused shared-memory kernel."""
     fa = fixture_a
     ctx = cs.Context(0, 1280, 960, 1, 8, 4096)
+    ctx.L.cs_set_profiling(ctx.h, split_kernels)
     _run_frame(cs, ctx, fa["img"], fa["K"], fa["T"], fa["boxes"], fa["lines"])
     ref = oracle.detect_cuboid(fa["img"], fa["K"], fa["T"], fa["boxes"], fa["lines"], trace_object=0)["trace"]
     roi = ctx.debug_roi(0)
@@ -106,6 +110,8 @@ def test_synthetic_batch_matches_oracle(cs, oracle, seed, w, h, kind, nb):
     imgs, Ts, boxes, lines, K = S.make_batch(seed, F, w, h, nb, kind=kind, poisson=(kind == "indoor"))
     ctx = cs.Context(0, w, h, F, 16, 4096)
     ctx.set_calibration(K)
+    if seed == 12:
+        ctx.L.cs_set_profiling(ctx.h, 2)  # one case through the split-kernel fallback
     p = cs.default_params(max_cuboid_num=3)
     out, counts = ctx.detect_batch_host(imgs, Ts, boxes, lines, p)
     st = ctx.stats()
