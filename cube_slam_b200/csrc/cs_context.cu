@@ -55,13 +55,15 @@ struct cs_ctx {
     std::vector<CsJob> jobs;
     std::vector<CsObj> objs;
     std::vector<int2> sweep_blocks;
-    std::vector<int32_t> dt_ids;
+    std::vector<int32_t> dt_ids, tile_job;
     int64_t total_px = 0, total_cand = 0, total_bits = 0;
     int n_tiles = 0, max_plane_words = 0, max_dpitch = 0, max_roi_h = 0;
-    int force_split_dt = 0; /* debug: use the two-kernel hysteresis + scan DT path */
+    int use_fused_dt = 0; /* experimental: fused hysteresis + wavefront DT kernel */
+    cudaStream_t stream2 = nullptr; /* side stream: the line kernel runs beside the image chain */
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
 
     /* device buffers (grow only) */
-    DevBuf d_img, d_gray, d_lines, d_frames, d_poses, d_yaws, d_jobs, d_objs, d_blocks, d_dtids;
+    DevBuf d_img, d_gray, d_lines, d_frames, d_poses, d_yaws, d_jobs, d_objs, d_blocks, d_dtids, d_tilejob;
     DevBuf d_bits, d_dist, d_mlines, d_lcounts, d_err;
     DevBuf d_cvalid, d_cdist, d_cangle, d_vlist, d_key, d_idx, d_flag, d_keep, d_norm, d_score, d_jcounts;
     DevBuf d_out, d_outcnt, d_gather;
@@ -277,6 +279,12 @@ int build_tables(cs_ctx *c)
         }
     }
     /* distance-transform order: jobs grouped by width class so neighbouring CTAs share an instantiation */
+    c->tile_job.clear();
+    c->tile_job.reserve(c->n_tiles);
+    for (size_t j = 0; j < c->jobs.size(); j++) {
+        const int nt = c->jobs[j].tiles_x * ((c->jobs[j].roi_h + 31) / 32);
+        c->tile_job.insert(c->tile_job.end(), nt, (int32_t)j);
+    }
     c->dt_ids.clear();
     for (int cls = 0; cls < CS_DT_CLASSES; cls++)
         for (size_t j = 0; j < c->jobs.size(); j++)
@@ -310,14 +318,11 @@ int alloc_work(cs_cuboid_params &, cs_ctx *c)
     return CS_OK;
 }
 
-int run_batch(cs_ctx *c, bool sync)
+/* Host tables (sample grids, pose hypotheses, ROI job descriptors) depend only on the batch's poses, boxes and
+ * parameters: they are built and uploaded once per batch, at upload time, with the images. */
+int prepare_tables(cs_ctx *c)
 {
-    if (!c->prepared) return fail(c, CS_ERR_NOT_PREPARED, "no batch uploaded");
     int rc;
-    cudaStream_t st = c->stream;
-    c->launches = 0;
-    if (c->profiling) cudaEventRecord(c->ev_total[0], st);
-    /* host tables: sample grids + job descriptors, then their (small) upload */
     if ((rc = build_tables(c))) return rc;
     if ((rc = alloc_work(c->prm, c))) return rc;
     if ((rc = upload(c, c->d_frames, c->frames))) return rc;
@@ -327,6 +332,17 @@ int run_batch(cs_ctx *c, bool sync)
     if ((rc = upload(c, c->d_objs, c->objs))) return rc;
     if ((rc = upload(c, c->d_blocks, c->sweep_blocks))) return rc;
     if ((rc = upload(c, c->d_dtids, c->dt_ids))) return rc;
+    if ((rc = upload(c, c->d_tilejob, c->tile_job))) return rc;
+    return CS_OK;
+}
+
+int run_batch(cs_ctx *c, bool sync)
+{
+    if (!c->prepared) return fail(c, CS_ERR_NOT_PREPARED, "no batch uploaded");
+    int rc;
+    cudaStream_t st = c->stream;
+    c->launches = 0;
+    if (c->profiling) cudaEventRecord(c->ev_total[0], st);
     CS_CUDA(c, cudaMemsetAsync(c->d_err.p, 0, 16, st));
 
     const int n_jobs = (int)c->jobs.size(), n_objs = (int)c->objs.size();
@@ -334,6 +350,13 @@ int run_batch(cs_ctx *c, bool sync)
     auto mark = [&](int s) {
         if (c->profiling) cudaEventRecord(c->ev[s], st);
     };
+    /* fork: the per-ROI line selection / merging only needs the uploaded lines and job table */
+    cudaEventRecord(c->ev_fork, st);
+    cudaStreamWaitEvent(c->stream2, c->ev_fork, 0);
+    cs_launch_roi_lines((const CsJob *)c->d_jobs.p, n_jobs, (const CsFrame *)c->d_frames.p, (const double *)c->d_lines.p, (double *)c->d_mlines.p,
+                        (int32_t *)c->d_lcounts.p, (int32_t *)c->d_err.p, c->prm.pre_merge_dist_thre, c->prm.pre_merge_angle_thre,
+                        c->prm.edge_length_threshold, c->stream2, &c->launches);
+    cudaEventRecord(c->ev_join, c->stream2);
     mark(ST_GRAY);
     if (c->channels == 3 || c->stride != c->w)
         cs_launch_gray((const uint8_t *)c->d_img.p, (uint8_t *)c->d_gray.p, c->n_frames, c->w, c->h, c->stride, c->channels, st, &c->launches);
@@ -341,11 +364,11 @@ int run_batch(cs_ctx *c, bool sync)
         gray = (const uint8_t *)c->d_img.p;
     mark(ST_CANNY);
     int low = (int)std::floor(std::min(c->prm.canny_low, c->prm.canny_high)), high = (int)std::floor(std::max(c->prm.canny_low, c->prm.canny_high));
-    cs_launch_canny(gray, c->w, c->h, (const CsJob *)c->d_jobs.p, n_jobs, c->n_tiles, (uint32_t *)c->d_bits.p, (size_t)c->total_bits * 4, low, high,
+    cs_launch_canny(gray, c->w, c->h, (const CsJob *)c->d_jobs.p, n_jobs, (const int32_t *)c->d_tilejob.p, c->n_tiles, (uint32_t *)c->d_bits.p, (size_t)c->total_bits * 4, low, high,
                     st, &c->launches);
     mark(ST_HYST);
     bool fused = false;
-    if (!c->force_split_dt)
+    if (c->use_fused_dt)
         fused = cs_launch_hyst_dt((const CsJob *)c->d_jobs.p, n_jobs, (uint32_t *)c->d_bits.p, (float *)c->d_dist.p, c->max_plane_words, c->max_dpitch,
                                   c->max_roi_h, st, &c->launches);
     if (!fused) cs_launch_hyst((const CsJob *)c->d_jobs.p, n_jobs, (uint32_t *)c->d_bits.p, c->max_plane_words, st, &c->launches);
@@ -354,9 +377,7 @@ int run_batch(cs_ctx *c, bool sync)
         cs_launch_dt((const CsJob *)c->d_jobs.p, (const int32_t *)c->d_dtids.p, n_jobs, c->max_dpitch, (const uint32_t *)c->d_bits.p, (float *)c->d_dist.p,
                      st, &c->launches);
     mark(ST_LINES);
-    cs_launch_roi_lines((const CsJob *)c->d_jobs.p, n_jobs, (const CsFrame *)c->d_frames.p, (const double *)c->d_lines.p, (double *)c->d_mlines.p,
-                        (int32_t *)c->d_lcounts.p, (int32_t *)c->d_err.p, c->prm.pre_merge_dist_thre, c->prm.pre_merge_angle_thre,
-                        c->prm.edge_length_threshold, st, &c->launches);
+    cudaStreamWaitEvent(st, c->ev_join, 0); /* join */
     mark(ST_SWEEP);
     cs_launch_sweep((const CsJob *)c->d_jobs.p, (const CsFrame *)c->d_frames.p, (const CsPose *)c->d_poses.p, (const double *)c->d_yaws.p,
                     (const int2 *)c->d_blocks.p, (int)c->sweep_blocks.size(), (const double *)c->d_mlines.p, (const int32_t *)c->d_lcounts.p,
@@ -423,7 +444,7 @@ int store_batch(cs_ctx *c, const uint8_t *imgs, int n_frames, int width, int hei
     CS_CUDA(c, cudaMemcpyAsync(c->d_img.p, imgs, img_bytes, cudaMemcpyHostToDevice, c->stream));
     if (nl) CS_CUDA(c, cudaMemcpyAsync(c->d_lines.p, lines, (size_t)nl * 4 * sizeof(double), cudaMemcpyHostToDevice, c->stream));
     c->prepared = true;
-    return CS_OK;
+    return prepare_tables(c);
 }
 
 int fetch(cs_ctx *c, cs_cuboid_rec *out, int32_t *out_counts)
@@ -511,6 +532,9 @@ cs_ctx *cs_create(int device, int max_width, int max_height, int max_frames, int
         delete c;
         return nullptr;
     }
+    cudaStreamCreateWithFlags(&c->stream2, cudaStreamNonBlocking);
+    cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming);
     for (int s = 0; s <= ST_COUNT; s++) cudaEventCreate(&c->ev[s]);
     cudaEventCreate(&c->ev_total[0]);
     cudaEventCreate(&c->ev_total[1]);
@@ -524,7 +548,7 @@ void cs_destroy(cs_ctx *c)
     cudaStreamSynchronize(c->stream);
     cs_nccl_teardown(c);
     DevBuf *all[] = {&c->d_img,   &c->d_gray,  &c->d_lines,  &c->d_frames, &c->d_poses,   &c->d_yaws, &c->d_jobs, &c->d_objs,
-                     &c->d_blocks, &c->d_dtids, &c->d_bits, &c->d_dist, &c->d_mlines, &c->d_lcounts, &c->d_err,
+                     &c->d_blocks, &c->d_dtids, &c->d_tilejob, &c->d_bits, &c->d_dist, &c->d_mlines, &c->d_lcounts, &c->d_err,
                      &c->d_cvalid, &c->d_cdist, &c->d_cangle, &c->d_vlist,  &c->d_key,     &c->d_idx,  &c->d_flag, &c->d_keep,  &c->d_norm,
                      &c->d_score,  &c->d_jcounts, &c->d_out,  &c->d_outcnt, &c->d_gather};
     for (DevBuf *b : all)
@@ -534,6 +558,9 @@ void cs_destroy(cs_ctx *c)
         if (c->ev[s]) cudaEventDestroy(c->ev[s]);
     cudaEventDestroy(c->ev_total[0]);
     cudaEventDestroy(c->ev_total[1]);
+    cudaEventDestroy(c->ev_fork);
+    cudaEventDestroy(c->ev_join);
+    cudaStreamDestroy(c->stream2);
     cudaStreamDestroy(c->stream);
     delete c;
 }
@@ -655,7 +682,7 @@ int cs_set_profiling(cs_ctx *c, int enable)
 {
     if (!c) return CS_ERR_INVALID_ARG;
     c->profiling = (enable & 1) != 0;
-    c->force_split_dt = (enable & 2) != 0; /* bit 1: take the split hysteresis / scan-DT kernels (fallback path testing) */
+    c->use_fused_dt = (enable & 4) != 0; /* bit 2: experimental fused hysteresis + wavefront-DT kernel */
     return CS_OK;
 }
 

@@ -74,29 +74,13 @@ __global__ void __launch_bounds__(256) k_bgr2gray_generic(const uint8_t *__restr
 #define CT 32 /* tile edge */
 
 __global__ void __launch_bounds__(256) k_canny_nms(const uint8_t *__restrict__ gray, int img_w, int img_h, const CsJob *__restrict__ jobs,
-                                                   int n_jobs, uint32_t *__restrict__ bits_arena, int low, int high)
+                                                   const int32_t *__restrict__ tile_job, uint32_t *__restrict__ bits_arena, int low, int high)
 {
     __shared__ uint8_t s_g[CT + 4][CT + 4 + 4];
     __shared__ int16_t s_dx[CT + 2][CT + 2 + 2];
     __shared__ int16_t s_dy[CT + 2][CT + 2 + 2];
     __shared__ uint16_t s_m[CT + 2][CT + 2 + 2];
-    __shared__ int s_job;
-
-    /* tile -> job: binary search in the per-job tile prefix */
-    if (threadIdx.x == 0 && threadIdx.y == 0) {
-        int lo = 0, hi = n_jobs - 1;
-        const int t = blockIdx.x;
-        while (lo < hi) {
-            const int mid = (lo + hi + 1) >> 1;
-            if (jobs[mid].tile_off <= t)
-                lo = mid;
-            else
-                hi = mid - 1;
-        }
-        s_job = lo;
-    }
-    __syncthreads();
-    const CsJob &jb = jobs[s_job];
+    const CsJob &jb = jobs[tile_job[blockIdx.x]];
     const int w = jb.roi_w, h = jb.roi_h;
     const int tl = blockIdx.x - jb.tile_off;
     const int tile_y = tl / jb.tiles_x, tile_x = tl - tile_y * jb.tiles_x;
@@ -104,17 +88,18 @@ __global__ void __launch_bounds__(256) k_canny_nms(const uint8_t *__restrict__ g
     const uint8_t *src = gray + ((size_t)jb.frame * img_h + jb.roi_t) * img_w + jb.roi_l;
     const int tx = threadIdx.x, ty = threadIdx.y;
 
-    for (int ly = ty; ly < CT + 4; ly += 8) {
+    const int tid = ty * 32 + tx;
+    for (int i = tid; i < (CT + 4) * (CT + 4); i += 256) {
+        const int ly = i / (CT + 4), lx = i - ly * (CT + 4);
         const int gy = min(max(y0 + ly - 2, 0), h - 1);
-        for (int lx = tx; lx < CT + 4; lx += 32) {
-            const int gx = min(max(x0 + lx - 2, 0), w - 1);
-            s_g[ly][lx] = src[(size_t)gy * img_w + gx];
-        }
+        const int gx = min(max(x0 + lx - 2, 0), w - 1);
+        s_g[ly][lx] = src[gy * img_w + gx];
     }
     __syncthreads();
-    for (int ly = ty; ly < CT + 2; ly += 8) {
-        const int gy = y0 + ly - 1;
-        for (int lx = tx; lx < CT + 2; lx += 32) {
+    for (int i = tid; i < (CT + 2) * (CT + 2); i += 256) {
+        {
+            const int ly = i / (CT + 2), lx = i - ly * (CT + 2);
+            const int gy = y0 + ly - 1;
             const int gx = x0 + lx - 1; /* ROI coordinates of this magnitude */
             int dx = 0, dy = 0, m = 0;
             if (gy >= 0 && gy < h && gx >= 0 && gx < w) {
@@ -266,19 +251,28 @@ __global__ void __launch_bounds__(HY_THREADS) k_canny_hyst(const CsJob *__restri
 #define DT_BIG (1 << 30)
 #define DT_PF 4   /* prefetch depth (rows) */
 
-/* the PPL edge bits of columns [c0, c0+PPL) of one bit-plane row, as 64-bit mask */
+/* raw bit-plane words covering columns [c0, c0+PPL) of one row (prefetched; shifted only when consumed so the
+ * loads stay in flight across DT_PF rows) */
+struct DtWords {
+    uint32_t a, b, c;
+};
 template <int PPL>
-__device__ __forceinline__ uint64_t dt_row_bits(const uint32_t *__restrict__ row_words /* word 0 = column 0 */, int c0, int bw)
+__device__ __forceinline__ DtWords dt_row_words(const uint32_t *__restrict__ row_words /* word 0 = column 0 */, int c0, int bw)
 {
-    const int w0 = c0 >> 5, sh = c0 & 31;
-    /* words beyond the row are the zero border / next row start: mask by bw */
-    const uint32_t a = (w0 < bw) ? __ldg(row_words + w0) : 0u;
-    const uint32_t b = (w0 + 1 < bw) ? __ldg(row_words + w0 + 1) : 0u;
-    uint64_t bits = __funnelshift_r(a, b, sh);
-    if (PPL > 32) {
-        const uint32_t c = (w0 + 2 < bw) ? __ldg(row_words + w0 + 2) : 0u;
-        bits |= (uint64_t)__funnelshift_r(b, c, sh) << 32;
-    }
+    const int w0 = c0 >> 5;
+    DtWords r;
+    r.a = (w0 < bw) ? __ldg(row_words + w0) : 0u;
+    r.b = (w0 + 1 < bw) ? __ldg(row_words + w0 + 1) : 0u;
+    r.c = 0u;
+    if (PPL > 32) r.c = (w0 + 2 < bw) ? __ldg(row_words + w0 + 2) : 0u;
+    return r;
+}
+template <int PPL>
+__device__ __forceinline__ uint64_t dt_bits_of(const DtWords &r, int c0)
+{
+    const int sh = c0 & 31;
+    uint64_t bits = __funnelshift_r(r.a, r.b, sh);
+    if (PPL > 32) bits |= (uint64_t)__funnelshift_r(r.b, r.c, sh) << 32;
     return bits;
 }
 
@@ -307,17 +301,17 @@ __device__ __forceinline__ void dt_warp(const uint32_t *__restrict__ planeS, int
     for (int k = 0; k < PPL; k++) up[k] = DT_BIG;
 
     /* ---- forward pass ---- */
-    uint64_t pf[DT_PF];
+    DtWords pf[DT_PF];
 #pragma unroll
-    for (int d = 0; d < DT_PF; d++) pf[d] = (d < h) ? dt_row_bits<PPL>(planeS + (size_t)(d + 1) * bwp + 1, c0, bw) : 0ull;
+    for (int d = 0; d < DT_PF; d++) pf[d] = dt_row_words<PPL>(planeS + (size_t)(min(d, h - 1) + 1) * bwp + 1, c0, bw);
     for (int i0 = 0; i0 < h; i0 += DT_PF) {
 #pragma unroll
         for (int d = 0; d < DT_PF; d++) {
             const int i = i0 + d;
             if (i < h) {
-                const uint64_t bits = pf[d];
-                const int nxt = i + DT_PF;
-                pf[d] = (nxt < h) ? dt_row_bits<PPL>(planeS + (size_t)(nxt + 1) * bwp + 1, c0, bw) : 0ull;
+                const uint64_t bits = dt_bits_of<PPL>(pf[d], c0);
+                const int nxt = min(i + DT_PF, h - 1);
+                pf[d] = dt_row_words<PPL>(planeS + (size_t)(nxt + 1) * bwp + 1, c0, bw);
                 int upL = __shfl_up_sync(FULL, up[PPL - 1], 1);
                 int upR = __shfl_down_sync(FULL, up[0], 1);
                 if (lane == 0) upL = DT_BIG;
@@ -482,6 +476,7 @@ __global__ void __launch_bounds__(32) k_chamfer_dt(const CsJob *__restrict__ job
  * ------------------------------------------------------------------------------------------ */
 #define WF_BIG (1 << 29)
 #define WF_MAX_WARPS 16
+#define WF_SLACK 24
 
 template <bool BWD>
 __device__ __forceinline__ void wf_pass(const uint32_t *S /* smem edge plane, bordered */, int bwp, uint32_t *__restrict__ tmp, int w, int h,
@@ -506,24 +501,40 @@ __device__ __forceinline__ void wf_pass(const uint32_t *S /* smem edge plane, bo
         int a = WF_BIG, b = WF_BIG, left = WF_BIG, last = WF_BIG;
         uint32_t bits = 0;
         uint32_t o0 = 0, o1 = 0, o2 = 0, o3 = 0;     /* forward: last four results of this row */
-        uint4 cg = make_uint4(WF_BIG, WF_BIG, WF_BIG, WF_BIG), ng = cg; /* backward: current / next group of forward values */
+        uint4 cg = make_uint4(WF_BIG, WF_BIG, WF_BIG, WF_BIG), ng = cg, ng2 = cg, ng3 = cg; /* backward: forward values, 3 groups ahead */
         if (BWD && row_ok) {
             const int g0 = (w - 1) & ~3;
             cg = *reinterpret_cast<const uint4 *>(trow + g0);
             if (g0 >= 4) ng = *reinterpret_cast<const uint4 *>(trow + g0 - 4);
+            if (g0 >= 8) ng2 = *reinterpret_cast<const uint4 *>(trow + g0 - 8);
+            if (g0 >= 12) ng3 = *reinterpret_cast<const uint4 *>(trow + g0 - 12);
+        }
+        /* start a band only once the band above is WF_SLACK columns ahead: afterwards both advance at the
+         * same rate and the per-step poll below finds its word ready (polling warps would otherwise eat
+         * the issue slots of the producers) */
+        if (band > 0 && lane == 0) {
+            const int need = min(WF_SLACK, w - 1);
+            while ((rb_in[need] & 0xc0000000u) != tag_in) __nanosleep(200);
+        }
+        __syncwarp();
+        int c_pref = WF_BIG; /* lane 0: upper-row value for the NEXT step, fetched one step early */
+        if (band > 0 && lane == 0) {
+            const uint32_t v = rb_in[0];
+            c_pref = (int)(v & 0x3fffffffu); /* column 0 is ready: need >= 0 */
         }
         const int n_steps = w + 64;
         for (int s = 0; s < n_steps; s++) {
             const int j = s - 2 * lane - 1; /* column in pass order; -1 = priming step */
             int c = __shfl_up_sync(FULL, last, 1);
             if (lane == 0) {
-                c = WF_BIG;
-                if (band > 0 && j + 1 >= 0 && j + 1 < w) {
-                    uint32_t v;
-                    do {
-                        v = rb_in[j + 1];
-                    } while ((v & 0xc0000000u) != tag_in);
-                    c = (int)(v & 0x3fffffffu);
+                c = (band > 0) ? c_pref : WF_BIG;
+                if (band > 0 && j + 2 < w) { /* prefetch column j+2 for the next step */
+                    uint32_t v = rb_in[j + 2];
+                    while ((v & 0xc0000000u) != tag_in) {
+                        __nanosleep(100);
+                        v = rb_in[j + 2];
+                    }
+                    c_pref = (int)(v & 0x3fffffffu);
                 }
             }
             if (j + 1 >= w) c = WF_BIG;
@@ -566,7 +577,9 @@ __device__ __forceinline__ void wf_pass(const uint32_t *S /* smem edge plane, bo
                     if (q == 0) {
                         *reinterpret_cast<uint4 *>(trow + col) = make_uint4(o0, o1, o2, o3);
                         cg = ng;
-                        if (col >= 8) ng = *reinterpret_cast<const uint4 *>(trow + col - 8);
+                        ng = ng2;
+                        ng2 = ng3;
+                        if (col >= 16) ng3 = *reinterpret_cast<const uint4 *>(trow + col - 16);
                     }
                 }
             }
@@ -650,13 +663,13 @@ void cs_launch_gray(const uint8_t *d_img, uint8_t *d_gray, int n_frames, int w, 
     }
 }
 
-void cs_launch_canny(const uint8_t *d_gray, int img_w, int img_h, const CsJob *d_jobs, int n_jobs, int n_tiles, uint32_t *d_bits,
+void cs_launch_canny(const uint8_t *d_gray, int img_w, int img_h, const CsJob *d_jobs, int n_jobs, const int32_t *d_tile_job, int n_tiles, uint32_t *d_bits,
                      size_t bits_bytes, int low, int high, cudaStream_t st, int64_t *launches)
 {
     if (n_jobs <= 0) return;
     cudaMemsetAsync(d_bits, 0, bits_bytes, st); /* zero borders (and stale bits) of every plane */
     if (n_tiles > 0) {
-        k_canny_nms<<<n_tiles, dim3(32, 8), 0, st>>>(d_gray, img_w, img_h, d_jobs, n_jobs, d_bits, low, high);
+        k_canny_nms<<<n_tiles, dim3(32, 8), 0, st>>>(d_gray, img_w, img_h, d_jobs, d_tile_job, d_bits, low, high);
         (*launches)++;
     }
 }

@@ -78,11 +78,11 @@ def test_fixture_a_modes(cs, oracle, fixture_a, mode):
     ctx.close()
 
 
-@pytest.mark.parametrize("split_kernels", [0, 2])
+@pytest.mark.parametrize("split_kernels", [0, 4])
 def test_fixture_a_stages(cs, oracle, fixture_a, split_kernels):
     """Stage by stage: gray/Canny/DT bit-exact, merged lines bit-exact, valid set + per-proposal errors.
-    split_kernels=2 forces the fallback path (separate hysteresis kernel + row-scan DT) used for ROIs too
-    large for the fused shared-memory kernel."""
+    split_kernels=4 selects the experimental fused hysteresis + wavefront-DT kernel instead of the default
+    separate hysteresis kernel + row-scan DT."""
     fa = fixture_a
     ctx = cs.Context(0, 1280, 960, 1, 8, 4096)
     ctx.L.cs_set_profiling(ctx.h, split_kernels)
@@ -111,7 +111,7 @@ def test_synthetic_batch_matches_oracle(cs, oracle, seed, w, h, kind, nb):
     ctx = cs.Context(0, w, h, F, 16, 4096)
     ctx.set_calibration(K)
     if seed == 12:
-        ctx.L.cs_set_profiling(ctx.h, 2)  # one case through the split-kernel fallback
+        ctx.L.cs_set_profiling(ctx.h, 4)  # one case through the fused wavefront kernel
     p = cs.default_params(max_cuboid_num=3)
     out, counts = ctx.detect_batch_host(imgs, Ts, boxes, lines, p)
     st = ctx.stats()
