@@ -6,8 +6,7 @@
  *   k_canny_hyst    cv::Canny: hysteresis (order independent)    box_proposal_detail.cpp:197
  *   k_chamfer_dt    cv::distanceTransform(DIST_L2, 3)            box_proposal_detail.cpp:199
  *
- * All stages are integer / fixed-point and therefore bit-exact against the oracle restatements
- * (oracle/cuboid_oracle.cpp: orc_bgr2gray, orc_canny, orc_chamfer_dt).
+ * All stages are integer / fixed-point and therefore reproduce OpenCV's results bit for bit (checked in tests/).
  *
  * Edge maps travel as BIT PLANES (1 bit per pixel): plane S = "edge" (strong, or weak reached by the
  * hysteresis), plane W = weak candidates.  A ROI of h rows x w columns is stored with a one-word / one-row
