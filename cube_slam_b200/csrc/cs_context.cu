@@ -80,6 +80,9 @@ struct cs_ctx {
     int64_t launches = 0;
     cs_batch_stats stats;
 
+    void *lsd_state = nullptr; /* line-detector workspace (cs_lsd.cu) */
+    int64_t line_launches = 0;
+
     /* NCCL (loaded at run time) */
     void *nccl_lib = nullptr;
     void *nccl_comm = nullptr;
@@ -87,6 +90,21 @@ struct cs_ctx {
 };
 
 #include "cs_nccl.h"
+
+cudaStream_t cs_ctx_stream(cs_ctx *c) { return c->stream; }
+int cs_ctx_device(cs_ctx *c) { return c->device; }
+void **cs_ctx_lsd_slot(cs_ctx *c) { return &c->lsd_state; }
+void cs_ctx_count_launches(cs_ctx *c, int64_t n) { c->line_launches += n; }
+int cs_ctx_fail(cs_ctx *c, int code, const char *fmt, ...)
+{
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    if (c) c->err = buf;
+    return code;
+}
 
 namespace {
 
@@ -547,6 +565,7 @@ void cs_destroy(cs_ctx *c)
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
     cs_nccl_teardown(c);
+    if (c->lsd_state) cs_lsd_destroy(c->lsd_state);
     DevBuf *all[] = {&c->d_img,   &c->d_gray,  &c->d_lines,  &c->d_frames, &c->d_poses,   &c->d_yaws, &c->d_jobs, &c->d_objs,
                      &c->d_blocks, &c->d_dtids, &c->d_tilejob, &c->d_bits, &c->d_dist, &c->d_mlines, &c->d_lcounts, &c->d_err,
                      &c->d_cvalid, &c->d_cdist, &c->d_cangle, &c->d_vlist,  &c->d_key,     &c->d_idx,  &c->d_flag, &c->d_keep,  &c->d_norm,

@@ -62,4 +62,16 @@ struct CsObj {
     int32_t left, top, width_raw, height_raw;
 };
 
+
+/* narrow view of the context for the other translation units (the struct itself lives in cs_context.cu) */
+#ifdef __CUDACC__
+#include <cuda_runtime.h>
+cudaStream_t cs_ctx_stream(cs_ctx *c);
+#endif
+int cs_ctx_device(cs_ctx *c);
+int cs_ctx_fail(cs_ctx *c, int code, const char *fmt, ...);
+void **cs_ctx_lsd_slot(cs_ctx *c);          /* owned by cs_lsd.cu */
+void cs_lsd_destroy(void *state);           /* called from cs_destroy */
+void cs_ctx_count_launches(cs_ctx *c, int64_t n);
+
 #endif

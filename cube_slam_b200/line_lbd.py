@@ -1,0 +1,61 @@
+"""Host-side mirror of `class line_lbd_detect` (line_lbd/include/line_lbd/line_lbd_allclass.h:22-70), detection half.
+
+detect_filter_lines(img) -> n x 4 float32 [x1 y1 x2 y2]: what the reference writes into its `cv::Mat& linesmat_out`
+(line_lbd/class/line_lbd_allclass.cpp:216-221).  Descriptor / matcher methods are out of scope."""
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+from .detect_3d_cuboid import Context, CubeSlamError
+
+
+class line_lbd_detect(object):
+    def __init__(self, numoctaves=1, octaveratio=1.0, device=0, max_width=2048, max_height=2048, context=None):
+        self.numoctaves_ = int(numoctaves)
+        self.octaveratio_ = float(octaveratio)
+        self.use_LSD = False            # line_lbd_allclass.cpp:121
+        self.line_length_thres = 50.0   # :122
+        self._ctx = context if context is not None else Context(device, max_width, max_height, 1, 1, 1)
+
+    def params(self):
+        p = _lib.LineParams()
+        self._ctx.L.cs_default_line_params(C.byref(p))
+        p.use_LSD = int(bool(self.use_LSD))
+        p.numoctaves = self.numoctaves_
+        p.octaveratio = self.octaveratio_
+        p.line_length_thres = float(self.line_length_thres)
+        return p
+
+    def detect_filter_lines(self, gray_img, cap=8192):
+        """One frame (H x W or H x W x 3 uint8) -> n x 4 float32."""
+        return self.detect_filter_lines_batch(np.asarray(gray_img)[None], cap)[0]
+
+    def detect_filter_lines_batch(self, imgs, cap=4096):
+        imgs = np.ascontiguousarray(imgs, np.uint8)
+        if imgs.ndim == 3:
+            F, H, W = imgs.shape
+            ch = 1
+        else:
+            F, H, W, ch = imgs.shape
+        out = np.zeros((F, cap, 4), np.float32)
+        n = np.zeros(F, np.int32)
+        p = self.params()
+        rc = self._ctx.L.cs_detect_lines_batch(self._ctx.h, imgs.ctypes.data, F, W, H, W * ch, ch, C.byref(p), _lib.ptr(out, C.c_float), cap,
+                                               _lib.ptr(n, C.c_int32))
+        if rc != 0:
+            raise CubeSlamError("%s: %s" % (_lib.STATUS_NAMES.get(rc, rc), self._ctx.L.cs_last_error(self._ctx.h).decode()))
+        return [out[f, :n[f]].copy() for f in range(F)]
+
+    def debug_frame(self, frame=0, cap=8192):
+        L = self._ctx.L
+        wh = np.zeros(2, np.int32)
+        self._ctx.check(L.cs_debug_lsd(self._ctx.h, frame, _lib.ptr(wh, C.c_int32), None, None, None, None, None, None, None, 0))
+        W, H = int(wh[0]), int(wh[1])
+        sc, mg, an = np.zeros((H, W)), np.zeros((H, W)), np.zeros((H, W))
+        lst = np.zeros(W * H, np.int32)
+        ll, nr = C.c_int32(), C.c_int32()
+        raw = np.zeros((cap, 4), np.float32)
+        self._ctx.check(L.cs_debug_lsd(self._ctx.h, frame, _lib.ptr(wh, C.c_int32), _lib.ptr(sc, C.c_double), _lib.ptr(mg, C.c_double),
+                                       _lib.ptr(an, C.c_double), _lib.ptr(lst, C.c_int32), C.byref(ll), _lib.ptr(raw, C.c_float), C.byref(nr), cap))
+        return dict(scaled=sc, modgrad=mg, angles=an, list=lst[:ll.value].copy(), raw_lines=raw[:nr.value].copy())

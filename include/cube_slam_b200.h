@@ -177,6 +177,10 @@ int cs_detect_lines_batch(cs_ctx *ctx, const uint8_t *imgs, int n_frames, int wi
                           int channels, const cs_line_params *params, float *lines_xyxy, int32_t max_lines_per_frame,
                           int32_t *n_lines /* n_frames */);
 
+/* inspection of the last cs_detect_lines[_batch] run (tests): intermediate images of one frame; any pointer may be NULL */
+int cs_debug_lsd(cs_ctx *ctx, int frame, int32_t scaled_wh[2], double *scaled, double *modgrad, double *angles, int32_t *list,
+                 int32_t *list_len, float *raw_lines, int32_t *n_raw, int cap_raw);
+
 /* ---- multi-GPU -------------------------------------------------------------------------- */
 /* Frames shard across ranks; the only exchange is one all-gather of the top-K record buffers.
  * No reference counterpart (the reference is single process); see BASELINE.json north_star. */

@@ -218,3 +218,46 @@ def detect_cuboid(img, K, T_wc, boxes, lines, params=None, topk_cap=None, trace_
             cand_index=bufs["cand_index"][:tr.n_valid].copy(),
             n_kept=tr.n_kept, kept_ids=bufs["kept_ids"][:tr.n_kept].copy(), kept_scores=bufs["kept_scores"][:tr.n_kept].copy())
     return res
+
+
+# ------------------------------------------------------------------------------------------- LSD
+def lsd_fast_atan2(y, x):
+    L = lib()
+    L.lsd_orc_fast_atan2.restype = C.c_float
+    L.lsd_orc_fast_atan2.argtypes = [C.c_float, C.c_float]
+    return L.lsd_orc_fast_atan2(y, x)
+
+
+def lsd_blur_resize(img64):
+    """GaussianBlur(7x7, 0.75) then resize(x0.8, INTER_LINEAR) on a float64 image (lsd.cpp:450-459)."""
+    src = np.ascontiguousarray(img64, np.float64)
+    h, w = src.shape
+    blur = np.empty_like(src)
+    dw, dh = C.c_int(), C.c_int()
+    scaled = np.empty((int(round(h * 0.8)) + 2) * (int(round(w * 0.8)) + 2), np.float64)
+    lib().lsd_orc_blur_resize(_p(src, C.c_double), w, h, _p(blur, C.c_double), _p(scaled, C.c_double), C.byref(dw), C.byref(dh))
+    return blur, scaled[:dw.value * dh.value].reshape(dh.value, dw.value).copy()
+
+
+def lsd_detect(img, line_length_thres=15.0, cap=8192, want_stages=False, refine_mode=2):
+    """line_lbd_detect::detect_filter_lines with use_LSD = true (line_lbd_allclass.cpp:216-221) -> n x 4 float32."""
+    img = np.ascontiguousarray(img, np.uint8)
+    h, w = img.shape[:2]
+    ch = 1 if img.ndim == 2 else img.shape[2]
+    out = np.zeros((cap, 4), np.float32)
+    raw = np.zeros((cap, 4), np.float32)
+    n_raw = C.c_int(0)
+    sw, sh = int(round(w * 0.8)), int(round(h * 0.8))
+    st = None
+    args = [None, None, None, None, None]
+    if want_stages:
+        st = dict(scaled=np.zeros((sh, sw)), modgrad=np.zeros((sh, sw)), angles=np.zeros((sh, sw)), list=np.zeros(sw * sh, np.int32))
+        ll = C.c_int(0)
+        args = [_p(st["scaled"], C.c_double), _p(st["modgrad"], C.c_double), _p(st["angles"], C.c_double), _p(st["list"], C.c_int32), C.byref(ll)]
+    n = lib().lsd_orc_detect(_p(img, C.c_uint8), w, h, img.strides[0], ch, C.c_float(line_length_thres), _p(out, C.c_float), cap,
+                             _p(raw, C.c_float), cap, C.byref(n_raw), *args, int(refine_mode))
+    res = dict(lines=out[:min(n, cap)].copy(), raw_lines=raw[:min(n_raw.value, cap)].copy())
+    if want_stages:
+        st["list"] = st["list"][:ll.value].copy()
+        res["stages"] = st
+    return res

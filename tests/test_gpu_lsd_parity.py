@@ -1,0 +1,82 @@
+"""GPU parity of the LSD line detector (cs_detect_lines) against the CPU oracle's restatement of line_lbd's LSD path.
+
+Streaming stages (blur, resize, gradient modulus / angle, pseudo-ordering) must be bit-exact; the detected segments are
+float32 and must be identical (the only non-IEEE operations are double cos/sin/log of CUDA vs glibc, <= 2 ulp before the
+float rounding)."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def det():
+    import cube_slam_b200 as cs
+    d = cs.line_lbd_detect()
+    d.use_LSD = True              # object_slam/src/main_obj.cpp:365
+    d.line_length_thres = 15      # :366
+    return d
+
+
+def _check_frame(det, oracle, img, frame=0):
+    ref = oracle.lsd_detect(img, 15.0, want_stages=True)
+    dbg = det.debug_frame(frame)
+    np.testing.assert_array_equal(dbg["scaled"], ref["stages"]["scaled"])
+    np.testing.assert_array_equal(dbg["modgrad"][:-1, :-1], ref["stages"]["modgrad"][:-1, :-1])
+    np.testing.assert_array_equal(dbg["angles"], ref["stages"]["angles"])
+    np.testing.assert_array_equal(dbg["list"], ref["stages"]["list"])
+    assert len(dbg["raw_lines"]) == len(ref["raw_lines"])
+    np.testing.assert_array_equal(dbg["raw_lines"], ref["raw_lines"])
+    return ref
+
+
+def test_fixture_frames(det, oracle, fixture_a, fixture_b):
+    imgs = [fixture_b["frames"][i][0] for i in (0, 17, 40)]
+    lines = det.detect_filter_lines_batch(np.stack(imgs))
+    for f, img in enumerate(imgs):
+        ref = _check_frame(det, oracle, img, f)
+        np.testing.assert_array_equal(lines[f], ref["lines"])
+        assert len(lines[f]) > 5
+    one = det.detect_filter_lines(fixture_a["img"])
+    ref = _check_frame(det, oracle, fixture_a["img"], 0)
+    np.testing.assert_array_equal(one, ref["lines"])
+
+
+def test_synthetic_and_gray_input(det, oracle):
+    from cube_slam_b200 import synthetic as S
+    imgs, Ts, boxes, lines, K = S.make_batch(41, 4, 640, 480, 3)
+    out = det.detect_filter_lines_batch(imgs)
+    for f in range(4):
+        ref = oracle.lsd_detect(imgs[f], 15.0)
+        np.testing.assert_array_equal(out[f], ref["lines"])
+    gray = np.ascontiguousarray(imgs[:, :, :, 1])
+    out = det.detect_filter_lines_batch(gray)
+    for f in range(4):
+        np.testing.assert_array_equal(out[f], oracle.lsd_detect(gray[f], 15.0)["lines"])
+    # a flat image has no gradient above the threshold: no lines, no crash
+    flat = np.full((1, 240, 320, 3), 90, np.uint8)
+    assert len(det.detect_filter_lines_batch(flat)[0]) == 0
+
+
+def test_unsupported_modes_fail_loudly(det):
+    import cube_slam_b200 as cs
+    d = cs.line_lbd_detect(context=det._ctx)
+    d.use_LSD = False
+    with pytest.raises(cs.CubeSlamError, match="UNSUPPORTED"):
+        d.detect_filter_lines(np.zeros((64, 64), np.uint8))
+
+
+def test_lines_feed_detect_cuboid(det, oracle, fixture_b):
+    """The online path of object_slam: line_lbd lines -> detect_cuboid (main_obj.cpp:424-450), frame 0 (no sampling)."""
+    import cube_slam_b200 as cs
+    img, boxes = fixture_b["frames"][0]
+    lines = det.detect_filter_lines(img)
+    d3 = cs.detect_3d_cuboid()
+    d3.set_calibration(fixture_b["K"])
+    d3.nominal_skew_ratio = 2  # main_obj.cpp:360
+    got = d3.detect_cuboid(img, fixture_b["T"], boxes, lines.astype(np.float64))
+    ref_lines = oracle.lsd_detect(img, 15.0)["lines"].astype(np.float64)
+    ref = oracle.detect_cuboid(img, fixture_b["K"], fixture_b["T"], boxes, ref_lines, oracle.default_params(nominal_skew_ratio=2))
+    assert len(got) == len(boxes) == 1
+    assert got[0][0].proposal_index == int(ref["cuboids"][0][0]["proposal_index"])
+    assert abs(got[0][0].normalized_error - float(ref["cuboids"][0][0]["normalized_error"])) < 1e-9
