@@ -80,3 +80,39 @@ def test_lines_feed_detect_cuboid(det, oracle, fixture_b):
     assert len(got) == len(boxes) == 1
     assert got[0][0].proposal_index == int(ref["cuboids"][0][0]["proposal_index"])
     assert abs(got[0][0].normalized_error - float(ref["cuboids"][0][0]["normalized_error"])) < 1e-9
+
+
+def test_object_slam_sequence_parity(det, oracle, fixture_b):
+    """north_star: best-proposal-index parity on the shipped object_slam/data sequence, online mode
+    (object_slam/src/main_obj.cpp:392-450): LSD lines (length > 15) -> detect_cuboid with nominal_skew_ratio 2,
+    roll/pitch sampling on every frame but the first, all frames at the first frame's pose."""
+    import cube_slam_b200 as cs
+    frames = fixture_b["frames"]
+    K, T = fixture_b["K"], fixture_b["T"]
+    imgs = np.stack([f[0] for f in frames])
+    gpu_lines = det.detect_filter_lines_batch(imgs)
+    ctx = cs.Context(0, 640, 480, len(frames), 8, 4096)
+    ctx.set_calibration(K)
+    n_checked = 0
+    for sampling, ids in ((0, [0]), (1, list(range(1, len(frames))))):
+        p = cs.default_params(whether_sample_cam_roll_pitch=sampling, nominal_skew_ratio=2.0)
+        out, counts = ctx.detect_batch_host(imgs[ids], np.stack([T] * len(ids)), [frames[i][1] for i in ids],
+                                            [gpu_lines[i].astype(np.float64) for i in ids], p)
+        o = 0
+        for i in ids:
+            ref_lines = oracle.lsd_detect(frames[i][0], 15.0)["lines"]
+            np.testing.assert_array_equal(gpu_lines[i], ref_lines)
+            ref = oracle.detect_cuboid(frames[i][0], K, T, frames[i][1], ref_lines.astype(np.float64),
+                                       oracle.default_params(whether_sample_cam_roll_pitch=sampling, nominal_skew_ratio=2.0))
+            for b in range(len(frames[i][1])):
+                assert counts[o] == len(ref["cuboids"][b]), (i, b)
+                if counts[o]:
+                    g, r = out[o, 0], ref["cuboids"][b][0]
+                    assert int(g["proposal_index"]) == int(r["proposal_index"]), i
+                    assert abs(float(g["normalized_error"]) - float(r["normalized_error"])) < 1e-4
+                    np.testing.assert_allclose(g["pos"], r["pos"], rtol=1e-9, atol=1e-9)
+                    np.testing.assert_array_equal(g["box_corners_2d"], r["box_corners_2d"])
+                    n_checked += 1
+                o += 1
+    assert n_checked >= 45  # 51 of the 58 frames carry a box
+    ctx.close()
