@@ -40,6 +40,7 @@ WORKLOADS = {
 
 # algorithmic bytes per unit of each stage
 STAGE_BYTES = {
+    "lsd": lambda s, shp: shp["frame_px"] * s["n_frames"] * (3 + 8 * 2 + 0.64 * 8 * 4),  # frame in, two f64 blur planes, scaled/modgrad/angle/list
     "gray": lambda s, shp: shp["frame_px"] * s["n_frames"] * 4,          # 3 B in + 1 B out per pixel
     "canny": lambda s, shp: s["roi_pixels"] * 2,                           # gray ROI read + edge map written
     "hyst": lambda s, shp: s["roi_pixels"] * 1,                            # edge map, in place
@@ -244,6 +245,33 @@ def run_ours(args, rank, world, local_rank):
     ms_per_step = ms_total / args.steps
     value = n_valid_all / (ms_per_step * 1e-3)
 
+    # ---- online mode (object_slam main_obj.cpp:424-450): lines detected on the resident frames by the LSD kernels, N = 1 only
+    online = None
+    if world == 1 and not args.no_online:
+        det = cs.line_lbd_detect(context=ctx)
+        det.use_LSD = True
+        det.line_length_thres = 15
+        lp = det.params()
+        ctx.upload_online(wl["imgs"], wl["Ts"], wl["boxes"], lp, params)
+        for _ in range(2):
+            ctx.run()
+        st_on = ctx.stats()
+        o0, o1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        n_on = max(3, min(args.steps, 5))
+        torch.cuda.synchronize()
+        o0.record(stream)
+        for _ in range(n_on):
+            ctx.run_async()
+        o1.record(stream)
+        torch.cuda.synchronize()
+        on_ms = o0.elapsed_time(o1) / n_on
+        ctx.run()
+        online = {"workload": "same frames, lines from cs_detect_lines (LSD, length > 15) on the device", "ms_per_step": on_ms,
+                  "frames_per_s": F / (on_ms * 1e-3), "value": st_on["n_valid"] / (on_ms * 1e-3), "unit": "proposals/s",
+                  "n_valid": st_on["n_valid"], "stage_ms": ctx.stage_ms(),
+                  "note": "the LSD seed loop is one warp per frame (order-dependent); at 256 frames it is latency-bound"}
+        ctx.upload(wl["imgs"], wl["Ts"], wl["boxes"], wl["lines"], params)
+
     # ---- end to end through the host-buffer ABI call ("e2e")
     pinned = torch.from_numpy(wl["imgs"]).pin_memory()
     imgs_pinned = pinned.numpy()
@@ -282,7 +310,7 @@ def run_ours(args, rank, world, local_rank):
     # ---- roofline of the dominant kernel
     hbm_peak, peak_src = measured_peaks()
     shp = {"frame_px": w * h}
-    kernel_ms = {k: v for k, v in stage_acc.items() if k != "total"}
+    kernel_ms = {k: v for k, v in stage_acc.items() if k not in ("total", "lsd")}
     dom = max(kernel_ms, key=kernel_ms.get)
     dom_bytes = float(STAGE_BYTES[dom](stats, shp))
     achieved = dom_bytes / (kernel_ms[dom] * 1e-3) / 1e9 if kernel_ms[dom] > 0 else 0.0
@@ -313,7 +341,7 @@ def run_ours(args, rank, world, local_rank):
         "e2e": {"value": n_valid_all / (e2e_ms_step * 1e-3), "unit": "proposals/s", "frames_per_s": n_frames_all / (e2e_ms_step * 1e-3),
                 "ms_per_step": e2e_ms_step, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)},
         "gpu_launches": int(stats["n_kernel_launches"]) * args.steps,
-        "roofline": roofline, "cpu_baseline": cpu, "clocks": sampler.summary(),
+        "roofline": roofline, "cpu_baseline": cpu, "online": online, "clocks": sampler.summary(),
     }
     print(json.dumps(line))
     if world > 1:
@@ -323,11 +351,12 @@ def run_ours(args, rank, world, local_rank):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="c3", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-online", action="store_true")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))

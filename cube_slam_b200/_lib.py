@@ -58,7 +58,7 @@ _lib = None
 EXPORTS = [
     "cs_abi_version", "cs_create", "cs_destroy", "cs_last_error", "cs_default_cuboid_params",
     "cs_default_line_params", "cs_set_calibration", "cs_cam_pose", "cs_detect_cuboids", "cs_detect_cuboids_batch",
-    "cs_batch_upload", "cs_batch_run", "cs_batch_run_async", "cs_batch_fetch", "cs_batch_stats_get",
+    "cs_batch_upload", "cs_batch_upload_online", "cs_detect_frames_batch", "cs_batch_run", "cs_batch_run_async", "cs_batch_fetch", "cs_batch_stats_get",
     "cs_batch_device_records", "cs_stream", "cs_stage_ms", "cs_set_profiling", "cs_debug_roi",
     "cs_debug_candidates", "cs_detect_lines", "cs_detect_lines_batch", "cs_debug_lsd", "cs_comm_unique_id", "cs_comm_init",
     "cs_allgather_topk", "cs_fetch_gathered",
@@ -90,6 +90,8 @@ def load():
     L.cs_detect_cuboids.argtypes = [vp, u8_p, i, i, i, i, d_p, d_p, i, d_p, i, C.POINTER(CuboidParams), vp, i32_p]
     L.cs_detect_cuboids_batch.argtypes = [vp, vp, i, i, i, i, i, d_p, d_p, i32_p, d_p, i32_p, C.POINTER(CuboidParams), vp, i32_p]
     L.cs_batch_upload.argtypes = [vp, vp, i, i, i, i, i, d_p, d_p, i32_p, d_p, i32_p, C.POINTER(CuboidParams)]
+    L.cs_batch_upload_online.argtypes = [vp, vp, i, i, i, i, i, d_p, d_p, i32_p, C.POINTER(LineParams), C.POINTER(CuboidParams)]
+    L.cs_detect_frames_batch.argtypes = [vp, vp, i, i, i, i, i, d_p, d_p, i32_p, C.POINTER(LineParams), C.POINTER(CuboidParams), vp, i32_p]
     L.cs_batch_run.argtypes = [vp]
     L.cs_batch_run_async.argtypes = [vp]
     L.cs_batch_fetch.argtypes = [vp, vp, i32_p]

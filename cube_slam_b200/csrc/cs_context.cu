@@ -26,8 +26,8 @@ struct DevBuf {
     size_t cap = 0;
 };
 
-enum Stage { ST_GRAY, ST_CANNY, ST_HYST, ST_DT, ST_LINES, ST_SWEEP, ST_FUSE, ST_COUNT };
-const char *kStageNames[ST_COUNT] = {"gray", "canny", "hyst", "dt", "lines", "sweep", "fuse"};
+enum Stage { ST_LSD, ST_GRAY, ST_CANNY, ST_HYST, ST_DT, ST_LINES, ST_SWEEP, ST_FUSE, ST_COUNT };
+const char *kStageNames[ST_COUNT] = {"lsd", "gray", "canny", "hyst", "dt", "lines", "sweep", "fuse"};
 
 }  // namespace
 
@@ -47,6 +47,9 @@ struct cs_ctx {
     std::vector<double> h_T, h_boxes, h_lines;
     std::vector<int32_t> h_box_off, h_line_off;
     int topk = 1;
+    bool online_lines = false; /* lines come from the line detector run on the uploaded frames */
+    cs_line_params line_prm;
+    int online_cap = 1024;
 
     /* host tables built by build_tables() */
     std::vector<CsFrame> frames;
@@ -368,12 +371,21 @@ int run_batch(cs_ctx *c, bool sync)
     auto mark = [&](int s) {
         if (c->profiling) cudaEventRecord(c->ev[s], st);
     };
-    /* fork: the per-ROI line selection / merging only needs the uploaded lines and job table */
+    const float *d_lines_f32 = nullptr;
+    const int32_t *d_nlines = nullptr;
+    mark(ST_LSD);
+    if (c->online_lines) { /* line_lbd_detect::detect_filter_lines on the resident frames (object_slam main_obj.cpp:428) */
+        if ((rc = cs_lsd_run_device(c, (const uint8_t *)c->d_img.p, c->n_frames, c->w, c->h, c->stride, c->channels, c->line_prm.line_length_thres,
+                                    c->online_cap, &d_lines_f32, &d_nlines)))
+            return rc;
+        c->launches += 8;
+    }
+    /* fork: the per-ROI line selection / merging only needs the lines and the job table */
     cudaEventRecord(c->ev_fork, st);
     cudaStreamWaitEvent(c->stream2, c->ev_fork, 0);
-    cs_launch_roi_lines((const CsJob *)c->d_jobs.p, n_jobs, (const CsFrame *)c->d_frames.p, (const double *)c->d_lines.p, (double *)c->d_mlines.p,
-                        (int32_t *)c->d_lcounts.p, (int32_t *)c->d_err.p, c->prm.pre_merge_dist_thre, c->prm.pre_merge_angle_thre,
-                        c->prm.edge_length_threshold, c->stream2, &c->launches);
+    cs_launch_roi_lines((const CsJob *)c->d_jobs.p, n_jobs, (const CsFrame *)c->d_frames.p, (const double *)c->d_lines.p, d_lines_f32, d_nlines,
+                        c->online_cap, (double *)c->d_mlines.p, (int32_t *)c->d_lcounts.p, (int32_t *)c->d_err.p, c->prm.pre_merge_dist_thre,
+                        c->prm.pre_merge_angle_thre, c->prm.edge_length_threshold, c->stream2, &c->launches);
     cudaEventRecord(c->ev_join, c->stream2);
     mark(ST_GRAY);
     if (c->channels == 3 || c->stride != c->w)
@@ -423,8 +435,14 @@ int run_batch(cs_ctx *c, bool sync)
 
 int store_batch(cs_ctx *c, const uint8_t *imgs, int n_frames, int width, int height, int stride, int channels, const double *T_wc,
                 const double *boxes, const int32_t *box_offsets, const double *lines, const int32_t *line_offsets,
-                const cs_cuboid_params *params)
+                const cs_cuboid_params *params, const cs_line_params *online = nullptr)
 {
+    std::vector<int32_t> zero_off;
+    if (online) { /* no input lines: CSR of zeros */
+        zero_off.assign((size_t)std::max(n_frames, 0) + 1, 0);
+        line_offsets = zero_off.data();
+        lines = nullptr;
+    }
     if (!c) return CS_ERR_INVALID_ARG;
     if (!imgs || n_frames <= 0 || width <= 0 || height <= 0 || !T_wc || !box_offsets || !line_offsets || !params)
         return fail(c, CS_ERR_INVALID_ARG, "null or empty argument");
@@ -442,6 +460,13 @@ int store_batch(cs_ctx *c, const uint8_t *imgs, int n_frames, int width, int hei
     const int nb = box_offsets[n_frames], nl = line_offsets[n_frames];
     if ((nb > 0 && !boxes) || (nl > 0 && !lines)) return fail(c, CS_ERR_INVALID_ARG, "null boxes/lines");
     c->prepared = false;
+    c->online_lines = online != nullptr;
+    if (online) {
+        if (!online->use_LSD) return fail(c, CS_ERR_UNSUPPORTED, "EDLines flavour (use_LSD = false) is not implemented yet");
+        if (online->numoctaves != 1) return fail(c, CS_ERR_UNSUPPORTED, "only one octave is supported");
+        c->line_prm = *online;
+        c->online_cap = std::max(64, std::min(c->max_lines > 0 ? c->max_lines : 1024, 4096));
+    }
     c->n_frames = n_frames;
     c->w = width;
     c->h = height;
@@ -451,7 +476,7 @@ int store_batch(cs_ctx *c, const uint8_t *imgs, int n_frames, int width, int hei
     c->topk = params->max_cuboid_num;
     c->h_T.assign(T_wc, T_wc + (size_t)n_frames * 16);
     c->h_boxes.assign(boxes, boxes + (size_t)nb * 5);
-    c->h_lines.assign(lines, lines + (size_t)nl * 4);
+    if (nl) c->h_lines.assign(lines, lines + (size_t)nl * 4); else c->h_lines.clear();
     c->h_box_off.assign(box_offsets, box_offsets + n_frames + 1);
     c->h_line_off.assign(line_offsets, line_offsets + n_frames + 1);
     int rc;
@@ -477,6 +502,7 @@ int fetch(cs_ctx *c, cs_cuboid_rec *out, int32_t *out_counts)
     CS_CUDA(c, cudaStreamSynchronize(c->stream));
     if (err & 1) return fail(c, CS_ERR_CAPACITY, "more than %d line segments inside one ROI", CS_LINE_CAP);
     if (err & 2) return fail(c, CS_ERR_CAPACITY, "more than %d merged segments inside one ROI", CS_MAXL_OUT);
+    if (err & 4) return fail(c, CS_ERR_CAPACITY, "the line detector found more than %d segments in a frame (raise max_lines_per_frame)", c->online_cap);
     if (out && out_counts) { /* slots past the count are not cuboids */
         for (size_t o = 0; o < no; o++)
             for (int k = out_counts[o]; k < c->topk; k++) std::memset(&out[o * c->topk + k], 0, sizeof(cs_cuboid_rec));
@@ -616,6 +642,31 @@ int cs_batch_upload(cs_ctx *c, const uint8_t *imgs, int n_frames, int width, int
     if (rc) return rc;
     CS_CUDA(c, cudaStreamSynchronize(c->stream));
     return CS_OK;
+}
+
+int cs_batch_upload_online(cs_ctx *c, const uint8_t *imgs, int n_frames, int width, int height, int stride, int channels, const double *T_wc,
+                           const double *boxes, const int32_t *box_offsets, const cs_line_params *line_params, const cs_cuboid_params *params)
+{
+    if (!c) return CS_ERR_INVALID_ARG;
+    if (!line_params) return fail(c, CS_ERR_INVALID_ARG, "null line params");
+    cudaSetDevice(c->device);
+    int rc = store_batch(c, imgs, n_frames, width, height, stride, channels, T_wc, boxes, box_offsets, nullptr, nullptr, params, line_params);
+    if (rc) return rc;
+    CS_CUDA(c, cudaStreamSynchronize(c->stream));
+    return CS_OK;
+}
+
+int cs_detect_frames_batch(cs_ctx *c, const uint8_t *imgs, int n_frames, int width, int height, int stride, int channels, const double *T_wc,
+                           const double *boxes, const int32_t *box_offsets, const cs_line_params *line_params, const cs_cuboid_params *params,
+                           cs_cuboid_rec *out, int32_t *out_counts)
+{
+    if (!c) return CS_ERR_INVALID_ARG;
+    if (!line_params) return fail(c, CS_ERR_INVALID_ARG, "null line params");
+    cudaSetDevice(c->device);
+    int rc = store_batch(c, imgs, n_frames, width, height, stride, channels, T_wc, boxes, box_offsets, nullptr, nullptr, params, line_params);
+    if (rc) return rc;
+    if ((rc = run_batch(c, false))) return rc;
+    return fetch(c, out, out_counts);
 }
 
 int cs_batch_run(cs_ctx *c)

@@ -72,6 +72,8 @@ int cs_ctx_device(cs_ctx *c);
 int cs_ctx_fail(cs_ctx *c, int code, const char *fmt, ...);
 void **cs_ctx_lsd_slot(cs_ctx *c);          /* owned by cs_lsd.cu */
 void cs_lsd_destroy(void *state);           /* called from cs_destroy */
+int cs_lsd_run_device(cs_ctx *c, const uint8_t *d_imgs, int n_frames, int w, int h, int stride, int channels, float line_length_thres, int cap,
+                      const float **d_lines, const int32_t **d_counts);
 void cs_ctx_count_launches(cs_ctx *c, int64_t n);
 
 #endif

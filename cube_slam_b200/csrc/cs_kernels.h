@@ -21,7 +21,8 @@ void cs_launch_dt(const CsJob *d_jobs, const int32_t *d_ids, int n_jobs, int max
                   cudaStream_t st, int64_t *launches);
 bool cs_launch_hyst_dt(const CsJob *d_jobs, int n_jobs, uint32_t *d_bits, float *d_dist, int max_plane_words, int max_dpitch, int max_h,
                        cudaStream_t st, int64_t *launches);
-void cs_launch_roi_lines(const CsJob *d_jobs, int n_jobs, const CsFrame *d_frames, const double *d_lines, double *d_out_lines,
+void cs_launch_roi_lines(const CsJob *d_jobs, int n_jobs, const CsFrame *d_frames, const double *d_lines, const float *d_lines_f32,
+                         const int32_t *d_n_lines_dev, int f32_pitch, double *d_out_lines,
                          int32_t *d_out_counts, int32_t *d_err, double dist_thre, double angle_thre_deg, double len_thre, cudaStream_t st,
                          int64_t *launches);
 void cs_launch_sweep(const CsJob *d_jobs, const CsFrame *d_frames, const CsPose *d_poses, const double *d_yaw, const int2 *d_blocks,

@@ -64,7 +64,8 @@ __device__ __forceinline__ bool merge_test(const LineSet &L, int s1, int s2, dou
 extern __shared__ unsigned char ln_smem_raw[];
 
 __global__ void __launch_bounds__(LN_THREADS) k_roi_lines(const CsJob *__restrict__ jobs, const CsFrame *__restrict__ frames,
-                                                          const double *__restrict__ lines /* batch, M x 4 */, double *__restrict__ out_lines,
+                                                          const double *__restrict__ lines /* batch, M x 4 */, const float *__restrict__ lines_f32 /* online mode: detector output */,
+                                                          const int32_t *__restrict__ n_lines_dev, int f32_pitch, double *__restrict__ out_lines,
                                                           int32_t *__restrict__ out_counts /* n_jobs x 2: inside, merged */,
                                                           int32_t *__restrict__ err_flag, double dist_thre, double angle_thre_deg,
                                                           double len_thre)
@@ -76,7 +77,15 @@ __global__ void __launch_bounds__(LN_THREADS) k_roi_lines(const CsJob *__restric
 
     const int job = blockIdx.x;
     const CsJob jb = jobs[job];
-    const CsFrame fr = frames[jb.frame];
+    CsFrame fr = frames[jb.frame];
+    if (n_lines_dev) { /* online mode: the line detector left n x 4 float32 per frame at a fixed pitch */
+        fr.n_lines = n_lines_dev[jb.frame];
+        if (fr.n_lines > f32_pitch) { /* the detector found more segments than the context's line capacity */
+            if (threadIdx.x == 0) atomicOr(err_flag, 4);
+            fr.n_lines = f32_pitch;
+        }
+        fr.line_off = jb.frame * f32_pitch;
+    }
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const double bl = jb.roi_l, bt = jb.roi_t, br = jb.roi_r, bb = jb.roi_b;
 
@@ -88,11 +97,19 @@ __global__ void __launch_bounds__(LN_THREADS) k_roi_lines(const CsJob *__restric
         bool in = false;
         double x1 = 0, y1 = 0, x2 = 0, y2 = 0;
         if (i < fr.n_lines) {
-            const double *p = lines + (size_t)(fr.line_off + i) * 4;
-            x1 = p[0];
-            y1 = p[1];
-            x2 = p[2];
-            y2 = p[3];
+            if (lines_f32) { /* float -> double exactly as main_obj.cpp:429-432 */
+                const float *p = lines_f32 + (size_t)(fr.line_off + i) * 4;
+                x1 = p[0];
+                y1 = p[1];
+                x2 = p[2];
+                y2 = p[3];
+            } else {
+                const double *p = lines + (size_t)(fr.line_off + i) * 4;
+                x1 = p[0];
+                y1 = p[1];
+                x2 = p[2];
+                y2 = p[3];
+            }
             if (x2 < x1) { /* align_left_right_edges */
                 double t = x1;
                 x1 = x2;
@@ -247,7 +264,8 @@ __global__ void __launch_bounds__(LN_THREADS) k_roi_lines(const CsJob *__restric
     }
 }
 
-void cs_launch_roi_lines(const CsJob *d_jobs, int n_jobs, const CsFrame *d_frames, const double *d_lines, double *d_out_lines,
+void cs_launch_roi_lines(const CsJob *d_jobs, int n_jobs, const CsFrame *d_frames, const double *d_lines, const float *d_lines_f32,
+                         const int32_t *d_n_lines_dev, int f32_pitch, double *d_out_lines,
                          int32_t *d_out_counts, int32_t *d_err, double dist_thre, double angle_thre_deg, double len_thre, cudaStream_t st,
                          int64_t *launches)
 {
@@ -257,7 +275,7 @@ void cs_launch_roi_lines(const CsJob *d_jobs, int n_jobs, const CsFrame *d_frame
         cudaFuncSetAttribute(k_roi_lines, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(LineSet));
         attr_set = true;
     }
-    k_roi_lines<<<n_jobs, LN_THREADS, sizeof(LineSet), st>>>(d_jobs, d_frames, d_lines, d_out_lines, d_out_counts, d_err, dist_thre,
+    k_roi_lines<<<n_jobs, LN_THREADS, sizeof(LineSet), st>>>(d_jobs, d_frames, d_lines, d_lines_f32, d_n_lines_dev, f32_pitch, d_out_lines, d_out_counts, d_err, dist_thre,
                                                              angle_thre_deg, len_thre);
     (*launches)++;
 }

@@ -910,6 +910,18 @@ LsdState *state_of(cs_ctx *c)
 
 }  // namespace
 
+/* device-to-device entry used by the online batch path: frames already in HBM, results stay in HBM */
+int cs_lsd_run_device(cs_ctx *c, const uint8_t *d_imgs, int n_frames, int w, int h, int stride, int channels, float line_length_thres, int cap,
+                      const float **d_lines, const int32_t **d_counts)
+{
+    LsdState *S = state_of(c);
+    const int rc = lsd_run(c, d_imgs, true, n_frames, w, h, stride, channels, line_length_thres, cap, *S);
+    if (rc) return rc;
+    *d_lines = (const float *)S->out.p;
+    *d_counts = (const int32_t *)S->nout.p;
+    return CS_OK;
+}
+
 void cs_lsd_destroy(void *state)
 {
     LsdState *S = (LsdState *)state;

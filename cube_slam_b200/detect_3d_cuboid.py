@@ -115,6 +115,31 @@ class Context(object):
                                           _lib.ptr(boxes, C.c_double), _lib.ptr(box_off, C.c_int32),
                                           _lib.ptr(lines, C.c_double), _lib.ptr(line_off, C.c_int32), C.byref(params)))
 
+    def upload_online(self, imgs, Ts, boxes_list, line_params, params):
+        """cs_batch_upload_online: no input lines, cs_batch_run detects them on the resident frames first."""
+        F = len(imgs)
+        imgs, F, H, W, ch, Ts, boxes, box_off, _, _ = self._pack(imgs, Ts, boxes_list, [np.zeros((0, 4))] * F)
+        self._n_obj = int(box_off[-1])
+        self._topk = int(params.max_cuboid_num)
+        self._box_off = box_off
+        self.check(self.L.cs_batch_upload_online(self.h, imgs.ctypes.data, F, W, H, W * ch, ch, _lib.ptr(Ts, C.c_double),
+                                                 _lib.ptr(boxes, C.c_double), _lib.ptr(box_off, C.c_int32), C.byref(line_params), C.byref(params)))
+
+    def detect_frames_host(self, imgs, Ts, boxes_list, line_params, params, out=None, counts=None):
+        """cs_detect_frames_batch: detect_filter_lines + detect_cuboid per frame, host buffers in / out."""
+        F = len(imgs)
+        imgs, F, H, W, ch, Ts, boxes, box_off, _, _ = self._pack(imgs, Ts, boxes_list, [np.zeros((0, 4))] * F)
+        n_obj = int(box_off[-1])
+        topk = int(params.max_cuboid_num)
+        if out is None:
+            out = np.zeros((max(n_obj, 1), topk), CUBOID_DTYPE)
+            counts = np.zeros(max(n_obj, 1), np.int32)
+        self.check(self.L.cs_detect_frames_batch(self.h, imgs.ctypes.data, F, W, H, W * ch, ch, _lib.ptr(Ts, C.c_double),
+                                                 _lib.ptr(boxes, C.c_double), _lib.ptr(box_off, C.c_int32), C.byref(line_params),
+                                                 C.byref(params), out.ctypes.data, _lib.ptr(counts, C.c_int32)))
+        self._n_obj, self._topk, self._box_off = n_obj, topk, box_off
+        return out[:n_obj], counts[:n_obj]
+
     def run(self):
         self.check(self.L.cs_batch_run(self.h))
 
@@ -153,7 +178,7 @@ class Context(object):
 
     def stage_ms(self):
         out = {}
-        for name in ("gray", "canny", "hyst", "dt", "lines", "sweep", "fuse", "total"):
+        for name in ("lsd", "gray", "canny", "hyst", "dt", "lines", "sweep", "fuse", "total"):
             v = C.c_float(0)
             self.check(self.L.cs_stage_ms(self.h, name.encode(), C.byref(v)))
             out[name] = v.value

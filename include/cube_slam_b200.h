@@ -143,10 +143,22 @@ int cs_detect_cuboids_batch(cs_ctx *ctx, const uint8_t *imgs, int n_frames, int 
                             const int32_t *box_offsets, const double *lines, const int32_t *line_offsets,
                             const cs_cuboid_params *params, cs_cuboid_rec *out, int32_t *out_counts);
 
+/* The whole per-frame front end of object_slam's online mode in one call (object_slam/src/main_obj.cpp:424-450):
+ * line_lbd_detect::detect_filter_lines on every frame, its n x 4 float output widened to double, then detect_cuboid.
+ * Lines never leave the device.  Host buffers in, host records out. */
+int cs_detect_frames_batch(cs_ctx *ctx, const uint8_t *imgs, int n_frames, int width, int height, int stride, int channels,
+                           const double *T_wc, const double *boxes, const int32_t *box_offsets,
+                           const cs_line_params *line_params, const cs_cuboid_params *params, cs_cuboid_rec *out,
+                           int32_t *out_counts);
+
 /* Device-resident variant used by the throughput benchmark: upload once, run many times, fetch. */
 int cs_batch_upload(cs_ctx *ctx, const uint8_t *imgs, int n_frames, int width, int height, int stride, int channels,
                     const double *T_wc, const double *boxes, const int32_t *box_offsets, const double *lines,
                     const int32_t *line_offsets, const cs_cuboid_params *params);
+/* same, online mode: no input lines, cs_batch_run detects them first (as cs_detect_frames_batch) */
+int cs_batch_upload_online(cs_ctx *ctx, const uint8_t *imgs, int n_frames, int width, int height, int stride, int channels,
+                           const double *T_wc, const double *boxes, const int32_t *box_offsets,
+                           const cs_line_params *line_params, const cs_cuboid_params *params);
 int cs_batch_run(cs_ctx *ctx);                       /* host-side sampling tables + every kernel; synchronous */
 int cs_batch_run_async(cs_ctx *ctx);                 /* same, returns after enqueueing on the context stream */
 int cs_batch_fetch(cs_ctx *ctx, cs_cuboid_rec *out, int32_t *out_counts);
@@ -155,7 +167,7 @@ int cs_batch_stats_get(cs_ctx *ctx, cs_batch_stats *stats);
 int cs_batch_device_records(cs_ctx *ctx, void **dev_ptr, size_t *n_bytes);
 /* raw CUDA stream of the context (cudaStream_t) so callers can time with events on it */
 void *cs_stream(cs_ctx *ctx);
-/* milliseconds spent in the named stage of the last cs_batch_run ("gray","canny","hyst","dt","lines","sweep","fuse","total") */
+/* milliseconds spent in the named stage of the last cs_batch_run ("lsd","gray","canny","hyst","dt","lines","sweep","fuse","total") */
 int cs_stage_ms(cs_ctx *ctx, const char *stage, float *ms);
 /* enable per-stage CUDA-event timing (adds event records only) */
 int cs_set_profiling(cs_ctx *ctx, int enable);

@@ -116,3 +116,33 @@ def test_object_slam_sequence_parity(det, oracle, fixture_b):
                 o += 1
     assert n_checked >= 45  # 51 of the 58 frames carry a box
     ctx.close()
+
+
+def test_online_batch_equals_two_calls(det, oracle):
+    """cs_detect_frames_batch (lines stay on the device) == cs_detect_lines_batch followed by cs_detect_cuboids_batch."""
+    import cube_slam_b200 as cs
+    from cube_slam_b200 import synthetic as S
+    F = 5
+    imgs, Ts, boxes, _, K = S.make_batch(51, F, 640, 480, 3, poisson=True)
+    ctx = cs.Context(0, 640, 480, F, 16, 2048)
+    ctx.set_calibration(K)
+    p = cs.default_params(max_cuboid_num=2)
+    lp = det.params()
+    out1, cnt1 = ctx.detect_frames_host(imgs, Ts, boxes, lp, p)
+    out1, cnt1 = out1.copy(), cnt1.copy()
+    lines = det.detect_filter_lines_batch(imgs)
+    out2, cnt2 = ctx.detect_batch_host(imgs, Ts, boxes, [l.astype(np.float64) for l in lines], p)
+    np.testing.assert_array_equal(cnt1, cnt2)
+    assert out1.tobytes() == out2.tobytes()
+    # and both equal the oracle's two-stage result
+    o = 0
+    for f in range(F):
+        rl = oracle.lsd_detect(imgs[f], float(lp.line_length_thres))["lines"].astype(np.float64)
+        ref = oracle.detect_cuboid(imgs[f], K, Ts[f], boxes[f], rl, oracle.default_params(max_cuboid_num=2))
+        for b in range(len(boxes[f])):
+            assert cnt1[o] == len(ref["cuboids"][b])
+            for k in range(cnt1[o]):
+                assert int(out1[o, k]["proposal_index"]) == int(ref["cuboids"][b][k]["proposal_index"])
+                assert abs(float(out1[o, k]["normalized_error"]) - float(ref["cuboids"][b][k]["normalized_error"])) < 1e-9
+            o += 1
+    ctx.close()
