@@ -58,6 +58,9 @@ struct cs_ctx {
     std::vector<CsJob> jobs;
     std::vector<CsObj> objs;
     std::vector<int2> sweep_blocks;
+    std::vector<int4> sweep_blocks4; /* warp sweep: (job, pose, first yaw, yaws in block) */
+    int max_n_cand = 0;
+    int use_cta_select = 0; /* debug: force the CTA-wide sweep / selection kernels */
     std::vector<int32_t> dt_ids, tile_job;
     int64_t total_px = 0, total_cand = 0, total_bits = 0;
     int n_tiles = 0, max_plane_words = 0, max_dpitch = 0, max_roi_h = 0;
@@ -66,7 +69,7 @@ struct cs_ctx {
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
 
     /* device buffers (grow only) */
-    DevBuf d_img, d_gray, d_lines, d_frames, d_poses, d_yaws, d_jobs, d_objs, d_blocks, d_dtids, d_tilejob;
+    DevBuf d_img, d_gray, d_lines, d_frames, d_poses, d_yaws, d_jobs, d_objs, d_blocks, d_blocks4, d_dtids, d_tilejob;
     DevBuf d_bits, d_dist, d_mlines, d_lcounts, d_err;
     DevBuf d_cvalid, d_cdist, d_cangle, d_vlist, d_key, d_idx, d_flag, d_keep, d_norm, d_score, d_jcounts;
     DevBuf d_out, d_outcnt, d_gather;
@@ -162,6 +165,8 @@ int build_tables(cs_ctx *c)
     c->jobs.clear();
     c->objs.clear();
     c->sweep_blocks.clear();
+    c->sweep_blocks4.clear();
+    c->max_n_cand = 0;
     c->total_px = 0;
     c->total_cand = 0;
     c->total_bits = 0;
@@ -292,7 +297,12 @@ int build_tables(cs_ctx *c)
                 jb.tiles_x = (jb.roi_w + 31) / 32;
                 c->n_tiles += jb.tiles_x * ((jb.roi_h + 31) / 32);
                 const int job_id = (int)c->jobs.size();
-                for (int ps = 0; ps < fr.n_pose; ps++) c->sweep_blocks.push_back(make_int2(job_id, ps));
+                for (int ps = 0; ps < fr.n_pose; ps++) {
+                    c->sweep_blocks.push_back(make_int2(job_id, ps));
+                    const int ypb = cs_sweep_warp_yaws();
+                    for (int y0 = 0; y0 < fr.n_yaw; y0 += ypb) c->sweep_blocks4.push_back(make_int4(job_id, ps, y0, std::min(ypb, fr.n_yaw - y0)));
+                }
+                c->max_n_cand = std::max(c->max_n_cand, jb.n_cand);
                 c->jobs.push_back(jb);
             }
             ob.n_jobs = (int32_t)c->jobs.size() - ob.job_off;
@@ -352,6 +362,7 @@ int prepare_tables(cs_ctx *c)
     if ((rc = upload(c, c->d_jobs, c->jobs))) return rc;
     if ((rc = upload(c, c->d_objs, c->objs))) return rc;
     if ((rc = upload(c, c->d_blocks, c->sweep_blocks))) return rc;
+    if ((rc = upload(c, c->d_blocks4, c->sweep_blocks4))) return rc;
     if ((rc = upload(c, c->d_dtids, c->dt_ids))) return rc;
     if ((rc = upload(c, c->d_tilejob, c->tile_job))) return rc;
     return CS_OK;
@@ -409,15 +420,27 @@ int run_batch(cs_ctx *c, bool sync)
     mark(ST_LINES);
     cudaStreamWaitEvent(st, c->ev_join, 0); /* join */
     mark(ST_SWEEP);
-    cs_launch_sweep((const CsJob *)c->d_jobs.p, (const CsFrame *)c->d_frames.p, (const CsPose *)c->d_poses.p, (const double *)c->d_yaws.p,
-                    (const int2 *)c->d_blocks.p, (int)c->sweep_blocks.size(), (const double *)c->d_mlines.p, (const int32_t *)c->d_lcounts.p,
-                    (const float *)c->d_dist.p, (uint8_t *)c->d_cvalid.p, (double *)c->d_cdist.p, (double *)c->d_cangle.p, &c->prm, st, &c->launches);
+    if (!c->use_cta_select)
+        cs_launch_sweep_warp((const CsJob *)c->d_jobs.p, (const CsFrame *)c->d_frames.p, (const CsPose *)c->d_poses.p, (const double *)c->d_yaws.p,
+                             (const int4 *)c->d_blocks4.p, (int)c->sweep_blocks4.size(), (const double *)c->d_mlines.p, (const int32_t *)c->d_lcounts.p,
+                             (const float *)c->d_dist.p, (uint8_t *)c->d_cvalid.p, (double *)c->d_cdist.p, (double *)c->d_cangle.p, &c->prm, st,
+                             &c->launches);
+    else
+        cs_launch_sweep((const CsJob *)c->d_jobs.p, (const CsFrame *)c->d_frames.p, (const CsPose *)c->d_poses.p, (const double *)c->d_yaws.p,
+                        (const int2 *)c->d_blocks.p, (int)c->sweep_blocks.size(), (const double *)c->d_mlines.p, (const int32_t *)c->d_lcounts.p,
+                        (const float *)c->d_dist.p, (uint8_t *)c->d_cvalid.p, (double *)c->d_cdist.p, (double *)c->d_cangle.p, &c->prm, st, &c->launches);
     mark(ST_FUSE);
-    cs_launch_fuse((const CsObj *)c->d_objs.p, n_objs, (const CsJob *)c->d_jobs.p, (const CsFrame *)c->d_frames.p, (const CsPose *)c->d_poses.p,
-                   (const double *)c->d_yaws.p, (const uint8_t *)c->d_cvalid.p, (const double *)c->d_cdist.p, (const double *)c->d_cangle.p,
-                   (int32_t *)c->d_vlist.p, (uint64_t *)c->d_key.p, (uint32_t *)c->d_idx.p, (uint8_t *)c->d_flag.p, (int32_t *)c->d_keep.p,
-                   (double *)c->d_norm.p, (double *)c->d_score.p, (int32_t *)c->d_jcounts.p, (cs_cuboid_rec *)c->d_out.p, (int32_t *)c->d_outcnt.p,
-                   c->topk, &c->prm, st, &c->launches);
+    if (!c->use_cta_select && c->max_n_cand <= cs_fuse_warp_cap())
+        cs_launch_fuse_warp((const CsObj *)c->d_objs.p, n_objs, (const CsJob *)c->d_jobs.p, (const CsFrame *)c->d_frames.p, (const CsPose *)c->d_poses.p,
+                            (const double *)c->d_yaws.p, (const uint8_t *)c->d_cvalid.p, (const double *)c->d_cdist.p, (const double *)c->d_cangle.p,
+                            (int32_t *)c->d_vlist.p, (int32_t *)c->d_keep.p, (double *)c->d_norm.p, (double *)c->d_score.p, (int32_t *)c->d_jcounts.p,
+                            (cs_cuboid_rec *)c->d_out.p, (int32_t *)c->d_outcnt.p, c->topk, &c->prm, st, &c->launches);
+    else
+        cs_launch_fuse((const CsObj *)c->d_objs.p, n_objs, (const CsJob *)c->d_jobs.p, (const CsFrame *)c->d_frames.p, (const CsPose *)c->d_poses.p,
+                       (const double *)c->d_yaws.p, (const uint8_t *)c->d_cvalid.p, (const double *)c->d_cdist.p, (const double *)c->d_cangle.p,
+                       (int32_t *)c->d_vlist.p, (uint64_t *)c->d_key.p, (uint32_t *)c->d_idx.p, (uint8_t *)c->d_flag.p, (int32_t *)c->d_keep.p,
+                       (double *)c->d_norm.p, (double *)c->d_score.p, (int32_t *)c->d_jcounts.p, (cs_cuboid_rec *)c->d_out.p, (int32_t *)c->d_outcnt.p,
+                       c->topk, &c->prm, st, &c->launches);
     mark(ST_COUNT);
     if (c->profiling) cudaEventRecord(c->ev_total[1], st);
     CS_CUDA(c, cudaGetLastError());
@@ -593,7 +616,7 @@ void cs_destroy(cs_ctx *c)
     cs_nccl_teardown(c);
     if (c->lsd_state) cs_lsd_destroy(c->lsd_state);
     DevBuf *all[] = {&c->d_img,   &c->d_gray,  &c->d_lines,  &c->d_frames, &c->d_poses,   &c->d_yaws, &c->d_jobs, &c->d_objs,
-                     &c->d_blocks, &c->d_dtids, &c->d_tilejob, &c->d_bits, &c->d_dist, &c->d_mlines, &c->d_lcounts, &c->d_err,
+                     &c->d_blocks, &c->d_blocks4, &c->d_dtids, &c->d_tilejob, &c->d_bits, &c->d_dist, &c->d_mlines, &c->d_lcounts, &c->d_err,
                      &c->d_cvalid, &c->d_cdist, &c->d_cangle, &c->d_vlist,  &c->d_key,     &c->d_idx,  &c->d_flag, &c->d_keep,  &c->d_norm,
                      &c->d_score,  &c->d_jcounts, &c->d_out,  &c->d_outcnt, &c->d_gather};
     for (DevBuf *b : all)
@@ -753,6 +776,7 @@ int cs_set_profiling(cs_ctx *c, int enable)
     if (!c) return CS_ERR_INVALID_ARG;
     c->profiling = (enable & 1) != 0;
     c->use_fused_dt = (enable & 4) != 0; /* bit 2: experimental fused hysteresis + wavefront-DT kernel */
+    c->use_cta_select = (enable & 8) != 0; /* bit 3: CTA-wide sweep / selection kernels (the general path) instead of the warp ones */
     return CS_OK;
 }
 

@@ -565,6 +565,370 @@ __global__ void __launch_bounds__(FU_THREADS) k_fuse_rank(const CsObj *__restric
     if (tid == 0) out_counts[blockIdx.x] = n_out;
 }
 
+
+/* ==========================================================================================
+ * Warp-centric variants (the default when they apply).  The batch holds only ~10^5 candidates, so the CTA-wide
+ * kernels above spend most of their time at __syncthreads; here one warp owns an independent unit of work and only
+ * __syncwarp is used.
+ * ========================================================================================== */
+#define SWW_WARPS 4
+
+struct SweepWarpShared {
+    double ang[CS_MAXL_OUT], midx[CS_MAXL_OUT], midy[CS_MAXL_OUT];
+    double vp_angles[SWW_WARPS][6];
+    D2 vps[SWW_WARPS][3];
+};
+
+/* one warp per (ROI job, pose, yaw): VP support by the warp, then one lane per (top-x, config) candidate does the FP64
+ * corner chain and, if valid, both error terms -- no block barrier after the line set is staged */
+__global__ void __launch_bounds__(32 * SWW_WARPS) k_sweep_warp(const CsJob *__restrict__ jobs, const CsFrame *__restrict__ frames,
+                                                               const CsPose *__restrict__ poses, const double *__restrict__ yaw_table,
+                                                               const int4 *__restrict__ blocks /* (job, pose, yaw0, n) */,
+                                                               const double *__restrict__ merged_lines, const int32_t *__restrict__ line_counts,
+                                                               const float *__restrict__ dist_arena, uint8_t *__restrict__ c_valid,
+                                                               double *__restrict__ c_dist, double *__restrict__ c_angle, cs_cuboid_params prm)
+{
+    __shared__ SweepWarpShared S;
+    const int4 bk = blocks[blockIdx.x];
+    const CsJob &jb = jobs[bk.x];
+    const CsFrame &fr = frames[jb.frame];
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const int n_lines = line_counts[bk.x * 2 + 1];
+    {
+        const double *ml = merged_lines + (size_t)bk.x * CS_MAXL_OUT * 7;
+        for (int i = tid; i < n_lines; i += 32 * SWW_WARPS) {
+            S.ang[i] = ml[4 * CS_MAXL_OUT + i];
+            S.midx[i] = ml[5 * CS_MAXL_OUT + i];
+            S.midy[i] = ml[6 * CS_MAXL_OUT + i];
+        }
+    }
+    __syncthreads();
+    if (wid >= bk.w) return;
+    const int yi = bk.z + wid;
+    const int n_top = jb.n_top, n_yaw = fr.n_yaw;
+    if (lane == 0) g_vanishing_points(poses[fr.pose_off + bk.y].KinvR, yaw_table[fr.yaw_off + yi], S.vps[wid]);
+    __syncwarp();
+    /* VP_support_edge_infos: three reductions over the line set */
+    {
+        /* vp_support_warp expects a SweepShared-like object with ang/midx/midy: the first three arrays of S match */
+        const SweepShared &SS = *reinterpret_cast<const SweepShared *>(&S);
+        for (int vp_id = 0; vp_id < 3; vp_id++) {
+            const double thre = ((vp_id != 2) ? prm.vp12_edge_angle_thre : prm.vp3_edge_angle_thre) / 180.0 * CS_PI;
+            if (n_lines > 0)
+                vp_support_warp(SS, n_lines, S.vps[wid][vp_id], thre, vp_id, &S.vp_angles[wid][vp_id * 2]);
+            else if (lane == 0) {
+                S.vp_angles[wid][vp_id * 2] = nan("");
+                S.vp_angles[wid][vp_id * 2 + 1] = nan("");
+            }
+        }
+    }
+    __syncwarp();
+    const float *dist = dist_arena + jb.px_off;
+    const int64_t cbase = jb.cand_off + ((int64_t)bk.y * n_yaw + yi) * n_top * 2;
+    const bool cfg1 = prm.consider_config_1 != 0, cfg2 = prm.consider_config_2 != 0;
+    for (int c0 = 0; c0 < n_top * 2; c0 += 32) {
+        const int ci = c0 + lane;
+        if (ci < n_top * 2) {
+            const int ti = ci >> 1, config_id = (ci & 1) + 1;
+            D2 c[8];
+            int vp1pos;
+            bool valid = false;
+            if ((config_id == 1) ? cfg1 : cfg2) valid = g_build_corners(jb, S.vps[wid], g_top_x(jb, ti), config_id, prm.shorted_edge_thre, c, vp1pos);
+            c_valid[cbase + ci] = valid ? 1 : 0;
+            if (valid) {
+                const double sum_dist = g_edge_sum_dists(dist, jb.dpitch, jb.roi_w, jb.roi_h, c, (double)jb.roi_l, (double)jb.roi_t, config_id,
+                                                         prm.reweight_edge_distance != 0);
+                c_dist[cbase + ci] = sum_dist / jb.diag;
+                c_angle[cbase + ci] = g_angle_error(S.vp_angles[wid], config_id, c);
+            }
+        }
+    }
+}
+
+/* ---- selection, one warp per 2D box (all valid counts <= FW_CAP) ---- */
+#define FW_CAP 1024
+#define FW_WARPS 2
+
+struct FuseWarpShared {
+    uint64_t key[FW_CAP];
+    uint16_t idx[FW_CAP];
+    uint16_t vlist[FW_CAP];
+    uint16_t keep[FW_CAP];
+    uint8_t flag[FW_CAP];
+};
+
+__device__ __forceinline__ void warp_bitonic(uint64_t *key, uint16_t *idx, int P)
+{
+    const int lane = threadIdx.x & 31;
+    for (int k = 2; k <= P; k <<= 1)
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            __syncwarp();
+            for (int i = lane; i < P; i += 32) {
+                const int l = i ^ j;
+                if (l > i) {
+                    const uint64_t ki = key[i], kl = key[l];
+                    const uint16_t ii = idx[i], il = idx[l];
+                    const bool gt = (ki > kl) || (ki == kl && ii > il);
+                    const bool up = ((i & k) == 0);
+                    if (gt == up) {
+                        key[i] = kl;
+                        key[l] = ki;
+                        idx[i] = il;
+                        idx[l] = ii;
+                    }
+                }
+            }
+        }
+    __syncwarp();
+}
+
+__device__ __forceinline__ double warp_min_d(double v)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = g_min(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+__device__ __forceinline__ double warp_max_d(double v)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = g_max(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+
+/* scale (half sizes) of a lifted proposal only: what the ranking needs (object_3d_util.cpp:615-625) */
+__device__ __forceinline__ void g_lift_scale(const D2 *c, const double *ground, const double *T, const double *invK, double *scale)
+{
+    double g[4][3];
+    for (int i = 0; i < 4; i++) g_plane_hit(T, invK, ground, c[4 + i], g[i]);
+    double dx = g[0][0] - g[3][0], dy = g[0][1] - g[3][1], dz = g[0][2] - g[3][2];
+    scale[0] = sqrt((dx * dx + dy * dy) + dz * dz) / 2;
+    dx = g[0][0] - g[1][0];
+    dy = g[0][1] - g[1][1];
+    dz = g[0][2] - g[1][2];
+    scale[1] = sqrt((dx * dx + dy * dy) + dz * dz) / 2;
+    double nrm[3] = {dy * 1.0 - dz * 0.0, dz * 0.0 - dx * 1.0, dx * 0.0 - dy * 0.0};
+    const double nn = sqrt((nrm[0] * nrm[0] + nrm[1] * nrm[1]) + nrm[2] * nrm[2]);
+    for (int i = 0; i < 3; i++) nrm[i] /= nn;
+    const double dist = -((nrm[0] * g[0][0] + nrm[1] * g[0][1]) + nrm[2] * g[0][2]);
+    double pw[4] = {nrm[0], nrm[1], nrm[2], dist};
+    if (dist < 0)
+        for (int i = 0; i < 4; i++) pw[i] = -pw[i];
+    double ps[4];
+    for (int i = 0; i < 4; i++) ps[i] = ((T[0 * 4 + i] * pw[0] + T[1 * 4 + i] * pw[1]) + T[2 * 4 + i] * pw[2]) + T[3 * 4 + i] * pw[3];
+    double top[3];
+    g_plane_hit(T, invK, ps, c[1], top);
+    scale[2] = top[2] / 2;
+}
+
+extern __shared__ unsigned char fw_smem_raw[];
+
+__global__ void __launch_bounds__(32 * FW_WARPS) k_fuse_warp(const CsObj *__restrict__ objs, int n_objs, const CsJob *__restrict__ jobs,
+                                                             const CsFrame *__restrict__ frames, const CsPose *__restrict__ poses,
+                                                             const double *__restrict__ yaw_table, const uint8_t *__restrict__ c_valid,
+                                                             const double *__restrict__ c_dist, const double *__restrict__ c_angle,
+                                                             int32_t *__restrict__ w_vlist, int32_t *__restrict__ w_keep, double *__restrict__ w_norm,
+                                                             double *__restrict__ w_score, int32_t *__restrict__ job_counts,
+                                                             cs_cuboid_rec *__restrict__ out, int32_t *__restrict__ out_counts, int topk,
+                                                             cs_cuboid_params prm)
+{
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int oi = blockIdx.x * FW_WARPS + wid;
+    if (oi >= n_objs) return;
+    FuseWarpShared &S = reinterpret_cast<FuseWarpShared *>(fw_smem_raw)[wid];
+    const unsigned FULL = 0xffffffffu;
+    const CsObj ob = objs[oi];
+    const CsFrame &fr = frames[ob.frame];
+
+    for (int jj = 0; jj < ob.n_jobs; jj++) {
+        const int job = ob.job_off + jj;
+        const CsJob &jb = jobs[job];
+        const int64_t co = jb.cand_off;
+        /* 1. valid proposals in enumeration order */
+        int n = 0;
+        for (int base = 0; base < jb.n_cand; base += 32) {
+            const int i = base + lane;
+            const bool v = (i < jb.n_cand) && c_valid[co + i];
+            const unsigned m = __ballot_sync(FULL, v);
+            if (v) S.vlist[n + __popc(m & ((1u << lane) - 1u))] = (uint16_t)i;
+            n += __popc(m);
+        }
+        __syncwarp();
+        int n_keep = 0;
+        /* 2. fuse_normalize_scores_v2 */
+        if (n > 4) {
+            const int bn = (int)round((double)((float)n) / 3.0 * 2.0);
+            int P = 1;
+            while (P < n) P <<= 1;
+            for (int i = lane; i < P; i += 32) {
+                S.key[i] = (i < n) ? sort_key(c_dist[co + S.vlist[i]]) : ~0ull;
+                S.idx[i] = (i < n) ? (uint16_t)i : (uint16_t)0xffff;
+            }
+            warp_bitonic(S.key, S.idx, P);
+            for (int i = lane; i < n; i += 32) S.flag[i] = 0;
+            __syncwarp();
+            for (int i = lane; i < bn - 1; i += 32) {
+                S.flag[S.idx[i]] = 1;
+                S.keep[i] = S.idx[i];
+            }
+            __syncwarp();
+            for (int i = lane; i < P; i += 32) {
+                S.key[i] = (i < n) ? sort_key(c_angle[co + S.vlist[i]]) : ~0ull;
+                S.idx[i] = (i < n) ? (uint16_t)i : (uint16_t)0xffff;
+            }
+            warp_bitonic(S.key, S.idx, P);
+            const double a1 = c_angle[co + S.vlist[S.idx[bn - 1]]], a2 = c_angle[co + S.vlist[S.idx[bn - 2]]];
+            if (a1 > a2) {
+                for (int i = lane; i < bn - 1; i += 32) S.flag[S.idx[i]] |= 2;
+                __syncwarp();
+                int cnt = 0;
+                for (int base = 0; base < n; base += 32) {
+                    const int i = base + lane;
+                    const bool v = (i < n) && (S.flag[i] == 3);
+                    const unsigned m = __ballot_sync(FULL, v);
+                    if (v) S.keep[cnt + __popc(m & ((1u << lane) - 1u))] = (uint16_t)i;
+                    cnt += __popc(m);
+                }
+                n_keep = cnt;
+            } else
+                n_keep = bn - 1;
+            __syncwarp();
+        } else {
+            for (int i = lane; i < n; i += 32) S.keep[i] = (uint16_t)i;
+            n_keep = n;
+            __syncwarp();
+        }
+        double mn_d = 1e6, mx_d = -1, mn_a = 1e6, mx_a = -1;
+        for (int i = lane; i < n_keep; i += 32) {
+            const int cand = S.vlist[S.keep[i]];
+            const double td = c_dist[co + cand], ta = c_angle[co + cand];
+            mn_d = g_min(mn_d, td);
+            mx_d = g_max(mx_d, td);
+            mn_a = g_min(mn_a, ta);
+            mx_a = g_max(mx_a, ta);
+        }
+        mn_d = warp_min_d(mn_d);
+        mx_d = warp_max_d(mx_d);
+        mn_a = warp_min_d(mn_a);
+        mx_a = warp_max_d(mx_a);
+        /* 3. normalised score + skew penalty per kept proposal */
+        for (int i = lane; i < n_keep; i += 32) {
+            const int raw = S.keep[i];
+            const int cand = S.vlist[raw];
+            const double dk = c_dist[co + cand];
+            double ak = c_angle[co + cand];
+            double comb;
+            if (prm.whether_normalize_two_errors && n_keep > 1) {
+                comb = (dk - mn_d) / (mx_d - mn_d);
+                if ((mx_a - mn_a) > 0) ak = (ak - mn_a) / (mx_a - mn_a);
+                comb = (comb + prm.weight_vp_angle * ak) / (1 + prm.weight_vp_angle);
+            } else
+                comb = (dk + prm.weight_vp_angle * ak) / (1 + prm.weight_vp_angle);
+            D2 c[8];
+            int vp1pos, config_id, pose_id, top_id;
+            double yaw;
+            rebuild_corners(jb, fr, poses, yaw_table, prm, cand, c, vp1pos, config_id, yaw, pose_id, top_id);
+            const CsPose &ps = poses[fr.pose_off + pose_id];
+            double sc3[3];
+            g_lift_scale(c, ps.ground, ps.T, fr.invK, sc3);
+            double sc;
+            if (sc3[0] < 0 || sc3[1] < 0 || sc3[2] < 0)
+                sc = nan("");
+            else {
+                const double skew_ratio = g_max(sc3[0], sc3[1]) / g_min(sc3[0], sc3[1]);
+                double skew_error = prm.weight_skew_error * g_max(skew_ratio - prm.nominal_skew_ratio, 0.0);
+                if (skew_ratio > prm.max_cut_skew) skew_error = 100;
+                sc = comb + prm.weight_skew_error * skew_error;
+                if (isnan(sc)) sc = __longlong_as_double(0x7ff0000000000000ll);
+            }
+            w_score[co + i] = sc;
+            w_norm[co + i] = comb;
+            w_keep[co + i] = raw;
+            w_vlist[co + i] = cand; /* NOTE: indexed by kept position here (the CTA kernel indexes by valid row) */
+        }
+        if (lane == 0) {
+            job_counts[job * 2 + 0] = n;
+            job_counts[job * 2 + 1] = n_keep;
+        }
+        __syncwarp();
+    }
+    __threadfence_block();
+    __syncwarp();
+    /* 4. final ranking: K rounds of arg-min by (score, position) */
+    const int K = min(topk, CS_MAX_TOPK);
+    long long chosen[CS_MAX_TOPK];
+    int n_out = 0;
+    for (int round = 0; round < K; round++) {
+        double bv = 0;
+        long long bp = -1;
+        for (int jj = 0; jj < ob.n_jobs; jj++) {
+            const int job = ob.job_off + jj;
+            const int64_t co = jobs[job].cand_off;
+            const int nk = job_counts[job * 2 + 1];
+            for (int i = lane; i < nk; i += 32) {
+                const double sc = w_score[co + i];
+                if (isnan(sc)) continue;
+                const long long p = ((long long)jj << 32) | (long long)i;
+                bool taken = false;
+                for (int r = 0; r < round; r++) taken |= (chosen[r] == p);
+                if (taken) continue;
+                if (bp < 0 || sc < bv || (sc == bv && p < bp)) {
+                    bv = sc;
+                    bp = p;
+                }
+            }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const double ov = __shfl_xor_sync(FULL, bv, o);
+            const long long op = __shfl_xor_sync(FULL, bp, o);
+            if (op >= 0 && (bp < 0 || ov < bv || (ov == bv && op < bp))) {
+                bv = ov;
+                bp = op;
+            }
+        }
+        chosen[round] = bp;
+        if (bp < 0) break;
+        n_out++;
+        if (lane == 0) {
+            const int jj = (int)(bp >> 32), i = (int)(bp & 0xffffffffll);
+            const int job = ob.job_off + jj;
+            const CsJob &jb = jobs[job];
+            const int64_t co = jb.cand_off;
+            const int raw = w_keep[co + i];
+            const int cand = w_vlist[co + i];
+            D2 c[8];
+            int vp1pos, config_id, pose_id, top_id;
+            double yaw;
+            rebuild_corners(jb, fr, poses, yaw_table, prm, cand, c, vp1pos, config_id, yaw, pose_id, top_id);
+            cs_cuboid_rec &o = out[(size_t)oi * topk + round];
+            const CsPose &ps = poses[fr.pose_off + pose_id];
+            g_lift_to_3d(c, (double)config_id, (double)vp1pos, yaw, ps.ground, ps.T, fr.invK, o);
+            o.rect_detect_2d[0] = ob.left;
+            o.rect_detect_2d[1] = ob.top;
+            o.rect_detect_2d[2] = ob.width_raw;
+            o.rect_detect_2d[3] = ob.height_raw;
+            o.edge_distance_error = c_dist[co + cand];
+            o.edge_angle_error = c_angle[co + cand];
+            o.normalized_error = w_norm[co + i];
+            o.skew_ratio = g_max(o.scale[0], o.scale[1]) / g_min(o.scale[0], o.scale[1]);
+            o.down_expand_height = (double)jb.down_expand;
+            if (prm.whether_sample_cam_roll_pitch) {
+                o.camera_roll_delta = ps.roll - fr.euler_raw[0];
+                o.camera_pitch_delta = ps.pitch - fr.euler_raw[1];
+            } else {
+                o.camera_roll_delta = 0;
+                o.camera_pitch_delta = 0;
+            }
+            o.combined_score = w_score[co + i];
+            o.proposal_index = raw;
+            o.height_sample_id = jb.hs;
+            o.valid = 1;
+            o.pad_ = 0;
+        }
+    }
+    if (lane == 0) out_counts[oi] = n_out;
+}
+
 /* ------------------------------------------------------------------------------------------ launchers */
 void cs_launch_sweep(const CsJob *d_jobs, const CsFrame *d_frames, const CsPose *d_poses, const double *d_yaw, const int2 *d_blocks,
                      int n_blocks, const double *d_mlines, const int32_t *d_line_counts, const float *d_dist, uint8_t *c_valid, double *c_dist,
@@ -595,5 +959,36 @@ void cs_launch_fuse(const CsObj *d_objs, int n_objs, const CsJob *d_jobs, const 
     }
     k_fuse_rank<<<n_objs, FU_THREADS, smem, st>>>(d_objs, d_jobs, d_frames, d_poses, d_yaw, c_valid, c_dist, c_angle, w_vlist, w_key, w_idx, w_flag,
                                                   w_keep, w_norm, w_score, job_counts, d_out, d_out_counts, topk, *prm);
+    (*launches)++;
+}
+
+void cs_launch_sweep_warp(const CsJob *d_jobs, const CsFrame *d_frames, const CsPose *d_poses, const double *d_yaw, const int4 *d_blocks,
+                          int n_blocks, const double *d_mlines, const int32_t *d_line_counts, const float *d_dist, uint8_t *c_valid,
+                          double *c_dist, double *c_angle, const cs_cuboid_params *prm, cudaStream_t st, int64_t *launches)
+{
+    if (n_blocks <= 0) return;
+    k_sweep_warp<<<n_blocks, 32 * SWW_WARPS, 0, st>>>(d_jobs, d_frames, d_poses, d_yaw, d_blocks, d_mlines, d_line_counts, d_dist, c_valid, c_dist,
+                                                      c_angle, *prm);
+    (*launches)++;
+}
+
+int cs_fuse_warp_cap(void) { return FW_CAP; }
+int cs_sweep_warp_yaws(void) { return SWW_WARPS; }
+
+void cs_launch_fuse_warp(const CsObj *d_objs, int n_objs, const CsJob *d_jobs, const CsFrame *d_frames, const CsPose *d_poses, const double *d_yaw,
+                         const uint8_t *c_valid, const double *c_dist, const double *c_angle, int32_t *w_vlist, int32_t *w_keep, double *w_norm,
+                         double *w_score, int32_t *job_counts, cs_cuboid_rec *d_out, int32_t *d_out_counts, int topk, const cs_cuboid_params *prm,
+                         cudaStream_t st, int64_t *launches)
+{
+    if (n_objs <= 0) return;
+    const size_t smem = sizeof(FuseWarpShared) * FW_WARPS;
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaFuncSetAttribute(k_fuse_warp, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        attr_set = true;
+    }
+    k_fuse_warp<<<(n_objs + FW_WARPS - 1) / FW_WARPS, 32 * FW_WARPS, smem, st>>>(d_objs, n_objs, d_jobs, d_frames, d_poses, d_yaw, c_valid, c_dist,
+                                                                                 c_angle, w_vlist, w_keep, w_norm, w_score, job_counts, d_out,
+                                                                                 d_out_counts, topk, *prm);
     (*launches)++;
 }

@@ -112,6 +112,8 @@ def test_synthetic_batch_matches_oracle(cs, oracle, seed, w, h, kind, nb):
     ctx.set_calibration(K)
     if seed == 12:
         ctx.L.cs_set_profiling(ctx.h, 4)  # one case through the fused wavefront kernel
+    if seed == 11:
+        ctx.L.cs_set_profiling(ctx.h, 8)  # one case through the CTA-wide sweep / selection kernels
     p = cs.default_params(max_cuboid_num=3)
     out, counts = ctx.detect_batch_host(imgs, Ts, boxes, lines, p)
     st = ctx.stats()
