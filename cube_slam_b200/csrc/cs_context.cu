@@ -71,7 +71,7 @@ struct cs_ctx {
     /* device buffers (grow only) */
     DevBuf d_img, d_gray, d_lines, d_frames, d_poses, d_yaws, d_jobs, d_objs, d_blocks, d_blocks4, d_dtids, d_tilejob;
     DevBuf d_bits, d_dist, d_mlines, d_lcounts, d_err;
-    DevBuf d_cvalid, d_cdist, d_cangle, d_vlist, d_key, d_idx, d_flag, d_keep, d_norm, d_score, d_jcounts;
+    DevBuf d_cvalid, d_cdist, d_cangle, d_cskew, d_vlist, d_key, d_idx, d_flag, d_keep, d_norm, d_score, d_jcounts;
     DevBuf d_out, d_outcnt, d_gather;
     void *pinned = nullptr;
     size_t pinned_cap = 0;
@@ -336,6 +336,7 @@ int alloc_work(cs_cuboid_params &, cs_ctx *c)
     if ((rc = ensure(c, c->d_cvalid, cand))) return rc;
     if ((rc = ensure(c, c->d_cdist, cand * 8))) return rc;
     if ((rc = ensure(c, c->d_cangle, cand * 8))) return rc;
+    if ((rc = ensure(c, c->d_cskew, cand * 8))) return rc;
     if ((rc = ensure(c, c->d_vlist, cand * 4))) return rc;
     if ((rc = ensure(c, c->d_key, cand * 2 * 8))) return rc;
     if ((rc = ensure(c, c->d_idx, cand * 2 * 4))) return rc;
@@ -423,8 +424,8 @@ int run_batch(cs_ctx *c, bool sync)
     if (!c->use_cta_select)
         cs_launch_sweep_warp((const CsJob *)c->d_jobs.p, (const CsFrame *)c->d_frames.p, (const CsPose *)c->d_poses.p, (const double *)c->d_yaws.p,
                              (const int4 *)c->d_blocks4.p, (int)c->sweep_blocks4.size(), (const double *)c->d_mlines.p, (const int32_t *)c->d_lcounts.p,
-                             (const float *)c->d_dist.p, (uint8_t *)c->d_cvalid.p, (double *)c->d_cdist.p, (double *)c->d_cangle.p, &c->prm, st,
-                             &c->launches);
+                             (const float *)c->d_dist.p, (uint8_t *)c->d_cvalid.p, (double *)c->d_cdist.p, (double *)c->d_cangle.p, (double *)c->d_cskew.p, &c->prm,
+                             st, &c->launches);
     else
         cs_launch_sweep((const CsJob *)c->d_jobs.p, (const CsFrame *)c->d_frames.p, (const CsPose *)c->d_poses.p, (const double *)c->d_yaws.p,
                         (const int2 *)c->d_blocks.p, (int)c->sweep_blocks.size(), (const double *)c->d_mlines.p, (const int32_t *)c->d_lcounts.p,
@@ -433,7 +434,7 @@ int run_batch(cs_ctx *c, bool sync)
     if (!c->use_cta_select && c->max_n_cand <= cs_fuse_warp_cap())
         cs_launch_fuse_warp((const CsObj *)c->d_objs.p, n_objs, (const CsJob *)c->d_jobs.p, (const CsFrame *)c->d_frames.p, (const CsPose *)c->d_poses.p,
                             (const double *)c->d_yaws.p, (const uint8_t *)c->d_cvalid.p, (const double *)c->d_cdist.p, (const double *)c->d_cangle.p,
-                            (int32_t *)c->d_vlist.p, (int32_t *)c->d_keep.p, (double *)c->d_norm.p, (double *)c->d_score.p, (int32_t *)c->d_jcounts.p,
+                            (const double *)c->d_cskew.p, (int32_t *)c->d_vlist.p, (int32_t *)c->d_keep.p, (double *)c->d_norm.p, (double *)c->d_score.p, (int32_t *)c->d_jcounts.p,
                             (cs_cuboid_rec *)c->d_out.p, (int32_t *)c->d_outcnt.p, c->topk, &c->prm, st, &c->launches);
     else
         cs_launch_fuse((const CsObj *)c->d_objs.p, n_objs, (const CsJob *)c->d_jobs.p, (const CsFrame *)c->d_frames.p, (const CsPose *)c->d_poses.p,
@@ -617,7 +618,7 @@ void cs_destroy(cs_ctx *c)
     if (c->lsd_state) cs_lsd_destroy(c->lsd_state);
     DevBuf *all[] = {&c->d_img,   &c->d_gray,  &c->d_lines,  &c->d_frames, &c->d_poses,   &c->d_yaws, &c->d_jobs, &c->d_objs,
                      &c->d_blocks, &c->d_blocks4, &c->d_dtids, &c->d_tilejob, &c->d_bits, &c->d_dist, &c->d_mlines, &c->d_lcounts, &c->d_err,
-                     &c->d_cvalid, &c->d_cdist, &c->d_cangle, &c->d_vlist,  &c->d_key,     &c->d_idx,  &c->d_flag, &c->d_keep,  &c->d_norm,
+                     &c->d_cvalid, &c->d_cdist, &c->d_cangle, &c->d_cskew, &c->d_vlist,  &c->d_key,     &c->d_idx,  &c->d_flag, &c->d_keep,  &c->d_norm,
                      &c->d_score,  &c->d_jcounts, &c->d_out,  &c->d_outcnt, &c->d_gather};
     for (DevBuf *b : all)
         if (b->p) cudaFree(b->p);

@@ -35,11 +35,11 @@ void cs_launch_fuse(const CsObj *d_objs, int n_objs, const CsJob *d_jobs, const 
 
 void cs_launch_sweep_warp(const CsJob *d_jobs, const CsFrame *d_frames, const CsPose *d_poses, const double *d_yaw, const int4 *d_blocks,
                           int n_blocks, const double *d_mlines, const int32_t *d_line_counts, const float *d_dist, uint8_t *c_valid,
-                          double *c_dist, double *c_angle, const cs_cuboid_params *prm, cudaStream_t st, int64_t *launches);
+                          double *c_dist, double *c_angle, double *c_skew, const cs_cuboid_params *prm, cudaStream_t st, int64_t *launches);
 void cs_launch_fuse_warp(const CsObj *d_objs, int n_objs, const CsJob *d_jobs, const CsFrame *d_frames, const CsPose *d_poses, const double *d_yaw,
-                         const uint8_t *c_valid, const double *c_dist, const double *c_angle, int32_t *w_vlist, int32_t *w_keep, double *w_norm,
-                         double *w_score, int32_t *job_counts, cs_cuboid_rec *d_out, int32_t *d_out_counts, int topk, const cs_cuboid_params *prm,
-                         cudaStream_t st, int64_t *launches);
+                         const uint8_t *c_valid, const double *c_dist, const double *c_angle, const double *c_skew, int32_t *w_vlist, int32_t *w_keep,
+                         double *w_norm, double *w_score, int32_t *job_counts, cs_cuboid_rec *d_out, int32_t *d_out_counts, int topk,
+                         const cs_cuboid_params *prm, cudaStream_t st, int64_t *launches);
 int cs_fuse_warp_cap(void);
 int cs_sweep_warp_yaws(void);
 

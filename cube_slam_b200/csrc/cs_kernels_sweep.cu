@@ -572,27 +572,73 @@ __global__ void __launch_bounds__(FU_THREADS) k_fuse_rank(const CsObj *__restric
  * __syncwarp is used.
  * ========================================================================================== */
 #define SWW_WARPS 4
+#define SWW_YAWS 4   /* yaws handled by one warp, one after the other */
+#define SWW_SLOTS 64
 
 struct SweepWarpShared {
     double ang[CS_MAXL_OUT], midx[CS_MAXL_OUT], midy[CS_MAXL_OUT];
-    double vp_angles[SWW_WARPS][6];
+    double vp_angles[SWW_WARPS][SWW_YAWS][6];
     D2 vps[SWW_WARPS][3];
+    D2 corners[SWW_WARPS][SWW_SLOTS][8];
+    int32_t slot_cand[SWW_WARPS][SWW_SLOTS]; /* candidate index inside the (job, pose) block */
+    int8_t slot_yaw[SWW_WARPS][SWW_SLOTS];
+    int8_t slot_cfg[SWW_WARPS][SWW_SLOTS];
 };
 
-/* one warp per (ROI job, pose, yaw): VP support by the warp, then one lane per (top-x, config) candidate does the FP64
- * corner chain and, if valid, both error terms -- no block barrier after the line set is staged */
+/* scale (half sizes) of a lifted proposal only: what the ranking needs (object_3d_util.cpp:615-625) */
+__device__ __forceinline__ void g_lift_scale(const D2 *c, const double *ground, const double *T, const double *invK, double *scale)
+{
+    double g[4][3];
+    for (int i = 0; i < 4; i++) g_plane_hit(T, invK, ground, c[4 + i], g[i]);
+    double dx = g[0][0] - g[3][0], dy = g[0][1] - g[3][1], dz = g[0][2] - g[3][2];
+    scale[0] = sqrt((dx * dx + dy * dy) + dz * dz) / 2;
+    dx = g[0][0] - g[1][0];
+    dy = g[0][1] - g[1][1];
+    dz = g[0][2] - g[1][2];
+    scale[1] = sqrt((dx * dx + dy * dy) + dz * dz) / 2;
+    double nrm[3] = {dy * 1.0 - dz * 0.0, dz * 0.0 - dx * 1.0, dx * 0.0 - dy * 0.0};
+    const double nn = sqrt((nrm[0] * nrm[0] + nrm[1] * nrm[1]) + nrm[2] * nrm[2]);
+    for (int i = 0; i < 3; i++) nrm[i] /= nn;
+    const double dist = -((nrm[0] * g[0][0] + nrm[1] * g[0][1]) + nrm[2] * g[0][2]);
+    double pw[4] = {nrm[0], nrm[1], nrm[2], dist};
+    if (dist < 0)
+        for (int i = 0; i < 4; i++) pw[i] = -pw[i];
+    double ps[4];
+    for (int i = 0; i < 4; i++) ps[i] = ((T[0 * 4 + i] * pw[0] + T[1 * 4 + i] * pw[1]) + T[2 * 4 + i] * pw[2]) + T[3 * 4 + i] * pw[3];
+    double top[3];
+    g_plane_hit(T, invK, ps, c[1], top);
+    scale[2] = top[2] / 2;
+}
+
+/* skew_ratio of the lifted cuboid, NaN when a scale is negative (the proposal is then dropped, box_proposal_detail.cpp:493) */
+__device__ __forceinline__ double g_skew_of(const D2 *c, const CsPose &ps, const double *invK)
+{
+    double sc3[3];
+    g_lift_scale(c, ps.ground, ps.T, invK, sc3);
+    if (sc3[0] < 0 || sc3[1] < 0 || sc3[2] < 0) return nan("");
+    const double r = g_max(sc3[0], sc3[1]) / g_min(sc3[0], sc3[1]);
+    return isnan(r) ? __longlong_as_double(0x7ff0000000000000ll) : r; /* NaN skew (degenerate lift) ranks as +inf, still a cuboid */
+}
+
+/* One warp per (ROI job, pose, group of SWW_YAWS yaws).  Per yaw: VP support by the warp, one lane per (top-x, config)
+ * candidate for the FP64 corner chain; valid candidates are compacted into the warp's slot list and scored 32 at a time, so
+ * the expensive part (99/77 dist-map gathers, 6 atan2, the 3D lift for the skew) runs with full lanes.  No block barrier
+ * after the line set is staged. */
 __global__ void __launch_bounds__(32 * SWW_WARPS) k_sweep_warp(const CsJob *__restrict__ jobs, const CsFrame *__restrict__ frames,
                                                                const CsPose *__restrict__ poses, const double *__restrict__ yaw_table,
                                                                const int4 *__restrict__ blocks /* (job, pose, yaw0, n) */,
                                                                const double *__restrict__ merged_lines, const int32_t *__restrict__ line_counts,
                                                                const float *__restrict__ dist_arena, uint8_t *__restrict__ c_valid,
-                                                               double *__restrict__ c_dist, double *__restrict__ c_angle, cs_cuboid_params prm)
+                                                               double *__restrict__ c_dist, double *__restrict__ c_angle,
+                                                               double *__restrict__ c_skew, cs_cuboid_params prm)
 {
     __shared__ SweepWarpShared S;
     const int4 bk = blocks[blockIdx.x];
     const CsJob &jb = jobs[bk.x];
     const CsFrame &fr = frames[jb.frame];
+    const CsPose &pose = poses[fr.pose_off + bk.y];
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const unsigned FULL = 0xffffffffu;
     const int n_lines = line_counts[bk.x * 2 + 1];
     {
         const double *ml = merged_lines + (size_t)bk.x * CS_MAXL_OUT * 7;
@@ -603,46 +649,92 @@ __global__ void __launch_bounds__(32 * SWW_WARPS) k_sweep_warp(const CsJob *__re
         }
     }
     __syncthreads();
-    if (wid >= bk.w) return;
-    const int yi = bk.z + wid;
+    const int y_first = bk.z + wid * SWW_YAWS, y_end = min(bk.z + bk.w, y_first + SWW_YAWS);
+    if (y_first >= y_end) return;
     const int n_top = jb.n_top, n_yaw = fr.n_yaw;
-    if (lane == 0) g_vanishing_points(poses[fr.pose_off + bk.y].KinvR, yaw_table[fr.yaw_off + yi], S.vps[wid]);
-    __syncwarp();
-    /* VP_support_edge_infos: three reductions over the line set */
-    {
-        /* vp_support_warp expects a SweepShared-like object with ang/midx/midy: the first three arrays of S match */
-        const SweepShared &SS = *reinterpret_cast<const SweepShared *>(&S);
+    const float *dist = dist_arena + jb.px_off;
+    const int64_t cbase = jb.cand_off + (int64_t)bk.y * n_yaw * n_top * 2;
+    const bool cfg1 = prm.consider_config_1 != 0, cfg2 = prm.consider_config_2 != 0;
+    const SweepShared &SS = *reinterpret_cast<const SweepShared *>(&S); /* ang / midx / midy share the layout */
+    int n_pending = 0;
+
+    auto score_slots = [&](int count) { /* lanes < count score slot `lane` */
+        if (lane < count) {
+            const D2 *c = S.corners[wid][lane];
+            const int cfg = S.slot_cfg[wid][lane];
+            const int64_t ci = cbase + S.slot_cand[wid][lane];
+            const double sum_dist = g_edge_sum_dists(dist, jb.dpitch, jb.roi_w, jb.roi_h, c, (double)jb.roi_l, (double)jb.roi_t, cfg,
+                                                     prm.reweight_edge_distance != 0);
+            c_dist[ci] = sum_dist / jb.diag;
+            c_angle[ci] = g_angle_error(S.vp_angles[wid][S.slot_yaw[wid][lane]], cfg, c);
+            c_skew[ci] = g_skew_of(c, pose, fr.invK);
+        }
+        __syncwarp();
+    };
+
+    for (int yy = 0; y_first + yy < y_end; yy++) {
+        const int yi = y_first + yy;
+        if (lane == 0) g_vanishing_points(pose.KinvR, yaw_table[fr.yaw_off + yi], S.vps[wid]);
+        __syncwarp();
         for (int vp_id = 0; vp_id < 3; vp_id++) {
             const double thre = ((vp_id != 2) ? prm.vp12_edge_angle_thre : prm.vp3_edge_angle_thre) / 180.0 * CS_PI;
             if (n_lines > 0)
-                vp_support_warp(SS, n_lines, S.vps[wid][vp_id], thre, vp_id, &S.vp_angles[wid][vp_id * 2]);
+                vp_support_warp(SS, n_lines, S.vps[wid][vp_id], thre, vp_id, &S.vp_angles[wid][yy][vp_id * 2]);
             else if (lane == 0) {
-                S.vp_angles[wid][vp_id * 2] = nan("");
-                S.vp_angles[wid][vp_id * 2 + 1] = nan("");
+                S.vp_angles[wid][yy][vp_id * 2] = nan("");
+                S.vp_angles[wid][yy][vp_id * 2 + 1] = nan("");
             }
         }
-    }
-    __syncwarp();
-    const float *dist = dist_arena + jb.px_off;
-    const int64_t cbase = jb.cand_off + ((int64_t)bk.y * n_yaw + yi) * n_top * 2;
-    const bool cfg1 = prm.consider_config_1 != 0, cfg2 = prm.consider_config_2 != 0;
-    for (int c0 = 0; c0 < n_top * 2; c0 += 32) {
-        const int ci = c0 + lane;
-        if (ci < n_top * 2) {
-            const int ti = ci >> 1, config_id = (ci & 1) + 1;
-            D2 c[8];
-            int vp1pos;
+        __syncwarp();
+        for (int c0 = 0; c0 < n_top * 2; c0 += 32) {
+            const int ci = c0 + lane;
             bool valid = false;
-            if ((config_id == 1) ? cfg1 : cfg2) valid = g_build_corners(jb, S.vps[wid], g_top_x(jb, ti), config_id, prm.shorted_edge_thre, c, vp1pos);
-            c_valid[cbase + ci] = valid ? 1 : 0;
+            D2 c[8];
+            int config_id = 1;
+            if (ci < n_top * 2) {
+                const int ti = ci >> 1;
+                config_id = (ci & 1) + 1;
+                int vp1pos;
+                if ((config_id == 1) ? cfg1 : cfg2) valid = g_build_corners(jb, S.vps[wid], g_top_x(jb, ti), config_id, prm.shorted_edge_thre, c, vp1pos);
+                c_valid[cbase + (int64_t)yi * n_top * 2 + ci] = valid ? 1 : 0;
+            }
+            const unsigned m = __ballot_sync(FULL, valid);
             if (valid) {
-                const double sum_dist = g_edge_sum_dists(dist, jb.dpitch, jb.roi_w, jb.roi_h, c, (double)jb.roi_l, (double)jb.roi_t, config_id,
-                                                         prm.reweight_edge_distance != 0);
-                c_dist[cbase + ci] = sum_dist / jb.diag;
-                c_angle[cbase + ci] = g_angle_error(S.vp_angles[wid], config_id, c);
+                const int slot = n_pending + __popc(m & ((1u << lane) - 1u));
+#pragma unroll
+                for (int k = 0; k < 8; k++) S.corners[wid][slot][k] = c[k];
+                S.slot_cand[wid][slot] = yi * n_top * 2 + ci;
+                S.slot_yaw[wid][slot] = (int8_t)yy;
+                S.slot_cfg[wid][slot] = (int8_t)config_id;
+            }
+            n_pending += __popc(m);
+            __syncwarp();
+            if (n_pending >= 32) {
+                score_slots(32);
+                const int rest = n_pending - 32; /* < 32: move the tail to the front */
+                D2 tc[8];
+                int tcand = 0, ty = 0, tcf = 0;
+                if (lane < rest) {
+#pragma unroll
+                    for (int k = 0; k < 8; k++) tc[k] = S.corners[wid][32 + lane][k];
+                    tcand = S.slot_cand[wid][32 + lane];
+                    ty = S.slot_yaw[wid][32 + lane];
+                    tcf = S.slot_cfg[wid][32 + lane];
+                }
+                __syncwarp();
+                if (lane < rest) {
+#pragma unroll
+                    for (int k = 0; k < 8; k++) S.corners[wid][lane][k] = tc[k];
+                    S.slot_cand[wid][lane] = tcand;
+                    S.slot_yaw[wid][lane] = (int8_t)ty;
+                    S.slot_cfg[wid][lane] = (int8_t)tcf;
+                }
+                n_pending = rest;
+                __syncwarp();
             }
         }
     }
+    if (n_pending > 0) score_slots(n_pending);
 }
 
 /* ---- selection, one warp per 2D box (all valid counts <= FW_CAP) ---- */
@@ -695,38 +787,14 @@ __device__ __forceinline__ double warp_max_d(double v)
     return v;
 }
 
-/* scale (half sizes) of a lifted proposal only: what the ranking needs (object_3d_util.cpp:615-625) */
-__device__ __forceinline__ void g_lift_scale(const D2 *c, const double *ground, const double *T, const double *invK, double *scale)
-{
-    double g[4][3];
-    for (int i = 0; i < 4; i++) g_plane_hit(T, invK, ground, c[4 + i], g[i]);
-    double dx = g[0][0] - g[3][0], dy = g[0][1] - g[3][1], dz = g[0][2] - g[3][2];
-    scale[0] = sqrt((dx * dx + dy * dy) + dz * dz) / 2;
-    dx = g[0][0] - g[1][0];
-    dy = g[0][1] - g[1][1];
-    dz = g[0][2] - g[1][2];
-    scale[1] = sqrt((dx * dx + dy * dy) + dz * dz) / 2;
-    double nrm[3] = {dy * 1.0 - dz * 0.0, dz * 0.0 - dx * 1.0, dx * 0.0 - dy * 0.0};
-    const double nn = sqrt((nrm[0] * nrm[0] + nrm[1] * nrm[1]) + nrm[2] * nrm[2]);
-    for (int i = 0; i < 3; i++) nrm[i] /= nn;
-    const double dist = -((nrm[0] * g[0][0] + nrm[1] * g[0][1]) + nrm[2] * g[0][2]);
-    double pw[4] = {nrm[0], nrm[1], nrm[2], dist};
-    if (dist < 0)
-        for (int i = 0; i < 4; i++) pw[i] = -pw[i];
-    double ps[4];
-    for (int i = 0; i < 4; i++) ps[i] = ((T[0 * 4 + i] * pw[0] + T[1 * 4 + i] * pw[1]) + T[2 * 4 + i] * pw[2]) + T[3 * 4 + i] * pw[3];
-    double top[3];
-    g_plane_hit(T, invK, ps, c[1], top);
-    scale[2] = top[2] / 2;
-}
-
 extern __shared__ unsigned char fw_smem_raw[];
 
 __global__ void __launch_bounds__(32 * FW_WARPS) k_fuse_warp(const CsObj *__restrict__ objs, int n_objs, const CsJob *__restrict__ jobs,
                                                              const CsFrame *__restrict__ frames, const CsPose *__restrict__ poses,
                                                              const double *__restrict__ yaw_table, const uint8_t *__restrict__ c_valid,
                                                              const double *__restrict__ c_dist, const double *__restrict__ c_angle,
-                                                             int32_t *__restrict__ w_vlist, int32_t *__restrict__ w_keep, double *__restrict__ w_norm,
+                                                             const double *__restrict__ c_skew, int32_t *__restrict__ w_vlist,
+                                                             int32_t *__restrict__ w_keep, double *__restrict__ w_norm,
                                                              double *__restrict__ w_score, int32_t *__restrict__ job_counts,
                                                              cs_cuboid_rec *__restrict__ out, int32_t *__restrict__ out_counts, int topk,
                                                              cs_cuboid_params prm)
@@ -823,18 +891,11 @@ __global__ void __launch_bounds__(32 * FW_WARPS) k_fuse_warp(const CsObj *__rest
                 comb = (comb + prm.weight_vp_angle * ak) / (1 + prm.weight_vp_angle);
             } else
                 comb = (dk + prm.weight_vp_angle * ak) / (1 + prm.weight_vp_angle);
-            D2 c[8];
-            int vp1pos, config_id, pose_id, top_id;
-            double yaw;
-            rebuild_corners(jb, fr, poses, yaw_table, prm, cand, c, vp1pos, config_id, yaw, pose_id, top_id);
-            const CsPose &ps = poses[fr.pose_off + pose_id];
-            double sc3[3];
-            g_lift_scale(c, ps.ground, ps.T, fr.invK, sc3);
+            const double skew_ratio = c_skew[co + cand]; /* from the sweep; NaN == negative scale == dropped */
             double sc;
-            if (sc3[0] < 0 || sc3[1] < 0 || sc3[2] < 0)
+            if (isnan(skew_ratio))
                 sc = nan("");
             else {
-                const double skew_ratio = g_max(sc3[0], sc3[1]) / g_min(sc3[0], sc3[1]);
                 double skew_error = prm.weight_skew_error * g_max(skew_ratio - prm.nominal_skew_ratio, 0.0);
                 if (skew_ratio > prm.max_cut_skew) skew_error = 100;
                 sc = comb + prm.weight_skew_error * skew_error;
@@ -964,21 +1025,21 @@ void cs_launch_fuse(const CsObj *d_objs, int n_objs, const CsJob *d_jobs, const 
 
 void cs_launch_sweep_warp(const CsJob *d_jobs, const CsFrame *d_frames, const CsPose *d_poses, const double *d_yaw, const int4 *d_blocks,
                           int n_blocks, const double *d_mlines, const int32_t *d_line_counts, const float *d_dist, uint8_t *c_valid,
-                          double *c_dist, double *c_angle, const cs_cuboid_params *prm, cudaStream_t st, int64_t *launches)
+                          double *c_dist, double *c_angle, double *c_skew, const cs_cuboid_params *prm, cudaStream_t st, int64_t *launches)
 {
     if (n_blocks <= 0) return;
     k_sweep_warp<<<n_blocks, 32 * SWW_WARPS, 0, st>>>(d_jobs, d_frames, d_poses, d_yaw, d_blocks, d_mlines, d_line_counts, d_dist, c_valid, c_dist,
-                                                      c_angle, *prm);
+                                                      c_angle, c_skew, *prm);
     (*launches)++;
 }
 
 int cs_fuse_warp_cap(void) { return FW_CAP; }
-int cs_sweep_warp_yaws(void) { return SWW_WARPS; }
+int cs_sweep_warp_yaws(void) { return SWW_WARPS * SWW_YAWS; }
 
 void cs_launch_fuse_warp(const CsObj *d_objs, int n_objs, const CsJob *d_jobs, const CsFrame *d_frames, const CsPose *d_poses, const double *d_yaw,
-                         const uint8_t *c_valid, const double *c_dist, const double *c_angle, int32_t *w_vlist, int32_t *w_keep, double *w_norm,
-                         double *w_score, int32_t *job_counts, cs_cuboid_rec *d_out, int32_t *d_out_counts, int topk, const cs_cuboid_params *prm,
-                         cudaStream_t st, int64_t *launches)
+                         const uint8_t *c_valid, const double *c_dist, const double *c_angle, const double *c_skew, int32_t *w_vlist, int32_t *w_keep,
+                         double *w_norm, double *w_score, int32_t *job_counts, cs_cuboid_rec *d_out, int32_t *d_out_counts, int topk,
+                         const cs_cuboid_params *prm, cudaStream_t st, int64_t *launches)
 {
     if (n_objs <= 0) return;
     const size_t smem = sizeof(FuseWarpShared) * FW_WARPS;
@@ -988,7 +1049,7 @@ void cs_launch_fuse_warp(const CsObj *d_objs, int n_objs, const CsJob *d_jobs, c
         attr_set = true;
     }
     k_fuse_warp<<<(n_objs + FW_WARPS - 1) / FW_WARPS, 32 * FW_WARPS, smem, st>>>(d_objs, n_objs, d_jobs, d_frames, d_poses, d_yaw, c_valid, c_dist,
-                                                                                 c_angle, w_vlist, w_keep, w_norm, w_score, job_counts, d_out,
+                                                                                 c_angle, c_skew, w_vlist, w_keep, w_norm, w_score, job_counts, d_out,
                                                                                  d_out_counts, topk, *prm);
     (*launches)++;
 }
