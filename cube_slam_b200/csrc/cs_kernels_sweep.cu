@@ -577,8 +577,8 @@ __global__ void __launch_bounds__(FU_THREADS) k_fuse_rank(const CsObj *__restric
 
 struct SweepWarpShared {
     double ang[CS_MAXL_OUT], midx[CS_MAXL_OUT], midy[CS_MAXL_OUT];
-    double vp_angles[SWW_WARPS][SWW_YAWS][6];
-    D2 vps[SWW_WARPS][3];
+    double vp_angles[SWW_WARPS * SWW_YAWS][6];
+    D2 vps[SWW_WARPS * SWW_YAWS][3];
     D2 corners[SWW_WARPS][SWW_SLOTS][8];
     int32_t slot_cand[SWW_WARPS][SWW_SLOTS]; /* candidate index inside the (job, pose) block */
     int8_t slot_yaw[SWW_WARPS][SWW_SLOTS];
@@ -620,6 +620,57 @@ __device__ __forceinline__ double g_skew_of(const D2 *c, const CsPose &ps, const
     return isnan(r) ? __longlong_as_double(0x7ff0000000000000ll) : r; /* NaN skew (degenerate lift) ranks as +inf, still a cuboid */
 }
 
+/* VP_support_edge_infos for ONE vanishing point by ONE lane (object_3d_util.cpp:380-425): a plain loop over the line set, so
+ * the first-occurrence semantics of maxCoeff / minCoeff and of smooth_jump_angles' base angle come for free. */
+__device__ __forceinline__ void vp_support_lane(const double *ang, const double *midx, const double *midy, int n_lines, D2 vp, double thre,
+                                                int vp_id, double *out2)
+{
+    bool have = false;
+    double base = 0, vmax = 0, vmin = 0;
+    int imax = 0, imin = 0;
+    for (int e = 0; e < n_lines; e++) {
+        const double raw = atan2(midy[e] - vp.y, midx[e] - vp.x);
+        const double nrm = g_normalize_to_pi(raw);
+        double d = fabs(ang[e] - nrm);
+        d = g_min(d, CS_PI - d);
+        if (d < thre) {
+            if (!have) {
+                have = true;
+                base = raw;
+                vmax = vmin = raw;
+                imax = imin = e;
+            } else {
+                double v = raw;
+                if ((raw - base) < -CS_PI)
+                    v = raw + 2 * CS_PI;
+                else if ((raw - base) > CS_PI)
+                    v = raw - 2 * CS_PI;
+                if (v > vmax) {
+                    vmax = v;
+                    imax = e;
+                }
+                if (v < vmin) {
+                    vmin = v;
+                    imin = e;
+                }
+            }
+        }
+    }
+    if (!have) {
+        out2[0] = nan("");
+        out2[1] = nan("");
+        return;
+    }
+    int low = imax, top = imin;
+    if (vp_id > 0) {
+        const int t = low;
+        low = top;
+        top = t;
+    }
+    out2[0] = ang[low];
+    out2[1] = ang[top];
+}
+
 /* One warp per (ROI job, pose, group of SWW_YAWS yaws).  Per yaw: VP support by the warp, one lane per (top-x, config)
  * candidate for the FP64 corner chain; valid candidates are compacted into the warp's slot list and scored 32 at a time, so
  * the expensive part (99/77 dist-map gathers, 6 atan2, the 3D lift for the skew) runs with full lanes.  No block barrier
@@ -649,13 +700,37 @@ __global__ void __launch_bounds__(32 * SWW_WARPS) k_sweep_warp(const CsJob *__re
         }
     }
     __syncthreads();
+    /* phase A: one lane per (yaw, VP) -- vanishing point + its two supporting line angles.  The vertical VP does not depend on
+     * the yaw: it is evaluated once per block and copied. */
+    {
+        const int n_tasks = 2 * bk.w + 1;
+        for (int t = tid; t < n_tasks; t += 32 * SWW_WARPS) {
+            const int ys = (t < 2 * bk.w) ? (t >> 1) : 0, vp_id = (t < 2 * bk.w) ? (t & 1) : 2;
+            D2 v3[3];
+            g_vanishing_points(pose.KinvR, yaw_table[fr.yaw_off + bk.z + ys], v3);
+            const double thre = ((vp_id != 2) ? prm.vp12_edge_angle_thre : prm.vp3_edge_angle_thre) / 180.0 * CS_PI;
+            double o2[2];
+            vp_support_lane(S.ang, S.midx, S.midy, n_lines, v3[vp_id], thre, vp_id, o2);
+            if (vp_id < 2) {
+                S.vps[ys][vp_id] = v3[vp_id];
+                S.vp_angles[ys][vp_id * 2] = o2[0];
+                S.vp_angles[ys][vp_id * 2 + 1] = o2[1];
+            } else {
+                for (int k = 0; k < bk.w; k++) {
+                    S.vps[k][2] = v3[2];
+                    S.vp_angles[k][4] = o2[0];
+                    S.vp_angles[k][5] = o2[1];
+                }
+            }
+        }
+    }
+    __syncthreads();
     const int y_first = bk.z + wid * SWW_YAWS, y_end = min(bk.z + bk.w, y_first + SWW_YAWS);
     if (y_first >= y_end) return;
     const int n_top = jb.n_top, n_yaw = fr.n_yaw;
     const float *dist = dist_arena + jb.px_off;
     const int64_t cbase = jb.cand_off + (int64_t)bk.y * n_yaw * n_top * 2;
     const bool cfg1 = prm.consider_config_1 != 0, cfg2 = prm.consider_config_2 != 0;
-    const SweepShared &SS = *reinterpret_cast<const SweepShared *>(&S); /* ang / midx / midy share the layout */
     int n_pending = 0;
 
     auto score_slots = [&](int count) { /* lanes < count score slot `lane` */
@@ -666,7 +741,7 @@ __global__ void __launch_bounds__(32 * SWW_WARPS) k_sweep_warp(const CsJob *__re
             const double sum_dist = g_edge_sum_dists(dist, jb.dpitch, jb.roi_w, jb.roi_h, c, (double)jb.roi_l, (double)jb.roi_t, cfg,
                                                      prm.reweight_edge_distance != 0);
             c_dist[ci] = sum_dist / jb.diag;
-            c_angle[ci] = g_angle_error(S.vp_angles[wid][S.slot_yaw[wid][lane]], cfg, c);
+            c_angle[ci] = g_angle_error(S.vp_angles[S.slot_yaw[wid][lane]], cfg, c);
             c_skew[ci] = g_skew_of(c, pose, fr.invK);
         }
         __syncwarp();
@@ -674,18 +749,7 @@ __global__ void __launch_bounds__(32 * SWW_WARPS) k_sweep_warp(const CsJob *__re
 
     for (int yy = 0; y_first + yy < y_end; yy++) {
         const int yi = y_first + yy;
-        if (lane == 0) g_vanishing_points(pose.KinvR, yaw_table[fr.yaw_off + yi], S.vps[wid]);
-        __syncwarp();
-        for (int vp_id = 0; vp_id < 3; vp_id++) {
-            const double thre = ((vp_id != 2) ? prm.vp12_edge_angle_thre : prm.vp3_edge_angle_thre) / 180.0 * CS_PI;
-            if (n_lines > 0)
-                vp_support_warp(SS, n_lines, S.vps[wid][vp_id], thre, vp_id, &S.vp_angles[wid][yy][vp_id * 2]);
-            else if (lane == 0) {
-                S.vp_angles[wid][yy][vp_id * 2] = nan("");
-                S.vp_angles[wid][yy][vp_id * 2 + 1] = nan("");
-            }
-        }
-        __syncwarp();
+        const int ys = yi - bk.z; /* yaw slot inside the block */
         for (int c0 = 0; c0 < n_top * 2; c0 += 32) {
             const int ci = c0 + lane;
             bool valid = false;
@@ -695,7 +759,7 @@ __global__ void __launch_bounds__(32 * SWW_WARPS) k_sweep_warp(const CsJob *__re
                 const int ti = ci >> 1;
                 config_id = (ci & 1) + 1;
                 int vp1pos;
-                if ((config_id == 1) ? cfg1 : cfg2) valid = g_build_corners(jb, S.vps[wid], g_top_x(jb, ti), config_id, prm.shorted_edge_thre, c, vp1pos);
+                if ((config_id == 1) ? cfg1 : cfg2) valid = g_build_corners(jb, S.vps[ys], g_top_x(jb, ti), config_id, prm.shorted_edge_thre, c, vp1pos);
                 c_valid[cbase + (int64_t)yi * n_top * 2 + ci] = valid ? 1 : 0;
             }
             const unsigned m = __ballot_sync(FULL, valid);
@@ -704,7 +768,7 @@ __global__ void __launch_bounds__(32 * SWW_WARPS) k_sweep_warp(const CsJob *__re
 #pragma unroll
                 for (int k = 0; k < 8; k++) S.corners[wid][slot][k] = c[k];
                 S.slot_cand[wid][slot] = yi * n_top * 2 + ci;
-                S.slot_yaw[wid][slot] = (int8_t)yy;
+                S.slot_yaw[wid][slot] = (int8_t)ys;
                 S.slot_cfg[wid][slot] = (int8_t)config_id;
             }
             n_pending += __popc(m);
