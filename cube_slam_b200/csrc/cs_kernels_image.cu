@@ -75,10 +75,9 @@ __global__ void __launch_bounds__(256) k_bgr2gray_generic(const uint8_t *__restr
 __global__ void __launch_bounds__(256) k_canny_nms(const uint8_t *__restrict__ gray, int img_w, int img_h, const CsJob *__restrict__ jobs,
                                                    const int32_t *__restrict__ tile_job, uint32_t *__restrict__ bits_arena, int low, int high)
 {
-    __shared__ uint8_t s_g[CT + 4][CT + 4 + 4];
-    __shared__ int16_t s_dx[CT + 2][CT + 2 + 2];
-    __shared__ int16_t s_dy[CT + 2][CT + 2 + 2];
-    __shared__ uint16_t s_m[CT + 2][CT + 2 + 2];
+    __shared__ uint8_t s_g[CT + 4][CT + 4 + 4];   /* gray, +2 halo */
+    __shared__ int32_t s_d[CT + 2][CT + 2 + 1];   /* (dy << 16) | (dx & 0xffff), +1 halo */
+    __shared__ uint16_t s_m[CT + 2][CT + 2 + 2];  /* |dx| + |dy|, zero outside the ROI */
     const CsJob &jb = jobs[tile_job[blockIdx.x]];
     const int w = jb.roi_w, h = jb.roi_h;
     const int tl = blockIdx.x - jb.tile_off;
@@ -86,33 +85,51 @@ __global__ void __launch_bounds__(256) k_canny_nms(const uint8_t *__restrict__ g
     const int x0 = tile_x * CT, y0 = tile_y * CT;
     const uint8_t *src = gray + ((size_t)jb.frame * img_h + jb.roi_t) * img_w + jb.roi_l;
     const int tx = threadIdx.x, ty = threadIdx.y;
-
     const int tid = ty * 32 + tx;
-    for (int i = tid; i < (CT + 4) * (CT + 4); i += 256) {
-        const int ly = i / (CT + 4), lx = i - ly * (CT + 4);
-        const int gy = min(max(y0 + ly - 2, 0), h - 1);
-        const int gx = min(max(x0 + lx - 2, 0), w - 1);
-        s_g[ly][lx] = src[gy * img_w + gx];
+
+    /* gray tile: interior tiles skip the replicate clamps */
+    const bool interior = (x0 >= 2) && (y0 >= 2) && (x0 + CT + 2 <= w) && (y0 + CT + 2 <= h);
+    if (interior) {
+        const uint8_t *base = src + (y0 - 2) * img_w + (x0 - 2);
+        for (int i = tid; i < (CT + 4) * (CT + 4); i += 256) {
+            const int ly = i / (CT + 4), lx = i - ly * (CT + 4);
+            s_g[ly][lx] = __ldg(base + ly * img_w + lx);
+        }
+    } else {
+        for (int i = tid; i < (CT + 4) * (CT + 4); i += 256) {
+            const int ly = i / (CT + 4), lx = i - ly * (CT + 4);
+            const int gy = min(max(y0 + ly - 2, 0), h - 1);
+            const int gx = min(max(x0 + lx - 2, 0), w - 1);
+            s_g[ly][lx] = __ldg(src + gy * img_w + gx);
+        }
     }
     __syncthreads();
-    for (int i = tid; i < (CT + 2) * (CT + 2); i += 256) {
-        {
-            const int ly = i / (CT + 2), lx = i - ly * (CT + 2);
-            const int gy = y0 + ly - 1;
-            const int gx = x0 + lx - 1; /* ROI coordinates of this magnitude */
-            int dx = 0, dy = 0, m = 0;
-            if (gy >= 0 && gy < h && gx >= 0 && gx < w) {
-                const int cy = ly + 1, cx = lx + 1; /* centre in s_g */
-                const int a = s_g[cy - 1][cx - 1], b = s_g[cy - 1][cx], c = s_g[cy - 1][cx + 1];
-                const int d = s_g[cy][cx - 1], f = s_g[cy][cx + 1];
-                const int g = s_g[cy + 1][cx - 1], hh = s_g[cy + 1][cx], k = s_g[cy + 1][cx + 1];
-                dx = (c + 2 * f + k) - (a + 2 * d + g);
-                dy = (g + 2 * hh + k) - (a + 2 * b + c);
-                m = abs(dx) + abs(dy);
+    /* Sobel + magnitude for the (CT+2)^2 halo region: a thread owns one column and a strip of 5 rows, the three-row
+     * window slides down in registers (21 shared loads for 5 results) */
+    if (tid < (CT + 2) * 7) {
+        const int strip = tid / (CT + 2), lx = tid - strip * (CT + 2);
+        const int r0 = strip * 5;
+        int rs[7], rd[7];
+#pragma unroll
+        for (int r = 0; r < 7; r++) {
+            const int row = min(r0 + r, CT + 3);
+            const int a = s_g[row][lx], b = s_g[row][lx + 1], c = s_g[row][lx + 2];
+            rs[r] = a + 2 * b + c;
+            rd[r] = c - a;
+        }
+        const int gx = x0 + lx - 1;
+        const bool col_in = (gx >= 0) && (gx < w);
+#pragma unroll
+        for (int j = 0; j < 5; j++) {
+            const int ly = r0 + j;
+            if (ly < CT + 2) {
+                const int gy = y0 + ly - 1;
+                const int dx = rd[j] + 2 * rd[j + 1] + rd[j + 2];
+                const int dy = rs[j + 2] - rs[j];
+                const bool in = col_in && (gy >= 0) && (gy < h);
+                s_d[ly][lx] = (dy << 16) | (dx & 0xffff);
+                s_m[ly][lx] = in ? (uint16_t)(abs(dx) + abs(dy)) : (uint16_t)0;
             }
-            s_dx[ly][lx] = (int16_t)dx;
-            s_dy[ly][lx] = (int16_t)dy;
-            s_m[ly][lx] = (uint16_t)m;
         }
     }
     __syncthreads();
@@ -121,37 +138,36 @@ __global__ void __launch_bounds__(256) k_canny_nms(const uint8_t *__restrict__ g
     const int bwp = jb.bw + 2;
     uint32_t *planeS = bits_arena + jb.bit_off;
     uint32_t *planeW = planeS + (size_t)(h + 2) * bwp;
+    const int MP = CT + 2 + 2; /* pitch of s_m in elements */
+    const uint16_t *mflat = &s_m[0][0];
 #pragma unroll
     for (int k = 0; k < 4; k++) {
         const int ly = ty + 8 * k, lx = tx;
         const int gy = y0 + ly, gx = x0 + lx;
         int code = 0;
         if (gy < h && gx < w) {
-            const int my = ly + 1, mx = lx + 1;
-            const int m = s_m[my][mx];
+            const int mi = (ly + 1) * MP + lx + 1;
+            const int m = mflat[mi];
             if (m > low) {
-                const int xs = s_dx[my][mx], ys = s_dy[my][mx];
+                const int d = s_d[ly + 1][lx + 1];
+                const int xs = (int)(int16_t)(d & 0xffff), ys = d >> 16;
                 const int ax = abs(xs), ay = abs(ys) << 15;
                 const int tg22x = ax * TG22;
-                bool is_max;
-                if (ay < tg22x) {
-                    is_max = (m > s_m[my][mx - 1]) && (m >= s_m[my][mx + 1]);
-                } else {
-                    const int tg67x = tg22x + (ax << 16);
-                    if (ay > tg67x)
-                        is_max = (m > s_m[my - 1][mx]) && (m >= s_m[my + 1][mx]);
-                    else {
-                        const int s = ((xs ^ ys) < 0) ? -1 : 1;
-                        is_max = (m > s_m[my - 1][mx - s]) && (m > s_m[my + 1][mx + s]);
-                    }
-                }
+                const int tg67x = tg22x + (ax << 16);
+                /* direction sector -> neighbour offset and comparison kind, without divergent branches */
+                const bool horiz = ay < tg22x;
+                const bool vert = !horiz && (ay > tg67x);
+                const int sgn = ((xs ^ ys) < 0) ? -1 : 1;
+                const int off = horiz ? 1 : (vert ? MP : MP + sgn);
+                const int ma = mflat[mi - off], mb = mflat[mi + off];
+                const bool is_max = (m > ma) && ((horiz || vert) ? (m >= mb) : (m > mb));
                 if (is_max) code = (m > high) ? 2 : 1;
             }
         }
         const unsigned strong = __ballot_sync(0xffffffffu, code == 2);
         const unsigned weak = __ballot_sync(0xffffffffu, code == 1);
         if (tx == 0 && gy < h) {
-            const size_t wi = (size_t)(gy + 1) * bwp + 1 + tile_x;
+            const int wi = (gy + 1) * bwp + 1 + tile_x;
             planeS[wi] = strong;
             planeW[wi] = weak;
         }
