@@ -313,8 +313,8 @@ int build_tables(cs_ctx *c)
     c->tile_job.clear();
     c->tile_job.reserve(c->n_tiles);
     for (size_t j = 0; j < c->jobs.size(); j++) {
-        const int nt = c->jobs[j].tiles_x * ((c->jobs[j].roi_h + 31) / 32);
-        c->tile_job.insert(c->tile_job.end(), nt, (int32_t)j);
+        const int rows = (c->jobs[j].roi_h + 31) / 32; /* one NMS block per row of tiles: (job << 8) | tile_y */
+        for (int ty = 0; ty < rows; ty++) c->tile_job.push_back((int32_t)((j << 8) | ty));
     }
     c->dt_ids.clear();
     for (int cls = 0; cls < CS_DT_CLASSES; cls++)
@@ -406,7 +406,7 @@ int run_batch(cs_ctx *c, bool sync)
         gray = (const uint8_t *)c->d_img.p;
     mark(ST_CANNY);
     int low = (int)std::floor(std::min(c->prm.canny_low, c->prm.canny_high)), high = (int)std::floor(std::max(c->prm.canny_low, c->prm.canny_high));
-    cs_launch_canny(gray, c->w, c->h, (const CsJob *)c->d_jobs.p, n_jobs, (const int32_t *)c->d_tilejob.p, c->n_tiles, (uint32_t *)c->d_bits.p, (size_t)c->total_bits * 4, low, high,
+    cs_launch_canny(gray, c->w, c->h, (const CsJob *)c->d_jobs.p, n_jobs, (const int32_t *)c->d_tilejob.p, (int)c->tile_job.size(), (uint32_t *)c->d_bits.p, (size_t)c->total_bits * 4, low, high,
                     st, &c->launches);
     mark(ST_HYST);
     bool fused = false;

@@ -78,99 +78,113 @@ __global__ void __launch_bounds__(256) k_canny_nms(const uint8_t *__restrict__ g
     __shared__ uint8_t s_g[CT + 4][CT + 4 + 4];   /* gray, +2 halo */
     __shared__ int32_t s_d[CT + 2][CT + 2 + 1];   /* (dy << 16) | (dx & 0xffff), +1 halo */
     __shared__ uint16_t s_m[CT + 2][CT + 2 + 2];  /* |dx| + |dy|, zero outside the ROI */
-    const CsJob &jb = jobs[tile_job[blockIdx.x]];
-    const int w = jb.roi_w, h = jb.roi_h;
-    const int tl = blockIdx.x - jb.tile_off;
-    const int tile_y = tl / jb.tiles_x, tile_x = tl - tile_y * jb.tiles_x;
-    const int x0 = tile_x * CT, y0 = tile_y * CT;
+    /* a block owns one ROW of tiles of one ROI and walks it left to right; the gray bytes of the next tile are fetched into
+     * registers while the current tile is being processed, so only the first tile of a row pays the global-load latency */
+    const int packed = tile_job[blockIdx.x];
+    const CsJob &jb = jobs[packed >> 8];
+    const int tile_y = packed & 255;
+    const int w = jb.roi_w, h = jb.roi_h, tiles_x = jb.tiles_x;
+    const int y0 = tile_y * CT;
     const uint8_t *src = gray + ((size_t)jb.frame * img_h + jb.roi_t) * img_w + jb.roi_l;
     const int tx = threadIdx.x, ty = threadIdx.y;
     const int tid = ty * 32 + tx;
-
-    /* gray tile: interior tiles skip the replicate clamps */
-    const bool interior = (x0 >= 2) && (y0 >= 2) && (x0 + CT + 2 <= w) && (y0 + CT + 2 <= h);
-    if (interior) {
-        const uint8_t *base = src + (y0 - 2) * img_w + (x0 - 2);
-        for (int i = tid; i < (CT + 4) * (CT + 4); i += 256) {
-            const int ly = i / (CT + 4), lx = i - ly * (CT + 4);
-            s_g[ly][lx] = __ldg(base + ly * img_w + lx);
-        }
-    } else {
-        for (int i = tid; i < (CT + 4) * (CT + 4); i += 256) {
-            const int ly = i / (CT + 4), lx = i - ly * (CT + 4);
-            const int gy = min(max(y0 + ly - 2, 0), h - 1);
-            const int gx = min(max(x0 + lx - 2, 0), w - 1);
-            s_g[ly][lx] = __ldg(src + gy * img_w + gx);
-        }
-    }
-    __syncthreads();
-    /* Sobel + magnitude for the (CT+2)^2 halo region: a thread owns one column and a strip of 5 rows, the three-row
-     * window slides down in registers (21 shared loads for 5 results) */
-    if (tid < (CT + 2) * 7) {
-        const int strip = tid / (CT + 2), lx = tid - strip * (CT + 2);
-        const int r0 = strip * 5;
-        int rs[7], rd[7];
-#pragma unroll
-        for (int r = 0; r < 7; r++) {
-            const int row = min(r0 + r, CT + 3);
-            const int a = s_g[row][lx], b = s_g[row][lx + 1], c = s_g[row][lx + 2];
-            rs[r] = a + 2 * b + c;
-            rd[r] = c - a;
-        }
-        const int gx = x0 + lx - 1;
-        const bool col_in = (gx >= 0) && (gx < w);
-#pragma unroll
-        for (int j = 0; j < 5; j++) {
-            const int ly = r0 + j;
-            if (ly < CT + 2) {
-                const int gy = y0 + ly - 1;
-                const int dx = rd[j] + 2 * rd[j + 1] + rd[j + 2];
-                const int dy = rs[j + 2] - rs[j];
-                const bool in = col_in && (gy >= 0) && (gy < h);
-                s_d[ly][lx] = (dy << 16) | (dx & 0xffff);
-                s_m[ly][lx] = in ? (uint16_t)(abs(dx) + abs(dy)) : (uint16_t)0;
-            }
-        }
-    }
-    __syncthreads();
-
     const int TG22 = 13573; /* (int)(0.4142135623730950488016887242097 * (1 << 15) + 0.5) */
     const int bwp = jb.bw + 2;
     uint32_t *planeS = bits_arena + jb.bit_off;
     uint32_t *planeW = planeS + (size_t)(h + 2) * bwp;
     const int MP = CT + 2 + 2; /* pitch of s_m in elements */
     const uint16_t *mflat = &s_m[0][0];
+    constexpr int NPRE = ((CT + 4) * (CT + 4) + 255) / 256;
+    uint8_t pre[NPRE];
+
+    auto fetch = [&](int x0) {
 #pragma unroll
-    for (int k = 0; k < 4; k++) {
-        const int ly = ty + 8 * k, lx = tx;
-        const int gy = y0 + ly, gx = x0 + lx;
-        int code = 0;
-        if (gy < h && gx < w) {
-            const int mi = (ly + 1) * MP + lx + 1;
-            const int m = mflat[mi];
-            if (m > low) {
-                const int d = s_d[ly + 1][lx + 1];
-                const int xs = (int)(int16_t)(d & 0xffff), ys = d >> 16;
-                const int ax = abs(xs), ay = abs(ys) << 15;
-                const int tg22x = ax * TG22;
-                const int tg67x = tg22x + (ax << 16);
-                /* direction sector -> neighbour offset and comparison kind, without divergent branches */
-                const bool horiz = ay < tg22x;
-                const bool vert = !horiz && (ay > tg67x);
-                const int sgn = ((xs ^ ys) < 0) ? -1 : 1;
-                const int off = horiz ? 1 : (vert ? MP : MP + sgn);
-                const int ma = mflat[mi - off], mb = mflat[mi + off];
-                const bool is_max = (m > ma) && ((horiz || vert) ? (m >= mb) : (m > mb));
-                if (is_max) code = (m > high) ? 2 : 1;
+        for (int q = 0; q < NPRE; q++) {
+            const int i = tid + q * 256;
+            pre[q] = 0;
+            if (i < (CT + 4) * (CT + 4)) {
+                const int ly = i / (CT + 4), lx = i - ly * (CT + 4);
+                const int gy = min(max(y0 + ly - 2, 0), h - 1);
+                const int gx = min(max(x0 + lx - 2, 0), w - 1);
+                pre[q] = __ldg(src + gy * img_w + gx);
             }
         }
-        const unsigned strong = __ballot_sync(0xffffffffu, code == 2);
-        const unsigned weak = __ballot_sync(0xffffffffu, code == 1);
-        if (tx == 0 && gy < h) {
-            const int wi = (gy + 1) * bwp + 1 + tile_x;
-            planeS[wi] = strong;
-            planeW[wi] = weak;
+    };
+    fetch(0);
+    for (int tile_x = 0; tile_x < tiles_x; tile_x++) {
+        const int x0 = tile_x * CT;
+#pragma unroll
+        for (int q = 0; q < NPRE; q++) {
+            const int i = tid + q * 256;
+            if (i < (CT + 4) * (CT + 4)) {
+                const int ly = i / (CT + 4), lx = i - ly * (CT + 4);
+                s_g[ly][lx] = pre[q];
+            }
         }
+        __syncthreads();
+        if (tile_x + 1 < tiles_x) fetch(x0 + CT);
+        /* Sobel + magnitude for the (CT+2)^2 halo region: a thread owns one column and a strip of 5 rows, the three-row
+         * window slides down in registers (21 shared loads for 5 results) */
+        if (tid < (CT + 2) * 7) {
+            const int strip = tid / (CT + 2), lx = tid - strip * (CT + 2);
+            const int r0 = strip * 5;
+            int rs[7], rd[7];
+#pragma unroll
+            for (int r = 0; r < 7; r++) {
+                const int row = min(r0 + r, CT + 3);
+                const int a = s_g[row][lx], b = s_g[row][lx + 1], c = s_g[row][lx + 2];
+                rs[r] = a + 2 * b + c;
+                rd[r] = c - a;
+            }
+            const int gx = x0 + lx - 1;
+            const bool col_in = (gx >= 0) && (gx < w);
+#pragma unroll
+            for (int j = 0; j < 5; j++) {
+                const int ly = r0 + j;
+                if (ly < CT + 2) {
+                    const int gy = y0 + ly - 1;
+                    const int dx = rd[j] + 2 * rd[j + 1] + rd[j + 2];
+                    const int dy = rs[j + 2] - rs[j];
+                    const bool in = col_in && (gy >= 0) && (gy < h);
+                    s_d[ly][lx] = (dy << 16) | (dx & 0xffff);
+                    s_m[ly][lx] = in ? (uint16_t)(abs(dx) + abs(dy)) : (uint16_t)0;
+                }
+            }
+        }
+        __syncthreads();
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            const int ly = ty + 8 * k, lx = tx;
+            const int gy = y0 + ly, gx = x0 + lx;
+            int code = 0;
+            if (gy < h && gx < w) {
+                const int mi = (ly + 1) * MP + lx + 1;
+                const int m = mflat[mi];
+                if (m > low) {
+                    const int d = s_d[ly + 1][lx + 1];
+                    const int xs = (int)(int16_t)(d & 0xffff), ys = d >> 16;
+                    const int ax = abs(xs), ay = abs(ys) << 15;
+                    const int tg22x = ax * TG22;
+                    const int tg67x = tg22x + (ax << 16);
+                    /* direction sector -> neighbour offset and comparison kind, without divergent branches */
+                    const bool horiz = ay < tg22x;
+                    const bool vert = !horiz && (ay > tg67x);
+                    const int sgn = ((xs ^ ys) < 0) ? -1 : 1;
+                    const int off = horiz ? 1 : (vert ? MP : MP + sgn);
+                    const int ma = mflat[mi - off], mb = mflat[mi + off];
+                    const bool is_max = (m > ma) && ((horiz || vert) ? (m >= mb) : (m > mb));
+                    if (is_max) code = (m > high) ? 2 : 1;
+                }
+            }
+            const unsigned strong = __ballot_sync(0xffffffffu, code == 2);
+            const unsigned weak = __ballot_sync(0xffffffffu, code == 1);
+            if (tx == 0 && gy < h) {
+                const int wi = (gy + 1) * bwp + 1 + tile_x;
+                planeS[wi] = strong;
+                planeW[wi] = weak;
+            }
+        }
+        __syncthreads();
     }
 }
 
