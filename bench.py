@@ -180,25 +180,7 @@ def run_ours(args, rank, world, local_rank):
     ctx.set_calibration(wl["K"])
     stream = torch.cuda.ExternalStream(ctx.stream(), device=torch.device("cuda", local_rank))
 
-    # NCCL communicator owned by the library (the top-K all-gather is issued on the context's stream)
     recs_per_rank = 0
-    if world > 1:
-        nccl_path = None
-        for d in sys.path:
-            cand = os.path.join(d, "nvidia", "nccl", "lib", "libnccl.so.2")
-            if os.path.exists(cand):
-                nccl_path = cand
-                break
-        uid = np.zeros(128, np.uint8)
-        if rank == 0:
-            ctx.check(ctx.L.cs_comm_unique_id(ctx.h, (nccl_path or "").encode(), _lib.ptr(uid, C.c_uint8)))
-        t = torch.from_numpy(uid).cuda()
-        dist.broadcast(t, 0)
-        uid = t.cpu().numpy()
-        ctx.check(ctx.L.cs_comm_init(ctx.h, (nccl_path or "").encode(), _lib.ptr(uid, C.c_uint8), world, rank))
-        n_obj = torch.tensor([sum(len(b) for b in wl["boxes"])], device="cuda")
-        dist.all_reduce(n_obj, op=dist.ReduceOp.MAX)
-        recs_per_rank = int(n_obj.item()) * topk
 
     def barrier():
         if world > 1:
@@ -218,15 +200,32 @@ def run_ours(args, rank, world, local_rank):
         streams.append(torch.cuda.ExternalStream(c2.stream(), device=torch.device("cuda", local_rank)))
     for cx in ctxs:
         cx.upload(wl["imgs"], wl["Ts"], wl["boxes"], wl["lines"], params)
+    # NCCL communicators owned by the library, one per context (the top-K all-gather is issued on that context's stream)
     if world > 1:
-        assert len(ctxs) == 1, "--inflight > 1 is a single-GPU option (the NCCL communicator belongs to one context)"
+        nccl_path = None
+        for d in sys.path:
+            cand = os.path.join(d, "nvidia", "nccl", "lib", "libnccl.so.2")
+            if os.path.exists(cand):
+                nccl_path = cand
+                break
+        for cx in ctxs:
+            uid = np.zeros(128, np.uint8)
+            if rank == 0:
+                cx.check(cx.L.cs_comm_unique_id(cx.h, (nccl_path or "").encode(), _lib.ptr(uid, C.c_uint8)))
+            t = torch.from_numpy(uid).cuda()
+            dist.broadcast(t, 0)
+            uid = t.cpu().numpy()
+            cx.check(cx.L.cs_comm_init(cx.h, (nccl_path or "").encode(), _lib.ptr(uid, C.c_uint8), world, rank))
+        n_obj = torch.tensor([sum(len(b) for b in wl["boxes"])], device="cuda")
+        dist.all_reduce(n_obj, op=dist.ReduceOp.MAX)
+        recs_per_rank = int(n_obj.item()) * topk
     ctx.set_profiling(True)
 
     def step_i(i):
         cx = ctxs[i % len(ctxs)]
         cx.run_async()
         if world > 1:
-            ctx.check(ctx.L.cs_allgather_topk(ctx.h, recs_per_rank, C.byref(gathered)))
+            cx.check(cx.L.cs_allgather_topk(cx.h, recs_per_rank, C.byref(gathered)))
 
     for i in range(max(args.warmup, 3) * len(ctxs)):
         step_i(i)
@@ -306,7 +305,8 @@ def run_ours(args, rank, world, local_rank):
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(stream)
     t0 = time.perf_counter()
-    for _ in range(args.steps):
+    e2e_steps = max(3, min(args.steps, 50))
+    for _ in range(e2e_steps):
         step_e2e()
     e1.record(stream)
     barrier()
@@ -315,7 +315,7 @@ def run_ours(args, rank, world, local_rank):
     e2e_t = torch.tensor([e2e_ms], device="cuda", dtype=torch.float64)
     if world > 1:
         dist.all_reduce(e2e_t, op=dist.ReduceOp.MAX)
-    e2e_ms_step = float(e2e_t.item()) / args.steps
+    e2e_ms_step = float(e2e_t.item()) / e2e_steps
     h2d = wl["imgs"].nbytes + sum(l.nbytes for l in wl["lines"]) + wl["Ts"].nbytes + sum(b.nbytes for b in wl["boxes"])
     d2h = out.nbytes + counts.nbytes
 
@@ -357,7 +357,7 @@ def run_ours(args, rank, world, local_rank):
                    "parallelism": "frames sharded x%d, one NCCL all-gather of top-K" % world if world > 1 else "single GPU",
                    "batches_in_flight": len(ctxs)},
         "e2e": {"value": n_valid_all / (e2e_ms_step * 1e-3), "unit": "proposals/s", "frames_per_s": n_frames_all / (e2e_ms_step * 1e-3),
-                "ms_per_step": e2e_ms_step, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)},
+                "ms_per_step": e2e_ms_step, "steps": e2e_steps, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)},
         "gpu_launches": int(stats["n_kernel_launches"]) * args.steps,
         "roofline": roofline, "cpu_baseline": cpu, "online": online, "clocks": sampler.summary(),
     }
@@ -369,22 +369,22 @@ def run_ours(args, rank, world, local_rank):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--steps", type=int, default=None)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="c3", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-online", action="store_true")
-    ap.add_argument("--inflight", type=int, default=2, help="batches in flight on one GPU (contexts driven round-robin)")
+    ap.add_argument("--inflight", type=int, default=3, help="batches in flight on one GPU (contexts driven round-robin)")
     args = ap.parse_args()
+    if args.steps is None:
+        args.steps = 1000 if args.impl == "ours" else 5
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     if args.impl == "reference":
         run_reference_arm(args, rank, world)
         return
-    if world > 1:
-        args.inflight = 1
     if world == 1 and args.gpus > 1:
         # convenience: python bench.py --gpus N re-launches itself under torchrun
         cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(args.gpus), "--master-addr", "127.0.0.1",
