@@ -162,7 +162,7 @@ __global__ void __launch_bounds__(256) k_lsd_resize(const double *__restrict__ b
 }
 
 __global__ void __launch_bounds__(256) k_lsd_grad(const double *__restrict__ scaled, int n_frames, int W, int H, double threshold,
-                                                  double *__restrict__ modgrad, double *__restrict__ angles,
+                                                  double *__restrict__ modgrad, double *__restrict__ angles, float2 *__restrict__ cs_angle,
                                                   unsigned long long *__restrict__ max_bits)
 {
     const int64_t total = (int64_t)n_frames * W * H;
@@ -184,6 +184,14 @@ __global__ void __launch_bounds__(256) k_lsd_grad(const double *__restrict__ sca
         }
         modgrad[p] = norm;
         angles[p] = ang;
+        /* (cos, sin) of float(angle), each the correctly rounded float: what region_grow accumulates (lsd.cpp:680-681) */
+        float2 cs = make_float2(0.f, 0.f);
+        if (ang != LSD_NOTDEF) {
+            const double af = (double)(float)ang;
+            cs.x = (float)cos(af);
+            cs.y = (float)sin(af);
+        }
+        cs_angle[p] = cs;
     }
 }
 
@@ -194,7 +202,7 @@ __device__ __forceinline__ double bin_coef_of(unsigned long long max_bits)
 }
 
 /* per (frame, chunk of rows) histogram of gradient bins */
-__global__ void __launch_bounds__(256) k_lsd_hist(const double *__restrict__ modgrad, int W, int H, int n_chunks,
+__global__ void __launch_bounds__(256) k_lsd_hist(const double *__restrict__ modgrad, const double *__restrict__ angles, int W, int H, int n_chunks,
                                                   const unsigned long long *__restrict__ max_bits, int32_t *__restrict__ cnt)
 {
     __shared__ int s_h[LSD_NBINS];
@@ -204,10 +212,11 @@ __global__ void __launch_bounds__(256) k_lsd_hist(const double *__restrict__ mod
     const double coef = bin_coef_of(max_bits[f]);
     const int y0 = ch * LSD_CHUNK_ROWS, y1 = min(y0 + LSD_CHUNK_ROWS, H - 1);
     const double *mg = modgrad + (size_t)f * W * H;
+    const double *an = angles + (size_t)f * W * H;
     const int npx = (y1 - y0) * (W - 1);
     for (int i = threadIdx.x; i < npx; i += 256) {
         const int y = y0 + i / (W - 1), x = i % (W - 1);
-        atomicAdd(&s_h[(int)(mg[(size_t)y * W + x] * coef)], 1);
+        if (an[(size_t)y * W + x] != LSD_NOTDEF) atomicAdd(&s_h[(int)(mg[(size_t)y * W + x] * coef)], 1);
     }
     __syncthreads();
     int32_t *o = cnt + ((size_t)f * n_chunks + ch) * LSD_NBINS;
@@ -243,7 +252,7 @@ __global__ void __launch_bounds__(LSD_NBINS) k_lsd_scan(int n_chunks, int32_t *_
 }
 
 /* stable scatter: one warp walks its chunk in raster order, 32 pixels per step */
-__global__ void __launch_bounds__(32) k_lsd_scatter(const double *__restrict__ modgrad, int W, int H, int n_chunks,
+__global__ void __launch_bounds__(32) k_lsd_scatter(const double *__restrict__ modgrad, const double *__restrict__ angles, int W, int H, int n_chunks,
                                                     const unsigned long long *__restrict__ max_bits, const int32_t *__restrict__ cnt,
                                                     int32_t *__restrict__ list)
 {
@@ -256,16 +265,18 @@ __global__ void __launch_bounds__(32) k_lsd_scatter(const double *__restrict__ m
     const double coef = bin_coef_of(max_bits[f]);
     const int y0 = ch * LSD_CHUNK_ROWS, y1 = min(y0 + LSD_CHUNK_ROWS, H - 1);
     const double *mg = modgrad + (size_t)f * W * H;
+    const double *an = angles + (size_t)f * W * H;
     int32_t *out = list + (size_t)f * W * H;
     const int npx = (y1 - y0) * (W - 1);
     for (int i0 = 0; i0 < npx; i0 += 32) {
         const int i = i0 + lane;
-        const bool ok = i < npx;
+        bool ok = i < npx;
         int addr = 0, bin = -1 - lane; /* inactive lanes get unique negative keys */
         if (ok) {
             const int y = y0 + i / (W - 1), x = i % (W - 1);
             addr = y * W + x;
-            bin = (int)(mg[addr] * coef);
+            ok = an[addr] != LSD_NOTDEF;
+            if (ok) bin = (int)(mg[addr] * coef);
         }
         const unsigned m = __match_any_sync(0xffffffffu, bin);
         const int rank = __popc(m & ((1u << lane) - 1u));
@@ -286,6 +297,7 @@ struct LsdFrame {
     int W, H;
     const double *angles;
     const double *modgrad;
+    const float2 *cs_angle;
     uint8_t *used;
     int32_t *reg;
     double LOG_NT;
@@ -400,16 +412,16 @@ __device__ void lsd_region_grow(const LsdFrame &F, int s_addr, int &reg_size, do
             const unsigned ok = __ballot_sync(FULL, cand && ((pending >> lane) & 1u) && lsd_aligned_val(a, reg_angle, prec));
             if (!ok) break;
             const int fl = __ffs(ok) - 1;
-            const double af = __shfl_sync(FULL, a, fl);
             const int addrf = __shfl_sync(FULL, c_addr, fl);
             if (lane == 0) {
                 F.used[addrf] = 1;
                 F.reg[reg_size] = addrf;
             }
             ++reg_size;
-            /* cos(float(angle)) pinned to the correctly rounded float */
-            sumdx += (float)cos((double)(float)af);
-            sumdy += (float)sin((double)(float)af);
+            /* cos(float(angle)), sin(float(angle)): precomputed per pixel by k_lsd_grad (pinned to the correctly rounded float) */
+            const float2 csf = F.cs_angle[addrf];
+            sumdx += csf.x;
+            sumdy += csf.y;
             reg_angle = (double)fast_atan2(sumdy, sumdx) * LSD_DEG2RAD;
             pending &= ~((2u << fl) - 1u);
         }
@@ -728,7 +740,7 @@ __device__ double lsd_rect_improve(const LsdFrame &F, LsdRect &rec)
 /* The seed loop of flsd (lsd.cpp:476-535) + the KeyLine filters of LSDDetector::detectImpl (:205-256) and filter_lines.
  * One warp per frame. */
 __global__ void __launch_bounds__(32) k_lsd_grow(int W, int H, int img_w, int img_h, const double *__restrict__ angles_all,
-                                                 const double *__restrict__ modgrad_all, uint8_t *__restrict__ used_all,
+                                                 const double *__restrict__ modgrad_all, const float2 *__restrict__ cs_all, uint8_t *__restrict__ used_all,
                                                  int32_t *__restrict__ reg_all, const int32_t *__restrict__ list_all,
                                                  const int32_t *__restrict__ list_len, double LOG_NT, int min_reg_size, double prec, double p,
                                                  double scale, float line_length_thres, float *__restrict__ raw_all, int32_t *__restrict__ n_raw_all,
@@ -741,6 +753,7 @@ __global__ void __launch_bounds__(32) k_lsd_grow(int W, int H, int img_w, int im
     F.H = H;
     F.angles = angles_all + f * npx;
     F.modgrad = modgrad_all + f * npx;
+    F.cs_angle = cs_all + f * npx;
     F.used = used_all + f * npx;
     F.reg = reg_all + f * npx;
     F.LOG_NT = LOG_NT;
@@ -759,7 +772,7 @@ __global__ void __launch_bounds__(32) k_lsd_grow(int W, int H, int img_w, int im
         bool seed = false;
         if (i < n_list) {
             adx = list[i];
-            seed = (F.used[adx] == 0) && (F.angles[adx] != LSD_NOTDEF);
+            seed = (F.used[adx] == 0); /* the list holds pixels with a defined angle only */
         }
         unsigned todo = __ballot_sync(0xffffffffu, seed);
         while (todo) {
@@ -830,7 +843,7 @@ struct Buf {
 };
 
 struct LsdState {
-    Buf img, tmp, blur, scaled, modgrad, angles, used, list, reg, maxg, cnt, llen, raw, nraw, out, nout;
+    Buf img, tmp, blur, scaled, modgrad, angles, csang, used, list, reg, maxg, cnt, llen, raw, nraw, out, nout;
     int last_frames = 0, last_W = 0, last_H = 0, cap = 0;
 };
 
@@ -866,7 +879,7 @@ int lsd_run(cs_ctx *c, const uint8_t *imgs, bool imgs_on_device, int n_frames, i
         d_img = (const uint8_t *)S.img.p;
     }
     if ((rc = ensure(c, S.tmp, px * 8)) || (rc = ensure(c, S.blur, px * 8)) || (rc = ensure(c, S.scaled, spx * 8)) ||
-        (rc = ensure(c, S.modgrad, spx * 8)) || (rc = ensure(c, S.angles, spx * 8)) || (rc = ensure(c, S.used, spx)) ||
+        (rc = ensure(c, S.modgrad, spx * 8)) || (rc = ensure(c, S.angles, spx * 8)) || (rc = ensure(c, S.csang, spx * 8)) || (rc = ensure(c, S.used, spx)) ||
         (rc = ensure(c, S.list, spx * 4)) || (rc = ensure(c, S.reg, spx * 4)) || (rc = ensure(c, S.maxg, (size_t)n_frames * 8)) ||
         (rc = ensure(c, S.cnt, (size_t)n_frames * n_chunks * LSD_NBINS * 4)) || (rc = ensure(c, S.llen, (size_t)n_frames * 4)) ||
         (rc = ensure(c, S.raw, (size_t)n_frames * cap * 16)) || (rc = ensure(c, S.nraw, (size_t)n_frames * 4)) ||
@@ -884,12 +897,13 @@ int lsd_run(cs_ctx *c, const uint8_t *imgs, bool imgs_on_device, int n_frames, i
     k_lsd_vblur<<<grid_for((int64_t)px), 256, 0, st>>>((const double *)S.tmp.p, n_frames, w, h, (double *)S.blur.p);
     k_lsd_resize<<<grid_for((int64_t)spx), 256, 0, st>>>((const double *)S.blur.p, n_frames, w, h, W, H, 1. / SCALE, (double *)S.scaled.p);
     k_lsd_grad<<<grid_for((int64_t)spx), 256, 0, st>>>((const double *)S.scaled.p, n_frames, W, H, rho, (double *)S.modgrad.p, (double *)S.angles.p,
-                                                       (unsigned long long *)S.maxg.p);
-    k_lsd_hist<<<n_frames * n_chunks, 256, 0, st>>>((const double *)S.modgrad.p, W, H, n_chunks, (const unsigned long long *)S.maxg.p, (int32_t *)S.cnt.p);
+                                                       (float2 *)S.csang.p, (unsigned long long *)S.maxg.p);
+    k_lsd_hist<<<n_frames * n_chunks, 256, 0, st>>>((const double *)S.modgrad.p, (const double *)S.angles.p, W, H, n_chunks, (const unsigned long long *)S.maxg.p, (int32_t *)S.cnt.p);
     k_lsd_scan<<<n_frames, LSD_NBINS, 0, st>>>(n_chunks, (int32_t *)S.cnt.p, (int32_t *)S.llen.p);
-    k_lsd_scatter<<<n_frames * n_chunks, 32, 0, st>>>((const double *)S.modgrad.p, W, H, n_chunks, (const unsigned long long *)S.maxg.p,
+    k_lsd_scatter<<<n_frames * n_chunks, 32, 0, st>>>((const double *)S.modgrad.p, (const double *)S.angles.p, W, H, n_chunks, (const unsigned long long *)S.maxg.p,
                                                       (const int32_t *)S.cnt.p, (int32_t *)S.list.p);
-    k_lsd_grow<<<n_frames, 32, 0, st>>>(W, H, w, h, (const double *)S.angles.p, (const double *)S.modgrad.p, (uint8_t *)S.used.p, (int32_t *)S.reg.p,
+    k_lsd_grow<<<n_frames, 32, 0, st>>>(W, H, w, h, (const double *)S.angles.p, (const double *)S.modgrad.p, (const float2 *)S.csang.p, (uint8_t *)S.used.p,
+                                        (int32_t *)S.reg.p,
                                         (const int32_t *)S.list.p, (const int32_t *)S.llen.p, LOG_NT, min_reg_size, prec, p, SCALE, line_length_thres,
                                         (float *)S.raw.p, (int32_t *)S.nraw.p, (float *)S.out.p, (int32_t *)S.nout.p, cap);
     cs_ctx_count_launches(c, 8);
@@ -925,7 +939,7 @@ int cs_lsd_run_device(cs_ctx *c, const uint8_t *d_imgs, int n_frames, int w, int
 void cs_lsd_destroy(void *state)
 {
     LsdState *S = (LsdState *)state;
-    Buf *all[] = {&S->img, &S->tmp, &S->blur, &S->scaled, &S->modgrad, &S->angles, &S->used, &S->list, &S->reg, &S->maxg, &S->cnt, &S->llen, &S->raw, &S->nraw, &S->out, &S->nout};
+    Buf *all[] = {&S->img, &S->tmp, &S->blur, &S->scaled, &S->modgrad, &S->angles, &S->csang, &S->used, &S->list, &S->reg, &S->maxg, &S->cnt, &S->llen, &S->raw, &S->nraw, &S->out, &S->nout};
     for (Buf *b : all)
         if (b->p) cudaFree(b->p);
     delete S;
