@@ -392,39 +392,52 @@ __device__ void lsd_region_grow(const LsdFrame &F, int s_addr, int &reg_size, do
         F.used[s_addr] = 1;
     }
     __syncwarp();
-    const int ky = lane / 3 - 1, kx = lane - (lane / 3) * 3 - 1; /* lanes 0..8: (yy, xx) in the reference's loop order */
-    for (int i = 0; i < reg_size; ++i) {
-        const int pa = F.reg[i];
-        const int py = pa / F.W, px = pa - py * F.W;
-        const int yy = py + ky, xx = px + kx;
+    /* Three region points per round: lanes 9g..9g+8 fetch the 3x3 neighbourhood of point i+g (used flag, angle, cos/sin) in one
+     * go, then the points are consumed strictly in order.  A neighbour claimed while an earlier point of the round is consumed is
+     * struck from the later groups, so the sequence of additions is exactly the reference's. */
+    const int grp = lane / 9, kk = lane - grp * 9;
+    const int ky = kk / 3 - 1, kx = kk - (kk / 3) * 3 - 1; /* (yy, xx) in the reference's loop order */
+    for (int i = 0; i < reg_size;) {
+        const int navail = min(3, reg_size - i);
         bool cand = false;
-        int c_addr = 0;
+        int c_addr = -1;
         double a = LSD_NOTDEF;
-        if (lane < 9 && yy >= 0 && yy < F.H && xx >= 0 && xx < F.W) {
-            c_addr = yy * F.W + xx;
-            if (F.used[c_addr] != 1) {
-                a = F.angles[c_addr];
-                cand = (a != LSD_NOTDEF);
+        float2 csf = make_float2(0.f, 0.f);
+        if (grp < navail) {
+            const int pa = F.reg[i + grp];
+            const int py = pa / F.W, px = pa - py * F.W;
+            const int yy = py + ky, xx = px + kx;
+            if (yy >= 0 && yy < F.H && xx >= 0 && xx < F.W) {
+                c_addr = yy * F.W + xx;
+                if (F.used[c_addr] != 1) {
+                    a = F.angles[c_addr];
+                    cand = (a != LSD_NOTDEF);
+                    if (cand) csf = F.cs_angle[c_addr];
+                }
             }
         }
-        unsigned pending = __ballot_sync(FULL, cand);
-        while (pending) {
-            const unsigned ok = __ballot_sync(FULL, cand && ((pending >> lane) & 1u) && lsd_aligned_val(a, reg_angle, prec));
-            if (!ok) break;
-            const int fl = __ffs(ok) - 1;
-            const int addrf = __shfl_sync(FULL, c_addr, fl);
-            if (lane == 0) {
-                F.used[addrf] = 1;
-                F.reg[reg_size] = addrf;
+        for (int g = 0; g < navail; g++) {
+            unsigned pending = __ballot_sync(FULL, cand && grp == g);
+            while (pending) {
+                const unsigned ok = __ballot_sync(FULL, cand && ((pending >> lane) & 1u) && lsd_aligned_val(a, reg_angle, prec));
+                if (!ok) break;
+                const int fl = __ffs(ok) - 1;
+                const int addrf = __shfl_sync(FULL, c_addr, fl);
+                const float cx = __shfl_sync(FULL, csf.x, fl), cy = __shfl_sync(FULL, csf.y, fl);
+                if (lane == 0) {
+                    F.used[addrf] = 1;
+                    F.reg[reg_size] = addrf;
+                }
+                ++reg_size;
+                /* cos(float(angle)), sin(float(angle)): precomputed per pixel by k_lsd_grad (pinned to the correctly rounded float) */
+                sumdx += cx;
+                sumdy += cy;
+                reg_angle = (double)fast_atan2(sumdy, sumdx) * LSD_DEG2RAD;
+                pending &= ~((2u << fl) - 1u);
+                if (c_addr == addrf) cand = false; /* the same pixel seen from a later point of this round */
             }
-            ++reg_size;
-            /* cos(float(angle)), sin(float(angle)): precomputed per pixel by k_lsd_grad (pinned to the correctly rounded float) */
-            const float2 csf = F.cs_angle[addrf];
-            sumdx += csf.x;
-            sumdy += csf.y;
-            reg_angle = (double)fast_atan2(sumdy, sumdx) * LSD_DEG2RAD;
-            pending &= ~((2u << fl) - 1u);
         }
+        i += navail;
         __syncwarp();
     }
 }
