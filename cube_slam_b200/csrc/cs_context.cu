@@ -87,6 +87,7 @@ struct cs_ctx {
     cs_batch_stats stats;
 
     void *lsd_state = nullptr; /* line-detector workspace (cs_lsd.cu) */
+    void *edl_state = nullptr; /* EDLines workspace (cs_edlines.cu) */
     int64_t line_launches = 0;
 
     /* NCCL (loaded at run time) */
@@ -100,6 +101,7 @@ struct cs_ctx {
 cudaStream_t cs_ctx_stream(cs_ctx *c) { return c->stream; }
 int cs_ctx_device(cs_ctx *c) { return c->device; }
 void **cs_ctx_lsd_slot(cs_ctx *c) { return &c->lsd_state; }
+void **cs_ctx_edl_slot(cs_ctx *c) { return &c->edl_state; }
 void cs_ctx_count_launches(cs_ctx *c, int64_t n) { c->line_launches += n; }
 int cs_ctx_fail(cs_ctx *c, int code, const char *fmt, ...)
 {
@@ -387,10 +389,14 @@ int run_batch(cs_ctx *c, bool sync)
     const int32_t *d_nlines = nullptr;
     mark(ST_LSD);
     if (c->online_lines) { /* line_lbd_detect::detect_filter_lines on the resident frames (object_slam main_obj.cpp:428) */
-        if ((rc = cs_lsd_run_device(c, (const uint8_t *)c->d_img.p, c->n_frames, c->w, c->h, c->stride, c->channels, c->line_prm.line_length_thres,
-                                    c->online_cap, &d_lines_f32, &d_nlines)))
+        if (c->line_prm.use_LSD) {
+            if ((rc = cs_lsd_run_device(c, (const uint8_t *)c->d_img.p, c->n_frames, c->w, c->h, c->stride, c->channels, c->line_prm.line_length_thres,
+                                        c->online_cap, &d_lines_f32, &d_nlines)))
+                return rc;
+            c->launches += 8;
+        } else if ((rc = cs_edl_run(c, (const uint8_t *)c->d_img.p, true, c->n_frames, c->w, c->h, c->stride, c->channels,
+                                    c->line_prm.line_length_thres, c->online_cap, &d_lines_f32, &d_nlines)))
             return rc;
-        c->launches += 8;
     }
     /* fork: the per-ROI line selection / merging only needs the lines and the job table */
     cudaEventRecord(c->ev_fork, st);
@@ -486,7 +492,6 @@ int store_batch(cs_ctx *c, const uint8_t *imgs, int n_frames, int width, int hei
     c->prepared = false;
     c->online_lines = online != nullptr;
     if (online) {
-        if (!online->use_LSD) return fail(c, CS_ERR_UNSUPPORTED, "EDLines flavour (use_LSD = false) is not implemented yet");
         if (online->numoctaves != 1) return fail(c, CS_ERR_UNSUPPORTED, "only one octave is supported");
         c->line_prm = *online;
         c->online_cap = std::max(64, std::min(c->max_lines > 0 ? c->max_lines : 1024, 4096));
@@ -616,6 +621,7 @@ void cs_destroy(cs_ctx *c)
     cudaStreamSynchronize(c->stream);
     cs_nccl_teardown(c);
     if (c->lsd_state) cs_lsd_destroy(c->lsd_state);
+    if (c->edl_state) cs_edl_destroy(c->edl_state);
     DevBuf *all[] = {&c->d_img,   &c->d_gray,  &c->d_lines,  &c->d_frames, &c->d_poses,   &c->d_yaws, &c->d_jobs, &c->d_objs,
                      &c->d_blocks, &c->d_blocks4, &c->d_dtids, &c->d_tilejob, &c->d_bits, &c->d_dist, &c->d_mlines, &c->d_lcounts, &c->d_err,
                      &c->d_cvalid, &c->d_cdist, &c->d_cangle, &c->d_cskew, &c->d_vlist,  &c->d_key,     &c->d_idx,  &c->d_flag, &c->d_keep,  &c->d_norm,

@@ -968,18 +968,25 @@ int cs_detect_lines_batch(cs_ctx *c, const uint8_t *imgs, int n_frames, int widt
         return cs_ctx_fail(c, CS_ERR_INVALID_ARG, "null or empty argument");
     if (channels != 1 && channels != 3) return cs_ctx_fail(c, CS_ERR_INVALID_ARG, "channels must be 1 or 3"); /* LSDDetector.cpp:163-164 throws on depth != 0 */
     if (stride < width * channels) return cs_ctx_fail(c, CS_ERR_INVALID_ARG, "stride smaller than a row");
-    if (!params->use_LSD) return cs_ctx_fail(c, CS_ERR_UNSUPPORTED, "EDLines flavour (use_LSD = false) is not implemented yet; set use_LSD = 1");
     if (params->numoctaves != 1) return cs_ctx_fail(c, CS_ERR_UNSUPPORTED, "only one octave is supported (filter_lines keeps octave 0 only)");
     cudaSetDevice(cs_ctx_device(c));
-    LsdState *S = state_of(c);
-    int rc = lsd_run(c, imgs, false, n_frames, width, height, stride, channels, params->line_length_thres, max_lines_per_frame, *S);
+    const float *d_out = nullptr;
+    const int32_t *d_nout = nullptr;
+    int rc;
+    if (params->use_LSD) {
+        LsdState *S = state_of(c);
+        rc = lsd_run(c, imgs, false, n_frames, width, height, stride, channels, params->line_length_thres, max_lines_per_frame, *S);
+        d_out = (const float *)S->out.p;
+        d_nout = (const int32_t *)S->nout.p;
+    } else
+        rc = cs_edl_run(c, imgs, false, n_frames, width, height, stride, channels, params->line_length_thres, max_lines_per_frame, &d_out, &d_nout);
     if (rc) return rc;
     cudaStream_t st = cs_ctx_stream(c);
     std::vector<int32_t> cnt(n_frames);
-    if (cudaMemcpyAsync(cnt.data(), S->nout.p, (size_t)n_frames * 4, cudaMemcpyDeviceToHost, st) != cudaSuccess ||
-        cudaMemcpyAsync(lines_xyxy, S->out.p, (size_t)n_frames * max_lines_per_frame * 16, cudaMemcpyDeviceToHost, st) != cudaSuccess ||
+    if (cudaMemcpyAsync(cnt.data(), d_nout, (size_t)n_frames * 4, cudaMemcpyDeviceToHost, st) != cudaSuccess ||
+        cudaMemcpyAsync(lines_xyxy, d_out, (size_t)n_frames * max_lines_per_frame * 16, cudaMemcpyDeviceToHost, st) != cudaSuccess ||
         cudaStreamSynchronize(st) != cudaSuccess)
-        return cs_ctx_fail(c, CS_ERR_CUDA, "LSD result copy failed: %s", cudaGetErrorString(cudaGetLastError()));
+        return cs_ctx_fail(c, CS_ERR_CUDA, "line result copy failed: %s", cudaGetErrorString(cudaGetLastError()));
     for (int f = 0; f < n_frames; f++) {
         if (cnt[f] > max_lines_per_frame) return cs_ctx_fail(c, CS_ERR_CAPACITY, "frame %d: %d segments exceed max_lines_per_frame", f, cnt[f]);
         n_lines[f] = cnt[f];

@@ -192,6 +192,10 @@ int cs_detect_lines_batch(cs_ctx *ctx, const uint8_t *imgs, int n_frames, int wi
 /* inspection of the last cs_detect_lines[_batch] run (tests): intermediate images of one frame; any pointer may be NULL */
 int cs_debug_lsd(cs_ctx *ctx, int frame, int32_t scaled_wh[2], double *scaled, double *modgrad, double *angles, int32_t *list,
                  int32_t *list_len, float *raw_lines, int32_t *n_raw, int cap_raw);
+/* same for the EDLines flavour (use_LSD = 0): EDLineDetector's maps (binary_descriptor.cpp:1617-1666: blurred image, dxImg_, dyImg_,
+ * gImgWO_ / 4, dirImg_), the anchors in scan order as y * width + x, the edge map after smart routing, the segments before the length filter */
+int cs_debug_edlines(cs_ctx *ctx, int frame, uint8_t *blur, int16_t *dx, int16_t *dy, int16_t *g, uint8_t *dir, int32_t *anchors,
+                     int32_t *n_anchors, uint8_t *edge, float *raw_lines, int32_t *n_raw, int cap_raw);
 
 /* ---- multi-GPU -------------------------------------------------------------------------- */
 /* Frames shard across ranks; the only exchange is one all-gather of the top-K record buffers.

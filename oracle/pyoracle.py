@@ -261,3 +261,33 @@ def lsd_detect(img, line_length_thres=15.0, cap=8192, want_stages=False, refine_
         st["list"] = st["list"][:ll.value].copy()
         res["stages"] = st
     return res
+
+
+# ------------------------------------------------------------------------------------------- EDLines
+def edl_detect(img, line_length_thres=50.0, cap=8192, want_stages=False):
+    """line_lbd_detect::detect_filter_lines with use_LSD = false (EDLines, the class default) -> n x 4 float32."""
+    img = np.ascontiguousarray(img, np.uint8)
+    h, w = img.shape[:2]
+    ch = 1 if img.ndim == 2 else img.shape[2]
+    out = np.zeros((cap, 4), np.float32)
+    raw = np.zeros((cap, 4), np.float32)
+    n_raw = C.c_int(0)
+    st = None
+    args = [None] * 8
+    if want_stages:
+        st = dict(blur=np.zeros((h, w), np.uint8), dx=np.zeros((h, w), np.int16), dy=np.zeros((h, w), np.int16), g=np.zeros((h, w), np.int16),
+                  dir=np.zeros((h, w), np.uint8), anchors=np.zeros(w * h // 4 + 16, np.int32), edge=np.zeros((h, w), np.uint8))
+        na = C.c_int(0)
+        args = [_p(st["blur"], C.c_uint8), _p(st["dx"], C.c_int16), _p(st["dy"], C.c_int16), _p(st["g"], C.c_int16), _p(st["dir"], C.c_uint8),
+                _p(st["anchors"], C.c_int32), C.byref(na), _p(st["edge"], C.c_uint8)]
+    L = lib()
+    L.edl_orc_detect.restype = C.c_int
+    n = L.edl_orc_detect(_p(img, C.c_uint8), w, h, img.strides[0], ch, C.c_float(line_length_thres), _p(out, C.c_float), cap,
+                         _p(raw, C.c_float), cap, C.byref(n_raw), *args)
+    if n < 0:
+        raise RuntimeError("edl_orc_detect failed (%d)" % n)
+    res = dict(lines=out[:min(n, cap)].copy(), raw_lines=raw[:min(n_raw.value, cap)].copy())
+    if want_stages:
+        st["anchors"] = st["anchors"][:na.value].copy()
+        res["stages"] = st
+    return res

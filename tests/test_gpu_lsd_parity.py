@@ -63,7 +63,8 @@ def test_synthetic_and_gray_input(det, oracle):
 def test_unsupported_modes_fail_loudly(det):
     import cube_slam_b200 as cs
     d = cs.line_lbd_detect(context=det._ctx)
-    d.use_LSD = False
+    d.use_LSD = True
+    d.numoctaves_ = 2             # filter_lines keeps octave 0 only; other octaves are never produced here
     with pytest.raises(cs.CubeSlamError, match="UNSUPPORTED"):
         d.detect_filter_lines(np.zeros((64, 64), np.uint8))
 
