@@ -7,7 +7,7 @@
  *   filter_lines + keylines_to_mat         line_lbd/class/line_lbd_allclass.cpp:26-36,200-221
  *
  * Streaming stages (one thread per pixel, FP64, evaluation order of OpenCV's C paths, -fmad=false):
- *   k_lsd_hblur   cvtColor + horizontal 7-tap Gaussian (sigma 0.75)      lsd.cpp:452-457
+ *   k_lsd_hblur   cvtColor + horizontal 7-tap Gaussian (sigma 0.6/0.8)      lsd.cpp:452-457
  *   k_lsd_vblur   vertical 7-tap                                          lsd.cpp:457
  *   k_lsd_resize  cv::resize(x0.8, INTER_LINEAR) on doubles               lsd.cpp:459
  *   k_lsd_grad    2x2 gradient, modulus, fastAtan2 angle, max modulus     lsd.cpp:562-586
@@ -43,9 +43,9 @@
 
 namespace {
 
-/* cv2 4.x getGaussianKernel(7, 0.75, CV_64F) */
-__constant__ double c_gauss7[7] = {0x1.763496d347539p-13, 0x1.f1e23259cfdc7p-7, 0x1.bfd7fac1bd5a9p-3, 0x1.10562a79786afp-1,
-                                   0x1.bfd7fac1bd5a9p-3, 0x1.f1e23259cfdc7p-7, 0x1.763496d347539p-13};
+/* cv2 4.x getGaussianKernel(7, 0.6 / 0.8, CV_64F): lsd.cpp:453 divides, sigma = 0.7499999999999999, not 0.75 */
+__constant__ double c_gauss7[7] = {0x1.763496d347532p-13, 0x1.f1e23259cfdc1p-7, 0x1.bfd7fac1bd5a8p-3, 0x1.10562a79786afp-1,
+                                   0x1.bfd7fac1bd5a8p-3, 0x1.f1e23259cfdc1p-7, 0x1.763496d347532p-13};
 
 __device__ __forceinline__ int reflect101(int p, int n)
 {

@@ -8,9 +8,9 @@
  *                                                                 scale 0.8, sigma_scale 0.6, quant 2, ang_th 22.5, log_eps 0,
  *                                                                 density_th 0.7, n_bins 1024 -- LSDDetector.cpp:173 ignores LSDOptions)
  * including the vendored quirks (rect_nfa's tailp->p.x-for-p.y slip and integer step slopes, lsd.cpp:1057-1065).
- * OpenCV calls inside (GaussianBlur 7x7 sigma 0.75 on CV_64F, resize INTER_LINEAR x0.8 on CV_64F, fastAtan2, cvtColor) are
+ * OpenCV calls inside (GaussianBlur 7x7 sigma 0.6/0.8 on CV_64F, resize INTER_LINEAR x0.8 on CV_64F, fastAtan2, cvtColor) are
  * restated from OpenCV's algorithms and pinned against the in-container cv2 4.13 (tests/test_oracle_lsd.py).
- * The Gaussian kernel is cv2 4.13's bit-exact getGaussianKernel(7, 0.75) (it differs from exp()-based kernels in the last ulp).
+ * The Gaussian kernel is cv2 4.13's bit-exact getGaussianKernel(7, 0.6 / 0.8) (sigma = 0.7499999999999999, lsd.cpp:453) (it differs from exp()-based kernels in the last ulp).
  *
  * PARITY: "parity unpinned" by the reference (no tests / goldens; cannot be compiled here).
  */
@@ -64,10 +64,10 @@ inline int reflect101(int p, int n)
     return p;
 }
 
-/* cv::GaussianBlur(CV_64F, 7x7, sigma 0.75, BORDER_REFLECT_101): row filter (k = 0..6 in order), then the symmetric column
+/* cv::GaussianBlur(CV_64F, 7x7, sigma 0.6/0.8, BORDER_REFLECT_101): row filter (k = 0..6 in order), then the symmetric column
  * filter (centre tap first, then ky[k] * (below + above)) -- the operation order of OpenCV's generic C paths */
-const double kGauss7[7] = {0x1.763496d347539p-13, 0x1.f1e23259cfdc7p-7, 0x1.bfd7fac1bd5a9p-3, 0x1.10562a79786afp-1,
-                           0x1.bfd7fac1bd5a9p-3, 0x1.f1e23259cfdc7p-7, 0x1.763496d347539p-13};
+const double kGauss7[7] = {0x1.763496d347532p-13, 0x1.f1e23259cfdc1p-7, 0x1.bfd7fac1bd5a8p-3, 0x1.10562a79786afp-1,
+                           0x1.bfd7fac1bd5a8p-3, 0x1.f1e23259cfdc1p-7, 0x1.763496d347532p-13};
 
 void gaussian_blur7(const std::vector<double> &src, int w, int h, std::vector<double> &dst)
 {
