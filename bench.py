@@ -219,7 +219,9 @@ def run_ours(args, rank, world, local_rank):
         n_obj = torch.tensor([sum(len(b) for b in wl["boxes"])], device="cuda")
         dist.all_reduce(n_obj, op=dist.ReduceOp.MAX)
         recs_per_rank = int(n_obj.item()) * topk
-    ctx.set_profiling(True)
+    dbg_flags = (16 if args.no_prio else 0) | (32 if args.raster_dt else 0)
+    for cx in ctxs:
+        cx.set_profiling(dbg_flags)
 
     def step_i(i):
         cx = ctxs[i % len(ctxs)]
@@ -248,6 +250,7 @@ def run_ours(args, rank, world, local_rank):
     barrier()
     ms_total = max(ev0.elapsed_time(e) for e in ev_end)
     # per-stage CUDA-event times of one more (profiled, alone) step
+    ctx.set_profiling(1 | dbg_flags)
     ctx.run()
     stage_acc = ctx.stage_ms()
     sampler.stop_flag = True
@@ -264,28 +267,30 @@ def run_ours(args, rank, world, local_rank):
     # ---- online mode (object_slam main_obj.cpp:424-450): lines detected on the resident frames by the LSD kernels, N = 1 only
     online = None
     if world == 1 and not args.no_online:
-        det = cs.line_lbd_detect(context=ctx)
-        det.use_LSD = True
-        det.line_length_thres = 15
-        lp = det.params()
-        ctx.upload_online(wl["imgs"], wl["Ts"], wl["boxes"], lp, params)
-        for _ in range(2):
+        online = {}
+        for flavour, use_lsd in (("lsd", True), ("edlines", False)):
+            det = cs.line_lbd_detect(context=ctx)
+            det.use_LSD = use_lsd            # object_slam sets true (main_obj.cpp:365); the class default is EDLines (line_lbd_allclass.cpp:121)
+            det.line_length_thres = 15
+            lp = det.params()
+            ctx.upload_online(wl["imgs"], wl["Ts"], wl["boxes"], lp, params)
+            for _ in range(2):
+                ctx.run()
+            st_on = ctx.stats()
+            o0, o1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            n_on = max(3, min(args.steps, 5))
+            torch.cuda.synchronize()
+            o0.record(stream)
+            for _ in range(n_on):
+                ctx.run_async()
+            o1.record(stream)
+            torch.cuda.synchronize()
+            on_ms = o0.elapsed_time(o1) / n_on
             ctx.run()
-        st_on = ctx.stats()
-        o0, o1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        n_on = max(3, min(args.steps, 5))
-        torch.cuda.synchronize()
-        o0.record(stream)
-        for _ in range(n_on):
-            ctx.run_async()
-        o1.record(stream)
-        torch.cuda.synchronize()
-        on_ms = o0.elapsed_time(o1) / n_on
-        ctx.run()
-        online = {"workload": "same frames, lines from cs_detect_lines (LSD, length > 15) on the device", "ms_per_step": on_ms,
-                  "frames_per_s": F / (on_ms * 1e-3), "value": st_on["n_valid"] / (on_ms * 1e-3), "unit": "proposals/s",
-                  "n_valid": st_on["n_valid"], "stage_ms": ctx.stage_ms(),
-                  "note": "the LSD seed loop is one warp per frame (order-dependent); at 256 frames it is latency-bound"}
+            online[flavour] = {"workload": "same frames, lines from cs_detect_lines (%s, length > 15) on the device" % flavour, "ms_per_step": on_ms,
+                               "frames_per_s": F / (on_ms * 1e-3), "value": st_on["n_valid"] / (on_ms * 1e-3), "unit": "proposals/s",
+                               "n_valid": st_on["n_valid"], "stage_ms": ctx.stage_ms()}
+        online["note"] = "the sequential half of either detector (LSD seed loop / EDLines routing + fitting) is one warp per frame; at 256 frames it is latency-bound"
         ctx.upload(wl["imgs"], wl["Ts"], wl["boxes"], wl["lines"], params)
 
     # ---- end to end through the host-buffer ABI call ("e2e")
@@ -375,6 +380,8 @@ def main():
     ap.add_argument("--workload", default="c3", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-online", action="store_true")
+    ap.add_argument("--no-prio", action="store_true", help="A/B: keep each batch's whole chain on one stream (no high-priority tail)")
+    ap.add_argument("--raster-dt", action="store_true", help="A/B: two-pass raster-scan distance transform kernel instead of the cone form")
     ap.add_argument("--inflight", type=int, default=3, help="batches in flight on one GPU (contexts driven round-robin)")
     args = ap.parse_args()
     if args.steps is None:

@@ -62,11 +62,19 @@ struct cs_ctx {
     int max_n_cand = 0;
     int use_cta_select = 0; /* debug: force the CTA-wide sweep / selection kernels */
     std::vector<int32_t> dt_ids, tile_job;
+    int dt_class_off[CS_DT_CLASSES + 1] = {0}, dt_class_plane_words[CS_DT_CLASSES] = {0};
     int64_t total_px = 0, total_cand = 0, total_bits = 0;
     int n_tiles = 0, max_plane_words = 0, max_dpitch = 0, max_roi_h = 0;
+    int use_raster_dt = 0; /* A/B: two-pass raster-scan distance transform instead of the cone form */
     int use_fused_dt = 0; /* experimental: fused hysteresis + wavefront DT kernel */
     cudaStream_t stream2 = nullptr; /* side stream: the line kernel runs beside the image chain */
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+    /* the skinny, latency-bound tail of the chain (distance transform -> sweep -> selection: a few warps per SM, long dependent chains) runs on
+     * a high-priority stream: with several batches in flight its blocks are dispatched ahead of another batch's machine-filling
+     * gray / Canny grids instead of queueing behind them */
+    cudaStream_t stream_hi = nullptr;
+    cudaEvent_t ev_mid = nullptr, ev_done = nullptr, ev_dt_fork = nullptr, ev_dt_join = nullptr;
+    int use_prio = 1;
 
     /* device buffers (grow only) */
     DevBuf d_img, d_gray, d_lines, d_frames, d_poses, d_yaws, d_jobs, d_objs, d_blocks, d_blocks4, d_dtids, d_tilejob;
@@ -318,10 +326,20 @@ int build_tables(cs_ctx *c)
         const int rows = (c->jobs[j].roi_h + 31) / 32; /* one NMS block per row of tiles: (job << 8) | tile_y */
         for (int ty = 0; ty < rows; ty++) c->tile_job.push_back((int32_t)((j << 8) | ty));
     }
+    /* distance transform work list: by width class, the tallest ROI of a class first (its dependency chain is the longest) */
     c->dt_ids.clear();
-    for (int cls = 0; cls < CS_DT_CLASSES; cls++)
+    for (int cls = 0; cls < CS_DT_CLASSES; cls++) {
+        c->dt_class_off[cls] = (int)c->dt_ids.size();
+        c->dt_class_plane_words[cls] = 0;
         for (size_t j = 0; j < c->jobs.size(); j++)
-            if (cs_dt_class_of(c->jobs[j].roi_w) == cls) c->dt_ids.push_back((int32_t)j);
+            if (cs_dt_class_of(c->jobs[j].roi_w) == cls) {
+                c->dt_ids.push_back((int32_t)j);
+                c->dt_class_plane_words[cls] = std::max(c->dt_class_plane_words[cls], (c->jobs[j].roi_h + 2) * (c->jobs[j].bw + 2));
+            }
+        std::stable_sort(c->dt_ids.begin() + c->dt_class_off[cls], c->dt_ids.end(),
+                         [&](int32_t a, int32_t b) { return c->jobs[a].roi_h > c->jobs[b].roi_h; });
+    }
+    c->dt_class_off[CS_DT_CLASSES] = (int)c->dt_ids.size();
     return CS_OK;
 }
 
@@ -421,9 +439,15 @@ int run_batch(cs_ctx *c, bool sync)
                                   c->max_roi_h, st, &c->launches);
     if (!fused) cs_launch_hyst((const CsJob *)c->d_jobs.p, n_jobs, (uint32_t *)c->d_bits.p, c->max_plane_words, st, &c->launches);
     mark(ST_DT);
+    const bool tail_hi = c->use_prio && !c->profiling;
+    if (tail_hi) { /* hand the rest of the chain to the high-priority stream */
+        cudaEventRecord(c->ev_mid, st);
+        st = c->stream_hi;
+        cudaStreamWaitEvent(st, c->ev_mid, 0);
+    }
     if (!fused)
-        cs_launch_dt((const CsJob *)c->d_jobs.p, (const int32_t *)c->d_dtids.p, n_jobs, c->max_dpitch, (const uint32_t *)c->d_bits.p, (float *)c->d_dist.p,
-                     st, &c->launches);
+        cs_launch_dt((const CsJob *)c->d_jobs.p, (const int32_t *)c->d_dtids.p, n_jobs, c->max_dpitch, c->dt_class_off, c->dt_class_plane_words, (const uint32_t *)c->d_bits.p,
+                     (float *)c->d_dist.p, c->use_raster_dt != 0, st, c->stream2, c->ev_dt_fork, c->ev_dt_join, &c->launches);
     mark(ST_LINES);
     cudaStreamWaitEvent(st, c->ev_join, 0); /* join */
     mark(ST_SWEEP);
@@ -449,6 +473,11 @@ int run_batch(cs_ctx *c, bool sync)
                        (double *)c->d_norm.p, (double *)c->d_score.p, (int32_t *)c->d_jcounts.p, (cs_cuboid_rec *)c->d_out.p, (int32_t *)c->d_outcnt.p,
                        c->topk, &c->prm, st, &c->launches);
     mark(ST_COUNT);
+    if (tail_hi) { /* everything queued on the context stream after this run is ordered behind the tail */
+        cudaEventRecord(c->ev_done, st);
+        st = c->stream;
+        cudaStreamWaitEvent(st, c->ev_done, 0);
+    }
     if (c->profiling) cudaEventRecord(c->ev_total[1], st);
     CS_CUDA(c, cudaGetLastError());
     c->stage_valid = false;
@@ -605,7 +634,14 @@ cs_ctx *cs_create(int device, int max_width, int max_height, int max_frames, int
         delete c;
         return nullptr;
     }
-    cudaStreamCreateWithFlags(&c->stream2, cudaStreamNonBlocking);
+    int prio_lo = 0, prio_hi = 0;
+    cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi); /* numerically lower = higher priority */
+    cudaStreamCreateWithPriority(&c->stream2, cudaStreamNonBlocking, prio_hi);
+    cudaStreamCreateWithPriority(&c->stream_hi, cudaStreamNonBlocking, prio_hi);
+    cudaEventCreateWithFlags(&c->ev_mid, cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&c->ev_dt_fork, cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&c->ev_dt_join, cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&c->ev_done, cudaEventDisableTiming);
     cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming);
     cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming);
     for (int s = 0; s <= ST_COUNT; s++) cudaEventCreate(&c->ev[s]);
@@ -636,6 +672,11 @@ void cs_destroy(cs_ctx *c)
     cudaEventDestroy(c->ev_fork);
     cudaEventDestroy(c->ev_join);
     cudaStreamDestroy(c->stream2);
+    cudaStreamDestroy(c->stream_hi);
+    cudaEventDestroy(c->ev_mid);
+    cudaEventDestroy(c->ev_dt_fork);
+    cudaEventDestroy(c->ev_dt_join);
+    cudaEventDestroy(c->ev_done);
     cudaStreamDestroy(c->stream);
     delete c;
 }
@@ -783,6 +824,8 @@ int cs_set_profiling(cs_ctx *c, int enable)
     if (!c) return CS_ERR_INVALID_ARG;
     c->profiling = (enable & 1) != 0;
     c->use_fused_dt = (enable & 4) != 0; /* bit 2: experimental fused hysteresis + wavefront-DT kernel */
+    c->use_raster_dt = (enable & 32) != 0; /* bit 5: two-pass raster-scan distance transform kernel */
+    c->use_prio = (enable & 16) == 0;      /* bit 4: keep the whole chain on one stream (no high-priority tail) */
     c->use_cta_select = (enable & 8) != 0; /* bit 3: CTA-wide sweep / selection kernels (the general path) instead of the warp ones */
     return CS_OK;
 }
@@ -801,6 +844,21 @@ int cs_stage_ms(cs_ctx *c, const char *stage, float *ms)
             return CS_OK;
         }
     return fail(c, CS_ERR_INVALID_ARG, "unknown stage %s", stage);
+}
+
+/* timeline of the last profiled run of `c`: milliseconds from the start of the last profiled run of `ref` to each stage mark of `c`
+ * (9 values: the 8 stage starts in kStageNames order and the end).  Both runs must have completed. */
+int cs_debug_stage_offsets(cs_ctx *c, cs_ctx *ref, float *offsets_ms)
+{
+    if (!c || !ref || !offsets_ms) return CS_ERR_INVALID_ARG;
+    if (!c->profiling || !ref->profiling) return fail(c, CS_ERR_NOT_PREPARED, "profiling must be enabled on both contexts");
+    cudaSetDevice(c->device);
+    for (int s = 0; s <= ST_COUNT; s++)
+        if (cudaEventElapsedTime(&offsets_ms[s], ref->ev_total[0], c->ev[s]) != cudaSuccess) {
+            cudaGetLastError();
+            return fail(c, CS_ERR_CUDA, "stage event %d not recorded or not complete", s);
+        }
+    return CS_OK;
 }
 
 int cs_debug_roi(cs_ctx *c, int job, int32_t roi_xywh[4], uint8_t *canny, float *dist, int cap_px, double *merged_lines, int cap_lines,

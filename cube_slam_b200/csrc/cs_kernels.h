@@ -7,8 +7,21 @@
 
 #include "cs_internal.h"
 
+/* One shared-memory carveout for every kernel of the chain: kernels of several batches share the SMs, and an SM only changes its
+ * L1 / shared split when it is idle.  -1 leaves the driver's per-kernel choice.  (CS_SMEM_CARVEOUT in the environment overrides.) */
+int cs_carveout_pref(void);
+#define CS_APPLY_CARVEOUT(kernel)                                                                            \
+    do {                                                                                                     \
+        static bool cv_done_ = false;                                                                        \
+        if (!cv_done_) {                                                                                     \
+            const int cv_ = cs_carveout_pref();                                                              \
+            if (cv_ >= 0) cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cv_); \
+            cv_done_ = true;                                                                                 \
+        }                                                                                                    \
+    } while (0)
+
 #define CS_DT_CLASSES 7
-extern const int cs_dt_class_ppl[CS_DT_CLASSES];
+extern const int cs_dt_class_width[CS_DT_CLASSES];
 int cs_dt_class_of(int roi_w);
 
 void cs_launch_gray(const uint8_t *d_img, uint8_t *d_gray, int n_frames, int w, int h, int stride, int channels, cudaStream_t st,
@@ -17,8 +30,9 @@ void cs_launch_canny(const uint8_t *d_gray, int img_w, int img_h, const CsJob *d
                      uint32_t *d_bits,
                      size_t bits_bytes, int low, int high, cudaStream_t st, int64_t *launches);
 void cs_launch_hyst(const CsJob *d_jobs, int n_jobs, uint32_t *d_bits, int max_plane_words, cudaStream_t st, int64_t *launches);
-void cs_launch_dt(const CsJob *d_jobs, const int32_t *d_ids, int n_jobs, int max_dpitch, const uint32_t *d_bits, float *d_dist,
-                  cudaStream_t st, int64_t *launches);
+void cs_launch_dt(const CsJob *d_jobs, const int32_t *d_ids, int n_jobs, int max_dpitch, const int *class_off, const int *class_plane_words,
+                  const uint32_t *d_bits, float *d_dist, bool raster, cudaStream_t st, cudaStream_t st_side, cudaEvent_t ev_fork, cudaEvent_t ev_join,
+                  int64_t *launches);
 bool cs_launch_hyst_dt(const CsJob *d_jobs, int n_jobs, uint32_t *d_bits, float *d_dist, int max_plane_words, int max_dpitch, int max_h,
                        cudaStream_t st, int64_t *launches);
 void cs_launch_roi_lines(const CsJob *d_jobs, int n_jobs, const CsFrame *d_frames, const double *d_lines, const float *d_lines_f32,

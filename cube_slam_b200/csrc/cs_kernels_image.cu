@@ -14,6 +14,7 @@
  * warp, hysteresis a word-parallel dilation in shared memory, and the distance transform's input 32x smaller.
  */
 #include <cuda_runtime.h>
+#include <stdlib.h>
 #include <stdint.h>
 
 #include "cs_internal.h"
@@ -490,6 +491,389 @@ __global__ void __launch_bounds__(32) k_chamfer_dt(const CsJob *__restrict__ job
 
 
 /* ------------------------------------------------------------------------------------------
+ * Distance transform, cone form (the default).  The two-pass 3x3 chamfer transform computes the exact path metric
+ *      D(p) = min over edge pixels q of  a * max(|dx|,|dy|) + (b - a) * min(|dx|,|dy|)           (a = DT_HV < b = DT_DG < 2a),
+ * so any evaluation order of that minimum gives the same integers.  Split the sources of p by octant pair:
+ *   - q in the closed VERTICAL cone (|dx| <= |dy|) is reached by |dx| diagonal and |dy| - |dx| vertical moves:
+ *        S(x,y) = min(edge ? 0 : inf, S(x,y-1) + a, S(x-1,y-1) + b, S(x+1,y-1) + b)      top-down sweep   (k_dt_down)
+ *        V(x,y) = min(S(x,y),         V(x,y+1) + a, V(x-1,y+1) + b, V(x+1,y+1) + b)      bottom-up sweep  (k_dt_up, warp 0)
+ *     neither recurrence has a dependency inside a row, so a row step is a handful of adds and mins per pixel;
+ *   - q in the HORIZONTAL cone (|dy| <= |dx|) is reached by |dy| diagonal moves to a pixel p' of p's own row -- for which q lies on the rim of
+ *     the vertical cone, so V(p') already holds that cost or less -- followed by horizontal moves:
+ *        D(x,y) = min over x' of V(x',y) + a * |x - x'|                                   two 1-D scans    (k_dt_up, warps 1..3)
+ *     rows are independent of each other: the scans are off the row-to-row dependency chain.
+ * Every term is the cost of a real path (>= D) and the best path of either kind is among them (<= D), hence D exactly; values the
+ * raster scan saturates at DIST_MAX (an edge-free ROI) come out >= DT_BIG and are written as DIST_MAX.  Columns between roi_w and the
+ * padded pitch are treated as non-edge pixels of a wider image: a shortest path between two pixels of the ROI never leaves their
+ * bounding box, so they change nothing inside the ROI.
+ * The raster-scan kernel above spends its time in a chain of 2H dependent row scans of one warp; here the chain is 2H cheap steps.
+ * Layout: a lane owns 4 consecutive columns of every 128-column chunk, so a row moves as one coalesced 16-byte access per lane and chunk.
+ * ------------------------------------------------------------------------------------------ */
+#define DT_PFC 8  /* rows of edge bits kept in flight by the down sweep when the plane does not fit in shared memory */
+#define DT_PFS 16 /* rows of S kept in flight by the up sweep */
+#define DT_VR 6   /* rows of V between the sweep warp and the scan warps of k_dt_up (a multiple of the 3 scan warps) */
+
+/* named barriers: the documented producer / consumer pairing of bar.arrive with bar.sync (no polling).  Slot s of the V ring uses barrier
+ * 1 + s for "row ready" and 1 + DT_VR + s for "slot free"; every barrier has at most one arrival outstanding. */
+__device__ __forceinline__ void dt_bar_sync(int id) { asm volatile("bar.sync %0, 64;" ::"r"(id) : "memory"); }
+__device__ __forceinline__ void dt_bar_arrive(int id) { asm volatile("bar.arrive %0, 64;" ::"r"(id) : "memory"); }
+
+/* left / right neighbours of a lane's 4-column group in chunk c: the lane beside it, or the rim lane of the next chunk */
+template <int NCH>
+__device__ __forceinline__ void dt_rim(const int (&v)[NCH][4], int c, int lane, int &L, int &R)
+{
+    const unsigned FULL = 0xffffffffu;
+    const int sendL = (c > 0 && lane == 31) ? v[c > 0 ? c - 1 : 0][3] : v[c][3];
+    const int sendR = (c < NCH - 1 && lane == 0) ? v[c < NCH - 1 ? c + 1 : c][0] : v[c][0];
+    L = __shfl_sync(FULL, sendL, (lane + 31) & 31);
+    R = __shfl_sync(FULL, sendR, (lane + 1) & 31);
+    if (c == 0 && lane == 0) L = DT_BIG;
+    if (c == NCH - 1 && lane == 31) R = DT_BIG;
+}
+
+template <int NCH, int PF>
+__device__ __forceinline__ void dt_down_warp(const uint32_t *__restrict__ planeS, int bwp, uint32_t *__restrict__ tmp, int h, int dpitch)
+{
+    const int lane = threadIdx.x & 31;
+    const int bw = bwp - 2;
+    const int sh = (lane & 7) * 4;
+    int up[NCH][4];
+#pragma unroll
+    for (int c = 0; c < NCH; c++)
+#pragma unroll
+        for (int j = 0; j < 4; j++) up[c][j] = DT_BIG;
+    uint32_t pf[PF][NCH];
+    auto fetch = [&](int d, int row) { /* planeS: the bordered plane in global memory, or its copy in shared memory */
+        const uint32_t *rw = planeS + (size_t)(row + 1) * bwp + 1;
+#pragma unroll
+        for (int c = 0; c < NCH; c++) {
+            const int wi = 4 * c + (lane >> 3);
+            pf[d][c] = (wi < bw) ? rw[wi] : 0u; /* bits beyond roi_w are zero (NMS writes none) */
+        }
+    };
+#pragma unroll
+    for (int d = 0; d < PF; d++) fetch(d, min(d, h - 1));
+    for (int i0 = 0; i0 < h; i0 += PF) {
+#pragma unroll
+        for (int d = 0; d < PF; d++) {
+            const int i = i0 + d;
+            if (i < h) {
+                uint32_t nib[NCH];
+#pragma unroll
+                for (int c = 0; c < NCH; c++) nib[c] = pf[d][c] >> sh;
+                fetch(d, min(i + PF, h - 1));
+                int nv[NCH][4], Lr[NCH], Rr[NCH];
+#pragma unroll
+                for (int c = 0; c < NCH; c++) dt_rim<NCH>(up, c, lane, Lr[c], Rr[c]); /* all shuffles of the row in flight together */
+#pragma unroll
+                for (int c = 0; c < NCH; c++) {
+                    const int L = Lr[c], R = Rr[c];
+#pragma unroll
+                    for (int j = 0; j < 4; j++) {
+                        const int l = (j == 0) ? L : up[c][j - 1];
+                        const int r = (j == 3) ? R : up[c][j + 1];
+                        int u = min(min(min(l, r) + DT_DG, up[c][j] + DT_HV), DT_BIG);
+                        if ((nib[c] >> j) & 1u) u = 0;
+                        nv[c][j] = u;
+                    }
+                }
+                uint32_t *trow = tmp + (size_t)i * dpitch;
+#pragma unroll
+                for (int c = 0; c < NCH; c++) {
+#pragma unroll
+                    for (int j = 0; j < 4; j++) up[c][j] = nv[c][j];
+                    const int col0 = c * 128 + lane * 4;
+                    if (col0 < dpitch) *reinterpret_cast<uint4 *>(trow + col0) = make_uint4(up[c][0], up[c][1], up[c][2], up[c][3]);
+                }
+            }
+        }
+    }
+}
+
+template <int NCH>
+__global__ void __launch_bounds__(32) k_dt_down(const CsJob *__restrict__ jobs, const int32_t *__restrict__ job_ids,
+                                                const uint32_t *__restrict__ bits_arena, float *__restrict__ dist_arena, int smem_words)
+{
+    const CsJob &jb = jobs[job_ids[blockIdx.x]];
+    const uint32_t *planeS = bits_arena + jb.bit_off;
+    uint32_t *tmp = reinterpret_cast<uint32_t *>(dist_arena + jb.px_off);
+    const int w = jb.roi_w, h = jb.roi_h, bwp = jb.bw + 2, dp = jb.dpitch;
+    if (w <= 0 || h <= 0) return;
+    /* the whole strong plane (1 bit per pixel) comes in with one burst of asynchronous copies; the sweep then never waits on memory */
+    const int n_words = (h + 2) * bwp;
+    if (n_words <= smem_words) {
+        const int lane = threadIdx.x;
+        for (int q = lane; q < n_words; q += 32) {
+            const unsigned sa = (unsigned)__cvta_generic_to_shared(dt_smem + q);
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" ::"r"(sa), "l"(planeS + q));
+        }
+        cp_async_commit();
+        cp_async_wait<0>();
+        __syncwarp();
+        planeS = dt_smem;
+    }
+    dt_down_warp<NCH, (NCH <= 5 ? DT_PFC : 2)>(planeS, bwp, tmp, h, dp);
+}
+
+/* bottom-up sweep of warp 0: S rows arrive through a cp.async ring, V rows leave through the ring `vring` the scan warps read */
+template <int NCH>
+__device__ __forceinline__ void dt_up_sweep(const uint32_t *__restrict__ tmp, int h, int dpitch, uint32_t *sring, uint32_t *vring)
+{
+    const int lane = threadIdx.x & 31;
+    int dn[NCH][4];
+#pragma unroll
+    for (int c = 0; c < NCH; c++)
+#pragma unroll
+        for (int j = 0; j < 4; j++) dn[c][j] = DT_BIG;
+    const int chunks = dpitch >> 2; /* 16-byte pieces per row */
+#pragma unroll
+    for (int d = 0; d < DT_PFS; d++) {
+        const int i = h - 1 - d;
+        if (i >= 0)
+            for (int q = lane; q < chunks; q += 32) cp_async16(sring + (size_t)d * dpitch + q * 4, tmp + (size_t)i * dpitch + q * 4);
+        cp_async_commit();
+    }
+    int slot = 0, vslot = 0;
+    for (int t = 0; t < h; t++) {
+        const int i = h - 1 - t;
+        cp_async_wait<DT_PFS - 1>();
+        __syncwarp();
+        const uint32_t *srow = sring + (size_t)slot * dpitch;
+        int cur[NCH][4];
+#pragma unroll
+        for (int c = 0; c < NCH; c++) {
+            const int col0 = c * 128 + lane * 4;
+            uint4 q = make_uint4(DT_BIG, DT_BIG, DT_BIG, DT_BIG);
+            if (col0 < dpitch) q = *reinterpret_cast<const uint4 *>(srow + col0);
+            cur[c][0] = (int)q.x;
+            cur[c][1] = (int)q.y;
+            cur[c][2] = (int)q.z;
+            cur[c][3] = (int)q.w;
+        }
+        __syncwarp();
+        {
+            const int nxt = i - DT_PFS;
+            if (nxt >= 0)
+                for (int q = lane; q < chunks; q += 32) cp_async16(sring + (size_t)slot * dpitch + q * 4, tmp + (size_t)nxt * dpitch + q * 4);
+            cp_async_commit();
+        }
+        slot = (slot + 1 == DT_PFS) ? 0 : slot + 1;
+        int nv[NCH][4], Lr[NCH], Rr[NCH];
+#pragma unroll
+        for (int c = 0; c < NCH; c++) dt_rim<NCH>(dn, c, lane, Lr[c], Rr[c]);
+#pragma unroll
+        for (int c = 0; c < NCH; c++) {
+            const int L = Lr[c], R = Rr[c];
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                const int l = (j == 0) ? L : dn[c][j - 1];
+                const int r = (j == 3) ? R : dn[c][j + 1];
+                nv[c][j] = min(cur[c][j], min(min(l, r) + DT_DG, dn[c][j] + DT_HV)); /* cur <= DT_BIG */
+            }
+        }
+        /* the slot is free once the scan warp that had row t - DT_VR is done with it */
+        if (t >= DT_VR) dt_bar_sync(1 + DT_VR + vslot);
+        uint32_t *vrow = vring + (size_t)vslot * dpitch;
+#pragma unroll
+        for (int c = 0; c < NCH; c++) {
+#pragma unroll
+            for (int j = 0; j < 4; j++) dn[c][j] = nv[c][j];
+            const int col0 = c * 128 + lane * 4;
+            if (col0 < dpitch) *reinterpret_cast<uint4 *>(vrow + col0) = make_uint4(dn[c][0], dn[c][1], dn[c][2], dn[c][3]);
+        }
+        dt_bar_arrive(1 + vslot);
+        vslot = (vslot + 1 == DT_VR) ? 0 : vslot + 1;
+    }
+    cp_async_wait<0>();
+}
+
+/* the two 1-D min-plus scans (slope a) of one row of V (shared memory) into the float row of the map.  A lane owns 4 consecutive columns of
+ * each 128-column chunk; the warp scans of all chunks advance together, stage by stage, so their shuffles overlap (a warp issues in order:
+ * chunk after chunk would serialise 5 x 5 dependent shuffles) */
+template <int NCH>
+__device__ __forceinline__ void dt_row_scan(const uint32_t *vrow, float *__restrict__ drow, int dpitch, int lane)
+{
+    const unsigned FULL = 0xffffffffu;
+    const float scale = 1.f / 65536.f;
+    const float dist_max = (float)(0xffffffffu - (uint32_t)DT_DG) * scale;
+    int t[NCH][4], incl[NCH], excl[NCH];
+    /* ---- forward: F(x) = min over x' <= x of V(x') + a (x - x') ---- */
+#pragma unroll
+    for (int c = 0; c < NCH; c++) {
+        const int col0 = c * 128 + lane * 4;
+        uint4 q = make_uint4(DT_BIG, DT_BIG, DT_BIG, DT_BIG);
+        if (col0 < dpitch) q = *reinterpret_cast<const uint4 *>(vrow + col0);
+        t[c][0] = (int)q.x - DT_HV * col0;
+        t[c][1] = min((int)q.y - DT_HV * (col0 + 1), t[c][0]);
+        t[c][2] = min((int)q.z - DT_HV * (col0 + 2), t[c][1]);
+        t[c][3] = min((int)q.w - DT_HV * (col0 + 3), t[c][2]);
+        incl[c] = t[c][3];
+    }
+#pragma unroll
+    for (int dd = 1; dd < 32; dd <<= 1) {
+        int o[NCH];
+#pragma unroll
+        for (int c = 0; c < NCH; c++) o[c] = __shfl_up_sync(FULL, incl[c], dd);
+        if (lane >= dd) {
+#pragma unroll
+            for (int c = 0; c < NCH; c++) incl[c] = min(incl[c], o[c]);
+        }
+    }
+#pragma unroll
+    for (int c = 0; c < NCH; c++) excl[c] = __shfl_up_sync(FULL, incl[c], 1);
+    {
+        int tot[NCH];
+#pragma unroll
+        for (int c = 0; c < NCH; c++) tot[c] = __shfl_sync(FULL, incl[c], 31);
+        int carry = INT_MAX;
+#pragma unroll
+        for (int c = 0; c < NCH; c++) {
+            if (lane == 0) excl[c] = INT_MAX;
+            excl[c] = min(excl[c], carry);
+            carry = min(carry, tot[c]);
+        }
+    }
+    /* forward result, already shifted for the backward scan: F + a col = min(t, excl) + 2 a col; then the in-lane suffix minima */
+#pragma unroll
+    for (int c = 0; c < NCH; c++) {
+        const int col0 = c * 128 + lane * 4;
+        t[c][3] = min(t[c][3], excl[c]) + 2 * DT_HV * (col0 + 3);
+        t[c][2] = min(min(t[c][2], excl[c]) + 2 * DT_HV * (col0 + 2), t[c][3]);
+        t[c][1] = min(min(t[c][1], excl[c]) + 2 * DT_HV * (col0 + 1), t[c][2]);
+        t[c][0] = min(min(t[c][0], excl[c]) + 2 * DT_HV * col0, t[c][1]);
+        incl[c] = t[c][0];
+    }
+    /* ---- backward: D(x) = min over x' >= x of F(x') + a (x' - x) ---- */
+#pragma unroll
+    for (int dd = 1; dd < 32; dd <<= 1) {
+        int o[NCH];
+#pragma unroll
+        for (int c = 0; c < NCH; c++) o[c] = __shfl_down_sync(FULL, incl[c], dd);
+        if (lane + dd < 32) {
+#pragma unroll
+            for (int c = 0; c < NCH; c++) incl[c] = min(incl[c], o[c]);
+        }
+    }
+#pragma unroll
+    for (int c = 0; c < NCH; c++) excl[c] = __shfl_down_sync(FULL, incl[c], 1);
+    {
+        int tot[NCH];
+#pragma unroll
+        for (int c = 0; c < NCH; c++) tot[c] = __shfl_sync(FULL, incl[c], 0);
+        int carry = INT_MAX;
+#pragma unroll
+        for (int c = NCH - 1; c >= 0; c--) {
+            if (lane == 31) excl[c] = INT_MAX;
+            excl[c] = min(excl[c], carry);
+            carry = min(carry, tot[c]);
+        }
+    }
+#pragma unroll
+    for (int c = 0; c < NCH; c++) {
+        const int col0 = c * 128 + lane * 4;
+        float o4[4];
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            const int r = min(t[c][k], excl[c]) - DT_HV * (col0 + k);
+            o4[k] = (r >= DT_BIG) ? dist_max : (float)(uint32_t)r * scale;
+        }
+        if (col0 < dpitch) *reinterpret_cast<float4 *>(drow + col0) = make_float4(o4[0], o4[1], o4[2], o4[3]);
+    }
+}
+
+/* rows wider than 640 px: same scans, the forward result parked in the shared row instead of registers */
+__device__ __noinline__ void dt_row_scan_wide(uint32_t *vrow, float *__restrict__ drow, int dpitch, int lane, int nch)
+{
+    const unsigned FULL = 0xffffffffu;
+    const float scale = 1.f / 65536.f;
+    const float dist_max = (float)(0xffffffffu - (uint32_t)DT_DG) * scale;
+    int carry = INT_MAX;
+    for (int c = 0; c < nch; c++) {
+        const int col0 = c * 128 + lane * 4;
+        uint4 q = make_uint4(DT_BIG, DT_BIG, DT_BIG, DT_BIG);
+        if (col0 < dpitch) q = *reinterpret_cast<const uint4 *>(vrow + col0);
+        int t[4] = {(int)q.x, (int)q.y, (int)q.z, (int)q.w};
+#pragma unroll
+        for (int k = 0; k < 4; k++) t[k] -= DT_HV * (col0 + k);
+        t[1] = min(t[1], t[0]);
+        t[2] = min(t[2], t[1]);
+        t[3] = min(t[3], t[2]);
+        int incl = t[3];
+#pragma unroll
+        for (int dd = 1; dd < 32; dd <<= 1) {
+            const int o = __shfl_up_sync(FULL, incl, dd);
+            if (lane >= dd) incl = min(incl, o);
+        }
+        int excl = __shfl_up_sync(FULL, incl, 1);
+        if (lane == 0) excl = INT_MAX;
+        excl = min(excl, carry);
+        carry = min(carry, __shfl_sync(FULL, incl, 31));
+        if (col0 < dpitch)
+            *reinterpret_cast<uint4 *>(vrow + col0) =
+                make_uint4(min(t[0], excl) + 2 * DT_HV * col0, min(t[1], excl) + 2 * DT_HV * (col0 + 1), min(t[2], excl) + 2 * DT_HV * (col0 + 2),
+                           min(t[3], excl) + 2 * DT_HV * (col0 + 3));
+    }
+    __syncwarp();
+    carry = INT_MAX;
+    for (int c = nch - 1; c >= 0; c--) {
+        const int col0 = c * 128 + lane * 4;
+        uint4 q = make_uint4(INT_MAX, INT_MAX, INT_MAX, INT_MAX);
+        if (col0 < dpitch) q = *reinterpret_cast<const uint4 *>(vrow + col0);
+        int t[4] = {(int)q.x, (int)q.y, (int)q.z, (int)q.w};
+        t[2] = min(t[2], t[3]);
+        t[1] = min(t[1], t[2]);
+        t[0] = min(t[0], t[1]);
+        int incl = t[0];
+#pragma unroll
+        for (int dd = 1; dd < 32; dd <<= 1) {
+            const int o = __shfl_down_sync(FULL, incl, dd);
+            if (lane + dd < 32) incl = min(incl, o);
+        }
+        int excl = __shfl_down_sync(FULL, incl, 1);
+        if (lane == 31) excl = INT_MAX;
+        excl = min(excl, carry);
+        carry = min(carry, __shfl_sync(FULL, incl, 0));
+        float o4[4];
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            const int r = min(t[k], excl) - DT_HV * (col0 + k);
+            o4[k] = (r >= DT_BIG) ? dist_max : (float)(uint32_t)r * scale;
+        }
+        if (col0 < dpitch) *reinterpret_cast<float4 *>(drow + col0) = make_float4(o4[0], o4[1], o4[2], o4[3]);
+    }
+}
+
+/* one CTA of 4 warps per ROI: warp 0 sweeps bottom-up and hands each row of V to one of the three scan warps through shared memory */
+template <int NCH>
+__global__ void __launch_bounds__(128, (NCH <= 3 ? 5 : (NCH <= 5 ? 4 : 1))) k_dt_up(const CsJob *__restrict__ jobs, const int32_t *__restrict__ job_ids, float *__restrict__ dist_arena,
+                                               int ring_pitch)
+{
+    const CsJob &jb = jobs[job_ids[blockIdx.x]];
+    uint32_t *tmp = reinterpret_cast<uint32_t *>(dist_arena + jb.px_off);
+    const int w = jb.roi_w, h = jb.roi_h, dp = jb.dpitch;
+    if (w <= 0 || h <= 0) return;
+    uint32_t *sring = dt_smem;                               /* DT_PFS rows of S */
+    uint32_t *vring = dt_smem + (size_t)DT_PFS * ring_pitch;  /* DT_VR rows of V */
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    if (wid == 0) {
+        dt_up_sweep<NCH>(tmp, h, dp, sring, vring);
+    } else {
+        const int k = wid - 1;
+        for (int t = k; t < h; t += 3) {
+            const int vslot = t % DT_VR;
+            dt_bar_sync(1 + vslot);
+            uint32_t *vrow = vring + (size_t)vslot * dp;
+            float *drow = reinterpret_cast<float *>(tmp + (size_t)(h - 1 - t) * dp);
+            if (NCH <= 5)
+                dt_row_scan<(NCH <= 5 ? NCH : 1)>(vrow, drow, dp, lane);
+            else
+                dt_row_scan_wide(vrow, drow, dp, lane, (w + 127) >> 7);
+            if (t + DT_VR < h) dt_bar_arrive(1 + DT_VR + vslot);
+        }
+    }
+}
+
+/* ------------------------------------------------------------------------------------------
  * Fused hysteresis + chamfer distance transform, one CTA per ROI (the default path).
  *
  * Hysteresis as in k_canny_hyst, with both bit planes in shared memory.  The distance transform then
@@ -661,13 +1045,24 @@ __global__ void __launch_bounds__(32 * WF_MAX_WARPS) k_hyst_dt(const CsJob *__re
 }
 
 /* ------------------------------------------------------------------------------------------ launchers */
-const int cs_dt_class_ppl[CS_DT_CLASSES] = {4, 8, 12, 16, 24, 40, 64};
+/* ROI width classes of the distance transform: 1..5, 8 or 16 chunks of 128 columns (one kernel instantiation and one launch per class) */
+const int cs_dt_class_width[CS_DT_CLASSES] = {128, 256, 384, 512, 640, 1024, 2048};
 
 int cs_dt_class_of(int roi_w)
 {
     for (int c = 0; c < CS_DT_CLASSES; c++)
-        if (roi_w <= 32 * cs_dt_class_ppl[c]) return c;
+        if (roi_w <= cs_dt_class_width[c]) return c;
     return -1;
+}
+
+int cs_carveout_pref(void)
+{
+    static int v = -2;
+    if (v == -2) {
+        const char *e = getenv("CS_SMEM_CARVEOUT");
+        v = e ? atoi(e) : -1;
+    }
+    return v;
 }
 
 void cs_launch_gray(const uint8_t *d_img, uint8_t *d_gray, int n_frames, int w, int h, int stride, int channels, cudaStream_t st,
@@ -679,6 +1074,7 @@ void cs_launch_gray(const uint8_t *d_img, uint8_t *d_gray, int n_frames, int w, 
         const int64_t groups = total / 16;
         if (groups > 0) {
             const int blocks = (int)((groups + 255) / 256 < 148 * 16 ? (groups + 255) / 256 : 148 * 16);
+            CS_APPLY_CARVEOUT(k_bgr2gray_flat);
             k_bgr2gray_flat<<<blocks, 256, 0, st>>>((const uint4 *)d_img, (uint4 *)d_gray, groups);
             (*launches)++;
         }
@@ -698,6 +1094,7 @@ void cs_launch_canny(const uint8_t *d_gray, int img_w, int img_h, const CsJob *d
     if (n_jobs <= 0) return;
     cudaMemsetAsync(d_bits, 0, bits_bytes, st); /* zero borders (and stale bits) of every plane */
     if (n_tiles > 0) {
+        CS_APPLY_CARVEOUT(k_canny_nms);
         k_canny_nms<<<n_tiles, dim3(32, 8), 0, st>>>(d_gray, img_w, img_h, d_jobs, d_tile_job, d_bits, low, high);
         (*launches)++;
     }
@@ -715,23 +1112,90 @@ void cs_launch_hyst(const CsJob *d_jobs, int n_jobs, uint32_t *d_bits, int max_p
         cudaFuncSetAttribute(k_canny_hyst, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
         cur_attr = bytes;
     }
+    CS_APPLY_CARVEOUT(k_canny_hyst);
     k_canny_hyst<<<n_jobs, HY_THREADS, bytes, st>>>(d_jobs, d_bits, smem_words);
     (*launches)++;
 }
 
-/* d_ids: all job ids ordered by width class; max_dpitch = widest padded row of the batch */
-void cs_launch_dt(const CsJob *d_jobs, const int32_t *d_ids, int n_jobs, int max_dpitch, const uint32_t *d_bits, float *d_dist,
-                  cudaStream_t st, int64_t *launches)
+/* d_ids: job ids grouped by width class, tallest ROI first inside a class; class_off[c] .. class_off[c + 1] is the slice of class c;
+ * class_plane_words[c]: words of the largest bordered bit plane of the class.
+ * raster = the two-pass raster-scan kernel (A/B switch); default is the cone form: down sweep, then up sweep + row scans */
+template <int NCH>
+static void dt_launch_class(const CsJob *d_jobs, const int32_t *d_ids, int count, int width, int plane_words, const uint32_t *d_bits, float *d_dist,
+                            cudaStream_t st, int64_t *launches)
+{
+    static int attr_down = 0, attr_up = 0;
+    int down_words = plane_words;
+    if (down_words > (96 * 1024) / 4) down_words = 0; /* huge ROIs: stream the bits from global memory */
+    if (down_words * 4 > attr_down && down_words * 4 > 48 * 1024) {
+        cudaFuncSetAttribute(k_dt_down<NCH>, cudaFuncAttributeMaxDynamicSharedMemorySize, down_words * 4);
+        attr_down = down_words * 4;
+    }
+    const int bytes_up = (DT_PFS + DT_VR) * width * 4;
+    if (bytes_up > attr_up && bytes_up > 48 * 1024) {
+        cudaFuncSetAttribute(k_dt_up<NCH>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes_up);
+        attr_up = bytes_up;
+    }
+    CS_APPLY_CARVEOUT(k_dt_down<NCH>);
+    CS_APPLY_CARVEOUT(k_dt_up<NCH>);
+    k_dt_down<NCH><<<count, 32, down_words * 4, st>>>(d_jobs, d_ids, d_bits, d_dist, down_words);
+    k_dt_up<NCH><<<count, 128, bytes_up, st>>>(d_jobs, d_ids, d_dist, width);
+    (*launches) += 2;
+}
+
+void cs_launch_dt(const CsJob *d_jobs, const int32_t *d_ids, int n_jobs, int max_dpitch, const int *class_off, const int *class_plane_words,
+                  const uint32_t *d_bits, float *d_dist, bool raster, cudaStream_t st, cudaStream_t st_side, cudaEvent_t ev_fork, cudaEvent_t ev_join,
+                  int64_t *launches)
 {
     if (n_jobs <= 0) return;
-    static int cur_attr = 0;
-    const int bytes = DT_PF * max_dpitch * 4;
-    if (bytes > cur_attr && bytes > 48 * 1024) {
-        cudaFuncSetAttribute(k_chamfer_dt, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
-        cur_attr = bytes;
+    if (raster) {
+        static int cur_attr = 0;
+        const int bytes = DT_PF * max_dpitch * 4;
+        if (bytes > cur_attr && bytes > 48 * 1024) {
+            cudaFuncSetAttribute(k_chamfer_dt, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+            cur_attr = bytes;
+        }
+        CS_APPLY_CARVEOUT(k_chamfer_dt);
+        k_chamfer_dt<<<n_jobs, 32, bytes, st>>>(d_jobs, d_ids, d_bits, d_dist);
+        (*launches)++;
+        return;
     }
-    k_chamfer_dt<<<n_jobs, 32, bytes, st>>>(d_jobs, d_ids, d_bits, d_dist);
-    (*launches)++;
+    /* the width classes are independent: the class with most work stays on `st`, the others run beside it on `st_side` */
+    int main_cls = -1, n_cls = 0;
+    int64_t best = -1;
+    for (int c = 0; c < CS_DT_CLASSES; c++) {
+        const int64_t work = (int64_t)(class_off[c + 1] - class_off[c]) * cs_dt_class_width[c];
+        if (work > 0) n_cls++;
+        if (work > best) {
+            best = work;
+            main_cls = c;
+        }
+    }
+    const bool side = st_side != nullptr && n_cls > 1;
+    if (side) {
+        cudaEventRecord(ev_fork, st);
+        cudaStreamWaitEvent(st_side, ev_fork, 0);
+    }
+    for (int c = CS_DT_CLASSES - 1; c >= 0; c--) {
+        const int count = class_off[c + 1] - class_off[c];
+        if (count <= 0) continue;
+        const int32_t *ids = d_ids + class_off[c];
+        const int width = cs_dt_class_width[c], pw = class_plane_words[c];
+        cudaStream_t s = (side && c != main_cls) ? st_side : st;
+        switch (c) {
+        case 0: dt_launch_class<1>(d_jobs, ids, count, width, pw, d_bits, d_dist, s, launches); break;
+        case 1: dt_launch_class<2>(d_jobs, ids, count, width, pw, d_bits, d_dist, s, launches); break;
+        case 2: dt_launch_class<3>(d_jobs, ids, count, width, pw, d_bits, d_dist, s, launches); break;
+        case 3: dt_launch_class<4>(d_jobs, ids, count, width, pw, d_bits, d_dist, s, launches); break;
+        case 4: dt_launch_class<5>(d_jobs, ids, count, width, pw, d_bits, d_dist, s, launches); break;
+        case 5: dt_launch_class<8>(d_jobs, ids, count, width, pw, d_bits, d_dist, s, launches); break;
+        default: dt_launch_class<16>(d_jobs, ids, count, width, pw, d_bits, d_dist, s, launches); break;
+        }
+    }
+    if (side) {
+        cudaEventRecord(ev_join, st_side);
+        cudaStreamWaitEvent(st, ev_join, 0);
+    }
 }
 
 /* fused hysteresis + wavefront DT; returns false if the batch's largest ROI does not fit shared memory

@@ -1092,6 +1092,7 @@ void cs_launch_sweep_warp(const CsJob *d_jobs, const CsFrame *d_frames, const Cs
                           double *c_dist, double *c_angle, double *c_skew, const cs_cuboid_params *prm, cudaStream_t st, int64_t *launches)
 {
     if (n_blocks <= 0) return;
+    CS_APPLY_CARVEOUT(k_sweep_warp);
     k_sweep_warp<<<n_blocks, 32 * SWW_WARPS, 0, st>>>(d_jobs, d_frames, d_poses, d_yaw, d_blocks, d_mlines, d_line_counts, d_dist, c_valid, c_dist,
                                                       c_angle, c_skew, *prm);
     (*launches)++;
@@ -1112,6 +1113,7 @@ void cs_launch_fuse_warp(const CsObj *d_objs, int n_objs, const CsJob *d_jobs, c
         cudaFuncSetAttribute(k_fuse_warp, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         attr_set = true;
     }
+    CS_APPLY_CARVEOUT(k_fuse_warp);
     k_fuse_warp<<<(n_objs + FW_WARPS - 1) / FW_WARPS, 32 * FW_WARPS, smem, st>>>(d_objs, n_objs, d_jobs, d_frames, d_poses, d_yaw, c_valid, c_dist,
                                                                                  c_angle, c_skew, w_vlist, w_keep, w_norm, w_score, job_counts, d_out,
                                                                                  d_out_counts, topk, *prm);

@@ -169,8 +169,14 @@ int cs_batch_device_records(cs_ctx *ctx, void **dev_ptr, size_t *n_bytes);
 void *cs_stream(cs_ctx *ctx);
 /* milliseconds spent in the named stage of the last cs_batch_run ("lsd","gray","canny","hyst","dt","lines","sweep","fuse","total") */
 int cs_stage_ms(cs_ctx *ctx, const char *stage, float *ms);
-/* enable per-stage CUDA-event timing (adds event records only) */
+/* bit 0: per-stage CUDA-event timing (adds event records only; the chain then stays on one stream).  Debug / A-B switches:
+ * bit 2 fused hysteresis + wavefront distance transform, bit 3 CTA-wide sweep / selection kernels, bit 4 no high-priority
+ * stream for the distance transform -> sweep -> selection tail, bit 5 raster-scan distance transform (one kernel) instead of the cone form */
 int cs_set_profiling(cs_ctx *ctx, int enable);
+
+/* debug: when several contexts run concurrently with profiling on, the offsets (ms) of the 8 stage starts and the end of ctx's last run
+ * from the start of ref's last run -- a timeline of how the batches in flight overlap (tools/timeline.py) */
+int cs_debug_stage_offsets(cs_ctx *ctx, cs_ctx *ref, float offsets_ms[9]);
 
 /* debug/inspection: copy intermediate per-ROI results of the last run back to the host.
  * job = ROI job index (object-major, height-sample-minor). Any pointer may be NULL. */

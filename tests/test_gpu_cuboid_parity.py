@@ -78,11 +78,11 @@ def test_fixture_a_modes(cs, oracle, fixture_a, mode):
     ctx.close()
 
 
-@pytest.mark.parametrize("split_kernels", [0, 4])
+@pytest.mark.parametrize("split_kernels", [0, 4, 32])
 def test_fixture_a_stages(cs, oracle, fixture_a, split_kernels):
     """Stage by stage: gray/Canny/DT bit-exact, merged lines bit-exact, valid set + per-proposal errors.
-    split_kernels=4 selects the experimental fused hysteresis + wavefront-DT kernel instead of the default
-    separate hysteresis kernel + row-scan DT."""
+    Default: hysteresis kernel + cone-form distance transform (two sweeps + row scans).  4 selects the experimental fused
+    hysteresis + wavefront-DT kernel, 32 the two-pass raster-scan distance transform kernel."""
     fa = fixture_a
     ctx = cs.Context(0, 1280, 960, 1, 8, 4096)
     ctx.L.cs_set_profiling(ctx.h, split_kernels)
@@ -114,6 +114,8 @@ def test_synthetic_batch_matches_oracle(cs, oracle, seed, w, h, kind, nb):
         ctx.L.cs_set_profiling(ctx.h, 4)  # one case through the fused wavefront kernel
     if seed == 11:
         ctx.L.cs_set_profiling(ctx.h, 8)  # one case through the CTA-wide sweep / selection kernels
+    if seed == 13:
+        ctx.L.cs_set_profiling(ctx.h, 32)  # one case through the raster-scan distance transform kernel
     p = cs.default_params(max_cuboid_num=3)
     out, counts = ctx.detect_batch_host(imgs, Ts, boxes, lines, p)
     st = ctx.stats()
@@ -164,6 +166,36 @@ def test_dense_sweep_and_sampling(cs, oracle):
                         assert int(out[o, k]["proposal_index"]) == int(ref["cuboids"][b][k]["proposal_index"])
                         assert abs(out[o, k]["normalized_error"] - ref["cuboids"][b][k]["normalized_error"]) < 1e-9
                 o += 1
+    ctx.close()
+
+
+@pytest.mark.parametrize("flags", [0, 32])
+def test_distance_transform_wide_sparse_and_empty_rois(cs, oracle, flags):
+    """ROIs wider than 640 px (the row scans park their forward result in the row), an ROI with a single edge pixel
+    (most pixels have no source in their vertical cone) and an edge-free ROI (DIST_MAX everywhere)."""
+    rng = np.random.RandomState(3)
+    K = np.array([[800.0, 0, 800], [0, 800, 250], [0, 0, 1]])
+    T = np.eye(4)
+    T[:3, :3] = np.array([[1.0, 0, 0], [0, 0, 1], [0, -1, 0]])
+    T[2, 3] = 1.4
+    H, W = 500, 1600
+    textured = np.kron(rng.randint(0, 255, (25, 80)).astype(np.uint8), np.ones((20, 20), np.uint8))
+    flat = np.full((H, W), 120, np.uint8)
+    dot = flat.copy()
+    dot[240:243, 1370:1373] = 255          # a tiny blob: a handful of edge pixels far from most of the ROI
+    ctx = cs.Context(0, W, H, 1, 8, 4096)
+    ctx.L.cs_set_profiling(ctx.h, flags)
+    for img, box in ((textured, [40, 30, 1500, 420, 0.9]), (dot, [30, 20, 1520, 450, 0.9]), (flat, [100, 60, 700, 300, 0.9])):
+        img3 = np.ascontiguousarray(np.stack([img] * 3, -1))
+        boxes = np.array([box], float)
+        lines = np.array([[100.0, 100, 400, 110], [500, 300, 900, 310]])
+        _run_frame(cs, ctx, img3, K, T, boxes, lines)
+        tr = oracle.detect_cuboid(img3, K, T, boxes, lines, trace_object=0)["trace"]
+        roi = ctx.debug_roi(0)
+        assert roi["roi"] == tuple(tr["roi"]) and roi["roi"][2] > 640
+        np.testing.assert_array_equal(roi["canny"], tr["canny"])
+        np.testing.assert_array_equal(roi["dist"], tr["dist"])
+    assert float(roi["dist"].min()) > 65000.0   # the flat frame: no edges, the transform saturates
     ctx.close()
 
 
