@@ -382,7 +382,7 @@ def main():
     ap.add_argument("--no-online", action="store_true")
     ap.add_argument("--no-prio", action="store_true", help="A/B: keep each batch's whole chain on one stream (no high-priority tail)")
     ap.add_argument("--raster-dt", action="store_true", help="A/B: two-pass raster-scan distance transform kernel instead of the cone form")
-    ap.add_argument("--inflight", type=int, default=3, help="batches in flight on one GPU (contexts driven round-robin)")
+    ap.add_argument("--inflight", type=int, default=4, help="batches in flight on one GPU (contexts driven round-robin)")
     args = ap.parse_args()
     if args.steps is None:
         args.steps = 1000 if args.impl == "ours" else 5
