@@ -299,24 +299,38 @@ def run_ours(args, rank, world, local_rank):
     out = np.zeros((max(int(stats["n_objects"]), 1), topk), cs.CUBOID_DTYPE)
     counts = np.zeros(max(int(stats["n_objects"]), 1), np.int32)
 
-    def step_e2e():
-        ctx.detect_batch_host(imgs_pinned, wl["Ts"], wl["boxes"], wl["lines"], params, out, counts)
-        if world > 1:
-            ctx.check(ctx.L.cs_allgather_topk(ctx.h, recs_per_rank, C.byref(gathered)))
+    # two host threads, one context each, call the synchronous ABI entry point: the copies of one batch overlap the kernels of the other
+    # (single GPU only: two threads issuing NCCL calls on two communicators in an unordered way could deadlock across ranks)
+    e2e_ctxs = ctxs[:2] if (len(ctxs) >= 2 and world == 1) else ctxs[:1]
+    e2e_out = [(out, counts)] + [(np.zeros_like(out), np.zeros_like(counts)) for _ in e2e_ctxs[1:]]
 
-    for _ in range(2):
-        step_e2e()
+    def step_e2e(k=0):
+        cx = e2e_ctxs[k]
+        cx.detect_batch_host(imgs_pinned, wl["Ts"], wl["boxes"], wl["lines"], params, e2e_out[k][0], e2e_out[k][1])
+        if world > 1:
+            cx.check(cx.L.cs_allgather_topk(cx.h, recs_per_rank, C.byref(C.c_void_p())))
+
+    for k in range(len(e2e_ctxs)):
+        for _ in range(2):
+            step_e2e(k)
     barrier()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record(stream)
+    e2e_steps = max(4, min(args.steps, 50))
+    e2e_steps -= e2e_steps % len(e2e_ctxs)
+    import threading
+
+    def e2e_worker(k):
+        torch.cuda.set_device(local_rank)
+        for _ in range(e2e_steps // len(e2e_ctxs)):
+            step_e2e(k)
+
     t0 = time.perf_counter()
-    e2e_steps = max(3, min(args.steps, 50))
-    for _ in range(e2e_steps):
-        step_e2e()
-    e1.record(stream)
+    workers = [threading.Thread(target=e2e_worker, args=(k,)) for k in range(len(e2e_ctxs))]
+    for t in workers:
+        t.start()
+    for t in workers:
+        t.join()
     barrier()
-    wall_ms = (time.perf_counter() - t0) * 1e3
-    e2e_ms = max(e0.elapsed_time(e1), wall_ms)  # host-synchronous call: the wall clock is the honest bound
+    e2e_ms = (time.perf_counter() - t0) * 1e3  # host-synchronous calls: the wall clock around all of them is the honest bound
     e2e_t = torch.tensor([e2e_ms], device="cuda", dtype=torch.float64)
     if world > 1:
         dist.all_reduce(e2e_t, op=dist.ReduceOp.MAX)
@@ -337,8 +351,16 @@ def run_ours(args, rank, world, local_rank):
     dom_bytes = float(STAGE_BYTES[dom](stats, shp))
     achieved = dom_bytes / (kernel_ms[dom] * 1e-3) / 1e9 if kernel_ms[dom] > 0 else 0.0
     path_bytes = float(path_alg_bytes(stats, shp, topk))
-    roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
-                "traffic": None, "peak_source": peak_src, "alg_bytes_per_launch": dom_bytes,
+    traffic = None  # DRAM bytes of the stage's kernels per launch, from the committed ncu capture of this workload (profiles/)
+    try:
+        tj = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "r1_traffic.json")))
+        traffic = tj.get(args.workload, {}).get(dom)
+    except (OSError, ValueError):
+        pass
+    STAGE_KERNELS = {"dt": "k_dt_down<N> + k_dt_up<N> (one pair per ROI width class)", "canny": "k_canny_nms", "hyst": "k_canny_hyst", "gray": "k_bgr2gray_flat",
+                     "sweep": "k_sweep_warp", "fuse": "k_fuse_warp", "lines": "k_roi_lines", "lsd": "line detector kernels"}
+    roofline = {"bound": "hbm", "kernel": "%s: %s" % (dom, STAGE_KERNELS.get(dom, dom)), "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
+                "traffic": traffic, "peak_source": peak_src, "alg_bytes_per_launch": dom_bytes,
                 "path": {"alg_bytes_per_step": path_bytes, "achieved": path_bytes / (ms_per_step * 1e-3) / 1e9,
                          "frac": path_bytes / (ms_per_step * 1e-3) / 1e9 / hbm_peak},
                 "stage_ms": stage_acc}
@@ -362,7 +384,8 @@ def run_ours(args, rank, world, local_rank):
                    "parallelism": "frames sharded x%d, one NCCL all-gather of top-K" % world if world > 1 else "single GPU",
                    "batches_in_flight": len(ctxs)},
         "e2e": {"value": n_valid_all / (e2e_ms_step * 1e-3), "unit": "proposals/s", "frames_per_s": n_frames_all / (e2e_ms_step * 1e-3),
-                "ms_per_step": e2e_ms_step, "steps": e2e_steps, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)},
+                "ms_per_step": e2e_ms_step, "steps": e2e_steps, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+                "host_threads": len(e2e_ctxs), "timer": "wall clock around all calls (cs_detect_cuboids_batch is synchronous)"},
         "gpu_launches": int(stats["n_kernel_launches"]) * args.steps,
         "roofline": roofline, "cpu_baseline": cpu, "online": online, "clocks": sampler.summary(),
     }

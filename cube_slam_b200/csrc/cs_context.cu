@@ -290,6 +290,7 @@ int build_tables(cs_ctx *c)
                     jb.roi_t >= img_height)
                     return fail(c, CS_ERR_INVALID_ARG, "frame %d box %d: empty or out-of-image ROI", f, b - c->h_box_off[f]);
                 if (cs_dt_class_of(jb.roi_w) < 0) return fail(c, CS_ERR_CAPACITY, "ROI wider than %d px", 32 * 64);
+                if (jb.roi_h > 255 * 32) return fail(c, CS_ERR_CAPACITY, "ROI taller than %d px", 255 * 32); /* tile-row table packs the row in 8 bits */
                 jb.n_cand = fr.n_pose * fr.n_yaw * jb.n_top * 2;
                 jb.bw = (jb.roi_w + 31) / 32;
                 jb.dpitch = (jb.roi_w + 3) & ~3;

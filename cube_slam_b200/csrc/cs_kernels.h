@@ -8,7 +8,8 @@
 #include "cs_internal.h"
 
 /* One shared-memory carveout for every kernel of the chain: kernels of several batches share the SMs, and an SM only changes its
- * L1 / shared split when it is idle.  -1 leaves the driver's per-kernel choice.  (CS_SMEM_CARVEOUT in the environment overrides.) */
+ * L1 / shared split when it is idle.  Default 75 (% shared); -1 leaves the driver's per-kernel choice (CS_SMEM_CARVEOUT in the environment overrides;
+ * it is a preference: a kernel that needs more shared memory still gets it). */
 int cs_carveout_pref(void);
 #define CS_APPLY_CARVEOUT(kernel)                                                                            \
     do {                                                                                                     \

@@ -1060,7 +1060,7 @@ int cs_carveout_pref(void)
     static int v = -2;
     if (v == -2) {
         const char *e = getenv("CS_SMEM_CARVEOUT");
-        v = e ? atoi(e) : -1;
+        v = e ? atoi(e) : 75; /* measured on c3 with 4 batches in flight: 75 % shared -> +4..5 % over the driver's per-kernel choice */
     }
     return v;
 }
