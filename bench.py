@@ -357,7 +357,7 @@ def run_ours(args, rank, world, local_rank):
         traffic = tj.get(args.workload, {}).get(dom)
     except (OSError, ValueError):
         pass
-    STAGE_KERNELS = {"dt": "k_dt_down<N> + k_dt_up<N> (one pair per ROI width class)", "canny": "k_canny_nms", "hyst": "k_canny_hyst", "gray": "k_bgr2gray_flat",
+    STAGE_KERNELS = {"dt": "k_dt_bi<N> (one launch per ROI width class)", "canny": "k_canny_nms", "hyst": "k_canny_hyst", "gray": "k_bgr2gray_flat",
                      "sweep": "k_sweep_warp", "fuse": "k_fuse_warp", "lines": "k_roi_lines", "lsd": "line detector kernels"}
     roofline = {"bound": "hbm", "kernel": "%s: %s" % (dom, STAGE_KERNELS.get(dom, dom)), "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
                 "traffic": traffic, "peak_source": peak_src, "alg_bytes_per_launch": dom_bytes,

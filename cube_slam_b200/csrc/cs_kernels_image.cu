@@ -495,26 +495,31 @@ __global__ void __launch_bounds__(32) k_chamfer_dt(const CsJob *__restrict__ job
  *      D(p) = min over edge pixels q of  a * max(|dx|,|dy|) + (b - a) * min(|dx|,|dy|)           (a = DT_HV < b = DT_DG < 2a),
  * so any evaluation order of that minimum gives the same integers.  Split the sources of p by octant pair:
  *   - q in the closed VERTICAL cone (|dx| <= |dy|) is reached by |dx| diagonal and |dy| - |dx| vertical moves:
- *        S(x,y) = min(edge ? 0 : inf, S(x,y-1) + a, S(x-1,y-1) + b, S(x+1,y-1) + b)      top-down sweep   (k_dt_down)
- *        V(x,y) = min(S(x,y),         V(x,y+1) + a, V(x-1,y+1) + b, V(x+1,y+1) + b)      bottom-up sweep  (k_dt_up, warp 0)
- *     neither recurrence has a dependency inside a row, so a row step is a handful of adds and mins per pixel;
+ *        S(x,y) = min(edge ? 0 : inf, S(x,y-1) + a, S(x-1,y-1) + b, S(x+1,y-1) + b)      sources above:  top-down sweep
+ *        N(x,y) = min(edge ? 0 : inf, N(x,y+1) + a, N(x-1,y+1) + b, N(x+1,y+1) + b)      sources below:  bottom-up sweep
+ *        V = min(S, N)
+ *     neither recurrence has a dependency inside a row (a row step is a handful of adds and mins per pixel), and the two sweeps are
+ *     independent of each other;
  *   - q in the HORIZONTAL cone (|dy| <= |dx|) is reached by |dy| diagonal moves to a pixel p' of p's own row -- for which q lies on the rim of
  *     the vertical cone, so V(p') already holds that cost or less -- followed by horizontal moves:
- *        D(x,y) = min over x' of V(x',y) + a * |x - x'|                                   two 1-D scans    (k_dt_up, warps 1..3)
+ *        D(x,y) = min over x' of V(x',y) + a * |x - x'|                                   two 1-D min-plus scans per row
  *     rows are independent of each other: the scans are off the row-to-row dependency chain.
  * Every term is the cost of a real path (>= D) and the best path of either kind is among them (<= D), hence D exactly; values the
  * raster scan saturates at DIST_MAX (an edge-free ROI) come out >= DT_BIG and are written as DIST_MAX.  Columns between roi_w and the
  * padded pitch are treated as non-edge pixels of a wider image: a shortest path between two pixels of the ROI never leaves their
  * bounding box, so they change nothing inside the ROI.
- * The raster-scan kernel above spends its time in a chain of 2H dependent row scans of one warp; here the chain is 2H cheap steps.
+ *
+ * k_dt_bi<N>: one CTA of 8 warps per ROI.  Warp 0 sweeps down and warp 1 sweeps up AT THE SAME TIME, each from its end of the ROI.  Until
+ * they meet in the middle they park their rows in the distance map itself (S in the top half, N in the bottom half).  Past the middle
+ * each hands its rows through a shared-memory ring (named barriers, no polling) to three scan warps, which fetch the other sweep's row
+ * from the map, take the minimum, run the two scans and write the final f32 row in place.  The dependency chain is H cheap row steps
+ * (the raster scan: 2H steps with a 5-stage warp scan in each).
  * Layout: a lane owns 4 consecutive columns of every 128-column chunk, so a row moves as one coalesced 16-byte access per lane and chunk.
  * ------------------------------------------------------------------------------------------ */
-#define DT_PFC 8  /* rows of edge bits kept in flight by the down sweep when the plane does not fit in shared memory */
-#define DT_PFS 16 /* rows of S kept in flight by the up sweep */
-#define DT_VR 6   /* rows of V between the sweep warp and the scan warps of k_dt_up (a multiple of the 3 scan warps) */
+#define DT_NC 3 /* scan warps behind each sweep warp, one ring slot each */
 
-/* named barriers: the documented producer / consumer pairing of bar.arrive with bar.sync (no polling).  Slot s of the V ring uses barrier
- * 1 + s for "row ready" and 1 + DT_VR + s for "slot free"; every barrier has at most one arrival outstanding. */
+/* named barriers: the documented producer / consumer pairing of bar.arrive with bar.sync.  Ring r (0 down, 1 up), scan warp k:
+ * barrier 1 + 6 r + k = "row ready", 4 + 6 r + k = "slot free"; every barrier has at most one arrival outstanding. */
 __device__ __forceinline__ void dt_bar_sync(int id) { asm volatile("bar.sync %0, 64;" ::"r"(id) : "memory"); }
 __device__ __forceinline__ void dt_bar_arrive(int id) { asm volatile("bar.arrive %0, 64;" ::"r"(id) : "memory"); }
 
@@ -531,167 +536,87 @@ __device__ __forceinline__ void dt_rim(const int (&v)[NCH][4], int c, int lane, 
     if (c == NCH - 1 && lane == 31) R = DT_BIG;
 }
 
-template <int NCH, int PF>
-__device__ __forceinline__ void dt_down_warp(const uint32_t *__restrict__ planeS, int bwp, uint32_t *__restrict__ tmp, int h, int dpitch)
+/* one sweep warp.  DIR = +1: rows 0 .. h-1, -1: rows h-1 .. 0.  The first n_park rows go to the map, the rest to the ring. */
+template <int NCH, int DIR>
+__device__ __forceinline__ void dt_sweep(const uint32_t *plane /* bordered strong plane, shared or global */, int bwp, uint32_t *__restrict__ tmp,
+                                         int h, int dpitch, int n_park, uint32_t *ring, int bar_base)
 {
     const int lane = threadIdx.x & 31;
     const int bw = bwp - 2;
     const int sh = (lane & 7) * 4;
-    int up[NCH][4];
+    int v[NCH][4];
 #pragma unroll
     for (int c = 0; c < NCH; c++)
 #pragma unroll
-        for (int j = 0; j < 4; j++) up[c][j] = DT_BIG;
-    uint32_t pf[PF][NCH];
-    auto fetch = [&](int d, int row) { /* planeS: the bordered plane in global memory, or its copy in shared memory */
-        const uint32_t *rw = planeS + (size_t)(row + 1) * bwp + 1;
+        for (int j = 0; j < 4; j++) v[c][j] = DT_BIG;
+    uint32_t nxt[NCH];
+    auto fetch = [&](int y) {
+        const uint32_t *rw = plane + (size_t)(y + 1) * bwp + 1;
 #pragma unroll
         for (int c = 0; c < NCH; c++) {
             const int wi = 4 * c + (lane >> 3);
-            pf[d][c] = (wi < bw) ? rw[wi] : 0u; /* bits beyond roi_w are zero (NMS writes none) */
+            nxt[c] = (wi < bw) ? rw[wi] : 0u; /* bits beyond roi_w are zero (NMS writes none) */
         }
     };
-#pragma unroll
-    for (int d = 0; d < PF; d++) fetch(d, min(d, h - 1));
-    for (int i0 = 0; i0 < h; i0 += PF) {
-#pragma unroll
-        for (int d = 0; d < PF; d++) {
-            const int i = i0 + d;
-            if (i < h) {
-                uint32_t nib[NCH];
-#pragma unroll
-                for (int c = 0; c < NCH; c++) nib[c] = pf[d][c] >> sh;
-                fetch(d, min(i + PF, h - 1));
-                int nv[NCH][4], Lr[NCH], Rr[NCH];
-#pragma unroll
-                for (int c = 0; c < NCH; c++) dt_rim<NCH>(up, c, lane, Lr[c], Rr[c]); /* all shuffles of the row in flight together */
-#pragma unroll
-                for (int c = 0; c < NCH; c++) {
-                    const int L = Lr[c], R = Rr[c];
-#pragma unroll
-                    for (int j = 0; j < 4; j++) {
-                        const int l = (j == 0) ? L : up[c][j - 1];
-                        const int r = (j == 3) ? R : up[c][j + 1];
-                        int u = min(min(min(l, r) + DT_DG, up[c][j] + DT_HV), DT_BIG);
-                        if ((nib[c] >> j) & 1u) u = 0;
-                        nv[c][j] = u;
-                    }
-                }
-                uint32_t *trow = tmp + (size_t)i * dpitch;
-#pragma unroll
-                for (int c = 0; c < NCH; c++) {
-#pragma unroll
-                    for (int j = 0; j < 4; j++) up[c][j] = nv[c][j];
-                    const int col0 = c * 128 + lane * 4;
-                    if (col0 < dpitch) *reinterpret_cast<uint4 *>(trow + col0) = make_uint4(up[c][0], up[c][1], up[c][2], up[c][3]);
-                }
-            }
-        }
+    fetch(DIR > 0 ? 0 : h - 1);
+    if (n_park == 0) { /* nothing to park: the other sweep parks everything (h == 1) */
+        __threadfence_block();
+        __syncthreads();
     }
-}
-
-template <int NCH>
-__global__ void __launch_bounds__(32) k_dt_down(const CsJob *__restrict__ jobs, const int32_t *__restrict__ job_ids,
-                                                const uint32_t *__restrict__ bits_arena, float *__restrict__ dist_arena, int smem_words)
-{
-    const CsJob &jb = jobs[job_ids[blockIdx.x]];
-    const uint32_t *planeS = bits_arena + jb.bit_off;
-    uint32_t *tmp = reinterpret_cast<uint32_t *>(dist_arena + jb.px_off);
-    const int w = jb.roi_w, h = jb.roi_h, bwp = jb.bw + 2, dp = jb.dpitch;
-    if (w <= 0 || h <= 0) return;
-    /* the whole strong plane (1 bit per pixel) comes in with one burst of asynchronous copies; the sweep then never waits on memory */
-    const int n_words = (h + 2) * bwp;
-    if (n_words <= smem_words) {
-        const int lane = threadIdx.x;
-        for (int q = lane; q < n_words; q += 32) {
-            const unsigned sa = (unsigned)__cvta_generic_to_shared(dt_smem + q);
-            asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" ::"r"(sa), "l"(planeS + q));
-        }
-        cp_async_commit();
-        cp_async_wait<0>();
-        __syncwarp();
-        planeS = dt_smem;
-    }
-    dt_down_warp<NCH, (NCH <= 5 ? DT_PFC : 2)>(planeS, bwp, tmp, h, dp);
-}
-
-/* bottom-up sweep of warp 0: S rows arrive through a cp.async ring, V rows leave through the ring `vring` the scan warps read */
-template <int NCH>
-__device__ __forceinline__ void dt_up_sweep(const uint32_t *__restrict__ tmp, int h, int dpitch, uint32_t *sring, uint32_t *vring)
-{
-    const int lane = threadIdx.x & 31;
-    int dn[NCH][4];
+    for (int step = 0; step < h; step++) {
+        const int y = DIR > 0 ? step : h - 1 - step;
+        uint32_t nib[NCH];
 #pragma unroll
-    for (int c = 0; c < NCH; c++)
-#pragma unroll
-        for (int j = 0; j < 4; j++) dn[c][j] = DT_BIG;
-    const int chunks = dpitch >> 2; /* 16-byte pieces per row */
-#pragma unroll
-    for (int d = 0; d < DT_PFS; d++) {
-        const int i = h - 1 - d;
-        if (i >= 0)
-            for (int q = lane; q < chunks; q += 32) cp_async16(sring + (size_t)d * dpitch + q * 4, tmp + (size_t)i * dpitch + q * 4);
-        cp_async_commit();
-    }
-    int slot = 0, vslot = 0;
-    for (int t = 0; t < h; t++) {
-        const int i = h - 1 - t;
-        cp_async_wait<DT_PFS - 1>();
-        __syncwarp();
-        const uint32_t *srow = sring + (size_t)slot * dpitch;
-        int cur[NCH][4];
-#pragma unroll
-        for (int c = 0; c < NCH; c++) {
-            const int col0 = c * 128 + lane * 4;
-            uint4 q = make_uint4(DT_BIG, DT_BIG, DT_BIG, DT_BIG);
-            if (col0 < dpitch) q = *reinterpret_cast<const uint4 *>(srow + col0);
-            cur[c][0] = (int)q.x;
-            cur[c][1] = (int)q.y;
-            cur[c][2] = (int)q.z;
-            cur[c][3] = (int)q.w;
-        }
-        __syncwarp();
-        {
-            const int nxt = i - DT_PFS;
-            if (nxt >= 0)
-                for (int q = lane; q < chunks; q += 32) cp_async16(sring + (size_t)slot * dpitch + q * 4, tmp + (size_t)nxt * dpitch + q * 4);
-            cp_async_commit();
-        }
-        slot = (slot + 1 == DT_PFS) ? 0 : slot + 1;
+        for (int c = 0; c < NCH; c++) nib[c] = nxt[c] >> sh;
+        if (step + 1 < h) fetch(y + DIR);
         int nv[NCH][4], Lr[NCH], Rr[NCH];
 #pragma unroll
-        for (int c = 0; c < NCH; c++) dt_rim<NCH>(dn, c, lane, Lr[c], Rr[c]);
+        for (int c = 0; c < NCH; c++) dt_rim<NCH>(v, c, lane, Lr[c], Rr[c]); /* all shuffles of the row in flight together */
 #pragma unroll
         for (int c = 0; c < NCH; c++) {
-            const int L = Lr[c], R = Rr[c];
 #pragma unroll
             for (int j = 0; j < 4; j++) {
-                const int l = (j == 0) ? L : dn[c][j - 1];
-                const int r = (j == 3) ? R : dn[c][j + 1];
-                nv[c][j] = min(cur[c][j], min(min(l, r) + DT_DG, dn[c][j] + DT_HV)); /* cur <= DT_BIG */
+                const int l = (j == 0) ? Lr[c] : v[c][j - 1];
+                const int r = (j == 3) ? Rr[c] : v[c][j + 1];
+                int u = min(min(min(l, r) + DT_DG, v[c][j] + DT_HV), DT_BIG);
+                if ((nib[c] >> j) & 1u) u = 0;
+                nv[c][j] = u;
             }
         }
-        /* the slot is free once the scan warp that had row t - DT_VR is done with it */
-        if (t >= DT_VR) dt_bar_sync(1 + DT_VR + vslot);
-        uint32_t *vrow = vring + (size_t)vslot * dpitch;
 #pragma unroll
-        for (int c = 0; c < NCH; c++) {
+        for (int c = 0; c < NCH; c++)
 #pragma unroll
-            for (int j = 0; j < 4; j++) dn[c][j] = nv[c][j];
-            const int col0 = c * 128 + lane * 4;
-            if (col0 < dpitch) *reinterpret_cast<uint4 *>(vrow + col0) = make_uint4(dn[c][0], dn[c][1], dn[c][2], dn[c][3]);
+            for (int j = 0; j < 4; j++) v[c][j] = nv[c][j];
+        if (step < n_park) {
+            uint32_t *trow = tmp + (size_t)y * dpitch;
+#pragma unroll
+            for (int c = 0; c < NCH; c++) {
+                const int col0 = c * 128 + lane * 4;
+                if (col0 < dpitch) *reinterpret_cast<uint4 *>(trow + col0) = make_uint4(v[c][0], v[c][1], v[c][2], v[c][3]);
+            }
+            if (step == n_park - 1) { /* both sweeps are at the middle: parked rows become visible to the scan warps */
+                __threadfence_block();
+                __syncthreads();
+            }
+        } else {
+            const int idx = step - n_park, k = idx % DT_NC;
+            if (idx >= DT_NC) dt_bar_sync(bar_base + DT_NC + k); /* slot free? */
+            uint32_t *vrow = ring + (size_t)k * dpitch;
+#pragma unroll
+            for (int c = 0; c < NCH; c++) {
+                const int col0 = c * 128 + lane * 4;
+                if (col0 < dpitch) *reinterpret_cast<uint4 *>(vrow + col0) = make_uint4(v[c][0], v[c][1], v[c][2], v[c][3]);
+            }
+            dt_bar_arrive(bar_base + k); /* row ready */
         }
-        dt_bar_arrive(1 + vslot);
-        vslot = (vslot + 1 == DT_VR) ? 0 : vslot + 1;
     }
-    cp_async_wait<0>();
 }
 
-/* the two 1-D min-plus scans (slope a) of one row of V (shared memory) into the float row of the map.  A lane owns 4 consecutive columns of
- * each 128-column chunk; the warp scans of all chunks advance together, stage by stage, so their shuffles overlap (a warp issues in order:
- * chunk after chunk would serialise 5 x 5 dependent shuffles) */
+/* the two 1-D min-plus scans (slope a) of one row: V = min(ring row (shared), parked row (already in registers)) -> f32 row of the map.
+ * A lane owns 4 consecutive columns of each 128-column chunk; the warp scans of all chunks advance together, stage by stage, so their
+ * shuffles overlap (a warp issues in order: chunk after chunk would serialise the dependent shuffles) */
 template <int NCH>
-__device__ __forceinline__ void dt_row_scan(const uint32_t *vrow, float *__restrict__ drow, int dpitch, int lane)
+__device__ __forceinline__ void dt_row_scan(const uint32_t *vrow, const uint4 (&other)[NCH], float *__restrict__ drow, int dpitch, int lane)
 {
     const unsigned FULL = 0xffffffffu;
     const float scale = 1.f / 65536.f;
@@ -703,10 +628,10 @@ __device__ __forceinline__ void dt_row_scan(const uint32_t *vrow, float *__restr
         const int col0 = c * 128 + lane * 4;
         uint4 q = make_uint4(DT_BIG, DT_BIG, DT_BIG, DT_BIG);
         if (col0 < dpitch) q = *reinterpret_cast<const uint4 *>(vrow + col0);
-        t[c][0] = (int)q.x - DT_HV * col0;
-        t[c][1] = min((int)q.y - DT_HV * (col0 + 1), t[c][0]);
-        t[c][2] = min((int)q.z - DT_HV * (col0 + 2), t[c][1]);
-        t[c][3] = min((int)q.w - DT_HV * (col0 + 3), t[c][2]);
+        t[c][0] = min((int)q.x, (int)other[c].x) - DT_HV * col0;
+        t[c][1] = min(min((int)q.y, (int)other[c].y) - DT_HV * (col0 + 1), t[c][0]);
+        t[c][2] = min(min((int)q.z, (int)other[c].z) - DT_HV * (col0 + 2), t[c][1]);
+        t[c][3] = min(min((int)q.w, (int)other[c].w) - DT_HV * (col0 + 3), t[c][2]);
         incl[c] = t[c][3];
     }
 #pragma unroll
@@ -781,8 +706,8 @@ __device__ __forceinline__ void dt_row_scan(const uint32_t *vrow, float *__restr
     }
 }
 
-/* rows wider than 640 px: same scans, the forward result parked in the shared row instead of registers */
-__device__ __noinline__ void dt_row_scan_wide(uint32_t *vrow, float *__restrict__ drow, int dpitch, int lane, int nch)
+/* rows wider than 640 px: V = min(ring row, parked row) written back into the ring row, same scans, the forward result parked there too */
+__device__ __noinline__ void dt_row_scan_wide(uint32_t *vrow, const uint32_t *__restrict__ orow, float *__restrict__ drow, int dpitch, int lane, int nch)
 {
     const unsigned FULL = 0xffffffffu;
     const float scale = 1.f / 65536.f;
@@ -790,9 +715,12 @@ __device__ __noinline__ void dt_row_scan_wide(uint32_t *vrow, float *__restrict_
     int carry = INT_MAX;
     for (int c = 0; c < nch; c++) {
         const int col0 = c * 128 + lane * 4;
-        uint4 q = make_uint4(DT_BIG, DT_BIG, DT_BIG, DT_BIG);
-        if (col0 < dpitch) q = *reinterpret_cast<const uint4 *>(vrow + col0);
-        int t[4] = {(int)q.x, (int)q.y, (int)q.z, (int)q.w};
+        uint4 q = make_uint4(DT_BIG, DT_BIG, DT_BIG, DT_BIG), o = q;
+        if (col0 < dpitch) {
+            q = *reinterpret_cast<const uint4 *>(vrow + col0);
+            o = *reinterpret_cast<const uint4 *>(orow + col0);
+        }
+        int t[4] = {min((int)q.x, (int)o.x), min((int)q.y, (int)o.y), min((int)q.z, (int)o.z), min((int)q.w, (int)o.w)};
 #pragma unroll
         for (int k = 0; k < 4; k++) t[k] -= DT_HV * (col0 + k);
         t[1] = min(t[1], t[0]);
@@ -801,8 +729,8 @@ __device__ __noinline__ void dt_row_scan_wide(uint32_t *vrow, float *__restrict_
         int incl = t[3];
 #pragma unroll
         for (int dd = 1; dd < 32; dd <<= 1) {
-            const int o = __shfl_up_sync(FULL, incl, dd);
-            if (lane >= dd) incl = min(incl, o);
+            const int oo = __shfl_up_sync(FULL, incl, dd);
+            if (lane >= dd) incl = min(incl, oo);
         }
         int excl = __shfl_up_sync(FULL, incl, 1);
         if (lane == 0) excl = INT_MAX;
@@ -826,8 +754,8 @@ __device__ __noinline__ void dt_row_scan_wide(uint32_t *vrow, float *__restrict_
         int incl = t[0];
 #pragma unroll
         for (int dd = 1; dd < 32; dd <<= 1) {
-            const int o = __shfl_down_sync(FULL, incl, dd);
-            if (lane + dd < 32) incl = min(incl, o);
+            const int oo = __shfl_down_sync(FULL, incl, dd);
+            if (lane + dd < 32) incl = min(incl, oo);
         }
         int excl = __shfl_down_sync(FULL, incl, 1);
         if (lane == 31) excl = INT_MAX;
@@ -843,32 +771,73 @@ __device__ __noinline__ void dt_row_scan_wide(uint32_t *vrow, float *__restrict_
     }
 }
 
-/* one CTA of 4 warps per ROI: warp 0 sweeps bottom-up and hands each row of V to one of the three scan warps through shared memory */
+/* scan warp k of ring r: rows first, first + stride, ... (n of them), row i of the list is ring slot k once "row ready" fires */
 template <int NCH>
-__global__ void __launch_bounds__(128, (NCH <= 3 ? 5 : (NCH <= 5 ? 4 : 1))) k_dt_up(const CsJob *__restrict__ jobs, const int32_t *__restrict__ job_ids, float *__restrict__ dist_arena,
-                                               int ring_pitch)
+__device__ __forceinline__ void dt_scan_rows(uint32_t *__restrict__ tmp, int dpitch, int w, uint32_t *ring, int bar_base, int k, int first, int stride,
+                                             int n_rows)
+{
+    const int lane = threadIdx.x & 31;
+    uint32_t *vrow = ring + (size_t)k * dpitch;
+    for (int i = 0; i < n_rows; i++) {
+        const int y = first + i * stride;
+        uint32_t *orow = tmp + (size_t)y * dpitch; /* the other sweep's row, parked before the middle barrier */
+        if (NCH <= 5) {
+            uint4 other[NCH <= 5 ? NCH : 1];
+#pragma unroll
+            for (int c = 0; c < (NCH <= 5 ? NCH : 1); c++) {
+                const int col0 = c * 128 + lane * 4;
+                other[c] = make_uint4(DT_BIG, DT_BIG, DT_BIG, DT_BIG);
+                if (col0 < dpitch) other[c] = *reinterpret_cast<const uint4 *>(orow + col0); /* in flight while waiting for the ring */
+            }
+            dt_bar_sync(bar_base + k);
+            dt_row_scan<(NCH <= 5 ? NCH : 1)>(vrow, other, reinterpret_cast<float *>(orow), dpitch, lane);
+        } else {
+            dt_bar_sync(bar_base + k);
+            dt_row_scan_wide(vrow, orow, reinterpret_cast<float *>(orow), dpitch, lane, (w + 127) >> 7);
+        }
+        if (i + 1 < n_rows) dt_bar_arrive(bar_base + DT_NC + k); /* slot free (the sweep waits for it before the row after next) */
+    }
+}
+
+template <int NCH>
+__global__ void __launch_bounds__(32 * (2 + 2 * DT_NC), (NCH <= 3 ? 3 : (NCH <= 5 ? 2 : 1)))
+    k_dt_bi(const CsJob *__restrict__ jobs, const int32_t *__restrict__ job_ids, const uint32_t *__restrict__ bits_arena,
+            float *__restrict__ dist_arena, int plane_smem_words, int ring_pitch)
 {
     const CsJob &jb = jobs[job_ids[blockIdx.x]];
+    const uint32_t *planeS = bits_arena + jb.bit_off;
     uint32_t *tmp = reinterpret_cast<uint32_t *>(dist_arena + jb.px_off);
-    const int w = jb.roi_w, h = jb.roi_h, dp = jb.dpitch;
+    const int w = jb.roi_w, h = jb.roi_h, bwp = jb.bw + 2, dp = jb.dpitch;
     if (w <= 0 || h <= 0) return;
-    uint32_t *sring = dt_smem;                               /* DT_PFS rows of S */
-    uint32_t *vring = dt_smem + (size_t)DT_PFS * ring_pitch;  /* DT_VR rows of V */
-    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    if (wid == 0) {
-        dt_up_sweep<NCH>(tmp, h, dp, sring, vring);
-    } else {
-        const int k = wid - 1;
-        for (int t = k; t < h; t += 3) {
-            const int vslot = t % DT_VR;
-            dt_bar_sync(1 + vslot);
-            uint32_t *vrow = vring + (size_t)vslot * dp;
-            float *drow = reinterpret_cast<float *>(tmp + (size_t)(h - 1 - t) * dp);
-            if (NCH <= 5)
-                dt_row_scan<(NCH <= 5 ? NCH : 1)>(vrow, drow, dp, lane);
-            else
-                dt_row_scan_wide(vrow, drow, dp, lane, (w + 127) >> 7);
-            if (t + DT_VR < h) dt_bar_arrive(1 + DT_VR + vslot);
+    uint32_t *ringD = dt_smem, *ringU = dt_smem + (size_t)DT_NC * ring_pitch;
+    uint32_t *plane_s = dt_smem + (size_t)2 * DT_NC * ring_pitch;
+    /* the whole strong plane (1 bit per pixel) comes in with one burst of asynchronous copies; the sweeps then never wait on memory */
+    const int n_words = (h + 2) * bwp;
+    if (n_words <= plane_smem_words) {
+        for (int q = threadIdx.x; q < n_words; q += blockDim.x) {
+            const unsigned sa = (unsigned)__cvta_generic_to_shared(plane_s + q);
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" ::"r"(sa), "l"(planeS + q));
+        }
+        cp_async_commit();
+        cp_async_wait<0>();
+        planeS = plane_s;
+    }
+    __syncthreads();
+    const int mid = h >> 1; /* the down sweep parks rows [0, mid), the up sweep rows [mid, h) */
+    const int wid = threadIdx.x >> 5;
+    if (wid == 0)
+        dt_sweep<NCH, 1>(planeS, bwp, tmp, h, dp, mid, ringD, 1);
+    else if (wid == 1)
+        dt_sweep<NCH, -1>(planeS, bwp, tmp, h, dp, h - mid, ringU, 1 + 2 * DT_NC);
+    else {
+        __syncthreads(); /* the middle barrier of the sweeps */
+        const int r = (wid - 2) / DT_NC, k = (wid - 2) % DT_NC;
+        if (r == 0) { /* rows mid .. h-1 from the down sweep; the parked row holds N */
+            const int n = h - mid;
+            dt_scan_rows<NCH>(tmp, dp, w, ringD, 1, k, mid + k, DT_NC, (n - k + DT_NC - 1) / DT_NC);
+        } else { /* rows mid-1 .. 0 from the up sweep; the parked row holds S */
+            const int n = mid;
+            dt_scan_rows<NCH>(tmp, dp, w, ringU, 1 + 2 * DT_NC, k, mid - 1 - k, -DT_NC, (n - k + DT_NC - 1) / DT_NC);
         }
     }
 }
@@ -1119,28 +1088,22 @@ void cs_launch_hyst(const CsJob *d_jobs, int n_jobs, uint32_t *d_bits, int max_p
 
 /* d_ids: job ids grouped by width class, tallest ROI first inside a class; class_off[c] .. class_off[c + 1] is the slice of class c;
  * class_plane_words[c]: words of the largest bordered bit plane of the class.
- * raster = the two-pass raster-scan kernel (A/B switch); default is the cone form: down sweep, then up sweep + row scans */
+ * raster = the two-pass raster-scan kernel (A/B switch); default is the cone form (k_dt_bi) */
 template <int NCH>
 static void dt_launch_class(const CsJob *d_jobs, const int32_t *d_ids, int count, int width, int plane_words, const uint32_t *d_bits, float *d_dist,
                             cudaStream_t st, int64_t *launches)
 {
-    static int attr_down = 0, attr_up = 0;
-    int down_words = plane_words;
-    if (down_words > (96 * 1024) / 4) down_words = 0; /* huge ROIs: stream the bits from global memory */
-    if (down_words * 4 > attr_down && down_words * 4 > 48 * 1024) {
-        cudaFuncSetAttribute(k_dt_down<NCH>, cudaFuncAttributeMaxDynamicSharedMemorySize, down_words * 4);
-        attr_down = down_words * 4;
+    static int attr = 0;
+    int pw = plane_words;
+    if (pw > (96 * 1024) / 4) pw = 0; /* huge ROIs: the sweeps read the bits from global memory */
+    const int bytes = (2 * DT_NC * width + pw) * 4;
+    if (bytes > attr && bytes > 48 * 1024) {
+        cudaFuncSetAttribute(k_dt_bi<NCH>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+        attr = bytes;
     }
-    const int bytes_up = (DT_PFS + DT_VR) * width * 4;
-    if (bytes_up > attr_up && bytes_up > 48 * 1024) {
-        cudaFuncSetAttribute(k_dt_up<NCH>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes_up);
-        attr_up = bytes_up;
-    }
-    CS_APPLY_CARVEOUT(k_dt_down<NCH>);
-    CS_APPLY_CARVEOUT(k_dt_up<NCH>);
-    k_dt_down<NCH><<<count, 32, down_words * 4, st>>>(d_jobs, d_ids, d_bits, d_dist, down_words);
-    k_dt_up<NCH><<<count, 128, bytes_up, st>>>(d_jobs, d_ids, d_dist, width);
-    (*launches) += 2;
+    CS_APPLY_CARVEOUT(k_dt_bi<NCH>);
+    k_dt_bi<NCH><<<count, 32 * (2 + 2 * DT_NC), bytes, st>>>(d_jobs, d_ids, d_bits, d_dist, pw, width);
+    (*launches)++;
 }
 
 void cs_launch_dt(const CsJob *d_jobs, const int32_t *d_ids, int n_jobs, int max_dpitch, const int *class_off, const int *class_plane_words,

@@ -11,18 +11,20 @@ def cone_dt(edges):
     h, w = edges.shape
     S = np.empty((h, w), np.int64)
     up = np.full(w + 2, BIG, np.int64)
-    for y in range(h):                                   # k_dt_down
+    for y in range(h):                                   # the down sweep of k_dt_bi
         nv = np.minimum(np.minimum(np.minimum(up[:-2], up[2:]) + B, up[1:-1] + A), BIG)
         nv[edges[y] > 0] = 0
         S[y] = nv
         up[1:-1] = nv
-    V = np.empty_like(S)
+    N = np.empty_like(S)
     dn = np.full(w + 2, BIG, np.int64)
-    for y in range(h - 1, -1, -1):                       # k_dt_up, sweep warp
-        nv = np.minimum(S[y], np.minimum(np.minimum(dn[:-2], dn[2:]) + B, dn[1:-1] + A))
-        V[y] = nv
+    for y in range(h - 1, -1, -1):                       # the up sweep, the mirror image
+        nv = np.minimum(np.minimum(np.minimum(dn[:-2], dn[2:]) + B, dn[1:-1] + A), BIG)
+        nv[edges[y] > 0] = 0
+        N[y] = nv
         dn[1:-1] = nv
-    cols = np.arange(w)                                   # k_dt_up, scan warps
+    V = np.minimum(S, N)                                  # taken by the scan warps
+    cols = np.arange(w)                                   # the scan warps
     F = np.minimum.accumulate(V - A * cols, axis=1) + A * cols
     D = np.minimum.accumulate((F + A * cols)[:, ::-1], axis=1)[:, ::-1] - A * cols
     dist_max = np.float32(0xffffffff - B) * np.float32(1 / 65536.0)
