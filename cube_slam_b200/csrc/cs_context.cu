@@ -448,7 +448,7 @@ int run_batch(cs_ctx *c, bool sync)
     }
     if (!fused)
         cs_launch_dt((const CsJob *)c->d_jobs.p, (const int32_t *)c->d_dtids.p, n_jobs, c->max_dpitch, c->dt_class_off, c->dt_class_plane_words, (const uint32_t *)c->d_bits.p,
-                     (float *)c->d_dist.p, c->use_raster_dt != 0, st, c->stream2, c->ev_dt_fork, c->ev_dt_join, &c->launches);
+                     (float *)c->d_dist.p, c->use_raster_dt, st, c->stream2, c->ev_dt_fork, c->ev_dt_join, &c->launches);
     mark(ST_LINES);
     cudaStreamWaitEvent(st, c->ev_join, 0); /* join */
     mark(ST_SWEEP);
@@ -825,7 +825,7 @@ int cs_set_profiling(cs_ctx *c, int enable)
     if (!c) return CS_ERR_INVALID_ARG;
     c->profiling = (enable & 1) != 0;
     c->use_fused_dt = (enable & 4) != 0; /* bit 2: experimental fused hysteresis + wavefront-DT kernel */
-    c->use_raster_dt = (enable & 32) != 0; /* bit 5: two-pass raster-scan distance transform kernel */
+    c->use_raster_dt = ((enable & 32) ? 1 : 0) | ((enable & 64) ? 2 : 0); /* bit 5: raster-scan distance transform kernel; bit 6: cone form, bits from global */
     c->use_prio = (enable & 16) == 0;      /* bit 4: keep the whole chain on one stream (no high-priority tail) */
     c->use_cta_select = (enable & 8) != 0; /* bit 3: CTA-wide sweep / selection kernels (the general path) instead of the warp ones */
     return CS_OK;

@@ -32,8 +32,8 @@ void cs_launch_canny(const uint8_t *d_gray, int img_w, int img_h, const CsJob *d
                      size_t bits_bytes, int low, int high, cudaStream_t st, int64_t *launches);
 void cs_launch_hyst(const CsJob *d_jobs, int n_jobs, uint32_t *d_bits, int max_plane_words, cudaStream_t st, int64_t *launches);
 void cs_launch_dt(const CsJob *d_jobs, const int32_t *d_ids, int n_jobs, int max_dpitch, const int *class_off, const int *class_plane_words,
-                  const uint32_t *d_bits, float *d_dist, bool raster, cudaStream_t st, cudaStream_t st_side, cudaEvent_t ev_fork, cudaEvent_t ev_join,
-                  int64_t *launches);
+                  const uint32_t *d_bits, float *d_dist, int raster_or_flags, cudaStream_t st, cudaStream_t st_side, cudaEvent_t ev_fork,
+                  cudaEvent_t ev_join, int64_t *launches);
 bool cs_launch_hyst_dt(const CsJob *d_jobs, int n_jobs, uint32_t *d_bits, float *d_dist, int max_plane_words, int max_dpitch, int max_h,
                        cudaStream_t st, int64_t *launches);
 void cs_launch_roi_lines(const CsJob *d_jobs, int n_jobs, const CsFrame *d_frames, const double *d_lines, const float *d_lines_f32,

@@ -126,6 +126,7 @@ __global__ void __launch_bounds__(256) k_canny_nms(const uint8_t *__restrict__ g
         if (tile_x + 1 < tiles_x) fetch(x0 + CT);
         /* Sobel + magnitude for the (CT+2)^2 halo region: a thread owns one column and a strip of 5 rows, the three-row
          * window slides down in registers (21 shared loads for 5 results) */
+        int loud = 0; /* does any pixel of the tile proper exceed the low threshold? (the +1 halo ring does not count) */
         if (tid < (CT + 2) * 7) {
             const int strip = tid / (CT + 2), lx = tid - strip * (CT + 2);
             const int r0 = strip * 5;
@@ -147,12 +148,15 @@ __global__ void __launch_bounds__(256) k_canny_nms(const uint8_t *__restrict__ g
                     const int dx = rd[j] + 2 * rd[j + 1] + rd[j + 2];
                     const int dy = rs[j + 2] - rs[j];
                     const bool in = col_in && (gy >= 0) && (gy < h);
+                    const int m = in ? abs(dx) + abs(dy) : 0;
                     s_d[ly][lx] = (dy << 16) | (dx & 0xffff);
-                    s_m[ly][lx] = in ? (uint16_t)(abs(dx) + abs(dy)) : (uint16_t)0;
+                    s_m[ly][lx] = (uint16_t)m;
+                    loud |= (m > low) && (lx >= 1) && (lx <= CT) && (ly >= 1) && (ly <= CT);
                 }
             }
         }
-        __syncthreads();
+        /* a quiet tile has no edge pixel whatever its neighbours are: its words stay as the memset left them */
+        if (!__syncthreads_or(loud)) continue;
 #pragma unroll
         for (int k = 0; k < 4; k++) {
             const int ly = ty + 8 * k, lx = tx;
@@ -1088,14 +1092,15 @@ void cs_launch_hyst(const CsJob *d_jobs, int n_jobs, uint32_t *d_bits, int max_p
 
 /* d_ids: job ids grouped by width class, tallest ROI first inside a class; class_off[c] .. class_off[c + 1] is the slice of class c;
  * class_plane_words[c]: words of the largest bordered bit plane of the class.
- * raster = the two-pass raster-scan kernel (A/B switch); default is the cone form (k_dt_bi) */
+ * flags: bit 0 = the two-pass raster-scan kernel (A/B switch) instead of the cone form (k_dt_bi); bit 1 = cone form reading the edge bits
+ * from global memory (the path of ROIs whose bit plane exceeds 96 KB, forced for the tests) */
 template <int NCH>
 static void dt_launch_class(const CsJob *d_jobs, const int32_t *d_ids, int count, int width, int plane_words, const uint32_t *d_bits, float *d_dist,
                             cudaStream_t st, int64_t *launches)
 {
     static int attr = 0;
     int pw = plane_words;
-    if (pw > (96 * 1024) / 4) pw = 0; /* huge ROIs: the sweeps read the bits from global memory */
+    if (pw > (96 * 1024) / 4 || pw < 0) pw = 0; /* huge ROIs (or the debug switch): the sweeps read the bits from global memory */
     const int bytes = (2 * DT_NC * width + pw) * 4;
     if (bytes > attr && bytes > 48 * 1024) {
         cudaFuncSetAttribute(k_dt_bi<NCH>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
@@ -1107,11 +1112,11 @@ static void dt_launch_class(const CsJob *d_jobs, const int32_t *d_ids, int count
 }
 
 void cs_launch_dt(const CsJob *d_jobs, const int32_t *d_ids, int n_jobs, int max_dpitch, const int *class_off, const int *class_plane_words,
-                  const uint32_t *d_bits, float *d_dist, bool raster, cudaStream_t st, cudaStream_t st_side, cudaEvent_t ev_fork, cudaEvent_t ev_join,
-                  int64_t *launches)
+                  const uint32_t *d_bits, float *d_dist, int raster_or_flags, cudaStream_t st, cudaStream_t st_side, cudaEvent_t ev_fork,
+                  cudaEvent_t ev_join, int64_t *launches)
 {
     if (n_jobs <= 0) return;
-    if (raster) {
+    if (raster_or_flags & 1) {
         static int cur_attr = 0;
         const int bytes = DT_PF * max_dpitch * 4;
         if (bytes > cur_attr && bytes > 48 * 1024) {
@@ -1143,7 +1148,7 @@ void cs_launch_dt(const CsJob *d_jobs, const int32_t *d_ids, int n_jobs, int max
         const int count = class_off[c + 1] - class_off[c];
         if (count <= 0) continue;
         const int32_t *ids = d_ids + class_off[c];
-        const int width = cs_dt_class_width[c], pw = class_plane_words[c];
+        const int width = cs_dt_class_width[c], pw = (raster_or_flags & 2) ? -1 : class_plane_words[c];
         cudaStream_t s = (side && c != main_cls) ? st_side : st;
         switch (c) {
         case 0: dt_launch_class<1>(d_jobs, ids, count, width, pw, d_bits, d_dist, s, launches); break;

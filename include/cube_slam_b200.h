@@ -171,7 +171,8 @@ void *cs_stream(cs_ctx *ctx);
 int cs_stage_ms(cs_ctx *ctx, const char *stage, float *ms);
 /* bit 0: per-stage CUDA-event timing (adds event records only; the chain then stays on one stream).  Debug / A-B switches:
  * bit 2 fused hysteresis + wavefront distance transform, bit 3 CTA-wide sweep / selection kernels, bit 4 no high-priority
- * stream for the distance transform -> sweep -> selection tail, bit 5 raster-scan distance transform (one kernel) instead of the cone form */
+ * stream for the distance transform -> sweep -> selection tail, bit 5 raster-scan distance transform (one kernel) instead of the cone form,
+ * bit 6 cone-form distance transform reading the edge bits from global memory (the path of ROIs whose bit plane exceeds 96 KB) */
 int cs_set_profiling(cs_ctx *ctx, int enable);
 
 /* debug: when several contexts run concurrently with profiling on, the offsets (ms) of the 8 stage starts and the end of ctx's last run

@@ -169,7 +169,7 @@ def test_dense_sweep_and_sampling(cs, oracle):
     ctx.close()
 
 
-@pytest.mark.parametrize("flags", [0, 32])
+@pytest.mark.parametrize("flags", [0, 32, 64])
 def test_distance_transform_wide_sparse_and_empty_rois(cs, oracle, flags):
     """ROIs wider than 640 px (the row scans park their forward result in the row), an ROI with a single edge pixel
     (most pixels have no source in their vertical cone) and an edge-free ROI (DIST_MAX everywhere)."""
