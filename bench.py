@@ -273,25 +273,39 @@ def run_ours(args, rank, world, local_rank):
             det.use_LSD = use_lsd            # object_slam sets true (main_obj.cpp:365); the class default is EDLines (line_lbd_allclass.cpp:121)
             det.line_length_thres = 15
             lp = det.params()
+            # one batch alone, profiled: latency of a batch and its stage times
+            ctx.set_profiling(1 | dbg_flags)
             ctx.upload_online(wl["imgs"], wl["Ts"], wl["boxes"], lp, params)
             for _ in range(2):
                 ctx.run()
             st_on = ctx.stats()
-            o0, o1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            n_on = max(3, min(args.steps, 5))
+            stage_on = ctx.stage_ms()
+            # throughput: the same `--inflight` contexts as above, round-robin (the sequential half of a detector is one warp per frame)
+            for cx in ctxs[1:]:
+                cx.upload_online(wl["imgs"], wl["Ts"], wl["boxes"], lp, params)
+            for cx in ctxs:
+                cx.set_profiling(dbg_flags)
+                cx.run_async()
             torch.cuda.synchronize()
-            o0.record(stream)
-            for _ in range(n_on):
-                ctx.run_async()
-            o1.record(stream)
+            n_on = 2 * len(ctxs)
+            o0 = torch.cuda.Event(enable_timing=True)
+            o_end = [torch.cuda.Event(enable_timing=True) for _ in ctxs]
+            o0.record(streams[0])
+            for st_ in streams[1:]:
+                st_.wait_event(o0)
+            for i in range(n_on):
+                ctxs[i % len(ctxs)].run_async()
+            for e, st_ in zip(o_end, streams):
+                e.record(st_)
             torch.cuda.synchronize()
-            on_ms = o0.elapsed_time(o1) / n_on
-            ctx.run()
+            on_ms = max(o0.elapsed_time(e) for e in o_end) / n_on
             online[flavour] = {"workload": "same frames, lines from cs_detect_lines (%s, length > 15) on the device" % flavour, "ms_per_step": on_ms,
                                "frames_per_s": F / (on_ms * 1e-3), "value": st_on["n_valid"] / (on_ms * 1e-3), "unit": "proposals/s",
-                               "n_valid": st_on["n_valid"], "stage_ms": ctx.stage_ms()}
+                               "n_valid": st_on["n_valid"], "batches_in_flight": len(ctxs), "one_batch_alone_ms": stage_on.get("total"),
+                               "stage_ms": stage_on}
         online["note"] = "the sequential half of either detector (LSD seed loop / EDLines routing + fitting) is one warp per frame; at 256 frames it is latency-bound"
-        ctx.upload(wl["imgs"], wl["Ts"], wl["boxes"], wl["lines"], params)
+        for cx in ctxs:
+            cx.upload(wl["imgs"], wl["Ts"], wl["boxes"], wl["lines"], params)
 
     # ---- end to end through the host-buffer ABI call ("e2e")
     pinned = torch.from_numpy(wl["imgs"]).pin_memory()
