@@ -75,7 +75,7 @@ def build(force=False, verbose=False):
         sys.stderr.write("\n".join(log) + "\n")
     if failed:
         raise RuntimeError("nvcc failed; see %s" % os.path.join(LIBDIR, "build.log"))
-    cmd = [nvcc, "-shared", "-o", LIB] + objs + ["-lcudart_static", "-ldl", "-lpthread", "-lrt"]
+    cmd = [nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", LIB] + objs + ["-lcudart_static", "-ldl", "-lpthread", "-lrt"]
     subprocess.check_call(cmd)
     return LIB
 
