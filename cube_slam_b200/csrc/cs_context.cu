@@ -704,6 +704,24 @@ int cs_cam_pose(const double K[9], const double T_wc[16], double euler_zyx[3], d
     return CS_OK;
 }
 
+int cs_cuboid_measurement(const cs_cuboid_rec *rec, const double cam_t[3], const double cam_q_xyzw[4], const double cam_euler_raw[3],
+                          double meas_t[3], double meas_q_xyzw[4], double meas_scale[3], double *meas_quality)
+{
+    if (!rec || !cam_t || !cam_q_xyzw || !meas_t || !meas_q_xyzw) return CS_ERR_INVALID_ARG;
+    double e[3];
+    const double *en = nullptr;
+    if (cam_euler_raw) { /* main_obj.cpp:465-471: the pose the winning proposal was generated with */
+        e[0] = cam_euler_raw[0] + rec->camera_roll_delta;
+        e[1] = cam_euler_raw[1] + rec->camera_pitch_delta;
+        e[2] = cam_euler_raw[2];
+        en = e;
+    }
+    cshost::cuboid_measurement(rec->pos, rec->rotY, cam_t, cam_q_xyzw, en, meas_t, meas_q_xyzw);
+    if (meas_scale) std::memcpy(meas_scale, rec->scale, 3 * sizeof(double));
+    if (meas_quality) *meas_quality = (1 - rec->normalized_error + 0.5) / 2; /* main_obj.cpp:505 */
+    return CS_OK;
+}
+
 int cs_batch_upload(cs_ctx *c, const uint8_t *imgs, int n_frames, int width, int height, int stride, int channels, const double *T_wc,
                     const double *boxes, const int32_t *box_offsets, const double *lines, const int32_t *line_offsets,
                     const cs_cuboid_params *params)

@@ -126,4 +126,123 @@ int linespace_count_i(int start, int end, int step)
     return n;
 }
 
+
+/* ---- cuboid -> g2o measurement (object_slam/src/main_obj.cpp:455-473,505; g2o_Object.h:36-41,127-133; Thirdparty/g2o/g2o/types/se3quat.h)
+ * Quaternions are (x, y, z, w) like Eigen's coeffs().  Each step is the g2o / Eigen operation it names. */
+namespace {
+struct Q {
+    double x, y, z, w;
+};
+/* SE3Quat::normalizeRotation: w >= 0, unit norm */
+void normalize_rotation(Q &q)
+{
+    if (q.w < 0) {
+        q.x = -q.x;
+        q.y = -q.y;
+        q.z = -q.z;
+        q.w = -q.w;
+    }
+    const double n = std::sqrt(q.x * q.x + q.y * q.y + q.z * q.z + q.w * q.w);
+    q.x /= n;
+    q.y /= n;
+    q.z /= n;
+    q.w /= n;
+}
+/* Eigen quaternion product a * b */
+Q qmul(const Q &a, const Q &b)
+{
+    Q r;
+    r.w = a.w * b.w - a.x * b.x - a.y * b.y - a.z * b.z;
+    r.x = a.w * b.x + a.x * b.w + a.y * b.z - a.z * b.y;
+    r.y = a.w * b.y + a.y * b.w + a.z * b.x - a.x * b.z;
+    r.z = a.w * b.z + a.z * b.w + a.x * b.y - a.y * b.x;
+    return r;
+}
+/* Eigen QuaternionBase::_transformVector: v + w * (2 q x v) + q x (2 q x v) */
+void qrot(const Q &q, const double *v, double *out)
+{
+    double uv[3] = {q.y * v[2] - q.z * v[1], q.z * v[0] - q.x * v[2], q.x * v[1] - q.y * v[0]};
+    uv[0] += uv[0];
+    uv[1] += uv[1];
+    uv[2] += uv[2];
+    out[0] = v[0] + q.w * uv[0] + (q.y * uv[2] - q.z * uv[1]);
+    out[1] = v[1] + q.w * uv[1] + (q.z * uv[0] - q.x * uv[2]);
+    out[2] = v[2] + q.w * uv[2] + (q.x * uv[1] - q.y * uv[0]);
+}
+/* Eigen::Quaterniond(Matrix3d): Shepperd's branches, as in euler_from_rot above */
+Q quat_from_rot(const double *R)
+{
+    Q q;
+    const double tr = R[0] + R[4] + R[8];
+    if (tr > 0.0) {
+        double t = std::sqrt(tr + 1.0);
+        q.w = 0.5 * t;
+        t = 0.5 / t;
+        q.x = (R[7] - R[5]) * t;
+        q.y = (R[2] - R[6]) * t;
+        q.z = (R[3] - R[1]) * t;
+    } else {
+        int i = 0;
+        if (R[4] > R[0]) i = 1;
+        if (R[8] > R[i * 4]) i = 2;
+        const int j = (i + 1) % 3, k = (j + 1) % 3;
+        double v[3];
+        double t = std::sqrt(R[i * 4] - R[j * 4] - R[k * 4] + 1.0);
+        v[i] = 0.5 * t;
+        t = 0.5 / t;
+        q.w = (R[k * 3 + j] - R[j * 3 + k]) * t;
+        v[j] = (R[j * 3 + i] + R[i * 3 + j]) * t;
+        v[k] = (R[k * 3 + i] + R[i * 3 + k]) * t;
+        q.x = v[0];
+        q.y = v[1];
+        q.z = v[2];
+    }
+    return q;
+}
+}  // namespace
+
+void cuboid_measurement(const double *pos, double rotY, const double *cam_t, const double *cam_q_xyzw, const double *cam_euler_new,
+                        double *meas_t, double *meas_q_xyzw)
+{
+    /* cube_ground_value.fromMinimalVector: pose = SE3Quat(zyx_euler_to_quat(0, 0, rotY), pos) */
+    Q qo;
+    {
+        const double sy = std::sin(rotY * 0.5), cy = std::cos(rotY * 0.5);
+        const double sp = std::sin(0.0), cp = std::cos(0.0), sr = std::sin(0.0), cr = std::cos(0.0);
+        qo.w = cr * cp * cy + sr * sp * sy;
+        qo.x = sr * cp * cy - cr * sp * sy;
+        qo.y = cr * sp * cy + sr * cp * sy;
+        qo.z = cr * cp * sy - sr * sp * cy;
+        normalize_rotation(qo);
+    }
+    /* the camera pose: SE3Quat(Vector7d) normalises; with sampled roll / pitch SE3Quat(euler_zyx_to_rot(new eulers), t) */
+    Q qc;
+    if (cam_euler_new) {
+        double R[9];
+        euler_to_rot(cam_euler_new[0], cam_euler_new[1], cam_euler_new[2], R);
+        qc = quat_from_rot(R);
+    } else {
+        qc.x = cam_q_xyzw[0];
+        qc.y = cam_q_xyzw[1];
+        qc.z = cam_q_xyzw[2];
+        qc.w = cam_q_xyzw[3];
+    }
+    normalize_rotation(qc);
+    /* transform_to: Twc.inverse() * pose.  inverse(): r = conj, t = r * (-t); operator*: t += r * t2, r *= r2, normalise */
+    Q qi = {-qc.x, -qc.y, -qc.z, qc.w};
+    const double nt[3] = {cam_t[0] * -1., cam_t[1] * -1., cam_t[2] * -1.};
+    double ti[3], rp[3];
+    qrot(qi, nt, ti);
+    qrot(qi, pos, rp);
+    meas_t[0] = ti[0] + rp[0];
+    meas_t[1] = ti[1] + rp[1];
+    meas_t[2] = ti[2] + rp[2];
+    Q qm = qmul(qi, qo);
+    normalize_rotation(qm);
+    meas_q_xyzw[0] = qm.x;
+    meas_q_xyzw[1] = qm.y;
+    meas_q_xyzw[2] = qm.z;
+    meas_q_xyzw[3] = qm.w;
+}
+
 }  // namespace cshost

@@ -218,6 +218,22 @@ class Context(object):
         return dict(n=n.value, valid=valid[:n.value], dist_err=de[:n.value], angle_err=ae[:n.value])
 
 
+def cuboid_measurement(rec, cam_t, cam_q_xyzw, cam_euler_raw=None):
+    """object_slam/src/main_obj.cpp:455-473,505: the cuboid record as a measurement in the camera frame.
+    Returns (t[3], q_xyzw[4], scale[3], meas_quality).  cam_euler_raw = cam_pose_raw.euler_angle when roll / pitch were sampled."""
+    L = _lib.load()
+    rec = np.ascontiguousarray(np.asarray(rec).reshape(-1)[:1])
+    t, q, s = np.zeros(3), np.zeros(4), np.zeros(3)
+    qual = C.c_double()
+    e = None if cam_euler_raw is None else _lib.ptr(np.ascontiguousarray(cam_euler_raw, np.float64), C.c_double)
+    rc = L.cs_cuboid_measurement(rec.ctypes.data, _lib.ptr(np.ascontiguousarray(cam_t, np.float64), C.c_double),
+                                 _lib.ptr(np.ascontiguousarray(cam_q_xyzw, np.float64), C.c_double), e, _lib.ptr(t, C.c_double),
+                                 _lib.ptr(q, C.c_double), _lib.ptr(s, C.c_double), C.byref(qual))
+    if rc != 0:
+        raise CubeSlamError(_lib.STATUS_NAMES.get(rc, str(rc)))
+    return t, q, s, qual.value
+
+
 def default_params(**kw):
     p = CuboidParams()
     _lib.load().cs_default_cuboid_params(C.byref(p))

@@ -126,6 +126,14 @@ int cs_set_calibration(cs_ctx *ctx, const double K[9]);
  * K*R^-1 of a camera-to-world transform.  Host-only, needs no context. */
 int cs_cam_pose(const double K[9], const double T_wc[16], double euler_zyx[3], double KinvR[9]);
 
+/* The step right after the path in object_slam (object_slam/src/main_obj.cpp:455-473,505): the best cuboid as a measurement in the
+ * camera frame, cube_ground_value.transform_to(Twc) of g2o::cuboid (object_slam/include/object_slam/g2o_Object.h:36-41,127-133) with
+ * g2o's SE3Quat algebra, and meas_quality = (1 - normalized_error + 0.5) / 2.  cam_t / cam_q_xyzw: the camera pose Twc as the
+ * truth-pose file gives it (x y z qx qy qz qw); cam_euler_raw: cam_pose_raw.euler_angle when whether_sample_cam_roll_pitch was on
+ * (the measurement is then taken in the frame of the sampled roll / pitch), else NULL.  Host-only, needs no context. */
+int cs_cuboid_measurement(const cs_cuboid_rec *rec, const double cam_t[3], const double cam_q_xyzw[4], const double cam_euler_raw[3],
+                          double meas_t[3], double meas_q_xyzw[4], double meas_scale[3], double *meas_quality);
+
 /* ---- cuboid proposals ------------------------------------------------------------------- */
 /* detect_3d_cuboid::detect_cuboid (box_proposal_detail.cpp:56-557; header detect_3d_cuboid.h:62-63)
  * for ONE frame with HOST buffers.  img: H x stride bytes, channels 3 (BGR) or 1; T_wc row-major 4x4;
