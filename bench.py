@@ -371,10 +371,12 @@ def run_ours(args, rank, world, local_rank):
         traffic = tj.get(args.workload, {}).get(dom)
     except (OSError, ValueError):
         pass
+    LIMITERS = {"canny": "integer ALU pipe 70 % active, issue slots 73 % busy (ncu, profiles/r1_g_canny_nms_ncu_full.md): not an HBM-bound kernel",
+                "dt": "dependency chain of H row steps per ROI (latency), DRAM traffic below the algorithmic bytes"}
     STAGE_KERNELS = {"dt": "k_dt_bi<N> (one launch per ROI width class)", "canny": "k_canny_nms", "hyst": "k_canny_hyst", "gray": "k_bgr2gray_flat",
                      "sweep": "k_sweep_warp", "fuse": "k_fuse_warp", "lines": "k_roi_lines", "lsd": "line detector kernels"}
     roofline = {"bound": "hbm", "kernel": "%s: %s" % (dom, STAGE_KERNELS.get(dom, dom)), "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
-                "traffic": traffic, "peak_source": peak_src, "alg_bytes_per_launch": dom_bytes,
+                "traffic": traffic, "limiter": LIMITERS.get(dom), "peak_source": peak_src, "alg_bytes_per_launch": dom_bytes,
                 "path": {"alg_bytes_per_step": path_bytes, "achieved": path_bytes / (ms_per_step * 1e-3) / 1e9,
                          "frac": path_bytes / (ms_per_step * 1e-3) / 1e9 / hbm_peak},
                 "stage_ms": stage_acc}
