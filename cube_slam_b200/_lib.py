@@ -57,7 +57,7 @@ _lib = None
 
 EXPORTS = [
     "cs_abi_version", "cs_create", "cs_destroy", "cs_last_error", "cs_default_cuboid_params",
-    "cs_default_line_params", "cs_set_calibration", "cs_cam_pose", "cs_cuboid_measurement", "cs_detect_cuboids", "cs_detect_cuboids_batch",
+    "cs_default_line_params", "cs_set_calibration", "cs_cam_pose", "cs_cuboid_measurement", "cs_cuboid_measurement_orb", "cs_detect_cuboids", "cs_detect_cuboids_batch",
     "cs_batch_upload", "cs_batch_upload_online", "cs_detect_frames_batch", "cs_batch_run", "cs_batch_run_async", "cs_batch_fetch", "cs_batch_stats_get",
     "cs_batch_device_records", "cs_stream", "cs_stage_ms", "cs_set_profiling", "cs_debug_roi",
     "cs_debug_candidates", "cs_detect_lines", "cs_detect_lines_batch", "cs_debug_lsd", "cs_debug_edlines", "cs_debug_stage_offsets", "cs_comm_unique_id", "cs_comm_init",
@@ -88,6 +88,7 @@ def load():
     L.cs_set_calibration.argtypes = [vp, d_p]
     L.cs_cam_pose.argtypes = [d_p, d_p, d_p, d_p]
     L.cs_cuboid_measurement.argtypes = [vp, d_p, d_p, d_p, d_p, d_p, d_p, d_p]
+    L.cs_cuboid_measurement_orb.argtypes = [vp, d_p, C.c_double, d_p, d_p, d_p, d_p]
     L.cs_detect_cuboids.argtypes = [vp, u8_p, i, i, i, i, d_p, d_p, i, d_p, i, C.POINTER(CuboidParams), vp, i32_p]
     L.cs_detect_cuboids_batch.argtypes = [vp, vp, i, i, i, i, i, d_p, d_p, i32_p, d_p, i32_p, C.POINTER(CuboidParams), vp, i32_p]
     L.cs_batch_upload.argtypes = [vp, vp, i, i, i, i, i, d_p, d_p, i32_p, d_p, i32_p, C.POINTER(CuboidParams)]

@@ -722,6 +722,27 @@ int cs_cuboid_measurement(const cs_cuboid_rec *rec, const double cam_t[3], const
     return CS_OK;
 }
 
+int cs_cuboid_measurement_orb(const cs_cuboid_rec *rec, const double T_cam_to_ground[16], double box_confidence, double meas_t[3],
+                              double meas_q_xyzw[4], double meas_scale[3], double *meas_quality)
+{
+    if (!rec || !T_cam_to_ground || !meas_t || !meas_q_xyzw) return CS_ERR_INVALID_ARG;
+    /* Converter::toSE3Quat(cv::Mat 4x4): SE3Quat(R, t) -> Quaterniond(R), normalised */
+    const double R[9] = {T_cam_to_ground[0], T_cam_to_ground[1], T_cam_to_ground[2], T_cam_to_ground[4], T_cam_to_ground[5],
+                         T_cam_to_ground[6], T_cam_to_ground[8], T_cam_to_ground[9], T_cam_to_ground[10]};
+    const double t[3] = {T_cam_to_ground[3], T_cam_to_ground[7], T_cam_to_ground[11]};
+    double q[4];
+    cshost::quat_of_rotation(R, q);
+    cshost::cuboid_measurement(rec->pos, rec->rotY, t, q, nullptr, meas_t, meas_q_xyzw);
+    if (meas_scale) std::memcpy(meas_scale, rec->scale, 3 * sizeof(double));
+    if (meas_quality) { /* Tracking.cc:1680-1687 */
+        const double obj_cam_dist = std::min(std::max(meas_t[2], 10.0), 30.0);
+        double quality = (60.0 - obj_cam_dist) / 40.0;
+        if (box_confidence > 0) quality *= box_confidence;
+        *meas_quality = quality;
+    }
+    return CS_OK;
+}
+
 int cs_batch_upload(cs_ctx *c, const uint8_t *imgs, int n_frames, int width, int height, int stride, int channels, const double *T_wc,
                     const double *boxes, const int32_t *box_offsets, const double *lines, const int32_t *line_offsets,
                     const cs_cuboid_params *params)

@@ -201,6 +201,15 @@ Q quat_from_rot(const double *R)
 }
 }  // namespace
 
+void quat_of_rotation(const double *R, double *q_xyzw)
+{
+    const Q q = quat_from_rot(R);
+    q_xyzw[0] = q.x;
+    q_xyzw[1] = q.y;
+    q_xyzw[2] = q.z;
+    q_xyzw[3] = q.w;
+}
+
 void cuboid_measurement(const double *pos, double rotY, const double *cam_t, const double *cam_q_xyzw, const double *cam_euler_new,
                         double *meas_t, double *meas_q_xyzw)
 {

@@ -134,6 +134,11 @@ int cs_cam_pose(const double K[9], const double T_wc[16], double euler_zyx[3], d
 int cs_cuboid_measurement(const cs_cuboid_rec *rec, const double cam_t[3], const double cam_q_xyzw[4], const double cam_euler_raw[3],
                           double meas_t[3], double meas_q_xyzw[4], double meas_scale[3], double *meas_quality);
 
+/* The same step in orb_object_slam (orb_object_slam/src/Tracking.cc:1636-1647,1680-1687): the camera pose comes as a 4x4 camera-to-ground
+ * matrix (Converter::toSE3Quat), meas_quality = (60 - clamp(z, 10, 30)) / 40, times the 2-D box confidence when that is positive. */
+int cs_cuboid_measurement_orb(const cs_cuboid_rec *rec, const double T_cam_to_ground[16], double box_confidence, double meas_t[3],
+                              double meas_q_xyzw[4], double meas_scale[3], double *meas_quality);
+
 /* ---- cuboid proposals ------------------------------------------------------------------- */
 /* detect_3d_cuboid::detect_cuboid (box_proposal_detail.cpp:56-557; header detect_3d_cuboid.h:62-63)
  * for ONE frame with HOST buffers.  img: H x stride bytes, channels 3 (BGR) or 1; T_wc row-major 4x4;

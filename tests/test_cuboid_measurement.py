@@ -70,6 +70,31 @@ def test_measurement_with_sampled_roll_pitch():
         np.testing.assert_allclose(Rotation.from_quat(q).as_matrix(), R_ref, rtol=0, atol=1e-11)
 
 
+def test_orb_variant_against_scipy():
+    """orb_object_slam/src/Tracking.cc:1636-1647,1680-1687."""
+    from cube_slam_b200 import _lib
+    L = _lib.load()
+    rng = np.random.default_rng(9)
+    for _ in range(100):
+        rec = _record(rng)
+        rec["pos"] = [rng.normal(0, 3), rng.normal(0, 3), rng.uniform(0, 40)]
+        Rc = Rotation.random(random_state=int(rng.integers(1 << 30)))
+        T = np.eye(4)
+        T[:3, :3] = Rc.as_matrix()
+        T[:3, 3] = rng.normal(0, 2, 3)
+        conf = float(rng.choice([0.0, 0.4, 0.9]))
+        t, q, s = np.zeros(3), np.zeros(4), np.zeros(3)
+        qual = C.c_double()
+        assert L.cs_cuboid_measurement_orb(rec.ctypes.data, _lib.ptr(np.ascontiguousarray(T), C.c_double), conf, _lib.ptr(t, C.c_double),
+                                           _lib.ptr(q, C.c_double), _lib.ptr(s, C.c_double), C.byref(qual)) == 0
+        t_ref = Rc.inv().apply(rec["pos"][0] - T[:3, 3])
+        R_ref = (Rc.inv() * Rotation.from_euler("z", float(rec["rotY"][0]))).as_matrix()
+        np.testing.assert_allclose(t, t_ref, rtol=0, atol=1e-11)
+        np.testing.assert_allclose(Rotation.from_quat(q).as_matrix(), R_ref, rtol=0, atol=1e-11)
+        ref_q = (60.0 - min(max(t[2], 10.0), 30.0)) / 40.0 * (conf if conf > 0 else 1.0)
+        assert abs(qual.value - ref_q) < 1e-15
+
+
 def test_python_wrapper_matches():
     import cube_slam_b200 as cs
     rng = np.random.default_rng(8)
