@@ -149,3 +149,45 @@ def test_online_batch_equals_two_calls(det, oracle):
                 assert abs(float(out1[o, k]["normalized_error"]) - float(ref["cuboids"][b][k]["normalized_error"])) < 1e-9
             o += 1
     ctx.close()
+
+
+def test_sequence_against_the_shipped_matlab_cuboids(det, fixture_b):
+    """The CUDA path end to end (cs_detect_lines -> cs_detect_cuboids_batch) against the cuboids the reference's authors ship for this
+    sequence (object_slam/data/detect_cuboids_saved.txt, MATLAB, local ground frame) at the per-frame poses of pop_cam_poses_saved.txt.
+    A soft check (another Canny / DT in MATLAB): same cuboid up to the sampling grid; tests/test_oracle_matlab_crosscheck.py is the CPU twin."""
+    import os
+    import cube_slam_b200 as cs
+    from scipy.spatial.transform import Rotation
+    from conftest import GOLD
+    fb = os.path.join(GOLD, "fixture_b")
+    pop = np.loadtxt(os.path.join(fb, "pop_cam_poses_saved.txt"))
+    sav = np.loadtxt(os.path.join(fb, "detect_cuboids_saved.txt"))
+    ids = [int(r[0]) for r in sav]
+    frames = fixture_b["frames"]
+    imgs = np.stack([frames[i][0] for i in ids])
+    Ts = []
+    for i in ids:
+        T = np.eye(4)
+        T[:3, :3] = Rotation.from_quat(pop[i][4:8]).as_matrix()
+        T[:3, 3] = pop[i][1:4]
+        Ts.append(T)
+    lines = det.detect_filter_lines_batch(imgs)
+    ctx = cs.Context(0, 640, 480, len(ids), 8, 4096)
+    ctx.set_calibration(fixture_b["K"])
+    out, counts = ctx.detect_batch_host(imgs, np.stack(Ts), [frames[i][1] for i in ids], [l.astype(np.float64) for l in lines],
+                                        cs.default_params(nominal_skew_ratio=2.0))
+    assert list(counts) == [1] * len(ids)
+    rows = []
+    for k, row in enumerate(sav):
+        c = out[k, 0]
+        d_pos = float(np.linalg.norm(np.array(c["pos"]) - row[1:4]))
+        d_yaw = (float(c["rotY"]) - row[4] + np.pi / 4) % (np.pi / 2) - np.pi / 4
+        swapped = abs(((float(c["rotY"]) - row[4] + np.pi / 2) % np.pi) - np.pi / 2) > np.pi / 4
+        sc = np.array(c["scale"])[[1, 0, 2]] if swapped else np.array(c["scale"])
+        rows.append((d_pos, abs(d_yaw), float((np.abs(sc - row[5:8]) / row[5:8]).max())))
+    rows = np.array(rows)
+    step = 6.0 / 180 * np.pi
+    assert np.median(rows[:, 0]) < 0.05 and np.median(rows[:, 1]) < 0.02 and np.median(rows[:, 2]) < 0.15
+    good = (rows[:, 0] < 0.15) & (rows[:, 1] < 2.1 * step) & (rows[:, 2] < 0.3)
+    assert good.sum() >= 44, int(good.sum())
+    ctx.close()

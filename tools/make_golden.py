@@ -88,6 +88,10 @@ def main():
         n += 1
     for f in sorted(os.listdir(os.path.join(src, "filter_2d_obj_txts"))):
         shutil.copy(os.path.join(src, "filter_2d_obj_txts", f), os.path.join(fb, "filter_2d_obj_txts"))
+    # the authors' own (MATLAB) cuboids for this sequence and the per-frame local-ground-frame camera poses they go with:
+    # a soft cross-check of the whole path (tests/test_oracle_matlab_crosscheck.py)
+    for f in ("detect_cuboids_saved.txt", "pop_cam_poses_saved.txt"):
+        shutil.copy(os.path.join(src, f), fb)
     poses = np.loadtxt(os.path.join(src, "truth_cam_poses.txt"))
     Tb = quat_pose_to_T(poses[0, 1:8])
     Kb = [[535.4, 0, 320.1], [0, 539.2, 247.6], [0, 0, 1.0]]
