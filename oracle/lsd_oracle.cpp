@@ -9,10 +9,13 @@
  *                                                                 density_th 0.7, n_bins 1024 -- LSDDetector.cpp:173 ignores LSDOptions)
  * including the vendored quirks (rect_nfa's tailp->p.x-for-p.y slip and integer step slopes, lsd.cpp:1057-1065).
  * OpenCV calls inside (GaussianBlur 7x7 sigma 0.6/0.8 on CV_64F, resize INTER_LINEAR x0.8 on CV_64F, fastAtan2, cvtColor) are
- * restated from OpenCV's algorithms and pinned against the in-container cv2 4.13 (tests/test_oracle_lsd.py).
+ * restated from OpenCV's algorithms and pinned against the in-container cv2 4.13 (tests/test_oracle_lines.py).
  * The Gaussian kernel is cv2 4.13's bit-exact getGaussianKernel(7, 0.6 / 0.8) (sigma = 0.7499999999999999, lsd.cpp:453) (it differs from exp()-based kernels in the last ulp).
  *
- * PARITY: "parity unpinned" by the reference (no tests / goldens; cannot be compiled here).
+ * PARITY: "parity unpinned" by the reference (no tests; cannot be compiled here).  Partial golden: 74 of the 271 segments of the one
+ * LSD output the reference ships (detect_3d_cuboid/data/edge_detection/LSD/0000_edge.txt) are reproduced to its six significant digits
+ * (cv2's rewritten LSD reproduces one); the rest differ because that file was not produced from the shipped JPEG bit for bit
+ * (tests/test_oracle_lines.py).
  */
 #include <algorithm>
 #include <cfloat>

@@ -9,7 +9,9 @@
  * PARITY STATUS: "parity unpinned" -- the reference ships no tests / golden outputs for this
  * path and cannot be compiled in this container (needs Eigen, OpenCV C++, ROS).  The
  * third-party OpenCV stages restated here are pinned bit-for-bit against the in-container
- * cv2 4.13 wheel (see tests/test_oracle_cv_parity.py, tools/make_golden.py).
+ * cv2 4.13 wheel (see tests/test_oracle_cv_parity.py, tests/test_oracle_lines.py, tools/make_golden.py).  Soft pins against what
+ * the reference does ship: its LSD segment file (partial golden) and its MATLAB cuboids for the object_slam sequence
+ * (tests/test_oracle_matlab_crosscheck.py).
  */
 #ifndef ORC_API_H
 #define ORC_API_H
