@@ -111,3 +111,22 @@ def test_edlines_segments_are_supported_by_edges(oracle, fixture_a):
     # the length filter is the only difference between the raw and the filtered list
     keep = np.hypot(raw[:, 0] - raw[:, 2], raw[:, 1] - raw[:, 3]) > 50.0
     np.testing.assert_array_equal(raw[keep], L)
+
+
+def test_edlines_segments_lie_on_cv2_canny_edges(oracle, fixture_a, fixture_b):
+    """Third-party sanity for the sequential half of EDLines (no reference output exists): every validated segment follows an edge that
+    cv2's Canny finds in the same blurred image."""
+    cv2 = pytest.importorskip("cv2")
+    n_seg = 0
+    for img in [fixture_a["img"]] + [fixture_b["frames"][i][0] for i in (0, 15, 30, 45)]:
+        L = oracle.edl_detect(img, 30.0)["lines"]
+        g = cv2.GaussianBlur(cv2.cvtColor(img, cv2.COLOR_BGR2GRAY), (5, 5), 1.0)
+        e = cv2.dilate(cv2.Canny(g, 20, 60), np.ones((5, 5), np.uint8)) > 0
+        h, w = e.shape
+        for x1, y1, x2, y2 in L:
+            t = np.linspace(0.03, 0.97, 50)
+            xs = np.clip(np.rint(x1 + t * (x2 - x1)).astype(int), 0, w - 1)
+            ys = np.clip(np.rint(y1 + t * (y2 - y1)).astype(int), 0, h - 1)
+            assert e[ys, xs].mean() >= 0.9
+            n_seg += 1
+    assert n_seg >= 60
