@@ -3,17 +3,19 @@
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload c3|c2|c4|c5]
 
-A "step" is one pass of the hot path (detect_cuboid over every box of every frame) over one batch of
-synthetic frames.  N=1 workload: BASELINE config 3 -- 256 synthetic 640x480 frames, ~3 boxes per frame.
-N>1 (torchrun, one rank per GPU): every rank processes its own shard of that size (weak scaling), then one
-NCCL all-gather of the top-K records.  Prints ONE JSON line on rank 0.
+A "step" is one pass of the north-star path over one batch of synthetic frames: line segments detected on the device
+(line_lbd_detect::detect_filter_lines, LSD flavour -- what object_slam sets, main_obj.cpp:365), then detect_cuboid over
+every box of every frame.  N=1 workload: BASELINE config 3 -- 256 synthetic 640x480 frames, ~3 boxes per frame.
+N>1 (torchrun, one rank per GPU): every rank processes its own shard of that size (weak scaling), then one NCCL all-gather
+of the top-K records.  Prints ONE JSON line on rank 0.
 
-  value     scored (valid) cuboid proposals / s, inputs resident in HBM, CUDA-event timed, max over ranks
-  e2e       the same through cs_detect_cuboids_batch with pinned HOST buffers (H2D + kernels + D2H inside)
-  roofline  dominant kernel: algorithmic bytes / CUDA-event time vs the measured HBM peak
-  cpu_baseline  the CPU oracle (a port of the reference's algorithm) on the host cores, bounded sample
---impl reference times that CPU path alone (the reference itself cannot be compiled here: needs Eigen,
-OpenCV C++ and ROS).
+  value         scored (valid) cuboid proposals / s, frames resident in HBM, CUDA-event timed, max over ranks
+  e2e           the same through cs_detect_frames_batch with pinned HOST buffers (H2D + kernels + D2H inside)
+  roofline      dominant stage: algorithmic bytes / CUDA-event time vs the measured HBM peak
+  cpu_baseline  the CPU oracle (a port of the reference's algorithm) on the host cores, same path, bounded sample
+  lines_given / online_edlines   the same frames with segments handed in (the detect_cuboid entry point) / with EDLines
+--impl reference times the CPU path alone (the reference itself cannot be compiled here: needs Eigen, OpenCV C++ and ROS;
+see DESIGN.md): oracle/batch_oracle.cpp, one frame per loop iteration, static schedule over the host cores.
 """
 import argparse
 import ctypes as C
@@ -37,10 +39,11 @@ WORKLOADS = {
     "c5": (64, 1280, 960, 8, "indoor", False, dict(yaw_step_deg=0.5, top_sample_count_override=30),
            "BASELINE config 5 shard: 64 frames 1280x960, 8 boxes, dense sweep 181 yaw x 30 top-x per GPU"),
 }
+LINE_LENGTH_THRES = 15.0  # object_slam/src/main_obj.cpp:366
 
 # algorithmic bytes per unit of each stage
 STAGE_BYTES = {
-    "lsd": lambda s, shp: shp["frame_px"] * s["n_frames"] * (3 + 8 * 2 + 0.64 * 8 * 4),  # frame in, two f64 blur planes, scaled/modgrad/angle/list
+    "lsd": lambda s, shp: shp["frame_px"] * s["n_frames"] * 3 + 16 * s["n_lines_in"],  # BGR frame read once + float4 per segment written
     "gray": lambda s, shp: shp["frame_px"] * s["n_frames"] * 4,          # 3 B in + 1 B out per pixel
     "canny": lambda s, shp: s["roi_pixels"] * 2,                           # gray ROI read + edge map written
     "hyst": lambda s, shp: s["roi_pixels"] * 1,                            # edge map, in place
@@ -49,6 +52,12 @@ STAGE_BYTES = {
     "sweep": lambda s, shp: s["n_valid"] * 200 + s["n_candidates"] * 1,    # 72 B error row + 128 B corners per scored proposal
     "fuse": lambda s, shp: s["n_valid"] * 16 + s["n_objects"] * 512,
 }
+STAGE_KERNELS = {"dt": "k_dt_bi<N> (one launch per ROI width class)", "canny": "k_canny_nms", "hyst": "k_canny_hyst", "gray": "k_bgr2gray_flat",
+                 "sweep": "k_sweep_warp", "fuse": "k_fuse_warp", "lines": "k_roi_lines",
+                 "lsd": "line detector (k_lsd_hblur/vblur/resize/grad/hist/scan/scatter + k_lsd_grow_par)"}
+LIMITERS = {"lsd": "the seed loop (k_lsd_grow_par) is a dependent chain of L2 / HBM gathers per region pixel: latency-bound, not HBM-bound",
+            "canny": "integer ALU pipe (ncu, profiles/): not an HBM-bound kernel",
+            "dt": "dependency chain of H row steps per ROI (latency), DRAM traffic below the algorithmic bytes"}
 
 
 def path_alg_bytes(stats, shp, topk):
@@ -63,6 +72,27 @@ def measured_peaks():
         d = json.load(open(p))
         return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
     return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def physical_cores():
+    try:
+        import psutil
+        n = psutil.cpu_count(logical=False)
+        if n:
+            return int(n)
+    except Exception:
+        pass
+    return os.cpu_count() or 1
+
+
+def cpu_model():
+    try:
+        for ln in open("/proc/cpuinfo"):
+            if ln.startswith("model name"):
+                return ln.split(":", 1)[1].strip()
+    except OSError:
+        pass
+    return "unknown"
 
 
 class ClockSampler(threading.Thread):
@@ -97,64 +127,72 @@ class ClockSampler(threading.Thread):
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": reasons, "samples": len(self.rows)}
 
 
-def make_workload(name, rank, seed_base=20260922):
+def make_workload(name, rank, seed_base=20260922, frames=None):
     from cube_slam_b200 import synthetic as S
     F, w, h, nb, kind, poisson, over, desc = WORKLOADS[name]
+    if frames:
+        F = frames
     imgs, Ts, boxes, lines, K = S.make_batch(seed_base + 1000 * rank + sum(map(ord, name)), F, w, h, nb, kind=kind, poisson=poisson,
                                              distinct=min(F, 32))
-    return dict(imgs=imgs, Ts=Ts, boxes=boxes, lines=lines, K=K, over=over, desc=desc, w=w, h=h, F=F)
+    return dict(imgs=imgs, Ts=Ts, boxes=boxes, lines=lines, K=K, over=over, desc=desc, w=w, h=h, F=F, name=name)
+
+
+def workload_shape(wl, stats=None):
+    allb = np.concatenate([np.asarray(b).reshape(-1, 5) for b in wl["boxes"]])
+    d = {"mean_box_w": float(allb[:, 2].mean()), "mean_box_h": float(allb[:, 3].mean()), "boxes_per_frame": len(allb) / wl["F"]}
+    if stats:
+        d["segments_per_frame_M"] = stats["n_lines_in"] / max(stats["n_frames"], 1)
+        d["mean_roi_px"] = stats["roi_pixels"] / max(stats["n_roi_jobs"], 1)
+    return d
 
 
 # ------------------------------------------------------------------------------------------- CPU arm
-def cpu_run(wl, frame_ids, n_threads):
-    """The reference's algorithm on the host (oracle port), one frame per task, n_threads workers."""
-    from concurrent.futures import ThreadPoolExecutor
+def cpu_run(wl, n_frames, n_threads, line_mode=1):
+    """The reference's per-frame path on the host (oracle port; oracle/batch_oracle.cpp): detect_filter_lines (LSD) then
+    detect_cuboid, one frame per loop iteration, static schedule over n_threads.  Returns (seconds, valid, candidates, segments)."""
     from oracle import pyoracle as O
     p = O.default_params(**wl["over"])
     O.lib()
-
-    def one(f):
-        r = O.detect_cuboid(wl["imgs"][f], wl["K"], wl["Ts"][f], wl["boxes"][f], wl["lines"][f], p)
-        return r["n_valid"], r["n_candidates"]
-
+    ids = slice(0, n_frames)
     t0 = time.perf_counter()
-    with ThreadPoolExecutor(n_threads) as ex:
-        res = list(ex.map(one, frame_ids))
+    r = O.detect_frames_batch(wl["imgs"][ids], wl["K"], wl["Ts"][ids], wl["boxes"][ids], wl["lines"][ids] if line_mode == 0 else None, p,
+                              line_mode=line_mode, line_length_thres=LINE_LENGTH_THRES, n_threads=n_threads)
     dt = time.perf_counter() - t0
-    return dt, sum(r[0] for r in res), sum(r[1] for r in res)
-
-
-def cpu_sample_size(wl, budget_s, n_threads):
-    dt, _, _ = cpu_run(wl, [0], 1)
-    n = int(max(1, min(wl["F"], budget_s * n_threads / max(dt, 1e-4))))
-    return n
+    return dt, int(r["n_valid"].sum()), int(r["n_cand"].sum()), int(r["n_lines"].sum())
 
 
 def run_reference_arm(args, rank, world):
     if rank != 0:
         return
+    from oracle import pyoracle as O
     wl = make_workload(args.workload, 0)
-    cores = os.cpu_count() or 1
-    n = cpu_sample_size(wl, 4.0, cores)
-    ids = list(range(n))
-    for _ in range(args.warmup):
-        cpu_run(wl, ids[:max(1, n // 4)], cores)
-    tot_t = tot_v = tot_c = 0.0
+    threads = os.cpu_count() or 1
+    phys = physical_cores()
+    dt1, _, _, _ = cpu_run(wl, min(wl["F"], 2), 1)
+    per_frame = dt1 / min(wl["F"], 2)
+    n = int(max(1, min(wl["F"], 4.0 * phys / max(per_frame, 1e-4))))  # about 4 s of wall clock per step at most
+    for _ in range(max(1, min(args.warmup, 2))):
+        cpu_run(wl, max(1, n // 4), threads)
+    tot_t = tot_v = tot_c = tot_l = 0.0
     for _ in range(args.steps):
-        dt, v, c = cpu_run(wl, ids, cores)
+        dt, v, c, l = cpu_run(wl, n, threads)
         tot_t += dt
         tot_v += v
         tot_c += c
+        tot_l += l
     val = tot_v / tot_t
     fps = n * args.steps / tot_t
     line = {
         "impl": "reference", "metric": "scored cuboid proposals/s", "value": val, "unit": "proposals/s", "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * tot_t / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic", "frames_per_s": fps, "candidates_per_s": tot_c / tot_t,
-        "config": {"workload": wl["desc"], "sample_frames_per_step": n, "note": "CPU oracle port of the reference algorithm; the reference "
-                   "itself needs Eigen/OpenCV C++/ROS and cannot be compiled on this image"},
-        "cpu_baseline": {"value": val, "unit": "proposals/s", "cores": cores, "kind": "port",
-                         "sample": "%d of %d frames per step, one frame per thread task, %d threads" % (n, wl["F"], cores)},
+        "config": {"workload": wl["desc"], "lines": "detected per frame by the LSD flavour of line_lbd (the north-star path)",
+                   "sample_frames_per_step": n, "segments_per_frame_M": tot_l / (n * args.steps),
+                   "note": "CPU oracle port of the reference algorithm (the reference itself needs Eigen/OpenCV C++/ROS and cannot be "
+                           "compiled on this image); oracle/batch_oracle.cpp, one frame per loop iteration, static schedule, openmp=%d" % O.lib().orc_has_openmp()},
+        "cpu_baseline": {"value": val, "unit": "proposals/s", "cores": threads, "physical_cores": phys, "cpu": cpu_model(), "kind": "port",
+                         "one_core_frames_per_s": 1.0 / per_frame,
+                         "sample": "%d of %d frames per step, line detection + detect_cuboid per frame, %d threads" % (n, wl["F"], threads)},
         "e2e": {"value": val, "unit": "proposals/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -162,6 +200,21 @@ def run_reference_arm(args, rank, world):
 
 
 # ------------------------------------------------------------------------------------------- GPU arm
+class Mode(object):
+    """One way of feeding the same frames through the path on a set of contexts driven round-robin."""
+
+    def __init__(self, name, ctxs, streams, wl, params, line_params=None):
+        self.name, self.ctxs, self.streams, self.wl, self.params, self.lp = name, ctxs, streams, wl, params, line_params
+
+    def upload(self, which=None):
+        wl = self.wl
+        for cx in (self.ctxs if which is None else which):
+            if self.lp is None:
+                cx.upload(wl["imgs"], wl["Ts"], wl["boxes"], wl["lines"], self.params)
+            else:
+                cx.upload_online(wl["imgs"], wl["Ts"], wl["boxes"], self.lp, self.params)
+
+
 def run_ours(args, rank, world, local_rank):
     import torch
     import cube_slam_b200 as cs
@@ -172,15 +225,26 @@ def run_ours(args, rank, world, local_rank):
         torch.cuda.set_device(local_rank)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
     wl = make_workload(args.workload, rank)
     F, w, h = wl["F"], wl["w"], wl["h"]
     params = cs.default_params(**wl["over"])
     topk = int(params.max_cuboid_num)
-    ctx = cs.Context(local_rank, w, h, F, 16, 8192)
-    ctx.set_calibration(wl["K"])
-    stream = torch.cuda.ExternalStream(ctx.stream(), device=torch.device("cuda", local_rank))
+    n_ctx = max(args.inflight, 1)
+    ctxs = []
+    for _ in range(n_ctx):
+        cx = cs.Context(local_rank, w, h, F, 16, 8192)
+        cx.set_calibration(wl["K"])
+        ctxs.append(cx)
+    ctx = ctxs[0]
+    streams = [torch.cuda.ExternalStream(cx.stream(), device=dev) for cx in ctxs]
+    dbg_flags = (16 if args.no_prio else 0) | (32 if args.raster_dt else 0) | (128 if args.seq_lines else 0)
 
-    recs_per_rank = 0
+    def line_params(use_lsd):
+        det = cs.line_lbd_detect(context=ctx)
+        det.use_LSD = use_lsd
+        det.line_length_thres = LINE_LENGTH_THRES
+        return det.params()
 
     def barrier():
         if world > 1:
@@ -188,19 +252,7 @@ def run_ours(args, rank, world, local_rank):
         torch.cuda.synchronize()
 
     gathered = C.c_void_p()
-
-    # ---- resident-input throughput ("value").  `--inflight` contexts hold the same batch and are driven round-robin, so
-    # the latency-bound kernels of one batch (distance transform, hysteresis, selection: one warp / CTA per ROI) overlap
-    # the issue-bound kernels of the next; every timed step is still one full pass over one batch of F frames.
-    ctxs, streams = [ctx], [stream]
-    for _ in range(max(args.inflight, 1) - 1):
-        c2 = cs.Context(local_rank, w, h, F, 16, 8192)
-        c2.set_calibration(wl["K"])
-        ctxs.append(c2)
-        streams.append(torch.cuda.ExternalStream(c2.stream(), device=torch.device("cuda", local_rank)))
-    for cx in ctxs:
-        cx.upload(wl["imgs"], wl["Ts"], wl["boxes"], wl["lines"], params)
-    # NCCL communicators owned by the library, one per context (the top-K all-gather is issued on that context's stream)
+    recs_per_rank = 0
     if world > 1:
         nccl_path = None
         for d in sys.path:
@@ -219,44 +271,59 @@ def run_ours(args, rank, world, local_rank):
         n_obj = torch.tensor([sum(len(b) for b in wl["boxes"])], device="cuda")
         dist.all_reduce(n_obj, op=dist.ReduceOp.MAX)
         recs_per_rank = int(n_obj.item()) * topk
-    dbg_flags = (16 if args.no_prio else 0) | (32 if args.raster_dt else 0)
-    for cx in ctxs:
-        cx.set_profiling(dbg_flags)
 
-    def step_i(i):
-        cx = ctxs[i % len(ctxs)]
-        cx.run_async()
-        if world > 1:
-            cx.check(cx.L.cs_allgather_topk(cx.h, recs_per_rank, C.byref(gathered)))
+    def timed(mode, steps, warm, with_gather):
+        """warm-up, then `steps` steps round-robin over the contexts; device time (ms, this rank) and the batch statistics."""
+        mode.upload()
+        for cx in ctxs:
+            cx.set_profiling(dbg_flags)
 
-    for i in range(max(args.warmup, 3) * len(ctxs)):
-        step_i(i)
-    torch.cuda.synchronize()
-    stats = ctx.stats()
+        def step_i(i):
+            cx = ctxs[i % len(ctxs)]
+            cx.run_async()
+            if with_gather:
+                cx.check(cx.L.cs_allgather_topk(cx.h, recs_per_rank, C.byref(gathered)))
+
+        for i in range(max(warm, 3) * len(ctxs)):
+            step_i(i)
+        torch.cuda.synchronize()
+        st = ctx.stats()
+        ev0 = torch.cuda.Event(enable_timing=True)
+        ev_end = [torch.cuda.Event(enable_timing=True) for _ in ctxs]
+        barrier()
+        ev0.record(streams[0])
+        for s_ in streams[1:]:
+            s_.wait_event(ev0)
+        for i in range(steps):
+            step_i(i)
+        for e, s_ in zip(ev_end, streams):
+            e.record(s_)
+        barrier()
+        ms = max(ev0.elapsed_time(e) for e in ev_end)
+        # one more step alone, profiled: latency of a batch and its stage times
+        ctx.set_profiling(1 | dbg_flags)
+        ctx.run()
+        stage = ctx.stage_ms()
+        ctx.set_profiling(dbg_flags)
+        return ms, st, stage
+
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
-    ev0 = torch.cuda.Event(enable_timing=True)
-    ev_end = [torch.cuda.Event(enable_timing=True) for _ in ctxs]
-    stage_acc = {}
-    barrier()
-    ev0.record(streams[0])
-    for st_ in streams[1:]:
-        st_.wait_event(ev0)
-    for i in range(args.steps):
-        step_i(i)
-    for e, st_ in zip(ev_end, streams):
-        e.record(st_)
-    barrier()
-    ms_total = max(ev0.elapsed_time(e) for e in ev_end)
-    # per-stage CUDA-event times of one more (profiled, alone) step
-    ctx.set_profiling(1 | dbg_flags)
-    ctx.run()
-    stage_acc = ctx.stage_ms()
+    main_mode = Mode("online_lsd", ctxs, streams, wl, params, line_params(True))
+    ms_total, stats, stage_acc = timed(main_mode, args.steps, args.warmup, world > 1)
     sampler.stop_flag = True
+    my_ms = ms_total
     ms_t = torch.tensor([ms_total], device="cuda", dtype=torch.float64)
     cnt = torch.tensor([stats["n_valid"], stats["n_candidates"], stats["n_frames"], stats["n_objects"]], device="cuda", dtype=torch.float64)
+    per_rank = None
     if world > 1:
+        allms = [torch.zeros_like(ms_t) for _ in range(world)]
+        dist.all_gather(allms, ms_t)
+        allcnt = [torch.zeros_like(cnt) for _ in range(world)]
+        dist.all_gather(allcnt, cnt)
+        per_rank = {"ms_per_step": [float(x.item()) / args.steps for x in allms], "boxes": [float(x[3].item()) for x in allcnt],
+                    "valid": [float(x[0].item()) for x in allcnt]}
         dist.all_reduce(ms_t, op=dist.ReduceOp.MAX)
         dist.all_reduce(cnt, op=dist.ReduceOp.SUM)
     ms_total = float(ms_t.item())
@@ -264,63 +331,33 @@ def run_ours(args, rank, world, local_rank):
     ms_per_step = ms_total / args.steps
     value = n_valid_all / (ms_per_step * 1e-3)
 
-    # ---- online mode (object_slam main_obj.cpp:424-450): lines detected on the resident frames by the LSD kernels, N = 1 only
-    online = None
-    if world == 1 and not args.no_online:
-        online = {}
-        for flavour, use_lsd in (("lsd", True), ("edlines", False)):
-            det = cs.line_lbd_detect(context=ctx)
-            det.use_LSD = use_lsd            # object_slam sets true (main_obj.cpp:365); the class default is EDLines (line_lbd_allclass.cpp:121)
-            det.line_length_thres = 15
-            lp = det.params()
-            # one batch alone, profiled: latency of a batch and its stage times
-            ctx.set_profiling(1 | dbg_flags)
-            ctx.upload_online(wl["imgs"], wl["Ts"], wl["boxes"], lp, params)
-            for _ in range(2):
-                ctx.run()
-            st_on = ctx.stats()
-            stage_on = ctx.stage_ms()
-            # throughput: the same `--inflight` contexts as above, round-robin (the sequential half of a detector is one warp per frame)
-            for cx in ctxs[1:]:
-                cx.upload_online(wl["imgs"], wl["Ts"], wl["boxes"], lp, params)
-            for cx in ctxs:
-                cx.set_profiling(dbg_flags)
-                cx.run_async()
-            torch.cuda.synchronize()
-            n_on = 2 * len(ctxs)
-            o0 = torch.cuda.Event(enable_timing=True)
-            o_end = [torch.cuda.Event(enable_timing=True) for _ in ctxs]
-            o0.record(streams[0])
-            for st_ in streams[1:]:
-                st_.wait_event(o0)
-            for i in range(n_on):
-                ctxs[i % len(ctxs)].run_async()
-            for e, st_ in zip(o_end, streams):
-                e.record(st_)
-            torch.cuda.synchronize()
-            on_ms = max(o0.elapsed_time(e) for e in o_end) / n_on
-            online[flavour] = {"workload": "same frames, lines from cs_detect_lines (%s, length > 15) on the device" % flavour, "ms_per_step": on_ms,
-                               "frames_per_s": F / (on_ms * 1e-3), "value": st_on["n_valid"] / (on_ms * 1e-3), "unit": "proposals/s",
-                               "n_valid": st_on["n_valid"], "batches_in_flight": len(ctxs), "one_batch_alone_ms": stage_on.get("total"),
-                               "stage_ms": stage_on}
-        online["note"] = "the sequential half of either detector (LSD seed loop / EDLines routing + fitting) is one warp per frame; at 256 frames it is latency-bound"
-        for cx in ctxs:
-            cx.upload(wl["imgs"], wl["Ts"], wl["boxes"], wl["lines"], params)
+    # ---- the same frames, other entry points (N = 1 only): segments handed in; EDLines instead of LSD
+    extra = {}
+    if world == 1 and not args.no_extra:
+        sub_steps = max(20, min(args.steps, 200))
+        for name, mode in (("lines_given", Mode("lines_given", ctxs, streams, wl, params, None)),
+                           ("online_edlines", Mode("online_edlines", ctxs, streams, wl, params, line_params(False)))):
+            ms_x, st_x, stage_x = timed(mode, sub_steps, 3, False)
+            extra[name] = {"ms_per_step": ms_x / sub_steps, "value": st_x["n_valid"] / (ms_x / sub_steps * 1e-3), "unit": "proposals/s",
+                           "frames_per_s": F / (ms_x / sub_steps * 1e-3), "n_valid": st_x["n_valid"], "segments_per_frame_M": st_x["n_lines_in"] / F,
+                           "one_batch_alone_ms": stage_x.get("total"), "stage_ms": stage_x}
+        extra["lines_given"]["workload"] = "segments given as input (the detect_cuboid entry point; how orb_object_slam feeds it, Tracking.cc:1583-1590)"
+        extra["online_edlines"]["workload"] = "lines from the EDLines flavour (use_LSD = false, the class default), length > 15"
+        main_mode.upload()
 
-    # ---- end to end through the host-buffer ABI call ("e2e")
+    # ---- end to end through the host-buffer ABI call ("e2e"): cs_detect_frames_batch, pinned host frames
     pinned = torch.from_numpy(wl["imgs"]).pin_memory()
     imgs_pinned = pinned.numpy()
-    out = np.zeros((max(int(stats["n_objects"]), 1), topk), cs.CUBOID_DTYPE)
-    counts = np.zeros(max(int(stats["n_objects"]), 1), np.int32)
-
+    n_obj_loc = max(int(stats["n_objects"]), 1)
     # two host threads, one context each, call the synchronous ABI entry point: the copies of one batch overlap the kernels of the other
     # (single GPU only: two threads issuing NCCL calls on two communicators in an unordered way could deadlock across ranks)
     e2e_ctxs = ctxs[:2] if (len(ctxs) >= 2 and world == 1) else ctxs[:1]
-    e2e_out = [(out, counts)] + [(np.zeros_like(out), np.zeros_like(counts)) for _ in e2e_ctxs[1:]]
+    e2e_out = [(np.zeros((n_obj_loc, topk), cs.CUBOID_DTYPE), np.zeros(n_obj_loc, np.int32)) for _ in e2e_ctxs]
+    lp_main = main_mode.lp
 
     def step_e2e(k=0):
         cx = e2e_ctxs[k]
-        cx.detect_batch_host(imgs_pinned, wl["Ts"], wl["boxes"], wl["lines"], params, e2e_out[k][0], e2e_out[k][1])
+        cx.detect_frames_host(imgs_pinned, wl["Ts"], wl["boxes"], lp_main, params, e2e_out[k][0], e2e_out[k][1])
         if world > 1:
             cx.check(cx.L.cs_allgather_topk(cx.h, recs_per_rank, C.byref(C.c_void_p())))
 
@@ -330,7 +367,6 @@ def run_ours(args, rank, world, local_rank):
     barrier()
     e2e_steps = max(4, min(args.steps, 50))
     e2e_steps -= e2e_steps % len(e2e_ctxs)
-    import threading
 
     def e2e_worker(k):
         torch.cuda.set_device(local_rank)
@@ -349,62 +385,69 @@ def run_ours(args, rank, world, local_rank):
     if world > 1:
         dist.all_reduce(e2e_t, op=dist.ReduceOp.MAX)
     e2e_ms_step = float(e2e_t.item()) / e2e_steps
-    h2d = wl["imgs"].nbytes + sum(l.nbytes for l in wl["lines"]) + wl["Ts"].nbytes + sum(b.nbytes for b in wl["boxes"])
-    d2h = out.nbytes + counts.nbytes
+    h2d = wl["imgs"].nbytes + wl["Ts"].nbytes + sum(np.asarray(b).nbytes for b in wl["boxes"])
+    d2h = e2e_out[0][0].nbytes + e2e_out[0][1].nbytes
 
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
         return
 
-    # ---- roofline of the dominant kernel
+    # ---- roofline of the dominant stage
     hbm_peak, peak_src = measured_peaks()
     shp = {"frame_px": w * h}
-    kernel_ms = {k: v for k, v in stage_acc.items() if k not in ("total", "lsd")}
+    kernel_ms = {k: v for k, v in stage_acc.items() if k != "total"}
     dom = max(kernel_ms, key=kernel_ms.get)
     dom_bytes = float(STAGE_BYTES[dom](stats, shp))
     achieved = dom_bytes / (kernel_ms[dom] * 1e-3) / 1e9 if kernel_ms[dom] > 0 else 0.0
     path_bytes = float(path_alg_bytes(stats, shp, topk))
     traffic = None  # DRAM bytes of the stage's kernels per launch, from the committed ncu capture of this workload (profiles/)
     try:
-        tj = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "r1_traffic.json")))
+        tj = json.load(open(os.path.join(ROOT, "profiles", "r2_traffic.json")))
         traffic = tj.get(args.workload, {}).get(dom)
     except (OSError, ValueError):
         pass
-    LIMITERS = {"canny": "integer ALU pipe 70 % active, issue slots 73 % busy (ncu, profiles/r1_g_canny_nms_ncu_full.md): not an HBM-bound kernel",
-                "dt": "dependency chain of H row steps per ROI (latency), DRAM traffic below the algorithmic bytes"}
-    STAGE_KERNELS = {"dt": "k_dt_bi<N> (one launch per ROI width class)", "canny": "k_canny_nms", "hyst": "k_canny_hyst", "gray": "k_bgr2gray_flat",
-                     "sweep": "k_sweep_warp", "fuse": "k_fuse_warp", "lines": "k_roi_lines", "lsd": "line detector kernels"}
     roofline = {"bound": "hbm", "kernel": "%s: %s" % (dom, STAGE_KERNELS.get(dom, dom)), "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
                 "traffic": traffic, "limiter": LIMITERS.get(dom), "peak_source": peak_src, "alg_bytes_per_launch": dom_bytes,
                 "path": {"alg_bytes_per_step": path_bytes, "achieved": path_bytes / (ms_per_step * 1e-3) / 1e9,
                          "frac": path_bytes / (ms_per_step * 1e-3) / 1e9 / hbm_peak},
-                "stage_ms": stage_acc}
+                "stage_ms": stage_acc,
+                "stage_gbs": {k: float(STAGE_BYTES[k](stats, shp)) / (v * 1e-3) / 1e9 for k, v in kernel_ms.items() if v > 0}}
 
-    # ---- CPU baseline (rank 0, N=1 only), bounded sample
+    # ---- CPU baseline (rank 0, N=1 only), bounded sample of the same workload, same path (line detection + detect_cuboid)
     cpu = None
     if world == 1 and not args.no_cpu:
-        cores = os.cpu_count() or 1
-        n = cpu_sample_size(wl, 3.0, cores)
-        dt, v, c = cpu_run(wl, list(range(n)), cores)
-        dt1, v1, _ = cpu_run(wl, list(range(min(n, 8))), 1)
-        cpu = {"value": v / dt, "unit": "proposals/s", "cores": cores, "kind": "port", "frames_per_s": n / dt,
-               "one_core_value": v1 / dt1, "sample": "%d of %d frames of this workload, one frame per task, %d threads" % (n, F, cores)}
+        from oracle import pyoracle as O
+        threads, phys = os.cpu_count() or 1, physical_cores()
+        dt1, v1, _, _ = cpu_run(wl, min(F, 2), 1)
+        per_frame = dt1 / min(F, 2)
+        n = int(max(1, min(F, 10.0 * phys / max(per_frame, 1e-4))))
+        cpu_run(wl, max(1, n // 8), threads)
+        dt, v, c, l = cpu_run(wl, n, threads)
+        dtp, vp, _, _ = cpu_run(wl, n, phys) if phys != threads else (dt, v, c, l)
+        cpu = {"value": v / dt, "unit": "proposals/s", "cores": threads, "physical_cores": phys, "cpu": cpu_model(), "kind": "port",
+               "frames_per_s": n / dt, "one_core_value": v1 / dt1, "one_core_frames_per_s": 1.0 / per_frame,
+               "physical_cores_value": vp / dtp, "scaling_vs_one_core": (v / dt) / (v1 / dt1), "openmp": int(O.lib().orc_has_openmp()),
+               "sample": "%d of %d frames of this workload, LSD line detection + detect_cuboid per frame, static schedule, %d threads" % (n, F, threads)}
 
     line = {
         "metric": "scored cuboid proposals/s", "value": value, "unit": "proposals/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
         "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "frames_per_s": n_frames_all / (ms_per_step * 1e-3), "candidates_per_s": n_cand_all / (ms_per_step * 1e-3),
-        "config": {"workload": wl["desc"], "frames_per_gpu": F, "boxes_total": n_obj_all, "valid_fraction": n_valid_all / max(n_cand_all, 1),
-                   "lines": "synthetic segments given as input (detect_cuboid entry point)", "l2": "inputs larger than L2 (%.0f MB of frames per GPU)" % (wl["imgs"].nbytes / 1e6),
-                   "parallelism": "frames sharded x%d, one NCCL all-gather of top-K" % world if world > 1 else "single GPU",
-                   "batches_in_flight": len(ctxs)},
+        "config": dict({"workload": wl["desc"], "frames_per_gpu": F, "boxes_total": n_obj_all, "valid_fraction": n_valid_all / max(n_cand_all, 1),
+                        "lines": "detected on the device from the resident frames: line_lbd_detect::detect_filter_lines, LSD flavour, length > 15 (stage (i) of the north star)",
+                        "l2": "inputs larger than L2 (%.0f MB of frames per GPU)" % (wl["imgs"].nbytes / 1e6),
+                        "parallelism": "frames sharded x%d, one NCCL all-gather of top-K" % world if world > 1 else "single GPU",
+                        "batches_in_flight": len(ctxs), "one_batch_alone_ms": stage_acc.get("total")}, **workload_shape(wl, stats)),
         "e2e": {"value": n_valid_all / (e2e_ms_step * 1e-3), "unit": "proposals/s", "frames_per_s": n_frames_all / (e2e_ms_step * 1e-3),
                 "ms_per_step": e2e_ms_step, "steps": e2e_steps, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-                "host_threads": len(e2e_ctxs), "timer": "wall clock around all calls (cs_detect_cuboids_batch is synchronous)"},
+                "host_threads": len(e2e_ctxs), "timer": "wall clock around all calls (cs_detect_frames_batch is synchronous)"},
         "gpu_launches": int(stats["n_kernel_launches"]) * args.steps,
-        "roofline": roofline, "cpu_baseline": cpu, "online": online, "clocks": sampler.summary(),
+        "roofline": roofline, "cpu_baseline": cpu, "clocks": sampler.summary(),
     }
+    line.update(extra)
+    if per_rank:
+        line["per_rank"] = per_rank
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
@@ -418,13 +461,14 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="c3", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu", action="store_true")
-    ap.add_argument("--no-online", action="store_true")
+    ap.add_argument("--no-extra", action="store_true", help="skip the lines-given / EDLines variants of the same frames")
     ap.add_argument("--no-prio", action="store_true", help="A/B: keep each batch's whole chain on one stream (no high-priority tail)")
     ap.add_argument("--raster-dt", action="store_true", help="A/B: two-pass raster-scan distance transform kernel instead of the cone form")
+    ap.add_argument("--seq-lines", action="store_true", help="A/B: the line detectors' sequential kernels (one warp per frame) instead of ordered speculation")
     ap.add_argument("--inflight", type=int, default=4, help="batches in flight on one GPU (contexts driven round-robin)")
     args = ap.parse_args()
     if args.steps is None:
-        args.steps = 1000 if args.impl == "ours" else 5
+        args.steps = 300 if args.impl == "ours" else 3
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))

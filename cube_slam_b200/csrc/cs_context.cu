@@ -75,12 +75,13 @@ struct cs_ctx {
     cudaStream_t stream_hi = nullptr;
     cudaEvent_t ev_mid = nullptr, ev_done = nullptr, ev_dt_fork = nullptr, ev_dt_join = nullptr;
     int use_prio = 1;
+    int seq_lines = 0;     /* A/B: the plain one-warp-per-frame sequential halves of the line detectors */
 
     /* device buffers (grow only) */
     DevBuf d_img, d_gray, d_lines, d_frames, d_poses, d_yaws, d_jobs, d_objs, d_blocks, d_blocks4, d_dtids, d_tilejob;
     DevBuf d_bits, d_dist, d_mlines, d_lcounts, d_err;
     DevBuf d_cvalid, d_cdist, d_cangle, d_cskew, d_vlist, d_key, d_idx, d_flag, d_keep, d_norm, d_score, d_jcounts;
-    DevBuf d_out, d_outcnt, d_gather;
+    DevBuf d_out, d_outcnt, d_gather, d_send;
     void *pinned = nullptr;
     size_t pinned_cap = 0;
 
@@ -109,6 +110,7 @@ struct cs_ctx {
 cudaStream_t cs_ctx_stream(cs_ctx *c) { return c->stream; }
 int cs_ctx_device(cs_ctx *c) { return c->device; }
 void **cs_ctx_lsd_slot(cs_ctx *c) { return &c->lsd_state; }
+int cs_ctx_seq_lines(cs_ctx *c) { return c->seq_lines; }
 void **cs_ctx_edl_slot(cs_ctx *c) { return &c->edl_state; }
 void cs_ctx_count_launches(cs_ctx *c, int64_t n) { c->line_launches += n; }
 int cs_ctx_fail(cs_ctx *c, int code, const char *fmt, ...)
@@ -400,6 +402,8 @@ int run_batch(cs_ctx *c, bool sync)
     CS_CUDA(c, cudaMemsetAsync(c->d_err.p, 0, 16, st));
 
     const int n_jobs = (int)c->jobs.size(), n_objs = (int)c->objs.size();
+    /* record slots past a box's count must read valid = 0 on the device too (the all-gather ships the whole buffer) */
+    if (n_objs > 0) CS_CUDA(c, cudaMemsetAsync(c->d_out.p, 0, (size_t)n_objs * c->topk * sizeof(cs_cuboid_rec), st));
     const uint8_t *gray = (const uint8_t *)c->d_gray.p;
     auto mark = [&](int s) {
         if (c->profiling) cudaEventRecord(c->ev[s], st);
@@ -512,6 +516,8 @@ int store_batch(cs_ctx *c, const uint8_t *imgs, int n_frames, int width, int hei
     if (params->max_cuboid_num < 1 || params->max_cuboid_num > CS_MAX_TOPK)
         return fail(c, CS_ERR_CAPACITY, "max_cuboid_num must be in [1,%d]", CS_MAX_TOPK);
     if (width > c->max_w || height > c->max_h || n_frames > c->max_frames) return fail(c, CS_ERR_CAPACITY, "batch exceeds cs_create capacities");
+    if (box_offsets[0] != 0 || line_offsets[0] != 0) /* records, counts and jobs are indexed from 0: a CSR slice must be rebased by the caller */
+        return fail(c, CS_ERR_INVALID_ARG, "box_offsets[0] and line_offsets[0] must be 0");
     for (int f = 0; f < n_frames; f++) {
         if (box_offsets[f + 1] < box_offsets[f] || line_offsets[f + 1] < line_offsets[f]) return fail(c, CS_ERR_INVALID_ARG, "offsets must be non-decreasing");
         if (box_offsets[f + 1] - box_offsets[f] > c->max_boxes) return fail(c, CS_ERR_CAPACITY, "frame %d: more than %d boxes", f, c->max_boxes);
@@ -662,7 +668,7 @@ void cs_destroy(cs_ctx *c)
     DevBuf *all[] = {&c->d_img,   &c->d_gray,  &c->d_lines,  &c->d_frames, &c->d_poses,   &c->d_yaws, &c->d_jobs, &c->d_objs,
                      &c->d_blocks, &c->d_blocks4, &c->d_dtids, &c->d_tilejob, &c->d_bits, &c->d_dist, &c->d_mlines, &c->d_lcounts, &c->d_err,
                      &c->d_cvalid, &c->d_cdist, &c->d_cangle, &c->d_cskew, &c->d_vlist,  &c->d_key,     &c->d_idx,  &c->d_flag, &c->d_keep,  &c->d_norm,
-                     &c->d_score,  &c->d_jcounts, &c->d_out,  &c->d_outcnt, &c->d_gather};
+                     &c->d_score,  &c->d_jcounts, &c->d_out,  &c->d_outcnt, &c->d_gather, &c->d_send};
     for (DevBuf *b : all)
         if (b->p) cudaFree(b->p);
     if (c->pinned) cudaFreeHost(c->pinned);
@@ -866,6 +872,7 @@ int cs_set_profiling(cs_ctx *c, int enable)
     c->use_fused_dt = (enable & 4) != 0; /* bit 2: experimental fused hysteresis + wavefront-DT kernel */
     c->use_raster_dt = ((enable & 32) ? 1 : 0) | ((enable & 64) ? 2 : 0); /* bit 5: raster-scan distance transform kernel; bit 6: cone form, bits from global */
     c->use_prio = (enable & 16) == 0;      /* bit 4: keep the whole chain on one stream (no high-priority tail) */
+    c->seq_lines = (enable & 128) != 0;    /* bit 7: sequential seed loop / routing of the line detectors (A/B reference of the speculative kernels) */
     c->use_cta_select = (enable & 8) != 0; /* bit 3: CTA-wide sweep / selection kernels (the general path) instead of the warp ones */
     return CS_OK;
 }

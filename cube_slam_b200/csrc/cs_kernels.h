@@ -11,15 +11,37 @@
  * L1 / shared split when it is idle.  Default 75 (% shared); -1 leaves the driver's per-kernel choice (CS_SMEM_CARVEOUT in the environment overrides;
  * it is a preference: a kernel that needs more shared memory still gets it). */
 int cs_carveout_pref(void);
-#define CS_APPLY_CARVEOUT(kernel)                                                                            \
-    do {                                                                                                     \
-        static bool cv_done_ = false;                                                                        \
-        if (!cv_done_) {                                                                                     \
-            const int cv_ = cs_carveout_pref();                                                              \
-            if (cv_ >= 0) cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cv_); \
-            cv_done_ = true;                                                                                 \
-        }                                                                                                    \
+/* Function attributes are per device: `cs_first_on_device(flags)` is true the first time it runs on the current device (the flag word is
+ * a bit per device ordinal, updated atomically: contexts on several devices / host threads may launch the same kernel). */
+#include <atomic>
+static inline bool cs_first_on_device(std::atomic<unsigned long long> &flags)
+{
+    int dev = 0;
+    cudaGetDevice(&dev);
+    const unsigned long long bit = 1ull << (dev & 63);
+    return (flags.fetch_or(bit) & bit) == 0;
+}
+#define CS_ONCE_PER_DEVICE(...)                                    \
+    do {                                                           \
+        static std::atomic<unsigned long long> once_flags_{0};     \
+        if (cs_first_on_device(once_flags_)) {                     \
+            __VA_ARGS__;                                           \
+        }                                                          \
     } while (0)
+/* let a kernel use as much dynamic shared memory as the device offers beyond its static allocation (the opt-in limit, 227 KB on sm_100) */
+template <typename K>
+static inline void cs_allow_max_dynamic_smem(K kernel)
+{
+    cudaFuncAttributes a;
+    int dev = 0, optin = 0;
+    if (cudaFuncGetAttributes(&a, kernel) != cudaSuccess || cudaGetDevice(&dev) != cudaSuccess ||
+        cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev) != cudaSuccess)
+        return;
+    cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, optin - (int)a.sharedSizeBytes);
+}
+#define CS_APPLY_CARVEOUT(kernel)                                                                                                     \
+    CS_ONCE_PER_DEVICE(const int cv_ = cs_carveout_pref();                                                                            \
+                       if (cv_ >= 0) cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cv_))
 
 #define CS_DT_CLASSES 7
 extern const int cs_dt_class_width[CS_DT_CLASSES];

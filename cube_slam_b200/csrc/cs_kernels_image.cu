@@ -1076,15 +1076,11 @@ void cs_launch_canny(const uint8_t *d_gray, int img_w, int img_h, const CsJob *d
 void cs_launch_hyst(const CsJob *d_jobs, int n_jobs, uint32_t *d_bits, int max_plane_words, cudaStream_t st, int64_t *launches)
 {
     if (n_jobs <= 0) return;
-    static int cur_attr = 0;
     int smem_words = 2 * max_plane_words;
     const int cap_words = (200 * 1024) / 4;
     if (smem_words > cap_words) smem_words = cap_words;
     const int bytes = smem_words * 4;
-    if (bytes > cur_attr) {
-        cudaFuncSetAttribute(k_canny_hyst, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
-        cur_attr = bytes;
-    }
+    CS_ONCE_PER_DEVICE(cs_allow_max_dynamic_smem(k_canny_hyst));
     CS_APPLY_CARVEOUT(k_canny_hyst);
     k_canny_hyst<<<n_jobs, HY_THREADS, bytes, st>>>(d_jobs, d_bits, smem_words);
     (*launches)++;
@@ -1098,14 +1094,10 @@ template <int NCH>
 static void dt_launch_class(const CsJob *d_jobs, const int32_t *d_ids, int count, int width, int plane_words, const uint32_t *d_bits, float *d_dist,
                             cudaStream_t st, int64_t *launches)
 {
-    static int attr = 0;
     int pw = plane_words;
     if (pw > (96 * 1024) / 4 || pw < 0) pw = 0; /* huge ROIs (or the debug switch): the sweeps read the bits from global memory */
     const int bytes = (2 * DT_NC * width + pw) * 4;
-    if (bytes > attr && bytes > 48 * 1024) {
-        cudaFuncSetAttribute(k_dt_bi<NCH>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
-        attr = bytes;
-    }
+    CS_ONCE_PER_DEVICE(cs_allow_max_dynamic_smem(k_dt_bi<NCH>));
     CS_APPLY_CARVEOUT(k_dt_bi<NCH>);
     k_dt_bi<NCH><<<count, 32 * (2 + 2 * DT_NC), bytes, st>>>(d_jobs, d_ids, d_bits, d_dist, pw, width);
     (*launches)++;
@@ -1117,12 +1109,8 @@ void cs_launch_dt(const CsJob *d_jobs, const int32_t *d_ids, int n_jobs, int max
 {
     if (n_jobs <= 0) return;
     if (raster_or_flags & 1) {
-        static int cur_attr = 0;
         const int bytes = DT_PF * max_dpitch * 4;
-        if (bytes > cur_attr && bytes > 48 * 1024) {
-            cudaFuncSetAttribute(k_chamfer_dt, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
-            cur_attr = bytes;
-        }
+        CS_ONCE_PER_DEVICE(cs_allow_max_dynamic_smem(k_chamfer_dt));
         CS_APPLY_CARVEOUT(k_chamfer_dt);
         k_chamfer_dt<<<n_jobs, 32, bytes, st>>>(d_jobs, d_ids, d_bits, d_dist);
         (*launches)++;
@@ -1178,11 +1166,7 @@ bool cs_launch_hyst_dt(const CsJob *d_jobs, int n_jobs, uint32_t *d_bits, float 
     const int rb_pitch = (max_dpitch + 3) & ~3;
     const size_t bytes = ((size_t)2 * max_plane_words + (size_t)nw * rb_pitch) * 4;
     if (bytes > 200 * 1024) return false;
-    static size_t cur_attr = 0;
-    if (bytes > cur_attr) {
-        cudaFuncSetAttribute(k_hyst_dt, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
-        cur_attr = bytes;
-    }
+    CS_ONCE_PER_DEVICE(cs_allow_max_dynamic_smem(k_hyst_dt));
     k_hyst_dt<<<n_jobs, 32 * nw, bytes, st>>>(d_jobs, d_bits, d_dist, max_plane_words, rb_pitch);
     (*launches)++;
     return true;

@@ -270,11 +270,7 @@ void cs_launch_roi_lines(const CsJob *d_jobs, int n_jobs, const CsFrame *d_frame
                          int64_t *launches)
 {
     if (n_jobs <= 0) return;
-    static bool attr_set = false;
-    if (!attr_set) {
-        cudaFuncSetAttribute(k_roi_lines, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(LineSet));
-        attr_set = true;
-    }
+    CS_ONCE_PER_DEVICE(cudaFuncSetAttribute(k_roi_lines, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(LineSet)));
     CS_APPLY_CARVEOUT(k_roi_lines);
     k_roi_lines<<<n_jobs, LN_THREADS, sizeof(LineSet), st>>>(d_jobs, d_frames, d_lines, d_lines_f32, d_n_lines_dev, f32_pitch, d_out_lines, d_out_counts, d_err, dist_thre,
                                                              angle_thre_deg, len_thre);

@@ -1060,11 +1060,7 @@ void cs_launch_sweep(const CsJob *d_jobs, const CsFrame *d_frames, const CsPose 
                      double *c_angle, const cs_cuboid_params *prm, cudaStream_t st, int64_t *launches)
 {
     if (n_blocks <= 0) return;
-    static bool attr_set = false;
-    if (!attr_set) {
-        cudaFuncSetAttribute(k_sweep_score, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SweepShared));
-        attr_set = true;
-    }
+    CS_ONCE_PER_DEVICE(cudaFuncSetAttribute(k_sweep_score, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SweepShared)));
     k_sweep_score<<<n_blocks, SW_THREADS, sizeof(SweepShared), st>>>(d_jobs, d_frames, d_poses, d_yaw, d_blocks, d_mlines, d_line_counts, d_dist,
                                                                      c_valid, c_dist, c_angle, *prm);
     (*launches)++;
@@ -1077,11 +1073,7 @@ void cs_launch_fuse(const CsObj *d_objs, int n_objs, const CsJob *d_jobs, const 
 {
     if (n_objs <= 0) return;
     const size_t smem = (sizeof(uint64_t) + sizeof(uint32_t)) * FU_SMEM_SORT;
-    static bool attr_set = false;
-    if (!attr_set) {
-        cudaFuncSetAttribute(k_fuse_rank, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        attr_set = true;
-    }
+    CS_ONCE_PER_DEVICE(cudaFuncSetAttribute(k_fuse_rank, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     k_fuse_rank<<<n_objs, FU_THREADS, smem, st>>>(d_objs, d_jobs, d_frames, d_poses, d_yaw, c_valid, c_dist, c_angle, w_vlist, w_key, w_idx, w_flag,
                                                   w_keep, w_norm, w_score, job_counts, d_out, d_out_counts, topk, *prm);
     (*launches)++;
@@ -1108,11 +1100,7 @@ void cs_launch_fuse_warp(const CsObj *d_objs, int n_objs, const CsJob *d_jobs, c
 {
     if (n_objs <= 0) return;
     const size_t smem = sizeof(FuseWarpShared) * FW_WARPS;
-    static bool attr_set = false;
-    if (!attr_set) {
-        cudaFuncSetAttribute(k_fuse_warp, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        attr_set = true;
-    }
+    CS_ONCE_PER_DEVICE(cudaFuncSetAttribute(k_fuse_warp, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     CS_APPLY_CARVEOUT(k_fuse_warp);
     k_fuse_warp<<<(n_objs + FW_WARPS - 1) / FW_WARPS, 32 * FW_WARPS, smem, st>>>(d_objs, n_objs, d_jobs, d_frames, d_poses, d_yaw, c_valid, c_dist,
                                                                                  c_angle, c_skew, w_vlist, w_keep, w_norm, w_score, job_counts, d_out,

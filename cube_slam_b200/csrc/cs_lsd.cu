@@ -13,12 +13,28 @@
  *   k_lsd_grad    2x2 gradient, modulus, fastAtan2 angle, max modulus     lsd.cpp:562-586
  *   k_lsd_hist / k_lsd_scan / k_lsd_scatter   the 1024-bin pseudo-ordering as a STABLE counting sort (bins descending,
  *                 raster order inside a bin == the reference's linked lists)  lsd.cpp:588-634
- * Sequential stage:
- *   k_lsd_grow    the seed loop (region_grow -> region2rect -> refine -> rect_improve/NFA), ONE WARP PER FRAME.  The order in
- *                 which seeds claim pixels defines the result, so a frame is inherently serial; the warp parallelises what is
- *                 order-free inside it (the 3x3 neighbour tests of a region point, list scanning, rectangle pixel counts,
- *                 min/max extents) and keeps every floating-point accumulation in the reference's order.  Throughput comes from
- *                 batching frames (thousands of warps resident per GPU).
+ *
+ * Seed loop (lsd.cpp:476-535): k_lsd_grow_par, one CTA of LSD_NW warps per frame, ORDERED SPECULATION.
+ *   The reference visits the ordered pixel list one seed at a time; a seed grows a region over the pixels no earlier seed used, so the
+ *   result is defined by the order.  Here the list positions are "candidates" with rank = list position.  Every warp pulls candidates
+ *   of a sliding window ahead of the commit frontier and processes each one completely (region_grow, region2rect, refine, rect_improve)
+ *   against the claim word of every pixel:
+ *       claim = (rank << 1) | former      member (former = 0) / dropped by refine (former = 1) of candidate `rank`;  0xffffffff = free
+ *       rank <  frontier  and member  ->  used for good (that candidate is final)
+ *       rank >= frontier              ->  speculative: a LOWER rank overrides it (compare-and-swap) and flags the victim invalid,
+ *                                         a HIGHER rank that needs the pixel (it is aligned with its region) gives up and retries later.
+ *   A candidate that finishes without having been overridden is CLEAN; it keeps its claims.  After each round the frontier advances over
+ *   the maximal prefix of list positions that are CLEAN, or whose pixel is used by a final region (the reference's `used` test),
+ *   or whose pixel is a member of a CLEAN lower candidate of that prefix.  Everything below the frontier equals the sequential result:
+ *   a CLEAN candidate saw every pixel it tested either used by a final region, or free (and claimed it, so any later lower-rank
+ *   interest would have flagged it), and pixels not aligned with its region do not depend on the used map at all.  The candidate at the
+ *   frontier can neither be refused nor overridden, so every round makes progress.  Segments are emitted in rank order at the end.
+ *   Capacity problems (a region larger than the per-warp staging area, record arena full) flag the frame, and
+ *   k_lsd_grow_seq -- the plain one-warp-per-frame seed loop -- redoes flagged frames (also the A/B path, cs_set_profiling bit 7).
+ *
+ * Inside one candidate the warp parallelises what is order-free (the 3x3 neighbour tests of three region points per step from ONE 16-byte
+ * record per pixel, rectangle pixel counts over rows, the five rectangles of a rect_improve phase and their NFA evaluations on separate
+ * lanes, min/max extents) and keeps every floating-point accumulation in the reference's order.
  */
 #include <cuda_runtime.h>
 #include <float.h>
@@ -40,6 +56,18 @@
 #define LSD_LN10 2.30258509299404568402
 #define LSD_NBINS 1024
 #define LSD_CHUNK_ROWS 8
+
+#define LSD_NW 16            /* warps per frame in k_lsd_grow_par */
+#define LSD_SCAP 512         /* region entries of a warp's staging area kept in shared memory (the rest spills to HBM) */
+#define LSD_SPILL 16384      /* staging capacity per warp (entries), first LSD_SCAP in shared memory */
+#define LSD_WINDOW 4096      /* list positions ahead of the frontier that may be speculated on */
+#define LSD_FREE 0xffffffffu
+#define LSD_ST_NEW 0u
+#define LSD_ST_GROWING 1u
+#define LSD_ST_CLEAN 2u
+#define LSD_ST_MASK 7u
+#define LSD_ST_INVALID 8u
+#define LSD_HDR 8            /* ints of a candidate record header in the arena: n1, n2, has_line, x1 y1 x2 y2 (float bits), pad */
 
 namespace {
 
@@ -161,8 +189,11 @@ __global__ void __launch_bounds__(256) k_lsd_resize(const double *__restrict__ b
     }
 }
 
+/* Per pixel: modulus (f64), level-line angle as the float fastAtan2 returns it (degrees; -1 = NOTDEF; the reference's double angle is
+ * (double)deg * DEG2RAD, recomputed where needed) and the 16-byte growth record {deg, cos, sin, claim}: (cos, sin) of float(angle),
+ * each the correctly rounded float -- what region_grow accumulates (lsd.cpp:680-681). */
 __global__ void __launch_bounds__(256) k_lsd_grad(const double *__restrict__ scaled, int n_frames, int W, int H, double threshold,
-                                                  double *__restrict__ modgrad, double *__restrict__ angles, float2 *__restrict__ cs_angle,
+                                                  double *__restrict__ modgrad, float *__restrict__ angf, uint4 *__restrict__ pix,
                                                   unsigned long long *__restrict__ max_bits)
 {
     const int64_t total = (int64_t)n_frames * W * H;
@@ -171,27 +202,28 @@ __global__ void __launch_bounds__(256) k_lsd_grad(const double *__restrict__ sca
         const int addr = (int)(p - f * (int64_t)W * H);
         const int y = addr / W, x = addr - y * W;
         const double *im = scaled + (size_t)f * W * H;
-        double norm = 0, ang = LSD_NOTDEF;
+        double norm = 0;
+        float deg = -1.f;
         if (x < W - 1 && y < H - 1) {
             const double DA = im[addr + W + 1] - im[addr];
             const double BC = im[addr + 1] - im[addr + W];
             const double gx = DA + BC, gy = DA - BC;
             norm = sqrt((gx * gx + gy * gy) / 4);
             if (!(norm <= threshold)) {
-                ang = (double)fast_atan2((float)gx, (float)(-gy)) * LSD_DEG2RAD;
+                deg = fast_atan2((float)gx, (float)(-gy));
                 atomicMax(max_bits + f, (unsigned long long)__double_as_longlong(norm)); /* positive doubles order like integers */
             }
         }
         modgrad[p] = norm;
-        angles[p] = ang;
-        /* (cos, sin) of float(angle), each the correctly rounded float: what region_grow accumulates (lsd.cpp:680-681) */
-        float2 cs = make_float2(0.f, 0.f);
-        if (ang != LSD_NOTDEF) {
+        angf[p] = deg;
+        uint4 r = make_uint4(__float_as_uint(deg), 0u, 0u, LSD_FREE);
+        if (deg >= 0.f) {
+            const double ang = (double)deg * LSD_DEG2RAD;
             const double af = (double)(float)ang;
-            cs.x = (float)cos(af);
-            cs.y = (float)sin(af);
+            r.y = __float_as_uint((float)cos(af));
+            r.z = __float_as_uint((float)sin(af));
         }
-        cs_angle[p] = cs;
+        pix[p] = r;
     }
 }
 
@@ -202,7 +234,7 @@ __device__ __forceinline__ double bin_coef_of(unsigned long long max_bits)
 }
 
 /* per (frame, chunk of rows) histogram of gradient bins */
-__global__ void __launch_bounds__(256) k_lsd_hist(const double *__restrict__ modgrad, const double *__restrict__ angles, int W, int H, int n_chunks,
+__global__ void __launch_bounds__(256) k_lsd_hist(const double *__restrict__ modgrad, const float *__restrict__ angf, int W, int H, int n_chunks,
                                                   const unsigned long long *__restrict__ max_bits, int32_t *__restrict__ cnt)
 {
     __shared__ int s_h[LSD_NBINS];
@@ -212,11 +244,11 @@ __global__ void __launch_bounds__(256) k_lsd_hist(const double *__restrict__ mod
     const double coef = bin_coef_of(max_bits[f]);
     const int y0 = ch * LSD_CHUNK_ROWS, y1 = min(y0 + LSD_CHUNK_ROWS, H - 1);
     const double *mg = modgrad + (size_t)f * W * H;
-    const double *an = angles + (size_t)f * W * H;
+    const float *an = angf + (size_t)f * W * H;
     const int npx = (y1 - y0) * (W - 1);
     for (int i = threadIdx.x; i < npx; i += 256) {
         const int y = y0 + i / (W - 1), x = i % (W - 1);
-        if (an[(size_t)y * W + x] != LSD_NOTDEF) atomicAdd(&s_h[(int)(mg[(size_t)y * W + x] * coef)], 1);
+        if (an[(size_t)y * W + x] >= 0.f) atomicAdd(&s_h[(int)(mg[(size_t)y * W + x] * coef)], 1);
     }
     __syncthreads();
     int32_t *o = cnt + ((size_t)f * n_chunks + ch) * LSD_NBINS;
@@ -252,7 +284,7 @@ __global__ void __launch_bounds__(LSD_NBINS) k_lsd_scan(int n_chunks, int32_t *_
 }
 
 /* stable scatter: one warp walks its chunk in raster order, 32 pixels per step */
-__global__ void __launch_bounds__(32) k_lsd_scatter(const double *__restrict__ modgrad, const double *__restrict__ angles, int W, int H, int n_chunks,
+__global__ void __launch_bounds__(32) k_lsd_scatter(const double *__restrict__ modgrad, const float *__restrict__ angf, int W, int H, int n_chunks,
                                                     const unsigned long long *__restrict__ max_bits, const int32_t *__restrict__ cnt,
                                                     int32_t *__restrict__ list)
 {
@@ -265,7 +297,7 @@ __global__ void __launch_bounds__(32) k_lsd_scatter(const double *__restrict__ m
     const double coef = bin_coef_of(max_bits[f]);
     const int y0 = ch * LSD_CHUNK_ROWS, y1 = min(y0 + LSD_CHUNK_ROWS, H - 1);
     const double *mg = modgrad + (size_t)f * W * H;
-    const double *an = angles + (size_t)f * W * H;
+    const float *an = angf + (size_t)f * W * H;
     int32_t *out = list + (size_t)f * W * H;
     const int npx = (y1 - y0) * (W - 1);
     for (int i0 = 0; i0 < npx; i0 += 32) {
@@ -275,7 +307,7 @@ __global__ void __launch_bounds__(32) k_lsd_scatter(const double *__restrict__ m
         if (ok) {
             const int y = y0 + i / (W - 1), x = i % (W - 1);
             addr = y * W + x;
-            ok = an[addr] != LSD_NOTDEF;
+            ok = an[addr] >= 0.f;
             if (ok) bin = (int)(mg[addr] * coef);
         }
         const unsigned m = __match_any_sync(0xffffffffu, bin);
@@ -292,16 +324,52 @@ __global__ void __launch_bounds__(32) k_lsd_scatter(const double *__restrict__ m
     }
 }
 
-/* ---------------------------------------------------------------------------------------- the sequential stage */
+/* ---------------------------------------------------------------------------------------- the seed loop */
 struct LsdFrame {
     int W, H;
-    const double *angles;
+    uint4 *pix;            /* {deg, cos, sin, claim} */
+    const float *angf;     /* deg plane for the rectangle scans */
     const double *modgrad;
-    const float2 *cs_angle;
-    uint8_t *used;
-    int32_t *reg;
     double LOG_NT;
+    /* ordered speculation only */
+    uint32_t *st;          /* per list position: state | invalid flag | record offset << 4 */
+    int32_t *arena;        /* records of finished candidates */
+    int arena_cap;
 };
+
+/* the region list of the candidate a warp works on: the first `scap` entries in shared memory, the rest in HBM */
+struct LsdReg {
+    int *s;
+    int *g;
+    int scap;
+    int cap;
+    __device__ __forceinline__ int get(int i) const { return i < scap ? s[i] : __ldcg(g + i); }
+    __device__ __forceinline__ void put(int i, int v) const
+    {
+        if (i < scap)
+            s[i] = v;
+        else
+            g[i] = v;
+    }
+};
+
+/* how a warp sees claim words */
+struct LsdView {
+    int rank;       /* the candidate's list position; -1 = sequential mode (0 = used, FREE = unused) */
+    int frontier;
+};
+enum { LSD_K_FREE = 0, LSD_K_USED = 1, LSD_K_MINE = 2, LSD_K_MINE_FORMER = 3, LSD_K_HIGHER = 4, LSD_K_LOWER = 5 };
+
+__device__ __forceinline__ int lsd_decode(uint32_t c, const LsdView &V)
+{
+    if (c == LSD_FREE) return LSD_K_FREE;
+    const int j = (int)(c >> 1);
+    if (j < V.frontier) return (c & 1u) ? LSD_K_FREE : LSD_K_USED;
+    if (j == V.rank) return (c & 1u) ? LSD_K_MINE_FORMER : LSD_K_MINE;
+    return j > V.rank ? LSD_K_HIGHER : LSD_K_LOWER;
+}
+__device__ __forceinline__ uint32_t *lsd_claim_ptr(const LsdFrame &F, int addr) { return reinterpret_cast<uint32_t *>(F.pix + addr) + 3; }
+__device__ __forceinline__ uint32_t lsd_ld_claim(const LsdFrame &F, int addr) { return __ldcg(lsd_claim_ptr(F, addr)); }
 
 struct LsdRect {
     double x1, y1, x2, y2, width, x, y, theta, dx, dy, prec, p;
@@ -325,10 +393,11 @@ __device__ __forceinline__ bool lsd_double_equal(double a, double b)
     if (abs_max < DBL_MIN) abs_max = DBL_MIN;
     return (abs_diff / abs_max) <= (100.0 * DBL_EPSILON);
 }
-/* lsd.cpp:1138-1154 on an angle value already loaded */
-__device__ __forceinline__ bool lsd_aligned_val(double a, double theta, double prec)
+/* lsd.cpp:1138-1154 on the float level-line angle in degrees (negative = NOTDEF) */
+__device__ __forceinline__ bool lsd_aligned_deg(float deg, double theta, double prec)
 {
-    if (a == LSD_NOTDEF) return false;
+    if (deg < 0.f) return false;
+    const double a = (double)deg * LSD_DEG2RAD;
     double n_theta = theta - a;
     if (n_theta < 0) n_theta = -n_theta;
     if (n_theta > LSD_3_2_PI) {
@@ -338,7 +407,7 @@ __device__ __forceinline__ bool lsd_aligned_val(double a, double theta, double p
     return n_theta <= prec;
 }
 
-__device__ __forceinline__ double lsd_log_gamma(double x)
+__device__ __noinline__ double lsd_log_gamma(double x)
 {
     if (x > 15.0) return 0.918938533204673 + (x - 0.5) * log(x) - x + 0.5 * x * log(x * sinh(1 / x) + 1 / (810.0 * pow(x, 6.0)));
     const double q[7] = {75122.6331530, 80916.6278952, 36308.2951477, 8687.24529705, 1168.92649479, 83.8676043424, 2.50662827511};
@@ -351,8 +420,8 @@ __device__ __forceinline__ double lsd_log_gamma(double x)
     return a + log(b);
 }
 
-/* lsd.cpp:1100-1136 (warp-uniform scalar code) */
-__device__ double lsd_nfa(int n, int k, double p, double LOG_NT)
+/* lsd.cpp:1100-1136; called with different (n, k, p) on different lanes */
+__device__ __noinline__ double lsd_nfa(int n, int k, double p, double LOG_NT)
 {
     if (n == 0 || k == 0) return -LOG_NT;
     if (n == k) return -LOG_NT - (double)n * log10(p);
@@ -378,56 +447,115 @@ __device__ double lsd_nfa(int n, int k, double p, double LOG_NT)
     return -log10(bin_tail) - LOG_NT;
 }
 
-/* lsd.cpp:637-688.  Neighbour tests of one region point run on lanes 0..8; additions stay in the reference's order. */
-__device__ void lsd_region_grow(const LsdFrame &F, int s_addr, int &reg_size, double &reg_angle, double prec)
+/* Claim one pixel for the candidate (compare-and-swap; a higher-rank speculative owner is overridden and flagged).
+ * `c` is the claim word last seen.  Returns false when a final or lower-rank owner holds it. */
+__device__ __forceinline__ bool lsd_claim(const LsdFrame &F, const LsdView &V, int addr, uint32_t c)
+{
+    uint32_t *cw = lsd_claim_ptr(F, addr);
+    if (V.rank < 0) { /* sequential mode */
+        *cw = 0u;
+        return true;
+    }
+    const uint32_t me0 = (uint32_t)V.rank << 1;
+    for (;;) {
+        const int kind = lsd_decode(c, V);
+        if (kind != LSD_K_FREE && kind != LSD_K_HIGHER && kind != LSD_K_MINE_FORMER) return kind == LSD_K_MINE;
+        const uint32_t old = atomicCAS(cw, c, me0);
+        if (old == c) {
+            if (kind == LSD_K_HIGHER) atomicOr(F.st + (c >> 1), LSD_ST_INVALID);
+            return true;
+        }
+        c = old;
+    }
+}
+/* member -> dropped (refine / reduce_region_radius clear `used`): false when a lower rank took the pixel meanwhile */
+__device__ __forceinline__ bool lsd_demote(const LsdFrame &F, const LsdView &V, int addr)
+{
+    uint32_t *cw = lsd_claim_ptr(F, addr);
+    if (V.rank < 0) {
+        *cw = LSD_FREE;
+        return true;
+    }
+    const uint32_t me0 = (uint32_t)V.rank << 1;
+    return atomicCAS(cw, me0, me0 | 1u) == me0;
+}
+/* give back every claim the candidate still holds on the listed pixels */
+__device__ void lsd_release(const LsdFrame &F, int rank, const LsdReg &R, int n)
+{
+    const int lane = threadIdx.x & 31;
+    for (int i = lane; i < n; i += 32) {
+        const int addr = R.get(i);
+        uint32_t *cw = lsd_claim_ptr(F, addr);
+        const uint32_t c = __ldcg(cw);
+        if ((int)(c >> 1) == rank && c != LSD_FREE) atomicCAS(cw, c, LSD_FREE);
+    }
+    __syncwarp();
+}
+
+/* lsd.cpp:637-688.  Neighbour tests of three region points per round on lanes 0..26 (one 16-byte record each); additions stay in the
+ * reference's order.  The region is R[base .. base + reg_size).  Returns 0 ok, 1 refused (a lower-rank speculative owner holds a pixel
+ * this region wants, or a claim was lost), 2 staging overflow. */
+__device__ int lsd_region_grow(const LsdFrame &F, const LsdView &V, const LsdReg &R, int base, int s_addr, int &reg_size, double &reg_angle, double prec)
 {
     const unsigned FULL = 0xffffffffu;
     const int lane = threadIdx.x & 31;
+    {
+        int ok = 1;
+        if (lane == 0) ok = lsd_claim(F, V, s_addr, lsd_ld_claim(F, s_addr)) ? 1 : 0;
+        if (!__shfl_sync(FULL, ok, 0)) return 1;
+    }
     reg_size = 1;
-    reg_angle = F.angles[s_addr];
+    reg_angle = (double)F.angf[s_addr] * LSD_DEG2RAD;
     float sumdx = (float)cos(reg_angle);
     float sumdy = (float)sin(reg_angle);
-    if (lane == 0) {
-        F.reg[0] = s_addr;
-        F.used[s_addr] = 1;
-    }
+    if (lane == 0) R.put(base, s_addr);
     __syncwarp();
-    /* Three region points per round: lanes 9g..9g+8 fetch the 3x3 neighbourhood of point i+g (used flag, angle, cos/sin) in one
-     * go, then the points are consumed strictly in order.  A neighbour claimed while an earlier point of the round is consumed is
-     * struck from the later groups, so the sequence of additions is exactly the reference's. */
     const int grp = lane / 9, kk = lane - grp * 9;
     const int ky = kk / 3 - 1, kx = kk - (kk / 3) * 3 - 1; /* (yy, xx) in the reference's loop order */
     for (int i = 0; i < reg_size;) {
         const int navail = min(3, reg_size - i);
-        bool cand = false;
+        if (base + reg_size + 27 > R.cap) return 2;
+        bool cand = false, low = false, mine = false;
         int c_addr = -1;
-        double a = LSD_NOTDEF;
-        float2 csf = make_float2(0.f, 0.f);
+        float deg = -1.f, csx = 0.f, csy = 0.f;
+        uint32_t cseen = LSD_FREE;
         if (grp < navail) {
-            const int pa = F.reg[i + grp];
+            const int pa = R.get(base + i + grp);
             const int py = pa / F.W, px = pa - py * F.W;
             const int yy = py + ky, xx = px + kx;
             if (yy >= 0 && yy < F.H && xx >= 0 && xx < F.W) {
                 c_addr = yy * F.W + xx;
-                if (F.used[c_addr] != 1) {
-                    a = F.angles[c_addr];
-                    cand = (a != LSD_NOTDEF);
-                    if (cand) csf = F.cs_angle[c_addr];
+                const uint4 r = __ldcg(F.pix + c_addr);
+                deg = __uint_as_float(r.x);
+                if (deg >= 0.f) {
+                    cseen = r.w;
+                    int kind;
+                    if (V.rank < 0)
+                        kind = (cseen == LSD_FREE) ? LSD_K_FREE : LSD_K_USED;
+                    else
+                        kind = lsd_decode(cseen, V);
+                    cand = (kind == LSD_K_FREE || kind == LSD_K_HIGHER || kind == LSD_K_MINE_FORMER || kind == LSD_K_LOWER);
+                    low = (kind == LSD_K_LOWER);
+                    csx = __uint_as_float(r.y);
+                    csy = __uint_as_float(r.z);
                 }
             }
         }
+        bool refused = false;
         for (int g = 0; g < navail; g++) {
             unsigned pending = __ballot_sync(FULL, cand && grp == g);
             while (pending) {
-                const unsigned ok = __ballot_sync(FULL, cand && ((pending >> lane) & 1u) && lsd_aligned_val(a, reg_angle, prec));
+                const unsigned ok = __ballot_sync(FULL, cand && ((pending >> lane) & 1u) && lsd_aligned_deg(deg, reg_angle, prec));
                 if (!ok) break;
                 const int fl = __ffs(ok) - 1;
-                const int addrf = __shfl_sync(FULL, c_addr, fl);
-                const float cx = __shfl_sync(FULL, csf.x, fl), cy = __shfl_sync(FULL, csf.y, fl);
-                if (lane == 0) {
-                    F.used[addrf] = 1;
-                    F.reg[reg_size] = addrf;
+                if (__shfl_sync(FULL, (int)low, fl)) {
+                    refused = true; /* the pixel belongs, for now, to a lower-rank candidate that is not final */
+                    break;
                 }
+                const int addrf = __shfl_sync(FULL, c_addr, fl);
+                const float cx = __shfl_sync(FULL, csx, fl), cy = __shfl_sync(FULL, csy, fl);
+                if (lane == 0) R.put(base + reg_size, addrf);
+                if (lane == fl) mine = true;
                 ++reg_size;
                 /* cos(float(angle)), sin(float(angle)): precomputed per pixel by k_lsd_grad (pinned to the correctly rounded float) */
                 sumdx += cx;
@@ -436,27 +564,33 @@ __device__ void lsd_region_grow(const LsdFrame &F, int s_addr, int &reg_size, do
                 pending &= ~((2u << fl) - 1u);
                 if (c_addr == addrf) cand = false; /* the same pixel seen from a later point of this round */
             }
+            if (refused) break;
         }
-        i += navail;
+        bool lost = false;
+        if (mine) lost = !lsd_claim(F, V, c_addr, cseen);
         __syncwarp();
+        if (refused || __any_sync(FULL, lost)) return 1;
+        i += navail;
     }
+    return 0;
 }
 
 /* ordered accumulation helper: lanes fetch 32 region points at once, every lane then replays them in order */
-#define LSD_FOR_REGION_ORDERED(F, reg_size, ...)                                    \
+#define LSD_FOR_REGION_ORDERED(F, R, base, reg_size, ...)                           \
     for (int i0__ = 0; i0__ < (reg_size); i0__ += 32) {                             \
         const int n__ = min(32, (reg_size)-i0__);                                   \
         int my_addr__ = 0;                                                          \
-        double my_w__ = 0, my_a__ = 0;                                              \
+        double my_w__ = 0;                                                          \
+        float my_a__ = 0;                                                           \
         if (lane < n__) {                                                           \
-            my_addr__ = (F).reg[i0__ + lane];                                       \
+            my_addr__ = (R).get((base) + i0__ + lane);                              \
             my_w__ = (F).modgrad[my_addr__];                                        \
-            my_a__ = (F).angles[my_addr__];                                         \
+            my_a__ = (F).angf[my_addr__];                                           \
         }                                                                           \
         for (int j__ = 0; j__ < n__; j__++) {                                       \
             const int addr = __shfl_sync(0xffffffffu, my_addr__, j__);              \
             const double weight = __shfl_sync(0xffffffffu, my_w__, j__);            \
-            const double pangle = __shfl_sync(0xffffffffu, my_a__, j__);            \
+            const double pangle = (double)__shfl_sync(0xffffffffu, my_a__, j__) * LSD_DEG2RAD; \
             const int ry = addr / (F).W, rx = addr - ry * (F).W;                    \
             (void)weight;                                                           \
             (void)pangle;                                                           \
@@ -465,11 +599,11 @@ __device__ void lsd_region_grow(const LsdFrame &F, int s_addr, int &reg_size, do
     }
 
 /* lsd.cpp:690-784 */
-__device__ void lsd_region2rect(const LsdFrame &F, int reg_size, double reg_angle, double prec, double p, LsdRect &rec)
+__device__ void lsd_region2rect(const LsdFrame &F, const LsdReg &R, int base, int reg_size, double reg_angle, double prec, double p, LsdRect &rec)
 {
     const int lane = threadIdx.x & 31;
     double x = 0, y = 0, sum = 0;
-    LSD_FOR_REGION_ORDERED(F, reg_size, {
+    LSD_FOR_REGION_ORDERED(F, R, base, reg_size, {
         x += (double)rx * weight;
         y += (double)ry * weight;
         sum += weight;
@@ -478,7 +612,7 @@ __device__ void lsd_region2rect(const LsdFrame &F, int reg_size, double reg_angl
     y /= sum;
     /* get_theta */
     double Ixx = 0.0, Iyy = 0.0, Ixy = 0.0;
-    LSD_FOR_REGION_ORDERED(F, reg_size, {
+    LSD_FOR_REGION_ORDERED(F, R, base, reg_size, {
         const double ddx = (double)rx - x, ddy = (double)ry - y;
         Ixx += ddy * ddy * weight;
         Iyy += ddx * ddx * weight;
@@ -492,7 +626,7 @@ __device__ void lsd_region2rect(const LsdFrame &F, int reg_size, double reg_angl
     /* extents: min / max are order-free, so lanes split the region */
     double l_min = 0, l_max = 0, w_min = 0, w_max = 0;
     for (int i = lane; i < reg_size; i += 32) {
-        const int addr = F.reg[i];
+        const int addr = R.get(base + i);
         const int ry = addr / F.W, rx = addr - ry * F.W;
         const double regdx = (double)rx - x, regdy = (double)ry - y;
         const double l = regdx * dx + regdy * dy;
@@ -524,52 +658,57 @@ __device__ void lsd_region2rect(const LsdFrame &F, int reg_size, double reg_angl
     if (rec.width < 1.0) rec.width = 1.0;
 }
 
-/* lsd.cpp:834-871 (lane 0 replays the reference's in-place compaction; it fixes the order later sums run in) */
-__device__ bool lsd_reduce_region_radius(const LsdFrame &F, int &reg_size, double reg_angle, double prec, double p, LsdRect &rec, double density,
-                                         double density_th)
+/* lsd.cpp:834-871 (lane 0 replays the reference's in-place compaction; it fixes the order later sums run in).
+ * Returns 0 ok, 1 claim lost, 3 region rejected. */
+__device__ int lsd_reduce_region_radius(const LsdFrame &F, const LsdView &V, const LsdReg &R, int base, int &reg_size, double reg_angle, double prec, double p,
+                                        LsdRect &rec, double density, double density_th)
 {
     const int lane = threadIdx.x & 31;
-    const int a0 = F.reg[0];
+    const int a0 = R.get(base);
     const double xc = (double)(a0 % F.W), yc = (double)(a0 / F.W);
     const double radSq1 = lsd_dist_sq(xc, yc, rec.x1, rec.y1), radSq2 = lsd_dist_sq(xc, yc, rec.x2, rec.y2);
     double radSq = radSq1 > radSq2 ? radSq1 : radSq2;
     while (density < density_th) {
         radSq *= 0.75 * 0.75;
-        int rs = reg_size;
+        int rs = reg_size, lost = 0;
         if (lane == 0) {
             for (int i = 0; i < rs; ++i) {
-                const int addr = F.reg[i];
+                const int addr = R.get(base + i);
                 if (lsd_dist_sq(xc, yc, (double)(addr % F.W), (double)(addr / F.W)) > radSq) {
-                    F.used[addr] = 0;
-                    const int last = F.reg[rs - 1];
-                    F.reg[rs - 1] = addr;
-                    F.reg[i] = last;
+                    if (!lsd_demote(F, V, addr)) lost = 1;
+                    const int last = R.get(base + rs - 1);
+                    R.put(base + rs - 1, addr);
+                    R.put(base + i, last);
                     --rs;
                     --i;
                 }
             }
         }
         reg_size = __shfl_sync(0xffffffffu, rs, 0);
+        lost = __shfl_sync(0xffffffffu, lost, 0);
         __syncwarp();
-        if (reg_size < 2) return false;
-        lsd_region2rect(F, reg_size, reg_angle, prec, p, rec);
+        if (lost) return 1;
+        if (reg_size < 2) return 3;
+        lsd_region2rect(F, R, base, reg_size, reg_angle, prec, p, rec);
         density = (double)reg_size / (lsd_dist(rec.x1, rec.y1, rec.x2, rec.y2) * rec.width);
     }
-    return true;
+    return 0;
 }
 
-/* lsd.cpp:786-832 */
-__device__ bool lsd_refine(const LsdFrame &F, int &reg_size, double reg_angle, double prec, double p, LsdRect &rec, double density_th)
+/* lsd.cpp:786-832.  The re-grown region is appended after the first one (base moves), so the record of a candidate lists every pixel
+ * it ever claimed.  Returns 0 ok, 1 refused / claim lost, 2 overflow, 3 region rejected. */
+__device__ int lsd_refine(const LsdFrame &F, const LsdView &V, const LsdReg &R, int &base, int &reg_size, double &reg_angle, double prec, double p, LsdRect &rec,
+                          double density_th, int &n_all)
 {
     const int lane = threadIdx.x & 31;
     double density = (double)reg_size / (lsd_dist(rec.x1, rec.y1, rec.x2, rec.y2) * rec.width);
-    if (density >= density_th) return true;
-    const int a0 = F.reg[0];
+    if (density >= density_th) return 0;
+    const int a0 = R.get(base);
     const double xc = (double)(a0 % F.W), yc = (double)(a0 / F.W);
-    const double ang_c = F.angles[a0];
+    const double ang_c = (double)F.angf[a0] * LSD_DEG2RAD;
     double sum = 0, s_sum = 0;
     int n = 0;
-    LSD_FOR_REGION_ORDERED(F, reg_size, {
+    LSD_FOR_REGION_ORDERED(F, R, base, reg_size, {
         if (lsd_dist(xc, yc, (double)rx, (double)ry) < rec.width) {
             const double ang_d = lsd_angle_diff_signed(pangle, ang_c);
             sum += ang_d;
@@ -577,20 +716,27 @@ __device__ bool lsd_refine(const LsdFrame &F, int &reg_size, double reg_angle, d
             ++n;
         }
     })
-    for (int i = lane; i < reg_size; i += 32) F.used[F.reg[i]] = 0;
+    bool lost = false;
+    for (int i = lane; i < reg_size; i += 32) lost |= !lsd_demote(F, V, R.get(base + i));
     __syncwarp();
+    if (__any_sync(0xffffffffu, lost)) return 1;
     const double mean_angle = sum / (double)n;
     const double tau = 2.0 * sqrt((s_sum - 2.0 * mean_angle * sum) / (double)n + mean_angle * mean_angle);
-    lsd_region_grow(F, a0, reg_size, reg_angle, tau);
-    if (reg_size < 2) return false;
-    lsd_region2rect(F, reg_size, reg_angle, prec, p, rec);
+    base += reg_size;
+    const int rc = lsd_region_grow(F, V, R, base, a0, reg_size, reg_angle, tau);
+    n_all = base + reg_size; /* reduce_region_radius below only permutes the second list */
+    if (rc) return rc;
+    if (reg_size < 2) return 3;
+    lsd_region2rect(F, R, base, reg_size, reg_angle, prec, p, rec);
     density = (double)reg_size / (lsd_dist(rec.x1, rec.y1, rec.x2, rec.y2) * rec.width);
-    if (density < density_th) return lsd_reduce_region_radius(F, reg_size, reg_angle, prec, p, rec, density, density_th);
-    return true;
+    if (density < density_th) return lsd_reduce_region_radius(F, V, R, base, reg_size, reg_angle, prec, p, rec, density, density_th);
+    return 0;
 }
 
-/* lsd.cpp:977-1098 with the vendored slips kept; the pixel count of a scan row is split over the lanes */
-__device__ double lsd_rect_nfa(const LsdFrame &F, const LsdRect &rec)
+/* lsd.cpp:977-1098 with the vendored slips kept: the (total, aligned) pixel counts of a rectangle.  The edge stepping of the
+ * reference adds integer-valued steps (its slopes are int / int divisions) to integer starts, once per row INSIDE the image, so the
+ * span of a row has a closed form and rows are scanned by separate lanes. */
+__device__ void lsd_rect_count(const LsdFrame &F, const LsdRect &rec, int &total_pts, int &alg_pts)
 {
     const int lane = threadIdx.x & 31;
     const double half_width = rec.width / 2.0;
@@ -650,202 +796,508 @@ __device__ double lsd_rect_nfa(const LsdFrame &F, const LsdRect &rec)
                 itail = i;
         }
     const int mx = ox[imin], my = oy[imin], lx = ox[ileft], ly = oy[ileft], rx = ox[iright], ry = oy[iright], tx = ox[itail];
-    const double flstep = (my != ly) ? (double)((mx - lx) / (my - ly)) : 0;
-    const double slstep = (ly != tx) ? (double)((lx - tx) / (ly - tx)) : 0;
-    const double frstep = (my != ry) ? (double)((mx - rx) / (my - ry)) : 0;
-    const double srstep = (ry != tx) ? (double)((rx - tx) / (ry - tx)) : 0;
-    double lstep = flstep, rstep = frstep;
-    double left_x = mx, right_x = mx;
-    int total_pts = 0, alg_pts = 0;
+    const long long flstep = (my != ly) ? (long long)((mx - lx) / (my - ly)) : 0;
+    const long long slstep = (ly != tx) ? (long long)((lx - tx) / (ly - tx)) : 0;
+    const long long frstep = (my != ry) ? (long long)((mx - rx) / (my - ry)) : 0;
+    const long long srstep = (ry != tx) ? (long long)((rx - tx) / (ry - tx)) : 0;
     const int max_iter = oy[imax];
-    for (int y = my; y <= max_iter; ++y) {
-        if (y < 0 || y >= F.H) continue; /* as the reference: rows outside the image also skip the edge stepping */
-        const int xa = (int)left_x, xb = (int)right_x;
-        const int lo = max(xa, 0), hi = min(xb, F.W - 1);
-        for (int x0 = lo; x0 <= hi; x0 += 32) {
-            const int x = x0 + lane;
-            const bool in = x <= hi;
-            bool al = false;
-            if (in) al = lsd_aligned_val(F.angles[y * F.W + x], rec.theta, rec.prec);
-            total_pts += __popc(__ballot_sync(0xffffffffu, in));
-            alg_pts += __popc(__ballot_sync(0xffffffffu, al));
+    /* rows outside the image skip the edge stepping too (as the reference): only rows y0..y1 count */
+    const int y0 = max(my, 0), y1 = min(max_iter, F.H - 1);
+    int tot = 0, alg = 0;
+    for (int y = y0 + lane; y <= y1; y += 32) {
+        /* steps added before row y: one per earlier inside row y' in [y0, y); row y' adds the second slope iff y' >= ly (ry) */
+        const long long n_l2 = (long long)max(0, y - max(ly, y0)), n_l1 = (long long)(y - y0) - n_l2;
+        const long long n_r2 = (long long)max(0, y - max(ry, y0)), n_r1 = (long long)(y - y0) - n_r2;
+        const long long left_x = (long long)mx + n_l1 * flstep + n_l2 * slstep;
+        const long long right_x = (long long)mx + n_r1 * frstep + n_r2 * srstep;
+        const long long lo = left_x > 0 ? left_x : 0, hi = right_x < (long long)(F.W - 1) ? right_x : (long long)(F.W - 1);
+        if (hi >= lo) {
+            tot += (int)(hi - lo + 1);
+            const float *row = F.angf + (size_t)y * F.W;
+            for (int x = (int)lo; x <= (int)hi; x++) alg += lsd_aligned_deg(row[x], rec.theta, rec.prec) ? 1 : 0;
         }
-        if (y >= ly) lstep = slstep;
-        if (y >= ry) rstep = srstep;
-        left_x += lstep;
-        right_x += rstep;
     }
-    return lsd_nfa(total_pts, alg_pts, rec.p, F.LOG_NT);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        tot += __shfl_xor_sync(0xffffffffu, tot, o);
+        alg += __shfl_xor_sync(0xffffffffu, alg, o);
+    }
+    total_pts = tot;
+    alg_pts = alg;
 }
 
-/* lsd.cpp:873-975 */
+/* the NFA of up to five rectangles of one rect_improve phase: counts one rectangle after the other (rows across lanes), then the
+ * binomial tails on five lanes at once */
+__device__ void lsd_rect_nfa5(const LsdFrame &F, const LsdRect *r, int n, double *v)
+{
+    const int lane = threadIdx.x & 31;
+    int my_tot = 0, my_alg = 0;
+    double my_p = 0.5;
+    for (int t = 0; t < n; t++) {
+        int tot, alg;
+        lsd_rect_count(F, r[t], tot, alg);
+        if (lane == t) {
+            my_tot = tot;
+            my_alg = alg;
+            my_p = r[t].p;
+        }
+    }
+    double mine = 0;
+    if (lane < n) mine = lsd_nfa(my_tot, my_alg, my_p, F.LOG_NT);
+    __syncwarp();
+    for (int t = 0; t < n; t++) v[t] = __shfl_sync(0xffffffffu, mine, t);
+}
+
+/* lsd.cpp:873-975: the rectangles of a phase do not depend on the NFA values of that phase, so they are evaluated together */
 __device__ double lsd_rect_improve(const LsdFrame &F, LsdRect &rec)
 {
     const double delta = 0.5, delta_2 = delta / 2.0, LOG_EPS = 0;
-    double log_nfa = lsd_rect_nfa(F, rec);
+    LsdRect cand[5];
+    double v[5];
+    lsd_rect_nfa5(F, &rec, 1, v);
+    double log_nfa = v[0];
     if (log_nfa > LOG_EPS) return log_nfa;
     LsdRect r = rec;
     for (int n = 0; n < 5; ++n) {
         r.p /= 2;
         r.prec = r.p * LSD_PI;
-        const double v = lsd_rect_nfa(F, r);
-        if (v > log_nfa) {
-            log_nfa = v;
-            rec = r;
-        }
+        cand[n] = r;
     }
-    if (log_nfa > LOG_EPS) return log_nfa;
-    r = rec;
+    lsd_rect_nfa5(F, cand, 5, v);
     for (int n = 0; n < 5; ++n)
-        if ((r.width - delta) >= 0.5) {
-            r.width -= delta;
-            const double v = lsd_rect_nfa(F, r);
-            if (v > log_nfa) {
-                rec = r;
-                log_nfa = v;
-            }
+        if (v[n] > log_nfa) {
+            log_nfa = v[n];
+            rec = cand[n];
         }
     if (log_nfa > LOG_EPS) return log_nfa;
-    r = rec;
-    for (int n = 0; n < 5; ++n)
-        if ((r.width - delta) >= 0.5) {
-            r.x1 += -r.dy * delta_2;
-            r.y1 += r.dx * delta_2;
-            r.x2 += -r.dy * delta_2;
-            r.y2 += r.dx * delta_2;
-            r.width -= delta;
-            const double v = lsd_rect_nfa(F, r);
-            if (v > log_nfa) {
-                rec = r;
-                log_nfa = v;
+    for (int phase = 0; phase < 4; phase++) {
+        r = rec;
+        int m = 0;
+        for (int n = 0; n < 5; ++n)
+            if ((r.width - delta) >= 0.5) {
+                if (phase == 0)
+                    r.width -= delta;
+                else if (phase == 1) {
+                    r.x1 += -r.dy * delta_2;
+                    r.y1 += r.dx * delta_2;
+                    r.x2 += -r.dy * delta_2;
+                    r.y2 += r.dx * delta_2;
+                    r.width -= delta;
+                } else if (phase == 2) {
+                    r.x1 -= -r.dy * delta_2;
+                    r.y1 -= r.dx * delta_2;
+                    r.x2 -= -r.dy * delta_2;
+                    r.y2 -= r.dx * delta_2;
+                    r.width -= delta;
+                } else {
+                    r.p /= 2;
+                    r.prec = r.p * LSD_PI;
+                }
+                cand[m++] = r;
             }
+        if (m) {
+            lsd_rect_nfa5(F, cand, m, v);
+            for (int n = 0; n < m; ++n)
+                if (v[n] > log_nfa) {
+                    rec = cand[n];
+                    log_nfa = v[n];
+                }
         }
-    if (log_nfa > LOG_EPS) return log_nfa;
-    r = rec;
-    for (int n = 0; n < 5; ++n)
-        if ((r.width - delta) >= 0.5) {
-            r.x1 -= -r.dy * delta_2;
-            r.y1 -= r.dx * delta_2;
-            r.x2 -= -r.dy * delta_2;
-            r.y2 -= r.dx * delta_2;
-            r.width -= delta;
-            const double v = lsd_rect_nfa(F, r);
-            if (v > log_nfa) {
-                rec = r;
-                log_nfa = v;
-            }
-        }
-    if (log_nfa > LOG_EPS) return log_nfa;
-    r = rec;
-    for (int n = 0; n < 5; ++n)
-        if ((r.width - delta) >= 0.5) {
-            r.p /= 2;
-            r.prec = r.p * LSD_PI;
-            const double v = lsd_rect_nfa(F, r);
-            if (v > log_nfa) {
-                rec = r;
-                log_nfa = v;
-            }
-        }
+        if (phase < 3 && log_nfa > LOG_EPS) return log_nfa;
+    }
     return log_nfa;
 }
 
-/* The seed loop of flsd (lsd.cpp:476-535) + the KeyLine filters of LSDDetector::detectImpl (:205-256) and filter_lines.
- * One warp per frame. */
-__global__ void __launch_bounds__(32) k_lsd_grow(int W, int H, int img_w, int img_h, const double *__restrict__ angles_all,
-                                                 const double *__restrict__ modgrad_all, const float2 *__restrict__ cs_all, uint8_t *__restrict__ used_all,
-                                                 int32_t *__restrict__ reg_all, const int32_t *__restrict__ list_all,
-                                                 const int32_t *__restrict__ list_len, double LOG_NT, int min_reg_size, double prec, double p,
-                                                 double scale, float line_length_thres, float *__restrict__ raw_all, int32_t *__restrict__ n_raw_all,
-                                                 float *__restrict__ out_all, int32_t *__restrict__ n_out_all, int cap)
+/* One seed, start to finish (the body of the loop lsd.cpp:478-535).  Returns 0 done (has_line / line set), 1 refused, 2 overflow.
+ * n_all = entries of R that hold every pixel the candidate ever claimed. */
+__device__ int lsd_process_seed(const LsdFrame &F, const LsdView &V, const LsdReg &R, int s_addr, int min_reg_size, double prec, double p, double scale,
+                                int &n_all, int &has_line, float *line)
+{
+    const double DENSITY_TH = 0.7, LOG_EPS = 0;
+    int base = 0, reg_size = 0;
+    double reg_angle = 0;
+    has_line = 0;
+    n_all = 0;
+    int rc = lsd_region_grow(F, V, R, 0, s_addr, reg_size, reg_angle, prec);
+    n_all = reg_size;
+    if (rc) return rc;
+    if (reg_size < min_reg_size) return 0;
+    LsdRect rec;
+    lsd_region2rect(F, R, 0, reg_size, reg_angle, prec, p, rec);
+    rc = lsd_refine(F, V, R, base, reg_size, reg_angle, prec, p, rec, DENSITY_TH, n_all);
+    if (rc == 3) return 0;
+    if (rc) return rc;
+    const double log_nfa = lsd_rect_improve(F, rec);
+    if (log_nfa <= LOG_EPS) return 0;
+    rec.x1 += 0.5;
+    rec.y1 += 0.5;
+    rec.x2 += 0.5;
+    rec.y2 += 0.5;
+    rec.x1 /= scale;
+    rec.y1 /= scale;
+    rec.x2 /= scale;
+    rec.y2 /= scale;
+    line[0] = (float)rec.x1;
+    line[1] = (float)rec.y1;
+    line[2] = (float)rec.x2;
+    line[3] = (float)rec.y2;
+    has_line = 1;
+    return 0;
+}
+
+/* checkLineExtremes + 10-px border rejection + length filter (LSDDetector.cpp:75-101,226-238; filter_lines): true = keep */
+__device__ __forceinline__ bool lsd_keyline_filter(const float *raw, int img_w, int img_h, float line_length_thres, float *o)
+{
+    const float pre_boundary_thre = 10;
+    float e[4] = {raw[0], raw[1], raw[2], raw[3]};
+    if (e[0] < 0) e[0] = 0;
+    if (e[0] >= img_w) e[0] = (float)img_w - 1.0f;
+    if (e[2] < 0) e[2] = 0;
+    if (e[2] >= img_w) e[2] = (float)img_w - 1.0f;
+    if (e[1] < 0) e[1] = 0;
+    if (e[1] >= img_h) e[1] = (float)img_h - 1.0f;
+    if (e[3] < 0) e[3] = 0;
+    if (e[3] >= img_h) e[3] = (float)img_h - 1.0f;
+    const float sx = e[0], sy = e[1], ex = e[2], ey = e[3];
+    if (((sx < pre_boundary_thre) && (ex < pre_boundary_thre)) || ((sx > img_w - pre_boundary_thre) && (ex > img_w - pre_boundary_thre)) ||
+        ((sy < pre_boundary_thre) && (ey < pre_boundary_thre)) || ((sy > img_h - pre_boundary_thre) && (ey > img_h - pre_boundary_thre)))
+        return false;
+    const double ddx = (double)(e[0] - e[2]), ddy = (double)(e[1] - e[3]);
+    const float line_length = (float)sqrt(ddx * ddx + ddy * ddy);
+    if (!(line_length > line_length_thres)) return false;
+    o[0] = sx;
+    o[1] = sy;
+    o[2] = ex;
+    o[3] = ey;
+    return true;
+}
+
+struct LsdGrowArgs {
+    int W, H, img_w, img_h;
+    uint4 *pix;
+    const float *angf;
+    const double *modgrad;
+    const int32_t *list;
+    const int32_t *list_len;
+    uint32_t *st;
+    int32_t *arena;
+    int arena_cap;       /* ints per frame */
+    int32_t *spill;      /* LSD_SPILL ints per warp (the first LSD_SCAP unused) */
+    double LOG_NT;
+    int min_reg_size;
+    double prec, p, scale;
+    float line_length_thres;
+    float *raw;
+    int32_t *n_raw;
+    float *out;
+    int32_t *n_out;
+    int cap;
+    int32_t *redo;       /* per frame: 1 = the sequential kernel must redo this frame */
+    int32_t *stats;      /* per frame: rounds, candidates processed, refused, invalidated (diagnostics) */
+};
+
+/* The seed loop of flsd (lsd.cpp:476-535) by ordered speculation, one CTA per frame (see the file header). */
+__global__ void __launch_bounds__(LSD_NW * 32, 2) k_lsd_grow_par(LsdGrowArgs A, int force_seq)
+{
+    __shared__ int s_stage[LSD_NW][LSD_SCAP];
+    __shared__ int s_next, s_first, s_arena_top, s_fail, s_cnt[4];
+    __shared__ int s_warp_cnt[LSD_NW], s_base_raw, s_base_out;
+    const int f = blockIdx.x, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const unsigned FULL = 0xffffffffu;
+    const int T = LSD_NW * 32;
+    const size_t npx = (size_t)A.W * A.H;
+    if (force_seq) {
+        if (tid == 0) A.redo[f] = 1;
+        return;
+    }
+    LsdFrame F;
+    F.W = A.W;
+    F.H = A.H;
+    F.pix = A.pix + f * npx;
+    F.angf = A.angf + f * npx;
+    F.modgrad = A.modgrad + f * npx;
+    F.LOG_NT = A.LOG_NT;
+    F.st = A.st + f * npx;
+    F.arena = A.arena + (size_t)f * A.arena_cap;
+    F.arena_cap = A.arena_cap;
+    const int32_t *list = A.list + f * npx;
+    const int n_list = A.list_len[f];
+    LsdReg R;
+    R.s = s_stage[wid];
+    R.g = A.spill + ((size_t)f * LSD_NW + wid) * LSD_SPILL;
+    R.scap = LSD_SCAP;
+    R.cap = LSD_SPILL;
+    if (tid == 0) {
+        s_arena_top = 0;
+        s_fail = 0;
+        s_cnt[0] = s_cnt[1] = s_cnt[2] = s_cnt[3] = 0;
+    }
+    int frontier = 0, rounds = 0;
+    __syncthreads();
+    while (frontier < n_list) {
+        const int E = min(frontier + LSD_WINDOW, n_list);
+        if (tid == 0) {
+            s_next = frontier;
+            s_first = E;
+        }
+        __syncthreads();
+        rounds++;
+        /* ---- speculation: warps pull 32 list positions at a time */
+        for (;;) {
+            int b = 0;
+            if (lane == 0) b = atomicAdd(&s_next, 32);
+            b = __shfl_sync(FULL, b, 0);
+            if (b >= E || *(volatile int *)&s_fail) break;
+            const int i = b + lane;
+            bool need = false, rel = false;
+            uint32_t sw = 0;
+            if (i < E) {
+                sw = __ldcg(F.st + i);
+                const uint32_t state = sw & LSD_ST_MASK;
+                if (state == LSD_ST_CLEAN) {
+                    rel = (sw & LSD_ST_INVALID) != 0; /* overridden by a lower rank: give the claims back, grow again */
+                } else {
+                    LsdView V0;
+                    V0.rank = i;
+                    V0.frontier = frontier;
+                    const int kind = lsd_decode(lsd_ld_claim(F, list[i]), V0);
+                    need = (kind == LSD_K_FREE || kind == LSD_K_HIGHER); /* used: final skip; lower: wait for that candidate */
+                }
+            }
+            unsigned todo = __ballot_sync(FULL, need || rel);
+            while (todo) {
+                const int sl = __ffs(todo) - 1;
+                todo &= todo - 1;
+                const int pos = b + sl;
+                if (__shfl_sync(FULL, (int)rel, sl)) {
+                    const uint32_t w0 = __shfl_sync(FULL, sw, sl);
+                    const int off = (int)(w0 >> 4);
+                    LsdReg RA;
+                    RA.s = nullptr;
+                    RA.g = F.arena + off + LSD_HDR;
+                    RA.scap = 0;
+                    RA.cap = 0;
+                    const int n_rec = __ldcg(F.arena + off) + __ldcg(F.arena + off + 1);
+                    lsd_release(F, pos, RA, n_rec);
+                    if (lane == 0) atomicAdd(&s_cnt[3], 1);
+                }
+                LsdView V;
+                V.rank = pos;
+                V.frontier = frontier;
+                const int s_addr = list[pos];
+                if (lane == 0) {
+                    F.st[pos] = LSD_ST_GROWING;
+                    __threadfence_block(); /* before any claim of this candidate can be seen (and its victim flag set) */
+                    atomicAdd(&s_cnt[1], 1);
+                }
+                __syncwarp();
+                int n_all = 0, has_line = 0;
+                float line[4] = {0.f, 0.f, 0.f, 0.f};
+                const int rc = lsd_process_seed(F, V, R, s_addr, A.min_reg_size, A.prec, A.p, A.scale, n_all, has_line, line);
+                __syncwarp();
+                bool keep = (rc == 0);
+                int off = 0;
+                if (keep) {
+                    const int need_ints = (LSD_HDR + n_all + 3) & ~3;
+                    if (lane == 0) off = atomicAdd(&s_arena_top, need_ints);
+                    off = __shfl_sync(FULL, off, 0);
+                    if (off + need_ints > F.arena_cap) {
+                        keep = false;
+                        if (lane == 0) s_fail = 1;
+                    }
+                }
+                if (rc == 2 && lane == 0) s_fail = 1;
+                if (keep) {
+                    for (int k = lane; k < n_all; k += 32) F.arena[off + LSD_HDR + k] = R.get(k);
+                    if (lane == 0) {
+                        F.arena[off + 0] = n_all;
+                        F.arena[off + 1] = 0;
+                        F.arena[off + 2] = has_line;
+                        F.arena[off + 3] = __float_as_int(line[0]);
+                        F.arena[off + 4] = __float_as_int(line[1]);
+                        F.arena[off + 5] = __float_as_int(line[2]);
+                        F.arena[off + 6] = __float_as_int(line[3]);
+                    }
+                    __threadfence_block();
+                    __syncwarp();
+                    int won = 1;
+                    if (lane == 0) won = (atomicCAS(F.st + pos, LSD_ST_GROWING, LSD_ST_CLEAN | ((uint32_t)off << 4)) == LSD_ST_GROWING) ? 1 : 0;
+                    keep = __shfl_sync(FULL, won, 0) != 0; /* lost: a lower rank overrode a pixel while this candidate was growing */
+                }
+                if (!keep) {
+                    lsd_release(F, pos, R, n_all);
+                    if (lane == 0) {
+                        F.st[pos] = LSD_ST_NEW;
+                        atomicAdd(&s_cnt[2], 1);
+                    }
+                    __syncwarp();
+                }
+            }
+        }
+        __syncthreads();
+        if (s_fail) break;
+        /* ---- advance the frontier over the resolved prefix */
+        int new_frontier = E;
+        for (int b = frontier; b < E; b += T) {
+            const int i = b + tid;
+            if (i < E) {
+                const uint32_t sw = __ldcg(F.st + i);
+                bool ok = ((sw & LSD_ST_MASK) == LSD_ST_CLEAN) && !(sw & LSD_ST_INVALID);
+                if (!ok) {
+                    const uint32_t c = lsd_ld_claim(F, list[i]);
+                    if (c != LSD_FREE && !(c & 1u)) {
+                        const int j = (int)(c >> 1);
+                        if (j < frontier)
+                            ok = true; /* used by a final region: the reference skips this seed */
+                        else if (j < i) {
+                            const uint32_t sj = __ldcg(F.st + j);
+                            ok = ((sj & LSD_ST_MASK) == LSD_ST_CLEAN) && !(sj & LSD_ST_INVALID); /* member of a region that becomes final with this prefix */
+                        }
+                    }
+                }
+                if (!ok) atomicMin(&s_first, i);
+            }
+            __syncthreads();
+            if (s_first < E) {
+                new_frontier = s_first;
+                break;
+            }
+        }
+        frontier = new_frontier;
+        __syncthreads();
+    }
+    if (s_fail) {
+        if (tid == 0) A.redo[f] = 1;
+        return;
+    }
+    /* ---- segments in rank order: ordered compaction of the records that carry one */
+    if (tid == 0) {
+        s_base_raw = 0;
+        s_base_out = 0;
+    }
+    __syncthreads();
+    float *raw = A.raw + (size_t)f * A.cap * 4;
+    float *out = A.out + (size_t)f * A.cap * 4;
+    for (int b = 0; b < n_list; b += T) {
+        const int i = b + tid;
+        bool has = false, kept = false;
+        float ln[4], fo[4];
+        if (i < n_list) {
+            const uint32_t sw = __ldcg(F.st + i);
+            if ((sw & LSD_ST_MASK) == LSD_ST_CLEAN) {
+                const int off = (int)(sw >> 4);
+                if (__ldcg(F.arena + off + 2)) {
+                    has = true;
+                    for (int k = 0; k < 4; k++) ln[k] = __int_as_float(__ldcg(F.arena + off + 3 + k));
+                    kept = lsd_keyline_filter(ln, A.img_w, A.img_h, A.line_length_thres, fo);
+                }
+            }
+        }
+        const unsigned mh = __ballot_sync(FULL, has), mk = __ballot_sync(FULL, kept);
+        if (lane == 0) s_warp_cnt[wid] = __popc(mh) | (__popc(mk) << 16);
+        __syncthreads();
+        int pre_r = s_base_raw, pre_o = s_base_out;
+        for (int k = 0; k < wid; k++) {
+            pre_r += s_warp_cnt[k] & 0xffff;
+            pre_o += s_warp_cnt[k] >> 16;
+        }
+        if (has) {
+            const int slot = pre_r + __popc(mh & ((1u << lane) - 1u));
+            if (slot < A.cap)
+                for (int k = 0; k < 4; k++) raw[4 * slot + k] = ln[k];
+        }
+        if (kept) {
+            const int slot = pre_o + __popc(mk & ((1u << lane) - 1u));
+            if (slot < A.cap)
+                for (int k = 0; k < 4; k++) out[4 * slot + k] = fo[k];
+        }
+        __syncthreads();
+        if (tid == 0) {
+            int tr = 0, to = 0;
+            for (int k = 0; k < LSD_NW; k++) {
+                tr += s_warp_cnt[k] & 0xffff;
+                to += s_warp_cnt[k] >> 16;
+            }
+            s_base_raw += tr;
+            s_base_out += to;
+        }
+        __syncthreads();
+    }
+    if (tid == 0) {
+        A.n_raw[f] = s_base_raw;
+        A.n_out[f] = s_base_out;
+        A.redo[f] = 0;
+        A.stats[4 * f + 0] = rounds;
+        A.stats[4 * f + 1] = s_cnt[1];
+        A.stats[4 * f + 2] = s_cnt[2];
+        A.stats[4 * f + 3] = s_cnt[3];
+    }
+}
+
+/* The plain seed loop, one warp per frame: redoes the frames the speculative kernel gave up on (capacity) and serves as its A/B
+ * reference (cs_set_profiling bit 7).  Claim words: FREE = unused, 0 = used. */
+__global__ void __launch_bounds__(32) k_lsd_grow_seq(LsdGrowArgs A)
 {
     const int f = blockIdx.x, lane = threadIdx.x;
-    const size_t npx = (size_t)W * H;
+    if (!A.redo[f]) return;
+    const size_t npx = (size_t)A.W * A.H;
     LsdFrame F;
-    F.W = W;
-    F.H = H;
-    F.angles = angles_all + f * npx;
-    F.modgrad = modgrad_all + f * npx;
-    F.cs_angle = cs_all + f * npx;
-    F.used = used_all + f * npx;
-    F.reg = reg_all + f * npx;
-    F.LOG_NT = LOG_NT;
-    const int32_t *list = list_all + f * npx;
-    const int n_list = list_len[f];
-    float *raw = raw_all + (size_t)f * cap * 4;
-    float *out = out_all + (size_t)f * cap * 4;
+    F.W = A.W;
+    F.H = A.H;
+    F.pix = A.pix + f * npx;
+    F.angf = A.angf + f * npx;
+    F.modgrad = A.modgrad + f * npx;
+    F.LOG_NT = A.LOG_NT;
+    F.st = nullptr;
+    F.arena = nullptr;
+    F.arena_cap = 0;
+    for (size_t i = lane; i < npx; i += 32) *lsd_claim_ptr(F, (int)i) = LSD_FREE;
+    __syncwarp();
+    LsdReg R;
+    R.s = nullptr;
+    R.g = A.arena + (size_t)f * A.arena_cap; /* the record arena is free in this mode: it holds the region list */
+    R.scap = 0;
+    R.cap = A.arena_cap;
+    LsdView V;
+    V.rank = -1;
+    V.frontier = 0;
+    const int32_t *list = A.list + f * npx;
+    const int n_list = A.list_len[f];
+    float *raw = A.raw + (size_t)f * A.cap * 4;
+    float *out = A.out + (size_t)f * A.cap * 4;
     int n_raw = 0, n_out = 0;
-    const double DENSITY_TH = 0.7, LOG_EPS = 0;
-    const float pre_boundary_thre = 10;
-
     for (int i0 = 0; i0 < n_list; i0 += 32) {
-        /* 32 list entries at a time: seeds whose pixel is already used or has no defined angle are skipped by ballot */
+        /* 32 list entries at a time: seeds whose pixel is already used are skipped by ballot */
         const int i = i0 + lane;
         int adx = 0;
         bool seed = false;
         if (i < n_list) {
             adx = list[i];
-            seed = (F.used[adx] == 0); /* the list holds pixels with a defined angle only */
+            seed = (lsd_ld_claim(F, adx) == LSD_FREE); /* the list holds pixels with a defined angle only */
         }
         unsigned todo = __ballot_sync(0xffffffffu, seed);
         while (todo) {
             const int sl = __ffs(todo) - 1;
             todo &= todo - 1;
             const int s_addr = __shfl_sync(0xffffffffu, adx, sl);
-            if (F.used[s_addr] != 0) continue; /* claimed by a region grown since the ballot */
-            int reg_size;
-            double reg_angle;
-            lsd_region_grow(F, s_addr, reg_size, reg_angle, prec);
-            if (reg_size < min_reg_size) continue;
-            LsdRect rec;
-            lsd_region2rect(F, reg_size, reg_angle, prec, p, rec);
-            if (!lsd_refine(F, reg_size, reg_angle, prec, p, rec, DENSITY_TH)) continue;
-            const double log_nfa = lsd_rect_improve(F, rec);
-            if (log_nfa <= LOG_EPS) continue;
-            rec.x1 += 0.5;
-            rec.y1 += 0.5;
-            rec.x2 += 0.5;
-            rec.y2 += 0.5;
-            rec.x1 /= scale;
-            rec.y1 /= scale;
-            rec.x2 /= scale;
-            rec.y2 /= scale;
-            float e[4] = {(float)rec.x1, (float)rec.y1, (float)rec.x2, (float)rec.y2};
-            if (lane == 0 && n_raw < cap) {
-                raw[4 * n_raw + 0] = e[0];
-                raw[4 * n_raw + 1] = e[1];
-                raw[4 * n_raw + 2] = e[2];
-                raw[4 * n_raw + 3] = e[3];
-            }
+            if (lsd_ld_claim(F, s_addr) != LSD_FREE) continue; /* claimed by a region grown since the ballot */
+            int n_all = 0, has_line = 0;
+            float line[4];
+            const int rc = lsd_process_seed(F, V, R, s_addr, A.min_reg_size, A.prec, A.p, A.scale, n_all, has_line, line);
+            if (rc || !has_line) continue; /* rc == 2 (a region larger than the whole arena) cannot happen: arena_cap >= W * H + 27 */
+            if (lane == 0 && n_raw < A.cap)
+                for (int k = 0; k < 4; k++) raw[4 * n_raw + k] = line[k];
             n_raw++;
-            /* checkLineExtremes + 10-px border rejection + length filter (LSDDetector.cpp:75-101,226-238; filter_lines) */
-            if (e[0] < 0) e[0] = 0;
-            if (e[0] >= img_w) e[0] = (float)img_w - 1.0f;
-            if (e[2] < 0) e[2] = 0;
-            if (e[2] >= img_w) e[2] = (float)img_w - 1.0f;
-            if (e[1] < 0) e[1] = 0;
-            if (e[1] >= img_h) e[1] = (float)img_h - 1.0f;
-            if (e[3] < 0) e[3] = 0;
-            if (e[3] >= img_h) e[3] = (float)img_h - 1.0f;
-            const float sx = e[0], sy = e[1], ex = e[2], ey = e[3];
-            if (((sx < pre_boundary_thre) && (ex < pre_boundary_thre)) || ((sx > img_w - pre_boundary_thre) && (ex > img_w - pre_boundary_thre)) ||
-                ((sy < pre_boundary_thre) && (ey < pre_boundary_thre)) || ((sy > img_h - pre_boundary_thre) && (ey > img_h - pre_boundary_thre)))
-                continue;
-            const double ddx = (double)(e[0] - e[2]), ddy = (double)(e[1] - e[3]);
-            const float line_length = (float)sqrt(ddx * ddx + ddy * ddy);
-            if (!(line_length > line_length_thres)) continue;
-            if (lane == 0 && n_out < cap) {
-                out[4 * n_out + 0] = sx;
-                out[4 * n_out + 1] = sy;
-                out[4 * n_out + 2] = ex;
-                out[4 * n_out + 3] = ey;
-            }
+            float fo[4];
+            if (!lsd_keyline_filter(line, A.img_w, A.img_h, A.line_length_thres, fo)) continue;
+            if (lane == 0 && n_out < A.cap)
+                for (int k = 0; k < 4; k++) out[4 * n_out + k] = fo[k];
             n_out++;
         }
     }
     if (lane == 0) {
-        n_raw_all[f] = n_raw;
-        n_out_all[f] = n_out;
+        A.n_raw[f] = n_raw;
+        A.n_out[f] = n_out;
     }
 }
 
@@ -856,7 +1308,7 @@ struct Buf {
 };
 
 struct LsdState {
-    Buf img, tmp, blur, scaled, modgrad, angles, csang, used, list, reg, maxg, cnt, llen, raw, nraw, out, nout;
+    Buf img, tmp, blur, scaled, modgrad, angf, pix, list, st, arena, spill, maxg, cnt, llen, raw, nraw, out, nout, redo, stats;
     int last_frames = 0, last_W = 0, last_H = 0, cap = 0;
 };
 
@@ -883,6 +1335,7 @@ int lsd_run(cs_ctx *c, const uint8_t *imgs, bool imgs_on_device, int n_frames, i
     if (W < 2 || H < 2) return cs_ctx_fail(c, CS_ERR_INVALID_ARG, "image too small for LSD");
     const size_t px = (size_t)n_frames * w * h, spx = (size_t)n_frames * W * H;
     const int n_chunks = (H - 1 + LSD_CHUNK_ROWS - 1) / LSD_CHUNK_ROWS;
+    const int arena_cap = (int)(((size_t)W * H * 2 + 64 + 3) & ~(size_t)3); /* ints per frame */
     int rc;
     const uint8_t *d_img = imgs;
     if (!imgs_on_device) {
@@ -892,11 +1345,13 @@ int lsd_run(cs_ctx *c, const uint8_t *imgs, bool imgs_on_device, int n_frames, i
         d_img = (const uint8_t *)S.img.p;
     }
     if ((rc = ensure(c, S.tmp, px * 8)) || (rc = ensure(c, S.blur, px * 8)) || (rc = ensure(c, S.scaled, spx * 8)) ||
-        (rc = ensure(c, S.modgrad, spx * 8)) || (rc = ensure(c, S.angles, spx * 8)) || (rc = ensure(c, S.csang, spx * 8)) || (rc = ensure(c, S.used, spx)) ||
-        (rc = ensure(c, S.list, spx * 4)) || (rc = ensure(c, S.reg, spx * 4)) || (rc = ensure(c, S.maxg, (size_t)n_frames * 8)) ||
+        (rc = ensure(c, S.modgrad, spx * 8)) || (rc = ensure(c, S.angf, spx * 4)) || (rc = ensure(c, S.pix, spx * 16)) ||
+        (rc = ensure(c, S.list, spx * 4)) || (rc = ensure(c, S.st, spx * 4)) || (rc = ensure(c, S.arena, (size_t)n_frames * arena_cap * 4)) ||
+        (rc = ensure(c, S.spill, (size_t)n_frames * LSD_NW * LSD_SPILL * 4)) || (rc = ensure(c, S.maxg, (size_t)n_frames * 8)) ||
         (rc = ensure(c, S.cnt, (size_t)n_frames * n_chunks * LSD_NBINS * 4)) || (rc = ensure(c, S.llen, (size_t)n_frames * 4)) ||
         (rc = ensure(c, S.raw, (size_t)n_frames * cap * 16)) || (rc = ensure(c, S.nraw, (size_t)n_frames * 4)) ||
-        (rc = ensure(c, S.out, (size_t)n_frames * cap * 16)) || (rc = ensure(c, S.nout, (size_t)n_frames * 4)))
+        (rc = ensure(c, S.out, (size_t)n_frames * cap * 16)) || (rc = ensure(c, S.nout, (size_t)n_frames * 4)) ||
+        (rc = ensure(c, S.redo, (size_t)n_frames * 4)) || (rc = ensure(c, S.stats, (size_t)n_frames * 16)))
         return rc;
     /* host-side constants of flsd (lsd.cpp:445-447,468-469), evaluated with libm like the reference */
     const double ANG_TH = 22.5, QUANT = 2.0;
@@ -905,21 +1360,47 @@ int lsd_run(cs_ctx *c, const uint8_t *imgs, bool imgs_on_device, int n_frames, i
     const int min_reg_size = (int)(-LOG_NT / std::log10(p));
 
     cudaMemsetAsync(S.maxg.p, 0, (size_t)n_frames * 8, st);
-    cudaMemsetAsync(S.used.p, 0, spx, st);
+    cudaMemsetAsync(S.st.p, 0, spx * 4, st);
+    cudaMemsetAsync(S.stats.p, 0, (size_t)n_frames * 16, st);
     k_lsd_hblur<<<grid_for((int64_t)px), 256, 0, st>>>(d_img, n_frames, w, h, stride, channels, (double *)S.tmp.p);
     k_lsd_vblur<<<grid_for((int64_t)px), 256, 0, st>>>((const double *)S.tmp.p, n_frames, w, h, (double *)S.blur.p);
     k_lsd_resize<<<grid_for((int64_t)spx), 256, 0, st>>>((const double *)S.blur.p, n_frames, w, h, W, H, 1. / SCALE, (double *)S.scaled.p);
-    k_lsd_grad<<<grid_for((int64_t)spx), 256, 0, st>>>((const double *)S.scaled.p, n_frames, W, H, rho, (double *)S.modgrad.p, (double *)S.angles.p,
-                                                       (float2 *)S.csang.p, (unsigned long long *)S.maxg.p);
-    k_lsd_hist<<<n_frames * n_chunks, 256, 0, st>>>((const double *)S.modgrad.p, (const double *)S.angles.p, W, H, n_chunks, (const unsigned long long *)S.maxg.p, (int32_t *)S.cnt.p);
+    k_lsd_grad<<<grid_for((int64_t)spx), 256, 0, st>>>((const double *)S.scaled.p, n_frames, W, H, rho, (double *)S.modgrad.p, (float *)S.angf.p,
+                                                       (uint4 *)S.pix.p, (unsigned long long *)S.maxg.p);
+    k_lsd_hist<<<n_frames * n_chunks, 256, 0, st>>>((const double *)S.modgrad.p, (const float *)S.angf.p, W, H, n_chunks, (const unsigned long long *)S.maxg.p, (int32_t *)S.cnt.p);
     k_lsd_scan<<<n_frames, LSD_NBINS, 0, st>>>(n_chunks, (int32_t *)S.cnt.p, (int32_t *)S.llen.p);
-    k_lsd_scatter<<<n_frames * n_chunks, 32, 0, st>>>((const double *)S.modgrad.p, (const double *)S.angles.p, W, H, n_chunks, (const unsigned long long *)S.maxg.p,
+    k_lsd_scatter<<<n_frames * n_chunks, 32, 0, st>>>((const double *)S.modgrad.p, (const float *)S.angf.p, W, H, n_chunks, (const unsigned long long *)S.maxg.p,
                                                       (const int32_t *)S.cnt.p, (int32_t *)S.list.p);
-    k_lsd_grow<<<n_frames, 32, 0, st>>>(W, H, w, h, (const double *)S.angles.p, (const double *)S.modgrad.p, (const float2 *)S.csang.p, (uint8_t *)S.used.p,
-                                        (int32_t *)S.reg.p,
-                                        (const int32_t *)S.list.p, (const int32_t *)S.llen.p, LOG_NT, min_reg_size, prec, p, SCALE, line_length_thres,
-                                        (float *)S.raw.p, (int32_t *)S.nraw.p, (float *)S.out.p, (int32_t *)S.nout.p, cap);
-    cs_ctx_count_launches(c, 8);
+    LsdGrowArgs A;
+    A.W = W;
+    A.H = H;
+    A.img_w = w;
+    A.img_h = h;
+    A.pix = (uint4 *)S.pix.p;
+    A.angf = (const float *)S.angf.p;
+    A.modgrad = (const double *)S.modgrad.p;
+    A.list = (const int32_t *)S.list.p;
+    A.list_len = (const int32_t *)S.llen.p;
+    A.st = (uint32_t *)S.st.p;
+    A.arena = (int32_t *)S.arena.p;
+    A.arena_cap = arena_cap;
+    A.spill = (int32_t *)S.spill.p;
+    A.LOG_NT = LOG_NT;
+    A.min_reg_size = min_reg_size;
+    A.prec = prec;
+    A.p = p;
+    A.scale = SCALE;
+    A.line_length_thres = line_length_thres;
+    A.raw = (float *)S.raw.p;
+    A.n_raw = (int32_t *)S.nraw.p;
+    A.out = (float *)S.out.p;
+    A.n_out = (int32_t *)S.nout.p;
+    A.cap = cap;
+    A.redo = (int32_t *)S.redo.p;
+    A.stats = (int32_t *)S.stats.p;
+    k_lsd_grow_par<<<n_frames, LSD_NW * 32, 0, st>>>(A, cs_ctx_seq_lines(c));
+    k_lsd_grow_seq<<<n_frames, 32, 0, st>>>(A);
+    cs_ctx_count_launches(c, 9);
     if (cudaGetLastError() != cudaSuccess) return cs_ctx_fail(c, CS_ERR_CUDA, "LSD kernel launch failed: %s", cudaGetErrorString(cudaGetLastError()));
     S.last_frames = n_frames;
     S.last_W = W;
@@ -952,7 +1433,8 @@ int cs_lsd_run_device(cs_ctx *c, const uint8_t *d_imgs, int n_frames, int w, int
 void cs_lsd_destroy(void *state)
 {
     LsdState *S = (LsdState *)state;
-    Buf *all[] = {&S->img, &S->tmp, &S->blur, &S->scaled, &S->modgrad, &S->angles, &S->csang, &S->used, &S->list, &S->reg, &S->maxg, &S->cnt, &S->llen, &S->raw, &S->nraw, &S->out, &S->nout};
+    Buf *all[] = {&S->img, &S->tmp, &S->blur, &S->scaled, &S->modgrad, &S->angf, &S->pix, &S->list, &S->st, &S->arena, &S->spill, &S->maxg, &S->cnt,
+                  &S->llen, &S->raw, &S->nraw, &S->out, &S->nout, &S->redo, &S->stats};
     for (Buf *b : all)
         if (b->p) cudaFree(b->p);
     delete S;
@@ -1021,7 +1503,12 @@ int cs_debug_lsd(cs_ctx *c, int frame, int32_t *scaled_wh, double *scaled, doubl
     }
     if (scaled) cudaMemcpy(scaled, (double *)S->scaled.p + frame * npx, npx * 8, cudaMemcpyDeviceToHost);
     if (modgrad) cudaMemcpy(modgrad, (double *)S->modgrad.p + frame * npx, npx * 8, cudaMemcpyDeviceToHost);
-    if (angles) cudaMemcpy(angles, (double *)S->angles.p + frame * npx, npx * 8, cudaMemcpyDeviceToHost);
+    if (angles) {
+        /* the level-line angle map as the reference holds it: (double)fastAtan2 * DEG2RAD, NOTDEF = -1024 (the product is IEEE-exact on either side) */
+        std::vector<float> deg(npx);
+        cudaMemcpy(deg.data(), (float *)S->angf.p + frame * npx, npx * 4, cudaMemcpyDeviceToHost);
+        for (size_t i = 0; i < npx; i++) angles[i] = deg[i] < 0.f ? LSD_NOTDEF : (double)deg[i] * LSD_DEG2RAD;
+    }
     int32_t ll = 0;
     cudaMemcpy(&ll, (int32_t *)S->llen.p + frame, 4, cudaMemcpyDeviceToHost);
     if (list_len) *list_len = ll;
@@ -1030,6 +1517,20 @@ int cs_debug_lsd(cs_ctx *c, int frame, int32_t *scaled_wh, double *scaled, doubl
     cudaMemcpy(&nr, (int32_t *)S->nraw.p + frame, 4, cudaMemcpyDeviceToHost);
     if (n_raw) *n_raw = nr;
     if (raw_lines) cudaMemcpy(raw_lines, (float *)S->raw.p + (size_t)frame * S->cap * 4, (size_t)std::min(nr, std::min(cap_raw, S->cap)) * 16, cudaMemcpyDeviceToHost);
+    return cudaGetLastError() == cudaSuccess ? CS_OK : cs_ctx_fail(c, CS_ERR_CUDA, "debug copy failed");
+}
+
+/* diagnostics of the speculative seed loop of the last run: per frame {rounds, candidates processed, refused or lost, re-grown after an
+ * override} and whether the sequential kernel redid the frame */
+int cs_debug_lsd_stats(cs_ctx *c, int32_t *stats4, int32_t *redo, int n_frames)
+{
+    if (!c) return CS_ERR_INVALID_ARG;
+    LsdState *S = state_of(c);
+    if (n_frames > S->last_frames) return cs_ctx_fail(c, CS_ERR_INVALID_ARG, "more frames than the last run held");
+    cudaSetDevice(cs_ctx_device(c));
+    cudaStreamSynchronize(cs_ctx_stream(c));
+    if (stats4) cudaMemcpy(stats4, S->stats.p, (size_t)n_frames * 16, cudaMemcpyDeviceToHost);
+    if (redo) cudaMemcpy(redo, S->redo.p, (size_t)n_frames * 4, cudaMemcpyDeviceToHost);
     return cudaGetLastError() == cudaSuccess ? CS_OK : cs_ctx_fail(c, CS_ERR_CUDA, "debug copy failed");
 }
 }

@@ -60,6 +60,12 @@ class line_lbd_detect(object):
                                        _lib.ptr(an, C.c_double), _lib.ptr(lst, C.c_int32), C.byref(ll), _lib.ptr(raw, C.c_float), C.byref(nr), cap))
         return dict(scaled=sc, modgrad=mg, angles=an, list=lst[:ll.value].copy(), raw_lines=raw[:nr.value].copy())
 
+    def seed_loop_stats(self, n_frames):
+        """Diagnostics of the last LSD run: (n_frames x 4 int32 {rounds, processed, refused, re-grown}, redo flags)."""
+        st, redo = np.zeros((n_frames, 4), np.int32), np.zeros(n_frames, np.int32)
+        self._ctx.check(self._ctx.L.cs_debug_lsd_stats(self._ctx.h, _lib.ptr(st, C.c_int32), _lib.ptr(redo, C.c_int32), n_frames))
+        return st, redo
+
     def debug_frame_edlines(self, width, height, frame=0, cap=8192):
         """EDLineDetector's intermediate maps of one frame of the last use_LSD = False run (tests)."""
         L = self._ctx.L

@@ -1,6 +1,6 @@
 """Deterministic synthetic frames for tests and bench.py.
 
-Each frame: mid-grey noisy background, 20-40 clutter segments and one rendered shaded cuboid per 2D box
+Each frame: mid-grey noisy background, the tile joints of a ground-plane grid, 25-50 clutter segments and one rendered shaded cuboid per 2D box
 (standing on the ground plane, seen by a camera shaped like the reference's demo camera,
 detect_3d_cuboid/src/main.cpp:35-44, or the KITTI camera of orb_object_slam's launch files).
 Returned per frame: BGR image, camera-to-world T, N x 5 boxes [x y w h prob] (0-based, integer),
@@ -64,13 +64,44 @@ _FACES = [((0, 1, 2, 3), 90), ((4, 5, 6, 7), 200), ((0, 1, 5, 4), 140), ((2, 3, 
 _EDGES = [(0, 1), (1, 2), (2, 3), (3, 0), (4, 5), (5, 6), (6, 7), (7, 4), (0, 4), (1, 5), (2, 6), (3, 7)]
 
 
-def make_frame(rng, width=640, height=480, n_boxes=3, kind="indoor", min_box=110):
+def _floor_grid(rng, img, K, T, kind, lines):
+    """Tile joints of the ground plane (z = 0): two families of parallel world lines, drawn thin and low-contrast before the objects.
+    They give the line detectors the long converging segments of a real indoor / road scene (the fixture frame has 271 segments)."""
+    height, width = img.shape
+    yaw = rng.uniform(-np.pi / 4, np.pi / 4)
+    step = rng.uniform(0.55, 0.95) if kind != "kitti" else rng.uniform(2.0, 3.5)
+    far = 6.5 if kind != "kitti" else 35.0
+    near = 0.9 if kind != "kitti" else 3.0
+    c, s = np.cos(yaw), np.sin(yaw)
+    val = int(np.clip(110 + rng.choice([-1, 1]) * rng.uniform(28, 60), 0, 255))
+    for fam in range(2):
+        d = np.array([c, s, 0.0]) if fam == 0 else np.array([-s, c, 0.0])
+        n = np.array([-d[1], d[0], 0.0])
+        for k in np.arange(-far, far, step):
+            p0, p1 = n * (k + rng.uniform(-0.02, 0.02)) - d * far, n * k + d * far
+            pts = np.stack([p0 + (p1 - p0) * t for t in np.linspace(0, 1, 65)])
+            uv, depth = _project(K, T, pts)
+            ok = (depth > near) & (depth < far)
+            if ok.sum() < 2:
+                continue
+            idx = np.nonzero(ok)[0]
+            a, b = uv[idx[0]], uv[idx[-1]]
+            hit, q0, q1 = cv2.clipLine((0, 0, width, height), (int(round(a[0])), int(round(a[1]))), (int(round(b[0])), int(round(b[1]))))
+            if not hit:
+                continue
+            cv2.line(img, q0, q1, val, 1, cv2.LINE_AA)
+            lines.append([q0[0], q0[1], q1[0], q1[1]])
+
+
+def make_frame(rng, width=640, height=480, n_boxes=3, kind="indoor", min_box=110, clutter=(25, 51), floor=True):
     """One synthetic frame -> (bgr uint8 HxWx3, T 4x4, boxes Nx5, lines Mx4)."""
     K = camera_for(width, height, kind)
     T = _pose(rng, kind)
     img = np.clip(110 + rng.normal(0, 4, (height, width)), 0, 255).astype(np.uint8)
     lines = []
-    for _ in range(int(rng.integers(20, 41))):
+    if floor:
+        _floor_grid(rng, img, K, T, kind, lines)
+    for _ in range(int(rng.integers(clutter[0], clutter[1]))):
         x0, y0 = rng.uniform(0, width - 1), rng.uniform(0, height - 1)
         ang, ln = rng.uniform(0, np.pi), rng.uniform(20, 200)
         x1, y1 = np.clip(x0 + ln * np.cos(ang), 0, width - 1), np.clip(y0 + ln * np.sin(ang), 0, height - 1)
@@ -85,8 +116,8 @@ def make_frame(rng, width=640, height=480, n_boxes=3, kind="indoor", min_box=110
             dims = np.array([rng.uniform(3.5, 4.5), rng.uniform(1.5, 1.9), rng.uniform(1.2, 1.5)]) / 2  # lower than the 1.7 m camera so a top face is visible
             centre = np.array([rng.uniform(-6, 6), rng.uniform(5, 16), 0.0])
         else:
-            dims = np.array([rng.uniform(0.3, 1.2), rng.uniform(0.3, 1.2), rng.uniform(0.3, 1.5)]) / 2
-            centre = np.array([rng.uniform(-1.5, 1.5), rng.uniform(1.6, 4.5), 0.0])
+            dims = np.array([rng.uniform(0.45, 1.2), rng.uniform(0.45, 1.2), rng.uniform(0.7, 1.5)]) / 2
+            centre = np.array([rng.uniform(-1.3, 1.3), rng.uniform(1.7, 3.6), 0.0])
         yaw = rng.uniform(-np.pi, np.pi)
         Rz = np.array([[np.cos(yaw), -np.sin(yaw), 0], [np.sin(yaw), np.cos(yaw), 0], [0, 0, 1]])
         pts = (Rz @ (_BODY * dims).T).T + centre + np.array([0, 0, dims[2]])

@@ -185,7 +185,8 @@ int cs_stage_ms(cs_ctx *ctx, const char *stage, float *ms);
 /* bit 0: per-stage CUDA-event timing (adds event records only; the chain then stays on one stream).  Debug / A-B switches:
  * bit 2 fused hysteresis + wavefront distance transform, bit 3 CTA-wide sweep / selection kernels, bit 4 no high-priority
  * stream for the distance transform -> sweep -> selection tail, bit 5 raster-scan distance transform (one kernel) instead of the cone form,
- * bit 6 cone-form distance transform reading the edge bits from global memory (the path of ROIs whose bit plane exceeds 96 KB) */
+ * bit 6 cone-form distance transform reading the edge bits from global memory (the path of ROIs whose bit plane exceeds 96 KB),
+ * bit 7 the line detectors' plain sequential kernels (one warp per frame) instead of the ordered-speculation kernels */
 int cs_set_profiling(cs_ctx *ctx, int enable);
 
 /* debug: when several contexts run concurrently with profiling on, the offsets (ms) of the 8 stage starts and the end of ctx's last run
@@ -212,6 +213,9 @@ int cs_detect_lines_batch(cs_ctx *ctx, const uint8_t *imgs, int n_frames, int wi
 /* inspection of the last cs_detect_lines[_batch] run (tests): intermediate images of one frame; any pointer may be NULL */
 int cs_debug_lsd(cs_ctx *ctx, int frame, int32_t scaled_wh[2], double *scaled, double *modgrad, double *angles, int32_t *list,
                  int32_t *list_len, float *raw_lines, int32_t *n_raw, int cap_raw);
+/* diagnostics of the last LSD run's seed loop (lsd.cpp:478-535 as ordered speculation, cs_lsd.cu): per frame 4 values {rounds, candidates
+ * processed, candidates refused or lost, candidates re-grown after an override}; redo[f] = 1 when the sequential kernel redid the frame */
+int cs_debug_lsd_stats(cs_ctx *ctx, int32_t *stats4, int32_t *redo, int n_frames);
 /* same for the EDLines flavour (use_LSD = 0): EDLineDetector's maps (binary_descriptor.cpp:1617-1666: blurred image, dxImg_, dyImg_,
  * gImgWO_ / 4, dirImg_), the anchors in scan order as y * width + x, the edge map after smart routing, the segments before the length filter */
 int cs_debug_edlines(cs_ctx *ctx, int frame, uint8_t *blur, int16_t *dx, int16_t *dy, int16_t *g, uint8_t *dir, int32_t *anchors,

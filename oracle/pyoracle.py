@@ -291,3 +291,51 @@ def edl_detect(img, line_length_thres=50.0, cap=8192, want_stages=False):
         st["anchors"] = st["anchors"][:na.value].copy()
         res["stages"] = st
     return res
+
+
+# ------------------------------------------------------------------------------------------- batch driver (OpenMP, no Python in the loop)
+def max_threads():
+    return int(lib().orc_max_threads())
+
+
+def detect_frames_batch(imgs, K, Ts, boxes_list, lines_list=None, params=None, line_mode=0, line_length_thres=15.0, n_threads=None,
+                        want_records=False):
+    """oracle/batch_oracle.cpp: the per-frame path (detect_filter_lines when line_mode > 0, then detect_cuboid) over a batch,
+    frames over `n_threads` host threads with a static OpenMP schedule.  Returns dict(n_valid, n_cand, n_lines per frame
+    [, records, counts])."""
+    L = lib()
+    if params is None:
+        params = default_params()
+    imgs = np.ascontiguousarray(imgs, np.uint8)
+    F, h, w = imgs.shape[:3]
+    ch = 1 if imgs.ndim == 3 else imgs.shape[3]
+    K = np.ascontiguousarray(K, np.float64).reshape(3, 3)
+    Ts = np.ascontiguousarray(Ts, np.float64).reshape(F, 16)
+    box_off = np.zeros(F + 1, np.int32)
+    box_off[1:] = np.cumsum([len(b) for b in boxes_list])
+    boxes = np.ascontiguousarray(np.concatenate([np.asarray(b, np.float64).reshape(-1, 5) for b in boxes_list]) if box_off[-1] else np.zeros((0, 5)))
+    if line_mode == 0:
+        line_off = np.zeros(F + 1, np.int32)
+        line_off[1:] = np.cumsum([len(l) for l in lines_list])
+        lines = np.ascontiguousarray(np.concatenate([np.asarray(l, np.float64).reshape(-1, 4) for l in lines_list]) if line_off[-1] else np.zeros((0, 4)))
+        lines_p, off_p = _p(lines, C.c_double), _p(line_off, C.c_int32)
+    else:
+        lines_p, off_p = None, None
+    topk = max(int(params.max_cuboid_num), 1)
+    nb = max(int(box_off[-1]), 1)
+    out = np.zeros((nb, topk), CUBOID_DTYPE) if want_records else None
+    counts = np.zeros(nb, np.int32) if want_records else None
+    nv, nc, nl = np.zeros(F, np.int64), np.zeros(F, np.int64), np.zeros(F, np.int32)
+    if n_threads is None:
+        n_threads = max_threads()
+    L.orc_detect_frames_batch.restype = C.c_int
+    rc = L.orc_detect_frames_batch(_p(imgs, C.c_uint8), F, w, h, w * ch, ch, _p(K, C.c_double), _p(Ts, C.c_double), _p(boxes, C.c_double),
+                                   _p(box_off, C.c_int32), lines_p, off_p, int(line_mode), C.c_float(line_length_thres), C.byref(params),
+                                   int(n_threads), topk, out.ctypes.data_as(C.POINTER(Cuboid)) if want_records else None,
+                                   _p(counts, C.c_int) if want_records else None, _p(nv, C.c_int64), _p(nc, C.c_int64), _p(nl, C.c_int32))
+    if rc != 0:
+        raise RuntimeError("orc_detect_frames_batch failed: %d" % rc)
+    res = dict(n_valid=nv, n_cand=nc, n_lines=nl)
+    if want_records:
+        res["records"], res["counts"], res["box_off"] = out, counts, box_off
+    return res
