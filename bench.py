@@ -85,6 +85,35 @@ def physical_cores():
     return os.cpu_count() or 1
 
 
+def cpu_quota():
+    """CPUs' worth of time the container may use (cgroup cpu.max / cfs quota), or None when unlimited."""
+    try:
+        q, per = open("/sys/fs/cgroup/cpu.max").read().split()
+        if q != "max":
+            return float(q) / float(per)
+    except (OSError, ValueError):
+        pass
+    try:
+        q = float(open("/sys/fs/cgroup/cpu/cpu.cfs_quota_us").read())
+        per = float(open("/sys/fs/cgroup/cpu/cpu.cfs_period_us").read())
+        if q > 0:
+            return q / per
+    except (OSError, ValueError):
+        pass
+    return None
+
+
+def cpu_thread_choices():
+    """Thread counts worth trying for the CPU arm: the logical CPUs, unless a cgroup quota caps the process below that (more runnable threads
+    than the quota allows only get throttled): then the quota and twice the quota."""
+    logical = os.cpu_count() or 1
+    q = cpu_quota()
+    if q is None or q >= logical:
+        return sorted({logical, physical_cores()})
+    base = max(1, int(round(q)))
+    return sorted({min(logical, base), min(logical, 2 * base)})
+
+
 def cpu_model():
     try:
         for ln in open("/proc/cpuinfo"):
@@ -166,13 +195,20 @@ def run_reference_arm(args, rank, world):
         return
     from oracle import pyoracle as O
     wl = make_workload(args.workload, 0)
-    threads = os.cpu_count() or 1
     phys = physical_cores()
     dt1, _, _, _ = cpu_run(wl, min(wl["F"], 2), 1)
     per_frame = dt1 / min(wl["F"], 2)
     n = int(max(1, min(wl["F"], 4.0 * phys / max(per_frame, 1e-4))))  # about 4 s of wall clock per step at most
-    for _ in range(max(1, min(args.warmup, 2))):
-        cpu_run(wl, max(1, n // 4), threads)
+    # all the host threads the process can use: the best of the candidate thread counts (cgroup quota aware), measured
+    best = None
+    for th in cpu_thread_choices():
+        cpu_run(wl, n, th)  # the same frames on the same threads: warms every thread's malloc arena
+        dt = cpu_run(wl, n, th)[0]
+        if best is None or dt < best[0]:
+            best = (dt, th)
+    threads = best[1]
+    for _ in range(max(0, min(args.warmup, 2) - 1)):
+        cpu_run(wl, n, threads)
     tot_t = tot_v = tot_c = tot_l = 0.0
     for _ in range(args.steps):
         dt, v, c, l = cpu_run(wl, n, threads)
@@ -190,8 +226,9 @@ def run_reference_arm(args, rank, world):
                    "sample_frames_per_step": n, "segments_per_frame_M": tot_l / (n * args.steps),
                    "note": "CPU oracle port of the reference algorithm (the reference itself needs Eigen/OpenCV C++/ROS and cannot be "
                            "compiled on this image); oracle/batch_oracle.cpp, one frame per loop iteration, static schedule, openmp=%d" % O.lib().orc_has_openmp()},
-        "cpu_baseline": {"value": val, "unit": "proposals/s", "cores": threads, "physical_cores": phys, "cpu": cpu_model(), "kind": "port",
-                         "one_core_frames_per_s": 1.0 / per_frame,
+        "cpu_baseline": {"value": val, "unit": "proposals/s", "cores": threads, "physical_cores": phys, "logical_cpus": os.cpu_count(),
+                         "cgroup_cpu_quota": cpu_quota(), "cpu": cpu_model(), "kind": "port", "one_core_frames_per_s": 1.0 / per_frame,
+                         "scaling_vs_one_core": fps * per_frame,
                          "sample": "%d of %d frames per step, line detection + detect_cuboid per frame, %d threads" % (n, wl["F"], threads)},
         "e2e": {"value": val, "unit": "proposals/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -418,17 +455,22 @@ def run_ours(args, rank, world, local_rank):
     cpu = None
     if world == 1 and not args.no_cpu:
         from oracle import pyoracle as O
-        threads, phys = os.cpu_count() or 1, physical_cores()
-        dt1, v1, _, _ = cpu_run(wl, min(F, 2), 1)
-        per_frame = dt1 / min(F, 2)
+        phys = physical_cores()
+        dt1, v1, _, _ = cpu_run(wl, min(F, 4), 1)
+        per_frame = dt1 / min(F, 4)
         n = int(max(1, min(F, 10.0 * phys / max(per_frame, 1e-4))))
-        cpu_run(wl, max(1, n // 8), threads)
-        dt, v, c, l = cpu_run(wl, n, threads)
-        dtp, vp, _, _ = cpu_run(wl, n, phys) if phys != threads else (dt, v, c, l)
-        cpu = {"value": v / dt, "unit": "proposals/s", "cores": threads, "physical_cores": phys, "cpu": cpu_model(), "kind": "port",
-               "frames_per_s": n / dt, "one_core_value": v1 / dt1, "one_core_frames_per_s": 1.0 / per_frame,
-               "physical_cores_value": vp / dtp, "scaling_vs_one_core": (v / dt) / (v1 / dt1), "openmp": int(O.lib().orc_has_openmp()),
-               "sample": "%d of %d frames of this workload, LSD line detection + detect_cuboid per frame, static schedule, %d threads" % (n, F, threads)}
+        tried = {}
+        for th in cpu_thread_choices():
+            cpu_run(wl, n, th)  # warm-up on every thread
+            tried[th] = min((cpu_run(wl, n, th) for _ in range(2)), key=lambda r: r[0])
+        threads = min(tried, key=lambda t: tried[t][0])
+        dt, v, c, l = tried[threads]
+        cpu = {"value": v / dt, "unit": "proposals/s", "cores": threads, "physical_cores": phys, "logical_cpus": os.cpu_count(), "cgroup_cpu_quota": cpu_quota(),
+               "cpu": cpu_model(), "kind": "port", "frames_per_s": n / dt, "one_core_value": v1 / dt1, "one_core_frames_per_s": 1.0 / per_frame,
+               "scaling_vs_one_core": (v / dt) / (v1 / dt1), "frames_per_s_by_threads": {str(t): n / r[0] for t, r in tried.items()},
+               "openmp": int(O.lib().orc_has_openmp()),
+               "sample": "%d of %d frames of this workload, LSD line detection + detect_cuboid per frame, static schedule, %d threads (the best of %s; "
+                         "the box caps the process at %s CPUs' worth of time)" % (n, F, threads, sorted(tried), cpu_quota())}
 
     line = {
         "metric": "scored cuboid proposals/s", "value": value, "unit": "proposals/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),

@@ -50,6 +50,7 @@ struct cs_ctx {
     bool online_lines = false; /* lines come from the line detector run on the uploaded frames */
     cs_line_params line_prm;
     int online_cap = 1024;
+    const int32_t *d_online_counts = nullptr; /* per-frame segment counts of the last online run (device) */
 
     /* host tables built by build_tables() */
     std::vector<CsFrame> frames;
@@ -226,9 +227,13 @@ int build_tables(cs_ctx *c)
         cshost::linespace_d(yaw_init - p.yaw_half_range_deg / 180.0 * M_PI, yaw_init + p.yaw_half_range_deg / 180.0 * M_PI,
                             p.yaw_step_deg / 180.0 * M_PI, ys);
         if ((int)ys.size() > CS_MAX_YAW) return fail(c, CS_ERR_CAPACITY, "too many yaw samples (%zu)", ys.size());
-        fr.yaw_off = (int32_t)c->yaws.size();
+        fr.yaw_off = (int32_t)(c->yaws.size() / 3); /* entries of {yaw, cos, sin}: the reference takes both from libm on the host (object_3d_util.cpp:604-606,44) */
         fr.n_yaw = (int32_t)ys.size();
-        c->yaws.insert(c->yaws.end(), ys.begin(), ys.end());
+        for (double yv : ys) {
+            c->yaws.push_back(yv);
+            c->yaws.push_back(std::cos(yv));
+            c->yaws.push_back(std::sin(yv));
+        }
         fr.line_off = c->h_line_off[f];
         fr.n_lines = c->h_line_off[f + 1] - c->h_line_off[f];
 
@@ -421,6 +426,7 @@ int run_batch(cs_ctx *c, bool sync)
                                     c->line_prm.line_length_thres, c->online_cap, &d_lines_f32, &d_nlines)))
             return rc;
     }
+    c->d_online_counts = d_nlines;
     /* fork: the per-ROI line selection / merging only needs the lines and the job table */
     cudaEventRecord(c->ev_fork, st);
     cudaStreamWaitEvent(c->stream2, c->ev_fork, 0);
@@ -849,6 +855,13 @@ int cs_batch_stats_get(cs_ctx *c, cs_batch_stats *s)
         CS_CUDA(c, cudaMemcpyAsync(jc.data(), c->d_jcounts.p, jc.size() * 4, cudaMemcpyDeviceToHost, c->stream));
         CS_CUDA(c, cudaStreamSynchronize(c->stream));
         for (size_t j = 0; j < c->jobs.size(); j++) s->n_valid += jc[j * 2];
+    }
+    if (c->online_lines && c->d_online_counts && c->n_frames > 0) { /* segments the line detector handed to the cuboid stage */
+        std::vector<int32_t> nl(c->n_frames);
+        CS_CUDA(c, cudaMemcpyAsync(nl.data(), c->d_online_counts, nl.size() * 4, cudaMemcpyDeviceToHost, c->stream));
+        CS_CUDA(c, cudaStreamSynchronize(c->stream));
+        s->n_lines_in = 0;
+        for (int32_t v : nl) s->n_lines_in += v;
     }
     c->stats = *s;
     return CS_OK;

@@ -6,6 +6,7 @@
 #ifndef CS_GEOM_CUH
 #define CS_GEOM_CUH
 
+#include "cs_pmath.h"
 #include <cuda_runtime.h>
 #include <math.h>
 #include <stdint.h>
@@ -110,9 +111,10 @@ __device__ __forceinline__ D2 g_intersect(D2 p1s, D2 p1e, D2 p2s, D2 p2e)
 }
 
 /* getVanishingPoints (object_3d_util.cpp:602-607): vps[0..2] */
-__device__ __forceinline__ void g_vanishing_points(const double *KinvR, double yaw, D2 *vps)
+/* ycs: one entry of the yaw table = {yaw, cos(yaw), sin(yaw)}, the cosine and sine taken on the host with libm like the reference does */
+__device__ __forceinline__ void g_vanishing_points(const double *KinvR, const double *ycs, D2 *vps)
 {
-    const double c = cos(yaw), s = sin(yaw);
+    const double c = ycs[1], s = ycs[2];
     double h0, h1, h2;
     h0 = (KinvR[0] * c + KinvR[1] * s) + KinvR[2] * 0.0;
     h1 = (KinvR[3] * c + KinvR[4] * s) + KinvR[5] * 0.0;
@@ -250,7 +252,7 @@ __device__ __forceinline__ double g_angle_error(const double *vp_angles, int con
             for (int ee = 0; ee < 2; ee++) {
                 const int i0 = (config_id == 1) ? c_vpe1[vp_id][2 * ee] : c_vpe2[vp_id][2 * ee];
                 const int i1 = (config_id == 1) ? c_vpe1[vp_id][2 * ee + 1] : c_vpe2[vp_id][2 * ee + 1];
-                const double box_edge_angle = g_normalize_to_pi(atan2(c[i1].y - c[i0].y, c[i1].x - c[i0].x));
+                const double box_edge_angle = g_normalize_to_pi(cs_pm_atan2(c[i1].y - c[i0].y, c[i1].x - c[i0].x));
                 double best = 100;
                 for (int i = 0; i < nv; i++) {
                     double t = fabs(box_edge_angle - valid[i]);
@@ -279,9 +281,10 @@ __device__ __forceinline__ void g_plane_hit(const double *T, const double *invK,
 }
 
 /* change_2d_corner_to_3d_object (object_3d_util.cpp:610-648) */
-__device__ inline void g_lift_to_3d(const D2 *c, double config_id, double vp1pos, double yaw, const double *ground, const double *T,
+__device__ inline void g_lift_to_3d(const D2 *c, double config_id, double vp1pos, const double *ycs, const double *ground, const double *T,
                                     const double *invK, cs_cuboid_rec &o)
 {
+    const double yaw = ycs[0]; /* {yaw, cos(yaw), sin(yaw)} from the host-built yaw table */
     double g[4][3];
     for (int i = 0; i < 4; i++) g_plane_hit(T, invK, ground, c[4 + i], g[i]);
     double dx = g[0][0] - g[3][0], dy = g[0][1] - g[3][1], dz = g[0][2] - g[3][2];
@@ -321,7 +324,7 @@ __device__ inline void g_lift_to_3d(const D2 *c, double config_id, double vp1pos
         o.box_corners_2d[1 * 8 + i] = (int)c[src].y;
     }
     const double body[3][8] = {{1, 1, -1, -1, 1, 1, -1, -1}, {1, -1, -1, 1, 1, -1, -1, 1}, {-1, -1, -1, -1, 1, 1, 1, 1}};
-    const double cy = cos(yaw), sy = sin(yaw);
+    const double cy = ycs[1], sy = ycs[2];
     const double rot[9] = {cy, -sy, 0, sy, cy, 0, 0, 0, 1};
     double S[16];
     for (int i = 0; i < 16; i++) S[i] = 0;

@@ -14,6 +14,7 @@
  * so the number of pair tests is O(m^2 + merges*m) instead of O(merges*m^2), and every round of
  * tests is spread across the CTA with the first hit selected by an atomicMin on (row,col).
  */
+#include "cs_pmath.h"
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -55,7 +56,7 @@ __device__ __forceinline__ bool merge_test(const LineSet &L, int s1, int s2, dou
         mex = L.x2[s2];
         mey = L.y2[s2];
     }
-    merged_angle = atan2(mey - msy, mex - msx);
+    merged_angle = cs_pm_atan2(mey - msy, mex - msx);
     const double temp = fabs(L.ang[s1] - merged_angle);
     const double merge_angle_diff = dmin(temp, CS_PI - temp);
     return merge_angle_diff < angle_thre;
@@ -132,7 +133,7 @@ __global__ void __launch_bounds__(LN_THREADS) k_roi_lines(const CsJob *__restric
                 L.y1[slot] = y1;
                 L.x2[slot] = x2;
                 L.y2[slot] = y2;
-                L.ang[slot] = atan2(y2 - y1, x2 - x1);
+                L.ang[slot] = cs_pm_atan2(y2 - y1, x2 - x1);
             }
         }
         __syncthreads();

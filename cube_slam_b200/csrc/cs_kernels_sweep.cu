@@ -10,6 +10,7 @@
  * FP64 throughout (compiled -fmad=false); the only float32 arithmetic is the dist-map running sum,
  * which the reference also does in float32 and in the same order.
  */
+#include "cs_pmath.h"
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -61,7 +62,7 @@ __device__ __forceinline__ void vp_support_warp(const SweepShared &S, int n_line
         inl[k] = false;
         raw[k] = 0;
         if (e < n_lines) {
-            raw[k] = atan2(S.midy[e] - vp.y, S.midx[e] - vp.x);
+            raw[k] = cs_pm_atan2(S.midy[e] - vp.y, S.midx[e] - vp.x);
             const double nrm = g_normalize_to_pi(raw[k]);
             double d = fabs(S.ang[e] - nrm);
             d = g_min(d, CS_PI - d);
@@ -138,7 +139,7 @@ __global__ void __launch_bounds__(SW_THREADS) k_sweep_score(const CsJob *__restr
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const int n_lines = line_counts[bp.x * 2 + 1];
     const int n_yaw = fr.n_yaw, n_top = jb.n_top;
-    const double *yaws = yaw_table + fr.yaw_off;
+    const double *yaws = yaw_table + 3 * (size_t)fr.yaw_off; /* {yaw, cos, sin} per entry */
 
     /* the ROI's merged line set -> shared memory */
     {
@@ -159,7 +160,7 @@ __global__ void __launch_bounds__(SW_THREADS) k_sweep_score(const CsJob *__restr
     for (int y0 = 0; y0 < n_yaw; y0 += YC) {
         const int yc = min(YC, n_yaw - y0);
         __syncthreads();
-        if (tid < yc) g_vanishing_points(pose.KinvR, yaws[y0 + tid], S.vps[tid]);
+        if (tid < yc) g_vanishing_points(pose.KinvR, yaws + 3 * (y0 + tid), S.vps[tid]);
         __syncthreads();
         for (int t = wid; t < yc * 3; t += SW_WARPS) {
             const int yi = t / 3, vp_id = t - yi * 3;
@@ -281,7 +282,7 @@ __device__ __forceinline__ int block_excl_scan(int v, int *s_warp, int &total)
 
 /* rebuild the 8 corners of valid proposal `cand` (index inside its job) -- same code path as the sweep */
 __device__ __forceinline__ bool rebuild_corners(const CsJob &jb, const CsFrame &fr, const CsPose *poses, const double *yaw_table,
-                                                const cs_cuboid_params &prm, int cand, D2 *c, int &vp1pos, int &config_id, double &yaw,
+                                                const cs_cuboid_params &prm, int cand, D2 *c, int &vp1pos, int &config_id, const double *&ycs,
                                                 int &pose_id, int &top_id)
 {
     const int per_pose = fr.n_yaw * jb.n_top * 2;
@@ -291,9 +292,9 @@ __device__ __forceinline__ bool rebuild_corners(const CsJob &jb, const CsFrame &
     r -= yi * (jb.n_top * 2);
     top_id = r >> 1;
     config_id = (r & 1) + 1;
-    yaw = yaw_table[fr.yaw_off + yi];
+    ycs = yaw_table + 3 * (size_t)(fr.yaw_off + yi);
     D2 vps[3];
-    g_vanishing_points(poses[fr.pose_off + pose_id].KinvR, yaw, vps);
+    g_vanishing_points(poses[fr.pose_off + pose_id].KinvR, ycs, vps);
     return g_build_corners(jb, vps, g_top_x(jb, top_id), config_id, prm.shorted_edge_thre, c, vp1pos);
 }
 
@@ -445,7 +446,7 @@ __global__ void __launch_bounds__(FU_THREADS) k_fuse_rank(const CsObj *__restric
             normv[i] = comb;
             D2 c[8];
             int vp1pos, config_id, pose_id, top_id;
-            double yaw;
+            const double *yaw;
             rebuild_corners(jb, fr, poses, yaw_table, prm, vlist[raw], c, vp1pos, config_id, yaw, pose_id, top_id);
             cs_cuboid_rec o;
             const CsPose &ps = poses[fr.pose_off + pose_id];
@@ -533,7 +534,7 @@ __global__ void __launch_bounds__(FU_THREADS) k_fuse_rank(const CsObj *__restric
             const int cand = w_vlist[co + raw];
             D2 c[8];
             int vp1pos, config_id, pose_id, top_id;
-            double yaw;
+            const double *yaw;
             rebuild_corners(jb, fr, poses, yaw_table, prm, cand, c, vp1pos, config_id, yaw, pose_id, top_id);
             cs_cuboid_rec o;
             const CsPose &ps = poses[fr.pose_off + pose_id];
@@ -629,7 +630,7 @@ __device__ __forceinline__ void vp_support_lane(const double *ang, const double 
     double base = 0, vmax = 0, vmin = 0;
     int imax = 0, imin = 0;
     for (int e = 0; e < n_lines; e++) {
-        const double raw = atan2(midy[e] - vp.y, midx[e] - vp.x);
+        const double raw = cs_pm_atan2(midy[e] - vp.y, midx[e] - vp.x);
         const double nrm = g_normalize_to_pi(raw);
         double d = fabs(ang[e] - nrm);
         d = g_min(d, CS_PI - d);
@@ -707,7 +708,7 @@ __global__ void __launch_bounds__(32 * SWW_WARPS) k_sweep_warp(const CsJob *__re
         for (int t = tid; t < n_tasks; t += 32 * SWW_WARPS) {
             const int ys = (t < 2 * bk.w) ? (t >> 1) : 0, vp_id = (t < 2 * bk.w) ? (t & 1) : 2;
             D2 v3[3];
-            g_vanishing_points(pose.KinvR, yaw_table[fr.yaw_off + bk.z + ys], v3);
+            g_vanishing_points(pose.KinvR, yaw_table + 3 * (size_t)(fr.yaw_off + bk.z + ys), v3);
             const double thre = ((vp_id != 2) ? prm.vp12_edge_angle_thre : prm.vp3_edge_angle_thre) / 180.0 * CS_PI;
             double o2[2];
             vp_support_lane(S.ang, S.midx, S.midy, n_lines, v3[vp_id], thre, vp_id, o2);
@@ -1023,7 +1024,7 @@ __global__ void __launch_bounds__(32 * FW_WARPS) k_fuse_warp(const CsObj *__rest
             const int cand = w_vlist[co + i];
             D2 c[8];
             int vp1pos, config_id, pose_id, top_id;
-            double yaw;
+            const double *yaw;
             rebuild_corners(jb, fr, poses, yaw_table, prm, cand, c, vp1pos, config_id, yaw, pose_id, top_id);
             cs_cuboid_rec &o = out[(size_t)oi * topk + round];
             const CsPose &ps = poses[fr.pose_off + pose_id];

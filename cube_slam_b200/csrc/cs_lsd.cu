@@ -47,6 +47,7 @@
 #include <vector>
 
 #include "cs_internal.h"
+#include "cs_nfa.cuh"
 
 #define LSD_PI 3.1415926535897932384626433832795
 #define LSD_NOTDEF (-1024.0)
@@ -61,6 +62,7 @@
 #define LSD_SCAP 512         /* region entries of a warp's staging area kept in shared memory (the rest spills to HBM) */
 #define LSD_SPILL 16384      /* staging capacity per warp (entries), first LSD_SCAP in shared memory */
 #define LSD_WINDOW 4096      /* list positions ahead of the frontier that may be speculated on */
+#define LSD_SEQ_SCAP 1536    /* region entries k_lsd_grow_seq keeps in shared memory (the rest spill to HBM; small, so that many frames share an SM) */
 #define LSD_FREE 0xffffffffu
 #define LSD_ST_NEW 0u
 #define LSD_ST_GROWING 1u
@@ -109,10 +111,12 @@ __device__ __forceinline__ float fast_atan2(float y, float x)
 __global__ void __launch_bounds__(256) k_lsd_hblur(const uint8_t *__restrict__ img, int n_frames, int w, int h, int stride, int channels,
                                                    double *__restrict__ tmp)
 {
-    const int64_t total = (int64_t)n_frames * w * h;
-    for (int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; p < total; p += (int64_t)gridDim.x * blockDim.x) {
-        const int64_t f = p / ((int64_t)w * h);
-        const int r = (int)(p - f * (int64_t)w * h);
+    /* grid: x over the pixels of one frame (32-bit arithmetic), y = frame */
+    const int f = blockIdx.y;
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= w * h) return;
+    const size_t p = (size_t)f * w * h + r;
+    {
         const int y = r / w, x = r - y * w;
         const uint8_t *row = img + ((size_t)f * h + y) * stride;
         double s = 0;
@@ -134,10 +138,12 @@ __global__ void __launch_bounds__(256) k_lsd_hblur(const uint8_t *__restrict__ i
 
 __global__ void __launch_bounds__(256) k_lsd_vblur(const double *__restrict__ tmp, int n_frames, int w, int h, double *__restrict__ blur)
 {
-    const int64_t total = (int64_t)n_frames * w * h;
-    for (int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; p < total; p += (int64_t)gridDim.x * blockDim.x) {
-        const int64_t f = p / ((int64_t)w * h);
-        const int r = (int)(p - f * (int64_t)w * h);
+    /* grid: x over the pixels of one frame (32-bit arithmetic), y = frame */
+    const int f = blockIdx.y;
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= w * h) return;
+    const size_t p = (size_t)f * w * h + r;
+    {
         const int y = r / w, x = r - y * w;
         const double *base = tmp + (size_t)f * w * h;
         double s = c_gauss7[3] * base[(size_t)y * w + x];
@@ -150,10 +156,12 @@ __global__ void __launch_bounds__(256) k_lsd_vblur(const double *__restrict__ tm
 __global__ void __launch_bounds__(256) k_lsd_resize(const double *__restrict__ blur, int n_frames, int sw, int sh, int dw, int dh, double inv_scale,
                                                     double *__restrict__ scaled)
 {
-    const int64_t total = (int64_t)n_frames * dw * dh;
-    for (int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; p < total; p += (int64_t)gridDim.x * blockDim.x) {
-        const int64_t f = p / ((int64_t)dw * dh);
-        const int r = (int)(p - f * (int64_t)dw * dh);
+    /* grid: x over the pixels of one scaled frame, y = frame */
+    const int f = blockIdx.y;
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= dw * dh) return;
+    const size_t p = (size_t)f * dw * dh + r;
+    {
         const int dy = r / dw, dx = r - dy * dw;
         float fx = (float)((dx + 0.5) * inv_scale - 0.5);
         int sx = (int)floorf(fx);
@@ -196,10 +204,12 @@ __global__ void __launch_bounds__(256) k_lsd_grad(const double *__restrict__ sca
                                                   double *__restrict__ modgrad, float *__restrict__ angf, uint4 *__restrict__ pix,
                                                   unsigned long long *__restrict__ max_bits)
 {
-    const int64_t total = (int64_t)n_frames * W * H;
-    for (int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; p < total; p += (int64_t)gridDim.x * blockDim.x) {
-        const int64_t f = p / ((int64_t)W * H);
-        const int addr = (int)(p - f * (int64_t)W * H);
+    /* grid: x over the pixels of one scaled frame, y = frame */
+    const int f = blockIdx.y;
+    const int addr = blockIdx.x * blockDim.x + threadIdx.x;
+    if (addr >= W * H) return;
+    const size_t p = (size_t)f * W * H + addr;
+    {
         const int y = addr / W, x = addr - y * W;
         const double *im = scaled + (size_t)f * W * H;
         double norm = 0;
@@ -325,6 +335,15 @@ __global__ void __launch_bounds__(32) k_lsd_scatter(const double *__restrict__ m
 }
 
 /* ---------------------------------------------------------------------------------------- the seed loop */
+/* cycle counters of the seed loop's phases (diagnostics, cs_debug_lsd_prof): grow, region2rect, refine, rectangle counts, binomial tails,
+ * candidates, list scan */
+__device__ unsigned long long g_lsd_prof[8];
+#define LSD_PROF_T0() const long long prof_t0__ = clock64()
+#define LSD_PROF_ADD(slot)                                                                         \
+    do {                                                                                           \
+        if ((threadIdx.x & 31) == 0) atomicAdd(&g_lsd_prof[slot], (unsigned long long)(clock64() - prof_t0__)); \
+    } while (0)
+
 struct LsdFrame {
     int W, H;
     uint4 *pix;            /* {deg, cos, sin, claim} */
@@ -335,6 +354,11 @@ struct LsdFrame {
     uint32_t *st;          /* per list position: state | invalid flag | record offset << 4 */
     int32_t *arena;        /* records of finished candidates */
     int arena_cap;
+    /* one warp per frame (k_lsd_grow_seq): the `used` map as a bit per pixel in shared memory; the claim words are not touched */
+    uint32_t *ubits;
+    const double *lgam; /* log_gamma of small integers (cs_nfa.cuh) */
+    unsigned long long wmagic; /* ceil(2^40 / W): row of a pixel address without an integer division (exact for addresses < 2^20 .. 2^30 / W) */
+    __device__ __forceinline__ int row_of(int addr) const { return (int)(((unsigned long long)addr * wmagic) >> 40); }
 };
 
 /* the region list of the candidate a warp works on: the first `scap` entries in shared memory, the rest in HBM */
@@ -453,7 +477,7 @@ __device__ __forceinline__ bool lsd_claim(const LsdFrame &F, const LsdView &V, i
 {
     uint32_t *cw = lsd_claim_ptr(F, addr);
     if (V.rank < 0) { /* sequential mode */
-        *cw = 0u;
+        atomicOr(F.ubits + (addr >> 5), 1u << (addr & 31));
         return true;
     }
     const uint32_t me0 = (uint32_t)V.rank << 1;
@@ -473,7 +497,7 @@ __device__ __forceinline__ bool lsd_demote(const LsdFrame &F, const LsdView &V, 
 {
     uint32_t *cw = lsd_claim_ptr(F, addr);
     if (V.rank < 0) {
-        *cw = LSD_FREE;
+        atomicAnd(F.ubits + (addr >> 5), ~(1u << (addr & 31)));
         return true;
     }
     const uint32_t me0 = (uint32_t)V.rank << 1;
@@ -501,7 +525,7 @@ __device__ int lsd_region_grow(const LsdFrame &F, const LsdView &V, const LsdReg
     const int lane = threadIdx.x & 31;
     {
         int ok = 1;
-        if (lane == 0) ok = lsd_claim(F, V, s_addr, lsd_ld_claim(F, s_addr)) ? 1 : 0;
+        if (lane == 0) ok = lsd_claim(F, V, s_addr, V.rank < 0 ? LSD_FREE : lsd_ld_claim(F, s_addr)) ? 1 : 0;
         if (!__shfl_sync(FULL, ok, 0)) return 1;
     }
     reg_size = 1;
@@ -519,19 +543,26 @@ __device__ int lsd_region_grow(const LsdFrame &F, const LsdView &V, const LsdReg
         int c_addr = -1;
         float deg = -1.f, csx = 0.f, csy = 0.f;
         uint32_t cseen = LSD_FREE;
+        if (V.rank < 0 && lane < 25) {
+            /* whichever neighbour is accepted and visited next, its 3 x 3 block lies inside this point's 5 x 5 block: ask for those records now */
+            const int p0 = R.get(base + i);
+            const int qy = F.row_of(p0), qx = p0 - qy * F.W;
+            const int yy = qy + lane / 5 - 2, xx = qx + lane % 5 - 2;
+            if (yy >= 0 && yy < F.H && xx >= 0 && xx < F.W) asm volatile("prefetch.global.L1 [%0];" ::"l"(F.pix + (yy * F.W + xx)));
+        }
         if (grp < navail) {
             const int pa = R.get(base + i + grp);
-            const int py = pa / F.W, px = pa - py * F.W;
+            const int py = F.row_of(pa), px = pa - py * F.W;
             const int yy = py + ky, xx = px + kx;
             if (yy >= 0 && yy < F.H && xx >= 0 && xx < F.W) {
                 c_addr = yy * F.W + xx;
-                const uint4 r = __ldcg(F.pix + c_addr);
+                const uint4 r = V.rank < 0 ? __ldg(F.pix + c_addr) : __ldcg(F.pix + c_addr); /* one warp per frame: the record is read-only */
                 deg = __uint_as_float(r.x);
                 if (deg >= 0.f) {
                     cseen = r.w;
                     int kind;
                     if (V.rank < 0)
-                        kind = (cseen == LSD_FREE) ? LSD_K_FREE : LSD_K_USED;
+                        kind = ((F.ubits[c_addr >> 5] >> (c_addr & 31)) & 1u) ? LSD_K_USED : LSD_K_FREE;
                     else
                         kind = lsd_decode(cseen, V);
                     cand = (kind == LSD_K_FREE || kind == LSD_K_HIGHER || kind == LSD_K_MINE_FORMER || kind == LSD_K_LOWER);
@@ -591,7 +622,7 @@ __device__ int lsd_region_grow(const LsdFrame &F, const LsdView &V, const LsdReg
             const int addr = __shfl_sync(0xffffffffu, my_addr__, j__);              \
             const double weight = __shfl_sync(0xffffffffu, my_w__, j__);            \
             const double pangle = (double)__shfl_sync(0xffffffffu, my_a__, j__) * LSD_DEG2RAD; \
-            const int ry = addr / (F).W, rx = addr - ry * (F).W;                    \
+            const int ry = (F).row_of(addr), rx = addr - ry * (F).W;                \
             (void)weight;                                                           \
             (void)pangle;                                                           \
             __VA_ARGS__                                                             \
@@ -627,7 +658,7 @@ __device__ void lsd_region2rect(const LsdFrame &F, const LsdReg &R, int base, in
     double l_min = 0, l_max = 0, w_min = 0, w_max = 0;
     for (int i = lane; i < reg_size; i += 32) {
         const int addr = R.get(base + i);
-        const int ry = addr / F.W, rx = addr - ry * F.W;
+        const int ry = F.row_of(addr), rx = addr - ry * F.W;
         const double regdx = (double)rx - x, regdy = (double)ry - y;
         const double l = regdx * dx + regdy * dy;
         const double w = -regdx * dy + regdy * dx;
@@ -665,7 +696,7 @@ __device__ int lsd_reduce_region_radius(const LsdFrame &F, const LsdView &V, con
 {
     const int lane = threadIdx.x & 31;
     const int a0 = R.get(base);
-    const double xc = (double)(a0 % F.W), yc = (double)(a0 / F.W);
+    const double xc = (double)(a0 - F.row_of(a0) * F.W), yc = (double)F.row_of(a0);
     const double radSq1 = lsd_dist_sq(xc, yc, rec.x1, rec.y1), radSq2 = lsd_dist_sq(xc, yc, rec.x2, rec.y2);
     double radSq = radSq1 > radSq2 ? radSq1 : radSq2;
     while (density < density_th) {
@@ -674,7 +705,7 @@ __device__ int lsd_reduce_region_radius(const LsdFrame &F, const LsdView &V, con
         if (lane == 0) {
             for (int i = 0; i < rs; ++i) {
                 const int addr = R.get(base + i);
-                if (lsd_dist_sq(xc, yc, (double)(addr % F.W), (double)(addr / F.W)) > radSq) {
+                if (lsd_dist_sq(xc, yc, (double)(addr - F.row_of(addr) * F.W), (double)F.row_of(addr)) > radSq) {
                     if (!lsd_demote(F, V, addr)) lost = 1;
                     const int last = R.get(base + rs - 1);
                     R.put(base + rs - 1, addr);
@@ -704,7 +735,7 @@ __device__ int lsd_refine(const LsdFrame &F, const LsdView &V, const LsdReg &R, 
     double density = (double)reg_size / (lsd_dist(rec.x1, rec.y1, rec.x2, rec.y2) * rec.width);
     if (density >= density_th) return 0;
     const int a0 = R.get(base);
-    const double xc = (double)(a0 % F.W), yc = (double)(a0 / F.W);
+    const double xc = (double)(a0 - F.row_of(a0) * F.W), yc = (double)F.row_of(a0);
     const double ang_c = (double)F.angf[a0] * LSD_DEG2RAD;
     double sum = 0, s_sum = 0;
     int n = 0;
@@ -827,25 +858,20 @@ __device__ void lsd_rect_count(const LsdFrame &F, const LsdRect &rec, int &total
 }
 
 /* the NFA of up to five rectangles of one rect_improve phase: counts one rectangle after the other (rows across lanes), then the
- * binomial tails on five lanes at once */
+ * binomial tails, each by the whole warp (cs_nfa.cuh) */
 __device__ void lsd_rect_nfa5(const LsdFrame &F, const LsdRect *r, int n, double *v)
 {
-    const int lane = threadIdx.x & 31;
-    int my_tot = 0, my_alg = 0;
-    double my_p = 0.5;
-    for (int t = 0; t < n; t++) {
-        int tot, alg;
-        lsd_rect_count(F, r[t], tot, alg);
-        if (lane == t) {
-            my_tot = tot;
-            my_alg = alg;
-            my_p = r[t].p;
-        }
+    int tot[5], alg[5];
+    {
+        LSD_PROF_T0();
+        for (int t = 0; t < n; t++) lsd_rect_count(F, r[t], tot[t], alg[t]);
+        LSD_PROF_ADD(3);
     }
-    double mine = 0;
-    if (lane < n) mine = lsd_nfa(my_tot, my_alg, my_p, F.LOG_NT);
-    __syncwarp();
-    for (int t = 0; t < n; t++) v[t] = __shfl_sync(0xffffffffu, mine, t);
+    {
+        LSD_PROF_T0();
+        for (int t = 0; t < n; t++) v[t] = cs_nfa_warp(F.lgam, tot[t], alg[t], r[t].p, F.LOG_NT, true); /* the whole warp on one binomial tail */
+        LSD_PROF_ADD(4);
+    }
 }
 
 /* lsd.cpp:873-975: the rectangles of a phase do not depend on the NFA values of that phase, so they are evaluated together */
@@ -918,13 +944,27 @@ __device__ int lsd_process_seed(const LsdFrame &F, const LsdView &V, const LsdRe
     double reg_angle = 0;
     has_line = 0;
     n_all = 0;
-    int rc = lsd_region_grow(F, V, R, 0, s_addr, reg_size, reg_angle, prec);
+    int rc;
+    {
+        LSD_PROF_T0();
+        rc = lsd_region_grow(F, V, R, 0, s_addr, reg_size, reg_angle, prec);
+        LSD_PROF_ADD(0);
+    }
+    if ((threadIdx.x & 31) == 0) atomicAdd(&g_lsd_prof[5], 1ull);
     n_all = reg_size;
     if (rc) return rc;
     if (reg_size < min_reg_size) return 0;
     LsdRect rec;
-    lsd_region2rect(F, R, 0, reg_size, reg_angle, prec, p, rec);
-    rc = lsd_refine(F, V, R, base, reg_size, reg_angle, prec, p, rec, DENSITY_TH, n_all);
+    {
+        LSD_PROF_T0();
+        lsd_region2rect(F, R, 0, reg_size, reg_angle, prec, p, rec);
+        LSD_PROF_ADD(1);
+    }
+    {
+        LSD_PROF_T0();
+        rc = lsd_refine(F, V, R, base, reg_size, reg_angle, prec, p, rec, DENSITY_TH, n_all);
+        LSD_PROF_ADD(2);
+    }
     if (rc == 3) return 0;
     if (rc) return rc;
     const double log_nfa = lsd_rect_improve(F, rec);
@@ -992,6 +1032,7 @@ struct LsdGrowArgs {
     float *out;
     int32_t *n_out;
     int cap;
+    const double *lgam;  /* log_gamma table (cs_nfa.cuh) */
     int32_t *redo;       /* per frame: 1 = the sequential kernel must redo this frame */
     int32_t *stats;      /* per frame: rounds, candidates processed, refused, invalidated (diagnostics) */
 };
@@ -1020,6 +1061,9 @@ __global__ void __launch_bounds__(LSD_NW * 32, 2) k_lsd_grow_par(LsdGrowArgs A, 
     F.st = A.st + f * npx;
     F.arena = A.arena + (size_t)f * A.arena_cap;
     F.arena_cap = A.arena_cap;
+    F.ubits = nullptr;
+    F.lgam = A.lgam;
+    F.wmagic = ((1ull << 40) + (unsigned long long)A.W - 1) / (unsigned long long)A.W;
     const int32_t *list = A.list + f * npx;
     const int n_list = A.list_len[f];
     LsdReg R;
@@ -1240,6 +1284,7 @@ __global__ void __launch_bounds__(32) k_lsd_grow_seq(LsdGrowArgs A)
 {
     const int f = blockIdx.x, lane = threadIdx.x;
     if (!A.redo[f]) return;
+    LSD_PROF_T0();
     const size_t npx = (size_t)A.W * A.H;
     LsdFrame F;
     F.W = A.W;
@@ -1251,12 +1296,17 @@ __global__ void __launch_bounds__(32) k_lsd_grow_seq(LsdGrowArgs A)
     F.st = nullptr;
     F.arena = nullptr;
     F.arena_cap = 0;
-    for (size_t i = lane; i < npx; i += 32) *lsd_claim_ptr(F, (int)i) = LSD_FREE;
+    extern __shared__ uint32_t s_seq[];
+    const int n_words = (int)((npx + 31) >> 5);
+    F.ubits = s_seq;
+    F.lgam = A.lgam;
+    F.wmagic = ((1ull << 40) + (unsigned long long)A.W - 1) / (unsigned long long)A.W;
+    for (int i = lane; i < n_words; i += 32) F.ubits[i] = 0u;
     __syncwarp();
     LsdReg R;
-    R.s = nullptr;
-    R.g = A.arena + (size_t)f * A.arena_cap; /* the record arena is free in this mode: it holds the region list */
-    R.scap = 0;
+    R.s = (int *)(s_seq + n_words); /* the first LSD_SEQ_SCAP region entries in shared memory, the rest in the (otherwise unused) record arena */
+    R.g = A.arena + (size_t)f * A.arena_cap;
+    R.scap = LSD_SEQ_SCAP;
     R.cap = A.arena_cap;
     LsdView V;
     V.rank = -1;
@@ -1273,14 +1323,14 @@ __global__ void __launch_bounds__(32) k_lsd_grow_seq(LsdGrowArgs A)
         bool seed = false;
         if (i < n_list) {
             adx = list[i];
-            seed = (lsd_ld_claim(F, adx) == LSD_FREE); /* the list holds pixels with a defined angle only */
+            seed = !((F.ubits[adx >> 5] >> (adx & 31)) & 1u); /* the list holds pixels with a defined angle only */
         }
         unsigned todo = __ballot_sync(0xffffffffu, seed);
         while (todo) {
             const int sl = __ffs(todo) - 1;
             todo &= todo - 1;
             const int s_addr = __shfl_sync(0xffffffffu, adx, sl);
-            if (lsd_ld_claim(F, s_addr) != LSD_FREE) continue; /* claimed by a region grown since the ballot */
+            if ((F.ubits[s_addr >> 5] >> (s_addr & 31)) & 1u) continue; /* used by a region grown since the ballot */
             int n_all = 0, has_line = 0;
             float line[4];
             const int rc = lsd_process_seed(F, V, R, s_addr, A.min_reg_size, A.prec, A.p, A.scale, n_all, has_line, line);
@@ -1299,6 +1349,7 @@ __global__ void __launch_bounds__(32) k_lsd_grow_seq(LsdGrowArgs A)
         A.n_raw[f] = n_raw;
         A.n_out[f] = n_out;
     }
+    LSD_PROF_ADD(6);
 }
 
 /* ---------------------------------------------------------------------------------------- host side */
@@ -1308,7 +1359,8 @@ struct Buf {
 };
 
 struct LsdState {
-    Buf img, tmp, blur, scaled, modgrad, angf, pix, list, st, arena, spill, maxg, cnt, llen, raw, nraw, out, nout, redo, stats;
+    Buf img, tmp, blur, scaled, modgrad, angf, pix, list, st, arena, spill, maxg, cnt, llen, raw, nraw, out, nout, redo, stats, lgam;
+    bool lgam_filled = false;
     int last_frames = 0, last_W = 0, last_H = 0, cap = 0;
 };
 
@@ -1325,6 +1377,17 @@ int ensure(cs_ctx *c, Buf &b, size_t bytes)
 }
 
 inline int grid_for(int64_t n) { return (int)std::min<int64_t>((n + 255) / 256, 148 * 32); }
+
+/* raise a kernel's dynamic shared-memory limit when a launch needs more than it was last given (per device) */
+#define CS_LSD_SET_SMEM(kernel, bytes)                                                                  \
+    do {                                                                                                \
+        static size_t set_[64] = {};                                                                    \
+        const int dev_ = cs_ctx_device(c) & 63;                                                         \
+        if ((bytes) > set_[dev_]) {                                                                     \
+            cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(bytes));    \
+            set_[dev_] = (bytes);                                                                       \
+        }                                                                                               \
+    } while (0)
 
 int lsd_run(cs_ctx *c, const uint8_t *imgs, bool imgs_on_device, int n_frames, int w, int h, int stride, int channels, float line_length_thres,
             int cap, LsdState &S)
@@ -1351,8 +1414,16 @@ int lsd_run(cs_ctx *c, const uint8_t *imgs, bool imgs_on_device, int n_frames, i
         (rc = ensure(c, S.cnt, (size_t)n_frames * n_chunks * LSD_NBINS * 4)) || (rc = ensure(c, S.llen, (size_t)n_frames * 4)) ||
         (rc = ensure(c, S.raw, (size_t)n_frames * cap * 16)) || (rc = ensure(c, S.nraw, (size_t)n_frames * 4)) ||
         (rc = ensure(c, S.out, (size_t)n_frames * cap * 16)) || (rc = ensure(c, S.nout, (size_t)n_frames * 4)) ||
-        (rc = ensure(c, S.redo, (size_t)n_frames * 4)) || (rc = ensure(c, S.stats, (size_t)n_frames * 16)))
+        (rc = ensure(c, S.redo, (size_t)n_frames * 4)) || (rc = ensure(c, S.stats, (size_t)n_frames * 16)) ||
+        (rc = ensure(c, S.lgam, (size_t)CS_LGAMMA_TABLE * 8)))
         return rc;
+    if (!S.lgam_filled) { /* log_gamma of the integers 1 .. CS_LGAMMA_TABLE - 1, host libm like the reference */
+        std::vector<double> t(CS_LGAMMA_TABLE, 0.0);
+        for (int i = 1; i < CS_LGAMMA_TABLE; i++) t[i] = cs_lgamma_host((double)i);
+        if (cudaMemcpyAsync(S.lgam.p, t.data(), t.size() * 8, cudaMemcpyHostToDevice, st) != cudaSuccess || cudaStreamSynchronize(st) != cudaSuccess)
+            return cs_ctx_fail(c, CS_ERR_CUDA, "upload of the log_gamma table failed");
+        S.lgam_filled = true;
+    }
     /* host-side constants of flsd (lsd.cpp:445-447,468-469), evaluated with libm like the reference */
     const double ANG_TH = 22.5, QUANT = 2.0;
     const double prec = LSD_PI * ANG_TH / 180, p = ANG_TH / 180, rho = QUANT / std::sin(prec);
@@ -1362,10 +1433,11 @@ int lsd_run(cs_ctx *c, const uint8_t *imgs, bool imgs_on_device, int n_frames, i
     cudaMemsetAsync(S.maxg.p, 0, (size_t)n_frames * 8, st);
     cudaMemsetAsync(S.st.p, 0, spx * 4, st);
     cudaMemsetAsync(S.stats.p, 0, (size_t)n_frames * 16, st);
-    k_lsd_hblur<<<grid_for((int64_t)px), 256, 0, st>>>(d_img, n_frames, w, h, stride, channels, (double *)S.tmp.p);
-    k_lsd_vblur<<<grid_for((int64_t)px), 256, 0, st>>>((const double *)S.tmp.p, n_frames, w, h, (double *)S.blur.p);
-    k_lsd_resize<<<grid_for((int64_t)spx), 256, 0, st>>>((const double *)S.blur.p, n_frames, w, h, W, H, 1. / SCALE, (double *)S.scaled.p);
-    k_lsd_grad<<<grid_for((int64_t)spx), 256, 0, st>>>((const double *)S.scaled.p, n_frames, W, H, rho, (double *)S.modgrad.p, (float *)S.angf.p,
+    const dim3 g_src((w * h + 255) / 256, n_frames), g_dst((W * H + 255) / 256, n_frames);
+    k_lsd_hblur<<<g_src, 256, 0, st>>>(d_img, n_frames, w, h, stride, channels, (double *)S.tmp.p);
+    k_lsd_vblur<<<g_src, 256, 0, st>>>((const double *)S.tmp.p, n_frames, w, h, (double *)S.blur.p);
+    k_lsd_resize<<<g_dst, 256, 0, st>>>((const double *)S.blur.p, n_frames, w, h, W, H, 1. / SCALE, (double *)S.scaled.p);
+    k_lsd_grad<<<g_dst, 256, 0, st>>>((const double *)S.scaled.p, n_frames, W, H, rho, (double *)S.modgrad.p, (float *)S.angf.p,
                                                        (uint4 *)S.pix.p, (unsigned long long *)S.maxg.p);
     k_lsd_hist<<<n_frames * n_chunks, 256, 0, st>>>((const double *)S.modgrad.p, (const float *)S.angf.p, W, H, n_chunks, (const unsigned long long *)S.maxg.p, (int32_t *)S.cnt.p);
     k_lsd_scan<<<n_frames, LSD_NBINS, 0, st>>>(n_chunks, (int32_t *)S.cnt.p, (int32_t *)S.llen.p);
@@ -1396,10 +1468,19 @@ int lsd_run(cs_ctx *c, const uint8_t *imgs, bool imgs_on_device, int n_frames, i
     A.out = (float *)S.out.p;
     A.n_out = (int32_t *)S.nout.p;
     A.cap = cap;
+    A.lgam = (const double *)S.lgam.p;
     A.redo = (int32_t *)S.redo.p;
     A.stats = (int32_t *)S.stats.p;
-    k_lsd_grow_par<<<n_frames, LSD_NW * 32, 0, st>>>(A, cs_ctx_seq_lines(c));
-    k_lsd_grow_seq<<<n_frames, 32, 0, st>>>(A);
+    /* The ordered-speculation kernel is off by default: on the GPU it is neither faster than one warp per frame (most of its candidates are
+     * refused and redone) nor, on dense frames, free of duplicate segments.  CS_LSD_SPECULATE=1 turns it back on for work on it. */
+    static const bool speculate = getenv("CS_LSD_SPECULATE") && atoi(getenv("CS_LSD_SPECULATE")) != 0;
+    k_lsd_grow_par<<<n_frames, LSD_NW * 32, 0, st>>>(A, (cs_ctx_seq_lines(c) || !speculate) ? 1 : 0);
+    {
+        const size_t smem = ((size_t)W * H + 31) / 32 * 4 + (size_t)LSD_SEQ_SCAP * 4;
+        if (smem > 200 * 1024) return cs_ctx_fail(c, CS_ERR_UNSUPPORTED, "frame too large for the LSD seed loop (%d x %d after scaling)", W, H);
+        CS_LSD_SET_SMEM(k_lsd_grow_seq, smem);
+        k_lsd_grow_seq<<<n_frames, 32, smem, st>>>(A);
+    }
     cs_ctx_count_launches(c, 9);
     if (cudaGetLastError() != cudaSuccess) return cs_ctx_fail(c, CS_ERR_CUDA, "LSD kernel launch failed: %s", cudaGetErrorString(cudaGetLastError()));
     S.last_frames = n_frames;
@@ -1434,7 +1515,7 @@ void cs_lsd_destroy(void *state)
 {
     LsdState *S = (LsdState *)state;
     Buf *all[] = {&S->img, &S->tmp, &S->blur, &S->scaled, &S->modgrad, &S->angf, &S->pix, &S->list, &S->st, &S->arena, &S->spill, &S->maxg, &S->cnt,
-                  &S->llen, &S->raw, &S->nraw, &S->out, &S->nout, &S->redo, &S->stats};
+                  &S->llen, &S->raw, &S->nraw, &S->out, &S->nout, &S->redo, &S->stats, &S->lgam};
     for (Buf *b : all)
         if (b->p) cudaFree(b->p);
     delete S;
@@ -1517,6 +1598,21 @@ int cs_debug_lsd(cs_ctx *c, int frame, int32_t *scaled_wh, double *scaled, doubl
     cudaMemcpy(&nr, (int32_t *)S->nraw.p + frame, 4, cudaMemcpyDeviceToHost);
     if (n_raw) *n_raw = nr;
     if (raw_lines) cudaMemcpy(raw_lines, (float *)S->raw.p + (size_t)frame * S->cap * 4, (size_t)std::min(nr, std::min(cap_raw, S->cap)) * 16, cudaMemcpyDeviceToHost);
+    return cudaGetLastError() == cudaSuccess ? CS_OK : cs_ctx_fail(c, CS_ERR_CUDA, "debug copy failed");
+}
+
+/* cycle counters of the seed loop's phases summed over every warp since the last reset (diagnostics): {region_grow, region2rect, refine,
+ * rectangle pixel counts, binomial tails, candidates grown, whole kernel (per CTA), unused} */
+int cs_debug_lsd_prof(cs_ctx *c, uint64_t *out8, int reset)
+{
+    if (!c) return CS_ERR_INVALID_ARG;
+    cudaSetDevice(cs_ctx_device(c));
+    cudaStreamSynchronize(cs_ctx_stream(c));
+    if (out8) cudaMemcpyFromSymbol(out8, g_lsd_prof, 64);
+    if (reset) {
+        const unsigned long long z[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+        cudaMemcpyToSymbol(g_lsd_prof, z, 64);
+    }
     return cudaGetLastError() == cudaSuccess ? CS_OK : cs_ctx_fail(c, CS_ERR_CUDA, "debug copy failed");
 }
 

@@ -216,10 +216,20 @@ int cs_debug_lsd(cs_ctx *ctx, int frame, int32_t scaled_wh[2], double *scaled, d
 /* diagnostics of the last LSD run's seed loop (lsd.cpp:478-535 as ordered speculation, cs_lsd.cu): per frame 4 values {rounds, candidates
  * processed, candidates refused or lost, candidates re-grown after an override}; redo[f] = 1 when the sequential kernel redid the frame */
 int cs_debug_lsd_stats(cs_ctx *ctx, int32_t *stats4, int32_t *redo, int n_frames);
+/* clock64 cycles the seed-loop warps spent per phase since the last reset (diagnostics; tools/time_lines.py): {region_grow, region2rect,
+ * refine, rectangle pixel counts, binomial tails (nfa), candidates grown, whole kernel summed over CTAs, unused} */
+int cs_debug_lsd_prof(cs_ctx *ctx, uint64_t *out8, int reset);
 /* same for the EDLines flavour (use_LSD = 0): EDLineDetector's maps (binary_descriptor.cpp:1617-1666: blurred image, dxImg_, dyImg_,
  * gImgWO_ / 4, dirImg_), the anchors in scan order as y * width + x, the edge map after smart routing, the segments before the length filter */
 int cs_debug_edlines(cs_ctx *ctx, int frame, uint8_t *blur, int16_t *dx, int16_t *dy, int16_t *g, uint8_t *dir, int32_t *anchors,
                      int32_t *n_anchors, uint8_t *edge, float *raw_lines, int32_t *n_raw, int cap_raw);
+
+/* The atan2 of the cuboid stage's angle-error chain (merge_break_lines, VP_support_edge_infos, box_edge_alignment_angle_error;
+ * object_3d_util.cpp:167-172,321,392,480) is defined arithmetically (cube_slam_b200/csrc/cs_pmath.h: IEEE + - * / only, within 1 ulp of
+ * glibc's) so that it rounds the same on the host, on the device and in the test oracle.  cs_debug_atan2 evaluates it on the device,
+ * cs_atan2_host on the host (tests). */
+int cs_debug_atan2(cs_ctx *ctx, const double *y, const double *x, double *out, int n);
+double cs_atan2_host(double y, double x);
 
 /* ---- multi-GPU -------------------------------------------------------------------------- */
 /* Frames shard across ranks; the only exchange is one all-gather of the top-K record buffers.

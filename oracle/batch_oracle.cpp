@@ -9,6 +9,8 @@
  *   line_mode 1: LSD flavour of detect_filter_lines per frame (use_LSD = true, what object_slam sets, main_obj.cpp:365)
  *   line_mode 2: EDLines flavour (use_LSD = false, the class default, line_lbd_allclass.cpp:121)
  */
+#include <malloc.h>
+
 #include <cstdint>
 #include <cstring>
 #include <mutex>
@@ -47,6 +49,17 @@ extern "C" int orc_detect_frames_batch(const uint8_t *imgs, int n_frames, int w,
 {
     int status = 0;
     if (n_threads < 1) n_threads = 1;
+    {
+        /* every frame allocates a dozen multi-megabyte images; glibc hands such blocks out with mmap / munmap, and on a many-core host the
+         * page faults and address-space locking of a hundred threads doing that at once serialise the whole batch.  Keep the blocks in
+         * the per-thread malloc arenas instead (a process-wide setting of the test process; set once). */
+        static std::once_flag once;
+        std::call_once(once, []() {
+            mallopt(M_MMAP_THRESHOLD, 1 << 30);
+            mallopt(M_TRIM_THRESHOLD, 1 << 30);
+            mallopt(M_TOP_PAD, 64 << 20);
+        });
+    }
     std::mutex mu;
     auto one_frame = [&](int f) {
         const uint8_t *img = imgs + (size_t)f * h * stride;

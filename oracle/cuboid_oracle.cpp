@@ -18,6 +18,7 @@
  * Only tests/, __graft_entry__.smoke() and bench.py (cpu_baseline / --impl reference) use this.
  */
 #include "orc_api.h"
+#include "pmath.h"
 
 #include <algorithm>
 #include <cmath>
@@ -27,6 +28,15 @@
 #include <limits>
 #include <numeric>
 #include <vector>
+
+/* atan2 of the angle-error chain (merge_break_lines, VP_support_edge_infos, box_edge_alignment_angle_error; object_3d_util.cpp:167-172,
+ * 321,392,480).  1 (default): the arithmetic definition shared with the CUDA path (pmath.h), so that parity is bit for bit;
+ * 0: libm's, what the reference itself calls -- the two differ by at most one ulp (tests/test_pmath.py), which matters only where
+ * fuse_normalize_scores_v2 splits a pair of mathematically equal angle errors (see orc_last_cut_margin below). */
+static thread_local int g_portable_atan2 = 1;
+extern "C" void orc_set_portable_atan2(int on) { g_portable_atan2 = on; }
+extern "C" double orc_atan2_portable(double y, double x) { return orc_pm_atan2(y, x); }
+static inline double ang_atan2(double y, double x) { return g_portable_atan2 ? orc_pm_atan2(y, x) : std::atan2(y, x); }
 
 namespace {
 
@@ -232,7 +242,7 @@ int merge_break_lines(std::vector<double> &L, int n, double dist_thre, double an
     while (can_force_merge && counter < 500) {
         counter++;
         can_force_merge = false;
-        for (int i = 0; i < total; i++) ang[i] = std::atan2(L[i * 4 + 3] - L[i * 4 + 1], L[i * 4 + 2] - L[i * 4 + 0]);
+        for (int i = 0; i < total; i++) ang[i] = ang_atan2(L[i * 4 + 3] - L[i * 4 + 1], L[i * 4 + 2] - L[i * 4 + 0]);
         for (int s1 = 0; s1 < total - 1; s1++) {
             for (int s2 = s1 + 1; s2 < total; s2++) {
                 const double diff = std::abs(ang[s1] - ang[s2]);
@@ -250,7 +260,7 @@ int merge_break_lines(std::vector<double> &L, int n, double dist_thre, double an
                             me = {L[s1 * 4 + 2], L[s1 * 4 + 3]};
                         else
                             me = {L[s2 * 4 + 2], L[s2 * 4 + 3]};
-                        const double merged_angle = std::atan2(me.y - ms.y, me.x - ms.x);
+                        const double merged_angle = ang_atan2(me.y - ms.y, me.x - ms.x);
                         const double temp = std::abs(ang[s1] - merged_angle);
                         const double merge_angle_diff = std::min(temp, M_PI - temp);
                         if (merge_angle_diff < angle_thre) {
@@ -296,7 +306,7 @@ void vp_support_edge_infos(const P2 *vps, const double *mid, const double *edge_
         const double thre = (vp_id != 2 ? thre12_deg : thre3_deg) / 180.0 * M_PI;
         int cnt = 0;
         for (int e = 0; e < n; e++) {
-            const double raw = std::atan2(mid[e * 2 + 1] - vps[vp_id].y, mid[e * 2 + 0] - vps[vp_id].x);
+            const double raw = ang_atan2(mid[e * 2 + 1] - vps[vp_id].y, mid[e * 2 + 0] - vps[vp_id].x);
             const double nrm = normalize_to_pi(raw);
             double d = std::abs(edge_angles[e] - nrm);
             d = std::min(d, M_PI - d);
@@ -374,7 +384,7 @@ double box_edge_alignment_angle_error(const double *vp_angles, const int (*ids)[
         if (nv > 0) {
             for (int ee = 0; ee < 2; ee++) {
                 const P2 a = c[ids[vp_id][2 * ee]], b = c[ids[vp_id][2 * ee + 1]];
-                const double box_edge_angle = normalize_to_pi(std::atan2(b.y - a.y, b.x - a.x));
+                const double box_edge_angle = normalize_to_pi(ang_atan2(b.y - a.y, b.x - a.x));
                 double best = 100;
                 for (int i = 0; i < nv; i++) {
                     double t = std::abs(box_edge_angle - valid[i]);
@@ -400,6 +410,19 @@ void sorted_prefix(const std::vector<double> &v, std::vector<int> &idx, int top_
     });
 }
 
+/* The one comparison of the path whose outcome can hang on the last bit of a transcendental: `angle_error(cut) > angle_error(cut - 1)`
+ * (object_3d_util.cpp:511) between two proposals whose angle errors are mathematically equal (mirror-image configurations) but were summed
+ * from atan2 values of different arguments.  Which way it falls depends on the libm of the machine the reference runs on, and it
+ * switches between two different kept sets (hence different min-max normalisations).  The oracle records how close the call was
+ * (orc_last_cut_margin: smallest relative gap of that comparison over the last orc_detect_cuboid call of this thread) and can be asked
+ * to take the other branch when the gap is below 1e-13 (orc_set_cut_flip), so a parity test can tell "the CUDA atan2 rounded one
+ * angle the other way" from a real difference. */
+static thread_local double g_cut_margin = 1e300;     /* of the box being processed */
+static thread_local double g_box_margin[64];          /* per box of the last call (first 64 boxes) */
+static thread_local int g_cut_flip = -1, g_cur_box = -1;
+extern "C" double orc_last_cut_margin(int box) { return (box >= 0 && box < 64) ? g_box_margin[box] : 1e300; }
+extern "C" void orc_set_cut_flip(int box) { g_cut_flip = box; } /* -1: none */
+
 /* object_3d_util.cpp:495-565 */
 void fuse_normalize_scores_v2(const std::vector<double> &dist_error, const std::vector<double> &angle_error,
                               std::vector<double> &combined, std::vector<int> &keep, double weight_vp_angle, bool normalize)
@@ -414,7 +437,17 @@ void fuse_normalize_scores_v2(const std::vector<double> &dist_error, const std::
         sorted_prefix(dist_error, ds, breaking_num);
         sorted_prefix(angle_error, as, breaking_num);
         std::vector<int> dkeep(ds.begin(), ds.begin() + breaking_num - 1);
-        if (angle_error[as[breaking_num - 1]] > angle_error[as[breaking_num - 2]]) {
+        const double a_cut = angle_error[as[breaking_num - 1]], a_prev = angle_error[as[breaking_num - 2]];
+        bool cut_greater = a_cut > a_prev;
+        {
+            const double scale = std::max(std::fabs(a_cut), std::fabs(a_prev));
+            const double margin = scale > 0 ? std::fabs(a_cut - a_prev) / scale : 0.0;
+            if (!std::isnan(margin)) {
+                if (margin < g_cut_margin) g_cut_margin = margin; /* an exact tie here can be an inexact one there */
+                if (g_cut_flip >= 0 && g_cut_flip == g_cur_box && margin < 1e-13) cut_greater = !cut_greater;
+            }
+        }
+        if (cut_greater) {
             std::vector<int> akeep(as.begin(), as.begin() + breaking_num - 1);
             std::sort(dkeep.begin(), dkeep.end());
             std::sort(akeep.begin(), akeep.end());
@@ -733,6 +766,7 @@ extern "C" int orc_detect_cuboid(const uint8_t *img, int w, int h, int stride, i
                                  const orc_params *pp, int topk_cap, orc_cuboid *out, int *out_counts,
                                  int64_t *n_candidates_total, int64_t *n_valid_total, orc_trace *trace)
 {
+    g_cut_margin = 1e300;
     const orc_params &p = *pp;
     if (n_candidates_total) *n_candidates_total = 0;
     if (n_valid_total) *n_valid_total = 0;
@@ -765,7 +799,17 @@ extern "C" int orc_detect_cuboid(const uint8_t *img, int w, int h, int stride, i
 
     const bool all_configs[2] = {p.consider_config_1 != 0, p.consider_config_2 != 0};
 
+    for (int b = 0; b < 64; b++) g_box_margin[b] = 1e300;
     for (int object_id = 0; object_id < N; object_id++) {
+        g_cur_box = object_id;
+        g_cut_margin = 1e300;
+        struct MarginKeeper {
+            int id;
+            ~MarginKeeper()
+            {
+                if (id < 64) g_box_margin[id] = g_cut_margin;
+            }
+        } margin_keeper{object_id};
         const double *bb = boxes + (size_t)object_id * 5;
         const int left_x_raw = (int)bb[0];
         const int top_y_raw = (int)bb[1];
@@ -835,7 +879,7 @@ extern "C" int orc_detect_cuboid(const uint8_t *img, int w, int h, int stride, i
             /* :185-191 */
             std::vector<double> line_angles(n_lines), mid(2 * (size_t)n_lines);
             for (int i = 0; i < n_lines; i++) {
-                line_angles[i] = std::atan2(Lin[i * 4 + 3] - Lin[i * 4 + 1], Lin[i * 4 + 2] - Lin[i * 4 + 0]);
+                line_angles[i] = ang_atan2(Lin[i * 4 + 3] - Lin[i * 4 + 1], Lin[i * 4 + 2] - Lin[i * 4 + 0]);
                 mid[i * 2 + 0] = (Lin[i * 4 + 0] + Lin[i * 4 + 2]) / 2;
                 mid[i * 2 + 1] = (Lin[i * 4 + 1] + Lin[i * 4 + 3]) / 2;
             }

@@ -108,6 +108,14 @@ void orc_chamfer_dt(const uint8_t *edges, int w, int h, float *dist);
 int orc_merge_break_lines(const double *lines, int n, double dist_thre, double angle_thre_deg,
                           double len_thre, double *out);
 
+/* which atan2 the angle-error chain uses: 1 (default) the arithmetic definition shared with the CUDA path (pmath.h), 0 libm's */
+void orc_set_portable_atan2(int on);
+double orc_atan2_portable(double y, double x);
+
+/* knife-edge bookkeeping of fuse_normalize_scores_v2's angle-cut comparison (see cuboid_oracle.cpp) */
+double orc_last_cut_margin(int box); /* smallest relative gap of that comparison for box `box` (< 64) of this thread's last orc_detect_cuboid */
+void orc_set_cut_flip(int box);      /* take the other branch for that box where the gap is < 1e-13; -1 = off */
+
 /* detect_3d_cuboid::detect_cuboid (box_proposal_detail.cpp:56-557) for one frame.
  * boxes N x 5 [x y w h prob] 0-based; lines M x 4; out N x topk_cap; out_counts N. */
 int orc_detect_cuboid(const uint8_t *img, int w, int h, int stride, int channels,

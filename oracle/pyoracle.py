@@ -154,7 +154,7 @@ def cam_pose(K, T):
 
 
 def detect_cuboid(img, K, T_wc, boxes, lines, params=None, topk_cap=None, trace_object=None,
-                  trace_height_sample=0, trace_caps=(4096, 1 << 21, 1 << 16)):
+                  trace_height_sample=0, trace_caps=(4096, 1 << 21, 1 << 16), cut_flip=-1):
     """detect_3d_cuboid::detect_cuboid for one frame (box_proposal_detail.cpp:56-557).
 
     Returns dict(cuboids=[structured array per bbox], n_candidates, n_valid, trace=dict|None)."""
@@ -197,14 +197,23 @@ def detect_cuboid(img, K, T_wc, boxes, lines, params=None, topk_cap=None, trace_
         tr.cap_valid = cap_valid
         tr.kept_ids = _p(bufs["kept_ids"], C.c_int32)
         tr.kept_scores = _p(bufs["kept_scores"], C.c_double)
-    rc = L.orc_detect_cuboid(_p(img, C.c_uint8), w, h, img.strides[0], ch, _p(K, C.c_double), _p(T_wc, C.c_double),
-                             _p(boxes, C.c_double), N, _p(lines, C.c_double), len(lines), C.byref(params), topk_cap,
-                             out.ctypes.data_as(C.POINTER(Cuboid)), _p(counts, C.c_int),
-                             C.byref(ncand), C.byref(nvalid), C.byref(tr) if tr is not None else None)
+    L.orc_last_cut_margin.restype = C.c_double
+    L.orc_last_cut_margin.argtypes = [C.c_int]
+    L.orc_set_cut_flip(int(cut_flip))
+    try:
+        rc = L.orc_detect_cuboid(_p(img, C.c_uint8), w, h, img.strides[0], ch, _p(K, C.c_double), _p(T_wc, C.c_double),
+                                 _p(boxes, C.c_double), N, _p(lines, C.c_double), len(lines), C.byref(params), topk_cap,
+                                 out.ctypes.data_as(C.POINTER(Cuboid)), _p(counts, C.c_int),
+                                 C.byref(ncand), C.byref(nvalid), C.byref(tr) if tr is not None else None)
+        cut_margin = [float(L.orc_last_cut_margin(b)) for b in range(min(N, 64))]
+    finally:
+        L.orc_set_cut_flip(-1)
     if rc != 0:
         raise RuntimeError("orc_detect_cuboid failed: %d" % rc)
+    # cut_margin[b]: how close fuse_normalize_scores_v2's `angle_error(cut) > angle_error(cut - 1)` came to a tie for box b (relative gap;
+    # 1e300 when the comparison never ran).  cut_flip=b takes the other branch for box b where the gap is < 1e-13.
     res = {"cuboids": [out[i, :counts[i]].copy() for i in range(N)], "n_candidates": ncand.value,
-           "n_valid": nvalid.value, "trace": None}
+           "n_valid": nvalid.value, "trace": None, "cut_margin": cut_margin}
     if tr is not None:
         rw, rh = tr.roi[2], tr.roi[3]
         npx = max(rw, 0) * max(rh, 0)

@@ -3,6 +3,8 @@
 Streaming stages (blur, resize, gradient modulus / angle, pseudo-ordering) must be bit-exact; the detected segments are
 float32 and must be identical (the only non-IEEE operations are double cos/sin/log of CUDA vs glibc, <= 2 ulp before the
 float rounding)."""
+import os
+
 import numpy as np
 import pytest
 
@@ -138,16 +140,19 @@ def test_online_batch_equals_two_calls(det, oracle):
     np.testing.assert_array_equal(cnt1, cnt2)
     assert out1.tobytes() == out2.tobytes()
     # and both equal the oracle's two-stage result
+    from test_gpu_cuboid_parity import _compare_box
     o = 0
+    n_knife = 0
     for f in range(F):
         rl = oracle.lsd_detect(imgs[f], float(lp.line_length_thres))["lines"].astype(np.float64)
-        ref = oracle.detect_cuboid(imgs[f], K, Ts[f], boxes[f], rl, oracle.default_params(max_cuboid_num=2))
+
+        def redo(cut_flip=-1, f=f, rl=rl):
+            return oracle.detect_cuboid(imgs[f], K, Ts[f], boxes[f], rl, oracle.default_params(max_cuboid_num=2), cut_flip=cut_flip)
+        ref = redo()
         for b in range(len(boxes[f])):
-            assert cnt1[o] == len(ref["cuboids"][b])
-            for k in range(cnt1[o]):
-                assert int(out1[o, k]["proposal_index"]) == int(ref["cuboids"][b][k]["proposal_index"])
-                assert abs(float(out1[o, k]["normalized_error"]) - float(ref["cuboids"][b][k]["normalized_error"])) < 1e-9
+            n_knife += _compare_box(oracle, out1[o], cnt1[o], ref, b, redo)
             o += 1
+    assert n_knife == 0
     ctx.close()
 
 
@@ -193,6 +198,8 @@ def test_sequence_against_the_shipped_matlab_cuboids(det, fixture_b):
     ctx.close()
 
 
+@pytest.mark.skipif(os.environ.get("CS_LSD_SPECULATE", "0") in ("", "0"), reason="the ordered-speculation seed loop is off by default (cs_lsd.cu); "
+                    "CS_LSD_SPECULATE=1 runs it")
 def test_speculative_seed_loop_equals_the_sequential_kernel(det, oracle, fixture_a, fixture_b):
     """k_lsd_grow_par (ordered speculation, many warps per frame) against k_lsd_grow_seq (the plain seed loop, cs_set_profiling
     bit 7) and the oracle: raw segments in the same order, repeated to shake out interleavings; no frame may need the redo path."""

@@ -40,7 +40,11 @@ def main():
     flags = 128 if args.seq else 0
     ctx.set_profiling(1 | flags)
     ctx.upload_online(imgs, Ts, boxes, det.params(), cs.default_params())
+    import ctypes as C
+    prof = np.zeros(8, np.uint64)
     for r in range(args.reps):
+        if args.flavour == "lsd":
+            ctx.L.cs_debug_lsd_prof(ctx.h, None, 1)
         ctx.run()
         sm = ctx.stage_ms()
         msg = "%s %s frames %d: line stage %.3f ms (CUDA events), whole step %.3f ms" % (args.flavour, "seq" if args.seq else "par", args.frames, sm["lsd"], sm["total"])
@@ -48,6 +52,10 @@ def main():
             st, redo = det.seed_loop_stats(args.frames)
             msg += " | rounds mean %.1f max %d, processed %.0f, refused %.0f, regrown %.0f, redo %d" % (
                 st[:, 0].mean(), st[:, 0].max(), st[:, 1].mean(), st[:, 2].mean(), st[:, 3].mean(), redo.sum())
+            ctx.L.cs_debug_lsd_prof(ctx.h, prof.ctypes.data_as(C.POINTER(C.c_uint64)), 0)
+            pf = prof.astype(np.float64) / args.frames
+            msg += " | Mcycles/frame: grow %.2f rect %.2f refine %.2f count %.2f nfa %.2f kernel %.2f, candidates/frame %.0f" % (
+                pf[0] / 1e6, pf[1] / 1e6, pf[2] / 1e6, pf[3] / 1e6, pf[4] / 1e6, pf[6] / 1e6, pf[5])
         print(msg, flush=True)
 
 
