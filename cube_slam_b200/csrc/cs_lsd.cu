@@ -62,7 +62,7 @@
 #define LSD_SCAP 512         /* region entries of a warp's staging area kept in shared memory (the rest spills to HBM) */
 #define LSD_SPILL 16384      /* staging capacity per warp (entries), first LSD_SCAP in shared memory */
 #define LSD_WINDOW 4096      /* list positions ahead of the frontier that may be speculated on */
-#define LSD_SEQ_SCAP 1536    /* region entries k_lsd_grow_seq keeps in shared memory (the rest spill to HBM; small, so that many frames share an SM) */
+#define LSD_SEQ_SCAP 2048    /* region entries k_lsd_grow_seq keeps in shared memory (the rest spill to HBM; small, so that many frames share an SM) */
 #define LSD_FREE 0xffffffffu
 #define LSD_ST_NEW 0u
 #define LSD_ST_GROWING 1u
@@ -207,23 +207,32 @@ __global__ void __launch_bounds__(256) k_lsd_grad(const double *__restrict__ sca
     /* grid: x over the pixels of one scaled frame, y = frame */
     const int f = blockIdx.y;
     const int addr = blockIdx.x * blockDim.x + threadIdx.x;
-    if (addr >= W * H) return;
+    const bool inside = addr < W * H; /* no early exit: the warp reduces its maximum below */
     const size_t p = (size_t)f * W * H + addr;
     {
         const int y = addr / W, x = addr - y * W;
         const double *im = scaled + (size_t)f * W * H;
         double norm = 0;
         float deg = -1.f;
-        if (x < W - 1 && y < H - 1) {
+        if (inside && x < W - 1 && y < H - 1) {
             const double DA = im[addr + W + 1] - im[addr];
             const double BC = im[addr + 1] - im[addr + W];
             const double gx = DA + BC, gy = DA - BC;
             norm = sqrt((gx * gx + gy * gy) / 4);
-            if (!(norm <= threshold)) {
-                deg = fast_atan2((float)gx, (float)(-gy));
-                atomicMax(max_bits + f, (unsigned long long)__double_as_longlong(norm)); /* positive doubles order like integers */
-            }
+            if (!(norm <= threshold)) deg = fast_atan2((float)gx, (float)(-gy));
         }
+        {
+            /* per-frame maximum of the defined gradients: one atomic per warp (positive doubles order like integers; a block never
+             * straddles two frames) */
+            unsigned long long mb = deg >= 0.f ? (unsigned long long)__double_as_longlong(norm) : 0ull;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                const unsigned long long t = __shfl_xor_sync(0xffffffffu, mb, o);
+                mb = t > mb ? t : mb;
+            }
+            if ((threadIdx.x & 31) == 0 && mb) atomicMax(max_bits + f, mb);
+        }
+        if (!inside) return;
         modgrad[p] = norm;
         angf[p] = deg;
         uint4 r = make_uint4(__float_as_uint(deg), 0u, 0u, LSD_FREE);
@@ -354,8 +363,11 @@ struct LsdFrame {
     uint32_t *st;          /* per list position: state | invalid flag | record offset << 4 */
     int32_t *arena;        /* records of finished candidates */
     int arena_cap;
-    /* one warp per frame (k_lsd_grow_seq): the `used` map as a bit per pixel in shared memory; the claim words are not touched */
+    /* one warp per frame (k_lsd_grow_seq): the `used` map as a bit per pixel (HBM, read and written through L2 only, so that it costs
+     * no shared memory: the seed loop issues one instruction every ~6 cycles, and the more frames share an SM the better); the claim
+     * words are not touched */
     uint32_t *ubits;
+    __device__ __forceinline__ bool used_bit(int addr) const { return (__ldcg(ubits + (addr >> 5)) >> (addr & 31)) & 1u; }
     const double *lgam; /* log_gamma of small integers (cs_nfa.cuh) */
     unsigned long long wmagic; /* ceil(2^40 / W): row of a pixel address without an integer division (exact for addresses < 2^20 .. 2^30 / W) */
     __device__ __forceinline__ int row_of(int addr) const { return (int)(((unsigned long long)addr * wmagic) >> 40); }
@@ -562,7 +574,7 @@ __device__ int lsd_region_grow(const LsdFrame &F, const LsdView &V, const LsdReg
                     cseen = r.w;
                     int kind;
                     if (V.rank < 0)
-                        kind = ((F.ubits[c_addr >> 5] >> (c_addr & 31)) & 1u) ? LSD_K_USED : LSD_K_FREE;
+                        kind = F.used_bit(c_addr) ? LSD_K_USED : LSD_K_FREE;
                     else
                         kind = lsd_decode(cseen, V);
                     cand = (kind == LSD_K_FREE || kind == LSD_K_HIGHER || kind == LSD_K_MINE_FORMER || kind == LSD_K_LOWER);
@@ -1033,6 +1045,7 @@ struct LsdGrowArgs {
     int32_t *n_out;
     int cap;
     const double *lgam;  /* log_gamma table (cs_nfa.cuh) */
+    uint32_t *ubits;     /* (W * H + 31) / 32 words per frame: the used map of k_lsd_grow_seq */
     int32_t *redo;       /* per frame: 1 = the sequential kernel must redo this frame */
     int32_t *stats;      /* per frame: rounds, candidates processed, refused, invalidated (diagnostics) */
 };
@@ -1298,13 +1311,13 @@ __global__ void __launch_bounds__(32) k_lsd_grow_seq(LsdGrowArgs A)
     F.arena_cap = 0;
     extern __shared__ uint32_t s_seq[];
     const int n_words = (int)((npx + 31) >> 5);
-    F.ubits = s_seq;
+    F.ubits = A.ubits + (size_t)f * n_words;
     F.lgam = A.lgam;
     F.wmagic = ((1ull << 40) + (unsigned long long)A.W - 1) / (unsigned long long)A.W;
     for (int i = lane; i < n_words; i += 32) F.ubits[i] = 0u;
     __syncwarp();
     LsdReg R;
-    R.s = (int *)(s_seq + n_words); /* the first LSD_SEQ_SCAP region entries in shared memory, the rest in the (otherwise unused) record arena */
+    R.s = (int *)s_seq; /* the first LSD_SEQ_SCAP region entries in shared memory, the rest in the (otherwise unused) record arena */
     R.g = A.arena + (size_t)f * A.arena_cap;
     R.scap = LSD_SEQ_SCAP;
     R.cap = A.arena_cap;
@@ -1323,14 +1336,14 @@ __global__ void __launch_bounds__(32) k_lsd_grow_seq(LsdGrowArgs A)
         bool seed = false;
         if (i < n_list) {
             adx = list[i];
-            seed = !((F.ubits[adx >> 5] >> (adx & 31)) & 1u); /* the list holds pixels with a defined angle only */
+            seed = !F.used_bit(adx); /* the list holds pixels with a defined angle only */
         }
         unsigned todo = __ballot_sync(0xffffffffu, seed);
         while (todo) {
             const int sl = __ffs(todo) - 1;
             todo &= todo - 1;
             const int s_addr = __shfl_sync(0xffffffffu, adx, sl);
-            if ((F.ubits[s_addr >> 5] >> (s_addr & 31)) & 1u) continue; /* used by a region grown since the ballot */
+            if (F.used_bit(s_addr)) continue; /* used by a region grown since the ballot */
             int n_all = 0, has_line = 0;
             float line[4];
             const int rc = lsd_process_seed(F, V, R, s_addr, A.min_reg_size, A.prec, A.p, A.scale, n_all, has_line, line);
@@ -1359,7 +1372,7 @@ struct Buf {
 };
 
 struct LsdState {
-    Buf img, tmp, blur, scaled, modgrad, angf, pix, list, st, arena, spill, maxg, cnt, llen, raw, nraw, out, nout, redo, stats, lgam;
+    Buf img, tmp, blur, scaled, modgrad, angf, pix, list, st, arena, spill, maxg, cnt, llen, raw, nraw, out, nout, redo, stats, lgam, ubits;
     bool lgam_filled = false;
     int last_frames = 0, last_W = 0, last_H = 0, cap = 0;
 };
@@ -1415,7 +1428,7 @@ int lsd_run(cs_ctx *c, const uint8_t *imgs, bool imgs_on_device, int n_frames, i
         (rc = ensure(c, S.raw, (size_t)n_frames * cap * 16)) || (rc = ensure(c, S.nraw, (size_t)n_frames * 4)) ||
         (rc = ensure(c, S.out, (size_t)n_frames * cap * 16)) || (rc = ensure(c, S.nout, (size_t)n_frames * 4)) ||
         (rc = ensure(c, S.redo, (size_t)n_frames * 4)) || (rc = ensure(c, S.stats, (size_t)n_frames * 16)) ||
-        (rc = ensure(c, S.lgam, (size_t)CS_LGAMMA_TABLE * 8)))
+        (rc = ensure(c, S.lgam, (size_t)CS_LGAMMA_TABLE * 8)) || (rc = ensure(c, S.ubits, (size_t)n_frames * (((size_t)W * H + 31) / 32) * 4)))
         return rc;
     if (!S.lgam_filled) { /* log_gamma of the integers 1 .. CS_LGAMMA_TABLE - 1, host libm like the reference */
         std::vector<double> t(CS_LGAMMA_TABLE, 0.0);
@@ -1469,6 +1482,7 @@ int lsd_run(cs_ctx *c, const uint8_t *imgs, bool imgs_on_device, int n_frames, i
     A.n_out = (int32_t *)S.nout.p;
     A.cap = cap;
     A.lgam = (const double *)S.lgam.p;
+    A.ubits = (uint32_t *)S.ubits.p;
     A.redo = (int32_t *)S.redo.p;
     A.stats = (int32_t *)S.stats.p;
     /* The ordered-speculation kernel is off by default: on the GPU it is neither faster than one warp per frame (most of its candidates are
@@ -1476,9 +1490,7 @@ int lsd_run(cs_ctx *c, const uint8_t *imgs, bool imgs_on_device, int n_frames, i
     static const bool speculate = getenv("CS_LSD_SPECULATE") && atoi(getenv("CS_LSD_SPECULATE")) != 0;
     k_lsd_grow_par<<<n_frames, LSD_NW * 32, 0, st>>>(A, (cs_ctx_seq_lines(c) || !speculate) ? 1 : 0);
     {
-        const size_t smem = ((size_t)W * H + 31) / 32 * 4 + (size_t)LSD_SEQ_SCAP * 4;
-        if (smem > 200 * 1024) return cs_ctx_fail(c, CS_ERR_UNSUPPORTED, "frame too large for the LSD seed loop (%d x %d after scaling)", W, H);
-        CS_LSD_SET_SMEM(k_lsd_grow_seq, smem);
+        const size_t smem = (size_t)LSD_SEQ_SCAP * 4;
         k_lsd_grow_seq<<<n_frames, 32, smem, st>>>(A);
     }
     cs_ctx_count_launches(c, 9);
@@ -1515,7 +1527,7 @@ void cs_lsd_destroy(void *state)
 {
     LsdState *S = (LsdState *)state;
     Buf *all[] = {&S->img, &S->tmp, &S->blur, &S->scaled, &S->modgrad, &S->angf, &S->pix, &S->list, &S->st, &S->arena, &S->spill, &S->maxg, &S->cnt,
-                  &S->llen, &S->raw, &S->nraw, &S->out, &S->nout, &S->redo, &S->stats, &S->lgam};
+                  &S->llen, &S->raw, &S->nraw, &S->out, &S->nout, &S->redo, &S->stats, &S->lgam, &S->ubits};
     for (Buf *b : all)
         if (b->p) cudaFree(b->p);
     delete S;
