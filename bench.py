@@ -30,6 +30,9 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
+# several batches are kept in flight, three streams each: give the driver enough hardware queues that streams of different batches do not share
+# one (the default of 8 makes a long kernel of one batch delay work of another that happens to sit behind it in the same queue)
+os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
 
 WORKLOADS = {
     # name: (frames per GPU, width, height, boxes/frame, kind, poisson, param overrides, description)
@@ -252,6 +255,103 @@ class Mode(object):
                 cx.upload_online(wl["imgs"], wl["Ts"], wl["boxes"], self.lp, self.params)
 
 
+def make_line_params(cs, cx, use_lsd=True):
+    det = cs.line_lbd_detect(context=cx)
+    det.use_LSD = use_lsd
+    det.line_length_thres = LINE_LENGTH_THRES
+    return det.params()
+
+
+def nccl_library_path():
+    for d in sys.path:
+        cand = os.path.join(d, "nvidia", "nccl", "lib", "libnccl.so.2")
+        if os.path.exists(cand):
+            return cand
+    return ""
+
+
+def init_comm(cx, rank, world, dist, torch, _lib):
+    """The library's own NCCL communicator for this context: unique id from rank 0, broadcast over torch.distributed."""
+    path = nccl_library_path().encode()
+    uid = np.zeros(128, np.uint8)
+    if rank == 0:
+        cx.check(cx.L.cs_comm_unique_id(cx.h, path, _lib.ptr(uid, C.c_uint8)))
+    t = torch.from_numpy(uid).cuda()
+    dist.broadcast(t, 0)
+    uid = t.cpu().numpy()
+    cx.check(cx.L.cs_comm_init(cx.h, path, _lib.ptr(uid, C.c_uint8), world, rank))
+
+
+def measure_config(name, args, rank, world, local_rank, dist, cs, _lib, torch):
+    """One of the other BASELINE configurations at this rank count: every rank holds its shard (WORKLOADS[name] frames per GPU), two batches in
+    flight, online LSD lines, the top-K all-gather inside every step when N > 1.  Returns the dict that goes under the config's key."""
+    wl = make_workload(name, rank)
+    F, w, h = wl["F"], wl["w"], wl["h"]
+    params = cs.default_params(**wl["over"])
+    topk = int(params.max_cuboid_num)
+    ctxs = []
+    for _ in range(2):
+        cx = cs.Context(local_rank, w, h, F, 16, 8192)
+        cx.set_calibration(wl["K"])
+        ctxs.append(cx)
+    dev = torch.device("cuda", local_rank)
+    streams = [torch.cuda.ExternalStream(cx.stream(), device=dev) for cx in ctxs]
+    recs_per_rank = 0
+    if world > 1:
+        for cx in ctxs:
+            init_comm(cx, rank, world, dist, torch, _lib)
+        n_obj = torch.tensor([sum(len(b) for b in wl["boxes"])], device="cuda")
+        dist.all_reduce(n_obj, op=dist.ReduceOp.MAX)
+        recs_per_rank = int(n_obj.item()) * topk
+    lp = make_line_params(cs, ctxs[0])
+    for cx in ctxs:
+        cx.upload_online(wl["imgs"], wl["Ts"], wl["boxes"], lp, params)
+    gathered = C.c_void_p()
+
+    def step_i(i):
+        cx = ctxs[i % len(ctxs)]
+        cx.run_async()
+        if world > 1:
+            cx.check(cx.L.cs_allgather_topk(cx.h, recs_per_rank, C.byref(gathered)))
+
+    steps = max(4, min(args.steps // 8, 16))
+    steps -= steps % len(ctxs)
+    for i in range(2 * len(ctxs)):
+        step_i(i)
+    torch.cuda.synchronize()
+    st = ctxs[0].stats()
+    ev0 = torch.cuda.Event(enable_timing=True)
+    ev_end = [torch.cuda.Event(enable_timing=True) for _ in ctxs]
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    ev0.record(streams[0])
+    for s_ in streams[1:]:
+        s_.wait_event(ev0)
+    for i in range(steps):
+        step_i(i)
+    for e, s_ in zip(ev_end, streams):
+        e.record(s_)
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    ms = max(ev0.elapsed_time(e) for e in ev_end) / steps
+    t = torch.tensor([ms, float(st["n_valid"]), float(st["n_candidates"]), float(st["n_frames"]), float(st["n_objects"])], device="cuda", dtype=torch.float64)
+    allt = [t.clone()]
+    if world > 1:
+        allt = [torch.zeros_like(t) for _ in range(world)]
+        dist.all_gather(allt, t)
+    for cx in ctxs:
+        cx.close()
+    ms_max = max(float(x[0].item()) for x in allt)
+    valid = sum(float(x[1].item()) for x in allt)
+    frames = sum(float(x[3].item()) for x in allt)
+    return {"workload": wl["desc"], "ms_per_step": ms_max, "value": valid / (ms_max * 1e-3), "unit": "proposals/s", "frames_per_s": frames / (ms_max * 1e-3),
+            "candidates_per_s": sum(float(x[2].item()) for x in allt) / (ms_max * 1e-3), "steps": steps, "batches_in_flight": len(ctxs),
+            "frames_per_gpu": F, "boxes_total": sum(float(x[4].item()) for x in allt), "segments_per_frame_M": st["n_lines_in"] / max(st["n_frames"], 1),
+            "per_rank_ms_per_step": [float(x[0].item()) for x in allt]}
+
+
 def run_ours(args, rank, world, local_rank):
     import torch
     import cube_slam_b200 as cs
@@ -291,20 +391,8 @@ def run_ours(args, rank, world, local_rank):
     gathered = C.c_void_p()
     recs_per_rank = 0
     if world > 1:
-        nccl_path = None
-        for d in sys.path:
-            cand = os.path.join(d, "nvidia", "nccl", "lib", "libnccl.so.2")
-            if os.path.exists(cand):
-                nccl_path = cand
-                break
         for cx in ctxs:
-            uid = np.zeros(128, np.uint8)
-            if rank == 0:
-                cx.check(cx.L.cs_comm_unique_id(cx.h, (nccl_path or "").encode(), _lib.ptr(uid, C.c_uint8)))
-            t = torch.from_numpy(uid).cuda()
-            dist.broadcast(t, 0)
-            uid = t.cpu().numpy()
-            cx.check(cx.L.cs_comm_init(cx.h, (nccl_path or "").encode(), _lib.ptr(uid, C.c_uint8), world, rank))
+            init_comm(cx, rank, world, dist, torch, _lib)
         n_obj = torch.tensor([sum(len(b) for b in wl["boxes"])], device="cuda")
         dist.all_reduce(n_obj, op=dist.ReduceOp.MAX)
         recs_per_rank = int(n_obj.item()) * topk
@@ -342,6 +430,14 @@ def run_ours(args, rank, world, local_rank):
         ctx.run()
         stage = ctx.stage_ms()
         ctx.set_profiling(dbg_flags)
+        if with_gather:  # the all-gather alone, CUDA events on the context's stream
+            g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            barrier()
+            g0.record(streams[0])
+            ctx.check(ctx.L.cs_allgather_topk(ctx.h, recs_per_rank, C.byref(gathered)))
+            g1.record(streams[0])
+            torch.cuda.synchronize()
+            stage["allgather"] = g0.elapsed_time(g1)
         return ms, st, stage
 
     sampler = ClockSampler(local_rank)
@@ -360,7 +456,8 @@ def run_ours(args, rank, world, local_rank):
         allcnt = [torch.zeros_like(cnt) for _ in range(world)]
         dist.all_gather(allcnt, cnt)
         per_rank = {"ms_per_step": [float(x.item()) / args.steps for x in allms], "boxes": [float(x[3].item()) for x in allcnt],
-                    "valid": [float(x[0].item()) for x in allcnt]}
+                    "valid": [float(x[0].item()) for x in allcnt], "allgather_ms_rank0": stage_acc.get("allgather"),
+                    "allgather_bytes_per_rank": recs_per_rank * cs.CUBOID_DTYPE.itemsize}
         dist.all_reduce(ms_t, op=dist.ReduceOp.MAX)
         dist.all_reduce(cnt, op=dist.ReduceOp.SUM)
     ms_total = float(ms_t.item())
@@ -425,6 +522,14 @@ def run_ours(args, rank, world, local_rank):
     h2d = wl["imgs"].nbytes + wl["Ts"].nbytes + sum(np.asarray(b).nbytes for b in wl["boxes"])
     d2h = e2e_out[0][0].nbytes + e2e_out[0][1].nbytes
 
+    # ---- the other north-star configurations (BASELINE configs 4 and 5), a short run each, same protocol (online LSD, all-gather when N > 1)
+    other = {}
+    if not args.no_configs and args.workload == "c3":
+        for cx in ctxs:
+            cx.close()
+        ctxs = []
+        for name in ("c4", "c5"):
+            other[name] = measure_config(name, args, rank, world, local_rank, dist, cs, _lib, torch)
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -433,7 +538,7 @@ def run_ours(args, rank, world, local_rank):
     # ---- roofline of the dominant stage
     hbm_peak, peak_src = measured_peaks()
     shp = {"frame_px": w * h}
-    kernel_ms = {k: v for k, v in stage_acc.items() if k != "total"}
+    kernel_ms = {k: v for k, v in stage_acc.items() if k not in ("total", "allgather")}
     dom = max(kernel_ms, key=kernel_ms.get)
     dom_bytes = float(STAGE_BYTES[dom](stats, shp))
     achieved = dom_bytes / (kernel_ms[dom] * 1e-3) / 1e9 if kernel_ms[dom] > 0 else 0.0
@@ -488,6 +593,7 @@ def run_ours(args, rank, world, local_rank):
         "roofline": roofline, "cpu_baseline": cpu, "clocks": sampler.summary(),
     }
     line.update(extra)
+    line.update(other)
     if per_rank:
         line["per_rank"] = per_rank
     print(json.dumps(line))
@@ -504,6 +610,7 @@ def main():
     ap.add_argument("--workload", default="c3", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-extra", action="store_true", help="skip the lines-given / EDLines variants of the same frames")
+    ap.add_argument("--no-configs", action="store_true", help="skip the short runs of BASELINE configs 4 and 5 (keys c4, c5)")
     ap.add_argument("--no-prio", action="store_true", help="A/B: keep each batch's whole chain on one stream (no high-priority tail)")
     ap.add_argument("--raster-dt", action="store_true", help="A/B: two-pass raster-scan distance transform kernel instead of the cone form")
     ap.add_argument("--seq-lines", action="store_true", help="A/B: the line detectors' sequential kernels (one warp per frame) instead of ordered speculation")

@@ -60,7 +60,7 @@ EXPORTS = [
     "cs_default_line_params", "cs_set_calibration", "cs_cam_pose", "cs_cuboid_measurement", "cs_cuboid_measurement_orb", "cs_detect_cuboids", "cs_detect_cuboids_batch",
     "cs_batch_upload", "cs_batch_upload_online", "cs_detect_frames_batch", "cs_batch_run", "cs_batch_run_async", "cs_batch_fetch", "cs_batch_stats_get",
     "cs_batch_device_records", "cs_stream", "cs_stage_ms", "cs_set_profiling", "cs_debug_roi",
-    "cs_debug_candidates", "cs_detect_lines", "cs_detect_lines_batch", "cs_debug_lsd", "cs_debug_lsd_stats", "cs_debug_lsd_prof", "cs_debug_atan2", "cs_atan2_host", "cs_debug_edlines", "cs_debug_stage_offsets", "cs_comm_unique_id", "cs_comm_init",
+    "cs_debug_candidates", "cs_detect_lines", "cs_detect_lines_batch", "cs_debug_lsd", "cs_debug_lsd_stats", "cs_debug_lsd_prof", "cs_debug_atan2", "cs_atan2_host", "cs_cuboid_draw_edges", "cs_debug_edlines", "cs_debug_stage_offsets", "cs_comm_unique_id", "cs_comm_init",
     "cs_allgather_topk", "cs_fetch_gathered",
 ]
 
@@ -114,6 +114,7 @@ def load():
     L.cs_debug_atan2.argtypes = [vp, d_p, d_p, d_p, i]
     L.cs_atan2_host.argtypes = [C.c_double, C.c_double]
     L.cs_atan2_host.restype = C.c_double
+    L.cs_cuboid_draw_edges.argtypes = [vp, i32_p]
     L.cs_debug_edlines.argtypes = [vp, i, u8_p, C.POINTER(C.c_int16), C.POINTER(C.c_int16), C.POINTER(C.c_int16), u8_p, i32_p, i32_p, u8_p, f_p, i32_p, i]
     L.cs_comm_unique_id.argtypes = [vp, C.c_char_p, u8_p]
     L.cs_comm_init.argtypes = [vp, C.c_char_p, u8_p, i, i]

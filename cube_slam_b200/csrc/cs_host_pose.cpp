@@ -255,3 +255,27 @@ void cuboid_measurement(const double *pos, double rotY, const double *cam_t, con
 }
 
 }  // namespace cshost
+
+
+/* get_cuboid_draw_edge_markers(final_universal_object = true) + plot_image_with_cuboid_edges' marker table
+ * (detect_3d_cuboid/src/object_3d_util.cpp:56-69,80-92,109-112): the 12 edges of a detected cuboid as the reference draws them. */
+extern "C" int cs_cuboid_draw_edges(const cs_cuboid_rec *rec, int32_t edges[12][8])
+{
+    if (!rec || !edges) return CS_ERR_INVALID_ARG;
+    /* rows: start corner, end corner (1-based, as the reference writes them), marker type (1-based) */
+    static const int cfg1_left[12][3] = {{3, 4, 4}, {4, 1, 2}, {4, 8, 6}, {1, 2, 3}, {2, 3, 1}, {2, 6, 5}, {1, 5, 5}, {3, 7, 5}, {5, 6, 3}, {6, 7, 1}, {7, 8, 3}, {8, 5, 1}};
+    static const int cfg1_right[12][3] = {{2, 3, 2}, {3, 4, 4}, {3, 7, 6}, {1, 2, 3}, {1, 4, 1}, {2, 6, 5}, {1, 5, 5}, {4, 8, 5}, {5, 6, 3}, {6, 7, 1}, {7, 8, 3}, {8, 5, 1}};
+    static const int cfg2[12][3] = {{2, 3, 2}, {3, 4, 4}, {4, 1, 2}, {3, 7, 6}, {4, 8, 6}, {1, 2, 3}, {2, 6, 5}, {1, 5, 5}, {5, 6, 3}, {6, 7, 1}, {7, 8, 3}, {8, 5, 1}};
+    /* line_markers: B, G, R, thickness */
+    static const int markers[6][4] = {{0, 0, 255, 2}, {0, 0, 255, 1}, {0, 255, 0, 2}, {0, 255, 0, 1}, {255, 0, 0, 2}, {255, 0, 0, 1}};
+    const int(*tab)[3] = (rec->box_config_type[0] == 1) ? ((rec->box_config_type[1] == 1) ? cfg1_left : cfg1_right) : cfg2;
+    for (int e = 0; e < 12; e++) {
+        const int a = tab[e][0] - 1, b = tab[e][1] - 1, m = tab[e][2] - 1;
+        edges[e][0] = rec->box_corners_2d[0 * 8 + a];
+        edges[e][1] = rec->box_corners_2d[1 * 8 + a];
+        edges[e][2] = rec->box_corners_2d[0 * 8 + b];
+        edges[e][3] = rec->box_corners_2d[1 * 8 + b];
+        for (int k = 0; k < 4; k++) edges[e][4 + k] = markers[m][k];
+    }
+    return CS_OK;
+}

@@ -62,6 +62,7 @@
 #define LSD_SCAP 512         /* region entries of a warp's staging area kept in shared memory (the rest spills to HBM) */
 #define LSD_SPILL 16384      /* staging capacity per warp (entries), first LSD_SCAP in shared memory */
 #define LSD_WINDOW 4096      /* list positions ahead of the frontier that may be speculated on */
+#define LSD_CAND_CAP 2048    /* candidate rectangles per frame handed from the seed loop to k_lsd_validate */
 #define LSD_SEQ_SCAP 2048    /* region entries k_lsd_grow_seq keeps in shared memory (the rest spill to HBM; small, so that many frames share an SM) */
 #define LSD_FREE 0xffffffffu
 #define LSD_ST_NEW 0u
@@ -150,6 +151,52 @@ __global__ void __launch_bounds__(256) k_lsd_vblur(const double *__restrict__ tm
 #pragma unroll
         for (int k = 1; k <= 3; k++) s += c_gauss7[3 + k] * (base[(size_t)reflect101(y + k, h) * w + x] + base[(size_t)reflect101(y - k, h) * w + x]);
         blur[p] = s;
+    }
+}
+
+/* cvtColor + the 7 x 7 Gaussian (both passes) on 64 x 16 tiles: the gray value of a pixel is computed once (k_lsd_hblur recomputes it for
+ * each of its seven taps) and the horizontal sums never leave shared memory.  Same operations in the same order as k_lsd_hblur followed
+ * by k_lsd_vblur (which stay as the A/B path, cs_set_profiling bit 7). */
+#define LSB_TW 64
+#define LSB_TH 16
+__global__ void __launch_bounds__(256) k_lsd_blur(const uint8_t *__restrict__ img, int w, int h, int stride, int channels, double *__restrict__ blur)
+{
+    __shared__ uint8_t s_g[LSB_TH + 6][LSB_TW + 8];
+    __shared__ double s_h[LSB_TH + 6][LSB_TW];
+    const int f = blockIdx.z, x0 = blockIdx.x * LSB_TW, y0 = blockIdx.y * LSB_TH, tid = threadIdx.x;
+    const uint8_t *frame = img + (size_t)f * h * stride;
+    for (int i = tid; i < (LSB_TH + 6) * (LSB_TW + 6); i += 256) {
+        const int r = i / (LSB_TW + 6), c = i - r * (LSB_TW + 6);
+        const int yy = reflect101(y0 - 3 + r, h), xx = reflect101(x0 - 3 + c, w);
+        const uint8_t *q = frame + (size_t)yy * stride;
+        uint32_t g;
+        if (channels == 3) {
+            q += 3 * xx;
+            g = (q[0] * 3735u + q[1] * 19235u + q[2] * 9798u + (1u << 14)) >> 15;
+        } else
+            g = q[xx];
+        s_g[r][c] = (uint8_t)g;
+    }
+    __syncthreads();
+    for (int i = tid; i < (LSB_TH + 6) * LSB_TW; i += 256) {
+        const int r = i / LSB_TW, c = i - r * LSB_TW;
+        double s = 0;
+#pragma unroll
+        for (int k = 0; k < 7; k++) {
+            const double t = c_gauss7[k] * (double)(int)s_g[r][c + k];
+            s = (k == 0) ? t : s + t;
+        }
+        s_h[r][c] = s;
+    }
+    __syncthreads();
+    for (int i = tid; i < LSB_TH * LSB_TW; i += 256) {
+        const int r = i / LSB_TW, c = i - r * LSB_TW;
+        const int x = x0 + c, y = y0 + r;
+        if (x >= w || y >= h) continue;
+        double s = c_gauss7[3] * s_h[r + 3][c];
+#pragma unroll
+        for (int k = 1; k <= 3; k++) s += c_gauss7[3 + k] * (s_h[r + 3 + k][c] + s_h[r + 3 - k][c]);
+        blur[((size_t)f * h + y) * w + x] = s;
     }
 }
 
@@ -343,6 +390,61 @@ __global__ void __launch_bounds__(32) k_lsd_scatter(const double *__restrict__ m
     }
 }
 
+/* the same scatter with one warp per ROW of the chunk: row histograms in shared memory, a prefix over the rows of each bin, then every warp
+ * walks only its own row (the chain of dependent steps is 8 times shorter than k_lsd_scatter's; that one stays as the A/B path) */
+__global__ void __launch_bounds__(32 * LSD_CHUNK_ROWS) k_lsd_scatter_rows(const double *__restrict__ modgrad, const float *__restrict__ angf, int W, int H, int n_chunks,
+                                                                          const unsigned long long *__restrict__ max_bits, const int32_t *__restrict__ cnt,
+                                                                          int32_t *__restrict__ list)
+{
+    __shared__ int s_c[LSD_CHUNK_ROWS][LSD_NBINS];
+    const int f = blockIdx.x / n_chunks, ch = blockIdx.x - f * n_chunks;
+    const int tid = threadIdx.x, lane = tid & 31, r = tid >> 5;
+    const int32_t *base = cnt + ((size_t)f * n_chunks + ch) * LSD_NBINS;
+    for (int i = lane; i < LSD_NBINS; i += 32) s_c[r][i] = 0;
+    __syncwarp();
+    const double coef = bin_coef_of(max_bits[f]);
+    const int y = ch * LSD_CHUNK_ROWS + r;
+    const bool row_ok = y < H - 1;
+    const double *mg = modgrad + (size_t)f * W * H + (size_t)y * W;
+    const float *an = angf + (size_t)f * W * H + (size_t)y * W;
+    int32_t *out = list + (size_t)f * W * H;
+    if (row_ok)
+        for (int x = lane; x < W - 1; x += 32)
+            if (an[x] >= 0.f) atomicAdd(&s_c[r][(int)(mg[x] * coef)], 1);
+    __syncthreads();
+    for (int b = tid; b < LSD_NBINS; b += 32 * LSD_CHUNK_ROWS) {
+        int run = base[b];
+#pragma unroll
+        for (int k = 0; k < LSD_CHUNK_ROWS; k++) {
+            const int v = s_c[k][b];
+            s_c[k][b] = run;
+            run += v;
+        }
+    }
+    __syncthreads();
+    if (!row_ok) return;
+    for (int x0 = 0; x0 < W - 1; x0 += 32) {
+        const int x = x0 + lane;
+        bool ok = x < W - 1;
+        int bin = -1 - lane; /* inactive lanes get unique negative keys */
+        if (ok) {
+            ok = an[x] >= 0.f;
+            if (ok) bin = (int)(mg[x] * coef);
+        }
+        const unsigned m = __match_any_sync(0xffffffffu, bin);
+        const int rank = __popc(m & ((1u << lane) - 1u));
+        const int leader = __ffs(m) - 1;
+        int old = 0;
+        if (ok && lane == leader) {
+            old = s_c[r][bin];
+            s_c[r][bin] = old + __popc(m);
+        }
+        old = __shfl_sync(0xffffffffu, old, leader);
+        if (ok) out[old + rank] = y * W + x;
+        __syncwarp();
+    }
+}
+
 /* ---------------------------------------------------------------------------------------- the seed loop */
 /* cycle counters of the seed loop's phases (diagnostics, cs_debug_lsd_prof): grow, region2rect, refine, rectangle counts, binomial tails,
  * candidates, list scan */
@@ -516,7 +618,7 @@ __device__ __forceinline__ bool lsd_demote(const LsdFrame &F, const LsdView &V, 
     return atomicCAS(cw, me0, me0 | 1u) == me0;
 }
 /* give back every claim the candidate still holds on the listed pixels */
-__device__ void lsd_release(const LsdFrame &F, int rank, const LsdReg &R, int n)
+__device__ __noinline__ void lsd_release(const LsdFrame &F, int rank, const LsdReg &R, int n)
 {
     const int lane = threadIdx.x & 31;
     for (int i = lane; i < n; i += 32) {
@@ -703,7 +805,7 @@ __device__ void lsd_region2rect(const LsdFrame &F, const LsdReg &R, int base, in
 
 /* lsd.cpp:834-871 (lane 0 replays the reference's in-place compaction; it fixes the order later sums run in).
  * Returns 0 ok, 1 claim lost, 3 region rejected. */
-__device__ int lsd_reduce_region_radius(const LsdFrame &F, const LsdView &V, const LsdReg &R, int base, int &reg_size, double reg_angle, double prec, double p,
+__device__ __noinline__ int lsd_reduce_region_radius(const LsdFrame &F, const LsdView &V, const LsdReg &R, int base, int &reg_size, double reg_angle, double prec, double p,
                                         LsdRect &rec, double density, double density_th)
 {
     const int lane = threadIdx.x & 31;
@@ -871,7 +973,7 @@ __device__ void lsd_rect_count(const LsdFrame &F, const LsdRect &rec, int &total
 
 /* the NFA of up to five rectangles of one rect_improve phase: counts one rectangle after the other (rows across lanes), then the
  * binomial tails, each by the whole warp (cs_nfa.cuh) */
-__device__ void lsd_rect_nfa5(const LsdFrame &F, const LsdRect *r, int n, double *v)
+__device__ __noinline__ void lsd_rect_nfa5(const LsdFrame &F, const LsdRect *r, int n, double *v)
 {
     int tot[5], alg[5];
     {
@@ -948,13 +1050,16 @@ __device__ double lsd_rect_improve(const LsdFrame &F, LsdRect &rec)
 
 /* One seed, start to finish (the body of the loop lsd.cpp:478-535).  Returns 0 done (has_line / line set), 1 refused, 2 overflow.
  * n_all = entries of R that hold every pixel the candidate ever claimed. */
-__device__ int lsd_process_seed(const LsdFrame &F, const LsdView &V, const LsdReg &R, int s_addr, int min_reg_size, double prec, double p, double scale,
-                                int &n_all, int &has_line, float *line)
+/* The first half of one seed (lsd.cpp:478-519): grow, rectangle, density refinement.  has_rect = 1 when a rectangle comes out that
+ * rect_improve / the NFA test still have to judge -- which they can do later, in any order and in parallel: they read the level-line
+ * angles only and never touch the `used` map.  Returns 0 done, 1 refused, 2 overflow. */
+__device__ int lsd_grow_candidate(const LsdFrame &F, const LsdView &V, const LsdReg &R, int s_addr, int min_reg_size, double prec, double p, int &n_all,
+                                  int &has_rect, LsdRect &rec)
 {
-    const double DENSITY_TH = 0.7, LOG_EPS = 0;
+    const double DENSITY_TH = 0.7;
     int base = 0, reg_size = 0;
     double reg_angle = 0;
-    has_line = 0;
+    has_rect = 0;
     n_all = 0;
     int rc;
     {
@@ -966,7 +1071,6 @@ __device__ int lsd_process_seed(const LsdFrame &F, const LsdView &V, const LsdRe
     n_all = reg_size;
     if (rc) return rc;
     if (reg_size < min_reg_size) return 0;
-    LsdRect rec;
     {
         LSD_PROF_T0();
         lsd_region2rect(F, R, 0, reg_size, reg_angle, prec, p, rec);
@@ -979,8 +1083,16 @@ __device__ int lsd_process_seed(const LsdFrame &F, const LsdView &V, const LsdRe
     }
     if (rc == 3) return 0;
     if (rc) return rc;
+    has_rect = 1;
+    return 0;
+}
+
+/* The second half (lsd.cpp:520-534): rect_improve, NFA test, back to image coordinates.  Returns whether the rectangle is a line. */
+__device__ bool lsd_validate_rect(const LsdFrame &F, LsdRect &rec, double scale, float *line)
+{
+    const double LOG_EPS = 0;
     const double log_nfa = lsd_rect_improve(F, rec);
-    if (log_nfa <= LOG_EPS) return 0;
+    if (log_nfa <= LOG_EPS) return false;
     rec.x1 += 0.5;
     rec.y1 += 0.5;
     rec.x2 += 0.5;
@@ -993,7 +1105,20 @@ __device__ int lsd_process_seed(const LsdFrame &F, const LsdView &V, const LsdRe
     line[1] = (float)rec.y1;
     line[2] = (float)rec.x2;
     line[3] = (float)rec.y2;
-    has_line = 1;
+    return true;
+}
+
+/* One seed, start to finish (the body of the loop lsd.cpp:478-535).  Returns 0 done (has_line / line set), 1 refused, 2 overflow.
+ * n_all = entries of R that hold every pixel the candidate ever claimed. */
+__device__ int lsd_process_seed(const LsdFrame &F, const LsdView &V, const LsdReg &R, int s_addr, int min_reg_size, double prec, double p, double scale,
+                                int &n_all, int &has_line, float *line)
+{
+    LsdRect rec;
+    int has_rect = 0;
+    has_line = 0;
+    const int rc = lsd_grow_candidate(F, V, R, s_addr, min_reg_size, prec, p, n_all, has_rect, rec);
+    if (rc || !has_rect) return rc;
+    has_line = lsd_validate_rect(F, rec, scale, line) ? 1 : 0;
     return 0;
 }
 
@@ -1044,6 +1169,11 @@ struct LsdGrowArgs {
     float *out;
     int32_t *n_out;
     int cap;
+    LsdRect *cand;       /* cand_cap rectangles per frame, seed order: k_lsd_grow_seq -> k_lsd_validate */
+    int32_t *n_cand;
+    int cand_cap;
+    int32_t *cand_line;  /* per candidate: {is a line, 4 floats} */
+    int32_t *err;        /* bit 2: more candidates in a frame than cand_cap */
     const double *lgam;  /* log_gamma table (cs_nfa.cuh) */
     uint32_t *ubits;     /* (W * H + 31) / 32 words per frame: the used map of k_lsd_grow_seq */
     int32_t *redo;       /* per frame: 1 = the sequential kernel must redo this frame */
@@ -1326,9 +1456,7 @@ __global__ void __launch_bounds__(32) k_lsd_grow_seq(LsdGrowArgs A)
     V.frontier = 0;
     const int32_t *list = A.list + f * npx;
     const int n_list = A.list_len[f];
-    float *raw = A.raw + (size_t)f * A.cap * 4;
-    float *out = A.out + (size_t)f * A.cap * 4;
-    int n_raw = 0, n_out = 0;
+    int n_cand = 0;
     for (int i0 = 0; i0 < n_list; i0 += 32) {
         /* 32 list entries at a time: seeds whose pixel is already used are skipped by ballot */
         const int i = i0 + lane;
@@ -1344,25 +1472,118 @@ __global__ void __launch_bounds__(32) k_lsd_grow_seq(LsdGrowArgs A)
             todo &= todo - 1;
             const int s_addr = __shfl_sync(0xffffffffu, adx, sl);
             if (F.used_bit(s_addr)) continue; /* used by a region grown since the ballot */
-            int n_all = 0, has_line = 0;
-            float line[4];
-            const int rc = lsd_process_seed(F, V, R, s_addr, A.min_reg_size, A.prec, A.p, A.scale, n_all, has_line, line);
-            if (rc || !has_line) continue; /* rc == 2 (a region larger than the whole arena) cannot happen: arena_cap >= W * H + 27 */
-            if (lane == 0 && n_raw < A.cap)
-                for (int k = 0; k < 4; k++) raw[4 * n_raw + k] = line[k];
-            n_raw++;
-            float fo[4];
-            if (!lsd_keyline_filter(line, A.img_w, A.img_h, A.line_length_thres, fo)) continue;
-            if (lane == 0 && n_out < A.cap)
-                for (int k = 0; k < 4; k++) out[4 * n_out + k] = fo[k];
-            n_out++;
+            int n_all = 0, has_rect = 0;
+            LsdRect rec;
+            const int rc = lsd_grow_candidate(F, V, R, s_addr, A.min_reg_size, A.prec, A.p, n_all, has_rect, rec);
+            if (rc || !has_rect) continue; /* rc == 2 (a region larger than the whole arena) cannot happen: arena_cap >= W * H + 27 */
+            /* the rectangle goes to k_lsd_validate (rect_improve + NFA never touch the used map): candidates in seed order */
+            if (lane == 0 && n_cand < A.cand_cap) A.cand[(size_t)f * A.cand_cap + n_cand] = rec;
+            n_cand++;
         }
     }
     if (lane == 0) {
-        A.n_raw[f] = n_raw;
-        A.n_out[f] = n_out;
+        A.n_cand[f] = n_cand;
+        if (n_cand > A.cand_cap) atomicOr(A.err, 4);
     }
     LSD_PROF_ADD(6);
+}
+
+/* rect_improve + NFA of every candidate rectangle (lsd.cpp:520-534), one warp each: thousands of warps running the same code. */
+__global__ void __launch_bounds__(128) k_lsd_validate(LsdGrowArgs A)
+{
+    const int f = blockIdx.y, lane = threadIdx.x & 31;
+    if (!A.redo[f]) return;
+    const size_t npx = (size_t)A.W * A.H;
+    LsdFrame F;
+    F.W = A.W;
+    F.H = A.H;
+    F.pix = A.pix + f * npx;
+    F.angf = A.angf + f * npx;
+    F.modgrad = A.modgrad + f * npx;
+    F.LOG_NT = A.LOG_NT;
+    F.st = nullptr;
+    F.arena = nullptr;
+    F.arena_cap = 0;
+    F.ubits = nullptr;
+    F.lgam = A.lgam;
+    F.wmagic = 0;
+    const int n = min(A.n_cand[f], A.cand_cap);
+    const int wpb = blockDim.x >> 5;
+    for (int c = blockIdx.x * wpb + (threadIdx.x >> 5); c < n; c += gridDim.x * wpb) {
+        LsdRect rec = A.cand[(size_t)f * A.cand_cap + c];
+        float line[4] = {0.f, 0.f, 0.f, 0.f};
+        const bool ok = lsd_validate_rect(F, rec, A.scale, line);
+        if (lane == 0) {
+            int32_t *o = A.cand_line + ((size_t)f * A.cand_cap + c) * 5;
+            o[0] = ok ? 1 : 0;
+            for (int k = 0; k < 4; k++) o[1 + k] = __float_as_int(line[k]);
+        }
+    }
+}
+
+/* the accepted candidates of a frame in seed order: raw segments, and those that pass the key-line filter */
+__global__ void __launch_bounds__(256) k_lsd_emit(LsdGrowArgs A)
+{
+    __shared__ int s_warp_cnt[8], s_base_raw, s_base_out;
+    const int f = blockIdx.x, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    if (!A.redo[f]) return;
+    const unsigned FULL = 0xffffffffu;
+    const int n = min(A.n_cand[f], A.cand_cap);
+    float *raw = A.raw + (size_t)f * A.cap * 4;
+    float *out = A.out + (size_t)f * A.cap * 4;
+    if (tid == 0) {
+        s_base_raw = 0;
+        s_base_out = 0;
+    }
+    __syncthreads();
+    for (int b = 0; b < n; b += 256) {
+        const int i = b + tid;
+        bool has = false, kept = false;
+        float ln[4], fo[4];
+        if (i < n) {
+            const int32_t *o = A.cand_line + ((size_t)f * A.cand_cap + i) * 5;
+            if (o[0]) {
+                has = true;
+                for (int k = 0; k < 4; k++) ln[k] = __int_as_float(o[1 + k]);
+                kept = lsd_keyline_filter(ln, A.img_w, A.img_h, A.line_length_thres, fo);
+            }
+        }
+        const unsigned mh = __ballot_sync(FULL, has), mk = __ballot_sync(FULL, kept);
+        if (lane == 0) s_warp_cnt[wid] = __popc(mh) | (__popc(mk) << 16);
+        __syncthreads();
+        int pre_r = s_base_raw, pre_o = s_base_out;
+        for (int k = 0; k < wid; k++) {
+            pre_r += s_warp_cnt[k] & 0xffff;
+            pre_o += s_warp_cnt[k] >> 16;
+        }
+        if (has) {
+            const int slot = pre_r + __popc(mh & ((1u << lane) - 1u));
+            if (slot < A.cap)
+                for (int k = 0; k < 4; k++) raw[4 * slot + k] = ln[k];
+        }
+        if (kept) {
+            const int slot = pre_o + __popc(mk & ((1u << lane) - 1u));
+            if (slot < A.cap)
+                for (int k = 0; k < 4; k++) out[4 * slot + k] = fo[k];
+        }
+        __syncthreads();
+        if (tid == 0) {
+            int tr = 0, to = 0;
+            for (int k = 0; k < 8; k++) {
+                tr += s_warp_cnt[k] & 0xffff;
+                to += s_warp_cnt[k] >> 16;
+            }
+            s_base_raw += tr;
+            s_base_out += to;
+        }
+        __syncthreads();
+    }
+    if (tid == 0) {
+        /* more candidate rectangles than the hand-off buffer holds: report it the way a segment overflow is reported (count > capacity) */
+        const bool overflow = A.n_cand[f] > A.cand_cap;
+        A.n_raw[f] = overflow ? A.cap + 1 : s_base_raw;
+        A.n_out[f] = overflow ? A.cap + 1 : s_base_out;
+    }
 }
 
 /* ---------------------------------------------------------------------------------------- host side */
@@ -1372,7 +1593,7 @@ struct Buf {
 };
 
 struct LsdState {
-    Buf img, tmp, blur, scaled, modgrad, angf, pix, list, st, arena, spill, maxg, cnt, llen, raw, nraw, out, nout, redo, stats, lgam, ubits;
+    Buf img, tmp, blur, scaled, modgrad, angf, pix, list, st, arena, spill, maxg, cnt, llen, raw, nraw, out, nout, redo, stats, lgam, ubits, cand, ncand, candline, err;
     bool lgam_filled = false;
     int last_frames = 0, last_W = 0, last_H = 0, cap = 0;
 };
@@ -1428,7 +1649,9 @@ int lsd_run(cs_ctx *c, const uint8_t *imgs, bool imgs_on_device, int n_frames, i
         (rc = ensure(c, S.raw, (size_t)n_frames * cap * 16)) || (rc = ensure(c, S.nraw, (size_t)n_frames * 4)) ||
         (rc = ensure(c, S.out, (size_t)n_frames * cap * 16)) || (rc = ensure(c, S.nout, (size_t)n_frames * 4)) ||
         (rc = ensure(c, S.redo, (size_t)n_frames * 4)) || (rc = ensure(c, S.stats, (size_t)n_frames * 16)) ||
-        (rc = ensure(c, S.lgam, (size_t)CS_LGAMMA_TABLE * 8)) || (rc = ensure(c, S.ubits, (size_t)n_frames * (((size_t)W * H + 31) / 32) * 4)))
+        (rc = ensure(c, S.lgam, (size_t)CS_LGAMMA_TABLE * 8)) || (rc = ensure(c, S.ubits, (size_t)n_frames * (((size_t)W * H + 31) / 32) * 4)) ||
+        (rc = ensure(c, S.cand, (size_t)n_frames * LSD_CAND_CAP * sizeof(LsdRect))) || (rc = ensure(c, S.ncand, (size_t)n_frames * 4)) ||
+        (rc = ensure(c, S.candline, (size_t)n_frames * LSD_CAND_CAP * 20)) || (rc = ensure(c, S.err, 16)))
         return rc;
     if (!S.lgam_filled) { /* log_gamma of the integers 1 .. CS_LGAMMA_TABLE - 1, host libm like the reference */
         std::vector<double> t(CS_LGAMMA_TABLE, 0.0);
@@ -1447,14 +1670,21 @@ int lsd_run(cs_ctx *c, const uint8_t *imgs, bool imgs_on_device, int n_frames, i
     cudaMemsetAsync(S.st.p, 0, spx * 4, st);
     cudaMemsetAsync(S.stats.p, 0, (size_t)n_frames * 16, st);
     const dim3 g_src((w * h + 255) / 256, n_frames), g_dst((W * H + 255) / 256, n_frames);
-    k_lsd_hblur<<<g_src, 256, 0, st>>>(d_img, n_frames, w, h, stride, channels, (double *)S.tmp.p);
-    k_lsd_vblur<<<g_src, 256, 0, st>>>((const double *)S.tmp.p, n_frames, w, h, (double *)S.blur.p);
+    if (cs_ctx_seq_lines(c)) { /* A/B: the two-pass kernels */
+        k_lsd_hblur<<<g_src, 256, 0, st>>>(d_img, n_frames, w, h, stride, channels, (double *)S.tmp.p);
+        k_lsd_vblur<<<g_src, 256, 0, st>>>((const double *)S.tmp.p, n_frames, w, h, (double *)S.blur.p);
+    } else
+        k_lsd_blur<<<dim3((w + LSB_TW - 1) / LSB_TW, (h + LSB_TH - 1) / LSB_TH, n_frames), 256, 0, st>>>(d_img, w, h, stride, channels, (double *)S.blur.p);
     k_lsd_resize<<<g_dst, 256, 0, st>>>((const double *)S.blur.p, n_frames, w, h, W, H, 1. / SCALE, (double *)S.scaled.p);
     k_lsd_grad<<<g_dst, 256, 0, st>>>((const double *)S.scaled.p, n_frames, W, H, rho, (double *)S.modgrad.p, (float *)S.angf.p,
                                                        (uint4 *)S.pix.p, (unsigned long long *)S.maxg.p);
     k_lsd_hist<<<n_frames * n_chunks, 256, 0, st>>>((const double *)S.modgrad.p, (const float *)S.angf.p, W, H, n_chunks, (const unsigned long long *)S.maxg.p, (int32_t *)S.cnt.p);
     k_lsd_scan<<<n_frames, LSD_NBINS, 0, st>>>(n_chunks, (int32_t *)S.cnt.p, (int32_t *)S.llen.p);
-    k_lsd_scatter<<<n_frames * n_chunks, 32, 0, st>>>((const double *)S.modgrad.p, (const float *)S.angf.p, W, H, n_chunks, (const unsigned long long *)S.maxg.p,
+    if (cs_ctx_seq_lines(c))
+        k_lsd_scatter<<<n_frames * n_chunks, 32, 0, st>>>((const double *)S.modgrad.p, (const float *)S.angf.p, W, H, n_chunks, (const unsigned long long *)S.maxg.p,
+                                                      (const int32_t *)S.cnt.p, (int32_t *)S.list.p);
+    else
+        k_lsd_scatter_rows<<<n_frames * n_chunks, 32 * LSD_CHUNK_ROWS, 0, st>>>((const double *)S.modgrad.p, (const float *)S.angf.p, W, H, n_chunks, (const unsigned long long *)S.maxg.p,
                                                       (const int32_t *)S.cnt.p, (int32_t *)S.list.p);
     LsdGrowArgs A;
     A.W = W;
@@ -1483,6 +1713,12 @@ int lsd_run(cs_ctx *c, const uint8_t *imgs, bool imgs_on_device, int n_frames, i
     A.cap = cap;
     A.lgam = (const double *)S.lgam.p;
     A.ubits = (uint32_t *)S.ubits.p;
+    A.cand = (LsdRect *)S.cand.p;
+    A.n_cand = (int32_t *)S.ncand.p;
+    A.cand_cap = LSD_CAND_CAP;
+    A.cand_line = (int32_t *)S.candline.p;
+    A.err = (int32_t *)S.err.p;
+    cudaMemsetAsync(S.err.p, 0, 16, st);
     A.redo = (int32_t *)S.redo.p;
     A.stats = (int32_t *)S.stats.p;
     /* The ordered-speculation kernel is off by default: on the GPU it is neither faster than one warp per frame (most of its candidates are
@@ -1492,8 +1728,10 @@ int lsd_run(cs_ctx *c, const uint8_t *imgs, bool imgs_on_device, int n_frames, i
     {
         const size_t smem = (size_t)LSD_SEQ_SCAP * 4;
         k_lsd_grow_seq<<<n_frames, 32, smem, st>>>(A);
+        k_lsd_validate<<<dim3(16, n_frames), 128, 0, st>>>(A);
+        k_lsd_emit<<<n_frames, 256, 0, st>>>(A);
     }
-    cs_ctx_count_launches(c, 9);
+    cs_ctx_count_launches(c, 10);
     if (cudaGetLastError() != cudaSuccess) return cs_ctx_fail(c, CS_ERR_CUDA, "LSD kernel launch failed: %s", cudaGetErrorString(cudaGetLastError()));
     S.last_frames = n_frames;
     S.last_W = W;
@@ -1527,7 +1765,7 @@ void cs_lsd_destroy(void *state)
 {
     LsdState *S = (LsdState *)state;
     Buf *all[] = {&S->img, &S->tmp, &S->blur, &S->scaled, &S->modgrad, &S->angf, &S->pix, &S->list, &S->st, &S->arena, &S->spill, &S->maxg, &S->cnt,
-                  &S->llen, &S->raw, &S->nraw, &S->out, &S->nout, &S->redo, &S->stats, &S->lgam, &S->ubits};
+                  &S->llen, &S->raw, &S->nraw, &S->out, &S->nout, &S->redo, &S->stats, &S->lgam, &S->ubits, &S->cand, &S->ncand, &S->candline, &S->err};
     for (Buf *b : all)
         if (b->p) cudaFree(b->p);
     delete S;

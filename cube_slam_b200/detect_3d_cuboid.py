@@ -234,6 +234,27 @@ def cuboid_measurement(rec, cam_t, cam_q_xyzw, cam_euler_raw=None):
     return t, q, s, qual.value
 
 
+def cuboid_draw_edges(rec):
+    """The 12 edges plot_image_with_cuboid draws for a cuboid record (object_3d_util.cpp:54-131): 12 x 8 int32 rows
+    [x1 y1 x2 y2 B G R thickness]."""
+    L = _lib.load()
+    rec = np.ascontiguousarray(np.asarray(rec).reshape(-1)[:1])
+    edges = np.zeros((12, 8), np.int32)
+    rc = L.cs_cuboid_draw_edges(rec.ctypes.data, _lib.ptr(edges, C.c_int32))
+    if rc != 0:
+        raise CubeSlamError(_lib.STATUS_NAMES.get(rc, str(rc)))
+    return edges
+
+
+def plot_image_with_cuboid(plot_img, rec):
+    """plot_image_with_cuboid (object_3d_util.cpp:126-131): draws the cuboid into plot_img in place with the reference's own call,
+    cv::line(img, p1, p2, colour, thickness, CV_AA, 0)."""
+    import cv2
+    for x1, y1, x2, y2, b, g, r, th in cuboid_draw_edges(rec):
+        cv2.line(plot_img, (int(x1), int(y1)), (int(x2), int(y2)), (int(b), int(g), int(r)), int(th), cv2.LINE_AA, 0)
+    return plot_img
+
+
 def default_params(**kw):
     p = CuboidParams()
     _lib.load().cs_default_cuboid_params(C.byref(p))
@@ -306,4 +327,11 @@ class detect_3d_cuboid(object):
         img = np.ascontiguousarray(rgb_img, np.uint8)
         out, counts = self._ctx.detect_batch_host(img[None], np.asarray(transToWolrd, np.float64).reshape(1, 16), [boxes],
                                                   [np.asarray(edges, np.float64).reshape(-1, 4)], self.params())
-        return [[cuboid(out[i, k]) for k in range(counts[i])] for i in range(len(boxes))]
+        res = [[cuboid(out[i, k]) for k in range(counts[i])] for i in range(len(boxes))]
+        if self.whether_save_final_images and img.ndim == 3:  # box_proposal_detail.cpp:541-556 (callers read cuboids_2d_img, main_obj.cpp:450)
+            frame_all_cubes_img = img.copy()
+            for i in range(len(boxes)):
+                if counts[i]:
+                    plot_image_with_cuboid(frame_all_cubes_img, out[i, 0])
+            self.cuboids_2d_img = frame_all_cubes_img
+        return res

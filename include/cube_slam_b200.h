@@ -224,6 +224,12 @@ int cs_debug_lsd_prof(cs_ctx *ctx, uint64_t *out8, int reset);
 int cs_debug_edlines(cs_ctx *ctx, int frame, uint8_t *blur, int16_t *dx, int16_t *dy, int16_t *g, uint8_t *dir, int32_t *anchors,
                      int32_t *n_anchors, uint8_t *edge, float *raw_lines, int32_t *n_raw, int cap_raw);
 
+/* How the reference draws a detected cuboid (plot_image_with_cuboid, detect_3d_cuboid/src/object_3d_util.cpp:54-131, called with
+ * whether_save_final_images / whether_plot_final_images, box_proposal_detail.cpp:541-556): its 12 edges in the reference's order, each
+ * {x1, y1, x2, y2, B, G, R, thickness}; the caller rasterises them with cv::line(..., CV_AA) exactly as the reference does
+ * (visible edges thick, hidden ones thin; red / green / blue per vanishing-point family).  Host-only, needs no context. */
+int cs_cuboid_draw_edges(const cs_cuboid_rec *rec, int32_t edges[12][8]);
+
 /* The atan2 of the cuboid stage's angle-error chain (merge_break_lines, VP_support_edge_infos, box_edge_alignment_angle_error;
  * object_3d_util.cpp:167-172,321,392,480) is defined arithmetically (cube_slam_b200/csrc/cs_pmath.h: IEEE + - * / only, within 1 ulp of
  * glibc's) so that it rounds the same on the host, on the device and in the test oracle.  cs_debug_atan2 evaluates it on the device,

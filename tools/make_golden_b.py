@@ -1,0 +1,67 @@
+#!/usr/bin/env python
+"""Oracle goldens for the 58-frame object_slam sequence (fixture B) and for seeded synthetic frames: regression pins of the oracle itself
+(SURVEY.md section 7 step 1), also checked against the CUDA path on the GPU.
+
+    python tools/make_golden_b.py
+
+Per frame and mode: LSD segment count and a checksum of the segments, candidates, valid proposals, and per box the best cuboid
+(proposal index, normalised error, position, yaw, scale).  Modes: default, and 5 x 5 camera roll / pitch sampling
+(whether_sample_cam_roll_pitch).  object_slam's own settings: length threshold 15, nominal_skew_ratio 2 (main_obj.cpp:359-366)."""
+import json
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+from oracle import pyoracle as O  # noqa: E402
+
+GOLD = os.path.join(ROOT, "tests", "golden")
+
+
+def seg_checksum(lines):
+    a = np.ascontiguousarray(lines, np.float32).view(np.uint32).astype(np.uint64)
+    w = (np.arange(a.size, dtype=np.uint64).reshape(a.shape) * np.uint64(2654435761) + np.uint64(1)) & np.uint64(0xffffffff)
+    return int(((a * w) & np.uint64(0xffffffffffff)).sum() & np.uint64(0xffffffffffff))
+
+
+def best(c):
+    return dict(proposal_index=int(c["proposal_index"]), normalized_error=float(c["normalized_error"]), pos=[float(v) for v in c["pos"]],
+                rotY=float(c["rotY"]), scale=[float(v) for v in c["scale"]])
+
+
+def frame_record(img, K, T, boxes, modes):
+    lines = O.lsd_detect(img, 15.0)["lines"]
+    rec = dict(n_lines=int(len(lines)), lines_checksum=seg_checksum(lines), modes={})
+    for name, kw in modes:
+        r = O.detect_cuboid(img, K, T, boxes, lines.astype(np.float64), O.default_params(nominal_skew_ratio=2.0, **kw))
+        rec["modes"][name] = dict(n_candidates=int(r["n_candidates"]), n_valid=int(r["n_valid"]),
+                                  boxes=[best(c[0]) if len(c) else None for c in r["cuboids"]])
+    return rec
+
+
+def main():
+    import conftest
+    fb = conftest.fixture_b.__wrapped__()
+    modes = [("default", {}), ("sample_roll_pitch", dict(whether_sample_cam_roll_pitch=1))]
+    out = dict(source="oracle (oracle/*.cpp) on tests/golden/fixture_b; tools/make_golden_b.py", frames=[])
+    for i, (img, boxes) in enumerate(fb["frames"]):
+        out["frames"].append(frame_record(img, fb["K"], fb["T"], boxes, modes))
+        print("fixture B frame", i, out["frames"][-1]["n_lines"], flush=True)
+    json.dump(out, open(os.path.join(GOLD, "expected_fixture_b.json"), "w"), indent=0)
+    from cube_slam_b200 import synthetic as S
+    syn = dict(source="oracle on cube_slam_b200.synthetic.make_batch(seed, 4, w, h, nb, kind); tools/make_golden_b.py", cases=[])
+    for seed, w, h, kind, nb in ((101, 640, 480, "indoor", 3), (102, 1242, 375, "kitti", 8), (103, 1280, 960, "indoor", 4)):
+        imgs, Ts, boxes, _, K = S.make_batch(seed, 4, w, h, nb, kind=kind, poisson=(kind == "indoor"))
+        case = dict(seed=seed, w=w, h=h, kind=kind, nb=nb, image_checksum=int(imgs.astype(np.uint64).sum()), frames=[])
+        for f in range(4):
+            case["frames"].append(frame_record(imgs[f], K, Ts[f], boxes[f], modes[:1]))
+        syn["cases"].append(case)
+        print("synthetic", seed, [fr["n_lines"] for fr in case["frames"]], flush=True)
+    json.dump(syn, open(os.path.join(GOLD, "expected_synthetic.json"), "w"), indent=0)
+
+
+if __name__ == "__main__":
+    main()
