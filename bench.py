@@ -483,9 +483,9 @@ def run_ours(args, rank, world, local_rank):
     pinned = torch.from_numpy(wl["imgs"]).pin_memory()
     imgs_pinned = pinned.numpy()
     n_obj_loc = max(int(stats["n_objects"]), 1)
-    # two host threads, one context each, call the synchronous ABI entry point: the copies of one batch overlap the kernels of the other
+    # host threads, one context each, call the synchronous ABI entry point: the copies of one batch overlap the kernels of the others
     # (single GPU only: two threads issuing NCCL calls on two communicators in an unordered way could deadlock across ranks)
-    e2e_ctxs = ctxs[:2] if (len(ctxs) >= 2 and world == 1) else ctxs[:1]
+    e2e_ctxs = ctxs[:8] if (len(ctxs) >= 2 and world == 1) else ctxs[:1]
     e2e_out = [(np.zeros((n_obj_loc, topk), cs.CUBOID_DTYPE), np.zeros(n_obj_loc, np.int32)) for _ in e2e_ctxs]
     lp_main = main_mode.lp
 
@@ -614,7 +614,7 @@ def main():
     ap.add_argument("--no-prio", action="store_true", help="A/B: keep each batch's whole chain on one stream (no high-priority tail)")
     ap.add_argument("--raster-dt", action="store_true", help="A/B: two-pass raster-scan distance transform kernel instead of the cone form")
     ap.add_argument("--seq-lines", action="store_true", help="A/B: the line detectors' sequential kernels (one warp per frame) instead of ordered speculation")
-    ap.add_argument("--inflight", type=int, default=4, help="batches in flight on one GPU (contexts driven round-robin)")
+    ap.add_argument("--inflight", type=int, default=8, help="batches in flight on one GPU (contexts driven round-robin)")
     args = ap.parse_args()
     if args.steps is None:
         args.steps = 300 if args.impl == "ours" else 3

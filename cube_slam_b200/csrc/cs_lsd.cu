@@ -803,6 +803,8 @@ __device__ void lsd_region2rect(const LsdFrame &F, const LsdReg &R, int base, in
     if (rec.width < 1.0) rec.width = 1.0;
 }
 
+__device__ __noinline__ void lsd_region2rect_cold(const LsdFrame &F, const LsdReg &R, int base, int reg_size, double reg_angle, double prec, double p, LsdRect &rec);
+
 /* lsd.cpp:834-871 (lane 0 replays the reference's in-place compaction; it fixes the order later sums run in).
  * Returns 0 ok, 1 claim lost, 3 region rejected. */
 __device__ __noinline__ int lsd_reduce_region_radius(const LsdFrame &F, const LsdView &V, const LsdReg &R, int base, int &reg_size, double reg_angle, double prec, double p,
@@ -834,47 +836,9 @@ __device__ __noinline__ int lsd_reduce_region_radius(const LsdFrame &F, const Ls
         __syncwarp();
         if (lost) return 1;
         if (reg_size < 2) return 3;
-        lsd_region2rect(F, R, base, reg_size, reg_angle, prec, p, rec);
+        lsd_region2rect_cold(F, R, base, reg_size, reg_angle, prec, p, rec);
         density = (double)reg_size / (lsd_dist(rec.x1, rec.y1, rec.x2, rec.y2) * rec.width);
     }
-    return 0;
-}
-
-/* lsd.cpp:786-832.  The re-grown region is appended after the first one (base moves), so the record of a candidate lists every pixel
- * it ever claimed.  Returns 0 ok, 1 refused / claim lost, 2 overflow, 3 region rejected. */
-__device__ int lsd_refine(const LsdFrame &F, const LsdView &V, const LsdReg &R, int &base, int &reg_size, double &reg_angle, double prec, double p, LsdRect &rec,
-                          double density_th, int &n_all)
-{
-    const int lane = threadIdx.x & 31;
-    double density = (double)reg_size / (lsd_dist(rec.x1, rec.y1, rec.x2, rec.y2) * rec.width);
-    if (density >= density_th) return 0;
-    const int a0 = R.get(base);
-    const double xc = (double)(a0 - F.row_of(a0) * F.W), yc = (double)F.row_of(a0);
-    const double ang_c = (double)F.angf[a0] * LSD_DEG2RAD;
-    double sum = 0, s_sum = 0;
-    int n = 0;
-    LSD_FOR_REGION_ORDERED(F, R, base, reg_size, {
-        if (lsd_dist(xc, yc, (double)rx, (double)ry) < rec.width) {
-            const double ang_d = lsd_angle_diff_signed(pangle, ang_c);
-            sum += ang_d;
-            s_sum += ang_d * ang_d;
-            ++n;
-        }
-    })
-    bool lost = false;
-    for (int i = lane; i < reg_size; i += 32) lost |= !lsd_demote(F, V, R.get(base + i));
-    __syncwarp();
-    if (__any_sync(0xffffffffu, lost)) return 1;
-    const double mean_angle = sum / (double)n;
-    const double tau = 2.0 * sqrt((s_sum - 2.0 * mean_angle * sum) / (double)n + mean_angle * mean_angle);
-    base += reg_size;
-    const int rc = lsd_region_grow(F, V, R, base, a0, reg_size, reg_angle, tau);
-    n_all = base + reg_size; /* reduce_region_radius below only permutes the second list */
-    if (rc) return rc;
-    if (reg_size < 2) return 3;
-    lsd_region2rect(F, R, base, reg_size, reg_angle, prec, p, rec);
-    density = (double)reg_size / (lsd_dist(rec.x1, rec.y1, rec.x2, rec.y2) * rec.width);
-    if (density < density_th) return lsd_reduce_region_radius(F, V, R, base, reg_size, reg_angle, prec, p, rec, density, density_th);
     return 0;
 }
 
@@ -1053,37 +1017,75 @@ __device__ double lsd_rect_improve(const LsdFrame &F, LsdRect &rec)
 /* The first half of one seed (lsd.cpp:478-519): grow, rectangle, density refinement.  has_rect = 1 when a rectangle comes out that
  * rect_improve / the NFA test still have to judge -- which they can do later, in any order and in parallel: they read the level-line
  * angles only and never touch the `used` map.  Returns 0 done, 1 refused, 2 overflow. */
+__device__ __noinline__ void lsd_region2rect_cold(const LsdFrame &F, const LsdReg &R, int base, int reg_size, double reg_angle, double prec, double p, LsdRect &rec)
+{
+    lsd_region2rect(F, R, base, reg_size, reg_angle, prec, p, rec);
+}
+
 __device__ int lsd_grow_candidate(const LsdFrame &F, const LsdView &V, const LsdReg &R, int s_addr, int min_reg_size, double prec, double p, int &n_all,
                                   int &has_rect, LsdRect &rec)
 {
+    /* region_grow -> region2rect -> density test, at most twice: the second round is refine()'s re-grow with the tolerance estimated from
+     * the first region (lsd.cpp:786-832).  One loop, so that the two big inlined bodies exist once in the kernel (instruction cache). */
     const double DENSITY_TH = 0.7;
-    int base = 0, reg_size = 0;
-    double reg_angle = 0;
+    const int lane = threadIdx.x & 31;
+    int base = 0, reg_size = 0, seed = s_addr;
+    double reg_angle = 0, tau = prec;
     has_rect = 0;
     n_all = 0;
-    int rc;
-    {
+    for (int pass = 0; pass < 2; pass++) {
+        int rc;
+        {
+            LSD_PROF_T0();
+            rc = lsd_region_grow(F, V, R, base, seed, reg_size, reg_angle, tau);
+            LSD_PROF_ADD(pass == 0 ? 0 : 2);
+        }
+        if (pass == 0 && lane == 0) atomicAdd(&g_lsd_prof[5], 1ull);
+        n_all = base + reg_size;
+        if (rc) return rc;
+        if (reg_size < (pass == 0 ? min_reg_size : 2)) return 0;
+        {
+            LSD_PROF_T0();
+            lsd_region2rect(F, R, base, reg_size, reg_angle, prec, p, rec);
+            LSD_PROF_ADD(1);
+        }
+        const double density = (double)reg_size / (lsd_dist(rec.x1, rec.y1, rec.x2, rec.y2) * rec.width);
+        if (density >= DENSITY_TH) {
+            has_rect = 1;
+            return 0;
+        }
+        if (pass == 1) { /* still too sparse after the re-grow: shrink it around the seed (lsd.cpp:834-871) */
+            const int r2 = lsd_reduce_region_radius(F, V, R, base, reg_size, reg_angle, prec, p, rec, density, DENSITY_TH);
+            if (r2 == 3) return 0;
+            if (r2) return r2;
+            has_rect = 1;
+            return 0;
+        }
+        /* refine(): tolerance from the angle spread near the seed, give the region back, grow again from the same seed */
         LSD_PROF_T0();
-        rc = lsd_region_grow(F, V, R, 0, s_addr, reg_size, reg_angle, prec);
-        LSD_PROF_ADD(0);
-    }
-    if ((threadIdx.x & 31) == 0) atomicAdd(&g_lsd_prof[5], 1ull);
-    n_all = reg_size;
-    if (rc) return rc;
-    if (reg_size < min_reg_size) return 0;
-    {
-        LSD_PROF_T0();
-        lsd_region2rect(F, R, 0, reg_size, reg_angle, prec, p, rec);
-        LSD_PROF_ADD(1);
-    }
-    {
-        LSD_PROF_T0();
-        rc = lsd_refine(F, V, R, base, reg_size, reg_angle, prec, p, rec, DENSITY_TH, n_all);
+        const int a0 = R.get(base);
+        const double xc = (double)(a0 - F.row_of(a0) * F.W), yc = (double)F.row_of(a0);
+        const double ang_c = (double)F.angf[a0] * LSD_DEG2RAD;
+        double sum = 0, s_sum = 0;
+        int n = 0;
+        LSD_FOR_REGION_ORDERED(F, R, base, reg_size, {
+            if (lsd_dist(xc, yc, (double)rx, (double)ry) < rec.width) {
+                const double ang_d = lsd_angle_diff_signed(pangle, ang_c);
+                sum += ang_d;
+                s_sum += ang_d * ang_d;
+                ++n;
+            }
+        })
+        bool lost = false;
+        for (int i = lane; i < reg_size; i += 32) lost |= !lsd_demote(F, V, R.get(base + i));
+        __syncwarp();
+        if (__any_sync(0xffffffffu, lost)) return 1;
+        const double mean_angle = sum / (double)n;
+        tau = 2.0 * sqrt((s_sum - 2.0 * mean_angle * sum) / (double)n + mean_angle * mean_angle);
+        seed = a0;
+        base += reg_size;
         LSD_PROF_ADD(2);
     }
-    if (rc == 3) return 0;
-    if (rc) return rc;
-    has_rect = 1;
     return 0;
 }
 
