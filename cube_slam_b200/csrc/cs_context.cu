@@ -67,6 +67,8 @@ struct cs_ctx {
     int64_t total_px = 0, total_cand = 0, total_bits = 0;
     int n_tiles = 0, max_plane_words = 0, max_dpitch = 0, max_roi_h = 0;
     int use_raster_dt = 0; /* A/B: two-pass raster-scan distance transform instead of the cone form */
+    bool use_tma = true;       /* tile kernels of the line detectors: interior tiles staged by the copy engine (cp.async.bulk.tensor); bit 8 of cs_set_profiling turns it off */
+    bool use_tma_canny = false; /* the same in k_canny_nms: measured 8 % slower than the byte loads (the kernel is bound by integer ALU work, not by its loads), so opt-in: bit 9 */
     int use_fused_dt = 0; /* experimental: fused hysteresis + wavefront DT kernel */
     cudaStream_t stream2 = nullptr; /* side stream: the line kernel runs beside the image chain */
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
@@ -112,6 +114,7 @@ cudaStream_t cs_ctx_stream(cs_ctx *c) { return c->stream; }
 int cs_ctx_device(cs_ctx *c) { return c->device; }
 void **cs_ctx_lsd_slot(cs_ctx *c) { return &c->lsd_state; }
 int cs_ctx_seq_lines(cs_ctx *c) { return c->seq_lines; }
+int cs_ctx_use_tma(cs_ctx *c) { return c->use_tma ? 1 : 0; }
 void **cs_ctx_edl_slot(cs_ctx *c) { return &c->edl_state; }
 void cs_ctx_count_launches(cs_ctx *c, int64_t n) { c->line_launches += n; }
 int cs_ctx_fail(cs_ctx *c, int code, const char *fmt, ...)
@@ -441,8 +444,8 @@ int run_batch(cs_ctx *c, bool sync)
         gray = (const uint8_t *)c->d_img.p;
     mark(ST_CANNY);
     int low = (int)std::floor(std::min(c->prm.canny_low, c->prm.canny_high)), high = (int)std::floor(std::max(c->prm.canny_low, c->prm.canny_high));
-    cs_launch_canny(gray, c->w, c->h, (const CsJob *)c->d_jobs.p, n_jobs, (const int32_t *)c->d_tilejob.p, (int)c->tile_job.size(), (uint32_t *)c->d_bits.p, (size_t)c->total_bits * 4, low, high,
-                    st, &c->launches);
+    cs_launch_canny(gray, c->w, c->h, c->n_frames, (const CsJob *)c->d_jobs.p, n_jobs, (const int32_t *)c->d_tilejob.p, (int)c->tile_job.size(), (uint32_t *)c->d_bits.p,
+                    (size_t)c->total_bits * 4, low, high, (int32_t *)c->d_err.p, c->use_tma_canny, st, &c->launches);
     mark(ST_HYST);
     bool fused = false;
     if (c->use_fused_dt)
@@ -574,6 +577,7 @@ int fetch(cs_ctx *c, cs_cuboid_rec *out, int32_t *out_counts)
     if (err & 1) return fail(c, CS_ERR_CAPACITY, "more than %d line segments inside one ROI", CS_LINE_CAP);
     if (err & 2) return fail(c, CS_ERR_CAPACITY, "more than %d merged segments inside one ROI", CS_MAXL_OUT);
     if (err & 4) return fail(c, CS_ERR_CAPACITY, "the line detector found more than %d segments in a frame (raise max_lines_per_frame)", c->online_cap);
+    if (err & 8) return fail(c, CS_ERR_CUDA, "a TMA tile copy of the Canny kernel did not complete");
     if (out && out_counts) { /* slots past the count are not cuboids */
         for (size_t o = 0; o < no; o++)
             for (int k = out_counts[o]; k < c->topk; k++) std::memset(&out[o * c->topk + k], 0, sizeof(cs_cuboid_rec));
@@ -886,6 +890,8 @@ int cs_set_profiling(cs_ctx *c, int enable)
     c->use_raster_dt = ((enable & 32) ? 1 : 0) | ((enable & 64) ? 2 : 0); /* bit 5: raster-scan distance transform kernel; bit 6: cone form, bits from global */
     c->use_prio = (enable & 16) == 0;      /* bit 4: keep the whole chain on one stream (no high-priority tail) */
     c->seq_lines = (enable & 128) != 0;    /* bit 7: sequential seed loop / routing of the line detectors (A/B reference of the speculative kernels) */
+    c->use_tma = (enable & 256) == 0;      /* bit 8: the line detectors' tile kernels stage every tile with byte loads (A/B of the TMA path) */
+    c->use_tma_canny = (enable & 512) != 0; /* bit 9: k_canny_nms stages interior gray tiles by TMA as well */
     c->use_cta_select = (enable & 8) != 0; /* bit 3: CTA-wide sweep / selection kernels (the general path) instead of the warp ones */
     return CS_OK;
 }

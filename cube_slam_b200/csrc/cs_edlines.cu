@@ -27,6 +27,7 @@
 
 #include "cs_internal.h"
 #include "cs_nfa.cuh"
+#include "cs_tma.cuh"
 
 #define ED_PI 3.14159265358979323846
 #define ED_LN10 2.30258509299404568402
@@ -122,27 +123,45 @@ __global__ void __launch_bounds__(256) k_ed_maps(const uint8_t *__restrict__ blu
  * sums are integers, also for the Sobel taps on the blurred image. */
 #define EDF_TW 64
 #define EDF_TH 32
-__global__ void __launch_bounds__(256) k_ed_front(const uint8_t *__restrict__ img, int w, int h, int stride, int channels, uint8_t *__restrict__ blur,
-                                                  int16_t *__restrict__ dxo, int16_t *__restrict__ dyo, int16_t *__restrict__ go, uint8_t *__restrict__ diro)
+#define EDF_BOXW 240 /* 3 * (EDF_TW + 6) = 210 bytes of BGR + up to 15 of alignment slack (a TMA box starts at a multiple of 16 bytes), a multiple of 16 */
+template <bool kTma>
+__global__ void __launch_bounds__(256) k_ed_front(const __grid_constant__ CUtensorMap tmap, const uint8_t *__restrict__ img, int w, int h, int stride,
+                                                  int channels, uint8_t *__restrict__ blur, int16_t *__restrict__ dxo, int16_t *__restrict__ dyo,
+                                                  int16_t *__restrict__ go, uint8_t *__restrict__ diro, int32_t *__restrict__ err_flag)
 {
     __shared__ uint8_t s_gray[EDF_TH + 6][EDF_TW + 8];
     __shared__ uint16_t s_h[EDF_TH + 6][EDF_TW + 4];
     __shared__ uint8_t s_blur[EDF_TH + 2][EDF_TW + 4];
+    __shared__ __align__(128) uint8_t s_rgb[kTma ? (EDF_TH + 6) * EDF_BOXW : 16]; /* kTma: BGR bytes of an interior tile, fetched by the copy engine */
+    __shared__ __align__(8) unsigned long long s_bar;
     const int f = blockIdx.z, x0 = blockIdx.x * EDF_TW, y0 = blockIdx.y * EDF_TH, tid = threadIdx.x;
     const uint8_t *frame = img + (size_t)f * h * stride;
-    /* gray, halo 3 */
-    for (int i = tid; i < (EDF_TH + 6) * (EDF_TW + 6); i += 256) {
-        const int r = i / (EDF_TW + 6), c = i - r * (EDF_TW + 6);
-        const int yy = ed_reflect101(y0 - 3 + r, h), xx = ed_reflect101(x0 - 3 + c, w);
-        const uint8_t *q = frame + (size_t)yy * stride;
-        uint32_t g;
-        if (channels == 3) {
-            q += 3 * xx;
-            g = (q[0] * 3735u + q[1] * 19235u + q[2] * 9798u + (1u << 14)) >> 15;
-        } else
-            g = q[xx];
-        s_gray[r][c] = (uint8_t)g;
-    }
+    const bool interior = kTma && x0 - 3 >= 0 && x0 + EDF_TW + 3 <= w - 1 && y0 - 3 >= 0 && y0 + EDF_TH + 3 <= h - 1;
+    if (interior) {
+        if (tid == 0) cs_mbar_init(&s_bar);
+        __syncthreads();
+        const int bx = 3 * (x0 - 3), boff = bx & 15; /* the box starts at a multiple of 16 bytes */
+        if (tid == 0) cs_tma_load_2d(&tmap, s_rgb, &s_bar, bx - boff, f * h + y0 - 3, (EDF_TH + 6) * EDF_BOXW);
+        if (!cs_mbar_wait(&s_bar, 0) && tid == 0) atomicOr(err_flag, 8);
+        for (int i = tid; i < (EDF_TH + 6) * (EDF_TW + 6); i += 256) {
+            const int r = i / (EDF_TW + 6), c = i - r * (EDF_TW + 6);
+            const uint8_t *q = &s_rgb[r * EDF_BOXW + boff + 3 * c];
+            s_gray[r][c] = (uint8_t)((q[0] * 3735u + q[1] * 19235u + q[2] * 9798u + (1u << 14)) >> 15);
+        }
+    } else
+        /* gray, halo 3 */
+        for (int i = tid; i < (EDF_TH + 6) * (EDF_TW + 6); i += 256) {
+            const int r = i / (EDF_TW + 6), c = i - r * (EDF_TW + 6);
+            const int yy = ed_reflect101(y0 - 3 + r, h), xx = ed_reflect101(x0 - 3 + c, w);
+            const uint8_t *q = frame + (size_t)yy * stride;
+            uint32_t g;
+            if (channels == 3) {
+                q += 3 * xx;
+                g = (q[0] * 3735u + q[1] * 19235u + q[2] * 9798u + (1u << 14)) >> 15;
+            } else
+                g = q[xx];
+            s_gray[r][c] = (uint8_t)g;
+        }
     __syncthreads();
     /* horizontal pass, columns -1 .. TW (halo 1), rows -3 .. TH + 2 */
     for (int i = tid; i < (EDF_TH + 6) * (EDF_TW + 2); i += 256) {
@@ -1517,8 +1536,14 @@ int cs_edl_run(cs_ctx *c, const uint8_t *imgs, bool imgs_on_device, int n_frames
                                                         (uint8_t *)S.dir.p);
         k_ed_anchors<<<n_frames, 256, 0, st>>>((const int16_t *)S.g.p, (const uint8_t *)S.dir.p, w, h, (int32_t *)S.anchors.p, (int32_t *)S.nanch.p, anchor_cap);
     } else {
-        k_ed_front<<<dim3((w + EDF_TW - 1) / EDF_TW, (h + EDF_TH - 1) / EDF_TH, n_frames), 256, 0, st>>>(
-            d_img, w, h, stride, channels, (uint8_t *)S.blur.p, (int16_t *)S.dx.p, (int16_t *)S.dy.p, (int16_t *)S.g.p, (uint8_t *)S.dir.p);
+        const dim3 g_tile((w + EDF_TW - 1) / EDF_TW, (h + EDF_TH - 1) / EDF_TH, n_frames);
+        CUtensorMap tm;
+        if (cs_ctx_use_tma(c) && channels == 3 && stride == 3 * w && cs_make_tmap_bytes(&tm, d_img, 3 * (int64_t)w, (int64_t)n_frames * h, stride, EDF_BOXW, EDF_TH + 6))
+            k_ed_front<true><<<g_tile, 256, 0, st>>>(tm, d_img, w, h, stride, channels, (uint8_t *)S.blur.p, (int16_t *)S.dx.p, (int16_t *)S.dy.p, (int16_t *)S.g.p,
+                                                    (uint8_t *)S.dir.p, (int32_t *)S.err.p);
+        else
+            k_ed_front<false><<<g_tile, 256, 0, st>>>(tm, d_img, w, h, stride, channels, (uint8_t *)S.blur.p, (int16_t *)S.dx.p, (int16_t *)S.dy.p, (int16_t *)S.g.p,
+                                                     (uint8_t *)S.dir.p, (int32_t *)S.err.p);
         cudaMemsetAsync(S.colcnt.p, 0, (size_t)n_frames * (nw + 1) * 4, st);
         k_ed_anchor_flags<<<dim3((nw + 255) / 256, nhw, n_frames), 256, 0, st>>>((const int16_t *)S.g.p, (const uint8_t *)S.dir.p, w, h, nw, nh, nhw,
                                                                                  (uint32_t *)S.abits.p, (int32_t *)S.colcnt.p);

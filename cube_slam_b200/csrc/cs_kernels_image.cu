@@ -13,7 +13,9 @@
  * zero border: (h+2) rows of (bw+2) 32-bit words, bw = ceil(w/32).  That makes NMS output two ballots per
  * warp, hysteresis a word-parallel dilation in shared memory, and the distance transform's input 32x smaller.
  */
+#include <cuda.h>
 #include <cuda_runtime.h>
+#include <string.h>
 #include <stdlib.h>
 #include <stdint.h>
 
@@ -73,10 +75,23 @@ __global__ void __launch_bounds__(256) k_bgr2gray_generic(const uint8_t *__restr
  * ------------------------------------------------------------------------------------------ */
 #define CT 32 /* tile edge */
 
-__global__ void __launch_bounds__(256) k_canny_nms(const uint8_t *__restrict__ gray, int img_w, int img_h, const CsJob *__restrict__ jobs,
-                                                   const int32_t *__restrict__ tile_job, uint32_t *__restrict__ bits_arena, int low, int high)
+/* TMA staging of the gray tile (kTma): a tile whose 36 x 36 halo region lies inside the ROI needs no clamping, so one elected thread
+ * asks the copy engine for it (cp.async.bulk.tensor.2d, box 64 x 36 bytes of the {width, frames x height} gray tensor, completion on
+ * an mbarrier) one tile ahead, into the other half of a double buffer.  The innermost start coordinate of a box must be a multiple of
+ * 16 bytes (anything else is an illegal-instruction fault on sm_100, tools/probe/tma_probe.cu), so the box starts at the tile's x rounded
+ * down and the tile is read at an offset of 0..15 bytes; tiles that touch the ROI border (cv::Canny on gray(roi) replicates
+ * the ROI's own border, TMA would zero-fill or read the neighbours) keep the clamped byte loads.  The tile pitch is 48 bytes either way. */
+#define CTP 64 /* pitch of the staged gray tile in bytes: 36 used + up to 15 of alignment slack (a TMA box starts at a multiple of 16 bytes) */
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+template <bool kTma>
+__global__ void __launch_bounds__(256) k_canny_nms(const __grid_constant__ CUtensorMap tmap, const uint8_t *__restrict__ gray, int img_w, int img_h,
+                                                   const CsJob *__restrict__ jobs, const int32_t *__restrict__ tile_job, uint32_t *__restrict__ bits_arena,
+                                                   int low, int high, int32_t *__restrict__ err_flag)
 {
-    __shared__ uint8_t s_g[CT + 4][CT + 4 + 4];   /* gray, +2 halo */
+    /* gray, +2 halo, two buffers; a TMA destination must be 128-byte aligned: 36 rows x 48 bytes = 1728, padded to 1792 */
+    __shared__ __align__(128) uint8_t s_gb_raw[2][((CT + 4) * CTP + 127) / 128 * 128];
+    __shared__ __align__(8) unsigned long long s_bar[2];
     __shared__ int32_t s_d[CT + 2][CT + 2 + 1];   /* (dy << 16) | (dx & 0xffff), +1 halo */
     __shared__ uint16_t s_m[CT + 2][CT + 2 + 2];  /* |dx| + |dy|, zero outside the ROI */
     /* a block owns one ROW of tiles of one ROI and walks it left to right; the gray bytes of the next tile are fetched into
@@ -97,8 +112,9 @@ __global__ void __launch_bounds__(256) k_canny_nms(const uint8_t *__restrict__ g
     const uint16_t *mflat = &s_m[0][0];
     constexpr int NPRE = ((CT + 4) * (CT + 4) + 255) / 256;
     uint8_t pre[NPRE];
-
-    auto fetch = [&](int x0) {
+    const bool rows_inside = (y0 - 2 >= 0) && (y0 + CT + 1 <= h - 1);
+    auto interior = [&](int x0) { return kTma && rows_inside && (x0 - 2 >= 0) && (x0 + CT + 1 <= w - 1); };
+    auto fetch = [&](int x0) { /* clamped byte loads into registers (ROI border tiles, or no TMA) */
 #pragma unroll
         for (int q = 0; q < NPRE; q++) {
             const int i = tid + q * 256;
@@ -111,19 +127,63 @@ __global__ void __launch_bounds__(256) k_canny_nms(const uint8_t *__restrict__ g
             }
         }
     };
-    fetch(0);
+    auto tma_issue = [&](int x0, int buf) { /* one thread: arm the barrier with the byte count, start the copy */
+        const uint32_t bar = smem_u32(&s_bar[buf]), dst = smem_u32(&s_gb_raw[buf][0]);
+        const int cx = (jb.roi_l + x0 - 2) & ~15, cy = jb.frame * img_h + jb.roi_t + y0 - 2; /* start rounded down to 16 bytes */
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); /* the buffer was last read through the generic proxy */
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"((uint32_t)((CT + 4) * CTP)) : "memory");
+        asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(dst),
+                     "l"(reinterpret_cast<uint64_t>(&tmap)), "r"(cx), "r"(cy), "r"(bar)
+                     : "memory");
+    };
+    uint32_t phase0 = 0, phase1 = 0; /* parity of the next completion of either barrier */
+    if (kTma) {
+        if (tid == 0) {
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&s_bar[0])) : "memory");
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&s_bar[1])) : "memory");
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        }
+        __syncthreads();
+    }
+    bool cur_tma = interior(0);
+    if (cur_tma) {
+        if (tid == 0) tma_issue(0, 0);
+    } else
+        fetch(0);
     for (int tile_x = 0; tile_x < tiles_x; tile_x++) {
         const int x0 = tile_x * CT;
+        const int buf = tile_x & 1;
+        uint8_t(*s_g)[CTP] = reinterpret_cast<uint8_t(*)[CTP]>(&s_gb_raw[buf][0]);
+        const int goff = cur_tma ? ((jb.roi_l + x0 - 2) & 15) : 0; /* where the tile starts inside the staged rows */
+        if (cur_tma) { /* wait for the copy engine: every thread polls the barrier's phase (bounded: a lost copy must not hang the GPU) */
+            const uint32_t bar = smem_u32(&s_bar[buf]);
+            const uint32_t parity = buf ? phase1 : phase0;
+            uint32_t done = 0;
+            for (int spin = 0; spin < (1 << 22) && !done; spin++)
+                asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}" : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+            if (!done && tid == 0) atomicOr(err_flag, 8);
+            if (buf)
+                phase1 ^= 1u;
+            else
+                phase0 ^= 1u;
+        } else {
 #pragma unroll
-        for (int q = 0; q < NPRE; q++) {
-            const int i = tid + q * 256;
-            if (i < (CT + 4) * (CT + 4)) {
-                const int ly = i / (CT + 4), lx = i - ly * (CT + 4);
-                s_g[ly][lx] = pre[q];
+            for (int q = 0; q < NPRE; q++) {
+                const int i = tid + q * 256;
+                if (i < (CT + 4) * (CT + 4)) {
+                    const int ly = i / (CT + 4), lx = i - ly * (CT + 4);
+                    s_g[ly][lx] = pre[q];
+                }
             }
         }
         __syncthreads();
-        if (tile_x + 1 < tiles_x) fetch(x0 + CT);
+        if (tile_x + 1 < tiles_x) { /* the next tile, into the other buffer (everybody left it before the barrier above) */
+            cur_tma = interior(x0 + CT);
+            if (cur_tma) {
+                if (tid == 0) tma_issue(x0 + CT, buf ^ 1);
+            } else
+                fetch(x0 + CT);
+        }
         /* Sobel + magnitude for the (CT+2)^2 halo region: a thread owns one column and a strip of 5 rows, the three-row
          * window slides down in registers (21 shared loads for 5 results) */
         int loud = 0; /* does any pixel of the tile proper exceed the low threshold? (the +1 halo ring does not count) */
@@ -134,7 +194,7 @@ __global__ void __launch_bounds__(256) k_canny_nms(const uint8_t *__restrict__ g
 #pragma unroll
             for (int r = 0; r < 7; r++) {
                 const int row = min(r0 + r, CT + 3);
-                const int a = s_g[row][lx], b = s_g[row][lx + 1], c = s_g[row][lx + 2];
+                const int a = s_g[row][goff + lx], b = s_g[row][goff + lx + 1], c = s_g[row][goff + lx + 2];
                 rs[r] = a + 2 * b + c;
                 rd[r] = c - a;
             }
@@ -1061,14 +1121,46 @@ void cs_launch_gray(const uint8_t *d_img, uint8_t *d_gray, int n_frames, int w, 
     }
 }
 
-void cs_launch_canny(const uint8_t *d_gray, int img_w, int img_h, const CsJob *d_jobs, int n_jobs, const int32_t *d_tile_job, int n_tiles, uint32_t *d_bits,
-                     size_t bits_bytes, int low, int high, cudaStream_t st, int64_t *launches)
+/* cuTensorMapEncodeTiled through the runtime (no link-time dependency on libcuda): the {width, frames x height} byte tensor of the gray
+ * frames, box CTP x (CT + 4).  Returns false when the driver entry point is missing or the layout does not qualify (pitch not a multiple
+ * of 16 bytes): the kernel then stages every tile with byte loads. */
+static bool cs_make_gray_tmap(CUtensorMap *tm, const uint8_t *d_gray, int img_w, int64_t rows)
+{
+    typedef CUresult (*EncodeFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *, const cuuint32_t *,
+                                 const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+    static EncodeFn fn = nullptr;
+    static bool tried = false;
+    if (!tried) {
+        tried = true;
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess) fn = (EncodeFn)p;
+        cudaGetLastError();
+    }
+    if (!fn || (img_w % 16) != 0 || (((uintptr_t)d_gray) & 15) != 0 || img_w < CTP || rows < CT + 4) return false;
+    const cuuint64_t dims[2] = {(cuuint64_t)img_w, (cuuint64_t)rows};
+    const cuuint64_t strides[1] = {(cuuint64_t)img_w};
+    const cuuint32_t box[2] = {CTP, CT + 4};
+    const cuuint32_t estr[2] = {1, 1};
+    return fn(tm, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, (void *)d_gray, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+              CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+void cs_launch_canny(const uint8_t *d_gray, int img_w, int img_h, int n_frames, const CsJob *d_jobs, int n_jobs, const int32_t *d_tile_job, int n_tiles,
+                     uint32_t *d_bits, size_t bits_bytes, int low, int high, int32_t *d_err, bool use_tma, cudaStream_t st, int64_t *launches)
 {
     if (n_jobs <= 0) return;
     cudaMemsetAsync(d_bits, 0, bits_bytes, st); /* zero borders (and stale bits) of every plane */
     if (n_tiles > 0) {
-        CS_APPLY_CARVEOUT(k_canny_nms);
-        k_canny_nms<<<n_tiles, dim3(32, 8), 0, st>>>(d_gray, img_w, img_h, d_jobs, d_tile_job, d_bits, low, high);
+        CUtensorMap tm;
+        memset(&tm, 0, sizeof(tm));
+        if (use_tma && cs_make_gray_tmap(&tm, d_gray, img_w, (int64_t)n_frames * img_h)) {
+            CS_APPLY_CARVEOUT(k_canny_nms<true>);
+            k_canny_nms<true><<<n_tiles, dim3(32, 8), 0, st>>>(tm, d_gray, img_w, img_h, d_jobs, d_tile_job, d_bits, low, high, d_err);
+        } else {
+            CS_APPLY_CARVEOUT(k_canny_nms<false>);
+            k_canny_nms<false><<<n_tiles, dim3(32, 8), 0, st>>>(tm, d_gray, img_w, img_h, d_jobs, d_tile_job, d_bits, low, high, d_err);
+        }
         (*launches)++;
     }
 }

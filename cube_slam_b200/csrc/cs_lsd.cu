@@ -48,6 +48,7 @@
 
 #include "cs_internal.h"
 #include "cs_nfa.cuh"
+#include "cs_tma.cuh"
 
 #define LSD_PI 3.1415926535897932384626433832795
 #define LSD_NOTDEF (-1024.0)
@@ -159,24 +160,44 @@ __global__ void __launch_bounds__(256) k_lsd_vblur(const double *__restrict__ tm
  * by k_lsd_vblur (which stay as the A/B path, cs_set_profiling bit 7). */
 #define LSB_TW 64
 #define LSB_TH 16
-__global__ void __launch_bounds__(256) k_lsd_blur(const uint8_t *__restrict__ img, int w, int h, int stride, int channels, double *__restrict__ blur)
+/* kTma: the BGR bytes of an interior tile (no reflection needed) are fetched by the copy engine -- one cp.async.bulk.tensor.2d of
+ * 224 x 22 bytes, completion on an mbarrier -- instead of three byte loads per pixel; border tiles keep the reflected loads. */
+#define LSB_BOXW 240 /* 3 * (LSB_TW + 6) = 210 bytes of BGR + up to 15 of alignment slack (a TMA box starts at a multiple of 16 bytes), a multiple of 16 */
+template <bool kTma>
+__global__ void __launch_bounds__(256) k_lsd_blur(const __grid_constant__ CUtensorMap tmap, const uint8_t *__restrict__ img, int w, int h, int stride,
+                                                  int channels, double *__restrict__ blur, int32_t *__restrict__ err_flag)
 {
     __shared__ uint8_t s_g[LSB_TH + 6][LSB_TW + 8];
     __shared__ double s_h[LSB_TH + 6][LSB_TW];
+    __shared__ __align__(128) uint8_t s_rgb[kTma ? (LSB_TH + 6) * LSB_BOXW : 16];
+    __shared__ __align__(8) unsigned long long s_bar;
     const int f = blockIdx.z, x0 = blockIdx.x * LSB_TW, y0 = blockIdx.y * LSB_TH, tid = threadIdx.x;
     const uint8_t *frame = img + (size_t)f * h * stride;
-    for (int i = tid; i < (LSB_TH + 6) * (LSB_TW + 6); i += 256) {
-        const int r = i / (LSB_TW + 6), c = i - r * (LSB_TW + 6);
-        const int yy = reflect101(y0 - 3 + r, h), xx = reflect101(x0 - 3 + c, w);
-        const uint8_t *q = frame + (size_t)yy * stride;
-        uint32_t g;
-        if (channels == 3) {
-            q += 3 * xx;
-            g = (q[0] * 3735u + q[1] * 19235u + q[2] * 9798u + (1u << 14)) >> 15;
-        } else
-            g = q[xx];
-        s_g[r][c] = (uint8_t)g;
-    }
+    const bool interior = kTma && x0 - 3 >= 0 && x0 + LSB_TW + 3 <= w - 1 && y0 - 3 >= 0 && y0 + LSB_TH + 3 <= h - 1;
+    if (interior) {
+        if (tid == 0) cs_mbar_init(&s_bar);
+        __syncthreads();
+        const int bx = 3 * (x0 - 3), boff = bx & 15; /* the box starts at a multiple of 16 bytes */
+        if (tid == 0) cs_tma_load_2d(&tmap, s_rgb, &s_bar, bx - boff, f * h + y0 - 3, (LSB_TH + 6) * LSB_BOXW);
+        if (!cs_mbar_wait(&s_bar, 0) && tid == 0) atomicOr(err_flag, 8);
+        for (int i = tid; i < (LSB_TH + 6) * (LSB_TW + 6); i += 256) {
+            const int r = i / (LSB_TW + 6), c = i - r * (LSB_TW + 6);
+            const uint8_t *q = &s_rgb[r * LSB_BOXW + boff + 3 * c];
+            s_g[r][c] = (uint8_t)((q[0] * 3735u + q[1] * 19235u + q[2] * 9798u + (1u << 14)) >> 15);
+        }
+    } else
+        for (int i = tid; i < (LSB_TH + 6) * (LSB_TW + 6); i += 256) {
+            const int r = i / (LSB_TW + 6), c = i - r * (LSB_TW + 6);
+            const int yy = reflect101(y0 - 3 + r, h), xx = reflect101(x0 - 3 + c, w);
+            const uint8_t *q = frame + (size_t)yy * stride;
+            uint32_t g;
+            if (channels == 3) {
+                q += 3 * xx;
+                g = (q[0] * 3735u + q[1] * 19235u + q[2] * 9798u + (1u << 14)) >> 15;
+            } else
+                g = q[xx];
+            s_g[r][c] = (uint8_t)g;
+        }
     __syncthreads();
     for (int i = tid; i < (LSB_TH + 6) * LSB_TW; i += 256) {
         const int r = i / LSB_TW, c = i - r * LSB_TW;
@@ -1643,7 +1664,7 @@ int lsd_run(cs_ctx *c, const uint8_t *imgs, bool imgs_on_device, int n_frames, i
             return cs_ctx_fail(c, CS_ERR_CUDA, "H2D copy of frames failed");
         d_img = (const uint8_t *)S.img.p;
     }
-    if ((rc = ensure(c, S.tmp, px * 8)) || (rc = ensure(c, S.blur, px * 8)) || (rc = ensure(c, S.scaled, spx * 8)) ||
+    if ((rc = ensure(c, S.tmp, cs_ctx_seq_lines(c) ? px * 8 : 0)) || (rc = ensure(c, S.blur, px * 8)) || (rc = ensure(c, S.scaled, spx * 8)) ||
         (rc = ensure(c, S.modgrad, spx * 8)) || (rc = ensure(c, S.angf, spx * 4)) || (rc = ensure(c, S.pix, spx * 16)) ||
         (rc = ensure(c, S.list, spx * 4)) || (rc = ensure(c, S.st, spx * 4)) || (rc = ensure(c, S.arena, (size_t)n_frames * arena_cap * 4)) ||
         (rc = ensure(c, S.spill, (size_t)n_frames * LSD_NW * LSD_SPILL * 4)) || (rc = ensure(c, S.maxg, (size_t)n_frames * 8)) ||
@@ -1669,6 +1690,7 @@ int lsd_run(cs_ctx *c, const uint8_t *imgs, bool imgs_on_device, int n_frames, i
     const int min_reg_size = (int)(-LOG_NT / std::log10(p));
 
     cudaMemsetAsync(S.maxg.p, 0, (size_t)n_frames * 8, st);
+    cudaMemsetAsync(S.err.p, 0, 16, st);
     cudaMemsetAsync(S.st.p, 0, spx * 4, st);
     cudaMemsetAsync(S.stats.p, 0, (size_t)n_frames * 16, st);
     const dim3 g_src((w * h + 255) / 256, n_frames), g_dst((W * H + 255) / 256, n_frames);
@@ -1676,7 +1698,15 @@ int lsd_run(cs_ctx *c, const uint8_t *imgs, bool imgs_on_device, int n_frames, i
         k_lsd_hblur<<<g_src, 256, 0, st>>>(d_img, n_frames, w, h, stride, channels, (double *)S.tmp.p);
         k_lsd_vblur<<<g_src, 256, 0, st>>>((const double *)S.tmp.p, n_frames, w, h, (double *)S.blur.p);
     } else
-        k_lsd_blur<<<dim3((w + LSB_TW - 1) / LSB_TW, (h + LSB_TH - 1) / LSB_TH, n_frames), 256, 0, st>>>(d_img, w, h, stride, channels, (double *)S.blur.p);
+    {
+        const dim3 g_tile((w + LSB_TW - 1) / LSB_TW, (h + LSB_TH - 1) / LSB_TH, n_frames);
+        CUtensorMap tm;
+        /* BGR frames whose rows are a multiple of 16 bytes (640 and 1280 wide are) can be staged by the copy engine */
+        if (cs_ctx_use_tma(c) && channels == 3 && stride == 3 * w && cs_make_tmap_bytes(&tm, d_img, 3 * (int64_t)w, (int64_t)n_frames * h, stride, LSB_BOXW, LSB_TH + 6))
+            k_lsd_blur<true><<<g_tile, 256, 0, st>>>(tm, d_img, w, h, stride, channels, (double *)S.blur.p, (int32_t *)S.err.p);
+        else
+            k_lsd_blur<false><<<g_tile, 256, 0, st>>>(tm, d_img, w, h, stride, channels, (double *)S.blur.p, (int32_t *)S.err.p);
+    }
     k_lsd_resize<<<g_dst, 256, 0, st>>>((const double *)S.blur.p, n_frames, w, h, W, H, 1. / SCALE, (double *)S.scaled.p);
     k_lsd_grad<<<g_dst, 256, 0, st>>>((const double *)S.scaled.p, n_frames, W, H, rho, (double *)S.modgrad.p, (float *)S.angf.p,
                                                        (uint4 *)S.pix.p, (unsigned long long *)S.maxg.p);
@@ -1720,7 +1750,6 @@ int lsd_run(cs_ctx *c, const uint8_t *imgs, bool imgs_on_device, int n_frames, i
     A.cand_cap = LSD_CAND_CAP;
     A.cand_line = (int32_t *)S.candline.p;
     A.err = (int32_t *)S.err.p;
-    cudaMemsetAsync(S.err.p, 0, 16, st);
     A.redo = (int32_t *)S.redo.p;
     A.stats = (int32_t *)S.stats.p;
     /* The ordered-speculation kernel is off by default: on the GPU it is neither faster than one warp per frame (most of its candidates are

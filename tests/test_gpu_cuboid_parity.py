@@ -153,6 +153,32 @@ def test_synthetic_batch_matches_oracle(cs, oracle, seed, w, h, kind, nb):
     ctx.close()
 
 
+def test_canny_tma_staging_equals_byte_staging(cs, oracle):
+    """k_canny_nms<true> (cs_set_profiling bit 9: interior gray tiles fetched by the copy engine, cp.async.bulk.tensor + mbarrier; 640 and
+    1280 wide frames qualify) against k_canny_nms<false> (the default: every tile by clamped byte loads) and the oracle: same edge
+    bits, same records."""
+    from cube_slam_b200 import synthetic as S
+    for seed, w, h, nb in ((61, 640, 480, 4), (62, 1280, 960, 3)):
+        imgs, Ts, boxes, lines, K = S.make_batch(seed, 3, w, h, nb, poisson=True)
+        outs = []
+        for flags in (0, 512):
+            ctx = cs.Context(0, w, h, 3, 16, 4096)
+            ctx.set_calibration(K)
+            ctx.L.cs_set_profiling(ctx.h, flags)
+            out, counts = ctx.detect_batch_host(imgs, Ts, boxes, lines, cs.default_params(max_cuboid_num=2))
+            rois = [ctx.debug_roi(j) for j in range(sum(len(b) for b in boxes))]
+            outs.append((out.copy(), counts.copy(), rois))
+            ctx.close()
+        assert outs[0][0].tobytes() == outs[1][0].tobytes() and (outs[0][1] == outs[1][1]).all()
+        job = 0
+        for f in range(3):
+            for b in range(len(boxes[f])):
+                tr = oracle.detect_cuboid(imgs[f], K, Ts[f], boxes[f], lines[f], trace_object=b)["trace"]
+                for k in (0, 1):
+                    np.testing.assert_array_equal(outs[k][2][job]["canny"], tr["canny"])
+                job += 1
+
+
 def test_dense_sweep_and_sampling(cs, oracle):
     """BASELINE config 5 shape (0.5 deg yaw step, 30 top-x samples) and roll/pitch sampling on synthetic frames."""
     from cube_slam_b200 import synthetic as S

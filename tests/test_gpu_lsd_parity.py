@@ -235,3 +235,23 @@ def test_seed_loop_redo_path_on_a_giant_region(det, oracle):
     ref = oracle.lsd_detect(ramp, 15.0)
     np.testing.assert_array_equal(got[0], ref["lines"])
     np.testing.assert_array_equal(det.debug_frame(0)["raw_lines"], ref["raw_lines"])
+
+
+def test_tma_staged_tiles_equal_byte_staged_tiles(det, oracle):
+    """k_lsd_blur<true> / k_ed_front<true> (BGR tiles fetched by the copy engine, the default on 640 / 1280 wide BGR frames) against the
+    byte-load instantiations (cs_set_profiling bit 8): identical segments for both detectors, and equal to the oracle."""
+    import cube_slam_b200 as cs
+    from cube_slam_b200 import synthetic as S
+    imgs = S.make_batch(71, 3, 640, 480, 3)[0]
+    for use_lsd, ref_fn in ((True, oracle.lsd_detect), (False, oracle.edl_detect)):
+        d = cs.line_lbd_detect(context=det._ctx)
+        d.use_LSD = use_lsd
+        d.line_length_thres = 15
+        got = {}
+        for flags in (0, 256):
+            det._ctx.set_profiling(flags)
+            got[flags] = d.detect_filter_lines_batch(imgs)
+        det._ctx.set_profiling(0)
+        for f in range(3):
+            np.testing.assert_array_equal(got[0][f], got[256][f])
+            np.testing.assert_array_equal(got[0][f], ref_fn(imgs[f], 15.0)["lines"])
