@@ -6,35 +6,32 @@
  *   LineSegmentDetectorImpl::flsd & co.    line_lbd/libs/lsd.cpp:440-1154   (LSD_REFINE_ADV, default parameters)
  *   filter_lines + keylines_to_mat         line_lbd/class/line_lbd_allclass.cpp:26-36,200-221
  *
- * Streaming stages (one thread per pixel, FP64, evaluation order of OpenCV's C paths, -fmad=false):
- *   k_lsd_hblur   cvtColor + horizontal 7-tap Gaussian (sigma 0.6/0.8)      lsd.cpp:452-457
- *   k_lsd_vblur   vertical 7-tap                                          lsd.cpp:457
+ * Streaming stages (FP64, evaluation order of OpenCV's C paths, -fmad=false):
+ *   k_lsd_blur    cvtColor + the 7 x 7 Gaussian (sigma 0.6/0.8), both passes, on 64 x 16 tiles; interior tiles' BGR bytes come in by TMA
+ *                 (k_lsd_hblur / k_lsd_vblur: the two-pass pair of round 1, A/B path, cs_set_profiling bit 7)     lsd.cpp:452-457
  *   k_lsd_resize  cv::resize(x0.8, INTER_LINEAR) on doubles               lsd.cpp:459
  *   k_lsd_grad    2x2 gradient, modulus, fastAtan2 angle, max modulus     lsd.cpp:562-586
- *   k_lsd_hist / k_lsd_scan / k_lsd_scatter   the 1024-bin pseudo-ordering as a STABLE counting sort (bins descending,
+ *   k_lsd_hist / k_lsd_scan / k_lsd_scatter_rows   the 1024-bin pseudo-ordering as a STABLE counting sort (bins descending,
  *                 raster order inside a bin == the reference's linked lists)  lsd.cpp:588-634
  *
- * Seed loop (lsd.cpp:476-535): k_lsd_grow_par, one CTA of LSD_NW warps per frame, ORDERED SPECULATION.
- *   The reference visits the ordered pixel list one seed at a time; a seed grows a region over the pixels no earlier seed used, so the
- *   result is defined by the order.  Here the list positions are "candidates" with rank = list position.  Every warp pulls candidates
- *   of a sliding window ahead of the commit frontier and processes each one completely (region_grow, region2rect, refine, rect_improve)
- *   against the claim word of every pixel:
- *       claim = (rank << 1) | former      member (former = 0) / dropped by refine (former = 1) of candidate `rank`;  0xffffffff = free
- *       rank <  frontier  and member  ->  used for good (that candidate is final)
- *       rank >= frontier              ->  speculative: a LOWER rank overrides it (compare-and-swap) and flags the victim invalid,
- *                                         a HIGHER rank that needs the pixel (it is aligned with its region) gives up and retries later.
- *   A candidate that finishes without having been overridden is CLEAN; it keeps its claims.  After each round the frontier advances over
- *   the maximal prefix of list positions that are CLEAN, or whose pixel is used by a final region (the reference's `used` test),
- *   or whose pixel is a member of a CLEAN lower candidate of that prefix.  Everything below the frontier equals the sequential result:
- *   a CLEAN candidate saw every pixel it tested either used by a final region, or free (and claimed it, so any later lower-rank
- *   interest would have flagged it), and pixels not aligned with its region do not depend on the used map at all.  The candidate at the
- *   frontier can neither be refused nor overridden, so every round makes progress.  Segments are emitted in rank order at the end.
- *   Capacity problems (a region larger than the per-warp staging area, record arena full) flag the frame, and
- *   k_lsd_grow_seq -- the plain one-warp-per-frame seed loop -- redoes flagged frames (also the A/B path, cs_set_profiling bit 7).
+ * Seed loop (lsd.cpp:476-535).  The reference visits the ordered pixel list one seed at a time; a seed grows a region over the pixels no
+ * earlier seed used, so the result is defined by the order -- but only through the `used` map.  It is cut in two:
+ *   k_lsd_grow_seq   everything that reads or writes `used`: list scan, region_grow, region2rect, the density test, refine /
+ *                    reduce_region_radius (lsd.cpp:478-519), one warp per frame (one 32-thread CTA, 8 KB of shared memory for the region
+ *                    list, `used` as a bit per pixel in HBM read through L2).  Emits the candidate rectangles in seed order.
+ *   k_lsd_validate   rect_improve and the NFA test (lsd.cpp:520-534, 873-1136) read the angle map only: one warp per candidate
+ *                    rectangle, all candidates of all frames at once.
+ *   k_lsd_emit       accepted candidates in seed order + the key-line filter.
+ * Why this shape (profiles/r2_lsd_seed_ncu.md): the one-warp loop is bound by instruction issue (an instruction every 6 cycles, ~12 M per
+ * frame in round 1), not by memory latency; what stops more frames from sharing an SM is the instruction cache, so the sequential kernel is
+ * kept small (grow -> rectangle -> density is ONE two-pass loop, 7.4 k instructions instead of 39 k) and everything order-free runs where
+ * thousands of warps execute the same code.  An ordered-speculation kernel (many warps per frame claiming pixels by rank) was built and
+ * measured in this round and removed: 74 % of the candidates it started were refused and redone, it needed ~25 barrier-separated rounds
+ * per frame, was not faster than one warp per frame, and emitted duplicate segments on dense frames (git history: k_lsd_grow_par).
  *
  * Inside one candidate the warp parallelises what is order-free (the 3x3 neighbour tests of three region points per step from ONE 16-byte
- * record per pixel, rectangle pixel counts over rows, the five rectangles of a rect_improve phase and their NFA evaluations on separate
- * lanes, min/max extents) and keeps every floating-point accumulation in the reference's order.
+ * record per pixel, rectangle pixel counts over rows, min/max extents, the binomial tail's break tests) and keeps every floating-point
+ * accumulation in the reference's order.
  */
 #include <cuda_runtime.h>
 #include <float.h>
@@ -59,10 +56,6 @@
 #define LSD_NBINS 1024
 #define LSD_CHUNK_ROWS 8
 
-#define LSD_NW 16            /* warps per frame in k_lsd_grow_par */
-#define LSD_SCAP 512         /* region entries of a warp's staging area kept in shared memory (the rest spills to HBM) */
-#define LSD_SPILL 16384      /* staging capacity per warp (entries), first LSD_SCAP in shared memory */
-#define LSD_WINDOW 4096      /* list positions ahead of the frontier that may be speculated on */
 #define LSD_CAND_CAP 2048    /* candidate rectangles per frame handed from the seed loop to k_lsd_validate */
 #define LSD_SEQ_SCAP 2048    /* region entries k_lsd_grow_seq keeps in shared memory (the rest spill to HBM; small, so that many frames share an SM) */
 #define LSD_FREE 0xffffffffu
@@ -638,19 +631,6 @@ __device__ __forceinline__ bool lsd_demote(const LsdFrame &F, const LsdView &V, 
     const uint32_t me0 = (uint32_t)V.rank << 1;
     return atomicCAS(cw, me0, me0 | 1u) == me0;
 }
-/* give back every claim the candidate still holds on the listed pixels */
-__device__ __noinline__ void lsd_release(const LsdFrame &F, int rank, const LsdReg &R, int n)
-{
-    const int lane = threadIdx.x & 31;
-    for (int i = lane; i < n; i += 32) {
-        const int addr = R.get(i);
-        uint32_t *cw = lsd_claim_ptr(F, addr);
-        const uint32_t c = __ldcg(cw);
-        if ((int)(c >> 1) == rank && c != LSD_FREE) atomicCAS(cw, c, LSD_FREE);
-    }
-    __syncwarp();
-}
-
 /* lsd.cpp:637-688.  Neighbour tests of three region points per round on lanes 0..26 (one 16-byte record each); additions stay in the
  * reference's order.  The region is R[base .. base + reg_size).  Returns 0 ok, 1 refused (a lower-rank speculative owner holds a pixel
  * this region wants, or a claim was lost), 2 staging overflow. */
@@ -934,7 +914,15 @@ __device__ void lsd_rect_count(const LsdFrame &F, const LsdRect &rec, int &total
     /* rows outside the image skip the edge stepping too (as the reference): only rows y0..y1 count */
     const int y0 = max(my, 0), y1 = min(max_iter, F.H - 1);
     int tot = 0, alg = 0;
-    for (int y = y0 + lane; y <= y1; y += 32) {
+    /* lanes over rows AND over the pixels of a row: G lanes share a row, G the largest power of two with rows * G <= 32 (a nearly horizontal
+     * segment has a handful of long rows, a nearly vertical one many short rows) */
+    const int n_rows = y1 - y0 + 1;
+    int G = 1;
+    while (G < 32 && n_rows * G * 2 <= 32) G <<= 1;
+    const int rows_per_step = 32 / G, sub = lane & (G - 1), rsel = lane / G;
+    for (int yb = y0; yb <= y1; yb += rows_per_step) {
+        const int y = yb + rsel;
+        if (y > y1) continue;
         /* steps added before row y: one per earlier inside row y' in [y0, y); row y' adds the second slope iff y' >= ly (ry) */
         const long long n_l2 = (long long)max(0, y - max(ly, y0)), n_l1 = (long long)(y - y0) - n_l2;
         const long long n_r2 = (long long)max(0, y - max(ry, y0)), n_r1 = (long long)(y - y0) - n_r2;
@@ -942,9 +930,9 @@ __device__ void lsd_rect_count(const LsdFrame &F, const LsdRect &rec, int &total
         const long long right_x = (long long)mx + n_r1 * frstep + n_r2 * srstep;
         const long long lo = left_x > 0 ? left_x : 0, hi = right_x < (long long)(F.W - 1) ? right_x : (long long)(F.W - 1);
         if (hi >= lo) {
-            tot += (int)(hi - lo + 1);
+            if (sub == 0) tot += (int)(hi - lo + 1);
             const float *row = F.angf + (size_t)y * F.W;
-            for (int x = (int)lo; x <= (int)hi; x++) alg += lsd_aligned_deg(row[x], rec.theta, rec.prec) ? 1 : 0;
+            for (int x = (int)lo + sub; x <= (int)hi; x += G) alg += lsd_aligned_deg(row[x], rec.theta, rec.prec) ? 1 : 0;
         }
     }
 #pragma unroll
@@ -1033,8 +1021,6 @@ __device__ double lsd_rect_improve(const LsdFrame &F, LsdRect &rec)
     return log_nfa;
 }
 
-/* One seed, start to finish (the body of the loop lsd.cpp:478-535).  Returns 0 done (has_line / line set), 1 refused, 2 overflow.
- * n_all = entries of R that hold every pixel the candidate ever claimed. */
 /* The first half of one seed (lsd.cpp:478-519): grow, rectangle, density refinement.  has_rect = 1 when a rectangle comes out that
  * rect_improve / the NFA test still have to judge -- which they can do later, in any order and in parallel: they read the level-line
  * angles only and never touch the `used` map.  Returns 0 done, 1 refused, 2 overflow. */
@@ -1131,20 +1117,6 @@ __device__ bool lsd_validate_rect(const LsdFrame &F, LsdRect &rec, double scale,
     return true;
 }
 
-/* One seed, start to finish (the body of the loop lsd.cpp:478-535).  Returns 0 done (has_line / line set), 1 refused, 2 overflow.
- * n_all = entries of R that hold every pixel the candidate ever claimed. */
-__device__ int lsd_process_seed(const LsdFrame &F, const LsdView &V, const LsdReg &R, int s_addr, int min_reg_size, double prec, double p, double scale,
-                                int &n_all, int &has_line, float *line)
-{
-    LsdRect rec;
-    int has_rect = 0;
-    has_line = 0;
-    const int rc = lsd_grow_candidate(F, V, R, s_addr, min_reg_size, prec, p, n_all, has_rect, rec);
-    if (rc || !has_rect) return rc;
-    has_line = lsd_validate_rect(F, rec, scale, line) ? 1 : 0;
-    return 0;
-}
-
 /* checkLineExtremes + 10-px border rejection + length filter (LSDDetector.cpp:75-101,226-238; filter_lines): true = keep */
 __device__ __forceinline__ bool lsd_keyline_filter(const float *raw, int img_w, int img_h, float line_length_thres, float *o)
 {
@@ -1203,253 +1175,10 @@ struct LsdGrowArgs {
     int32_t *stats;      /* per frame: rounds, candidates processed, refused, invalidated (diagnostics) */
 };
 
-/* The seed loop of flsd (lsd.cpp:476-535) by ordered speculation, one CTA per frame (see the file header). */
-__global__ void __launch_bounds__(LSD_NW * 32, 2) k_lsd_grow_par(LsdGrowArgs A, int force_seq)
-{
-    __shared__ int s_stage[LSD_NW][LSD_SCAP];
-    __shared__ int s_next, s_first, s_arena_top, s_fail, s_cnt[4];
-    __shared__ int s_warp_cnt[LSD_NW], s_base_raw, s_base_out;
-    const int f = blockIdx.x, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-    const unsigned FULL = 0xffffffffu;
-    const int T = LSD_NW * 32;
-    const size_t npx = (size_t)A.W * A.H;
-    if (force_seq) {
-        if (tid == 0) A.redo[f] = 1;
-        return;
-    }
-    LsdFrame F;
-    F.W = A.W;
-    F.H = A.H;
-    F.pix = A.pix + f * npx;
-    F.angf = A.angf + f * npx;
-    F.modgrad = A.modgrad + f * npx;
-    F.LOG_NT = A.LOG_NT;
-    F.st = A.st + f * npx;
-    F.arena = A.arena + (size_t)f * A.arena_cap;
-    F.arena_cap = A.arena_cap;
-    F.ubits = nullptr;
-    F.lgam = A.lgam;
-    F.wmagic = ((1ull << 40) + (unsigned long long)A.W - 1) / (unsigned long long)A.W;
-    const int32_t *list = A.list + f * npx;
-    const int n_list = A.list_len[f];
-    LsdReg R;
-    R.s = s_stage[wid];
-    R.g = A.spill + ((size_t)f * LSD_NW + wid) * LSD_SPILL;
-    R.scap = LSD_SCAP;
-    R.cap = LSD_SPILL;
-    if (tid == 0) {
-        s_arena_top = 0;
-        s_fail = 0;
-        s_cnt[0] = s_cnt[1] = s_cnt[2] = s_cnt[3] = 0;
-    }
-    int frontier = 0, rounds = 0;
-    __syncthreads();
-    while (frontier < n_list) {
-        const int E = min(frontier + LSD_WINDOW, n_list);
-        if (tid == 0) {
-            s_next = frontier;
-            s_first = E;
-        }
-        __syncthreads();
-        rounds++;
-        /* ---- speculation: warps pull 32 list positions at a time */
-        for (;;) {
-            int b = 0;
-            if (lane == 0) b = atomicAdd(&s_next, 32);
-            b = __shfl_sync(FULL, b, 0);
-            if (b >= E || *(volatile int *)&s_fail) break;
-            const int i = b + lane;
-            bool need = false, rel = false;
-            uint32_t sw = 0;
-            if (i < E) {
-                sw = __ldcg(F.st + i);
-                const uint32_t state = sw & LSD_ST_MASK;
-                if (state == LSD_ST_CLEAN) {
-                    rel = (sw & LSD_ST_INVALID) != 0; /* overridden by a lower rank: give the claims back, grow again */
-                } else {
-                    LsdView V0;
-                    V0.rank = i;
-                    V0.frontier = frontier;
-                    const int kind = lsd_decode(lsd_ld_claim(F, list[i]), V0);
-                    need = (kind == LSD_K_FREE || kind == LSD_K_HIGHER); /* used: final skip; lower: wait for that candidate */
-                }
-            }
-            unsigned todo = __ballot_sync(FULL, need || rel);
-            while (todo) {
-                const int sl = __ffs(todo) - 1;
-                todo &= todo - 1;
-                const int pos = b + sl;
-                if (__shfl_sync(FULL, (int)rel, sl)) {
-                    const uint32_t w0 = __shfl_sync(FULL, sw, sl);
-                    const int off = (int)(w0 >> 4);
-                    LsdReg RA;
-                    RA.s = nullptr;
-                    RA.g = F.arena + off + LSD_HDR;
-                    RA.scap = 0;
-                    RA.cap = 0;
-                    const int n_rec = __ldcg(F.arena + off) + __ldcg(F.arena + off + 1);
-                    lsd_release(F, pos, RA, n_rec);
-                    if (lane == 0) atomicAdd(&s_cnt[3], 1);
-                }
-                LsdView V;
-                V.rank = pos;
-                V.frontier = frontier;
-                const int s_addr = list[pos];
-                if (lane == 0) {
-                    F.st[pos] = LSD_ST_GROWING;
-                    __threadfence_block(); /* before any claim of this candidate can be seen (and its victim flag set) */
-                    atomicAdd(&s_cnt[1], 1);
-                }
-                __syncwarp();
-                int n_all = 0, has_line = 0;
-                float line[4] = {0.f, 0.f, 0.f, 0.f};
-                const int rc = lsd_process_seed(F, V, R, s_addr, A.min_reg_size, A.prec, A.p, A.scale, n_all, has_line, line);
-                __syncwarp();
-                bool keep = (rc == 0);
-                int off = 0;
-                if (keep) {
-                    const int need_ints = (LSD_HDR + n_all + 3) & ~3;
-                    if (lane == 0) off = atomicAdd(&s_arena_top, need_ints);
-                    off = __shfl_sync(FULL, off, 0);
-                    if (off + need_ints > F.arena_cap) {
-                        keep = false;
-                        if (lane == 0) s_fail = 1;
-                    }
-                }
-                if (rc == 2 && lane == 0) s_fail = 1;
-                if (keep) {
-                    for (int k = lane; k < n_all; k += 32) F.arena[off + LSD_HDR + k] = R.get(k);
-                    if (lane == 0) {
-                        F.arena[off + 0] = n_all;
-                        F.arena[off + 1] = 0;
-                        F.arena[off + 2] = has_line;
-                        F.arena[off + 3] = __float_as_int(line[0]);
-                        F.arena[off + 4] = __float_as_int(line[1]);
-                        F.arena[off + 5] = __float_as_int(line[2]);
-                        F.arena[off + 6] = __float_as_int(line[3]);
-                    }
-                    __threadfence_block();
-                    __syncwarp();
-                    int won = 1;
-                    if (lane == 0) won = (atomicCAS(F.st + pos, LSD_ST_GROWING, LSD_ST_CLEAN | ((uint32_t)off << 4)) == LSD_ST_GROWING) ? 1 : 0;
-                    keep = __shfl_sync(FULL, won, 0) != 0; /* lost: a lower rank overrode a pixel while this candidate was growing */
-                }
-                if (!keep) {
-                    lsd_release(F, pos, R, n_all);
-                    if (lane == 0) {
-                        F.st[pos] = LSD_ST_NEW;
-                        atomicAdd(&s_cnt[2], 1);
-                    }
-                    __syncwarp();
-                }
-            }
-        }
-        __syncthreads();
-        if (s_fail) break;
-        /* ---- advance the frontier over the resolved prefix */
-        int new_frontier = E;
-        for (int b = frontier; b < E; b += T) {
-            const int i = b + tid;
-            if (i < E) {
-                const uint32_t sw = __ldcg(F.st + i);
-                bool ok = ((sw & LSD_ST_MASK) == LSD_ST_CLEAN) && !(sw & LSD_ST_INVALID);
-                if (!ok) {
-                    const uint32_t c = lsd_ld_claim(F, list[i]);
-                    if (c != LSD_FREE && !(c & 1u)) {
-                        const int j = (int)(c >> 1);
-                        if (j < frontier)
-                            ok = true; /* used by a final region: the reference skips this seed */
-                        else if (j < i) {
-                            const uint32_t sj = __ldcg(F.st + j);
-                            ok = ((sj & LSD_ST_MASK) == LSD_ST_CLEAN) && !(sj & LSD_ST_INVALID); /* member of a region that becomes final with this prefix */
-                        }
-                    }
-                }
-                if (!ok) atomicMin(&s_first, i);
-            }
-            __syncthreads();
-            if (s_first < E) {
-                new_frontier = s_first;
-                break;
-            }
-        }
-        frontier = new_frontier;
-        __syncthreads();
-    }
-    if (s_fail) {
-        if (tid == 0) A.redo[f] = 1;
-        return;
-    }
-    /* ---- segments in rank order: ordered compaction of the records that carry one */
-    if (tid == 0) {
-        s_base_raw = 0;
-        s_base_out = 0;
-    }
-    __syncthreads();
-    float *raw = A.raw + (size_t)f * A.cap * 4;
-    float *out = A.out + (size_t)f * A.cap * 4;
-    for (int b = 0; b < n_list; b += T) {
-        const int i = b + tid;
-        bool has = false, kept = false;
-        float ln[4], fo[4];
-        if (i < n_list) {
-            const uint32_t sw = __ldcg(F.st + i);
-            if ((sw & LSD_ST_MASK) == LSD_ST_CLEAN) {
-                const int off = (int)(sw >> 4);
-                if (__ldcg(F.arena + off + 2)) {
-                    has = true;
-                    for (int k = 0; k < 4; k++) ln[k] = __int_as_float(__ldcg(F.arena + off + 3 + k));
-                    kept = lsd_keyline_filter(ln, A.img_w, A.img_h, A.line_length_thres, fo);
-                }
-            }
-        }
-        const unsigned mh = __ballot_sync(FULL, has), mk = __ballot_sync(FULL, kept);
-        if (lane == 0) s_warp_cnt[wid] = __popc(mh) | (__popc(mk) << 16);
-        __syncthreads();
-        int pre_r = s_base_raw, pre_o = s_base_out;
-        for (int k = 0; k < wid; k++) {
-            pre_r += s_warp_cnt[k] & 0xffff;
-            pre_o += s_warp_cnt[k] >> 16;
-        }
-        if (has) {
-            const int slot = pre_r + __popc(mh & ((1u << lane) - 1u));
-            if (slot < A.cap)
-                for (int k = 0; k < 4; k++) raw[4 * slot + k] = ln[k];
-        }
-        if (kept) {
-            const int slot = pre_o + __popc(mk & ((1u << lane) - 1u));
-            if (slot < A.cap)
-                for (int k = 0; k < 4; k++) out[4 * slot + k] = fo[k];
-        }
-        __syncthreads();
-        if (tid == 0) {
-            int tr = 0, to = 0;
-            for (int k = 0; k < LSD_NW; k++) {
-                tr += s_warp_cnt[k] & 0xffff;
-                to += s_warp_cnt[k] >> 16;
-            }
-            s_base_raw += tr;
-            s_base_out += to;
-        }
-        __syncthreads();
-    }
-    if (tid == 0) {
-        A.n_raw[f] = s_base_raw;
-        A.n_out[f] = s_base_out;
-        A.redo[f] = 0;
-        A.stats[4 * f + 0] = rounds;
-        A.stats[4 * f + 1] = s_cnt[1];
-        A.stats[4 * f + 2] = s_cnt[2];
-        A.stats[4 * f + 3] = s_cnt[3];
-    }
-}
-
-/* The plain seed loop, one warp per frame: redoes the frames the speculative kernel gave up on (capacity) and serves as its A/B
- * reference (cs_set_profiling bit 7).  Claim words: FREE = unused, 0 = used. */
+/* The order-dependent half of the seed loop, one warp per frame (see the file header). */
 __global__ void __launch_bounds__(32) k_lsd_grow_seq(LsdGrowArgs A)
 {
     const int f = blockIdx.x, lane = threadIdx.x;
-    if (!A.redo[f]) return;
     LSD_PROF_T0();
     const size_t npx = (size_t)A.W * A.H;
     LsdFrame F;
@@ -1515,7 +1244,6 @@ __global__ void __launch_bounds__(32) k_lsd_grow_seq(LsdGrowArgs A)
 __global__ void __launch_bounds__(128) k_lsd_validate(LsdGrowArgs A)
 {
     const int f = blockIdx.y, lane = threadIdx.x & 31;
-    if (!A.redo[f]) return;
     const size_t npx = (size_t)A.W * A.H;
     LsdFrame F;
     F.W = A.W;
@@ -1549,7 +1277,6 @@ __global__ void __launch_bounds__(256) k_lsd_emit(LsdGrowArgs A)
 {
     __shared__ int s_warp_cnt[8], s_base_raw, s_base_out;
     const int f = blockIdx.x, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-    if (!A.redo[f]) return;
     const unsigned FULL = 0xffffffffu;
     const int n = min(A.n_cand[f], A.cand_cap);
     float *raw = A.raw + (size_t)f * A.cap * 4;
@@ -1666,8 +1393,7 @@ int lsd_run(cs_ctx *c, const uint8_t *imgs, bool imgs_on_device, int n_frames, i
     }
     if ((rc = ensure(c, S.tmp, cs_ctx_seq_lines(c) ? px * 8 : 0)) || (rc = ensure(c, S.blur, px * 8)) || (rc = ensure(c, S.scaled, spx * 8)) ||
         (rc = ensure(c, S.modgrad, spx * 8)) || (rc = ensure(c, S.angf, spx * 4)) || (rc = ensure(c, S.pix, spx * 16)) ||
-        (rc = ensure(c, S.list, spx * 4)) || (rc = ensure(c, S.st, spx * 4)) || (rc = ensure(c, S.arena, (size_t)n_frames * arena_cap * 4)) ||
-        (rc = ensure(c, S.spill, (size_t)n_frames * LSD_NW * LSD_SPILL * 4)) || (rc = ensure(c, S.maxg, (size_t)n_frames * 8)) ||
+        (rc = ensure(c, S.list, spx * 4)) || (rc = ensure(c, S.arena, (size_t)n_frames * arena_cap * 4)) || (rc = ensure(c, S.maxg, (size_t)n_frames * 8)) ||
         (rc = ensure(c, S.cnt, (size_t)n_frames * n_chunks * LSD_NBINS * 4)) || (rc = ensure(c, S.llen, (size_t)n_frames * 4)) ||
         (rc = ensure(c, S.raw, (size_t)n_frames * cap * 16)) || (rc = ensure(c, S.nraw, (size_t)n_frames * 4)) ||
         (rc = ensure(c, S.out, (size_t)n_frames * cap * 16)) || (rc = ensure(c, S.nout, (size_t)n_frames * 4)) ||
@@ -1691,7 +1417,6 @@ int lsd_run(cs_ctx *c, const uint8_t *imgs, bool imgs_on_device, int n_frames, i
 
     cudaMemsetAsync(S.maxg.p, 0, (size_t)n_frames * 8, st);
     cudaMemsetAsync(S.err.p, 0, 16, st);
-    cudaMemsetAsync(S.st.p, 0, spx * 4, st);
     cudaMemsetAsync(S.stats.p, 0, (size_t)n_frames * 16, st);
     const dim3 g_src((w * h + 255) / 256, n_frames), g_dst((W * H + 255) / 256, n_frames);
     if (cs_ctx_seq_lines(c)) { /* A/B: the two-pass kernels */
@@ -1728,10 +1453,10 @@ int lsd_run(cs_ctx *c, const uint8_t *imgs, bool imgs_on_device, int n_frames, i
     A.modgrad = (const double *)S.modgrad.p;
     A.list = (const int32_t *)S.list.p;
     A.list_len = (const int32_t *)S.llen.p;
-    A.st = (uint32_t *)S.st.p;
+    A.st = nullptr;
     A.arena = (int32_t *)S.arena.p;
     A.arena_cap = arena_cap;
-    A.spill = (int32_t *)S.spill.p;
+    A.spill = nullptr;
     A.LOG_NT = LOG_NT;
     A.min_reg_size = min_reg_size;
     A.prec = prec;
@@ -1752,10 +1477,6 @@ int lsd_run(cs_ctx *c, const uint8_t *imgs, bool imgs_on_device, int n_frames, i
     A.err = (int32_t *)S.err.p;
     A.redo = (int32_t *)S.redo.p;
     A.stats = (int32_t *)S.stats.p;
-    /* The ordered-speculation kernel is off by default: on the GPU it is neither faster than one warp per frame (most of its candidates are
-     * refused and redone) nor, on dense frames, free of duplicate segments.  CS_LSD_SPECULATE=1 turns it back on for work on it. */
-    static const bool speculate = getenv("CS_LSD_SPECULATE") && atoi(getenv("CS_LSD_SPECULATE")) != 0;
-    k_lsd_grow_par<<<n_frames, LSD_NW * 32, 0, st>>>(A, (cs_ctx_seq_lines(c) || !speculate) ? 1 : 0);
     {
         const size_t smem = (size_t)LSD_SEQ_SCAP * 4;
         k_lsd_grow_seq<<<n_frames, 32, smem, st>>>(A);
@@ -1907,7 +1628,8 @@ int cs_debug_lsd_stats(cs_ctx *c, int32_t *stats4, int32_t *redo, int n_frames)
     cudaSetDevice(cs_ctx_device(c));
     cudaStreamSynchronize(cs_ctx_stream(c));
     if (stats4) cudaMemcpy(stats4, S->stats.p, (size_t)n_frames * 16, cudaMemcpyDeviceToHost);
-    if (redo) cudaMemcpy(redo, S->redo.p, (size_t)n_frames * 4, cudaMemcpyDeviceToHost);
+    if (redo)
+        for (int f = 0; f < n_frames; f++) redo[f] = 1; /* every frame goes through k_lsd_grow_seq (there is no speculative kernel any more) */
     return cudaGetLastError() == cudaSuccess ? CS_OK : cs_ctx_fail(c, CS_ERR_CUDA, "debug copy failed");
 }
 }

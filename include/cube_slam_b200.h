@@ -213,8 +213,8 @@ int cs_detect_lines_batch(cs_ctx *ctx, const uint8_t *imgs, int n_frames, int wi
 /* inspection of the last cs_detect_lines[_batch] run (tests): intermediate images of one frame; any pointer may be NULL */
 int cs_debug_lsd(cs_ctx *ctx, int frame, int32_t scaled_wh[2], double *scaled, double *modgrad, double *angles, int32_t *list,
                  int32_t *list_len, float *raw_lines, int32_t *n_raw, int cap_raw);
-/* diagnostics of the last LSD run's seed loop (lsd.cpp:478-535 as ordered speculation, cs_lsd.cu): per frame 4 values {rounds, candidates
- * processed, candidates refused or lost, candidates re-grown after an override}; redo[f] = 1 when the sequential kernel redid the frame */
+/* diagnostics of the last LSD run's seed loop: stats4 is kept for ABI stability and reads zero (it described the ordered-speculation kernel
+ * that round 2 measured and removed); redo[f] = 1: the frame went through the one-warp-per-frame kernel, as every frame does now */
 int cs_debug_lsd_stats(cs_ctx *ctx, int32_t *stats4, int32_t *redo, int n_frames);
 /* clock64 cycles the seed-loop warps spent per phase since the last reset (diagnostics; tools/time_lines.py): {region_grow, region2rect,
  * refine, rectangle pixel counts, binomial tails (nfa), candidates grown, whole kernel summed over CTAs, unused} */
