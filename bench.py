@@ -518,26 +518,32 @@ def run_ours(args, rank, world, local_rank):
         barrier()
         e2e_ms = (time.perf_counter() - t0) * 1e3  # host-synchronous calls: the wall clock around all of them is the honest bound
     else:
-        # N > 1: one host thread keeps four batches in flight with the split calls (cs_batch_upload_online from pinned host frames,
-        # cs_batch_run_async, cs_allgather_topk, cs_batch_fetch), so that every rank issues its collectives in the same order
-        e2e_mode = "one host thread, four contexts pipelined: cs_batch_upload_online + cs_batch_run_async + cs_allgather_topk + cs_batch_fetch"
-        e2e_ctxs = ctxs[:4]
+        # N > 1: one host thread keeps the batches in flight with the split calls (cs_batch_upload_online from pinned host frames,
+        # cs_batch_run_async, cs_allgather_topk, cs_batch_fetch) as a rolling pipeline, so that every rank issues its collectives in the
+        # same order: step s is issued on context s mod K, then the oldest outstanding step is fetched
+        e2e_ctxs = ctxs[:8]
+        K_ = len(e2e_ctxs)
+        e2e_mode = "one host thread, %d contexts as a rolling pipeline: cs_batch_upload_online + cs_batch_run_async + cs_allgather_topk + cs_batch_fetch" % K_
 
-        def e2e_round():
-            for cx in e2e_ctxs:
-                cx.upload_online(imgs_pinned, wl["Ts"], wl["boxes"], lp_main, params)
-                cx.run_async()
-                cx.check(cx.L.cs_allgather_topk(cx.h, recs_per_rank, C.byref(C.c_void_p())))
-            for cx in e2e_ctxs:
-                cx.fetch()
+        def e2e_issue(cx):
+            cx.upload_online(imgs_pinned, wl["Ts"], wl["boxes"], lp_main, params)
+            cx.run_async()
+            cx.check(cx.L.cs_allgather_topk(cx.h, recs_per_rank, C.byref(C.c_void_p())))
 
-        e2e_round()
+        def e2e_run(n_steps):
+            issued = fetched = 0
+            while fetched < n_steps:
+                while issued < n_steps and issued - fetched < K_:
+                    e2e_issue(e2e_ctxs[issued % K_])
+                    issued += 1
+                e2e_ctxs[fetched % K_].fetch()
+                fetched += 1
+
+        e2e_run(K_)
         barrier()
-        e2e_steps = max(len(e2e_ctxs), min(args.steps, 48))
-        e2e_steps -= e2e_steps % len(e2e_ctxs)
+        e2e_steps = max(K_, min(args.steps, 48))
         t0 = time.perf_counter()
-        for _ in range(e2e_steps // len(e2e_ctxs)):
-            e2e_round()
+        e2e_run(e2e_steps)
         barrier()
         e2e_ms = (time.perf_counter() - t0) * 1e3
     e2e_t = torch.tensor([e2e_ms], device="cuda", dtype=torch.float64)
@@ -640,7 +646,7 @@ def main():
     ap.add_argument("--no-prio", action="store_true", help="A/B: keep each batch's whole chain on one stream (no high-priority tail)")
     ap.add_argument("--raster-dt", action="store_true", help="A/B: two-pass raster-scan distance transform kernel instead of the cone form")
     ap.add_argument("--seq-lines", action="store_true", help="A/B: the line detectors' sequential kernels (one warp per frame) instead of ordered speculation")
-    ap.add_argument("--inflight", type=int, default=8, help="batches in flight on one GPU (contexts driven round-robin)")
+    ap.add_argument("--inflight", type=int, default=12, help="batches in flight on one GPU (contexts driven round-robin)")
     args = ap.parse_args()
     if args.steps is None:
         args.steps = 300 if args.impl == "ours" else 3

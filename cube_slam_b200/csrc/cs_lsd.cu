@@ -545,10 +545,20 @@ __device__ __forceinline__ bool lsd_double_equal(double a, double b)
     if (abs_max < DBL_MIN) abs_max = DBL_MIN;
     return (abs_diff / abs_max) <= (100.0 * DBL_EPSILON);
 }
-/* lsd.cpp:1138-1154 on the float level-line angle in degrees (negative = NOTDEF) */
+/* lsd.cpp:1138-1154 on the float level-line angle in degrees (negative = NOTDEF).  The decision is the reference's double comparison; a
+ * float evaluation of the same difference (error < 1e-5 rad) settles every case that is not within 2e-4 rad of the tolerance, so the
+ * double arithmetic (half-rate pipe, and this test runs for every pixel of every rectangle scan and every neighbour of every growth step)
+ * is only executed on the rare borderline pixel. */
 __device__ __forceinline__ bool lsd_aligned_deg(float deg, double theta, double prec)
 {
     if (deg < 0.f) return false;
+    {
+        float nf = fabsf((float)theta - deg * 0.017453292f);
+        if (nf > 4.712389f) nf = fabsf(nf - 6.2831855f);
+        const float pf = (float)prec;
+        if (nf < pf - 2e-4f) return true;
+        if (nf > pf + 2e-4f) return false;
+    }
     const double a = (double)deg * LSD_DEG2RAD;
     double n_theta = theta - a;
     if (n_theta < 0) n_theta = -n_theta;
@@ -658,13 +668,6 @@ __device__ int lsd_region_grow(const LsdFrame &F, const LsdView &V, const LsdReg
         int c_addr = -1;
         float deg = -1.f, csx = 0.f, csy = 0.f;
         uint32_t cseen = LSD_FREE;
-        if (V.rank < 0 && lane < 25) {
-            /* whichever neighbour is accepted and visited next, its 3 x 3 block lies inside this point's 5 x 5 block: ask for those records now */
-            const int p0 = R.get(base + i);
-            const int qy = F.row_of(p0), qx = p0 - qy * F.W;
-            const int yy = qy + lane / 5 - 2, xx = qx + lane % 5 - 2;
-            if (yy >= 0 && yy < F.H && xx >= 0 && xx < F.W) asm volatile("prefetch.global.L1 [%0];" ::"l"(F.pix + (yy * F.W + xx)));
-        }
         if (grp < navail) {
             const int pa = R.get(base + i + grp);
             const int py = F.row_of(pa), px = pa - py * F.W;
@@ -1240,8 +1243,9 @@ __global__ void __launch_bounds__(32) k_lsd_grow_seq(LsdGrowArgs A)
     LSD_PROF_ADD(6);
 }
 
-/* rect_improve + NFA of every candidate rectangle (lsd.cpp:520-534), one warp each: thousands of warps running the same code. */
-__global__ void __launch_bounds__(128) k_lsd_validate(LsdGrowArgs A)
+/* rect_improve + NFA of every candidate rectangle (lsd.cpp:520-534), one warp each: thousands of warps running the same code.  (A CTA of
+ * five warps per candidate, one warp per rectangle of a rect_improve phase, was measured slower: 3.5 vs 2.45 ms per 256 frames.) */
+__global__ void __launch_bounds__(128, 5) k_lsd_validate(LsdGrowArgs A)
 {
     const int f = blockIdx.y, lane = threadIdx.x & 31;
     const size_t npx = (size_t)A.W * A.H;
@@ -1480,7 +1484,7 @@ int lsd_run(cs_ctx *c, const uint8_t *imgs, bool imgs_on_device, int n_frames, i
     {
         const size_t smem = (size_t)LSD_SEQ_SCAP * 4;
         k_lsd_grow_seq<<<n_frames, 32, smem, st>>>(A);
-        k_lsd_validate<<<dim3(16, n_frames), 128, 0, st>>>(A);
+        k_lsd_validate<<<dim3(64, n_frames), 128, 0, st>>>(A); /* 256 warps per frame: a warp per candidate for all but the densest frames */
         k_lsd_emit<<<n_frames, 256, 0, st>>>(A);
     }
     cs_ctx_count_launches(c, 10);
