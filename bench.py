@@ -57,8 +57,8 @@ STAGE_BYTES = {
 }
 STAGE_KERNELS = {"dt": "k_dt_bi<N> (one launch per ROI width class)", "canny": "k_canny_nms", "hyst": "k_canny_hyst", "gray": "k_bgr2gray_flat",
                  "sweep": "k_sweep_warp", "fuse": "k_fuse_warp", "lines": "k_roi_lines",
-                 "lsd": "line detector (k_lsd_hblur/vblur/resize/grad/hist/scan/scatter + k_lsd_grow_par)"}
-LIMITERS = {"lsd": "the seed loop (k_lsd_grow_par) is a dependent chain of L2 / HBM gathers per region pixel: latency-bound, not HBM-bound",
+                 "lsd": "line detector (k_lsd_blur/resize/grad + k_lsd_grow_seq + k_lsd_validate/emit)"}
+LIMITERS = {"lsd": "the seed loop (k_lsd_grow_seq, one warp per frame, seeds in raster order) is a dependent chain of L2 / HBM gathers per region pixel: latency-bound, not HBM-bound",
             "canny": "integer ALU pipe (ncu, profiles/): not an HBM-bound kernel",
             "dt": "dependency chain of H row steps per ROI (latency), DRAM traffic below the algorithmic bytes"}
 
@@ -485,7 +485,7 @@ def run_ours(args, rank, world, local_rank):
     n_obj_loc = max(int(stats["n_objects"]), 1)
     # host threads, one context each, call the synchronous ABI entry point: the copies of one batch overlap the kernels of the others
     # (single GPU only: two threads issuing NCCL calls on two communicators in an unordered way could deadlock across ranks)
-    e2e_ctxs = ctxs[:8] if (len(ctxs) >= 2 and world == 1) else ctxs[:1]
+    e2e_ctxs = ctxs[:12] if (len(ctxs) >= 2 and world == 1) else ctxs[:1]
     e2e_out = [(np.zeros((n_obj_loc, topk), cs.CUBOID_DTYPE), np.zeros(n_obj_loc, np.int32)) for _ in e2e_ctxs]
     lp_main = main_mode.lp
 
@@ -521,7 +521,7 @@ def run_ours(args, rank, world, local_rank):
         # N > 1: one host thread keeps the batches in flight with the split calls (cs_batch_upload_online from pinned host frames,
         # cs_batch_run_async, cs_allgather_topk, cs_batch_fetch) as a rolling pipeline, so that every rank issues its collectives in the
         # same order: step s is issued on context s mod K, then the oldest outstanding step is fetched
-        e2e_ctxs = ctxs[:8]
+        e2e_ctxs = ctxs[:12]
         K_ = len(e2e_ctxs)
         e2e_mode = "one host thread, %d contexts as a rolling pipeline: cs_batch_upload_online + cs_batch_run_async + cs_allgather_topk + cs_batch_fetch" % K_
 

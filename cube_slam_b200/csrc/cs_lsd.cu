@@ -10,13 +10,14 @@
  *   k_lsd_blur    cvtColor + the 7 x 7 Gaussian (sigma 0.6/0.8), both passes, on 64 x 16 tiles; interior tiles' BGR bytes come in by TMA
  *                 (k_lsd_hblur / k_lsd_vblur: the two-pass pair of round 1, A/B path, cs_set_profiling bit 7)     lsd.cpp:452-457
  *   k_lsd_resize  cv::resize(x0.8, INTER_LINEAR) on doubles               lsd.cpp:459
- *   k_lsd_grad    2x2 gradient, modulus, fastAtan2 angle, max modulus     lsd.cpp:562-586
- *   k_lsd_hist / k_lsd_scan / k_lsd_scatter_rows   the 1024-bin pseudo-ordering as a STABLE counting sort (bins descending,
- *                 raster order inside a bin == the reference's linked lists)  lsd.cpp:588-634
+ *   k_lsd_grad    2x2 gradient, modulus, fastAtan2 angle                  lsd.cpp:562-586
+ *   (no ordering pass: ll_angle's 1024-bin pseudo-ordering, lsd.cpp:588-634, links the pixels by gradient bin, but flsd walks the node
+ *   vector by index, lsd.cpp:478-480, i.e. in the raster order the nodes were allocated in -- established in round 2 by compiling the
+ *   reference's own lsd.cpp, oracle/ref/; the counting-sort kernels of round 1 are gone)
  *
  * Seed loop (lsd.cpp:476-535).  The reference visits the ordered pixel list one seed at a time; a seed grows a region over the pixels no
  * earlier seed used, so the result is defined by the order -- but only through the `used` map.  It is cut in two:
- *   k_lsd_grow_seq   everything that reads or writes `used`: list scan, region_grow, region2rect, the density test, refine /
+ *   k_lsd_grow_seq   everything that reads or writes `used`: the raster scan for seeds, region_grow, region2rect, the density test, refine /
  *                    reduce_region_radius (lsd.cpp:478-519), one warp per frame (one 32-thread CTA, 8 KB of shared memory for the region
  *                    list, `used` as a bit per pixel in HBM read through L2).  Emits the candidate rectangles in seed order.
  *   k_lsd_validate   rect_improve and the NFA test (lsd.cpp:520-534, 873-1136) read the angle map only: one warp per candidate
@@ -262,13 +263,12 @@ __global__ void __launch_bounds__(256) k_lsd_resize(const double *__restrict__ b
  * (double)deg * DEG2RAD, recomputed where needed) and the 16-byte growth record {deg, cos, sin, claim}: (cos, sin) of float(angle),
  * each the correctly rounded float -- what region_grow accumulates (lsd.cpp:680-681). */
 __global__ void __launch_bounds__(256) k_lsd_grad(const double *__restrict__ scaled, int n_frames, int W, int H, double threshold,
-                                                  double *__restrict__ modgrad, float *__restrict__ angf, uint4 *__restrict__ pix,
-                                                  unsigned long long *__restrict__ max_bits)
+                                                  double *__restrict__ modgrad, float *__restrict__ angf, uint4 *__restrict__ pix)
 {
     /* grid: x over the pixels of one scaled frame, y = frame */
     const int f = blockIdx.y;
     const int addr = blockIdx.x * blockDim.x + threadIdx.x;
-    const bool inside = addr < W * H; /* no early exit: the warp reduces its maximum below */
+    const bool inside = addr < W * H;
     const size_t p = (size_t)f * W * H + addr;
     {
         const int y = addr / W, x = addr - y * W;
@@ -282,17 +282,6 @@ __global__ void __launch_bounds__(256) k_lsd_grad(const double *__restrict__ sca
             norm = sqrt((gx * gx + gy * gy) / 4);
             if (!(norm <= threshold)) deg = fast_atan2((float)gx, (float)(-gy));
         }
-        {
-            /* per-frame maximum of the defined gradients: one atomic per warp (positive doubles order like integers; a block never
-             * straddles two frames) */
-            unsigned long long mb = deg >= 0.f ? (unsigned long long)__double_as_longlong(norm) : 0ull;
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) {
-                const unsigned long long t = __shfl_xor_sync(0xffffffffu, mb, o);
-                mb = t > mb ? t : mb;
-            }
-            if ((threadIdx.x & 31) == 0 && mb) atomicMax(max_bits + f, mb);
-        }
         if (!inside) return;
         modgrad[p] = norm;
         angf[p] = deg;
@@ -304,158 +293,6 @@ __global__ void __launch_bounds__(256) k_lsd_grad(const double *__restrict__ sca
             r.z = __float_as_uint((float)sin(af));
         }
         pix[p] = r;
-    }
-}
-
-__device__ __forceinline__ double bin_coef_of(unsigned long long max_bits)
-{
-    const double max_grad = max_bits ? __longlong_as_double((long long)max_bits) : -1.0;
-    return (max_grad > 0) ? (double)(LSD_NBINS - 1) / max_grad : 0.0;
-}
-
-/* per (frame, chunk of rows) histogram of gradient bins */
-__global__ void __launch_bounds__(256) k_lsd_hist(const double *__restrict__ modgrad, const float *__restrict__ angf, int W, int H, int n_chunks,
-                                                  const unsigned long long *__restrict__ max_bits, int32_t *__restrict__ cnt)
-{
-    __shared__ int s_h[LSD_NBINS];
-    const int f = blockIdx.x / n_chunks, ch = blockIdx.x - f * n_chunks;
-    for (int i = threadIdx.x; i < LSD_NBINS; i += 256) s_h[i] = 0;
-    __syncthreads();
-    const double coef = bin_coef_of(max_bits[f]);
-    const int y0 = ch * LSD_CHUNK_ROWS, y1 = min(y0 + LSD_CHUNK_ROWS, H - 1);
-    const double *mg = modgrad + (size_t)f * W * H;
-    const float *an = angf + (size_t)f * W * H;
-    const int npx = (y1 - y0) * (W - 1);
-    for (int i = threadIdx.x; i < npx; i += 256) {
-        const int y = y0 + i / (W - 1), x = i % (W - 1);
-        if (an[(size_t)y * W + x] >= 0.f) atomicAdd(&s_h[(int)(mg[(size_t)y * W + x] * coef)], 1);
-    }
-    __syncthreads();
-    int32_t *o = cnt + ((size_t)f * n_chunks + ch) * LSD_NBINS;
-    for (int i = threadIdx.x; i < LSD_NBINS; i += 256) o[i] = s_h[i];
-}
-
-/* per frame: turn the per-chunk counts into absolute list offsets (bins descending, chunks ascending) */
-__global__ void __launch_bounds__(LSD_NBINS) k_lsd_scan(int n_chunks, int32_t *__restrict__ cnt, int32_t *__restrict__ list_len)
-{
-    __shared__ int s_tot[LSD_NBINS];
-    const int f = blockIdx.x, b = threadIdx.x;
-    int32_t *c = cnt + (size_t)f * n_chunks * LSD_NBINS;
-    int run = 0;
-    for (int ch = 0; ch < n_chunks; ch++) {
-        const int v = c[(size_t)ch * LSD_NBINS + b];
-        c[(size_t)ch * LSD_NBINS + b] = run;
-        run += v;
-    }
-    s_tot[b] = run;
-    __syncthreads();
-    /* start[b] = sum of totals of the higher bins: inclusive scan over the reversed order */
-    const int rb = LSD_NBINS - 1 - b; /* rank in descending order */
-    for (int d = 1; d < LSD_NBINS; d <<= 1) {
-        int v = 0;
-        if (rb >= d) v = s_tot[b + d]; /* element d places earlier in descending order == bin b + d */
-        __syncthreads();
-        s_tot[b] += v;
-        __syncthreads();
-    }
-    const int start = s_tot[b] - run;
-    if (b == 0) list_len[f] = s_tot[0];
-    for (int ch = 0; ch < n_chunks; ch++) c[(size_t)ch * LSD_NBINS + b] += start;
-}
-
-/* stable scatter: one warp walks its chunk in raster order, 32 pixels per step */
-__global__ void __launch_bounds__(32) k_lsd_scatter(const double *__restrict__ modgrad, const float *__restrict__ angf, int W, int H, int n_chunks,
-                                                    const unsigned long long *__restrict__ max_bits, const int32_t *__restrict__ cnt,
-                                                    int32_t *__restrict__ list)
-{
-    __shared__ int s_c[LSD_NBINS];
-    const int f = blockIdx.x / n_chunks, ch = blockIdx.x - f * n_chunks;
-    const int lane = threadIdx.x;
-    const int32_t *base = cnt + ((size_t)f * n_chunks + ch) * LSD_NBINS;
-    for (int i = lane; i < LSD_NBINS; i += 32) s_c[i] = base[i];
-    __syncwarp();
-    const double coef = bin_coef_of(max_bits[f]);
-    const int y0 = ch * LSD_CHUNK_ROWS, y1 = min(y0 + LSD_CHUNK_ROWS, H - 1);
-    const double *mg = modgrad + (size_t)f * W * H;
-    const float *an = angf + (size_t)f * W * H;
-    int32_t *out = list + (size_t)f * W * H;
-    const int npx = (y1 - y0) * (W - 1);
-    for (int i0 = 0; i0 < npx; i0 += 32) {
-        const int i = i0 + lane;
-        bool ok = i < npx;
-        int addr = 0, bin = -1 - lane; /* inactive lanes get unique negative keys */
-        if (ok) {
-            const int y = y0 + i / (W - 1), x = i % (W - 1);
-            addr = y * W + x;
-            ok = an[addr] >= 0.f;
-            if (ok) bin = (int)(mg[addr] * coef);
-        }
-        const unsigned m = __match_any_sync(0xffffffffu, bin);
-        const int rank = __popc(m & ((1u << lane) - 1u));
-        const int leader = __ffs(m) - 1;
-        int old = 0;
-        if (ok && lane == leader) {
-            old = s_c[bin];
-            s_c[bin] = old + __popc(m);
-        }
-        old = __shfl_sync(0xffffffffu, old, leader);
-        if (ok) out[old + rank] = addr;
-        __syncwarp();
-    }
-}
-
-/* the same scatter with one warp per ROW of the chunk: row histograms in shared memory, a prefix over the rows of each bin, then every warp
- * walks only its own row (the chain of dependent steps is 8 times shorter than k_lsd_scatter's; that one stays as the A/B path) */
-__global__ void __launch_bounds__(32 * LSD_CHUNK_ROWS) k_lsd_scatter_rows(const double *__restrict__ modgrad, const float *__restrict__ angf, int W, int H, int n_chunks,
-                                                                          const unsigned long long *__restrict__ max_bits, const int32_t *__restrict__ cnt,
-                                                                          int32_t *__restrict__ list)
-{
-    __shared__ int s_c[LSD_CHUNK_ROWS][LSD_NBINS];
-    const int f = blockIdx.x / n_chunks, ch = blockIdx.x - f * n_chunks;
-    const int tid = threadIdx.x, lane = tid & 31, r = tid >> 5;
-    const int32_t *base = cnt + ((size_t)f * n_chunks + ch) * LSD_NBINS;
-    for (int i = lane; i < LSD_NBINS; i += 32) s_c[r][i] = 0;
-    __syncwarp();
-    const double coef = bin_coef_of(max_bits[f]);
-    const int y = ch * LSD_CHUNK_ROWS + r;
-    const bool row_ok = y < H - 1;
-    const double *mg = modgrad + (size_t)f * W * H + (size_t)y * W;
-    const float *an = angf + (size_t)f * W * H + (size_t)y * W;
-    int32_t *out = list + (size_t)f * W * H;
-    if (row_ok)
-        for (int x = lane; x < W - 1; x += 32)
-            if (an[x] >= 0.f) atomicAdd(&s_c[r][(int)(mg[x] * coef)], 1);
-    __syncthreads();
-    for (int b = tid; b < LSD_NBINS; b += 32 * LSD_CHUNK_ROWS) {
-        int run = base[b];
-#pragma unroll
-        for (int k = 0; k < LSD_CHUNK_ROWS; k++) {
-            const int v = s_c[k][b];
-            s_c[k][b] = run;
-            run += v;
-        }
-    }
-    __syncthreads();
-    if (!row_ok) return;
-    for (int x0 = 0; x0 < W - 1; x0 += 32) {
-        const int x = x0 + lane;
-        bool ok = x < W - 1;
-        int bin = -1 - lane; /* inactive lanes get unique negative keys */
-        if (ok) {
-            ok = an[x] >= 0.f;
-            if (ok) bin = (int)(mg[x] * coef);
-        }
-        const unsigned m = __match_any_sync(0xffffffffu, bin);
-        const int rank = __popc(m & ((1u << lane) - 1u));
-        const int leader = __ffs(m) - 1;
-        int old = 0;
-        if (ok && lane == leader) {
-            old = s_c[r][bin];
-            s_c[r][bin] = old + __popc(m);
-        }
-        old = __shfl_sync(0xffffffffu, old, leader);
-        if (ok) out[old + rank] = y * W + x;
-        __syncwarp();
     }
 }
 
@@ -1209,18 +1046,14 @@ __global__ void __launch_bounds__(32) k_lsd_grow_seq(LsdGrowArgs A)
     LsdView V;
     V.rank = -1;
     V.frontier = 0;
-    const int32_t *list = A.list + f * npx;
-    const int n_list = A.list_len[f];
+    const int n_px = (int)npx;
     int n_cand = 0;
-    for (int i0 = 0; i0 < n_list; i0 += 32) {
-        /* 32 list entries at a time: seeds whose pixel is already used are skipped by ballot */
-        const int i = i0 + lane;
-        int adx = 0;
-        bool seed = false;
-        if (i < n_list) {
-            adx = list[i];
-            seed = !F.used_bit(adx); /* the list holds pixels with a defined angle only */
-        }
+    for (int i0 = 0; i0 < n_px; i0 += 32) {
+        /* Seeds in RASTER order: flsd walks its coorlist vector by index (lsd.cpp:478-480), and ll_angle fills that vector in scan order; the
+         * gradient-bin links it also builds (lsd.cpp:588-634) are never followed.  32 pixels at a time: those without a defined angle (which
+         * includes the last row and column) or already used are skipped by ballot. */
+        const int adx = i0 + lane;
+        const bool seed = adx < n_px && F.angf[adx] >= 0.f && !F.used_bit(adx);
         unsigned todo = __ballot_sync(0xffffffffu, seed);
         while (todo) {
             const int sl = __ffs(todo) - 1;
@@ -1347,7 +1180,7 @@ struct Buf {
 };
 
 struct LsdState {
-    Buf img, tmp, blur, scaled, modgrad, angf, pix, list, st, arena, spill, maxg, cnt, llen, raw, nraw, out, nout, redo, stats, lgam, ubits, cand, ncand, candline, err;
+    Buf img, tmp, blur, scaled, modgrad, angf, pix, arena, raw, nraw, out, nout, redo, stats, lgam, ubits, cand, ncand, candline, err;
     bool lgam_filled = false;
     int last_frames = 0, last_W = 0, last_H = 0, cap = 0;
 };
@@ -1385,7 +1218,6 @@ int lsd_run(cs_ctx *c, const uint8_t *imgs, bool imgs_on_device, int n_frames, i
     const int W = (int)std::lrint(w * SCALE), H = (int)std::lrint(h * SCALE);
     if (W < 2 || H < 2) return cs_ctx_fail(c, CS_ERR_INVALID_ARG, "image too small for LSD");
     const size_t px = (size_t)n_frames * w * h, spx = (size_t)n_frames * W * H;
-    const int n_chunks = (H - 1 + LSD_CHUNK_ROWS - 1) / LSD_CHUNK_ROWS;
     const int arena_cap = (int)(((size_t)W * H * 2 + 64 + 3) & ~(size_t)3); /* ints per frame */
     int rc;
     const uint8_t *d_img = imgs;
@@ -1397,8 +1229,7 @@ int lsd_run(cs_ctx *c, const uint8_t *imgs, bool imgs_on_device, int n_frames, i
     }
     if ((rc = ensure(c, S.tmp, cs_ctx_seq_lines(c) ? px * 8 : 0)) || (rc = ensure(c, S.blur, px * 8)) || (rc = ensure(c, S.scaled, spx * 8)) ||
         (rc = ensure(c, S.modgrad, spx * 8)) || (rc = ensure(c, S.angf, spx * 4)) || (rc = ensure(c, S.pix, spx * 16)) ||
-        (rc = ensure(c, S.list, spx * 4)) || (rc = ensure(c, S.arena, (size_t)n_frames * arena_cap * 4)) || (rc = ensure(c, S.maxg, (size_t)n_frames * 8)) ||
-        (rc = ensure(c, S.cnt, (size_t)n_frames * n_chunks * LSD_NBINS * 4)) || (rc = ensure(c, S.llen, (size_t)n_frames * 4)) ||
+        (rc = ensure(c, S.arena, (size_t)n_frames * arena_cap * 4)) ||
         (rc = ensure(c, S.raw, (size_t)n_frames * cap * 16)) || (rc = ensure(c, S.nraw, (size_t)n_frames * 4)) ||
         (rc = ensure(c, S.out, (size_t)n_frames * cap * 16)) || (rc = ensure(c, S.nout, (size_t)n_frames * 4)) ||
         (rc = ensure(c, S.redo, (size_t)n_frames * 4)) || (rc = ensure(c, S.stats, (size_t)n_frames * 16)) ||
@@ -1419,7 +1250,6 @@ int lsd_run(cs_ctx *c, const uint8_t *imgs, bool imgs_on_device, int n_frames, i
     const double LOG_NT = 5 * (std::log10((double)W) + std::log10((double)H)) / 2 + std::log10(11.0);
     const int min_reg_size = (int)(-LOG_NT / std::log10(p));
 
-    cudaMemsetAsync(S.maxg.p, 0, (size_t)n_frames * 8, st);
     cudaMemsetAsync(S.err.p, 0, 16, st);
     cudaMemsetAsync(S.stats.p, 0, (size_t)n_frames * 16, st);
     const dim3 g_src((w * h + 255) / 256, n_frames), g_dst((W * H + 255) / 256, n_frames);
@@ -1438,15 +1268,7 @@ int lsd_run(cs_ctx *c, const uint8_t *imgs, bool imgs_on_device, int n_frames, i
     }
     k_lsd_resize<<<g_dst, 256, 0, st>>>((const double *)S.blur.p, n_frames, w, h, W, H, 1. / SCALE, (double *)S.scaled.p);
     k_lsd_grad<<<g_dst, 256, 0, st>>>((const double *)S.scaled.p, n_frames, W, H, rho, (double *)S.modgrad.p, (float *)S.angf.p,
-                                                       (uint4 *)S.pix.p, (unsigned long long *)S.maxg.p);
-    k_lsd_hist<<<n_frames * n_chunks, 256, 0, st>>>((const double *)S.modgrad.p, (const float *)S.angf.p, W, H, n_chunks, (const unsigned long long *)S.maxg.p, (int32_t *)S.cnt.p);
-    k_lsd_scan<<<n_frames, LSD_NBINS, 0, st>>>(n_chunks, (int32_t *)S.cnt.p, (int32_t *)S.llen.p);
-    if (cs_ctx_seq_lines(c))
-        k_lsd_scatter<<<n_frames * n_chunks, 32, 0, st>>>((const double *)S.modgrad.p, (const float *)S.angf.p, W, H, n_chunks, (const unsigned long long *)S.maxg.p,
-                                                      (const int32_t *)S.cnt.p, (int32_t *)S.list.p);
-    else
-        k_lsd_scatter_rows<<<n_frames * n_chunks, 32 * LSD_CHUNK_ROWS, 0, st>>>((const double *)S.modgrad.p, (const float *)S.angf.p, W, H, n_chunks, (const unsigned long long *)S.maxg.p,
-                                                      (const int32_t *)S.cnt.p, (int32_t *)S.list.p);
+                                                       (uint4 *)S.pix.p);
     LsdGrowArgs A;
     A.W = W;
     A.H = H;
@@ -1455,8 +1277,8 @@ int lsd_run(cs_ctx *c, const uint8_t *imgs, bool imgs_on_device, int n_frames, i
     A.pix = (uint4 *)S.pix.p;
     A.angf = (const float *)S.angf.p;
     A.modgrad = (const double *)S.modgrad.p;
-    A.list = (const int32_t *)S.list.p;
-    A.list_len = (const int32_t *)S.llen.p;
+    A.list = nullptr;
+    A.list_len = nullptr;
     A.st = nullptr;
     A.arena = (int32_t *)S.arena.p;
     A.arena_cap = arena_cap;
@@ -1487,7 +1309,7 @@ int lsd_run(cs_ctx *c, const uint8_t *imgs, bool imgs_on_device, int n_frames, i
         k_lsd_validate<<<dim3(64, n_frames), 128, 0, st>>>(A); /* 256 warps per frame: a warp per candidate for all but the densest frames */
         k_lsd_emit<<<n_frames, 256, 0, st>>>(A);
     }
-    cs_ctx_count_launches(c, 10);
+    cs_ctx_count_launches(c, 6);
     if (cudaGetLastError() != cudaSuccess) return cs_ctx_fail(c, CS_ERR_CUDA, "LSD kernel launch failed: %s", cudaGetErrorString(cudaGetLastError()));
     S.last_frames = n_frames;
     S.last_W = W;
@@ -1520,8 +1342,7 @@ int cs_lsd_run_device(cs_ctx *c, const uint8_t *d_imgs, int n_frames, int w, int
 void cs_lsd_destroy(void *state)
 {
     LsdState *S = (LsdState *)state;
-    Buf *all[] = {&S->img, &S->tmp, &S->blur, &S->scaled, &S->modgrad, &S->angf, &S->pix, &S->list, &S->st, &S->arena, &S->spill, &S->maxg, &S->cnt,
-                  &S->llen, &S->raw, &S->nraw, &S->out, &S->nout, &S->redo, &S->stats, &S->lgam, &S->ubits, &S->cand, &S->ncand, &S->candline, &S->err};
+    Buf *all[] = {&S->img, &S->tmp, &S->blur, &S->scaled, &S->modgrad, &S->angf, &S->pix, &S->arena, &S->raw, &S->nraw, &S->out, &S->nout, &S->redo, &S->stats, &S->lgam, &S->ubits, &S->cand, &S->ncand, &S->candline, &S->err};
     for (Buf *b : all)
         if (b->p) cudaFree(b->p);
     delete S;
@@ -1596,10 +1417,18 @@ int cs_debug_lsd(cs_ctx *c, int frame, int32_t *scaled_wh, double *scaled, doubl
         cudaMemcpy(deg.data(), (float *)S->angf.p + frame * npx, npx * 4, cudaMemcpyDeviceToHost);
         for (size_t i = 0; i < npx; i++) angles[i] = deg[i] < 0.f ? LSD_NOTDEF : (double)deg[i] * LSD_DEG2RAD;
     }
-    int32_t ll = 0;
-    cudaMemcpy(&ll, (int32_t *)S->llen.p + frame, 4, cudaMemcpyDeviceToHost);
-    if (list_len) *list_len = ll;
-    if (list) cudaMemcpy(list, (int32_t *)S->list.p + frame * npx, (size_t)ll * 4, cudaMemcpyDeviceToHost);
+    if (list || list_len) {
+        /* the order seeds are visited in: raster order over the pixels with a defined angle (lsd.cpp:478-481) */
+        std::vector<float> deg(npx);
+        cudaMemcpy(deg.data(), (float *)S->angf.p + frame * npx, npx * 4, cudaMemcpyDeviceToHost);
+        int32_t ll = 0;
+        for (size_t i = 0; i < npx; i++)
+            if (deg[i] >= 0.f) {
+                if (list) list[ll] = (int32_t)i;
+                ll++;
+            }
+        if (list_len) *list_len = ll;
+    }
     int32_t nr = 0;
     cudaMemcpy(&nr, (int32_t *)S->nraw.p + frame, 4, cudaMemcpyDeviceToHost);
     if (n_raw) *n_raw = nr;

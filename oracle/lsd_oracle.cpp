@@ -229,23 +229,19 @@ struct Lsd {
                     if (norm > max_grad) max_grad = norm;
                 }
             }
-        /* bucket sort: bins descending, raster order inside a bin */
-        const double bin_coef = (max_grad > 0) ? double(n_bins - 1) / max_grad : 0;
-        std::vector<int> count(n_bins, 0);
+        /* The order seeds are visited in.  ll_angle (lsd.cpp:588-634) files every pixel into one of 1024 gradient bins and links the bins,
+         * highest first, through coorlist::next -- but the nodes live in a std::vector filled in RASTER order (count increments with the scan),
+         * and flsd walks that vector by index (lsd.cpp:478-480: `for i < list.size(): adx = list[i].p.x + list[i].p.y * img_width`), never
+         * through the links.  So the reference visits seeds in raster order over x < W - 1, y < H - 1; the pseudo-ordering is dead code in this
+         * vendored file.  (Round 1 restated the links, not the loop: compiled from its own source -- oracle/ref/lsd_ref.cpp -- the reference
+         * reproduces all 271 segments of its shipped 0000_edge.txt, the round-1 restatement reproduced 116.)  The vector has W * H nodes; the
+         * ones past (W - 1)(H - 1) keep their default point (0, 0), a seed already used by then. */
+        (void)n_bins;
+        (void)max_grad;
+        list.assign((size_t)(W - 1) * (H - 1), 0);
+        size_t k = 0;
         for (int y = 0; y < H - 1; ++y)
-            for (int x = 0; x < W - 1; ++x) count[int(modgrad[(size_t)y * W + x] * bin_coef)]++;
-        std::vector<int> start(n_bins, 0);
-        int acc = 0;
-        for (int b = (int)n_bins - 1; b >= 0; b--) {
-            start[b] = acc;
-            acc += count[b];
-        }
-        list.assign(acc, 0);
-        for (int y = 0; y < H - 1; ++y)
-            for (int x = 0; x < W - 1; ++x) {
-                const int b = int(modgrad[(size_t)y * W + x] * bin_coef);
-                list[start[b]++] = y * W + x;
-            }
+            for (int x = 0; x < W - 1; ++x) list[k++] = y * W + x;
     }
 
     /* lsd.cpp:637-688 */
@@ -577,6 +573,24 @@ struct Lsd {
 }  // namespace
 
 extern "C" float lsd_orc_fast_atan2(float y, float x) { return fast_atan2(y, x); }
+
+/* the two OpenCV primitives of lsd.cpp:457-459 on their own (oracle/ref/minicv.hpp forwards cv::GaussianBlur / cv::resize to them when the
+ * reference's lsd.cpp is compiled into oracle/_ref) */
+extern "C" void lsd_orc_gaussian7(const double *src, int w, int h, double *dst)
+{
+    std::vector<double> s(src, src + (size_t)w * h), b;
+    gaussian_blur7(s, w, h, b);
+    std::memcpy(dst, b.data(), sizeof(double) * b.size());
+}
+extern "C" void lsd_orc_resize(const double *src, int w, int h, double scale, double *dst, int *dw, int *dh)
+{
+    std::vector<double> s(src, src + (size_t)w * h), r;
+    int W = 0, H = 0;
+    resize_linear(s, w, h, scale, r, W, H);
+    std::memcpy(dst, r.data(), sizeof(double) * r.size());
+    *dw = W;
+    *dh = H;
+}
 
 extern "C" void lsd_orc_blur_resize(const double *src, int w, int h, double *blur_out, double *scaled_out, int *dw, int *dh)
 {

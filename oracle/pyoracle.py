@@ -16,8 +16,14 @@ _LIB_PATH = os.path.join(_HERE, "_build", "liboracle.so")
 def build(force=False):
     """Compile the oracle with the committed Makefile (g++ -O2 -ffp-contract=off)."""
     srcs = [os.path.join(_HERE, f) for f in os.listdir(_HERE) if f.endswith((".cpp", ".h"))]
-    if (not force and os.path.exists(_LIB_PATH)
-            and all(os.path.getmtime(_LIB_PATH) >= os.path.getmtime(s) for s in srcs)):
+    fresh = os.path.exists(_LIB_PATH) and all(os.path.getmtime(_LIB_PATH) >= os.path.getmtime(s) for s in srcs)
+    # oracle/_ref (the reference's own lsd.cpp) is built where the reference checkout exists; elsewhere the prebuilt file is used as it is
+    ref_src = "/root/reference/line_lbd/libs/lsd.cpp"
+    ref_lib = os.path.join(_HERE, "_ref", "liblsd_ref.so")
+    if os.path.exists(ref_src):
+        deps = [ref_src, _LIB_PATH] + [os.path.join(_HERE, "ref", f) for f in os.listdir(os.path.join(_HERE, "ref"))]
+        fresh = fresh and os.path.exists(ref_lib) and all(os.path.getmtime(ref_lib) >= os.path.getmtime(d) for d in deps)
+    if not force and fresh:
         return _LIB_PATH
     subprocess.check_call(["make", "-C", _HERE, "-s"] + (["-B"] if force else []))
     return _LIB_PATH
@@ -270,6 +276,32 @@ def lsd_detect(img, line_length_thres=15.0, cap=8192, want_stages=False, refine_
         st["list"] = st["list"][:ll.value].copy()
         res["stages"] = st
     return res
+
+
+_REF_LSD = None
+_REF_LSD_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_ref", "liblsd_ref.so")
+
+
+def ref_lsd_available():
+    return os.path.exists(_REF_LSD_PATH)
+
+
+def ref_lsd_detect(img, cap=8192):
+    """The reference's OWN LSD (line_lbd/libs/lsd.cpp compiled from /root/reference into oracle/_ref/liblsd_ref.so, see oracle/ref/):
+    createLineSegmentDetector(LSD_REFINE_ADV)->detect(gray) as LSDDetector::detectImpl calls it for octave 0 -> n x 4 float32, the raw
+    segments before the key-line filter.  BGR input is converted with the oracle's cvtColor restatement (pinned to cv2)."""
+    global _REF_LSD
+    lib()  # liblsd_ref.so resolves the three OpenCV primitives from liboracle.so
+    if _REF_LSD is None:
+        _REF_LSD = C.CDLL(_REF_LSD_PATH)
+        _REF_LSD.ref_lsd_detect.restype = C.c_int
+    img = np.ascontiguousarray(img, np.uint8)
+    gray = img if img.ndim == 2 else np.ascontiguousarray(bgr2gray(img))
+    out = np.zeros((cap, 4), np.float32)
+    n = _REF_LSD.ref_lsd_detect(_p(gray, C.c_uint8), gray.shape[1], gray.shape[0], _p(out, C.c_float), cap)
+    if n < 0:
+        raise RuntimeError("ref_lsd_detect failed")
+    return out[:min(n, cap)].copy()
 
 
 # ------------------------------------------------------------------------------------------- EDLines

@@ -1,0 +1,312 @@
+/*
+ * oracle/ref/minicv.hpp -- CPU ORACLE, TEST INFRASTRUCTURE ONLY.
+ *
+ * The smallest stand-in for the OpenCV C++ API that lets the reference's OWN line_lbd/libs/lsd.cpp compile unmodified from where it lies
+ * (/root/reference; this image has no OpenCV C++ headers).  oracle/ref/lsd_ref.cpp defines the include guard of the reference's
+ * precomp.hpp, includes this file and then the reference source: the seed loop, region growing, rectangle fitting, refinement and NFA
+ * test that end up in oracle/_ref/liblsd_ref.so are the reference's code, not a restatement.
+ *
+ * What is NOT the reference here, and how it is pinned instead: the three OpenCV primitives lsd.cpp calls -- cv::GaussianBlur (7 x 7,
+ * CV_64F), cv::resize (x 0.8, INTER_LINEAR, CV_64F) and cv::fastAtan2 -- are forwarded to the oracle's restatements
+ * (lsd_orc_gaussian7 / lsd_orc_resize / lsd_orc_fast_atan2 in oracle/lsd_oracle.cpp), which tests/test_oracle_lines.py checks bit for
+ * bit against the in-container cv2 4.13.  Everything else below is containers: Mat as a contiguous row-major buffer, Point, Vec, Size,
+ * Input/OutputArray as thin views, and abort() stubs for the drawing helpers at the end of lsd.cpp that the path never calls.
+ */
+#ifndef ORC_MINICV_HPP
+#define ORC_MINICV_HPP
+
+#include <algorithm>
+#include <cfloat>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <memory>
+#include <stdexcept>
+#include <vector>
+
+extern "C" void lsd_orc_gaussian7(const double *src, int w, int h, double *dst);
+extern "C" void lsd_orc_resize(const double *src, int w, int h, double scale, double *dst, int *dw, int *dh);
+extern "C" float lsd_orc_fast_atan2(float y, float x);
+
+#define CV_PI 3.1415926535897932384626433832795
+#define CV_EXPORTS
+#define CV_WRAP
+#define CV_8U 0
+#define CV_32F 5
+#define CV_64F 6
+#define CV_MAKETYPE(depth, cn) ((depth) + (((cn)-1) << 3))
+#define CV_8UC1 CV_MAKETYPE(CV_8U, 1)
+#define CV_8UC3 CV_MAKETYPE(CV_8U, 3)
+#define CV_32FC4 CV_MAKETYPE(CV_32F, 4)
+#define CV_64FC1 CV_MAKETYPE(CV_64F, 1)
+#define CV_BGR2GRAY 6
+#define CV_Assert(expr)                                                                     \
+    do {                                                                                    \
+        if (!(expr)) throw std::runtime_error(std::string("CV_Assert failed: ") + #expr);  \
+    } while (0)
+
+namespace cv {
+typedef unsigned char uchar;
+
+template <typename T>
+struct Point_ {
+    T x, y;
+    Point_() : x(0), y(0) {}
+    Point_(T x_, T y_) : x(x_), y(y_) {}
+};
+typedef Point_<int> Point2i;
+typedef Point2i Point;
+typedef Point_<float> Point2f;
+typedef Point_<double> Point2d;
+
+template <typename T, int N>
+struct Vec {
+    T val[N];
+    Vec() { for (int i = 0; i < N; i++) val[i] = T(0); }
+    Vec(T a, T b, T c, T d) { val[0] = a; val[1] = b; val[2] = c; val[3] = d; }
+    T &operator[](int i) { return val[i]; }
+    const T &operator[](int i) const { return val[i]; }
+};
+typedef Vec<float, 4> Vec4f;
+typedef Vec<int, 4> Vec4i;
+
+struct Size {
+    int width, height;
+    Size() : width(0), height(0) {}
+    Size(int w, int h) : width(w), height(h) {}
+    int area() const { return width * height; }
+    bool operator==(const Size &o) const { return width == o.width && height == o.height; }
+    bool operator!=(const Size &o) const { return !(*this == o); }
+};
+
+struct Scalar {
+    double val[4];
+    Scalar(double a = 0, double b = 0, double c = 0, double d = 0) { val[0] = a; val[1] = b; val[2] = c; val[3] = d; }
+    static Scalar all(double v) { return Scalar(v, v, v, v); }
+};
+
+template <typename T> struct DepthOf;
+template <> struct DepthOf<uchar> { enum { value = CV_8U }; };
+template <> struct DepthOf<float> { enum { value = CV_32F }; };
+template <> struct DepthOf<double> { enum { value = CV_64F }; };
+
+inline size_t depth_bytes(int type)
+{
+    switch (type & 7) {
+        case CV_8U: return 1;
+        case CV_32F: return 4;
+        case CV_64F: return 8;
+        default: throw std::runtime_error("minicv: unsupported depth");
+    }
+}
+
+class _OutputArray;
+class Mat {
+public:
+    int rows, cols;
+    uchar *data;
+    Mat() : rows(0), cols(0), data(nullptr), type_(CV_8UC1) {}
+    Mat(int r, int c, int type) : rows(0), cols(0), data(nullptr), type_(type) { create(r, c, type); }
+    explicit Mat(const std::vector<Vec4f> &v) : rows(0), cols(0), data(nullptr), type_(CV_32FC4)
+    {
+        create((int)v.size(), 1, CV_32FC4);
+        if (!v.empty()) memcpy(data, v.data(), v.size() * sizeof(Vec4f));
+    }
+    explicit Mat(const std::vector<double> &v) : rows(0), cols(0), data(nullptr), type_(CV_64FC1)
+    {
+        create((int)v.size(), 1, CV_64FC1);
+        if (!v.empty()) memcpy(data, v.data(), v.size() * sizeof(double));
+    }
+    void create(int r, int c, int type)
+    {
+        if (r == rows && c == cols && type == type_ && data) return;
+        rows = r;
+        cols = c;
+        type_ = type;
+        store_ = std::make_shared<std::vector<uchar>>((size_t)r * c * elemSize() + 64, 0);
+        data = store_->data();
+    }
+    void create(Size s, int type) { create(s.height, s.width, type); }
+    bool empty() const { return data == nullptr || rows * cols == 0; }
+    int type() const { return type_; }
+    int depth() const { return type_ & 7; }
+    int channels() const { return (type_ >> 3) + 1; }
+    size_t elemSize() const { return depth_bytes(type_) * (size_t)channels(); }
+    size_t total() const { return (size_t)rows * cols; }
+    Size size() const { return Size(cols, rows); }
+    bool isContinuous() const { return true; }
+    uchar *ptr(int r = 0) { return data + (size_t)r * cols * elemSize(); }
+    const uchar *ptr(int r = 0) const { return data + (size_t)r * cols * elemSize(); }
+    template <typename T> T *ptr(int r = 0) { return reinterpret_cast<T *>(ptr(r)); }
+    template <typename T> const T *ptr(int r = 0) const { return reinterpret_cast<const T *>(ptr(r)); }
+    template <typename T> T &at(int i) { return reinterpret_cast<T *>(data)[i]; }
+    template <typename T> const T &at(int i) const { return reinterpret_cast<const T *>(data)[i]; }
+    int checkVector(int) const { return -1; }
+    Mat clone() const
+    {
+        Mat m(rows, cols, type_);
+        if (!empty()) memcpy(m.data, data, total() * elemSize());
+        return m;
+    }
+    /* depth conversion between the two types the path uses (8U -> 64F, or a copy) */
+    void convertTo(Mat &dst, int rtype) const
+    {
+        if (channels() != 1) throw std::runtime_error("minicv: convertTo of a multi-channel Mat");
+        Mat out(rows, cols, CV_MAKETYPE(rtype & 7, 1));
+        const size_t n = total();
+        if (depth() == (rtype & 7))
+            memcpy(out.data, data, n * elemSize());
+        else if (depth() == CV_8U && (rtype & 7) == CV_64F)
+            for (size_t i = 0; i < n; i++) out.ptr<double>()[i] = (double)data[i];
+        else
+            throw std::runtime_error("minicv: unsupported conversion");
+        dst = out;
+    }
+    void copyTo(const _OutputArray &dst) const;
+
+protected:
+    int type_;
+    std::shared_ptr<std::vector<uchar>> store_;
+};
+
+template <typename T>
+class Mat_ : public Mat {
+public:
+    struct Line { /* one row or column of the matrix, for setTo */
+        T *p;
+        size_t stride;
+        int n;
+        void setTo(double v)
+        {
+            for (int i = 0; i < n; i++) p[(size_t)i * stride] = (T)v;
+        }
+    };
+    Mat_() : Mat() { type_ = CV_MAKETYPE(DepthOf<T>::value, 1); }
+    Mat_(int r, int c) : Mat(r, c, CV_MAKETYPE(DepthOf<T>::value, 1)) {}
+    explicit Mat_(Size s) : Mat(s.height, s.width, CV_MAKETYPE(DepthOf<T>::value, 1)) {}
+    Mat_(const Mat &m) : Mat() { assign(m); } /* converts the depth like cv::Mat_<T>(const Mat&) does */
+    Mat_ &operator=(const Mat &m)
+    {
+        assign(m);
+        return *this;
+    }
+    static Mat_ zeros(Size s) { return Mat_(s); } /* create() zero-fills */
+    T &operator()(int r, int c) { return reinterpret_cast<T *>(data)[(size_t)r * cols + c]; }
+    Line row(int r) { return Line{reinterpret_cast<T *>(data) + (size_t)r * cols, 1, cols}; }
+    Line col(int c) { return Line{reinterpret_cast<T *>(data) + c, (size_t)cols, rows}; }
+    using Mat::ptr;
+
+private:
+    void assign(const Mat &m)
+    {
+        const int want = CV_MAKETYPE(DepthOf<T>::value, 1);
+        if (m.empty()) {
+            static_cast<Mat &>(*this) = Mat();
+            type_ = want;
+        } else if (m.type() == want)
+            static_cast<Mat &>(*this) = m;
+        else {
+            Mat tmp;
+            m.convertTo(tmp, want);
+            static_cast<Mat &>(*this) = tmp;
+        }
+    }
+};
+
+class _InputArray {
+public:
+    _InputArray() : m_(nullptr), v_(nullptr) {}
+    _InputArray(const Mat &m) : m_(const_cast<Mat *>(&m)), v_(nullptr) {}
+    _InputArray(const std::vector<Vec4f> &v) : m_(nullptr), v_(const_cast<std::vector<Vec4f> *>(&v)) {}
+    Mat getMat() const { return m_ ? *m_ : (v_ ? Mat(*v_) : Mat()); }
+    bool empty() const { return m_ ? m_->empty() : (v_ ? v_->empty() : true); }
+    int channels() const { return m_ ? m_->channels() : 4; }
+    Size size() const { return m_ ? m_->size() : Size(); }
+    bool needed() const { return m_ != nullptr || v_ != nullptr; }
+
+protected:
+    Mat *m_;
+    std::vector<Vec4f> *v_;
+};
+class _OutputArray : public _InputArray {
+public:
+    _OutputArray() {}
+    _OutputArray(Mat &m) : _InputArray(m) {}
+    template <typename T> _OutputArray(Mat_<T> &m) : _InputArray(m), typed_(CV_MAKETYPE(DepthOf<T>::value, 1)) {}
+    _OutputArray(std::vector<Vec4f> &v) : _InputArray(v) {}
+    Mat &getMatRef() const
+    {
+        if (!m_) throw std::runtime_error("minicv: getMatRef of a non-Mat array");
+        return *m_;
+    }
+    void assign(const Mat &src) const
+    {
+        if (v_) {
+            if (src.type() != CV_32FC4) throw std::runtime_error("minicv: only Vec4f vectors are supported as output");
+            v_->resize(src.total());
+            if (src.total()) memcpy(v_->data(), src.data, src.total() * sizeof(Vec4f));
+        } else if (m_) {
+            if (typed_ >= 0 && src.type() != typed_) throw std::runtime_error("minicv: output type mismatch");
+            static_cast<Mat &>(*m_) = src;
+        }
+    }
+
+private:
+    int typed_ = -1;
+};
+typedef const _InputArray &InputArray;
+typedef const _OutputArray &OutputArray;
+typedef const _OutputArray &InputOutputArray;
+inline const _OutputArray &noArray()
+{
+    static _OutputArray none;
+    return none;
+}
+inline void Mat::copyTo(const _OutputArray &dst) const { dst.assign(clone()); }
+
+class Algorithm {
+public:
+    virtual ~Algorithm() {}
+};
+template <typename T> using Ptr = std::shared_ptr<T>;
+template <typename T, typename... A> Ptr<T> makePtr(A &&...a) { return std::make_shared<T>(std::forward<A>(a)...); }
+
+/* the three primitives of the path: forwarded to the oracle's cv2-pinned restatements (see the header) */
+inline float fastAtan2(float y, float x) { return lsd_orc_fast_atan2(y, x); }
+inline void GaussianBlur(InputArray src_, OutputArray dst, Size ksize, double sigma)
+{
+    const Mat src = src_.getMat();
+    if (src.type() != CV_64FC1 || ksize.width != 7 || ksize.height != 7 || std::fabs(sigma - 0.6 / 0.8) > 1e-12)
+        throw std::runtime_error("minicv: GaussianBlur is only provided for the call lsd.cpp makes (CV_64F, 7 x 7, sigma 0.6 / 0.8)");
+    Mat out(src.rows, src.cols, CV_64FC1);
+    lsd_orc_gaussian7(src.ptr<double>(), src.cols, src.rows, out.ptr<double>());
+    dst.assign(out);
+}
+inline void resize(InputArray src_, OutputArray dst, Size dsize, double fx, double fy)
+{
+    const Mat src = src_.getMat();
+    if (src.type() != CV_64FC1 || dsize.area() != 0 || fx != fy) throw std::runtime_error("minicv: resize is only provided for the call lsd.cpp makes");
+    /* cv::resize: dsize = Size(saturate_cast<int>(cols * fx), saturate_cast<int>(rows * fy)), saturate_cast<int>(double) = lrint */
+    const int dw = (int)std::lrint(src.cols * fx), dh = (int)std::lrint(src.rows * fy);
+    Mat out(dh, dw, CV_64FC1);
+    int ow = 0, oh = 0;
+    lsd_orc_resize(src.ptr<double>(), src.cols, src.rows, fx, out.ptr<double>(), &ow, &oh);
+    if (ow != dw || oh != dh) throw std::runtime_error("minicv: resize size mismatch");
+    dst.assign(out);
+}
+
+/* drawing helpers referenced by LineSegmentDetectorImpl::drawSegments / compareSegments, which the path never calls */
+[[noreturn]] inline void minicv_unreachable(const char *what)
+{
+    fprintf(stderr, "minicv: %s is not provided (the line-detection path does not call it)\n", what);
+    abort();
+}
+inline void cvtColor(InputArray, OutputArray, int) { minicv_unreachable("cvtColor"); }
+inline void merge(const std::vector<Mat> &, OutputArray) { minicv_unreachable("merge"); }
+template <typename P> inline void line(InputOutputArray, P, P, const Scalar &, int) { minicv_unreachable("line"); }
+inline void bitwise_xor(InputArray, InputArray, OutputArray) { minicv_unreachable("bitwise_xor"); }
+inline int countNonZero(InputArray) { minicv_unreachable("countNonZero"); }
+
+}  // namespace cv
+#endif /* ORC_MINICV_HPP */

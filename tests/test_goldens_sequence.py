@@ -39,8 +39,11 @@ def test_oracle_reproduces_the_fixture_b_goldens(oracle, fixture_b):
     for i in range(0, len(exp["frames"]), 3):  # every third frame keeps the CPU suite short; the GPU test walks all of them
         img, boxes = fixture_b["frames"][i]
         e = exp["frames"][i]
-        lines = oracle.lsd_detect(img, 15.0)["lines"]
+        res = oracle.lsd_detect(img, 15.0)
+        lines = res["lines"]
         assert len(lines) == e["n_lines"] and _checksum(lines) == e["lines_checksum"]
+        # the raw segments of the reference's own lsd.cpp, recorded when the golden was made (oracle/_ref): pins the oracle to the reference
+        assert len(res["raw_lines"]) == e["n_raw_ref"] and _checksum(res["raw_lines"]) == e["raw_checksum_ref"]
         for mode, kw in MODES.items():
             if mode != "default" and i % 6:
                 continue
@@ -59,8 +62,10 @@ def test_oracle_reproduces_the_synthetic_goldens(oracle):
         assert int(imgs.astype(np.uint64).sum()) == case["image_checksum"]  # the generator itself is part of the golden
         for f in (0, 3):
             e = case["frames"][f]
-            lines = oracle.lsd_detect(imgs[f], 15.0)["lines"]
+            res = oracle.lsd_detect(imgs[f], 15.0)
+            lines = res["lines"]
             assert len(lines) == e["n_lines"] and _checksum(lines) == e["lines_checksum"]
+            assert len(res["raw_lines"]) == e["n_raw_ref"] and _checksum(res["raw_lines"]) == e["raw_checksum_ref"]
             r = oracle.detect_cuboid(imgs[f], K, Ts[f], boxes[f], lines.astype(np.float64), oracle.default_params(nominal_skew_ratio=2.0))
             em = e["modes"]["default"]
             assert (r["n_candidates"], r["n_valid"]) == (em["n_candidates"], em["n_valid"])

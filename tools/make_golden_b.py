@@ -4,7 +4,9 @@
 
     python tools/make_golden_b.py
 
-Per frame and mode: LSD segment count and a checksum of the segments, candidates, valid proposals, and per box the best cuboid
+Needs oracle/_ref/liblsd_ref.so (the reference's lsd.cpp compiled where /root/reference exists): the raw LSD segments recorded here
+(`n_raw_ref`, `raw_checksum_ref`) are the REFERENCE's output, so the committed file pins the oracle to the reference wherever the tests
+run.  Per frame and mode: LSD segment count and a checksum of the segments, candidates, valid proposals, and per box the best cuboid
 (proposal index, normalised error, position, yaw, scale).  Modes: default, and 5 x 5 camera roll / pitch sampling
 (whether_sample_cam_roll_pitch).  object_slam's own settings: length threshold 15, nominal_skew_ratio 2 (main_obj.cpp:359-366)."""
 import json
@@ -33,8 +35,15 @@ def best(c):
 
 
 def frame_record(img, K, T, boxes, modes):
-    lines = O.lsd_detect(img, 15.0)["lines"]
-    rec = dict(n_lines=int(len(lines)), lines_checksum=seg_checksum(lines), modes={})
+    res = O.lsd_detect(img, 15.0)
+    lines = res["lines"]
+    # the raw segments come from the REFERENCE's own lsd.cpp (oracle/_ref/liblsd_ref.so, built from /root/reference by oracle/Makefile);
+    # the oracle restatement has to agree with it bit for bit before anything is written
+    ref_raw = O.ref_lsd_detect(img)
+    if not np.array_equal(ref_raw, res["raw_lines"]):
+        raise SystemExit("oracle LSD differs from the reference's lsd.cpp on this frame: fix the oracle first")
+    rec = dict(n_lines=int(len(lines)), lines_checksum=seg_checksum(lines), n_raw_ref=int(len(ref_raw)), raw_checksum_ref=seg_checksum(ref_raw),
+               modes={})
     for name, kw in modes:
         r = O.detect_cuboid(img, K, T, boxes, lines.astype(np.float64), O.default_params(nominal_skew_ratio=2.0, **kw))
         rec["modes"][name] = dict(n_candidates=int(r["n_candidates"]), n_valid=int(r["n_valid"]),
@@ -46,7 +55,7 @@ def main():
     import conftest
     fb = conftest.fixture_b.__wrapped__()
     modes = [("default", {}), ("sample_roll_pitch", dict(whether_sample_cam_roll_pitch=1))]
-    out = dict(source="oracle (oracle/*.cpp) on tests/golden/fixture_b; tools/make_golden_b.py", frames=[])
+    out = dict(source="oracle (oracle/*.cpp) on tests/golden/fixture_b, raw LSD segments from the reference lsd.cpp (oracle/_ref); tools/make_golden_b.py", frames=[])
     for i, (img, boxes) in enumerate(fb["frames"]):
         out["frames"].append(frame_record(img, fb["K"], fb["T"], boxes, modes))
         print("fixture B frame", i, out["frames"][-1]["n_lines"], flush=True)
