@@ -485,7 +485,7 @@ def run_ours(args, rank, world, local_rank):
     n_obj_loc = max(int(stats["n_objects"]), 1)
     # host threads, one context each, call the synchronous ABI entry point: the copies of one batch overlap the kernels of the others
     # (single GPU only: two threads issuing NCCL calls on two communicators in an unordered way could deadlock across ranks)
-    e2e_ctxs = ctxs[:12] if (len(ctxs) >= 2 and world == 1) else ctxs[:1]
+    e2e_ctxs = ctxs if (len(ctxs) >= 2 and world == 1) else ctxs[:1]
     e2e_out = [(np.zeros((n_obj_loc, topk), cs.CUBOID_DTYPE), np.zeros(n_obj_loc, np.int32)) for _ in e2e_ctxs]
     lp_main = main_mode.lp
 
@@ -501,7 +501,8 @@ def run_ours(args, rank, world, local_rank):
             for _ in range(2):
                 step_e2e(k)
         barrier()
-        e2e_steps = max(4, min(args.steps, 50))
+        # enough rounds per thread that filling and draining the pipeline (a batch alone takes ~55 ms) does not dominate
+        e2e_steps = max(args.steps, 8 * len(e2e_ctxs))
         e2e_steps -= e2e_steps % len(e2e_ctxs)
 
         def e2e_worker(k):
@@ -521,7 +522,7 @@ def run_ours(args, rank, world, local_rank):
         # N > 1: one host thread keeps the batches in flight with the split calls (cs_batch_upload_online from pinned host frames,
         # cs_batch_run_async, cs_allgather_topk, cs_batch_fetch) as a rolling pipeline, so that every rank issues its collectives in the
         # same order: step s is issued on context s mod K, then the oldest outstanding step is fetched
-        e2e_ctxs = ctxs[:12]
+        e2e_ctxs = ctxs
         K_ = len(e2e_ctxs)
         e2e_mode = "one host thread, %d contexts as a rolling pipeline: cs_batch_upload_online + cs_batch_run_async + cs_allgather_topk + cs_batch_fetch" % K_
 
@@ -541,7 +542,7 @@ def run_ours(args, rank, world, local_rank):
 
         e2e_run(K_)
         barrier()
-        e2e_steps = max(K_, min(args.steps, 48))
+        e2e_steps = max(args.steps, 8 * K_)
         t0 = time.perf_counter()
         e2e_run(e2e_steps)
         barrier()

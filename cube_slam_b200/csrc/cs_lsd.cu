@@ -59,12 +59,6 @@
 
 #define LSD_CAND_CAP 2048    /* candidate rectangles per frame handed from the seed loop to k_lsd_validate */
 #define LSD_SEQ_SCAP 2048    /* region entries k_lsd_grow_seq keeps in shared memory (the rest spill to HBM; small, so that many frames share an SM) */
-#define LSD_FREE 0xffffffffu
-#define LSD_ST_NEW 0u
-#define LSD_ST_GROWING 1u
-#define LSD_ST_CLEAN 2u
-#define LSD_ST_MASK 7u
-#define LSD_ST_INVALID 8u
 #define LSD_HDR 8            /* ints of a candidate record header in the arena: n1, n2, has_line, x1 y1 x2 y2 (float bits), pad */
 
 namespace {
@@ -285,7 +279,7 @@ __global__ void __launch_bounds__(256) k_lsd_grad(const double *__restrict__ sca
         if (!inside) return;
         modgrad[p] = norm;
         angf[p] = deg;
-        uint4 r = make_uint4(__float_as_uint(deg), 0u, 0u, LSD_FREE);
+        uint4 r = make_uint4(__float_as_uint(deg), 0u, 0u, 0u);
         if (deg >= 0.f) {
             const double ang = (double)deg * LSD_DEG2RAD;
             const double af = (double)(float)ang;
@@ -299,7 +293,7 @@ __global__ void __launch_bounds__(256) k_lsd_grad(const double *__restrict__ sca
 /* ---------------------------------------------------------------------------------------- the seed loop */
 /* cycle counters of the seed loop's phases (diagnostics, cs_debug_lsd_prof): grow, region2rect, refine, rectangle counts, binomial tails,
  * candidates, list scan */
-__device__ unsigned long long g_lsd_prof[8];
+__device__ unsigned long long g_lsd_prof[16];
 #define LSD_PROF_T0() const long long prof_t0__ = clock64()
 #define LSD_PROF_ADD(slot)                                                                         \
     do {                                                                                           \
@@ -308,18 +302,15 @@ __device__ unsigned long long g_lsd_prof[8];
 
 struct LsdFrame {
     int W, H;
-    uint4 *pix;            /* {deg, cos, sin, claim} */
+    uint4 *pix;            /* {deg, cos, sin, 0}: one 16-byte record per neighbour test */
     const float *angf;     /* deg plane for the rectangle scans */
     const double *modgrad;
     double LOG_NT;
-    /* ordered speculation only */
-    uint32_t *st;          /* per list position: state | invalid flag | record offset << 4 */
-    int32_t *arena;        /* records of finished candidates */
-    int arena_cap;
-    /* one warp per frame (k_lsd_grow_seq): the `used` map as a bit per pixel (HBM, read and written through L2 only, so that it costs
-     * no shared memory: the seed loop issues one instruction every ~6 cycles, and the more frames share an SM the better); the claim
-     * words are not touched */
+    /* the `used` map as a bit per pixel (HBM, read and written through L2 only, so that it costs no shared memory: the seed loop issues
+     * one instruction every ~6 cycles, and the more frames share an SM the better) */
     uint32_t *ubits;
+    struct LsdSpan *span; /* k_lsd_validate: room for five row-span records per warp (shared memory) */
+    double *stage;        /* k_lsd_grow_seq: 96 doubles of shared memory per warp (ordered sums) */
     __device__ __forceinline__ bool used_bit(int addr) const { return (__ldcg(ubits + (addr >> 5)) >> (addr & 31)) & 1u; }
     const double *lgam; /* log_gamma of small integers (cs_nfa.cuh) */
     unsigned long long wmagic; /* ceil(2^40 / W): row of a pixel address without an integer division (exact for addresses < 2^20 .. 2^30 / W) */
@@ -342,23 +333,7 @@ struct LsdReg {
     }
 };
 
-/* how a warp sees claim words */
-struct LsdView {
-    int rank;       /* the candidate's list position; -1 = sequential mode (0 = used, FREE = unused) */
-    int frontier;
-};
-enum { LSD_K_FREE = 0, LSD_K_USED = 1, LSD_K_MINE = 2, LSD_K_MINE_FORMER = 3, LSD_K_HIGHER = 4, LSD_K_LOWER = 5 };
-
-__device__ __forceinline__ int lsd_decode(uint32_t c, const LsdView &V)
-{
-    if (c == LSD_FREE) return LSD_K_FREE;
-    const int j = (int)(c >> 1);
-    if (j < V.frontier) return (c & 1u) ? LSD_K_FREE : LSD_K_USED;
-    if (j == V.rank) return (c & 1u) ? LSD_K_MINE_FORMER : LSD_K_MINE;
-    return j > V.rank ? LSD_K_HIGHER : LSD_K_LOWER;
-}
-__device__ __forceinline__ uint32_t *lsd_claim_ptr(const LsdFrame &F, int addr) { return reinterpret_cast<uint32_t *>(F.pix + addr) + 3; }
-__device__ __forceinline__ uint32_t lsd_ld_claim(const LsdFrame &F, int addr) { return __ldcg(lsd_claim_ptr(F, addr)); }
+__device__ __forceinline__ void lsd_prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 
 struct LsdRect {
     double x1, y1, x2, y2, width, x, y, theta, dx, dy, prec, p;
@@ -446,164 +421,167 @@ __device__ __noinline__ double lsd_nfa(int n, int k, double p, double LOG_NT)
     return -log10(bin_tail) - LOG_NT;
 }
 
-/* Claim one pixel for the candidate (compare-and-swap; a higher-rank speculative owner is overridden and flagged).
- * `c` is the claim word last seen.  Returns false when a final or lower-rank owner holds it. */
-__device__ __forceinline__ bool lsd_claim(const LsdFrame &F, const LsdView &V, int addr, uint32_t c)
-{
-    uint32_t *cw = lsd_claim_ptr(F, addr);
-    if (V.rank < 0) { /* sequential mode */
-        atomicOr(F.ubits + (addr >> 5), 1u << (addr & 31));
-        return true;
-    }
-    const uint32_t me0 = (uint32_t)V.rank << 1;
-    for (;;) {
-        const int kind = lsd_decode(c, V);
-        if (kind != LSD_K_FREE && kind != LSD_K_HIGHER && kind != LSD_K_MINE_FORMER) return kind == LSD_K_MINE;
-        const uint32_t old = atomicCAS(cw, c, me0);
-        if (old == c) {
-            if (kind == LSD_K_HIGHER) atomicOr(F.st + (c >> 1), LSD_ST_INVALID);
-            return true;
-        }
-        c = old;
-    }
-}
-/* member -> dropped (refine / reduce_region_radius clear `used`): false when a lower rank took the pixel meanwhile */
-__device__ __forceinline__ bool lsd_demote(const LsdFrame &F, const LsdView &V, int addr)
-{
-    uint32_t *cw = lsd_claim_ptr(F, addr);
-    if (V.rank < 0) {
-        atomicAnd(F.ubits + (addr >> 5), ~(1u << (addr & 31)));
-        return true;
-    }
-    const uint32_t me0 = (uint32_t)V.rank << 1;
-    return atomicCAS(cw, me0, me0 | 1u) == me0;
-}
-/* lsd.cpp:637-688.  Neighbour tests of three region points per round on lanes 0..26 (one 16-byte record each); additions stay in the
- * reference's order.  The region is R[base .. base + reg_size).  Returns 0 ok, 1 refused (a lower-rank speculative owner holds a pixel
- * this region wants, or a claim was lost), 2 staging overflow. */
-__device__ int lsd_region_grow(const LsdFrame &F, const LsdView &V, const LsdReg &R, int base, int s_addr, int &reg_size, double &reg_angle, double prec)
+/* lsd.cpp:637-688, one warp.  Three region points per round, their 3 x 3 neighbourhoods on lanes 0..26 in the reference's (point, yy, xx)
+ * order, so "the first lane" is "the next pixel the reference would test".
+ *
+ * The reference updates the region angle after EVERY added pixel and tests the next neighbour against the new angle: a chain of
+ * fastAtan2 -> compare -> add per pixel.  Most of those tests cannot come out differently, though.  Let S be the running sum of unit
+ * vectors, L = |S|.  A pixel that passes the test lies within A = prec + D of the (computed) region direction, so adding it turns S by at
+ * most sin(A + e) / L <= (A + e) / L and does not shorten it (e <= 1e-3 rad: error of the fastAtan2 polynomial, measured 1.7e-4).  With
+ * at most m additions in this round, every angle the round will test against is within
+ *     D = m (prec + 0.2 + e) / L + 2 e + float slack
+ * of the angle at the start of the round (D <= 0.2 required).  A neighbour whose difference from the round-start angle is below prec - D
+ * is accepted whenever its turn comes, one above prec + D is rejected whenever: neither needs the angle at its turn.  Only the pixels in
+ * between are tested the reference's way, against fastAtan2 of the sums as they stand at their turn (the sums are always added in the
+ * reference's order, in float, so they are the reference's bits).  prec + D stays below pi / 2, where the reference's wrapped difference
+ * (lsd.cpp:1138-1154) equals the circular distance or exceeds pi / 2, so the argument holds across the 0 / 2 pi seam. */
+__device__ void lsd_region_grow(const LsdFrame &F, const LsdReg &R, int base, int s_addr, int &reg_size, double &reg_angle, double prec)
 {
     const unsigned FULL = 0xffffffffu;
     const int lane = threadIdx.x & 31;
-    {
-        int ok = 1;
-        if (lane == 0) ok = lsd_claim(F, V, s_addr, V.rank < 0 ? LSD_FREE : lsd_ld_claim(F, s_addr)) ? 1 : 0;
-        if (!__shfl_sync(FULL, ok, 0)) return 1;
-    }
-    reg_size = 1;
-    reg_angle = (double)F.angf[s_addr] * LSD_DEG2RAD;
+    float reg_deg = F.angf[s_addr];
+    reg_angle = (double)reg_deg * LSD_DEG2RAD;
     float sumdx = (float)cos(reg_angle);
     float sumdy = (float)sin(reg_angle);
-    if (lane == 0) R.put(base, s_addr);
+    if (lane == 0) {
+        atomicOr(F.ubits + (s_addr >> 5), 1u << (s_addr & 31));
+        R.put(base, s_addr);
+    }
+    reg_size = 1;
     __syncwarp();
     const int grp = lane / 9, kk = lane - grp * 9;
     const int ky = kk / 3 - 1, kx = kk - (kk / 3) * 3 - 1; /* (yy, xx) in the reference's loop order */
+    const float precf = (float)prec;
+    const unsigned lt_mask = (1u << lane) - 1u;
     for (int i = 0; i < reg_size;) {
         const int navail = min(3, reg_size - i);
-        if (base + reg_size + 27 > R.cap) return 2;
-        bool cand = false, low = false, mine = false;
+        bool cand = false;
         int c_addr = -1;
         float deg = -1.f, csx = 0.f, csy = 0.f;
-        uint32_t cseen = LSD_FREE;
         if (grp < navail) {
             const int pa = R.get(base + i + grp);
             const int py = F.row_of(pa), px = pa - py * F.W;
             const int yy = py + ky, xx = px + kx;
             if (yy >= 0 && yy < F.H && xx >= 0 && xx < F.W) {
                 c_addr = yy * F.W + xx;
-                const uint4 r = V.rank < 0 ? __ldg(F.pix + c_addr) : __ldcg(F.pix + c_addr); /* one warp per frame: the record is read-only */
+                const uint4 r = __ldg(F.pix + c_addr); /* {deg, cos, sin, -}: read-only */
+                const uint32_t uw = __ldcg(F.ubits + (c_addr >> 5)); /* issued together with the record: one round trip per round, not two */
                 deg = __uint_as_float(r.x);
-                if (deg >= 0.f) {
-                    cseen = r.w;
-                    int kind;
-                    if (V.rank < 0)
-                        kind = F.used_bit(c_addr) ? LSD_K_USED : LSD_K_FREE;
-                    else
-                        kind = lsd_decode(cseen, V);
-                    cand = (kind == LSD_K_FREE || kind == LSD_K_HIGHER || kind == LSD_K_MINE_FORMER || kind == LSD_K_LOWER);
-                    low = (kind == LSD_K_LOWER);
+                if (deg >= 0.f && !((uw >> (c_addr & 31)) & 1u)) {
+                    cand = true;
                     csx = __uint_as_float(r.y);
                     csy = __uint_as_float(r.z);
                 }
             }
         }
-        bool refused = false;
-        for (int g = 0; g < navail; g++) {
-            unsigned pending = __ballot_sync(FULL, cand && grp == g);
-            while (pending) {
-                const unsigned ok = __ballot_sync(FULL, cand && ((pending >> lane) & 1u) && lsd_aligned_deg(deg, reg_angle, prec));
-                if (!ok) break;
-                const int fl = __ffs(ok) - 1;
-                if (__shfl_sync(FULL, (int)low, fl)) {
-                    refused = true; /* the pixel belongs, for now, to a lower-rank candidate that is not final */
-                    break;
+        unsigned maybe = __ballot_sync(FULL, cand);
+        if (maybe) {
+            /* the float difference from the round-start angle (error < 1e-5 rad) and the drift bound D */
+            float nf = fabsf(reg_deg * 0.017453292f - deg * 0.017453292f);
+            if (nf > 4.712389f) nf = fabsf(nf - 6.2831855f);
+            const float inv_l = rsqrtf(sumdx * sumdx + sumdy * sumdy) * 1.001f;
+            const float per_add = (precf + 0.201f) * inv_l;
+            unsigned sure = 0u;
+            float D = (float)__popc(maybe) * per_add + 0.0022f;
+            if (D <= 0.2f && precf + D < 1.5f) {
+                const unsigned m1 = __ballot_sync(FULL, cand && nf < precf + D); /* everything else is rejected whatever the angle */
+                D = (float)__popc(m1) * per_add + 0.0022f;                          /* at most popc(m1) additions this round */
+                sure = __ballot_sync(FULL, cand && nf < precf - D);
+                maybe = __ballot_sync(FULL, cand && nf < precf + D);
+            }
+            unsigned accepted = 0u;
+            bool stale = false; /* sums changed since reg_deg was computed */
+            while (maybe) {
+                const int fl = __ffs(maybe) - 1;
+                maybe &= ~(1u << fl);
+                if (!((sure >> fl) & 1u)) {
+                    /* the reference's own test, at this pixel's turn */
+                    if (stale) {
+                        reg_deg = fast_atan2(sumdy, sumdx);
+                        stale = false;
+                    }
+                    const bool ok = lsd_aligned_deg(deg, (double)reg_deg * LSD_DEG2RAD, prec);
+                    if (!((__ballot_sync(FULL, ok) >> fl) & 1u)) continue;
                 }
                 const int addrf = __shfl_sync(FULL, c_addr, fl);
-                const float cx = __shfl_sync(FULL, csx, fl), cy = __shfl_sync(FULL, csy, fl);
-                if (lane == 0) R.put(base + reg_size, addrf);
-                if (lane == fl) mine = true;
-                ++reg_size;
                 /* cos(float(angle)), sin(float(angle)): precomputed per pixel by k_lsd_grad (pinned to the correctly rounded float) */
-                sumdx += cx;
-                sumdy += cy;
-                reg_angle = (double)fast_atan2(sumdy, sumdx) * LSD_DEG2RAD;
-                pending &= ~((2u << fl) - 1u);
-                if (c_addr == addrf) cand = false; /* the same pixel seen from a later point of this round */
+                sumdx += __shfl_sync(FULL, csx, fl);
+                sumdy += __shfl_sync(FULL, csy, fl);
+                stale = true;
+                accepted |= 1u << fl;
+                maybe &= ~__ballot_sync(FULL, c_addr == addrf); /* the same pixel seen from a later point of this round */
             }
-            if (refused) break;
+            if (accepted) {
+                if ((accepted >> lane) & 1u) {
+                    R.put(base + reg_size + __popc(accepted & lt_mask), c_addr);
+                    atomicOr(F.ubits + (c_addr >> 5), 1u << (c_addr & 31));
+                    /* this pixel is a region point now: its 3 x 3 neighbourhood will be gathered a few rounds from here.  Ask L2 for the three
+                     * 48-byte runs of records (a DRAM miss is ~3x an L2 hit, and the gather is on the warp's critical path). */
+                    const uint4 *q = F.pix + c_addr - 1;
+                    if (c_addr >= F.W + 1) lsd_prefetch_l2(q - F.W);
+                    lsd_prefetch_l2(q);
+                    if (c_addr + F.W + 1 < F.W * F.H) lsd_prefetch_l2(q + F.W);
+                }
+                reg_size += __popc(accepted);
+                if (stale) reg_deg = fast_atan2(sumdy, sumdx);
+                __syncwarp();
+            }
         }
-        bool lost = false;
-        if (mine) lost = !lsd_claim(F, V, c_addr, cseen);
-        __syncwarp();
-        if (refused || __any_sync(FULL, lost)) return 1;
         i += navail;
     }
-    return 0;
+    reg_angle = (double)reg_deg * LSD_DEG2RAD;
 }
 
-/* ordered accumulation helper: lanes fetch 32 region points at once, every lane then replays them in order */
-#define LSD_FOR_REGION_ORDERED(F, R, base, reg_size, ...)                           \
-    for (int i0__ = 0; i0__ < (reg_size); i0__ += 32) {                             \
-        const int n__ = min(32, (reg_size)-i0__);                                   \
-        int my_addr__ = 0;                                                          \
-        double my_w__ = 0;                                                          \
-        float my_a__ = 0;                                                           \
-        if (lane < n__) {                                                           \
-            my_addr__ = (R).get((base) + i0__ + lane);                              \
-            my_w__ = (F).modgrad[my_addr__];                                        \
-            my_a__ = (F).angf[my_addr__];                                           \
-        }                                                                           \
-        for (int j__ = 0; j__ < n__; j__++) {                                       \
-            const int addr = __shfl_sync(0xffffffffu, my_addr__, j__);              \
-            const double weight = __shfl_sync(0xffffffffu, my_w__, j__);            \
-            const double pangle = (double)__shfl_sync(0xffffffffu, my_a__, j__) * LSD_DEG2RAD; \
-            const int ry = (F).row_of(addr), rx = addr - ry * (F).W;                \
-            (void)weight;                                                           \
-            (void)pangle;                                                           \
-            __VA_ARGS__                                                             \
-        }                                                                           \
-    }
-
+/* Sums over the region in the reference's order (the order decides the last bits of a double sum): 32 region points at a time, every lane
+ * computes the addend(s) of ITS point -- the products round the same wherever they are computed -- and stages them in shared memory
+ * (F.stage, 96 doubles per warp); then the additions run as one chain over the staged values, read as broadcasts. */
 /* lsd.cpp:690-784 */
 __device__ void lsd_region2rect(const LsdFrame &F, const LsdReg &R, int base, int reg_size, double reg_angle, double prec, double p, LsdRect &rec)
 {
     const int lane = threadIdx.x & 31;
+    double *st = F.stage;
     double x = 0, y = 0, sum = 0;
-    LSD_FOR_REGION_ORDERED(F, R, base, reg_size, {
-        x += (double)rx * weight;
-        y += (double)ry * weight;
-        sum += weight;
-    })
+    for (int i0 = 0; i0 < reg_size; i0 += 32) {
+        const int n = min(32, reg_size - i0);
+        __syncwarp();
+        if (lane < n) {
+            const int addr = R.get(base + i0 + lane);
+            const double weight = F.modgrad[addr];
+            const int ry = F.row_of(addr), rx = addr - ry * F.W;
+            st[lane] = (double)rx * weight;
+            st[32 + lane] = (double)ry * weight;
+            st[64 + lane] = weight;
+        }
+        __syncwarp();
+        for (int j = 0; j < n; j++) {
+            x += st[j];
+            y += st[32 + j];
+            sum += st[64 + j];
+        }
+    }
     x /= sum;
     y /= sum;
     /* get_theta */
     double Ixx = 0.0, Iyy = 0.0, Ixy = 0.0;
-    LSD_FOR_REGION_ORDERED(F, R, base, reg_size, {
-        const double ddx = (double)rx - x, ddy = (double)ry - y;
-        Ixx += ddy * ddy * weight;
-        Iyy += ddx * ddx * weight;
-        Ixy -= ddx * ddy * weight;
-    })
+    for (int i0 = 0; i0 < reg_size; i0 += 32) {
+        const int n = min(32, reg_size - i0);
+        __syncwarp();
+        if (lane < n) {
+            const int addr = R.get(base + i0 + lane);
+            const double weight = F.modgrad[addr];
+            const int ry = F.row_of(addr), rx = addr - ry * F.W;
+            const double ddx = (double)rx - x, ddy = (double)ry - y;
+            st[lane] = ddy * ddy * weight;
+            st[32 + lane] = ddx * ddx * weight;
+            st[64 + lane] = ddx * ddy * weight;
+        }
+        __syncwarp();
+        for (int j = 0; j < n; j++) {
+            Ixx += st[j];
+            Iyy += st[32 + j];
+            Ixy -= st[64 + j];
+        }
+    }
     const double lambda = 0.5 * (Ixx + Iyy - sqrt((Ixx - Iyy) * (Ixx - Iyy) + 4.0 * Ixy * Ixy));
     double theta = (fabs(Ixx) > fabs(Iyy)) ? (double)fast_atan2((float)(lambda - Ixx), (float)Ixy) : (double)fast_atan2((float)Ixy, (float)(lambda - Iyy));
     theta *= LSD_DEG2RAD;
@@ -647,8 +625,8 @@ __device__ void lsd_region2rect(const LsdFrame &F, const LsdReg &R, int base, in
 __device__ __noinline__ void lsd_region2rect_cold(const LsdFrame &F, const LsdReg &R, int base, int reg_size, double reg_angle, double prec, double p, LsdRect &rec);
 
 /* lsd.cpp:834-871 (lane 0 replays the reference's in-place compaction; it fixes the order later sums run in).
- * Returns 0 ok, 1 claim lost, 3 region rejected. */
-__device__ __noinline__ int lsd_reduce_region_radius(const LsdFrame &F, const LsdView &V, const LsdReg &R, int base, int &reg_size, double reg_angle, double prec, double p,
+ * Returns 0 ok, 3 region rejected. */
+__device__ __noinline__ int lsd_reduce_region_radius(const LsdFrame &F, const LsdReg &R, int base, int &reg_size, double reg_angle, double prec, double p,
                                         LsdRect &rec, double density, double density_th)
 {
     const int lane = threadIdx.x & 31;
@@ -658,12 +636,12 @@ __device__ __noinline__ int lsd_reduce_region_radius(const LsdFrame &F, const Ls
     double radSq = radSq1 > radSq2 ? radSq1 : radSq2;
     while (density < density_th) {
         radSq *= 0.75 * 0.75;
-        int rs = reg_size, lost = 0;
+        int rs = reg_size;
         if (lane == 0) {
             for (int i = 0; i < rs; ++i) {
                 const int addr = R.get(base + i);
                 if (lsd_dist_sq(xc, yc, (double)(addr - F.row_of(addr) * F.W), (double)F.row_of(addr)) > radSq) {
-                    if (!lsd_demote(F, V, addr)) lost = 1;
+                    atomicAnd(F.ubits + (addr >> 5), ~(1u << (addr & 31)));
                     const int last = R.get(base + rs - 1);
                     R.put(base + rs - 1, addr);
                     R.put(base + i, last);
@@ -673,9 +651,7 @@ __device__ __noinline__ int lsd_reduce_region_radius(const LsdFrame &F, const Ls
             }
         }
         reg_size = __shfl_sync(0xffffffffu, rs, 0);
-        lost = __shfl_sync(0xffffffffu, lost, 0);
         __syncwarp();
-        if (lost) return 1;
         if (reg_size < 2) return 3;
         lsd_region2rect_cold(F, R, base, reg_size, reg_angle, prec, p, rec);
         density = (double)reg_size / (lsd_dist(rec.x1, rec.y1, rec.x2, rec.y2) * rec.width);
@@ -685,10 +661,14 @@ __device__ __noinline__ int lsd_reduce_region_radius(const LsdFrame &F, const Ls
 
 /* lsd.cpp:977-1098 with the vendored slips kept: the (total, aligned) pixel counts of a rectangle.  The edge stepping of the
  * reference adds integer-valued steps (its slopes are int / int divisions) to integer starts, once per row INSIDE the image, so the
- * span of a row has a closed form and rows are scanned by separate lanes. */
-__device__ void lsd_rect_count(const LsdFrame &F, const LsdRect &rec, int &total_pts, int &alg_pts)
+ * span of a row has a closed form (LsdSpan) and rows are scanned by separate lanes. */
+struct LsdSpan {
+    int mx, ly, ry, y0, y1; /* start column, the rows where the left / right edge changes slope, first and last row inside the image */
+    int fl, sl, fr, sr;     /* the four integer steps */
+};
+
+__device__ void lsd_span_setup(const LsdFrame &F, const LsdRect &rec, LsdSpan &P)
 {
-    const int lane = threadIdx.x & 31;
     const double half_width = rec.width / 2.0;
     const double dyhw = rec.dy * half_width, dxhw = rec.dx * half_width;
     int ox[4], oy[4];
@@ -746,33 +726,51 @@ __device__ void lsd_rect_count(const LsdFrame &F, const LsdRect &rec, int &total
                 itail = i;
         }
     const int mx = ox[imin], my = oy[imin], lx = ox[ileft], ly = oy[ileft], rx = ox[iright], ry = oy[iright], tx = ox[itail];
-    const long long flstep = (my != ly) ? (long long)((mx - lx) / (my - ly)) : 0;
-    const long long slstep = (ly != tx) ? (long long)((lx - tx) / (ly - tx)) : 0;
-    const long long frstep = (my != ry) ? (long long)((mx - rx) / (my - ry)) : 0;
-    const long long srstep = (ry != tx) ? (long long)((rx - tx) / (ry - tx)) : 0;
-    const int max_iter = oy[imax];
+    P.mx = mx;
+    P.ly = ly;
+    P.ry = ry;
+    P.fl = (my != ly) ? (mx - lx) / (my - ly) : 0;
+    P.sl = (ly != tx) ? (lx - tx) / (ly - tx) : 0;
+    P.fr = (my != ry) ? (mx - rx) / (my - ry) : 0;
+    P.sr = (ry != tx) ? (rx - tx) / (ry - tx) : 0;
     /* rows outside the image skip the edge stepping too (as the reference): only rows y0..y1 count */
-    const int y0 = max(my, 0), y1 = min(max_iter, F.H - 1);
+    P.y0 = max(my, 0);
+    P.y1 = min(oy[imax], F.H - 1);
+}
+
+/* the columns [lo, hi] of row y (y0 <= y <= y1); empty when hi < lo */
+__device__ __forceinline__ void lsd_span_row(const LsdSpan &P, int y, int W, int &lo, int &hi)
+{
+    /* steps added before row y: one per earlier inside row y' in [y0, y); row y' adds the second slope iff y' >= ly (ry) */
+    const long long n_l2 = (long long)max(0, y - max(P.ly, P.y0)), n_l1 = (long long)(y - P.y0) - n_l2;
+    const long long n_r2 = (long long)max(0, y - max(P.ry, P.y0)), n_r1 = (long long)(y - P.y0) - n_r2;
+    const long long left_x = (long long)P.mx + n_l1 * (long long)P.fl + n_l2 * (long long)P.sl;
+    const long long right_x = (long long)P.mx + n_r1 * (long long)P.fr + n_r2 * (long long)P.sr;
+    lo = (int)(left_x > 0 ? left_x : 0);
+    hi = (int)(right_x < (long long)(W - 1) ? right_x : (long long)(W - 1));
+}
+
+__device__ void lsd_rect_count(const LsdFrame &F, const LsdRect &rec, int &total_pts, int &alg_pts)
+{
+    const int lane = threadIdx.x & 31;
+    LsdSpan P;
+    lsd_span_setup(F, rec, P);
     int tot = 0, alg = 0;
     /* lanes over rows AND over the pixels of a row: G lanes share a row, G the largest power of two with rows * G <= 32 (a nearly horizontal
      * segment has a handful of long rows, a nearly vertical one many short rows) */
-    const int n_rows = y1 - y0 + 1;
+    const int n_rows = P.y1 - P.y0 + 1;
     int G = 1;
     while (G < 32 && n_rows * G * 2 <= 32) G <<= 1;
     const int rows_per_step = 32 / G, sub = lane & (G - 1), rsel = lane / G;
-    for (int yb = y0; yb <= y1; yb += rows_per_step) {
+    for (int yb = P.y0; yb <= P.y1; yb += rows_per_step) {
         const int y = yb + rsel;
-        if (y > y1) continue;
-        /* steps added before row y: one per earlier inside row y' in [y0, y); row y' adds the second slope iff y' >= ly (ry) */
-        const long long n_l2 = (long long)max(0, y - max(ly, y0)), n_l1 = (long long)(y - y0) - n_l2;
-        const long long n_r2 = (long long)max(0, y - max(ry, y0)), n_r1 = (long long)(y - y0) - n_r2;
-        const long long left_x = (long long)mx + n_l1 * flstep + n_l2 * slstep;
-        const long long right_x = (long long)mx + n_r1 * frstep + n_r2 * srstep;
-        const long long lo = left_x > 0 ? left_x : 0, hi = right_x < (long long)(F.W - 1) ? right_x : (long long)(F.W - 1);
+        if (y > P.y1) continue;
+        int lo, hi;
+        lsd_span_row(P, y, F.W, lo, hi);
         if (hi >= lo) {
-            if (sub == 0) tot += (int)(hi - lo + 1);
+            if (sub == 0) tot += hi - lo + 1;
             const float *row = F.angf + (size_t)y * F.W;
-            for (int x = (int)lo + sub; x <= (int)hi; x += G) alg += lsd_aligned_deg(row[x], rec.theta, rec.prec) ? 1 : 0;
+            for (int x = lo + sub; x <= hi; x += G) alg += lsd_aligned_deg(row[x], rec.theta, rec.prec) ? 1 : 0;
         }
     }
 #pragma unroll
@@ -784,14 +782,107 @@ __device__ void lsd_rect_count(const LsdFrame &F, const LsdRect &rec, int &total
     alg_pts = alg;
 }
 
-/* the NFA of up to five rectangles of one rect_improve phase: counts one rectangle after the other (rows across lanes), then the
- * binomial tails, each by the whole warp (cs_nfa.cuh) */
-__device__ __noinline__ void lsd_rect_nfa5(const LsdFrame &F, const LsdRect *r, int n, double *v)
+/* The (total, aligned) counts of the up to five rectangles of one rect_improve phase in ONE scan of the angle map.  Within a phase the
+ * rectangles share the direction theta and differ either in the tolerance only (lsd.cpp:889-903, 957-972: p halved, same geometry) or in
+ * the geometry only (lsd.cpp:905-955: width reduced / one side moved, same tolerance): the level-line angle of a pixel is loaded and
+ * compared once, the per-rectangle part is a threshold or a column-range test.  The spans are built by lanes 0..n-1 in parallel and
+ * shared through F.span (shared memory, 5 LsdSpan per warp). */
+__device__ void lsd_rect_count_multi(const LsdFrame &F, const LsdRect *r, int n, bool same_geom, int *tot, int *alg)
+{
+    const unsigned FULL = 0xffffffffu;
+    const int lane = threadIdx.x & 31;
+    LsdSpan *sp = F.span;
+    const int n_geom = same_geom ? 1 : n;
+    __syncwarp();
+    if (lane < n_geom) lsd_span_setup(F, r[lane], sp[lane]);
+    __syncwarp();
+    int y_min = sp[0].y0, y_max = sp[0].y1;
+    for (int t = 1; t < n_geom; t++) {
+        y_min = min(y_min, sp[t].y0);
+        y_max = max(y_max, sp[t].y1);
+    }
+    const double theta = r[0].theta;
+    const float thetaf = (float)theta;
+    float pf[5];
+#pragma unroll
+    for (int t = 0; t < 5; t++) pf[t] = (float)r[t < n ? t : 0].prec;
+    int c_tot[5] = {0, 0, 0, 0, 0}, c_alg[5] = {0, 0, 0, 0, 0};
+    const int n_rows = y_max - y_min + 1;
+    int G = 1;
+    while (G < 32 && n_rows * G * 2 <= 32) G <<= 1;
+    const int rows_per_step = 32 / G, sub = lane & (G - 1), rsel = lane / G;
+    for (int yb = y_min; yb <= y_max; yb += rows_per_step) {
+        const int y = yb + rsel;
+        if (y > y_max) continue;
+        int lo[5], hi[5];
+        int x_lo = 0x7fffffff, x_hi = -1;
+#pragma unroll
+        for (int t = 0; t < 5; t++) {
+            lo[t] = 1;
+            hi[t] = 0;
+            if (t < n_geom && y >= sp[t].y0 && y <= sp[t].y1) {
+                lsd_span_row(sp[t], y, F.W, lo[t], hi[t]);
+                if (hi[t] >= lo[t]) {
+                    x_lo = min(x_lo, lo[t]);
+                    x_hi = max(x_hi, hi[t]);
+                    if (sub == 0) c_tot[t] += hi[t] - lo[t] + 1;
+                }
+            }
+        }
+        if (x_hi < 0) continue; /* no rectangle has pixels in this row */
+        const float *row = F.angf + (size_t)y * F.W;
+        for (int x = x_lo + sub; x <= x_hi; x += G) {
+            const float deg = row[x];
+            if (deg < 0.f) continue;
+            float nf = fabsf(thetaf - deg * 0.017453292f);
+            if (nf > 4.712389f) nf = fabsf(nf - 6.2831855f);
+            if (same_geom) {
+#pragma unroll
+                for (int t = 0; t < 5; t++)
+                    if (t < n) {
+                        bool a = nf < pf[t] - 2e-4f;
+                        if (!a && !(nf > pf[t] + 2e-4f)) a = lsd_aligned_deg(deg, theta, r[t].prec); /* borderline: the reference's doubles */
+                        c_alg[t] += a ? 1 : 0;
+                    }
+            } else {
+                bool a = nf < pf[0] - 2e-4f;
+                if (!a && !(nf > pf[0] + 2e-4f)) a = lsd_aligned_deg(deg, theta, r[0].prec);
+                if (a) {
+#pragma unroll
+                    for (int t = 0; t < 5; t++) c_alg[t] += (x >= lo[t] && x <= hi[t]) ? 1 : 0;
+                }
+            }
+        }
+    }
+    if (same_geom) {
+#pragma unroll
+        for (int t = 1; t < 5; t++) c_tot[t] = c_tot[0];
+    }
+#pragma unroll
+    for (int t = 0; t < 5; t++) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            c_tot[t] += __shfl_xor_sync(FULL, c_tot[t], o);
+            c_alg[t] += __shfl_xor_sync(FULL, c_alg[t], o);
+        }
+        if (t < n) {
+            tot[t] = c_tot[t];
+            alg[t] = c_alg[t];
+        }
+    }
+}
+
+/* the NFA of up to five rectangles of one rect_improve phase: the pixel counts in one scan (rows across lanes), then the binomial tails,
+ * each by the whole warp (cs_nfa.cuh) */
+__device__ __noinline__ void lsd_rect_nfa5(const LsdFrame &F, const LsdRect *r, int n, bool same_geom, double *v)
 {
     int tot[5], alg[5];
     {
         LSD_PROF_T0();
-        for (int t = 0; t < n; t++) lsd_rect_count(F, r[t], tot[t], alg[t]);
+        if (n == 1)
+            lsd_rect_count(F, r[0], tot[0], alg[0]);
+        else
+            lsd_rect_count_multi(F, r, n, same_geom, tot, alg);
         LSD_PROF_ADD(3);
     }
     {
@@ -807,7 +898,7 @@ __device__ double lsd_rect_improve(const LsdFrame &F, LsdRect &rec)
     const double delta = 0.5, delta_2 = delta / 2.0, LOG_EPS = 0;
     LsdRect cand[5];
     double v[5];
-    lsd_rect_nfa5(F, &rec, 1, v);
+    lsd_rect_nfa5(F, &rec, 1, true, v);
     double log_nfa = v[0];
     if (log_nfa > LOG_EPS) return log_nfa;
     LsdRect r = rec;
@@ -816,7 +907,7 @@ __device__ double lsd_rect_improve(const LsdFrame &F, LsdRect &rec)
         r.prec = r.p * LSD_PI;
         cand[n] = r;
     }
-    lsd_rect_nfa5(F, cand, 5, v);
+    lsd_rect_nfa5(F, cand, 5, true, v);
     for (int n = 0; n < 5; ++n)
         if (v[n] > log_nfa) {
             log_nfa = v[n];
@@ -849,7 +940,7 @@ __device__ double lsd_rect_improve(const LsdFrame &F, LsdRect &rec)
                 cand[m++] = r;
             }
         if (m) {
-            lsd_rect_nfa5(F, cand, m, v);
+            lsd_rect_nfa5(F, cand, m, phase == 3, v);
             for (int n = 0; n < m; ++n)
                 if (v[n] > log_nfa) {
                     rec = cand[n];
@@ -863,13 +954,13 @@ __device__ double lsd_rect_improve(const LsdFrame &F, LsdRect &rec)
 
 /* The first half of one seed (lsd.cpp:478-519): grow, rectangle, density refinement.  has_rect = 1 when a rectangle comes out that
  * rect_improve / the NFA test still have to judge -- which they can do later, in any order and in parallel: they read the level-line
- * angles only and never touch the `used` map.  Returns 0 done, 1 refused, 2 overflow. */
+ * angles only and never touch the `used` map. */
 __device__ __noinline__ void lsd_region2rect_cold(const LsdFrame &F, const LsdReg &R, int base, int reg_size, double reg_angle, double prec, double p, LsdRect &rec)
 {
     lsd_region2rect(F, R, base, reg_size, reg_angle, prec, p, rec);
 }
 
-__device__ int lsd_grow_candidate(const LsdFrame &F, const LsdView &V, const LsdReg &R, int s_addr, int min_reg_size, double prec, double p, int &n_all,
+__device__ void lsd_grow_candidate(const LsdFrame &F, const LsdReg &R, int s_addr, int min_reg_size, double prec, double p, int &n_all,
                                   int &has_rect, LsdRect &rec)
 {
     /* region_grow -> region2rect -> density test, at most twice: the second round is refine()'s re-grow with the tolerance estimated from
@@ -881,16 +972,17 @@ __device__ int lsd_grow_candidate(const LsdFrame &F, const LsdView &V, const Lsd
     has_rect = 0;
     n_all = 0;
     for (int pass = 0; pass < 2; pass++) {
-        int rc;
         {
             LSD_PROF_T0();
-            rc = lsd_region_grow(F, V, R, base, seed, reg_size, reg_angle, tau);
+            lsd_region_grow(F, R, base, seed, reg_size, reg_angle, tau);
             LSD_PROF_ADD(pass == 0 ? 0 : 2);
         }
-        if (pass == 0 && lane == 0) atomicAdd(&g_lsd_prof[5], 1ull);
+        if (pass == 0 && lane == 0) {
+            atomicAdd(&g_lsd_prof[5], 1ull);
+            atomicAdd(&g_lsd_prof[7], (unsigned long long)reg_size);
+        }
         n_all = base + reg_size;
-        if (rc) return rc;
-        if (reg_size < (pass == 0 ? min_reg_size : 2)) return 0;
+        if (reg_size < (pass == 0 ? min_reg_size : 2)) return;
         {
             LSD_PROF_T0();
             lsd_region2rect(F, R, base, reg_size, reg_angle, prec, p, rec);
@@ -899,14 +991,11 @@ __device__ int lsd_grow_candidate(const LsdFrame &F, const LsdView &V, const Lsd
         const double density = (double)reg_size / (lsd_dist(rec.x1, rec.y1, rec.x2, rec.y2) * rec.width);
         if (density >= DENSITY_TH) {
             has_rect = 1;
-            return 0;
+            return;
         }
         if (pass == 1) { /* still too sparse after the re-grow: shrink it around the seed (lsd.cpp:834-871) */
-            const int r2 = lsd_reduce_region_radius(F, V, R, base, reg_size, reg_angle, prec, p, rec, density, DENSITY_TH);
-            if (r2 == 3) return 0;
-            if (r2) return r2;
-            has_rect = 1;
-            return 0;
+            if (lsd_reduce_region_radius(F, R, base, reg_size, reg_angle, prec, p, rec, density, DENSITY_TH) == 0) has_rect = 1;
+            return;
         }
         /* refine(): tolerance from the angle spread near the seed, give the region back, grow again from the same seed */
         LSD_PROF_T0();
@@ -915,25 +1004,41 @@ __device__ int lsd_grow_candidate(const LsdFrame &F, const LsdView &V, const Lsd
         const double ang_c = (double)F.angf[a0] * LSD_DEG2RAD;
         double sum = 0, s_sum = 0;
         int n = 0;
-        LSD_FOR_REGION_ORDERED(F, R, base, reg_size, {
-            if (lsd_dist(xc, yc, (double)rx, (double)ry) < rec.width) {
-                const double ang_d = lsd_angle_diff_signed(pangle, ang_c);
-                sum += ang_d;
-                s_sum += ang_d * ang_d;
-                ++n;
+        for (int i0 = 0; i0 < reg_size; i0 += 32) {
+            const int m = min(32, reg_size - i0);
+            bool near = false;
+            __syncwarp();
+            if (lane < m) {
+                const int addr = R.get(base + i0 + lane);
+                const int ry = F.row_of(addr), rx = addr - ry * F.W;
+                if (lsd_dist(xc, yc, (double)rx, (double)ry) < rec.width) {
+                    near = true;
+                    const double ang_d = lsd_angle_diff_signed((double)F.angf[addr] * LSD_DEG2RAD, ang_c);
+                    F.stage[lane] = ang_d;
+                    F.stage[32 + lane] = ang_d * ang_d;
+                }
             }
-        })
-        bool lost = false;
-        for (int i = lane; i < reg_size; i += 32) lost |= !lsd_demote(F, V, R.get(base + i));
+            __syncwarp();
+            unsigned todo = __ballot_sync(0xffffffffu, near);
+            n += __popc(todo);
+            while (todo) {
+                const int j = __ffs(todo) - 1;
+                todo &= todo - 1;
+                sum += F.stage[j];
+                s_sum += F.stage[32 + j];
+            }
+        }
+        for (int i = lane; i < reg_size; i += 32) {
+            const int addr = R.get(base + i);
+            atomicAnd(F.ubits + (addr >> 5), ~(1u << (addr & 31)));
+        }
         __syncwarp();
-        if (__any_sync(0xffffffffu, lost)) return 1;
         const double mean_angle = sum / (double)n;
         tau = 2.0 * sqrt((s_sum - 2.0 * mean_angle * sum) / (double)n + mean_angle * mean_angle);
         seed = a0;
         base += reg_size;
         LSD_PROF_ADD(2);
     }
-    return 0;
 }
 
 /* The second half (lsd.cpp:520-534): rect_improve, NFA test, back to image coordinates.  Returns whether the rectangle is a line. */
@@ -1008,6 +1113,7 @@ struct LsdGrowArgs {
     int32_t *n_cand;
     int cand_cap;
     int32_t *cand_line;  /* per candidate: {is a line, 4 floats} */
+    struct LsdCandState *cand_state; /* per candidate: the state of the phase-split validation */
     int32_t *err;        /* bit 2: more candidates in a frame than cand_cap */
     const double *lgam;  /* log_gamma table (cs_nfa.cuh) */
     uint32_t *ubits;     /* (W * H + 31) / 32 words per frame: the used map of k_lsd_grow_seq */
@@ -1016,7 +1122,8 @@ struct LsdGrowArgs {
 };
 
 /* The order-dependent half of the seed loop, one warp per frame (see the file header). */
-__global__ void __launch_bounds__(32) k_lsd_grow_seq(LsdGrowArgs A)
+template <int kMinCtas>
+__global__ void __launch_bounds__(32, kMinCtas) k_lsd_grow_seq(LsdGrowArgs A, int scap)
 {
     const int f = blockIdx.x, lane = threadIdx.x;
     LSD_PROF_T0();
@@ -1028,12 +1135,11 @@ __global__ void __launch_bounds__(32) k_lsd_grow_seq(LsdGrowArgs A)
     F.angf = A.angf + f * npx;
     F.modgrad = A.modgrad + f * npx;
     F.LOG_NT = A.LOG_NT;
-    F.st = nullptr;
-    F.arena = nullptr;
-    F.arena_cap = 0;
     extern __shared__ uint32_t s_seq[];
     const int n_words = (int)((npx + 31) >> 5);
     F.ubits = A.ubits + (size_t)f * n_words;
+    F.span = nullptr;
+    F.stage = reinterpret_cast<double *>(s_seq + scap);
     F.lgam = A.lgam;
     F.wmagic = ((1ull << 40) + (unsigned long long)A.W - 1) / (unsigned long long)A.W;
     for (int i = lane; i < n_words; i += 32) F.ubits[i] = 0u;
@@ -1041,19 +1147,30 @@ __global__ void __launch_bounds__(32) k_lsd_grow_seq(LsdGrowArgs A)
     LsdReg R;
     R.s = (int *)s_seq; /* the first LSD_SEQ_SCAP region entries in shared memory, the rest in the (otherwise unused) record arena */
     R.g = A.arena + (size_t)f * A.arena_cap;
-    R.scap = LSD_SEQ_SCAP;
+    R.scap = scap;
     R.cap = A.arena_cap;
-    LsdView V;
-    V.rank = -1;
-    V.frontier = 0;
     const int n_px = (int)npx;
     int n_cand = 0;
-    for (int i0 = 0; i0 < n_px; i0 += 32) {
-        /* Seeds in RASTER order: flsd walks its coorlist vector by index (lsd.cpp:478-480), and ll_angle fills that vector in scan order; the
-         * gradient-bin links it also builds (lsd.cpp:588-634) are never followed.  32 pixels at a time: those without a defined angle (which
-         * includes the last row and column) or already used are skipped by ballot. */
-        const int adx = i0 + lane;
-        const bool seed = adx < n_px && F.angf[adx] >= 0.f && !F.used_bit(adx);
+    /* Seeds in RASTER order: flsd walks its coorlist vector by index (lsd.cpp:478-480), and ll_angle fills that vector in scan order; the
+     * gradient-bin links it also builds (lsd.cpp:588-634) are never followed.  128 pixels per step, four independent loads per lane in
+     * flight: pixels without a defined angle (which includes the last row and column) or already used are skipped by ballot.  The used
+     * words are read when no region is in progress: a bit that is set then belongs to a finished region and stays set, and a pixel that
+     * gets used after the fetch is caught by the re-check at its turn. */
+    for (int i0 = 0; i0 < n_px; i0 += 128) {
+        float a4[4];
+        uint32_t u4[4];
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            const int adx = i0 + 32 * j + lane;
+            a4[j] = adx < n_px ? F.angf[adx] : -1.f;
+            u4[j] = i0 + 32 * j < n_px ? __ldcg(F.ubits + ((i0 + 32 * j) >> 5)) : 0xffffffffu;
+        }
+#pragma unroll 1 /* the body holds the whole seed pipeline: once in the kernel (instruction cache) */
+        for (int j = 0; j < 4; j++) {
+        const int adx = i0 + 32 * j + lane;
+        const float a_j = j == 0 ? a4[0] : j == 1 ? a4[1] : j == 2 ? a4[2] : a4[3];
+        const uint32_t u_j = j == 0 ? u4[0] : j == 1 ? u4[1] : j == 2 ? u4[2] : u4[3];
+        const bool seed = a_j >= 0.f && !((u_j >> lane) & 1u);
         unsigned todo = __ballot_sync(0xffffffffu, seed);
         while (todo) {
             const int sl = __ffs(todo) - 1;
@@ -1062,11 +1179,12 @@ __global__ void __launch_bounds__(32) k_lsd_grow_seq(LsdGrowArgs A)
             if (F.used_bit(s_addr)) continue; /* used by a region grown since the ballot */
             int n_all = 0, has_rect = 0;
             LsdRect rec;
-            const int rc = lsd_grow_candidate(F, V, R, s_addr, A.min_reg_size, A.prec, A.p, n_all, has_rect, rec);
-            if (rc || !has_rect) continue; /* rc == 2 (a region larger than the whole arena) cannot happen: arena_cap >= W * H + 27 */
+            lsd_grow_candidate(F, R, s_addr, A.min_reg_size, A.prec, A.p, n_all, has_rect, rec); /* arena_cap >= 2 W H: both passes fit */
+            if (!has_rect) continue;
             /* the rectangle goes to k_lsd_validate (rect_improve + NFA never touch the used map): candidates in seed order */
             if (lane == 0 && n_cand < A.cand_cap) A.cand[(size_t)f * A.cand_cap + n_cand] = rec;
             n_cand++;
+        }
         }
     }
     if (lane == 0) {
@@ -1078,7 +1196,8 @@ __global__ void __launch_bounds__(32) k_lsd_grow_seq(LsdGrowArgs A)
 
 /* rect_improve + NFA of every candidate rectangle (lsd.cpp:520-534), one warp each: thousands of warps running the same code.  (A CTA of
  * five warps per candidate, one warp per rectangle of a rect_improve phase, was measured slower: 3.5 vs 2.45 ms per 256 frames.) */
-__global__ void __launch_bounds__(128, 5) k_lsd_validate(LsdGrowArgs A)
+template <int kMinCtas>
+__global__ void __launch_bounds__(128, kMinCtas) k_lsd_validate(LsdGrowArgs A)
 {
     const int f = blockIdx.y, lane = threadIdx.x & 31;
     const size_t npx = (size_t)A.W * A.H;
@@ -1089,10 +1208,10 @@ __global__ void __launch_bounds__(128, 5) k_lsd_validate(LsdGrowArgs A)
     F.angf = A.angf + f * npx;
     F.modgrad = A.modgrad + f * npx;
     F.LOG_NT = A.LOG_NT;
-    F.st = nullptr;
-    F.arena = nullptr;
-    F.arena_cap = 0;
     F.ubits = nullptr;
+    __shared__ LsdSpan s_span[4][5];
+    F.span = s_span[threadIdx.x >> 5];
+    F.stage = nullptr;
     F.lgam = A.lgam;
     F.wmagic = 0;
     const int n = min(A.n_cand[f], A.cand_cap);
@@ -1107,6 +1226,154 @@ __global__ void __launch_bounds__(128, 5) k_lsd_validate(LsdGrowArgs A)
             for (int k = 0; k < 4; k++) o[1 + k] = __float_as_int(line[k]);
         }
     }
+}
+
+/* ---- the same, split by phase into small kernels ---------------------------------------------------------------------------------
+ * k_lsd_validate is ~6.6 k instructions (the scans, the double-precision log / exp / pow of the binomial tail, the improvement logic), the
+ * L1.5 instruction cache holds 2 k, and its warps sit in different places of that code: ncu shows 40 % of its issue stalls as
+ * `no_instruction`.  rect_improve is six rounds of {count the pixels of up to five rectangles, turn the counts into NFA values, keep the
+ * best} (lsd.cpp:873-975); run as twelve launches -- k_lsd_val_count(round), k_lsd_val_nfa(round) -- every warp of a launch is in the
+ * same few hundred instructions.  State between launches: the candidate's current rectangle (A.cand, updated in place), its best
+ * log_nfa and the counts of the round (A.cand_state). */
+struct LsdCandState {
+    double log_nfa;
+    int32_t status; /* 0 = still being improved, 1 = decided (A.cand_line holds the verdict) */
+    int32_t n;      /* rectangles counted in this round */
+    int32_t tot[5], alg[5];
+};
+
+/* the rectangles round `round` evaluates, from the current one (lsd.cpp:873-975; round 0 = the rectangle itself) */
+__device__ int lsd_improve_variants(const LsdRect &rec, int round, LsdRect *cand)
+{
+    const double delta = 0.5, delta_2 = delta / 2.0;
+    LsdRect r = rec;
+    if (round == 0) {
+        cand[0] = r;
+        return 1;
+    }
+    if (round == 1) {
+        for (int n = 0; n < 5; ++n) {
+            r.p /= 2;
+            r.prec = r.p * LSD_PI;
+            cand[n] = r;
+        }
+        return 5;
+    }
+    const int phase = round - 2;
+    int m = 0;
+    for (int n = 0; n < 5; ++n)
+        if ((r.width - delta) >= 0.5) {
+            if (phase == 0)
+                r.width -= delta;
+            else if (phase == 1) {
+                r.x1 += -r.dy * delta_2;
+                r.y1 += r.dx * delta_2;
+                r.x2 += -r.dy * delta_2;
+                r.y2 += r.dx * delta_2;
+                r.width -= delta;
+            } else if (phase == 2) {
+                r.x1 -= -r.dy * delta_2;
+                r.y1 -= r.dx * delta_2;
+                r.x2 -= -r.dy * delta_2;
+                r.y2 -= r.dx * delta_2;
+                r.width -= delta;
+            } else {
+                r.p /= 2;
+                r.prec = r.p * LSD_PI;
+            }
+            cand[m++] = r;
+        }
+    return m;
+}
+
+__global__ void __launch_bounds__(128, 5) k_lsd_val_count(LsdGrowArgs A, int round)
+{
+    const int f = blockIdx.y, lane = threadIdx.x & 31;
+    const size_t npx = (size_t)A.W * A.H;
+    LsdFrame F;
+    F.W = A.W;
+    F.H = A.H;
+    F.pix = nullptr;
+    F.angf = A.angf + f * npx;
+    F.modgrad = nullptr;
+    F.LOG_NT = A.LOG_NT;
+    F.ubits = nullptr;
+    __shared__ LsdSpan s_span[4][5];
+    F.span = s_span[threadIdx.x >> 5];
+    F.stage = nullptr;
+    F.lgam = A.lgam;
+    F.wmagic = 0;
+    const int n = min(A.n_cand[f], A.cand_cap);
+    const int wpb = blockDim.x >> 5;
+    for (int c = blockIdx.x * wpb + (threadIdx.x >> 5); c < n; c += gridDim.x * wpb) {
+        LsdCandState *S = A.cand_state + (size_t)f * A.cand_cap + c;
+        if (round > 0 && S->status != 0) continue;
+        const LsdRect rec = A.cand[(size_t)f * A.cand_cap + c];
+        LsdRect cv[5];
+        const int m = lsd_improve_variants(rec, round, cv);
+        int tot[5] = {0, 0, 0, 0, 0}, alg[5] = {0, 0, 0, 0, 0};
+        if (m == 1)
+            lsd_rect_count(F, cv[0], tot[0], alg[0]);
+        else if (m > 1)
+            lsd_rect_count_multi(F, cv, m, round == 1 || round == 5, tot, alg);
+        if (lane == 0) {
+            S->n = m;
+            for (int t = 0; t < 5; t++) {
+                S->tot[t] = tot[t];
+                S->alg[t] = alg[t];
+            }
+        }
+    }
+}
+
+__global__ void __launch_bounds__(128, 5) k_lsd_val_nfa(LsdGrowArgs A, int round)
+{
+    const int f = blockIdx.y, lane = threadIdx.x & 31;
+    const int n = min(A.n_cand[f], A.cand_cap);
+    const int wpb = blockDim.x >> 5;
+    for (int c = blockIdx.x * wpb + (threadIdx.x >> 5); c < n; c += gridDim.x * wpb) {
+        LsdCandState *S = A.cand_state + (size_t)f * A.cand_cap + c;
+        if (round > 0 && S->status != 0) continue;
+        LsdRect rec = A.cand[(size_t)f * A.cand_cap + c];
+        LsdRect cv[5];
+        const int m = lsd_improve_variants(rec, round, cv);
+        double log_nfa = round == 0 ? 0.0 : S->log_nfa;
+        bool changed = false;
+        for (int t = 0; t < m; t++) {
+            const double v = cs_nfa_warp(A.lgam, S->tot[t], S->alg[t], cv[t].p, A.LOG_NT, true); /* the whole warp on one binomial tail */
+            if (round == 0 || v > log_nfa) {
+                log_nfa = v;
+                rec = cv[t];
+                changed = round > 0;
+            }
+        }
+        const bool done = round == 5 || log_nfa > 0.0; /* lsd.cpp:887,903,921,938,955: leave as soon as the rectangle is meaningful */
+        __syncwarp();
+        if (lane == 0) {
+            if (done) {
+                int32_t *o = A.cand_line + ((size_t)f * A.cand_cap + c) * 5;
+                const bool ok = log_nfa > 0.0;
+                o[0] = ok ? 1 : 0;
+                /* lsd.cpp:524-534: the half-pixel offset, back to the scale of the input image */
+                o[1] = __float_as_int((float)((rec.x1 + 0.5) / A.scale));
+                o[2] = __float_as_int((float)((rec.y1 + 0.5) / A.scale));
+                o[3] = __float_as_int((float)((rec.x2 + 0.5) / A.scale));
+                o[4] = __float_as_int((float)((rec.y2 + 0.5) / A.scale));
+                S->status = 1;
+            } else {
+                if (changed) A.cand[(size_t)f * A.cand_cap + c] = rec;
+                S->log_nfa = log_nfa;
+                S->status = 0;
+            }
+        }
+    }
+}
+
+/* kernels one LSD run launches: blur, resize, gradient, seed loop, validation (12 phase kernels, or the single kernel of the A/B variants), emit */
+static int cs_lsd_launches_per_run()
+{
+    static const int v_val = getenv("CS_LSD_VAL_VARIANT") ? atoi(getenv("CS_LSD_VAL_VARIANT")) : 0;
+    return 3 + 1 + (v_val == 0 ? 12 : 1) + 1;
 }
 
 /* the accepted candidates of a frame in seed order: raw segments, and those that pass the key-line filter */
@@ -1180,7 +1447,7 @@ struct Buf {
 };
 
 struct LsdState {
-    Buf img, tmp, blur, scaled, modgrad, angf, pix, arena, raw, nraw, out, nout, redo, stats, lgam, ubits, cand, ncand, candline, err;
+    Buf img, tmp, blur, scaled, modgrad, angf, pix, arena, raw, nraw, out, nout, redo, stats, lgam, ubits, cand, ncand, candline, candstate, err;
     bool lgam_filled = false;
     int last_frames = 0, last_W = 0, last_H = 0, cap = 0;
 };
@@ -1235,7 +1502,7 @@ int lsd_run(cs_ctx *c, const uint8_t *imgs, bool imgs_on_device, int n_frames, i
         (rc = ensure(c, S.redo, (size_t)n_frames * 4)) || (rc = ensure(c, S.stats, (size_t)n_frames * 16)) ||
         (rc = ensure(c, S.lgam, (size_t)CS_LGAMMA_TABLE * 8)) || (rc = ensure(c, S.ubits, (size_t)n_frames * (((size_t)W * H + 31) / 32) * 4)) ||
         (rc = ensure(c, S.cand, (size_t)n_frames * LSD_CAND_CAP * sizeof(LsdRect))) || (rc = ensure(c, S.ncand, (size_t)n_frames * 4)) ||
-        (rc = ensure(c, S.candline, (size_t)n_frames * LSD_CAND_CAP * 20)) || (rc = ensure(c, S.err, 16)))
+        (rc = ensure(c, S.candline, (size_t)n_frames * LSD_CAND_CAP * 20)) || (rc = ensure(c, S.candstate, (size_t)n_frames * LSD_CAND_CAP * sizeof(LsdCandState))) || (rc = ensure(c, S.err, 16)))
         return rc;
     if (!S.lgam_filled) { /* log_gamma of the integers 1 .. CS_LGAMMA_TABLE - 1, host libm like the reference */
         std::vector<double> t(CS_LGAMMA_TABLE, 0.0);
@@ -1300,16 +1567,34 @@ int lsd_run(cs_ctx *c, const uint8_t *imgs, bool imgs_on_device, int n_frames, i
     A.n_cand = (int32_t *)S.ncand.p;
     A.cand_cap = LSD_CAND_CAP;
     A.cand_line = (int32_t *)S.candline.p;
+    A.cand_state = (LsdCandState *)S.candstate.p;
     A.err = (int32_t *)S.err.p;
     A.redo = (int32_t *)S.redo.p;
     A.stats = (int32_t *)S.stats.p;
     {
-        const size_t smem = (size_t)LSD_SEQ_SCAP * 4;
-        k_lsd_grow_seq<<<n_frames, 32, smem, st>>>(A);
-        k_lsd_validate<<<dim3(64, n_frames), 128, 0, st>>>(A); /* 256 warps per frame: a warp per candidate for all but the densest frames */
+        static const int v_grow = getenv("CS_LSD_GROW_VARIANT") ? atoi(getenv("CS_LSD_GROW_VARIANT")) : 0;
+        static const int v_val = getenv("CS_LSD_VAL_VARIANT") ? atoi(getenv("CS_LSD_VAL_VARIANT")) : 0;
+        static const int scap = getenv("CS_LSD_SCAP") ? atoi(getenv("CS_LSD_SCAP")) : LSD_SEQ_SCAP;
+        const size_t smem = (size_t)scap * 4 + 96 * 8; /* region list + the staging of the ordered sums (scap is even: 8-byte aligned) */
+        if (v_grow == 1)
+            k_lsd_grow_seq<32><<<n_frames, 32, smem, st>>>(A, scap);
+        else if (v_grow == 2)
+            k_lsd_grow_seq<25><<<n_frames, 32, smem, st>>>(A, scap);
+        else
+            k_lsd_grow_seq<21><<<n_frames, 32, smem, st>>>(A, scap);
+        /* 256 warps per frame: a warp per candidate for all but the densest frames */
+        if (v_val == 1)
+            k_lsd_validate<8><<<dim3(64, n_frames), 128, 0, st>>>(A);
+        else if (v_val == 2)
+            k_lsd_validate<5><<<dim3(64, n_frames), 128, 0, st>>>(A);
+        else
+            for (int round = 0; round < 6; round++) {
+                k_lsd_val_count<<<dim3(64, n_frames), 128, 0, st>>>(A, round);
+                k_lsd_val_nfa<<<dim3(64, n_frames), 128, 0, st>>>(A, round);
+            }
         k_lsd_emit<<<n_frames, 256, 0, st>>>(A);
     }
-    cs_ctx_count_launches(c, 6);
+    cs_ctx_count_launches(c, cs_lsd_launches_per_run());
     if (cudaGetLastError() != cudaSuccess) return cs_ctx_fail(c, CS_ERR_CUDA, "LSD kernel launch failed: %s", cudaGetErrorString(cudaGetLastError()));
     S.last_frames = n_frames;
     S.last_W = W;
@@ -1342,7 +1627,7 @@ int cs_lsd_run_device(cs_ctx *c, const uint8_t *d_imgs, int n_frames, int w, int
 void cs_lsd_destroy(void *state)
 {
     LsdState *S = (LsdState *)state;
-    Buf *all[] = {&S->img, &S->tmp, &S->blur, &S->scaled, &S->modgrad, &S->angf, &S->pix, &S->arena, &S->raw, &S->nraw, &S->out, &S->nout, &S->redo, &S->stats, &S->lgam, &S->ubits, &S->cand, &S->ncand, &S->candline, &S->err};
+    Buf *all[] = {&S->img, &S->tmp, &S->blur, &S->scaled, &S->modgrad, &S->angf, &S->pix, &S->arena, &S->raw, &S->nraw, &S->out, &S->nout, &S->redo, &S->stats, &S->lgam, &S->ubits, &S->cand, &S->ncand, &S->candline, &S->candstate, &S->err};
     for (Buf *b : all)
         if (b->p) cudaFree(b->p);
     delete S;
@@ -1438,15 +1723,15 @@ int cs_debug_lsd(cs_ctx *c, int frame, int32_t *scaled_wh, double *scaled, doubl
 
 /* cycle counters of the seed loop's phases summed over every warp since the last reset (diagnostics): {region_grow, region2rect, refine,
  * rectangle pixel counts, binomial tails, candidates grown, whole kernel (per CTA), unused} */
-int cs_debug_lsd_prof(cs_ctx *c, uint64_t *out8, int reset)
+int cs_debug_lsd_prof(cs_ctx *c, uint64_t *out16, int reset)
 {
     if (!c) return CS_ERR_INVALID_ARG;
     cudaSetDevice(cs_ctx_device(c));
     cudaStreamSynchronize(cs_ctx_stream(c));
-    if (out8) cudaMemcpyFromSymbol(out8, g_lsd_prof, 64);
+    if (out16) cudaMemcpyFromSymbol(out16, g_lsd_prof, 128);
     if (reset) {
-        const unsigned long long z[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-        cudaMemcpyToSymbol(g_lsd_prof, z, 64);
+        const unsigned long long z[16] = {0};
+        cudaMemcpyToSymbol(g_lsd_prof, z, 128);
     }
     return cudaGetLastError() == cudaSuccess ? CS_OK : cs_ctx_fail(c, CS_ERR_CUDA, "debug copy failed");
 }

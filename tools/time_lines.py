@@ -41,7 +41,7 @@ def main():
     ctx.set_profiling(1 | flags)
     ctx.upload_online(imgs, Ts, boxes, det.params(), cs.default_params())
     import ctypes as C
-    prof = np.zeros(8, np.uint64)
+    prof = np.zeros(16, np.uint64)
     for r in range(args.reps):
         if args.flavour == "lsd":
             ctx.L.cs_debug_lsd_prof(ctx.h, None, 1)
@@ -54,8 +54,8 @@ def main():
                 st[:, 0].mean(), st[:, 0].max(), st[:, 1].mean(), st[:, 2].mean(), st[:, 3].mean(), redo.sum())
             ctx.L.cs_debug_lsd_prof(ctx.h, prof.ctypes.data_as(C.POINTER(C.c_uint64)), 0)
             pf = prof.astype(np.float64) / args.frames
-            msg += " | Mcycles/frame: grow %.2f rect %.2f refine %.2f count %.2f nfa %.2f kernel %.2f, candidates/frame %.0f" % (
-                pf[0] / 1e6, pf[1] / 1e6, pf[2] / 1e6, pf[3] / 1e6, pf[4] / 1e6, pf[6] / 1e6, pf[5])
+            msg += " | Mcycles/frame: grow %.2f rect %.2f refine %.2f count %.2f nfa %.2f kernel %.2f, seeds grown/frame %.0f, region px/frame %.0f" % (
+                pf[0] / 1e6, pf[1] / 1e6, pf[2] / 1e6, pf[3] / 1e6, pf[4] / 1e6, pf[6] / 1e6, pf[5], pf[7])
         print(msg, flush=True)
 
 
