@@ -10,8 +10,8 @@
  *
  * PARITY: "parity unpinned" by the reference (it ships no tests or expected C++ outputs and cannot
  * be compiled here).  What exists: the OpenCV stages are bit-exact against cv2; and, run on the shipped object_slam sequence at the
- * shipped per-frame poses, this oracle (with the LSD oracle's lines) lands on the cuboids the authors ship from their MATLAB
- * implementation (object_slam/data/detect_cuboids_saved.txt) up to the sampling grid -- median 3.3 cm, same yaw sample on most
+ * shipped per-frame poses, this oracle (with the LSD oracle's lines, themselves pinned to the compiled reference) lands on the cuboids the authors ship from their MATLAB
+ * implementation (object_slam/data/detect_cuboids_saved.txt) up to the sampling grid -- median 3.2 cm, same yaw sample on most
  * frames (tests/test_oracle_matlab_crosscheck.py).  A soft pin, not equality.  Build with -O2 -ffp-contract=off (no FMA contraction) so + - * / sqrt
  * are IEEE-exact and comparable with the CUDA path compiled with -fmad=false.
  *

@@ -19,7 +19,13 @@
  * (14, 62, 104, 62, 14) / 256 in both directions with one final (+32768) >> 16; Sobel 3x3 with BORDER_REFLECT_101;
  * threshold(TOZERO, 81) on |dx|+|dy|; `mat / 4` == round-half-to-even; compare(CMP_LT).
  *
- * PARITY: "parity unpinned" by the reference (no tests / goldens; cannot be compiled here).
+ * PARITY: PINNED to the reference.  The reference's own binary_descriptor.cpp and headers, compiled from /root/reference into
+ * oracle/_ref/libedl_ref.so (oracle/ref/edl_ref.cpp, oracle/Makefile target `ref`) and driven as detect_raw_lines drives them, return
+ * byte-identical key lines on every fixture, synthetic and degenerate image tried (tests/test_oracle_ref_edlines.py); counts and
+ * checksums are recorded in the committed goldens (tests/test_goldens_sequence.py).  One input class has no reference output to compare
+ * with: EDLineDetector::EDline sizes lines.sId as 5 x (number of chains) (binary_descriptor.cpp:2394) and overruns the heap when chains
+ * split into more segments than that (AddressSanitizer: heap-buffer-overflow at :2438, e.g. one long curved chain); this restatement
+ * keeps every segment.
  */
 #include <algorithm>
 #include <cfloat>
@@ -65,6 +71,16 @@ void gaussian5_u8(const std::vector<uint8_t> &src, int w, int h, std::vector<uin
             dst[(size_t)y * w + x] = (uint8_t)((s + 32768u) >> 16);
         }
 }
+
+} // namespace (reopened below)
+/* for oracle/ref/minicv.hpp: the one restatement of OpenCV's 8-bit 5 x 5 Gaussian, pinned against cv2 (tests/test_oracle_cv_parity.py) */
+extern "C" void edl_orc_gaussian5_u8(const uint8_t *src, int w, int h, uint8_t *dst)
+{
+    std::vector<uint8_t> in(src, src + (size_t)w * h), out;
+    gaussian5_u8(in, w, h, out);
+    std::memcpy(dst, out.data(), out.size());
+}
+namespace {
 
 inline int div4_half_even(int s)
 {

@@ -12,10 +12,15 @@
  * restated from OpenCV's algorithms and pinned against the in-container cv2 4.13 (tests/test_oracle_lines.py).
  * The Gaussian kernel is cv2 4.13's bit-exact getGaussianKernel(7, 0.6 / 0.8) (sigma = 0.7499999999999999, lsd.cpp:453) (it differs from exp()-based kernels in the last ulp).
  *
- * PARITY: "parity unpinned" by the reference (no tests; cannot be compiled here).  Partial golden: 74 of the 271 segments of the one
- * LSD output the reference ships (detect_3d_cuboid/data/edge_detection/LSD/0000_edge.txt) are reproduced to its six significant digits
- * (cv2's rewritten LSD reproduces one); the rest differ because that file was not produced from the shipped JPEG bit for bit
- * (tests/test_oracle_lines.py).
+ * The seed list is visited in RASTER order: flsd walks its coorlist vector by index (lsd.cpp:478-480), the gradient-bin links that ll_angle
+ * also builds (lsd.cpp:588-634) are never followed.
+ *
+ * PARITY: PINNED to the reference.  (1) The reference's own lsd.cpp, compiled from /root/reference into oracle/_ref/liblsd_ref.so
+ * (oracle/ref/lsd_ref.cpp, oracle/Makefile target `ref`), returns byte-identical raw segments on every fixture, synthetic and
+ * degenerate image tried (tests/test_oracle_ref_lsd.py); its segment counts and checksums are recorded in the committed goldens, so the
+ * pin also holds where the reference is absent (tests/test_goldens_sequence.py).  (2) The one LSD output the reference ships
+ * (detect_3d_cuboid/data/edge_detection/LSD/0000_edge.txt) is reproduced whole: 271 of 271 segments, in order, to its six significant
+ * digits (tests/test_oracle_lines.py).  The OpenCV primitives inside are pinned against cv2 4.13.
  */
 #include <algorithm>
 #include <cfloat>

@@ -6,12 +6,15 @@
  * cpu_baseline / --impl reference legs may load it.  The product library
  * (cube_slam_b200/lib/libcubeslam_b200.so) never links or calls anything in oracle/.
  *
- * PARITY STATUS: "parity unpinned" -- the reference ships no tests / golden outputs for this
- * path and cannot be compiled in this container (needs Eigen, OpenCV C++, ROS).  The
- * third-party OpenCV stages restated here are pinned bit-for-bit against the in-container
- * cv2 4.13 wheel (see tests/test_oracle_cv_parity.py, tests/test_oracle_lines.py, tools/make_golden.py).  Soft pins against what
- * the reference does ship: its LSD segment file (partial golden) and its MATLAB cuboids for the object_slam sequence
- * (tests/test_oracle_matlab_crosscheck.py).
+ * PARITY STATUS, per stage:
+ *   line detection (stage i, both flavours): PINNED -- the reference's own lsd.cpp and binary_descriptor.cpp compile from
+ *     /root/reference against a small OpenCV stand-in (oracle/ref/, oracle/_ref/*.so) and the restatements are byte-identical to them
+ *     (tests/test_oracle_ref_lsd.py, tests/test_oracle_ref_edlines.py, checksums in tests/golden/); the shipped LSD segment file is
+ *     reproduced whole (tests/test_oracle_lines.py).
+ *   cuboid proposals (stage ii): "parity unpinned" -- detect_3d_cuboid needs Eigen and OpenCV C++, neither is in this image, and the
+ *     reference ships no tests or expected outputs for it.  The OpenCV stages inside (cvtColor, Canny, distanceTransform) are pinned bit
+ *     for bit against the in-container cv2 4.13 (tests/test_oracle_cv_parity.py); the whole path is soft-pinned against the MATLAB
+ *     cuboids the authors ship for the object_slam sequence (tests/test_oracle_matlab_crosscheck.py).
  */
 #ifndef ORC_API_H
 #define ORC_API_H

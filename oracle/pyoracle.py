@@ -19,10 +19,10 @@ def build(force=False):
     fresh = os.path.exists(_LIB_PATH) and all(os.path.getmtime(_LIB_PATH) >= os.path.getmtime(s) for s in srcs)
     # oracle/_ref (the reference's own lsd.cpp) is built where the reference checkout exists; elsewhere the prebuilt file is used as it is
     ref_src = "/root/reference/line_lbd/libs/lsd.cpp"
-    ref_lib = os.path.join(_HERE, "_ref", "liblsd_ref.so")
+    ref_libs = [os.path.join(_HERE, "_ref", "liblsd_ref.so"), os.path.join(_HERE, "_ref", "libedl_ref.so")]
     if os.path.exists(ref_src):
-        deps = [ref_src, _LIB_PATH] + [os.path.join(_HERE, "ref", f) for f in os.listdir(os.path.join(_HERE, "ref"))]
-        fresh = fresh and os.path.exists(ref_lib) and all(os.path.getmtime(ref_lib) >= os.path.getmtime(d) for d in deps)
+        deps = [ref_src, _LIB_PATH] + [os.path.join(_HERE, "ref", f) for f in os.listdir(os.path.join(_HERE, "ref")) if f.endswith((".cpp", ".hpp"))]
+        fresh = fresh and all(os.path.exists(r) and all(os.path.getmtime(r) >= os.path.getmtime(d) for d in deps) for r in ref_libs)
     if not force and fresh:
         return _LIB_PATH
     subprocess.check_call(["make", "-C", _HERE, "-s"] + (["-B"] if force else []))
@@ -301,6 +301,32 @@ def ref_lsd_detect(img, cap=8192):
     n = _REF_LSD.ref_lsd_detect(_p(gray, C.c_uint8), gray.shape[1], gray.shape[0], _p(out, C.c_float), cap)
     if n < 0:
         raise RuntimeError("ref_lsd_detect failed")
+    return out[:min(n, cap)].copy()
+
+
+_REF_EDL = None
+_REF_EDL_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_ref", "libedl_ref.so")
+
+
+def ref_edl_available():
+    return os.path.exists(_REF_EDL_PATH)
+
+
+def ref_edl_detect(img, cap=8192):
+    """The reference's OWN EDLines detector (line_lbd/libs/binary_descriptor.cpp compiled from /root/reference into
+    oracle/_ref/libedl_ref.so, see oracle/ref/edl_ref.cpp): BinaryDescriptor::detect with one octave, as line_lbd_detect::detect_raw_lines
+    drives it for use_LSD = false -> n x 4 float32 key-line end points, before detect_filter_lines' length filter."""
+    global _REF_EDL
+    lib()
+    if _REF_EDL is None:
+        _REF_EDL = C.CDLL(_REF_EDL_PATH)
+        _REF_EDL.ref_edl_detect.restype = C.c_int
+    img = np.ascontiguousarray(img, np.uint8)
+    gray = img if img.ndim == 2 else np.ascontiguousarray(bgr2gray(img))
+    out = np.zeros((cap, 4), np.float32)
+    n = _REF_EDL.ref_edl_detect(_p(gray, C.c_uint8), gray.shape[1], gray.shape[0], _p(out, C.c_float), cap)
+    if n < 0:
+        raise RuntimeError("ref_edl_detect failed")
     return out[:min(n, cap)].copy()
 
 

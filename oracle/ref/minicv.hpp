@@ -20,24 +20,34 @@
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
+#include <cstdint>
 #include <cstring>
 #include <memory>
 #include <stdexcept>
+#include <string>
 #include <vector>
 
 extern "C" void lsd_orc_gaussian7(const double *src, int w, int h, double *dst);
 extern "C" void lsd_orc_resize(const double *src, int w, int h, double scale, double *dst, int *dw, int *dh);
 extern "C" float lsd_orc_fast_atan2(float y, float x);
+extern "C" void edl_orc_gaussian5_u8(const uint8_t *src, int w, int h, uint8_t *dst);
 
 #define CV_PI 3.1415926535897932384626433832795
 #define CV_EXPORTS
 #define CV_WRAP
+#define CV_OUT
+#define CV_IN_OUT
 #define CV_8U 0
+#define CV_8S 1
+#define CV_16S 3
 #define CV_32F 5
 #define CV_64F 6
 #define CV_MAKETYPE(depth, cn) ((depth) + (((cn)-1) << 3))
 #define CV_8UC1 CV_MAKETYPE(CV_8U, 1)
 #define CV_8UC3 CV_MAKETYPE(CV_8U, 3)
+#define CV_8SC1 CV_MAKETYPE(CV_8S, 1)
+#define CV_16SC1 CV_MAKETYPE(CV_16S, 1)
+#define CV_32FC1 CV_MAKETYPE(CV_32F, 1)
 #define CV_32FC4 CV_MAKETYPE(CV_32F, 4)
 #define CV_64FC1 CV_MAKETYPE(CV_64F, 1)
 #define CV_BGR2GRAY 6
@@ -88,6 +98,9 @@ struct Scalar {
 
 template <typename T> struct DepthOf;
 template <> struct DepthOf<uchar> { enum { value = CV_8U }; };
+template <> struct DepthOf<signed char> { enum { value = CV_8S }; };
+template <> struct DepthOf<short> { enum { value = CV_16S }; };
+template <> struct DepthOf<int> { enum { value = 4 /* CV_32S */ }; };
 template <> struct DepthOf<float> { enum { value = CV_32F }; };
 template <> struct DepthOf<double> { enum { value = CV_64F }; };
 
@@ -95,6 +108,9 @@ inline size_t depth_bytes(int type)
 {
     switch (type & 7) {
         case CV_8U: return 1;
+        case CV_8S: return 1;
+        case CV_16S: return 2;
+        case 4: return 4; /* CV_32S */
         case CV_32F: return 4;
         case CV_64F: return 8;
         default: throw std::runtime_error("minicv: unsupported depth");
@@ -142,6 +158,22 @@ public:
     template <typename T> const T *ptr(int r = 0) const { return reinterpret_cast<const T *>(ptr(r)); }
     template <typename T> T &at(int i) { return reinterpret_cast<T *>(data)[i]; }
     template <typename T> const T &at(int i) const { return reinterpret_cast<const T *>(data)[i]; }
+    template <typename T> T &at(int r, int c) { return reinterpret_cast<T *>(data)[(size_t)r * cols + c]; }
+    template <typename T> const T &at(int r, int c) const { return reinterpret_cast<const T *>(data)[(size_t)r * cols + c]; }
+    static Mat ones(Size s, int type)
+    {
+        Mat m(s.height, s.width, type);
+        if ((type & 7) != CV_8U) throw std::runtime_error("minicv: Mat::ones is provided for 8-bit only");
+        memset(m.data, 1, m.total() * m.elemSize());
+        return m;
+    }
+    static Mat zeros(int r, int c, int type) { return Mat(r, c, type); } /* create() zero-fills */
+    void setTo(int v)
+    {
+        if (v != 0) throw std::runtime_error("minicv: setTo is provided for 0 only");
+        if (data) memset(data, 0, total() * elemSize());
+    }
+    Mat t() const; /* transpose (float / double single channel) */
     int checkVector(int) const { return -1; }
     Mat clone() const
     {
@@ -159,6 +191,8 @@ public:
             memcpy(out.data, data, n * elemSize());
         else if (depth() == CV_8U && (rtype & 7) == CV_64F)
             for (size_t i = 0; i < n; i++) out.ptr<double>()[i] = (double)data[i];
+        else if (depth() == 4 && (rtype & 7) == CV_32F) /* CV_32S -> CV_32F (EDLineDetector::InitEDLine_ sizes its float matrices this way) */
+            for (size_t i = 0; i < n; i++) out.ptr<float>()[i] = (float)ptr<int>()[i];
         else
             throw std::runtime_error("minicv: unsupported conversion");
         dst = out;
@@ -193,6 +227,8 @@ public:
     }
     static Mat_ zeros(Size s) { return Mat_(s); } /* create() zero-fills */
     T &operator()(int r, int c) { return reinterpret_cast<T *>(data)[(size_t)r * cols + c]; }
+    T *operator[](int r) { return reinterpret_cast<T *>(data) + (size_t)r * cols; }
+    const T *operator[](int r) const { return reinterpret_cast<const T *>(data) + (size_t)r * cols; }
     Line row(int r) { return Line{reinterpret_cast<T *>(data) + (size_t)r * cols, 1, cols}; }
     Line col(int c) { return Line{reinterpret_cast<T *>(data) + c, (size_t)cols, rows}; }
     using Mat::ptr;
@@ -265,20 +301,74 @@ inline const _OutputArray &noArray()
 }
 inline void Mat::copyTo(const _OutputArray &dst) const { dst.assign(clone()); }
 
+inline Mat Mat::t() const
+{
+    Mat o(cols, rows, type_);
+    const size_t es = elemSize();
+    for (int r = 0; r < rows; r++)
+        for (int c = 0; c < cols; c++) memcpy(o.data + ((size_t)c * rows + r) * es, data + ((size_t)r * cols + c) * es, es);
+    return o;
+}
+
+/* declarations only: parameter persistence is never exercised */
+class FileNode {
+public:
+    operator int() const { return 0; }
+    template <typename T> void operator>>(T &) const {}
+    FileNode operator[](const char *) const { return FileNode(); }
+    bool empty() const { return true; }
+};
+class FileStorage {
+public:
+    template <typename T> FileStorage &operator<<(const T &) { return *this; }
+};
+typedef std::string String;
+struct Range {
+    int start, end;
+    Range() : start(0), end(0) {}
+    Range(int s, int e) : start(s), end(e) {}
+};
+struct KeyPoint {
+    Point2f pt;
+    float size, angle, response;
+    int octave, class_id;
+};
+struct DMatch {
+    int queryIdx, trainIdx, imgIdx;
+    float distance;
+    DMatch() : queryIdx(-1), trainIdx(-1), imgIdx(-1), distance(FLT_MAX) {}
+    DMatch(int q, int t, float d) : queryIdx(q), trainIdx(t), imgIdx(-1), distance(d) {}
+    DMatch(int q, int t, int i, float d) : queryIdx(q), trainIdx(t), imgIdx(i), distance(d) {}
+    bool operator<(const DMatch &m) const { return distance < m.distance; }
+};
+enum { NORM_HAMMING = 6, COLOR_BGR2GRAY = 6, THRESH_TOZERO = 3, CMP_LT = 3, INTER_LINEAR = 1 };
+
 class Algorithm {
 public:
     virtual ~Algorithm() {}
+    virtual void read(const FileNode &) {}
+    virtual void write(FileStorage &) const {}
 };
 template <typename T> using Ptr = std::shared_ptr<T>;
 template <typename T, typename... A> Ptr<T> makePtr(A &&...a) { return std::make_shared<T>(std::forward<A>(a)...); }
 
-/* the three primitives of the path: forwarded to the oracle's cv2-pinned restatements (see the header) */
+using std::max;
+using std::min;
+
+/* the three primitives of the LSD path: forwarded to the oracle's cv2-pinned restatements (see the header) */
 inline float fastAtan2(float y, float x) { return lsd_orc_fast_atan2(y, x); }
 inline void GaussianBlur(InputArray src_, OutputArray dst, Size ksize, double sigma)
 {
     const Mat src = src_.getMat();
+    if (src.type() == CV_8UC1 && ksize.width == 5 && ksize.height == 5 && std::fabs(sigma - 1.0) < 1e-6) {
+        /* BinaryDescriptor::OctaveKeyLines, octave 0 (binary_descriptor.cpp:813-814): OpenCV's fixed-point 8-bit smoothing */
+        Mat out(src.rows, src.cols, CV_8UC1);
+        edl_orc_gaussian5_u8(src.data, src.cols, src.rows, out.data);
+        dst.assign(out);
+        return;
+    }
     if (src.type() != CV_64FC1 || ksize.width != 7 || ksize.height != 7 || std::fabs(sigma - 0.6 / 0.8) > 1e-12)
-        throw std::runtime_error("minicv: GaussianBlur is only provided for the call lsd.cpp makes (CV_64F, 7 x 7, sigma 0.6 / 0.8)");
+        throw std::runtime_error("minicv: GaussianBlur is only provided for the calls lsd.cpp (CV_64F, 7 x 7, sigma 0.6 / 0.8) and binary_descriptor.cpp (CV_8U, 5 x 5, sigma 1) make");
     Mat out(src.rows, src.cols, CV_64FC1);
     lsd_orc_gaussian7(src.ptr<double>(), src.cols, src.rows, out.ptr<double>());
     dst.assign(out);
@@ -286,6 +376,16 @@ inline void GaussianBlur(InputArray src_, OutputArray dst, Size ksize, double si
 inline void resize(InputArray src_, OutputArray dst, Size dsize, double fx, double fy)
 {
     const Mat src = src_.getMat();
+    if (src.type() == CV_8UC1 && dsize.area() == 0) {
+        /* OctaveKeyLines shrinks the image for the NEXT octave after every octave, also after the last one (binary_descriptor.cpp:838):
+         * with numOfOctave_ = 1 the result is never read.  Sizes as cv::resize computes them, contents a plain 2 x 2 pick. */
+        const int dw = (int)std::lrint(src.cols * fx), dh = (int)std::lrint(src.rows * fy);
+        Mat out(dh, dw, CV_8UC1);
+        for (int y = 0; y < dh; y++)
+            for (int x = 0; x < dw; x++) out.data[(size_t)y * dw + x] = src.data[(size_t)std::min(src.rows - 1, (int)(y / fy)) * src.cols + std::min(src.cols - 1, (int)(x / fx))];
+        dst.assign(out);
+        return;
+    }
     if (src.type() != CV_64FC1 || dsize.area() != 0 || fx != fy) throw std::runtime_error("minicv: resize is only provided for the call lsd.cpp makes");
     /* cv::resize: dsize = Size(saturate_cast<int>(cols * fx), saturate_cast<int>(rows * fy)), saturate_cast<int>(double) = lrint */
     const int dw = (int)std::lrint(src.cols * fx), dh = (int)std::lrint(src.rows * fy);
@@ -294,6 +394,96 @@ inline void resize(InputArray src_, OutputArray dst, Size dsize, double fx, doub
     lsd_orc_resize(src.ptr<double>(), src.cols, src.rows, fx, out.ptr<double>(), &ow, &oh);
     if (ow != dw || oh != dh) throw std::runtime_error("minicv: resize size mismatch");
     dst.assign(out);
+}
+
+/* ---- what EDLineDetector::EdgeDrawing and the line fit call (binary_descriptor.cpp:1617-1629, 2652-2655, 2743-2749), on the types they call
+ * it with; integer semantics as OpenCV defines them (saturate_cast, cvRound = round half to even, BORDER_REFLECT_101) */
+inline int reflect101_(int p, int n)
+{
+    if (n == 1) return 0;
+    while (p < 0 || p >= n) p = (p < 0) ? -p : 2 * n - 2 - p;
+    return p;
+}
+inline short sat16_(int v) { return (short)(v < -32768 ? -32768 : (v > 32767 ? 32767 : v)); }
+inline void Sobel(InputArray src_, OutputArray dst, int ddepth, int dx, int dy, int ksize)
+{
+    const Mat src = src_.getMat();
+    if (src.type() != CV_8UC1 || (ddepth & 7) != CV_16S || ksize != 3 || dx + dy != 1) throw std::runtime_error("minicv: Sobel is only provided for 8-bit -> 16-bit, 3 x 3, first order");
+    const int w = src.cols, h = src.rows;
+    Mat out(h, w, CV_16SC1);
+    for (int y = 0; y < h; y++)
+        for (int x = 0; x < w; x++) {
+            auto px = [&](int yy, int xx) { return (int)src.data[(size_t)reflect101_(yy, h) * w + reflect101_(xx, w)]; };
+            int v;
+            if (dx == 1)
+                v = (px(y - 1, x + 1) - px(y - 1, x - 1)) + 2 * (px(y, x + 1) - px(y, x - 1)) + (px(y + 1, x + 1) - px(y + 1, x - 1));
+            else
+                v = (px(y + 1, x - 1) - px(y - 1, x - 1)) + 2 * (px(y + 1, x) - px(y - 1, x)) + (px(y + 1, x + 1) - px(y - 1, x + 1));
+            out.ptr<short>()[(size_t)y * w + x] = sat16_(v);
+        }
+    dst.assign(out);
+}
+inline Mat abs(const Mat &a)
+{
+    if (a.type() != CV_16SC1) throw std::runtime_error("minicv: abs is only provided for 16-bit");
+    Mat o(a.rows, a.cols, CV_16SC1);
+    for (size_t i = 0; i < a.total(); i++) o.ptr<short>()[i] = sat16_(std::abs((int)a.ptr<short>()[i]));
+    return o;
+}
+inline void add(InputArray a_, InputArray b_, OutputArray dst)
+{
+    const Mat a = a_.getMat(), b = b_.getMat();
+    if (a.type() != CV_16SC1 || b.type() != CV_16SC1 || a.size() != b.size()) throw std::runtime_error("minicv: add is only provided for 16-bit");
+    Mat o(a.rows, a.cols, CV_16SC1);
+    for (size_t i = 0; i < a.total(); i++) o.ptr<short>()[i] = sat16_((int)a.ptr<short>()[i] + (int)b.ptr<short>()[i]);
+    dst.assign(o);
+}
+inline double threshold(InputArray src_, OutputArray dst, double thresh, double, int type)
+{
+    const Mat a = src_.getMat();
+    if (a.type() != CV_16SC1 || type != THRESH_TOZERO) throw std::runtime_error("minicv: threshold is only provided for 16-bit THRESH_TOZERO");
+    const int ith = (int)std::floor(thresh); /* the integer types compare against cvFloor(thresh) */
+    Mat o(a.rows, a.cols, CV_16SC1);
+    for (size_t i = 0; i < a.total(); i++) o.ptr<short>()[i] = a.ptr<short>()[i] > ith ? a.ptr<short>()[i] : (short)0;
+    dst.assign(o);
+    return thresh;
+}
+inline void compare(InputArray a_, InputArray b_, OutputArray dst, int op)
+{
+    const Mat a = a_.getMat(), b = b_.getMat();
+    if (a.type() != CV_16SC1 || b.type() != CV_16SC1 || op != CMP_LT) throw std::runtime_error("minicv: compare is only provided for 16-bit CMP_LT");
+    Mat o(a.rows, a.cols, CV_8UC1);
+    for (size_t i = 0; i < a.total(); i++) o.data[i] = a.ptr<short>()[i] < b.ptr<short>()[i] ? 255 : 0;
+    dst.assign(o);
+}
+/* Mat / s on 16-bit: a scaled conversion, saturate_cast<short>(v * (1 / s)) with round-half-to-even */
+inline Mat operator/(const Mat &a, int s)
+{
+    if (a.type() != CV_16SC1) throw std::runtime_error("minicv: Mat / int is only provided for 16-bit");
+    Mat o(a.rows, a.cols, CV_16SC1);
+    const double alpha = 1.0 / s;
+    for (size_t i = 0; i < a.total(); i++) o.ptr<short>()[i] = sat16_((int)std::nearbyint(a.ptr<short>()[i] * alpha));
+    return o;
+}
+/* float matrix product: double accumulators, rounded to float once (cv::gemm's float path) */
+inline Mat operator*(const Mat &a, const Mat &b)
+{
+    if (a.type() != CV_32FC1 || b.type() != CV_32FC1 || a.cols != b.rows) throw std::runtime_error("minicv: Mat * Mat is only provided for float matrices");
+    Mat o(a.rows, b.cols, CV_32FC1);
+    for (int r = 0; r < a.rows; r++)
+        for (int c = 0; c < b.cols; c++) {
+            double acc = 0;
+            for (int k = 0; k < a.cols; k++) acc += (double)a.ptr<float>()[(size_t)r * a.cols + k] * (double)b.ptr<float>()[(size_t)k * b.cols + c];
+            o.ptr<float>()[(size_t)r * b.cols + c] = (float)acc;
+        }
+    return o;
+}
+inline Mat operator+(const Mat &a, const Mat &b)
+{
+    if (a.type() != CV_32FC1 || b.type() != CV_32FC1 || a.size() != b.size()) throw std::runtime_error("minicv: Mat + Mat is only provided for float matrices");
+    Mat o(a.rows, a.cols, CV_32FC1);
+    for (size_t i = 0; i < a.total(); i++) o.ptr<float>()[i] = a.ptr<float>()[i] + b.ptr<float>()[i];
+    return o;
 }
 
 /* drawing helpers referenced by LineSegmentDetectorImpl::drawSegments / compareSegments, which the path never calls */
@@ -307,6 +497,7 @@ inline void merge(const std::vector<Mat> &, OutputArray) { minicv_unreachable("m
 template <typename P> inline void line(InputOutputArray, P, P, const Scalar &, int) { minicv_unreachable("line"); }
 inline void bitwise_xor(InputArray, InputArray, OutputArray) { minicv_unreachable("bitwise_xor"); }
 inline int countNonZero(InputArray) { minicv_unreachable("countNonZero"); }
+template <typename... A> inline void pyrDown(InputArray, OutputArray, A...) { minicv_unreachable("pyrDown"); } /* BinaryDescriptor::computeGaussianPyramid: the descriptor side */
 
 }  // namespace cv
 #endif /* ORC_MINICV_HPP */

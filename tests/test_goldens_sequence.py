@@ -44,6 +44,9 @@ def test_oracle_reproduces_the_fixture_b_goldens(oracle, fixture_b):
         assert len(lines) == e["n_lines"] and _checksum(lines) == e["lines_checksum"]
         # the raw segments of the reference's own lsd.cpp, recorded when the golden was made (oracle/_ref): pins the oracle to the reference
         assert len(res["raw_lines"]) == e["n_raw_ref"] and _checksum(res["raw_lines"]) == e["raw_checksum_ref"]
+        edl = oracle.edl_detect(img, 15.0)   # the EDLines flavour against the reference's own binary_descriptor.cpp, the same way
+        assert len(edl["raw_lines"]) == e["edl_n_raw_ref"] and _checksum(edl["raw_lines"]) == e["edl_raw_checksum_ref"]
+        assert len(edl["lines"]) == e["edl_n_lines"] and _checksum(edl["lines"]) == e["edl_lines_checksum"]
         for mode, kw in MODES.items():
             if mode != "default" and i % 6:
                 continue
@@ -66,6 +69,8 @@ def test_oracle_reproduces_the_synthetic_goldens(oracle):
             lines = res["lines"]
             assert len(lines) == e["n_lines"] and _checksum(lines) == e["lines_checksum"]
             assert len(res["raw_lines"]) == e["n_raw_ref"] and _checksum(res["raw_lines"]) == e["raw_checksum_ref"]
+            edl = oracle.edl_detect(imgs[f], 15.0)
+            assert len(edl["raw_lines"]) == e["edl_n_raw_ref"] and _checksum(edl["raw_lines"]) == e["edl_raw_checksum_ref"]
             r = oracle.detect_cuboid(imgs[f], K, Ts[f], boxes[f], lines.astype(np.float64), oracle.default_params(nominal_skew_ratio=2.0))
             em = e["modes"]["default"]
             assert (r["n_candidates"], r["n_valid"]) == (em["n_candidates"], em["n_valid"])
@@ -93,6 +98,12 @@ def test_cuda_path_reproduces_the_fixture_b_goldens(fixture_b, mode):
         assert len(lines[i]) == exp["frames"][i]["n_lines"] and _checksum(lines[i]) == exp["frames"][i]["lines_checksum"], i
     p = cs.default_params(nominal_skew_ratio=2.0, **MODES[mode])
     out, counts = ctx.detect_frames_host(imgs, np.stack([fixture_b["T"]] * F), boxes, det.params(), p)
+    if mode == "default":   # the EDLines flavour of the line stage against the same goldens
+        det.use_LSD = False
+        elines = det.detect_filter_lines_batch(imgs)
+        for i in range(F):
+            assert len(elines[i]) == exp["frames"][i]["edl_n_lines"] and _checksum(elines[i]) == exp["frames"][i]["edl_lines_checksum"], i
+        det.use_LSD = True
     o = 0
     for i in range(F):
         for b, want in enumerate(exp["frames"][i]["modes"][mode]["boxes"]):
@@ -121,6 +132,10 @@ def test_cuda_path_reproduces_the_synthetic_goldens():
         for f in range(4):
             assert len(lines[f]) == case["frames"][f]["n_lines"] and _checksum(lines[f]) == case["frames"][f]["lines_checksum"], (case["seed"], f)
         out, counts = ctx.detect_frames_host(imgs, Ts, boxes, det.params(), cs.default_params(nominal_skew_ratio=2.0))
+        det.use_LSD = False
+        elines = det.detect_filter_lines_batch(imgs)
+        for f in range(4):
+            assert len(elines[f]) == case["frames"][f]["edl_n_lines"] and _checksum(elines[f]) == case["frames"][f]["edl_lines_checksum"], (case["seed"], f)
         o = 0
         for f in range(4):
             for want in case["frames"][f]["modes"]["default"]["boxes"]:

@@ -2,7 +2,8 @@
 # A/B of environment-selected kernel variants inside ONE GPU-box session (boxes differ by a few per cent, so only same-box numbers compare).
 # usage: tools/ab_bench.sh "<ENV=.. ENV=..>" "<...>" ...   prints ms/step of the headline path and the e2e figure per variant
 for v in "$@"; do
-  env $v timeout 300 python bench.py --steps 48 --warmup 3 --inflight 16 --no-configs --no-cpu --no-extra > /tmp/ab.json 2>/tmp/ab.err
+  AB_INFLIGHT=$(echo "$v" | sed -n 's/.*AB_INFLIGHT=\([0-9]*\).*/\1/p'); AB_INFLIGHT=${AB_INFLIGHT:-16}
+  env $v timeout 300 python bench.py --steps 48 --warmup 3 --inflight ${AB_INFLIGHT:-16} --no-configs --no-cpu --no-extra > /tmp/ab.json 2>/tmp/ab.err
   python - "$v" <<'PY'
 import json, sys
 try:

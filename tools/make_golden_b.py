@@ -4,8 +4,9 @@
 
     python tools/make_golden_b.py
 
-Needs oracle/_ref/liblsd_ref.so (the reference's lsd.cpp compiled where /root/reference exists): the raw LSD segments recorded here
-(`n_raw_ref`, `raw_checksum_ref`) are the REFERENCE's output, so the committed file pins the oracle to the reference wherever the tests
+Needs oracle/_ref/liblsd_ref.so and libedl_ref.so (the reference's lsd.cpp and binary_descriptor.cpp compiled where /root/reference exists):
+the raw LSD segments (`n_raw_ref`, `raw_checksum_ref`) and raw EDLines key lines (`edl_n_raw_ref`, `edl_raw_checksum_ref`) recorded here
+are the REFERENCE's output, so the committed file pins the oracle to the reference wherever the tests
 run.  Per frame and mode: LSD segment count and a checksum of the segments, candidates, valid proposals, and per box the best cuboid
 (proposal index, normalised error, position, yaw, scale).  Modes: default, and 5 x 5 camera roll / pitch sampling
 (whether_sample_cam_roll_pitch).  object_slam's own settings: length threshold 15, nominal_skew_ratio 2 (main_obj.cpp:359-366)."""
@@ -42,8 +43,14 @@ def frame_record(img, K, T, boxes, modes):
     ref_raw = O.ref_lsd_detect(img)
     if not np.array_equal(ref_raw, res["raw_lines"]):
         raise SystemExit("oracle LSD differs from the reference's lsd.cpp on this frame: fix the oracle first")
+    # the EDLines flavour (use_LSD = false) the same way: the reference's own binary_descriptor.cpp (oracle/_ref/libedl_ref.so)
+    edl = O.edl_detect(img, 15.0)
+    ref_edl = O.ref_edl_detect(img)
+    if not np.array_equal(ref_edl, edl["raw_lines"]):
+        raise SystemExit("oracle EDLines differs from the reference's binary_descriptor.cpp on this frame: fix the oracle first")
     rec = dict(n_lines=int(len(lines)), lines_checksum=seg_checksum(lines), n_raw_ref=int(len(ref_raw)), raw_checksum_ref=seg_checksum(ref_raw),
-               modes={})
+               edl_n_lines=int(len(edl["lines"])), edl_lines_checksum=seg_checksum(edl["lines"]), edl_n_raw_ref=int(len(ref_edl)),
+               edl_raw_checksum_ref=seg_checksum(ref_edl), modes={})
     for name, kw in modes:
         r = O.detect_cuboid(img, K, T, boxes, lines.astype(np.float64), O.default_params(nominal_skew_ratio=2.0, **kw))
         rec["modes"][name] = dict(n_candidates=int(r["n_candidates"]), n_valid=int(r["n_valid"]),
