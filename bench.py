@@ -193,6 +193,27 @@ def cpu_run(wl, n_frames, n_threads, line_mode=1):
     return dt, int(r["n_valid"].sum()), int(r["n_cand"].sum()), int(r["n_lines"].sum())
 
 
+def lsd_reference_vs_port(wl, n=4):
+    """One core, the first n frames: the reference's own lsd.cpp (oracle/_ref/liblsd_ref.so, compiled from the reference where that
+    exists) beside the oracle's restatement of it, which the batch driver of the CPU arm runs.  Same segments (tests); ms per frame."""
+    from oracle import pyoracle as O
+    if not O.ref_lsd_available():
+        return None
+    frames = [np.ascontiguousarray(O.bgr2gray(wl["imgs"][i])) for i in range(min(n, wl["F"]))]
+    O.ref_lsd_detect(frames[0])
+    O.lsd_detect(frames[0], LINE_LENGTH_THRES)
+    t0 = time.perf_counter()
+    for g in frames:
+        O.ref_lsd_detect(g)
+    t1 = time.perf_counter()
+    for g in frames:
+        O.lsd_detect(g, LINE_LENGTH_THRES)
+    t2 = time.perf_counter()
+    return {"reference_lsd_cpp_ms_per_frame": 1e3 * (t1 - t0) / len(frames), "port_ms_per_frame": 1e3 * (t2 - t1) / len(frames), "frames": len(frames),
+            "note": "createLineSegmentDetector(LSD_REFINE_ADV)->detect on the gray frame, one core; the reference's lsd.cpp compiled against "
+                    "oracle/ref/minicv.hpp vs the oracle port the CPU arm runs"}
+
+
 def run_reference_arm(args, rank, world):
     if rank != 0:
         return
@@ -227,11 +248,12 @@ def run_reference_arm(args, rank, world):
         "dtype": "f64", "data": "synthetic", "frames_per_s": fps, "candidates_per_s": tot_c / tot_t,
         "config": {"workload": wl["desc"], "lines": "detected per frame by the LSD flavour of line_lbd (the north-star path)",
                    "sample_frames_per_step": n, "segments_per_frame_M": tot_l / (n * args.steps),
-                   "note": "CPU oracle port of the reference algorithm (the reference itself needs Eigen/OpenCV C++/ROS and cannot be "
-                           "compiled on this image); oracle/batch_oracle.cpp, one frame per loop iteration, static schedule, openmp=%d" % O.lib().orc_has_openmp()},
+                   "note": "CPU oracle port of the reference algorithm (detect_3d_cuboid needs Eigen/OpenCV C++/ROS and cannot be compiled on this "
+                           "image; the reference's lsd.cpp and binary_descriptor.cpp do compile, pin the port byte for byte, and the LSD is timed "
+                           "beside the port under cpu_baseline.lsd_stage_one_core); oracle/batch_oracle.cpp, one frame per loop iteration, static schedule, openmp=%d" % O.lib().orc_has_openmp()},
         "cpu_baseline": {"value": val, "unit": "proposals/s", "cores": threads, "physical_cores": phys, "logical_cpus": os.cpu_count(),
                          "cgroup_cpu_quota": cpu_quota(), "cpu": cpu_model(), "kind": "port", "one_core_frames_per_s": 1.0 / per_frame,
-                         "scaling_vs_one_core": fps * per_frame,
+                         "scaling_vs_one_core": fps * per_frame, "lsd_stage_one_core": lsd_reference_vs_port(wl),
                          "sample": "%d of %d frames per step, line detection + detect_cuboid per frame, %d threads" % (n, wl["F"], threads)},
         "e2e": {"value": val, "unit": "proposals/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -605,7 +627,7 @@ def run_ours(args, rank, world, local_rank):
         cpu = {"value": v / dt, "unit": "proposals/s", "cores": threads, "physical_cores": phys, "logical_cpus": os.cpu_count(), "cgroup_cpu_quota": cpu_quota(),
                "cpu": cpu_model(), "kind": "port", "frames_per_s": n / dt, "one_core_value": v1 / dt1, "one_core_frames_per_s": 1.0 / per_frame,
                "scaling_vs_one_core": (v / dt) / (v1 / dt1), "frames_per_s_by_threads": {str(t): n / r[0] for t, r in tried.items()},
-               "openmp": int(O.lib().orc_has_openmp()),
+               "openmp": int(O.lib().orc_has_openmp()), "lsd_stage_one_core": lsd_reference_vs_port(wl),
                "sample": "%d of %d frames of this workload, LSD line detection + detect_cuboid per frame, static schedule, %d threads (the best of %s; "
                          "the box caps the process at %s CPUs' worth of time)" % (n, F, threads, sorted(tried), cpu_quota())}
 
@@ -647,7 +669,7 @@ def main():
     ap.add_argument("--no-prio", action="store_true", help="A/B: keep each batch's whole chain on one stream (no high-priority tail)")
     ap.add_argument("--raster-dt", action="store_true", help="A/B: two-pass raster-scan distance transform kernel instead of the cone form")
     ap.add_argument("--seq-lines", action="store_true", help="A/B: the line detectors' sequential kernels (one warp per frame) instead of ordered speculation")
-    ap.add_argument("--inflight", type=int, default=12, help="batches in flight on one GPU (contexts driven round-robin)")
+    ap.add_argument("--inflight", type=int, default=24, help="batches in flight on one GPU (contexts driven round-robin)")
     args = ap.parse_args()
     if args.steps is None:
         args.steps = 300 if args.impl == "ours" else 3

@@ -122,6 +122,7 @@ class Mat {
 public:
     int rows, cols;
     uchar *data;
+    size_t step = 0; /* bytes per row (always continuous here) */
     Mat() : rows(0), cols(0), data(nullptr), type_(CV_8UC1) {}
     Mat(int r, int c, int type) : rows(0), cols(0), data(nullptr), type_(type) { create(r, c, type); }
     explicit Mat(const std::vector<Vec4f> &v) : rows(0), cols(0), data(nullptr), type_(CV_32FC4)
@@ -142,6 +143,7 @@ public:
         type_ = type;
         store_ = std::make_shared<std::vector<uchar>>((size_t)r * c * elemSize() + 64, 0);
         data = store_->data();
+        step = (size_t)c * elemSize();
     }
     void create(Size s, int type) { create(s.height, s.width, type); }
     bool empty() const { return data == nullptr || rows * cols == 0; }

@@ -27,3 +27,19 @@ def test_shim_translation_unit_compiles(name, tmp_path):
     r = subprocess.run([cxx, "-std=c++14", "-Wall", "-c", src, "-o", out] + inc, capture_output=True, text=True)
     assert r.returncode == 0, r.stderr
     assert os.path.getsize(out) > 0
+
+
+def test_line_shim_body_compiles_against_the_reference_class_header(tmp_path):
+    """Where the reference checkout exists, the line shim's BODY is compiled too: against the reference's own line_lbd_allclass.h, with
+    oracle/ref/fakecv (-> minicv.hpp) standing in for the OpenCV headers this image lacks.  The object must define the three members the
+    shim takes over from line_lbd_allclass.cpp."""
+    ref_inc = "/root/reference/line_lbd/include"
+    cxx = shutil.which("g++")
+    if not cxx or not os.path.isdir(ref_inc):
+        pytest.skip("needs g++ and the reference checkout")
+    out = str(tmp_path / "line_shim.o")
+    r = subprocess.run([cxx, "-std=c++14", "-Wall", "-c", os.path.join(ROOT, "shim", "line_lbd_b200.cpp"), "-o", out, "-I", os.path.join(ROOT, "include"),
+                        "-I", os.path.join(ROOT, "oracle", "ref", "fakecv"), "-I", ref_inc], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    syms = subprocess.run(["nm", "-C", out], capture_output=True, text=True).stdout
+    assert syms.count("line_lbd_detect::detect_filter_lines(") == 2 and "line_lbd_detect::detect_raw_lines(" in syms
