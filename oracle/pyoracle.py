@@ -19,7 +19,7 @@ def build(force=False):
     fresh = os.path.exists(_LIB_PATH) and all(os.path.getmtime(_LIB_PATH) >= os.path.getmtime(s) for s in srcs)
     # oracle/_ref (the reference's own lsd.cpp) is built where the reference checkout exists; elsewhere the prebuilt file is used as it is
     ref_src = "/root/reference/line_lbd/libs/lsd.cpp"
-    ref_libs = [os.path.join(_HERE, "_ref", "liblsd_ref.so"), os.path.join(_HERE, "_ref", "libedl_ref.so")]
+    ref_libs = [os.path.join(_HERE, "_ref", n) for n in ("liblsd_ref.so", "libedl_ref.so", "liblinelbd_ref.so")]
     if os.path.exists(ref_src):
         deps = [ref_src, _LIB_PATH] + [os.path.join(_HERE, "ref", f) for f in os.listdir(os.path.join(_HERE, "ref")) if f.endswith((".cpp", ".hpp"))]
         fresh = fresh and all(os.path.exists(r) and all(os.path.getmtime(r) >= os.path.getmtime(d) for d in deps) for r in ref_libs)
@@ -327,6 +327,33 @@ def ref_edl_detect(img, cap=8192):
     n = _REF_EDL.ref_edl_detect(_p(gray, C.c_uint8), gray.shape[1], gray.shape[0], _p(out, C.c_float), cap)
     if n < 0:
         raise RuntimeError("ref_edl_detect failed")
+    return out[:min(n, cap)].copy()
+
+
+_REF_ALL = None
+_REF_ALL_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_ref", "liblinelbd_ref.so")
+
+
+def ref_detect_filter_lines_available():
+    return os.path.exists(_REF_ALL_PATH)
+
+
+def ref_detect_filter_lines(img, use_LSD=True, line_length_thres=50.0, cap=8192):
+    """The reference's OWN line_lbd_detect::detect_filter_lines(image, lines_mat), whole (oracle/_ref/liblinelbd_ref.so: lsd.cpp,
+    LSDDetector.cpp, binary_descriptor.cpp and line_lbd_allclass.cpp compiled from /root/reference, see oracle/ref/linelbd_ref.cpp), called
+    as object_slam/src/main_obj.cpp:363-366,428 calls it -> the n x 4 CV_32F matrix as float32.  img: gray or BGR."""
+    global _REF_ALL
+    lib()
+    if _REF_ALL is None:
+        _REF_ALL = C.CDLL(_REF_ALL_PATH)
+        _REF_ALL.ref_detect_filter_lines.restype = C.c_int
+    img = np.ascontiguousarray(img, np.uint8)
+    h, w = img.shape[:2]
+    ch = 1 if img.ndim == 2 else img.shape[2]
+    out = np.zeros((cap, 4), np.float32)
+    n = _REF_ALL.ref_detect_filter_lines(_p(img, C.c_uint8), w, h, ch, int(bool(use_LSD)), C.c_float(line_length_thres), _p(out, C.c_float), cap)
+    if n < 0:
+        raise RuntimeError("ref_detect_filter_lines failed (%d)" % n)
     return out[:min(n, cap)].copy()
 
 

@@ -31,6 +31,7 @@ extern "C" void lsd_orc_gaussian7(const double *src, int w, int h, double *dst);
 extern "C" void lsd_orc_resize(const double *src, int w, int h, double scale, double *dst, int *dw, int *dh);
 extern "C" float lsd_orc_fast_atan2(float y, float x);
 extern "C" void edl_orc_gaussian5_u8(const uint8_t *src, int w, int h, uint8_t *dst);
+extern "C" void orc_bgr2gray(const uint8_t *bgr, int w, int h, int stride, uint8_t *gray, int gstride, int fixed15);
 
 #define CV_PI 3.1415926535897932384626433832795
 #define CV_EXPORTS
@@ -125,6 +126,30 @@ public:
     size_t step = 0; /* bytes per row (always continuous here) */
     Mat() : rows(0), cols(0), data(nullptr), type_(CV_8UC1) {}
     Mat(int r, int c, int type) : rows(0), cols(0), data(nullptr), type_(type) { create(r, c, type); }
+    Mat(Size s, int type, const Scalar &v) : rows(0), cols(0), data(nullptr), type_(type)
+    {
+        create(s.height, s.width, type);
+        if (v.val[0] != 0) throw std::runtime_error("minicv: Mat(size, type, value) is provided for 0 only");
+    }
+    /* one row as a matrix of its own, and appending rows: the LBD descriptor helpers of line_lbd_allclass.cpp (outside the cuboid path) */
+    Mat row(int r) const
+    {
+        Mat m(1, cols, type_);
+        memcpy(m.data, ptr(r), (size_t)cols * elemSize());
+        return m;
+    }
+    void push_back(const Mat &m)
+    {
+        if (empty()) {
+            *this = m.clone();
+            return;
+        }
+        if (m.cols != cols || m.type() != type_) throw std::runtime_error("minicv: push_back of a different row type");
+        Mat o(rows + m.rows, cols, type_);
+        memcpy(o.data, data, total() * elemSize());
+        memcpy(o.data + total() * elemSize(), m.data, m.total() * m.elemSize());
+        *this = o;
+    }
     explicit Mat(const std::vector<Vec4f> &v) : rows(0), cols(0), data(nullptr), type_(CV_32FC4)
     {
         create((int)v.size(), 1, CV_32FC4);
@@ -357,6 +382,21 @@ template <typename T, typename... A> Ptr<T> makePtr(A &&...a) { return std::make
 using std::max;
 using std::min;
 
+/* cv::LineIterator as the KeyLine fill uses it: only `count`, the number of pixels of the 8-connected line between the two points (rounded
+ * to pixels, clipped to the image by moving an outside end point onto the border).  KeyLine::numOfPixels feeds the LBD descriptor only;
+ * nothing on the cuboid path reads it and no test compares it. */
+class LineIterator {
+public:
+    int count;
+    LineIterator(const Mat &img, Point2f p1, Point2f p2)
+    {
+        auto clampi = [](long v, int n) { return (int)(v < 0 ? 0 : (v >= n ? n - 1 : v)); };
+        const int x1 = clampi(std::lrint(p1.x), img.cols), y1 = clampi(std::lrint(p1.y), img.rows);
+        const int x2 = clampi(std::lrint(p2.x), img.cols), y2 = clampi(std::lrint(p2.y), img.rows);
+        count = std::max(std::abs(x2 - x1), std::abs(y2 - y1)) + 1;
+    }
+};
+
 /* the three primitives of the LSD path: forwarded to the oracle's cv2-pinned restatements (see the header) */
 inline float fastAtan2(float y, float x) { return lsd_orc_fast_atan2(y, x); }
 inline void GaussianBlur(InputArray src_, OutputArray dst, Size ksize, double sigma)
@@ -494,7 +534,16 @@ inline Mat operator+(const Mat &a, const Mat &b)
     fprintf(stderr, "minicv: %s is not provided (the line-detection path does not call it)\n", what);
     abort();
 }
-inline void cvtColor(InputArray, OutputArray, int) { minicv_unreachable("cvtColor"); }
+inline void cvtColor(InputArray src_, OutputArray dst, int code)
+{
+    /* LSDDetector::detectImpl / BinaryDescriptor::detectImpl convert a colour input themselves (LSDDetector.cpp:165-168,
+     * binary_descriptor.cpp:487-490): OpenCV's 15-bit fixed-point BGR -> gray, the oracle's cv2-pinned restatement */
+    const Mat src = src_.getMat();
+    if (code != COLOR_BGR2GRAY || src.type() != CV_8UC3) minicv_unreachable("cvtColor other than 8-bit BGR2GRAY");
+    Mat out(src.rows, src.cols, CV_8UC1);
+    orc_bgr2gray(src.data, src.cols, src.rows, src.cols * 3, out.data, src.cols, 1);
+    dst.assign(out);
+}
 inline void merge(const std::vector<Mat> &, OutputArray) { minicv_unreachable("merge"); }
 template <typename P> inline void line(InputOutputArray, P, P, const Scalar &, int) { minicv_unreachable("line"); }
 inline void bitwise_xor(InputArray, InputArray, OutputArray) { minicv_unreachable("bitwise_xor"); }

@@ -48,6 +48,11 @@ def frame_record(img, K, T, boxes, modes):
     ref_edl = O.ref_edl_detect(img)
     if not np.array_equal(ref_edl, edl["raw_lines"]):
         raise SystemExit("oracle EDLines differs from the reference's binary_descriptor.cpp on this frame: fix the oracle first")
+    # ... and the whole function, line_lbd_detect::detect_filter_lines as the reference's class computes it (oracle/_ref/liblinelbd_ref.so):
+    # the recorded `lines_checksum` / `edl_lines_checksum` ARE the reference's output
+    for use_lsd, got in ((True, lines), (False, edl["lines"])):
+        if not np.array_equal(O.ref_detect_filter_lines(img, use_lsd, 15.0), got):
+            raise SystemExit("oracle detect_filter_lines differs from the reference's on this frame: fix the oracle first")
     rec = dict(n_lines=int(len(lines)), lines_checksum=seg_checksum(lines), n_raw_ref=int(len(ref_raw)), raw_checksum_ref=seg_checksum(ref_raw),
                edl_n_lines=int(len(edl["lines"])), edl_lines_checksum=seg_checksum(edl["lines"]), edl_n_raw_ref=int(len(ref_edl)),
                edl_raw_checksum_ref=seg_checksum(ref_edl), modes={})
