@@ -214,28 +214,45 @@ def lsd_reference_vs_port(wl, n=4):
                     "oracle/ref/minicv.hpp vs the oracle port the CPU arm runs"}
 
 
+def cpu_line_mode():
+    """3 = stage (i) by the reference's own detect_filter_lines (oracle/_ref/liblinelbd_ref.so, compiled from the reference's sources where
+    that checkout existed), stage (ii) by the oracle port; 1 = the oracle port for both (the reference library is not there)."""
+    from oracle import pyoracle as O
+    return 3 if O.lib().orc_reference_lines_available() else 1
+
+
+CPU_KIND = {3: "reference", 1: "port"}
+CPU_KIND_NOTE = {
+    3: "stage (i), line_lbd_detect::detect_filter_lines: the reference's OWN code (lsd.cpp, LSDDetector.cpp, binary_descriptor.cpp, line_lbd_allclass.cpp "
+       "compiled from its sources against oracle/ref/minicv.hpp, oracle/_ref/liblinelbd_ref.so); stage (ii), detect_cuboid: the oracle port "
+       "(detect_3d_cuboid needs Eigen, which this image does not have)",
+    1: "CPU oracle port of the reference algorithm for both stages (oracle/_ref was not built: no reference checkout at build time)"}
+
+
 def run_reference_arm(args, rank, world):
     if rank != 0:
         return
     from oracle import pyoracle as O
     wl = make_workload(args.workload, 0)
     phys = physical_cores()
-    dt1, _, _, _ = cpu_run(wl, min(wl["F"], 2), 1)
+    mode = cpu_line_mode()
+    dt1, _, _, _ = cpu_run(wl, min(wl["F"], 2), 1, mode)
     per_frame = dt1 / min(wl["F"], 2)
     n = int(max(1, min(wl["F"], 4.0 * phys / max(per_frame, 1e-4))))  # about 4 s of wall clock per step at most
     # all the host threads the process can use: the best of the candidate thread counts (cgroup quota aware), measured
     best = None
     for th in cpu_thread_choices():
-        cpu_run(wl, n, th)  # the same frames on the same threads: warms every thread's malloc arena
-        dt = cpu_run(wl, n, th)[0]
+        cpu_run(wl, n, th, mode)  # the same frames on the same threads: warms every thread's malloc arena
+        dt = cpu_run(wl, n, th, mode)[0]
         if best is None or dt < best[0]:
             best = (dt, th)
     threads = best[1]
     for _ in range(max(0, min(args.warmup, 2) - 1)):
-        cpu_run(wl, n, threads)
+        cpu_run(wl, n, threads, mode)
+    port_dt = cpu_run(wl, n, threads, 1)[0] if mode != 1 else None  # the all-port arm on the same frames and threads, for the record
     tot_t = tot_v = tot_c = tot_l = 0.0
     for _ in range(args.steps):
-        dt, v, c, l = cpu_run(wl, n, threads)
+        dt, v, c, l = cpu_run(wl, n, threads, mode)
         tot_t += dt
         tot_v += v
         tot_c += c
@@ -248,11 +265,10 @@ def run_reference_arm(args, rank, world):
         "dtype": "f64", "data": "synthetic", "frames_per_s": fps, "candidates_per_s": tot_c / tot_t,
         "config": {"workload": wl["desc"], "lines": "detected per frame by the LSD flavour of line_lbd (the north-star path)",
                    "sample_frames_per_step": n, "segments_per_frame_M": tot_l / (n * args.steps),
-                   "note": "CPU oracle port of the reference algorithm (detect_3d_cuboid needs Eigen/OpenCV C++/ROS and cannot be compiled on this "
-                           "image; the reference's lsd.cpp and binary_descriptor.cpp do compile, pin the port byte for byte, and the LSD is timed "
-                           "beside the port under cpu_baseline.lsd_stage_one_core); oracle/batch_oracle.cpp, one frame per loop iteration, static schedule, openmp=%d" % O.lib().orc_has_openmp()},
+                   "note": CPU_KIND_NOTE[mode] + "; oracle/batch_oracle.cpp, one frame per loop iteration, static schedule, openmp=%d" % O.lib().orc_has_openmp()},
         "cpu_baseline": {"value": val, "unit": "proposals/s", "cores": threads, "physical_cores": phys, "logical_cpus": os.cpu_count(),
-                         "cgroup_cpu_quota": cpu_quota(), "cpu": cpu_model(), "kind": "port", "one_core_frames_per_s": 1.0 / per_frame,
+                         "cgroup_cpu_quota": cpu_quota(), "cpu": cpu_model(), "kind": CPU_KIND[mode], "kind_detail": CPU_KIND_NOTE[mode],
+                         "all_port_frames_per_s": (n / port_dt) if port_dt else None, "one_core_frames_per_s": 1.0 / per_frame,
                          "scaling_vs_one_core": fps * per_frame, "lsd_stage_one_core": lsd_reference_vs_port(wl),
                          "sample": "%d of %d frames per step, line detection + detect_cuboid per frame, %d threads" % (n, wl["F"], threads)},
         "e2e": {"value": val, "unit": "proposals/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -615,17 +631,20 @@ def run_ours(args, rank, world, local_rank):
     if world == 1 and not args.no_cpu:
         from oracle import pyoracle as O
         phys = physical_cores()
-        dt1, v1, _, _ = cpu_run(wl, min(F, 4), 1)
+        mode = cpu_line_mode()
+        dt1, v1, _, _ = cpu_run(wl, min(F, 4), 1, mode)
         per_frame = dt1 / min(F, 4)
         n = int(max(1, min(F, 10.0 * phys / max(per_frame, 1e-4))))
         tried = {}
         for th in cpu_thread_choices():
-            cpu_run(wl, n, th)  # warm-up on every thread
-            tried[th] = min((cpu_run(wl, n, th) for _ in range(2)), key=lambda r: r[0])
+            cpu_run(wl, n, th, mode)  # warm-up on every thread
+            tried[th] = min((cpu_run(wl, n, th, mode) for _ in range(2)), key=lambda r: r[0])
         threads = min(tried, key=lambda t: tried[t][0])
         dt, v, c, l = tried[threads]
+        port_dt = cpu_run(wl, n, threads, 1)[0] if mode != 1 else None
         cpu = {"value": v / dt, "unit": "proposals/s", "cores": threads, "physical_cores": phys, "logical_cpus": os.cpu_count(), "cgroup_cpu_quota": cpu_quota(),
-               "cpu": cpu_model(), "kind": "port", "frames_per_s": n / dt, "one_core_value": v1 / dt1, "one_core_frames_per_s": 1.0 / per_frame,
+               "cpu": cpu_model(), "kind": CPU_KIND[mode], "kind_detail": CPU_KIND_NOTE[mode], "all_port_frames_per_s": (n / port_dt) if port_dt else None,
+               "frames_per_s": n / dt, "one_core_value": v1 / dt1, "one_core_frames_per_s": 1.0 / per_frame,
                "scaling_vs_one_core": (v / dt) / (v1 / dt1), "frames_per_s_by_threads": {str(t): n / r[0] for t, r in tried.items()},
                "openmp": int(O.lib().orc_has_openmp()), "lsd_stage_one_core": lsd_reference_vs_port(wl),
                "sample": "%d of %d frames of this workload, LSD line detection + detect_cuboid per frame, static schedule, %d threads (the best of %s; "

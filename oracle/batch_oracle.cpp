@@ -8,12 +8,16 @@
  *   line_mode 0: segments are an input (the detect_cuboid entry point, how orb_object_slam feeds it, Tracking.cc:1583-1590)
  *   line_mode 1: LSD flavour of detect_filter_lines per frame (use_LSD = true, what object_slam sets, main_obj.cpp:365)
  *   line_mode 2: EDLines flavour (use_LSD = false, the class default, line_lbd_allclass.cpp:121)
+ *   line_mode 3 / 4: as 1 / 2, but stage (i) is executed by the REFERENCE'S OWN detect_filter_lines (oracle/_ref/liblinelbd_ref.so, compiled
+ *                    from /root/reference, looked up at run time next to this library); -3 when that library is not there
  */
+#include <dlfcn.h>
 #include <malloc.h>
 
 #include <cstdint>
 #include <cstring>
 #include <mutex>
+#include <string>
 #include <thread>
 #include <vector>
 
@@ -29,6 +33,23 @@ extern "C" int lsd_orc_detect(const uint8_t *img, int w, int h, int stride, int 
 extern "C" int edl_orc_detect(const uint8_t *img, int w, int h, int stride, int channels, float line_length_thres, float *lines_out, int cap,
                               float *raw_lines, int cap_raw, int *n_raw_out, uint8_t *blur_out, int16_t *dx_out, int16_t *dy_out,
                               int16_t *g_out, uint8_t *dir_out, int32_t *anchors_out, int *n_anchors_out, uint8_t *edge_out);
+
+typedef int (*ref_dfl_fn)(const uint8_t *img, int w, int h, int channels, int use_LSD, float line_length_thres, float *out, int cap);
+static ref_dfl_fn ref_detect_filter_lines_sym()
+{
+    static ref_dfl_fn fn = []() -> ref_dfl_fn {
+        Dl_info info;
+        if (!dladdr((void *)&lsd_orc_detect, &info) || !info.dli_fname) return nullptr;
+        std::string p(info.dli_fname); /* .../oracle/_build/liboracle.so -> .../oracle/_ref/liblinelbd_ref.so */
+        const size_t k = p.rfind("/_build/");
+        if (k == std::string::npos) return nullptr;
+        p = p.substr(0, k) + "/_ref/liblinelbd_ref.so";
+        void *h = dlopen(p.c_str(), RTLD_NOW | RTLD_GLOBAL);
+        return h ? (ref_dfl_fn)dlsym(h, "ref_detect_filter_lines") : nullptr;
+    }();
+    return fn;
+}
+extern "C" int orc_reference_lines_available(void) { return ref_detect_filter_lines_sym() ? 1 : 0; }
 
 extern "C" int orc_max_threads(void)
 {
@@ -49,6 +70,8 @@ extern "C" int orc_detect_frames_batch(const uint8_t *imgs, int n_frames, int w,
 {
     int status = 0;
     if (n_threads < 1) n_threads = 1;
+    const ref_dfl_fn ref_lines = (line_mode == 3 || line_mode == 4) ? ref_detect_filter_lines_sym() : nullptr;
+    if ((line_mode == 3 || line_mode == 4) && !ref_lines) return -3;
     {
         /* every frame allocates a dozen multi-megabyte images; glibc hands such blocks out with mmap / munmap, and on a many-core host the
          * page faults and address-space locking of a hundred threads doing that at once serialise the whole batch.  Keep the blocks in
@@ -72,7 +95,8 @@ extern "C" int orc_detect_frames_batch(const uint8_t *imgs, int n_frames, int w,
         } else {
             const int cap = 8192;
             std::vector<float> seg((size_t)cap * 4);
-            int n = (line_mode == 1) ? lsd_orc_detect(img, w, h, stride, channels, line_length_thres, seg.data(), cap, nullptr, 0, nullptr, nullptr,
+            int n = ref_lines ? (stride == w * channels ? ref_lines(img, w, h, channels, line_mode == 3, line_length_thres, seg.data(), cap) : -1)
+                    : (line_mode == 1) ? lsd_orc_detect(img, w, h, stride, channels, line_length_thres, seg.data(), cap, nullptr, 0, nullptr, nullptr,
                                                       nullptr, nullptr, nullptr, nullptr, 2)
                                      : edl_orc_detect(img, w, h, stride, channels, line_length_thres, seg.data(), cap, nullptr, 0, nullptr, nullptr, nullptr,
                                                       nullptr, nullptr, nullptr, nullptr, nullptr, nullptr);

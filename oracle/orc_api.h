@@ -8,7 +8,7 @@
  *
  * PARITY STATUS, per stage:
  *   line detection (stage i, both flavours): PINNED -- the reference's own lsd.cpp and binary_descriptor.cpp compile from
- *     /root/reference against a small OpenCV stand-in (oracle/ref/, oracle/_ref/*.so) and the restatements are byte-identical to them
+ *     /root/reference against a small OpenCV stand-in (oracle/ref/, oracle/_ref/) and the restatements are byte-identical to them
  *     (tests/test_oracle_ref_lsd.py, tests/test_oracle_ref_edlines.py, checksums in tests/golden/); the shipped LSD segment file is
  *     reproduced whole (tests/test_oracle_lines.py).
  *   cuboid proposals (stage ii): "parity unpinned" -- detect_3d_cuboid needs Eigen and OpenCV C++, neither is in this image, and the

@@ -33,12 +33,22 @@ void BinaryDescriptorMatcher::match(const Mat &, const Mat &, std::vector<DMatch
 }  // namespace line_descriptor
 }  // namespace cv
 
+/* The reference reports on std::cout on every call ("BinaryDescriptor line detector reset save octave lines ..."): the C++ stream of this
+ * process is switched off when the library loads, so that a host program's own stdout (bench.py prints one JSON line there) stays clean.
+ * Python's sys.stdout and C stdio are not affected. */
+namespace {
+struct SilenceCout {
+    SilenceCout() { std::cout.setstate(std::ios_base::failbit); }
+} silence_cout;
+}  // namespace
+
 /* img: h x w x channels bytes (1 or 3 channels, BGR).  out: room for cap rows [x1 y1 x2 y2].  Returns the number of rows of the n x 4 CV_32F
  * matrix detect_filter_lines produced (-1: exception, message on stderr). */
 extern "C" int ref_detect_filter_lines(const uint8_t *img, int w, int h, int channels, int use_LSD, float line_length_thres, float *out, int cap)
 {
     try {
-        line_lbd_detect det(1, 2.0f);
+        /* one detector object per host thread, constructed once (main_obj.cpp:363 constructs it once per run) */
+        thread_local line_lbd_detect det(1, 2.0f);
         det.use_LSD = use_LSD != 0;
         det.line_length_thres = line_length_thres;
         cv::Mat image(h, w, channels == 3 ? CV_8UC3 : CV_8UC1);
