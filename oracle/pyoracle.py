@@ -19,7 +19,7 @@ def build(force=False):
     fresh = os.path.exists(_LIB_PATH) and all(os.path.getmtime(_LIB_PATH) >= os.path.getmtime(s) for s in srcs)
     # oracle/_ref (the reference's own lsd.cpp) is built where the reference checkout exists; elsewhere the prebuilt file is used as it is
     ref_src = "/root/reference/line_lbd/libs/lsd.cpp"
-    ref_libs = [os.path.join(_HERE, "_ref", n) for n in ("liblsd_ref.so", "libedl_ref.so", "liblinelbd_ref.so")]
+    ref_libs = [os.path.join(_HERE, "_ref", n) for n in ("liblsd_ref.so", "libedl_ref.so", "liblinelbd_ref.so", "libcuboid_ref.so")]
     if os.path.exists(ref_src):
         deps = [ref_src, _LIB_PATH] + [os.path.join(_HERE, "ref", f) for f in os.listdir(os.path.join(_HERE, "ref")) if f.endswith((".cpp", ".hpp"))]
         fresh = fresh and all(os.path.exists(r) and all(os.path.getmtime(r) >= os.path.getmtime(d) for d in deps) for r in ref_libs)
@@ -355,6 +355,49 @@ def ref_detect_filter_lines(img, use_LSD=True, line_length_thres=50.0, cap=8192)
     if n < 0:
         raise RuntimeError("ref_detect_filter_lines failed (%d)" % n)
     return out[:min(n, cap)].copy()
+
+
+_REF_CUB = None
+_REF_CUB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_ref", "libcuboid_ref.so")
+REF_CUBOID_DTYPE = np.dtype([
+    ("pos", "f8", 3), ("rotY", "f8"), ("scale", "f8", 3), ("box_config_type", "f8", 2), ("box_corners_2d", "f8", (2, 8)),
+    ("box_corners_3d_world", "f8", (3, 8)), ("rect_detect_2d", "f8", 4), ("edge_distance_error", "f8"), ("edge_angle_error", "f8"),
+    ("normalized_error", "f8"), ("skew_ratio", "f8"), ("down_expand_height", "f8"), ("camera_roll_delta", "f8"), ("camera_pitch_delta", "f8")])
+assert REF_CUBOID_DTYPE.itemsize == 60 * 8
+
+
+def ref_detect_cuboid_available():
+    return os.path.exists(_REF_CUB_PATH)
+
+
+def ref_detect_cuboid(img, K, T_wc, boxes, lines, params=None, cap_per_box=8):
+    """The reference's OWN detect_3d_cuboid::detect_cuboid (detect_3d_cuboid/src/*.cpp compiled from /root/reference into
+    oracle/_ref/libcuboid_ref.so against oracle/ref/minieigen.hpp / minicv.hpp, see oracle/ref/cuboid_ref.cpp), driven as
+    object_slam/src/main_obj.cpp:354-361,449 drives it.  Returns a list (one entry per box) of REF_CUBOID_DTYPE arrays, best first."""
+    global _REF_CUB
+    lib()
+    if _REF_CUB is None:
+        _REF_CUB = C.CDLL(_REF_CUB_PATH)
+        _REF_CUB.ref_detect_cuboid.restype = C.c_int
+    if params is None:
+        params = default_params()
+    img = np.ascontiguousarray(img, np.uint8)
+    h, w = img.shape[:2]
+    ch = 1 if img.ndim == 2 else img.shape[2]
+    K = np.ascontiguousarray(K, np.float64).reshape(3, 3)
+    T_wc = np.ascontiguousarray(T_wc, np.float64).reshape(4, 4)
+    boxes = np.ascontiguousarray(boxes, np.float64).reshape(-1, 5)
+    lines = np.ascontiguousarray(lines, np.float64).reshape(-1, 4)
+    N = len(boxes)
+    flags = np.array([params.consider_config_1, params.consider_config_2, params.whether_sample_cam_roll_pitch, params.whether_sample_bbox_height], np.int32)
+    out = np.zeros((max(N, 1), cap_per_box), REF_CUBOID_DTYPE)
+    counts = np.zeros(max(N, 1), np.int32)
+    rc = _REF_CUB.ref_detect_cuboid(_p(img, C.c_uint8), w, h, ch, _p(K, C.c_double), _p(T_wc, C.c_double), _p(boxes, C.c_double), N,
+                                    _p(lines, C.c_double), len(lines), _p(flags, C.c_int32), C.c_double(params.nominal_skew_ratio),
+                                    int(params.max_cuboid_num), out.ctypes.data_as(C.POINTER(C.c_double)), cap_per_box, _p(counts, C.c_int32))
+    if rc != 0:
+        raise RuntimeError("ref_detect_cuboid failed (%d)" % rc)
+    return [out[b, :min(counts[b], cap_per_box)].copy() for b in range(N)]
 
 
 # ------------------------------------------------------------------------------------------- EDLines

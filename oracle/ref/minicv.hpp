@@ -31,6 +31,8 @@ extern "C" void lsd_orc_gaussian7(const double *src, int w, int h, double *dst);
 extern "C" void lsd_orc_resize(const double *src, int w, int h, double scale, double *dst, int *dw, int *dh);
 extern "C" float lsd_orc_fast_atan2(float y, float x);
 extern "C" void edl_orc_gaussian5_u8(const uint8_t *src, int w, int h, uint8_t *dst);
+extern "C" void orc_canny(const uint8_t *src, int w, int h, int stride, double low, double high, uint8_t *dst);
+extern "C" void orc_chamfer_dt(const uint8_t *edges, int w, int h, float *dist);
 extern "C" void orc_bgr2gray(const uint8_t *bgr, int w, int h, int stride, uint8_t *gray, int gstride, int fixed15);
 
 #define CV_PI 3.1415926535897932384626433832795
@@ -52,6 +54,8 @@ extern "C" void orc_bgr2gray(const uint8_t *bgr, int w, int h, int stride, uint8
 #define CV_32FC4 CV_MAKETYPE(CV_32F, 4)
 #define CV_64FC1 CV_MAKETYPE(CV_64F, 1)
 #define CV_BGR2GRAY 6
+#define CV_DIST_L2 2
+#define CV_AA 16
 #define CV_Assert(expr)                                                                     \
     do {                                                                                    \
         if (!(expr)) throw std::runtime_error(std::string("CV_Assert failed: ") + #expr);  \
@@ -90,6 +94,27 @@ struct Size {
     bool operator==(const Size &o) const { return width == o.width && height == o.height; }
     bool operator!=(const Size &o) const { return !(*this == o); }
 };
+
+template <typename T>
+struct Rect_ {
+    T x, y, width, height;
+    Rect_() : x(0), y(0), width(0), height(0) {}
+    Rect_(T x_, T y_, T w_, T h_) : x(x_), y(y_), width(w_), height(h_) {}
+    T area() const { return width * height; }
+    Point_<T> tl() const { return Point_<T>(x, y); }
+    Point_<T> br() const { return Point_<T>(x + width, y + height); }
+};
+template <typename T> Rect_<T> operator&(const Rect_<T> &a, const Rect_<T> &b)
+{
+    const T x1 = std::max(a.x, b.x), y1 = std::max(a.y, b.y), x2 = std::min(a.x + a.width, b.x + b.width), y2 = std::min(a.y + a.height, b.y + b.height);
+    return (x2 <= x1 || y2 <= y1) ? Rect_<T>() : Rect_<T>(x1, y1, x2 - x1, y2 - y1);
+}
+template <typename T> Rect_<T> operator|(const Rect_<T> &a, const Rect_<T> &b)
+{
+    const T x1 = std::min(a.x, b.x), y1 = std::min(a.y, b.y), x2 = std::max(a.x + a.width, b.x + b.width), y2 = std::max(a.y + a.height, b.y + b.height);
+    return Rect_<T>(x1, y1, x2 - x1, y2 - y1);
+}
+typedef Rect_<int> Rect;
 
 struct Scalar {
     double val[4];
@@ -185,8 +210,20 @@ public:
     template <typename T> const T *ptr(int r = 0) const { return reinterpret_cast<const T *>(ptr(r)); }
     template <typename T> T &at(int i) { return reinterpret_cast<T *>(data)[i]; }
     template <typename T> const T &at(int i) const { return reinterpret_cast<const T *>(data)[i]; }
-    template <typename T> T &at(int r, int c) { return reinterpret_cast<T *>(data)[(size_t)r * cols + c]; }
-    template <typename T> const T &at(int r, int c) const { return reinterpret_cast<const T *>(data)[(size_t)r * cols + c]; }
+    /* at(row, col): indices are clamped into the matrix.  The reference reads dist_map.at<float>(int(y), int(x)) for box corners that may sit
+     * on the inclusive border of the ROI (object_3d_util.cpp:441), one past the last row / column: undefined there, the last row / column
+     * here (the behaviour oracle/cuboid_oracle.cpp defines too). */
+    template <typename T> T &at(int r, int c) { return reinterpret_cast<T *>(data)[(size_t)clamp_(r, rows) * cols + clamp_(c, cols)]; }
+    template <typename T> const T &at(int r, int c) const { return reinterpret_cast<const T *>(data)[(size_t)clamp_(r, rows) * cols + clamp_(c, cols)]; }
+    static int clamp_(int v, int n) { return v < 0 ? 0 : (v >= n ? n - 1 : v); }
+    Mat operator()(const Rect &r) const /* a COPY of the region (the callers only read it) */
+    {
+        if (r.x < 0 || r.y < 0 || r.x + r.width > cols || r.y + r.height > rows) throw std::runtime_error("minicv: ROI outside the image");
+        Mat m(r.height, r.width, type_);
+        const size_t es = elemSize();
+        for (int y = 0; y < r.height; y++) memcpy(m.data + (size_t)y * r.width * es, data + ((size_t)(r.y + y) * cols + r.x) * es, (size_t)r.width * es);
+        return m;
+    }
     static Mat ones(Size s, int type)
     {
         Mat m(s.height, s.width, type);
@@ -528,6 +565,42 @@ inline Mat operator+(const Mat &a, const Mat &b)
     return o;
 }
 
+/* ---- detect_3d_cuboid::detect_cuboid (box_proposal_detail.cpp:196-199): Canny on the ROI, 255 - edges, L2 3 x 3 distance transform: the
+ * oracle's restatements, pinned bit for bit against cv2 (tests/test_oracle_cv_parity.py, tests/golden/cv_pins.npz) */
+inline void Canny(InputArray src_, OutputArray dst, double low, double high)
+{
+    const Mat src = src_.getMat();
+    if (src.type() != CV_8UC1) throw std::runtime_error("minicv: Canny is provided for 8-bit single channel");
+    Mat out(src.rows, src.cols, CV_8UC1);
+    orc_canny(src.data, src.cols, src.rows, src.cols, low, high, out.data);
+    dst.assign(out);
+}
+inline Mat operator-(int s, const Mat &a)
+{
+    if (a.type() != CV_8UC1) throw std::runtime_error("minicv: scalar - Mat is provided for 8-bit");
+    Mat o(a.rows, a.cols, CV_8UC1);
+    for (size_t i = 0; i < a.total(); i++) {
+        const int v = s - (int)a.data[i];
+        o.data[i] = (uchar)(v < 0 ? 0 : (v > 255 ? 255 : v));
+    }
+    return o;
+}
+inline void distanceTransform(InputArray src_, OutputArray dst, int distanceType, int maskSize)
+{
+    const Mat src = src_.getMat();
+    if (src.type() != CV_8UC1 || distanceType != CV_DIST_L2 || maskSize != 3) throw std::runtime_error("minicv: distanceTransform is provided for 8-bit, DIST_L2, 3 x 3");
+    /* distance to the nearest ZERO pixel; the oracle's routine takes the edge map (non-zero = distance 0) */
+    Mat edges(src.rows, src.cols, CV_8UC1);
+    for (size_t i = 0; i < src.total(); i++) edges.data[i] = src.data[i] == 0 ? 255 : 0;
+    Mat out(src.rows, src.cols, CV_32FC1);
+    orc_chamfer_dt(edges.data, src.cols, src.rows, out.ptr<float>());
+    dst.assign(out);
+}
+enum { NORM_MINMAX = 32 };
+template <typename... A> inline void imshow(A &&...) {}
+inline int waitKey(int = 0) { return -1; }
+template <typename... A> inline void normalize(A &&...) {}
+
 /* drawing helpers referenced by LineSegmentDetectorImpl::drawSegments / compareSegments, which the path never calls */
 [[noreturn]] inline void minicv_unreachable(const char *what)
 {
@@ -545,7 +618,7 @@ inline void cvtColor(InputArray src_, OutputArray dst, int code)
     dst.assign(out);
 }
 inline void merge(const std::vector<Mat> &, OutputArray) { minicv_unreachable("merge"); }
-template <typename P> inline void line(InputOutputArray, P, P, const Scalar &, int) { minicv_unreachable("line"); }
+template <typename P, typename... A> inline void line(InputOutputArray, P, P, const Scalar &, A...) { minicv_unreachable("line"); }
 inline void bitwise_xor(InputArray, InputArray, OutputArray) { minicv_unreachable("bitwise_xor"); }
 inline int countNonZero(InputArray) { minicv_unreachable("countNonZero"); }
 template <typename... A> inline void pyrDown(InputArray, OutputArray, A...) { minicv_unreachable("pyrDown"); } /* BinaryDescriptor::computeGaussianPyramid: the descriptor side */
