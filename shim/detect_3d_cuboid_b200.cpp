@@ -52,8 +52,15 @@ CtxTable &table()
     return t;
 }
 
-typedef Eigen::Matrix<double, 3, 3, Eigen::RowMajor> Mat3r;
-typedef Eigen::Matrix<double, 4, 4, Eigen::RowMajor> Mat4r;
+/* the ABI takes row-major arrays; Eigen's default storage is column-major */
+template <typename M>
+std::vector<double> row_major(const M &m, int cols)
+{
+    std::vector<double> v((size_t)m.rows() * cols);
+    for (int i = 0; i < (int)m.rows(); i++)
+        for (int j = 0; j < cols; j++) v[(size_t)i * cols + j] = m(i, j);
+    return v;
+}
 
 }  // namespace
 
@@ -62,23 +69,21 @@ void detect_3d_cuboid::set_calibration(const Eigen::Matrix3d &Kalib)
 {
     cam_pose.Kalib = Kalib;
     cam_pose.invK = Kalib.inverse();
-    const Mat3r K = Kalib; /* the ABI is row-major */
-    cs_set_calibration(table().get(this), K.data());
+    cs_set_calibration(table().get(this), row_major(Kalib, 3).data());
 }
 
 /* box_proposal_detail.cpp:42-54: callers read cam_pose_raw.euler_angle (main_obj.cpp:465) */
 void detect_3d_cuboid::set_cam_pose(const Eigen::Matrix4d &transToWolrd)
 {
-    const Mat3r K = cam_pose.Kalib;
-    const Mat4r T = transToWolrd;
     double e[3], kr[9];
-    cs_cam_pose(K.data(), T.data(), e, kr);
+    cs_cam_pose(row_major(cam_pose.Kalib, 3).data(), row_major(transToWolrd, 4).data(), e, kr);
     cam_pose.transToWolrd = transToWolrd;
     cam_pose.rotationToWorld = transToWolrd.topLeftCorner<3, 3>();
     cam_pose.euler_angle = Eigen::Vector3d(e[0], e[1], e[2]);
     cam_pose.invR = cam_pose.rotationToWorld.inverse();
     cam_pose.projectionMatrix = cam_pose.Kalib * transToWolrd.inverse().topRows<3>();
-    cam_pose.KinvR = Eigen::Map<const Mat3r>(kr);
+    for (int i = 0; i < 3; i++)
+        for (int j = 0; j < 3; j++) cam_pose.KinvR(i, j) = kr[i * 3 + j];
     cam_pose.camera_yaw = e[2];
 }
 
@@ -101,15 +106,13 @@ void detect_3d_cuboid::detect_cuboid(const cv::Mat &rgb_img, const Eigen::Matrix
     p.max_cuboid_num = max_cuboid_num;
     p.nominal_skew_ratio = nominal_skew_ratio;
     p.max_cut_skew = max_cut_skew;
-    const Eigen::Matrix<double, Eigen::Dynamic, 5, Eigen::RowMajor> boxes = obj_bbox_coors.leftCols<5>();
-    const Eigen::Matrix<double, Eigen::Dynamic, 4, Eigen::RowMajor> lines = all_lines_raw.leftCols<4>();
-    const Mat4r T = transToWolrd;
+    const std::vector<double> boxes = row_major(obj_bbox_coors, 5), lines = row_major(all_lines_raw, 4), T = row_major(transToWolrd, 4);
     const cv::Mat img = rgb_img.isContinuous() ? rgb_img : rgb_img.clone();
     const int topk = max_cuboid_num > 0 ? max_cuboid_num : 1;
     std::vector<cs_cuboid_rec> recs((size_t)N * topk);
     std::vector<int32_t> counts(N);
     const int rc = cs_detect_cuboids(ctx, img.data, img.cols, img.rows, (int)img.step, img.channels(), T.data(), boxes.data(), N, lines.data(),
-                                     (int)lines.rows(), &p, recs.data(), counts.data());
+                                     (int)all_lines_raw.rows(), &p, recs.data(), counts.data());
     if (rc != CS_OK) { /* the reference prints and carries on; it never throws from detect_cuboid */
         std::printf("detect_cuboid: %s\n", cs_last_error(ctx));
         return;
@@ -123,8 +126,12 @@ void detect_3d_cuboid::detect_cuboid(const cv::Mat &rgb_img, const Eigen::Matrix
             c->scale = Eigen::Vector3d(r.scale[0], r.scale[1], r.scale[2]);
             c->rotY = r.rotY;
             c->box_config_type = Eigen::Vector2d(r.box_config_type[0], r.box_config_type[1]);
-            c->box_corners_2d = Eigen::Map<const Eigen::Matrix<int, 2, 8, Eigen::RowMajor>>(r.box_corners_2d);
-            c->box_corners_3d_world = Eigen::Map<const Eigen::Matrix<double, 3, 8, Eigen::RowMajor>>(r.box_corners_3d_world);
+            c->box_corners_2d.resize(2, 8);
+            c->box_corners_3d_world.resize(3, 8);
+            for (int j = 0; j < 8; j++) {
+                for (int a = 0; a < 2; a++) c->box_corners_2d(a, j) = r.box_corners_2d[a * 8 + j];
+                for (int a = 0; a < 3; a++) c->box_corners_3d_world(a, j) = r.box_corners_3d_world[a * 8 + j];
+            }
             c->rect_detect_2d = Eigen::Vector4d(r.rect_detect_2d[0], r.rect_detect_2d[1], r.rect_detect_2d[2], r.rect_detect_2d[3]);
             c->edge_distance_error = r.edge_distance_error;
             c->edge_angle_error = r.edge_angle_error;

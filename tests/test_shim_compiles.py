@@ -43,3 +43,22 @@ def test_line_shim_body_compiles_against_the_reference_class_header(tmp_path):
     assert r.returncode == 0, r.stderr
     syms = subprocess.run(["nm", "-C", out], capture_output=True, text=True).stdout
     assert syms.count("line_lbd_detect::detect_filter_lines(") == 2 and "line_lbd_detect::detect_raw_lines(" in syms
+
+
+def test_cuboid_shim_body_compiles_against_the_reference_class_header(tmp_path):
+    """The same for shim/detect_3d_cuboid_b200.cpp: the reference's detect_3d_cuboid.h, with oracle/ref/minieigen (Eigen) and fakecv
+    (OpenCV) standing in for the libraries this image lacks.  The object must define the three members the shim takes over from
+    box_proposal_detail.cpp."""
+    ref_inc = "/root/reference/detect_3d_cuboid/include"
+    cxx = shutil.which("g++")
+    if not cxx or not os.path.isdir(ref_inc):
+        pytest.skip("needs g++ and the reference checkout")
+    out = str(tmp_path / "cuboid_shim.o")
+    ref = os.path.join(ROOT, "oracle", "ref")
+    r = subprocess.run([cxx, "-std=c++14", "-Wall", "-c", os.path.join(ROOT, "shim", "detect_3d_cuboid_b200.cpp"), "-o", out, "-I", os.path.join(ROOT, "include"),
+                        "-I", os.path.join(ref, "minieigen"), "-I", os.path.join(ref, "fakecv"), "-I", os.path.join(ref, "fakeros"), "-I", ref_inc],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    syms = subprocess.run(["nm", "-C", out], capture_output=True, text=True).stdout
+    for member in ("detect_3d_cuboid::set_calibration(", "detect_3d_cuboid::set_cam_pose(", "detect_3d_cuboid::detect_cuboid("):
+        assert member in syms, member

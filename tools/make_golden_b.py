@@ -4,7 +4,8 @@
 
     python tools/make_golden_b.py
 
-Needs oracle/_ref/liblsd_ref.so and libedl_ref.so (the reference's lsd.cpp and binary_descriptor.cpp compiled where /root/reference exists):
+Needs oracle/_ref/*.so (the reference's line_lbd and detect_3d_cuboid sources compiled where /root/reference exists; every record written
+here was first checked equal to the reference's own output for the same inputs):
 the raw LSD segments (`n_raw_ref`, `raw_checksum_ref`) and raw EDLines key lines (`edl_n_raw_ref`, `edl_raw_checksum_ref`) recorded here
 are the REFERENCE's output, so the committed file pins the oracle to the reference wherever the tests
 run.  Per frame and mode: LSD segment count and a checksum of the segments, candidates, valid proposals, and per box the best cuboid
@@ -57,6 +58,17 @@ def frame_record(img, K, T, boxes, modes):
                edl_n_lines=int(len(edl["lines"])), edl_lines_checksum=seg_checksum(edl["lines"]), edl_n_raw_ref=int(len(ref_edl)),
                edl_raw_checksum_ref=seg_checksum(ref_edl), modes={})
     for name, kw in modes:
+        # stage (ii): the reference's own detect_cuboid (oracle/_ref/libcuboid_ref.so) must return the oracle's records, field for field,
+        # when both use libm's atan2; the golden itself is then written with the arithmetic atan2 the CUDA path shares (tests/test_pmath.py)
+        pr = O.default_params(nominal_skew_ratio=2.0, **kw)
+        O.lib().orc_set_portable_atan2(0)
+        got = O.detect_cuboid(img, K, T, boxes, lines.astype(np.float64), pr)["cuboids"]
+        O.lib().orc_set_portable_atan2(1)
+        want = O.ref_detect_cuboid(img, K, T, boxes, lines.astype(np.float64), pr)
+        for b in range(len(want)):
+            if len(got[b]) != len(want[b]) or any(not np.array_equal(np.asarray(got[b][j][f], np.float64), np.asarray(want[b][j][f], np.float64))
+                                                  for j in range(len(want[b])) for f in ("pos", "rotY", "scale", "normalized_error", "box_corners_2d")):
+                raise SystemExit("oracle detect_cuboid differs from the reference's on this frame: fix the oracle first")
         r = O.detect_cuboid(img, K, T, boxes, lines.astype(np.float64), O.default_params(nominal_skew_ratio=2.0, **kw))
         rec["modes"][name] = dict(n_candidates=int(r["n_candidates"]), n_valid=int(r["n_valid"]),
                                   boxes=[best(c[0]) if len(c) else None for c in r["cuboids"]])
