@@ -33,6 +33,10 @@ sys.path.insert(0, ROOT)
 # several batches are kept in flight, three streams each: give the driver enough hardware queues that streams of different batches do not share
 # one (the default of 8 makes a long kernel of one batch delay work of another that happens to sit behind it in the same queue)
 os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
+# N > 1: every batch ends with an all-gather of < 1 MB of cuboid records on its own stream, two dozen of them in flight.  One NCCL channel
+# = one CTA per collective: with the default channel count the waiting all-gather kernels of the batches in flight sat on the SMs the seed
+# loops need (measured at N = 2 on one box: 8.29 -> 7.74 ms per step, i.e. 2 x the single-GPU rate)
+os.environ.setdefault("NCCL_MAX_NCHANNELS", "1")
 
 WORKLOADS = {
     # name: (frames per GPU, width, height, boxes/frame, kind, poisson, param overrides, description)

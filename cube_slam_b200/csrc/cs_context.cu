@@ -419,16 +419,17 @@ int run_batch(cs_ctx *c, bool sync)
     const float *d_lines_f32 = nullptr;
     const int32_t *d_nlines = nullptr;
     mark(ST_LSD);
+    const int64_t line_launches_before = c->line_launches; /* the line detectors count their own kernels (cs_ctx_count_launches) */
     if (c->online_lines) { /* line_lbd_detect::detect_filter_lines on the resident frames (object_slam main_obj.cpp:428) */
         if (c->line_prm.use_LSD) {
             if ((rc = cs_lsd_run_device(c, (const uint8_t *)c->d_img.p, c->n_frames, c->w, c->h, c->stride, c->channels, c->line_prm.line_length_thres,
                                         c->online_cap, &d_lines_f32, &d_nlines)))
                 return rc;
-            c->launches += 8;
         } else if ((rc = cs_edl_run(c, (const uint8_t *)c->d_img.p, true, c->n_frames, c->w, c->h, c->stride, c->channels,
                                     c->line_prm.line_length_thres, c->online_cap, &d_lines_f32, &d_nlines)))
             return rc;
     }
+    c->launches += c->line_launches - line_launches_before;
     c->d_online_counts = d_nlines;
     /* fork: the per-ROI line selection / merging only needs the lines and the job table */
     cudaEventRecord(c->ev_fork, st);
