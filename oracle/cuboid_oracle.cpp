@@ -8,12 +8,16 @@
  * plus the three OpenCV calls on the path (cvtColor / Canny / distanceTransform), restated
  * from OpenCV's published algorithms and pinned bit-for-bit to the in-container cv2 4.13.
  *
- * PARITY: "parity unpinned" by the reference (it ships no tests or expected C++ outputs and cannot
- * be compiled here).  What exists: the OpenCV stages are bit-exact against cv2; and, run on the shipped object_slam sequence at the
- * shipped per-frame poses, this oracle (with the LSD oracle's lines, themselves pinned to the compiled reference) lands on the cuboids the authors ship from their MATLAB
- * implementation (object_slam/data/detect_cuboids_saved.txt) up to the sampling grid -- median 3.2 cm, same yaw sample on most
- * frames (tests/test_oracle_matlab_crosscheck.py).  A soft pin, not equality.  Build with -O2 -ffp-contract=off (no FMA contraction) so + - * / sqrt
- * are IEEE-exact and comparable with the CUDA path compiled with -fmad=false.
+ * PARITY: PINNED to the reference.  It ships no tests or expected C++ outputs, but its own sources (matrix_utils.cpp, object_3d_util.cpp,
+ * box_proposal_detail.cpp) compile from /root/reference against oracle/ref/minieigen.hpp / minicv.hpp into oracle/_ref/libcuboid_ref.so,
+ * and every field of every cuboid that library returns equals this restatement's, == on doubles, in every mode tried (default, top-k,
+ * roll / pitch sampling with several boxes, no height samples, one configuration; tests/test_oracle_ref_detect_cuboid.py; with libm's
+ * atan2 on both sides -- the parity tests against CUDA use the arithmetic atan2 of pmath.h, tied to libm by tests/test_pmath.py).
+ * The OpenCV stages are bit-exact against cv2; and, run on the shipped object_slam sequence at the shipped per-frame poses, this oracle
+ * lands on the cuboids the authors ship from their MATLAB implementation (object_slam/data/detect_cuboids_saved.txt) up to the sampling
+ * grid -- median 3.2 cm, same yaw sample on most frames (tests/test_oracle_matlab_crosscheck.py), a soft cross-check.
+ * Build with -O2 -ffp-contract=off (no FMA contraction) so + - * / sqrt are IEEE-exact and comparable with the CUDA path compiled with
+ * -fmad=false.
  *
  * Only tests/, __graft_entry__.smoke() and bench.py (cpu_baseline / --impl reference) use this.
  */

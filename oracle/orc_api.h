@@ -11,10 +11,13 @@
  *     /root/reference against a small OpenCV stand-in (oracle/ref/, oracle/_ref/) and the restatements are byte-identical to them
  *     (tests/test_oracle_ref_lsd.py, tests/test_oracle_ref_edlines.py, checksums in tests/golden/); the shipped LSD segment file is
  *     reproduced whole (tests/test_oracle_lines.py).
- *   cuboid proposals (stage ii): "parity unpinned" -- detect_3d_cuboid needs Eigen and OpenCV C++, neither is in this image, and the
- *     reference ships no tests or expected outputs for it.  The OpenCV stages inside (cvtColor, Canny, distanceTransform) are pinned bit
- *     for bit against the in-container cv2 4.13 (tests/test_oracle_cv_parity.py); the whole path is soft-pinned against the MATLAB
- *     cuboids the authors ship for the object_slam sequence (tests/test_oracle_matlab_crosscheck.py).
+ *   cuboid proposals (stage ii): PINNED -- detect_3d_cuboid's three sources compile from /root/reference against small stand-ins for
+ *     Eigen and OpenCV (oracle/ref/minieigen.hpp, minicv.hpp; oracle/_ref/libcuboid_ref.so) and every field of every cuboid they return
+ *     equals this oracle's record, == on doubles, in every mode tried (tests/test_oracle_ref_detect_cuboid.py).  The loops, thresholds,
+ *     indices and branches are the reference's code; the linear algebra under them is the stand-in's, written as Eigen documents it.
+ *     The OpenCV stages inside (cvtColor, Canny, distanceTransform) are pinned bit for bit against the in-container cv2 4.13
+ *     (tests/test_oracle_cv_parity.py); a soft cross-check against the MATLAB cuboids the authors ship for the object_slam sequence
+ *     remains (tests/test_oracle_matlab_crosscheck.py).
  */
 #ifndef ORC_API_H
 #define ORC_API_H
