@@ -325,14 +325,14 @@ def init_comm(cx, rank, world, dist, torch, _lib):
 
 
 def measure_config(name, args, rank, world, local_rank, dist, cs, _lib, torch):
-    """One of the other BASELINE configurations at this rank count: every rank holds its shard (WORKLOADS[name] frames per GPU), six batches in
-    flight, online LSD lines, the top-K all-gather inside every step when N > 1.  Returns the dict that goes under the config's key."""
+    """One of the other BASELINE configurations at this rank count: every rank holds its shard (WORKLOADS[name] frames per GPU), twelve batches in
+    flight (with the all-gather of N > 1 coupling the ranks batch by batch, six were too few to hide the wait for the slower rank), online LSD lines, the top-K all-gather inside every step when N > 1.  Returns the dict that goes under the config's key."""
     wl = make_workload(name, rank)
     F, w, h = wl["F"], wl["w"], wl["h"]
     params = cs.default_params(**wl["over"])
     topk = int(params.max_cuboid_num)
     ctxs = []
-    for _ in range(6):
+    for _ in range(12):
         cx = cs.Context(local_rank, w, h, F, 16, 8192)
         cx.set_calibration(wl["K"])
         ctxs.append(cx)
@@ -662,7 +662,7 @@ def run_ours(args, rank, world, local_rank):
                         "lines": "detected on the device from the resident frames: line_lbd_detect::detect_filter_lines, LSD flavour, length > 15 (stage (i) of the north star)",
                         "l2": "inputs larger than L2 (%.0f MB of frames per GPU)" % (wl["imgs"].nbytes / 1e6),
                         "parallelism": "frames sharded x%d, one NCCL all-gather of top-K" % world if world > 1 else "single GPU",
-                        "batches_in_flight": len(ctxs), "one_batch_alone_ms": stage_acc.get("total")}, **workload_shape(wl, stats)),
+                        "batches_in_flight": n_ctx, "one_batch_alone_ms": stage_acc.get("total")}, **workload_shape(wl, stats)),
         "e2e": {"value": n_valid_all / (e2e_ms_step * 1e-3), "unit": "proposals/s", "frames_per_s": n_frames_all / (e2e_ms_step * 1e-3),
                 "ms_per_step": e2e_ms_step, "steps": e2e_steps, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                 "host_threads": len(e2e_ctxs) if world == 1 else 1, "batches_in_flight": len(e2e_ctxs), "mode": e2e_mode,
