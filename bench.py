@@ -560,18 +560,25 @@ def run_ours(args, rank, world, local_rank):
             t.join()
         barrier()
         e2e_ms = (time.perf_counter() - t0) * 1e3  # host-synchronous calls: the wall clock around all of them is the honest bound
+        e2e_sync = {"ms_per_step": e2e_ms / e2e_steps, "frames_per_s": n_frames_all / (e2e_ms / e2e_steps * 1e-3), "steps": e2e_steps,
+                    "host_threads": len(e2e_ctxs), "mode": e2e_mode}
     else:
-        # N > 1: one host thread keeps the batches in flight with the split calls (cs_batch_upload_online from pinned host frames,
-        # cs_batch_run_async, cs_allgather_topk, cs_batch_fetch) as a rolling pipeline, so that every rank issues its collectives in the
-        # same order: step s is issued on context s mod K, then the oldest outstanding step is fetched
+        e2e_sync = None
+    if True:
+        # The pipelined form of the same ABI (every N): one host thread keeps the batches in flight with the split calls --
+        # cs_batch_upload_online (pinned host frames -> device, tables), cs_batch_run_async, cs_allgather_topk when N > 1, cs_batch_fetch
+        # (records -> host) -- as a rolling pipeline: step s is issued on context s mod K, then the oldest outstanding step is fetched.  Every
+        # rank issues its collectives in the same order, and no host thread sleeps in a synchronous call while its context could be copying.
         e2e_ctxs = ctxs
         K_ = len(e2e_ctxs)
-        e2e_mode = "one host thread, %d contexts as a rolling pipeline: cs_batch_upload_online + cs_batch_run_async + cs_allgather_topk + cs_batch_fetch" % K_
+        e2e_mode = "one host thread, %d contexts as a rolling pipeline: cs_batch_upload_online + cs_batch_run_async%s + cs_batch_fetch" % (
+            K_, " + cs_allgather_topk" if world > 1 else "")
 
         def e2e_issue(cx):
             cx.upload_online(imgs_pinned, wl["Ts"], wl["boxes"], lp_main, params)
             cx.run_async()
-            cx.check(cx.L.cs_allgather_topk(cx.h, recs_per_rank, C.byref(C.c_void_p())))
+            if world > 1:
+                cx.check(cx.L.cs_allgather_topk(cx.h, recs_per_rank, C.byref(C.c_void_p())))
 
         def e2e_run(n_steps):
             issued = fetched = 0
@@ -665,7 +672,7 @@ def run_ours(args, rank, world, local_rank):
                         "batches_in_flight": n_ctx, "one_batch_alone_ms": stage_acc.get("total")}, **workload_shape(wl, stats)),
         "e2e": {"value": n_valid_all / (e2e_ms_step * 1e-3), "unit": "proposals/s", "frames_per_s": n_frames_all / (e2e_ms_step * 1e-3),
                 "ms_per_step": e2e_ms_step, "steps": e2e_steps, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-                "host_threads": len(e2e_ctxs) if world == 1 else 1, "batches_in_flight": len(e2e_ctxs), "mode": e2e_mode,
+                "host_threads": 1, "batches_in_flight": len(e2e_ctxs), "mode": e2e_mode, "sync_calls": e2e_sync,
                 "timer": "wall clock around all calls"},
         "gpu_launches": int(stats["n_kernel_launches"]) * args.steps,
         "roofline": roofline, "cpu_baseline": cpu, "clocks": sampler.summary(),
