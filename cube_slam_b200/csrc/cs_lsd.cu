@@ -443,6 +443,7 @@ __device__ void lsd_region_grow(const LsdFrame &F, const LsdReg &R, int base, in
     reg_angle = (double)reg_deg * LSD_DEG2RAD;
     float sumdx = (float)cos(reg_angle);
     float sumdy = (float)sin(reg_angle);
+    __syncwarp(); /* every lane is done reading the previous region's list before its slots are written again */
     if (lane == 0) {
         atomicOr(F.ubits + (s_addr >> 5), 1u << (s_addr & 31));
         R.put(base, s_addr);
