@@ -61,7 +61,7 @@ STAGE_BYTES = {
 }
 STAGE_KERNELS = {"dt": "k_dt_bi<N> (one launch per ROI width class)", "canny": "k_canny_nms", "hyst": "k_canny_hyst", "gray": "k_bgr2gray_flat",
                  "sweep": "k_sweep_warp", "fuse": "k_fuse_warp", "lines": "k_roi_lines",
-                 "lsd": "line detector (k_lsd_blur/resize/grad + k_lsd_grow_seq + k_lsd_validate/emit)"}
+                 "lsd": "line detector (k_lsd_blur/resize/grad + k_lsd_grow_seq + k_lsd_val_count/nfa x 6 + k_lsd_emit)"}
 LIMITERS = {"lsd": "the seed loop (k_lsd_grow_seq, one warp per frame, seeds in raster order) is a dependent chain of L2 / HBM gathers per region pixel: latency-bound, not HBM-bound",
             "canny": "integer ALU pipe (ncu, profiles/): not an HBM-bound kernel",
             "dt": "dependency chain of H row steps per ROI (latency), DRAM traffic below the algorithmic bytes"}
