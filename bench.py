@@ -356,8 +356,7 @@ def measure_config(name, args, rank, world, local_rank, dist, cs, _lib, torch):
         if world > 1:
             cx.check(cx.L.cs_allgather_topk(cx.h, recs_per_rank, C.byref(gathered)))
 
-    steps = max(6, min(args.steps // 4, 24))
-    steps -= steps % len(ctxs)
+    steps = 2 * len(ctxs)
     for i in range(2 * len(ctxs)):
         step_i(i)
     torch.cuda.synchronize()
@@ -372,6 +371,9 @@ def measure_config(name, args, rank, world, local_rank, dist, cs, _lib, torch):
         s_.wait_event(ev0)
     for i in range(steps):
         step_i(i)
+    if world > 1:  # the collectives run on the contexts' gather streams: the end events go behind the last one of each context
+        for cx in ctxs:
+            cx.check(cx.L.cs_allgather_wait(cx.h))
     for e, s_ in zip(ev_end, streams):
         e.record(s_)
     if world > 1:
@@ -451,6 +453,12 @@ def run_ours(args, rank, world, local_rank):
             if with_gather:
                 cx.check(cx.L.cs_allgather_topk(cx.h, recs_per_rank, C.byref(gathered)))
 
+        def join_gathers():
+            # the collectives run on the contexts' gather streams: order each context stream behind its last one before the end events
+            if with_gather:
+                for cx in ctxs:
+                    cx.check(cx.L.cs_allgather_wait(cx.h))
+
         for i in range(max(warm, 3) * len(ctxs)):
             step_i(i)
         torch.cuda.synchronize()
@@ -463,6 +471,7 @@ def run_ours(args, rank, world, local_rank):
             s_.wait_event(ev0)
         for i in range(steps):
             step_i(i)
+        join_gathers()
         for e, s_ in zip(ev_end, streams):
             e.record(s_)
         barrier()
@@ -477,6 +486,7 @@ def run_ours(args, rank, world, local_rank):
             barrier()
             g0.record(streams[0])
             ctx.check(ctx.L.cs_allgather_topk(ctx.h, recs_per_rank, C.byref(gathered)))
+            ctx.check(ctx.L.cs_allgather_wait(ctx.h))
             g1.record(streams[0])
             torch.cuda.synchronize()
             stage["allgather"] = g0.elapsed_time(g1)
@@ -586,6 +596,8 @@ def run_ours(args, rank, world, local_rank):
                 while issued < n_steps and issued - fetched < K_:
                     e2e_issue(e2e_ctxs[issued % K_])
                     issued += 1
+                if world > 1:  # a step is complete when its all-gather is: order the fetch behind it
+                    e2e_ctxs[fetched % K_].check(e2e_ctxs[fetched % K_].L.cs_allgather_wait(e2e_ctxs[fetched % K_].h))
                 e2e_ctxs[fetched % K_].fetch()
                 fetched += 1
 

@@ -61,7 +61,7 @@ EXPORTS = [
     "cs_batch_upload", "cs_batch_upload_online", "cs_detect_frames_batch", "cs_batch_run", "cs_batch_run_async", "cs_batch_fetch", "cs_batch_stats_get",
     "cs_batch_device_records", "cs_stream", "cs_stage_ms", "cs_set_profiling", "cs_debug_roi",
     "cs_debug_candidates", "cs_detect_lines", "cs_detect_lines_batch", "cs_debug_lsd", "cs_debug_lsd_stats", "cs_debug_lsd_prof", "cs_debug_atan2", "cs_atan2_host", "cs_cuboid_draw_edges", "cs_debug_edlines", "cs_debug_stage_offsets", "cs_comm_unique_id", "cs_comm_init",
-    "cs_allgather_topk", "cs_fetch_gathered",
+    "cs_allgather_topk", "cs_allgather_wait", "cs_fetch_gathered",
 ]
 
 
@@ -119,6 +119,7 @@ def load():
     L.cs_comm_unique_id.argtypes = [vp, C.c_char_p, u8_p]
     L.cs_comm_init.argtypes = [vp, C.c_char_p, u8_p, i, i]
     L.cs_allgather_topk.argtypes = [vp, i, C.POINTER(vp)]
+    L.cs_allgather_wait.argtypes = [vp]
     L.cs_fetch_gathered.argtypes = [vp, vp, i]
     for name in EXPORTS:
         fn = getattr(L, name)

@@ -105,6 +105,11 @@ struct cs_ctx {
     /* NCCL (loaded at run time) */
     void *nccl_lib = nullptr;
     void *nccl_comm = nullptr;
+    /* the all-gather runs on a stream of its own (cs_nccl_impl.inc): a rank that reaches a batch's gather before its peer must not hold
+     * up the kernels of the context's next batch, only that batch's final write of the record buffer */
+    cudaStream_t gather_stream = nullptr;
+    cudaEvent_t ev_gather_ready = nullptr, ev_gather_done = nullptr;
+    bool gather_pending = false;
     int world = 1, rank = 0;
 };
 
@@ -410,8 +415,6 @@ int run_batch(cs_ctx *c, bool sync)
     CS_CUDA(c, cudaMemsetAsync(c->d_err.p, 0, 16, st));
 
     const int n_jobs = (int)c->jobs.size(), n_objs = (int)c->objs.size();
-    /* record slots past a box's count must read valid = 0 on the device too (the all-gather ships the whole buffer) */
-    if (n_objs > 0) CS_CUDA(c, cudaMemsetAsync(c->d_out.p, 0, (size_t)n_objs * c->topk * sizeof(cs_cuboid_rec), st));
     const uint8_t *gray = (const uint8_t *)c->d_gray.p;
     auto mark = [&](int s) {
         if (c->profiling) cudaEventRecord(c->ev[s], st);
@@ -476,6 +479,10 @@ int run_batch(cs_ctx *c, bool sync)
                         (const int2 *)c->d_blocks.p, (int)c->sweep_blocks.size(), (const double *)c->d_mlines.p, (const int32_t *)c->d_lcounts.p,
                         (const float *)c->d_dist.p, (uint8_t *)c->d_cvalid.p, (double *)c->d_cdist.p, (double *)c->d_cangle.p, &c->prm, st, &c->launches);
     mark(ST_FUSE);
+    /* the previous batch's all-gather (its own stream) may still be reading the record buffer: only this point has to wait for it */
+    if (c->gather_pending) cudaStreamWaitEvent(st, c->ev_gather_done, 0);
+    /* record slots past a box's count must read valid = 0 on the device too (the all-gather ships the whole buffer) */
+    if (n_objs > 0) CS_CUDA(c, cudaMemsetAsync(c->d_out.p, 0, (size_t)n_objs * c->topk * sizeof(cs_cuboid_rec), st));
     if (!c->use_cta_select && c->max_n_cand <= cs_fuse_warp_cap())
         cs_launch_fuse_warp((const CsObj *)c->d_objs.p, n_objs, (const CsJob *)c->d_jobs.p, (const CsFrame *)c->d_frames.p, (const CsPose *)c->d_poses.p,
                             (const double *)c->d_yaws.p, (const uint8_t *)c->d_cvalid.p, (const double *)c->d_cdist.p, (const double *)c->d_cangle.p,
@@ -691,6 +698,9 @@ void cs_destroy(cs_ctx *c)
     cudaEventDestroy(c->ev_join);
     cudaStreamDestroy(c->stream2);
     cudaStreamDestroy(c->stream_hi);
+    if (c->gather_stream) cudaStreamDestroy(c->gather_stream);
+    if (c->ev_gather_ready) cudaEventDestroy(c->ev_gather_ready);
+    if (c->ev_gather_done) cudaEventDestroy(c->ev_gather_done);
     cudaEventDestroy(c->ev_mid);
     cudaEventDestroy(c->ev_dt_fork);
     cudaEventDestroy(c->ev_dt_join);

@@ -244,8 +244,13 @@ double cs_atan2_host(double y, double x);
 int cs_comm_unique_id(cs_ctx *ctx, const char *nccl_library_path, uint8_t id_out[128]);
 int cs_comm_init(cs_ctx *ctx, const char *nccl_library_path, const uint8_t id[128], int world_size, int rank);
 /* all-gather recs_per_rank records from every rank's record buffer into gathered (DEVICE pointer owned by the
- * context, returned through *gathered_dev; world_size x recs_per_rank records). */
+ * context, returned through *gathered_dev; world_size x recs_per_rank records).
+ * The collective runs on a stream of its own, ordered after the work queued on the context so far; the context's next batch only waits
+ * for it where it overwrites the record buffer.  cs_fetch_gathered waits for it; anything else a caller queues on the context stream and
+ * wants ordered behind the gather (a timing event, its own copy of *gathered_dev) goes after cs_allgather_wait (a stream-level wait, the
+ * host does not block). */
 int cs_allgather_topk(cs_ctx *ctx, int recs_per_rank, void **gathered_dev);
+int cs_allgather_wait(cs_ctx *ctx);
 int cs_fetch_gathered(cs_ctx *ctx, cs_cuboid_rec *out, int n_records);
 
 #ifdef __cplusplus
