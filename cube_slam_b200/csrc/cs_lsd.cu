@@ -20,8 +20,10 @@
  *   k_lsd_grow_seq   everything that reads or writes `used`: the raster scan for seeds, region_grow, region2rect, the density test, refine /
  *                    reduce_region_radius (lsd.cpp:478-519), one warp per frame (one 32-thread CTA, 8 KB of shared memory for the region
  *                    list, `used` as a bit per pixel in HBM read through L2).  Emits the candidate rectangles in seed order.
- *   k_lsd_validate   rect_improve and the NFA test (lsd.cpp:520-534, 873-1136) read the angle map only: one warp per candidate
- *                    rectangle, all candidates of all frames at once.
+ *   k_lsd_val_count / k_lsd_val_nfa (six rounds)   rect_improve and the NFA test (lsd.cpp:520-534, 873-1136) read the angle map only: one
+ *                    warp per undecided candidate rectangle, all frames at once; a round's up-to-five rectangles counted in one scan of the
+ *                    angle map, the binomial tails in a kernel of their own (k_lsd_validate: the same as ONE kernel, kept as the A/B path --
+ *                    its 6.6 k instructions against a 32 KB instruction cache cost 40 % of its issue stalls).
  *   k_lsd_emit       accepted candidates in seed order + the key-line filter.
  * Why this shape (profiles/r2_lsd_seed_ncu.md): the one-warp loop is bound by instruction issue (an instruction every 6 cycles, ~12 M per
  * frame in round 1), not by memory latency; what stops more frames from sharing an SM is the instruction cache, so the sequential kernel is
@@ -31,8 +33,9 @@
  * per frame, was not faster than one warp per frame, and emitted duplicate segments on dense frames (git history: k_lsd_grow_par).
  *
  * Inside one candidate the warp parallelises what is order-free (the 3x3 neighbour tests of three region points per step from ONE 16-byte
- * record per pixel, rectangle pixel counts over rows, min/max extents, the binomial tail's break tests) and keeps every floating-point
- * accumulation in the reference's order.
+ * record per pixel, the addends of the ordered sums, rectangle pixel counts over rows, min/max extents, the binomial tail's break tests) and
+ * keeps every floating-point accumulation in the reference's order; neighbours whose angle difference is clear of the tolerance by more
+ * than the region angle can drift within a round are accepted / rejected without re-deriving the angle per pixel (lsd_region_grow).
  */
 #include <cuda_runtime.h>
 #include <float.h>
