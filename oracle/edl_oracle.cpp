@@ -317,9 +317,11 @@ struct Ed {
 }  // namespace
 
 /* line_lbd_detect::detect_filter_lines with use_LSD = false, one octave.  Optional stage outputs for pinning / GPU parity. */
-extern "C" int edl_orc_detect(const uint8_t *img, int w, int h, int stride, int channels, float line_length_thres, float *lines_out, int cap,
-                              float *raw_lines, int cap_raw, int *n_raw_out, uint8_t *blur_out, int16_t *dx_out, int16_t *dy_out,
-                              int16_t *g_out, uint8_t *dir_out, int32_t *anchors_out, int *n_anchors_out, uint8_t *edge_out)
+/* kl_out (optional): the key-line fields of every KEPT line that the descriptor side reads (detectImpl :526-540): cap x
+ * {direction, lineLength, numOfPixels} as three floats (numOfPixels is a small integer); same order as lines_out */
+static int edl_detect_impl(const uint8_t *img, int w, int h, int stride, int channels, float line_length_thres, float *lines_out, int cap,
+                           float *raw_lines, int cap_raw, int *n_raw_out, uint8_t *blur_out, int16_t *dx_out, int16_t *dy_out,
+                           int16_t *g_out, uint8_t *dir_out, int32_t *anchors_out, int *n_anchors_out, uint8_t *edge_out, float *kl_out)
 {
     if (n_raw_out) *n_raw_out = 0;
     if (n_anchors_out) *n_anchors_out = 0;
@@ -439,6 +441,7 @@ extern "C" int edl_orc_detect(const uint8_t *img, int w, int h, int stride, int 
     /* EDline :2379-2626 */
     std::vector<float> endpoints; /* 4 per line */
     std::vector<float> directions;
+    std::vector<int> npixels; /* lines_.sId[k + 1] - lines_.sId[k] (:1077): the pixels of the fitted line */
     if (numEdges > 0) {
         std::vector<uint32_t> lx(cx.size()), ly(cx.size());
         E.logNT = 2.0 * (std::log10((double)w) + std::log10((double)h));
@@ -508,6 +511,7 @@ extern "C" int edl_orc_detect(const uint8_t *img, int w, int h, int stride, int 
                     endpoints.push_back((float)(a1 * Px - a3 * Py - a4));
                     endpoints.push_back((float)(a2 * Py - a3 * Px - a5));
                     directions.push_back(direction);
+                    npixels.push_back((int)(offsetInLineArray - lineStart));
                 } else
                     offsetInLineArray = lineStart;
             }
@@ -555,8 +559,29 @@ extern "C" int edl_orc_detect(const uint8_t *img, int w, int h, int stride, int 
             lines_out[4 * n_out + 1] = sy;
             lines_out[4 * n_out + 2] = ex;
             lines_out[4 * n_out + 3] = ey;
+            if (kl_out) {
+                kl_out[3 * n_out + 0] = direction;
+                kl_out[3 * n_out + 1] = lineLength;
+                kl_out[3 * n_out + 2] = (float)npixels[k];
+            }
         }
         n_out++;
     }
     return n_out;
+}
+
+extern "C" int edl_orc_detect(const uint8_t *img, int w, int h, int stride, int channels, float line_length_thres, float *lines_out, int cap,
+                              float *raw_lines, int cap_raw, int *n_raw_out, uint8_t *blur_out, int16_t *dx_out, int16_t *dy_out,
+                              int16_t *g_out, uint8_t *dir_out, int32_t *anchors_out, int *n_anchors_out, uint8_t *edge_out)
+{
+    return edl_detect_impl(img, w, h, stride, channels, line_length_thres, lines_out, cap, raw_lines, cap_raw, n_raw_out, blur_out, dx_out, dy_out, g_out,
+                           dir_out, anchors_out, n_anchors_out, edge_out, nullptr);
+}
+
+/* the same, returning per kept line {direction, lineLength, numOfPixels} as well, and the Sobel maps the descriptor reads */
+extern "C" int edl_orc_detect_keylines(const uint8_t *img, int w, int h, int stride, int channels, float line_length_thres, float *lines_out, float *kl_out,
+                                       int cap, int16_t *dx_out, int16_t *dy_out)
+{
+    return edl_detect_impl(img, w, h, stride, channels, line_length_thres, lines_out, cap, nullptr, 0, nullptr, nullptr, dx_out, dy_out, nullptr, nullptr,
+                           nullptr, nullptr, nullptr, kl_out);
 }

@@ -430,6 +430,133 @@ def edl_detect(img, line_length_thres=50.0, cap=8192, want_stages=False):
     return res
 
 
+# ------------------------------------------------------------------------------------------- LBD descriptors + matcher
+KEYLINE_DTYPE = np.dtype([("sx", np.float32), ("sy", np.float32), ("ex", np.float32), ("ey", np.float32), ("angle", np.float32),
+                          ("line_length", np.float32), ("response", np.float32), ("size", np.float32), ("num_pixels", np.int32),
+                          ("class_id", np.int32)])
+
+
+def _img_args(img):
+    img = np.ascontiguousarray(img, np.uint8)
+    h, w = img.shape[:2]
+    ch = 1 if img.ndim == 2 else img.shape[2]
+    return img, w, h, ch
+
+
+def lbd_detect_keylines(img, use_LSD=True, line_length_thres=15.0, cap=8192):
+    """The key lines line_lbd_detect::detect_descrip_lines(gray, keylines_out, descrips) keeps (line_lbd_allclass.cpp:253-272)."""
+    img, w, h, ch = _img_args(img)
+    out = np.zeros(cap, KEYLINE_DTYPE)
+    L = lib()
+    L.lbd_orc_detect_keylines.restype = C.c_int
+    n = L.lbd_orc_detect_keylines(_p(img, C.c_uint8), w, h, img.strides[0], ch, int(bool(use_LSD)), C.c_float(line_length_thres), out.ctypes.data_as(C.c_void_p), cap)
+    if n < 0:
+        raise RuntimeError("lbd_orc_detect_keylines failed (%d)" % n)
+    return out[:n].copy()
+
+
+def lbd_keylines_from_lsd(lines, w, h):
+    """KeyLine fields of the LSD flavour from the n x 4 rows detect_filter_lines returns (LSDDetector.cpp:226-250)."""
+    lines = np.ascontiguousarray(lines, np.float32).reshape(-1, 4)
+    out = np.zeros(len(lines), KEYLINE_DTYPE)
+    lib().lbd_orc_keylines_from_lsd(_p(lines, C.c_float), len(lines), int(w), int(h), out.ctypes.data_as(C.c_void_p))
+    return out
+
+
+def lbd_order_keylines(kl):
+    """detect_descrip_lines_octaves' start / end swap and angle fold (line_lbd_allclass.cpp:321-330) on a copy."""
+    kl = np.ascontiguousarray(kl, KEYLINE_DTYPE).copy()
+    lib().lbd_orc_order_keylines(kl.ctypes.data_as(C.c_void_p), len(kl))
+    return kl
+
+
+def lbd_compute(img, keylines, want_float=False):
+    """BinaryDescriptor::compute(image, keylines, descriptors) -> n x 32 uint8 (and n x 72 float32 with want_float)."""
+    img, w, h, ch = _img_args(img)
+    kl = np.ascontiguousarray(keylines, KEYLINE_DTYPE)
+    n = len(kl)
+    desc = np.zeros((n, 32), np.uint8)
+    fdesc = np.zeros((n, 72), np.float32)
+    L = lib()
+    L.lbd_orc_compute.restype = C.c_int
+    rc = L.lbd_orc_compute(_p(img, C.c_uint8), w, h, img.strides[0], ch, kl.ctypes.data_as(C.c_void_p), n, _p(desc, C.c_uint8), _p(fdesc, C.c_float))
+    if rc < 0:
+        raise RuntimeError("lbd_orc_compute failed (%d)" % rc)
+    return (desc, fdesc) if want_float else desc
+
+
+def lbd_match(query, train, thres=25.0):
+    """line_lbd_detect::match_line_descrip -> (query_idx, train_idx, distance) of the good matches, query order."""
+    q = np.ascontiguousarray(query, np.uint8).reshape(-1, 32)
+    t = np.ascontiguousarray(train, np.uint8).reshape(-1, 32)
+    qi = np.zeros(max(len(q), 1), np.int32)
+    ti = np.zeros(max(len(q), 1), np.int32)
+    di = np.zeros(max(len(q), 1), np.float32)
+    L = lib()
+    L.lbd_orc_match.restype = C.c_int
+    n = L.lbd_orc_match(_p(q, C.c_uint8), len(q), _p(t, C.c_uint8), len(t), C.c_float(thres), _p(qi, C.c_int32), _p(ti, C.c_int32), _p(di, C.c_float))
+    return qi[:n].copy(), ti[:n].copy(), di[:n].copy()
+
+
+def lbd_tables():
+    """(F_g 63 doubles, F_l 21 doubles, rank of each one-byte xor pattern in Mihasher::query's enumeration)."""
+    G = np.zeros(63, np.float64)
+    Lw = np.zeros(21, np.float64)
+    rank = np.zeros(256, np.int32)
+    lib().lbd_orc_gauss_tables(_p(G, C.c_double), _p(Lw, C.c_double))
+    lib().lbd_orc_pattern_rank(_p(rank, C.c_int32))
+    return G, Lw, rank
+
+
+def _ref_all():
+    global _REF_ALL
+    lib()
+    if _REF_ALL is None:
+        _REF_ALL = C.CDLL(_REF_ALL_PATH)
+        _REF_ALL.ref_detect_filter_lines.restype = C.c_int
+    for name in ("ref_detect_descrip_lines", "ref_lbd_compute", "ref_match_line_descrip"):
+        getattr(_REF_ALL, name).restype = C.c_int
+    return _REF_ALL
+
+
+def ref_detect_descrip_lines(img, use_LSD=True, line_length_thres=15.0, cap=8192):
+    """The reference's OWN detect_descrip_lines(gray, keylines_out, line_descrips) -> (key lines, n x 32 descriptors)."""
+    img, w, h, ch = _img_args(img)
+    kl = np.zeros(cap, KEYLINE_DTYPE)
+    desc = np.zeros((cap, 32), np.uint8)
+    n = _ref_all().ref_detect_descrip_lines(_p(img, C.c_uint8), w, h, ch, int(bool(use_LSD)), C.c_float(line_length_thres), kl.ctypes.data_as(C.c_void_p),
+                                            _p(desc, C.c_uint8), cap)
+    if n < 0 or n > cap:
+        raise RuntimeError("ref_detect_descrip_lines failed (%d)" % n)
+    return kl[:n].copy(), desc[:n].copy()
+
+
+def ref_lbd_compute(img, keylines, want_float=False):
+    """The reference's OWN BinaryDescriptor::compute on the given key lines."""
+    img, w, h, ch = _img_args(img)
+    kl = np.ascontiguousarray(keylines, KEYLINE_DTYPE)
+    n = len(kl)
+    desc = np.zeros((n, 32), np.uint8)
+    fdesc = np.zeros((n, 72), np.float32)
+    rc = _ref_all().ref_lbd_compute(_p(img, C.c_uint8), w, h, ch, kl.ctypes.data_as(C.c_void_p), n, _p(desc, C.c_uint8), _p(fdesc, C.c_float) if want_float else None)
+    if rc < 0:
+        raise RuntimeError("ref_lbd_compute failed (%d)" % rc)
+    return (desc, fdesc) if want_float else desc
+
+
+def ref_match_line_descrip(query, train, thres=25.0):
+    """The reference's OWN match_line_descrip."""
+    q = np.ascontiguousarray(query, np.uint8).reshape(-1, 32)
+    t = np.ascontiguousarray(train, np.uint8).reshape(-1, 32)
+    qi = np.zeros(max(len(q), 1), np.int32)
+    ti = np.zeros(max(len(q), 1), np.int32)
+    di = np.zeros(max(len(q), 1), np.float32)
+    n = _ref_all().ref_match_line_descrip(_p(q, C.c_uint8), len(q), _p(t, C.c_uint8), len(t), C.c_float(thres), _p(qi, C.c_int32), _p(ti, C.c_int32), _p(di, C.c_float))
+    if n < 0:
+        raise RuntimeError("ref_match_line_descrip failed (%d)" % n)
+    return qi[:n].copy(), ti[:n].copy(), di[:n].copy()
+
+
 # ------------------------------------------------------------------------------------------- batch driver (OpenMP, no Python in the loop)
 def max_threads():
     return int(lib().orc_max_threads())

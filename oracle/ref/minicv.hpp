@@ -197,6 +197,13 @@ public:
     }
     void create(Size s, int type) { create(s.height, s.width, type); }
     bool empty() const { return data == nullptr || rows * cols == 0; }
+    void release()
+    {
+        rows = cols = 0;
+        data = nullptr;
+        step = 0;
+        store_.reset();
+    }
     int type() const { return type_; }
     int depth() const { return type_ & 7; }
     int channels() const { return (type_ >> 3) + 1; }
@@ -416,8 +423,17 @@ public:
 template <typename T> using Ptr = std::shared_ptr<T>;
 template <typename T, typename... A> Ptr<T> makePtr(A &&...a) { return std::make_shared<T>(std::forward<A>(a)...); }
 
+/* opencv2/core/cvstd.hpp puts these names into namespace cv; the reference's sources, written inside namespace cv::line_descriptor, call
+ * them unqualified, so `1 / sqrt(float)` in BinaryDescriptor::computeLBD is a float root and a float division (with only the C library's
+ * ::sqrt(double) visible it would be computed in double and rounded once) */
+using std::abs;
+using std::exp;
+using std::log;
 using std::max;
 using std::min;
+using std::pow;
+using std::sqrt;
+using std::swap;
 
 /* cv::LineIterator as the KeyLine fill uses it: only `count`, the number of pixels of the 8-connected line between the two points (rounded
  * to pixels, clipped to the image by moving an outside end point onto the border).  KeyLine::numOfPixels feeds the LBD descriptor only;
