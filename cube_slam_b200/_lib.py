@@ -53,6 +53,11 @@ CUBOID_DTYPE = np.dtype([
     ("proposal_index", "i4"), ("height_sample_id", "i4"), ("valid", "i4"), ("pad_", "i4"),
 ])
 
+# numpy views of cs_keyline (40 bytes) and cs_dmatch (16 bytes)
+KEYLINE_DTYPE = np.dtype([("start_x", "f4"), ("start_y", "f4"), ("end_x", "f4"), ("end_y", "f4"), ("angle", "f4"), ("line_length", "f4"),
+                          ("response", "f4"), ("size", "f4"), ("num_pixels", "i4"), ("class_id", "i4")])
+DMATCH_DTYPE = np.dtype([("query_idx", "i4"), ("train_idx", "i4"), ("img_idx", "i4"), ("distance", "f4")])
+
 _lib = None
 
 EXPORTS = [
@@ -62,6 +67,8 @@ EXPORTS = [
     "cs_batch_device_records", "cs_stream", "cs_stage_ms", "cs_set_profiling", "cs_debug_roi",
     "cs_debug_candidates", "cs_detect_lines", "cs_detect_lines_batch", "cs_debug_lsd", "cs_debug_lsd_stats", "cs_debug_lsd_prof", "cs_debug_atan2", "cs_atan2_host", "cs_cuboid_draw_edges", "cs_debug_edlines", "cs_debug_stage_offsets", "cs_comm_unique_id", "cs_comm_init",
     "cs_allgather_topk", "cs_allgather_wait", "cs_fetch_gathered",
+    "cs_keylines_from_lines", "cs_lbd_compute", "cs_lbd_compute_batch", "cs_detect_descrip_lines", "cs_detect_descrip_lines_batch",
+    "cs_match_line_descrip", "cs_match_line_descrip_batch", "cs_lbd_debug_prepare",
 ]
 
 
@@ -121,6 +128,14 @@ def load():
     L.cs_allgather_topk.argtypes = [vp, i, C.POINTER(vp)]
     L.cs_allgather_wait.argtypes = [vp]
     L.cs_fetch_gathered.argtypes = [vp, vp, i]
+    L.cs_keylines_from_lines.argtypes = [f_p, i, i, i, vp]
+    L.cs_lbd_compute.argtypes = [vp, vp, i, i, i, i, vp, i, u8_p, f_p]
+    L.cs_lbd_compute_batch.argtypes = [vp, vp, i, i, i, i, i, vp, i32_p, u8_p, f_p]
+    L.cs_detect_descrip_lines.argtypes = [vp, vp, i, i, i, i, C.POINTER(LineParams), vp, u8_p, i32_p]
+    L.cs_detect_descrip_lines_batch.argtypes = [vp, vp, i, i, i, i, i, C.POINTER(LineParams), vp, u8_p, C.c_int32, i32_p]
+    L.cs_match_line_descrip.argtypes = [vp, u8_p, i, u8_p, i, C.c_float, vp, i32_p]
+    L.cs_match_line_descrip_batch.argtypes = [vp, u8_p, i32_p, u8_p, i32_p, i, C.c_float, vp, i32_p]
+    L.cs_lbd_debug_prepare.argtypes = [vp, i, vp, f_p, f_p]
     for name in EXPORTS:
         fn = getattr(L, name)
         if fn.restype is C.c_int and name not in ("cs_abi_version",):

@@ -100,6 +100,7 @@ struct cs_ctx {
 
     void *lsd_state = nullptr; /* line-detector workspace (cs_lsd.cu) */
     void *edl_state = nullptr; /* EDLines workspace (cs_edlines.cu) */
+    void *lbd_state = nullptr; /* descriptor / matcher workspace (cs_lbd.cu) */
     int64_t line_launches = 0;
 
     /* NCCL (loaded at run time) */
@@ -121,6 +122,7 @@ void **cs_ctx_lsd_slot(cs_ctx *c) { return &c->lsd_state; }
 int cs_ctx_seq_lines(cs_ctx *c) { return c->seq_lines; }
 int cs_ctx_use_tma(cs_ctx *c) { return c->use_tma ? 1 : 0; }
 void **cs_ctx_edl_slot(cs_ctx *c) { return &c->edl_state; }
+void **cs_ctx_lbd_slot(cs_ctx *c) { return &c->lbd_state; }
 void cs_ctx_count_launches(cs_ctx *c, int64_t n) { c->line_launches += n; }
 int cs_ctx_fail(cs_ctx *c, int code, const char *fmt, ...)
 {
@@ -683,6 +685,7 @@ void cs_destroy(cs_ctx *c)
     cs_nccl_teardown(c);
     if (c->lsd_state) cs_lsd_destroy(c->lsd_state);
     if (c->edl_state) cs_edl_destroy(c->edl_state);
+    if (c->lbd_state) cs_lbd_destroy(c->lbd_state);
     DevBuf *all[] = {&c->d_img,   &c->d_gray,  &c->d_lines,  &c->d_frames, &c->d_poses,   &c->d_yaws, &c->d_jobs, &c->d_objs,
                      &c->d_blocks, &c->d_blocks4, &c->d_dtids, &c->d_tilejob, &c->d_bits, &c->d_dist, &c->d_mlines, &c->d_lcounts, &c->d_err,
                      &c->d_cvalid, &c->d_cdist, &c->d_cangle, &c->d_cskew, &c->d_vlist,  &c->d_key,     &c->d_idx,  &c->d_flag, &c->d_keep,  &c->d_norm,

@@ -577,7 +577,8 @@ __global__ void __launch_bounds__(32) k_ed_route_fit(int W, int H, const int16_t
                                                      const int32_t *__restrict__ n_anchors, int anchor_cap, uint32_t *__restrict__ scratch_all,
                                                      size_t scratch_per_frame, double logNT, float line_length_thres, float *__restrict__ raw_all,
                                                      int32_t *__restrict__ n_raw_all, float *__restrict__ out_all, int32_t *__restrict__ n_out_all,
-                                                     int cap, int32_t *__restrict__ err_flag, const int32_t *__restrict__ redo)
+                                                     int cap, int32_t *__restrict__ err_flag, const int32_t *__restrict__ redo,
+                                                     float *__restrict__ klx_all /* optional: cap x {direction, numOfPixels} per frame */)
 {
     if (threadIdx.x != 0) return;
     const int f = blockIdx.x;
@@ -743,6 +744,11 @@ __global__ void __launch_bounds__(32) k_ed_route_fit(int W, int H, const int16_t
                         out[4 * n_out + 1] = sy;
                         out[4 * n_out + 2] = ex;
                         out[4 * n_out + 3] = ey;
+                        if (klx_all) { /* KeyLine::angle = lineDirection_, KeyLine::numOfPixels = the fitted line's pixels (:1073-1077) */
+                            float *kx = klx_all + ((size_t)f * cap + n_out) * 2;
+                            kx[0] = direction;
+                            kx[1] = __int_as_float((int)(offL - lineStart));
+                        }
                     }
                     n_out++;
                 }
@@ -1133,7 +1139,7 @@ __device__ __forceinline__ int ed_warp_sum_i(int v)
 
 /* the chain [S, Eend) of one edge -> segments; every lane returns the same counts.  seg: 5 words per temporary slot. */
 __device__ void ed_fit_chain(const EdFrame &F, const uint32_t *__restrict__ chain, unsigned S, const unsigned Eend, float line_length_thres, float *seg,
-                             int &n_raw, int &n_kept)
+                             float *segx /* optional: 2 floats per temporary slot, {direction, numOfPixels} */, int &n_raw, int &n_kept)
 {
     const unsigned FULL = 0xffffffffu;
     const int lane = threadIdx.x & 31, W = F.W;
@@ -1320,6 +1326,10 @@ __device__ void ed_fit_chain(const EdFrame &F, const uint32_t *__restrict__ chai
                 o[2] = sw ? s1 : e1;
                 o[3] = sw ? s2 : e2;
                 o[4] = __int_as_float(kept ? 1 : 0);
+                if (segx) {
+                    segx[2 * n_raw] = direction;
+                    segx[2 * n_raw + 1] = __int_as_float(n);
+                }
             }
             n_raw++;
             n_kept += kept ? 1 : 0;
@@ -1330,7 +1340,8 @@ __device__ void ed_fit_chain(const EdFrame &F, const uint32_t *__restrict__ chai
 __global__ void __launch_bounds__(128) k_ed_fit(int W, int H, const int16_t *__restrict__ dx_all, const int16_t *__restrict__ dy_all,
                                                 const uint8_t *__restrict__ dir_all, const uint32_t *__restrict__ xy_all, size_t node_cap,
                                                 uint32_t *__restrict__ scratch_all, size_t scratch_per_frame, double logNT, float line_length_thres,
-                                                const int32_t *__restrict__ redo, const double *__restrict__ lgam)
+                                                const int32_t *__restrict__ redo, const double *__restrict__ lgam, float *__restrict__ segx_all,
+                                                size_t segx_per_frame)
 {
     const int f = blockIdx.y, lane = threadIdx.x & 31;
     if (redo[f]) return;
@@ -1358,7 +1369,8 @@ __global__ void __launch_bounds__(128) k_ed_fit(int W, int H, const int16_t *__r
         for (unsigned t = lane; t < ns; t += 32) S.chain[c0 + nf + t] = xy[S.sP[s0 + 1 + t]];
         __syncwarp();
         int n_raw, n_kept;
-        ed_fit_chain(F, S.chain, c0, c0 + nf + ns, line_length_thres, S.seg + 5 * (size_t)(c0 / ED_MINLEN), n_raw, n_kept);
+        ed_fit_chain(F, S.chain, c0, c0 + nf + ns, line_length_thres, S.seg + 5 * (size_t)(c0 / ED_MINLEN),
+                     segx_all ? segx_all + (size_t)f * segx_per_frame + 2 * (size_t)(c0 / ED_MINLEN) : nullptr, n_raw, n_kept);
         if (lane == 0) S.segcnt[e] = (uint32_t)n_raw | ((uint32_t)n_kept << 16);
     }
 }
@@ -1366,7 +1378,8 @@ __global__ void __launch_bounds__(128) k_ed_fit(int W, int H, const int16_t *__r
 /* segments of a frame in chain order */
 __global__ void __launch_bounds__(256) k_ed_emit(int W, int H, uint32_t *__restrict__ scratch_all, size_t scratch_per_frame, float *__restrict__ raw_all,
                                                  int32_t *__restrict__ n_raw_all, float *__restrict__ out_all, int32_t *__restrict__ n_out_all, int cap,
-                                                 const int32_t *__restrict__ redo)
+                                                 const int32_t *__restrict__ redo, const float *__restrict__ segx_all, size_t segx_per_frame,
+                                                 float *__restrict__ klx_all)
 {
     __shared__ int s_w[8];
     __shared__ int s_base_raw, s_base_out;
@@ -1401,14 +1414,21 @@ __global__ void __launch_bounds__(256) k_ed_emit(int W, int H, uint32_t *__restr
         int off_r = s_base_raw + ((pre + inc) & 0xffff) - nr, off_o = s_base_out + ((pre + inc) >> 16) - nk;
         if (nr) {
             const float *seg = S.seg + 5 * (size_t)(S.sId[e] / ED_MINLEN);
+            const float *segx = (segx_all && klx_all) ? segx_all + (size_t)f * segx_per_frame + 2 * (size_t)(S.sId[e] / ED_MINLEN) : nullptr;
             for (int k = 0; k < nr; k++) {
                 const float *q = seg + 5 * k;
                 if (off_r < cap)
                     for (int j = 0; j < 4; j++) raw[4 * off_r + j] = q[j];
                 off_r++;
                 if (__float_as_int(q[4])) {
-                    if (off_o < cap)
+                    if (off_o < cap) {
                         for (int j = 0; j < 4; j++) out[4 * off_o + j] = q[j];
+                        if (segx) {
+                            float *kx = klx_all + ((size_t)f * cap + off_o) * 2;
+                            kx[0] = segx[2 * k];
+                            kx[1] = segx[2 * k + 1];
+                        }
+                    }
                     off_o++;
                 }
             }
@@ -1434,6 +1454,7 @@ struct Buf {
 struct EdState {
     Buf img, tmp, blur, dx, dy, g, dir, edge, anchors, nanch, scratch, raw, nraw, out, nout, err;
     Buf rowcnt, pid, xy, flags, next, anid, redo, abits, colcnt, lgam;
+    Buf segx, klx; /* key-line extras for the descriptor (cs_edl_run_keylines): per temporary slot, per kept segment */
     bool lgam_filled = false;
     int last_frames = 0, last_w = 0, last_h = 0, cap = 0, anchor_cap = 0;
     size_t node_cap = 0;
@@ -1479,15 +1500,15 @@ void cs_edl_destroy(void *state)
 {
     EdState *S = (EdState *)state;
     Buf *all[] = {&S->img, &S->tmp, &S->blur, &S->dx, &S->dy, &S->g, &S->dir, &S->edge, &S->anchors, &S->nanch, &S->scratch, &S->raw, &S->nraw, &S->out, &S->nout, &S->err,
-                  &S->rowcnt, &S->pid, &S->xy, &S->flags, &S->next, &S->anid, &S->redo, &S->abits, &S->colcnt, &S->lgam};
+                  &S->rowcnt, &S->pid, &S->xy, &S->flags, &S->next, &S->anid, &S->redo, &S->abits, &S->colcnt, &S->lgam, &S->segx, &S->klx};
     for (Buf *b : all)
         if (b->p) cudaFree(b->p);
     delete S;
 }
 
-/* frames in HBM (or host) -> filtered segments in HBM */
-int cs_edl_run(cs_ctx *c, const uint8_t *imgs, bool imgs_on_device, int n_frames, int w, int h, int stride, int channels, float line_length_thres,
-               int cap, const float **d_lines, const int32_t **d_counts)
+/* frames in HBM (or host) -> filtered segments in HBM; want_keylines: also {direction, numOfPixels} of every kept segment (S.klx) */
+static int ed_run(cs_ctx *c, const uint8_t *imgs, bool imgs_on_device, int n_frames, int w, int h, int stride, int channels, float line_length_thres,
+                  int cap, const float **d_lines, const int32_t **d_counts, bool want_keylines)
 {
     EdState &S = *ed_state_of(c);
     cudaStream_t st = cs_ctx_stream(c);
@@ -1495,6 +1516,7 @@ int cs_edl_run(cs_ctx *c, const uint8_t *imgs, bool imgs_on_device, int n_frames
     const size_t px = (size_t)n_frames * w * h, npx = (size_t)w * h;
     const unsigned P = (unsigned)(npx / 5), maxEdges = P / 20;
     const size_t scratch_per_frame = std::max((size_t)P * 2 + (size_t)(maxEdges + 2) * 3 + (size_t)P * 4 + 64, ed_scratch_words(P, maxEdges));
+    const size_t segx_per_frame = ((size_t)2 * P / ED_MINLEN + 2) * 2; /* one {direction, numOfPixels} pair per temporary segment slot */
     const int anchor_cap = (int)P + 1;
     const size_t node_cap = npx / 2; /* pixels with g > 0 (gradient magnitude above the threshold); denser frames take the pixel-map kernel */
     const int force_seq = cs_ctx_seq_lines(c);
@@ -1519,6 +1541,8 @@ int cs_edl_run(cs_ctx *c, const uint8_t *imgs, bool imgs_on_device, int n_frames
         (rc = ed_ensure(c, S.redo, (size_t)n_frames * 4)) || (rc = ed_ensure(c, S.abits, (size_t)n_frames * nw * nhw * 4)) ||
         (rc = ed_ensure(c, S.colcnt, (size_t)n_frames * (nw + 1) * 4)) || (rc = ed_ensure(c, S.lgam, (size_t)CS_LGAMMA_TABLE * 8)))
         return rc;
+    if (want_keylines && ((rc = ed_ensure(c, S.segx, (size_t)n_frames * segx_per_frame * 4)) || (rc = ed_ensure(c, S.klx, (size_t)n_frames * cap * 8)))) return rc;
+    float *d_segx = want_keylines ? (float *)S.segx.p : nullptr, *d_klx = want_keylines ? (float *)S.klx.p : nullptr;
     if (!S.lgam_filled) { /* log_gamma of the integers 1 .. CS_LGAMMA_TABLE - 1, host libm like the reference */
         std::vector<double> t(CS_LGAMMA_TABLE, 0.0);
         for (int i = 1; i < CS_LGAMMA_TABLE; i++) t[i] = cs_lgamma_host((double)i);
@@ -1576,16 +1600,16 @@ int cs_edl_run(cs_ctx *c, const uint8_t *imgs, bool imgs_on_device, int n_frames
     if (!force_seq) {
         k_ed_fit<<<dim3(16, n_frames), 128, 0, st>>>(w, h, (const int16_t *)S.dx.p, (const int16_t *)S.dy.p, (const uint8_t *)S.dir.p, (const uint32_t *)S.xy.p,
                                                      node_cap, (uint32_t *)S.scratch.p, scratch_per_frame, logNT, line_length_thres, (const int32_t *)S.redo.p,
-                                                     (const double *)S.lgam.p);
+                                                     (const double *)S.lgam.p, d_segx, segx_per_frame);
         k_ed_emit<<<n_frames, 256, 0, st>>>(w, h, (uint32_t *)S.scratch.p, scratch_per_frame, (float *)S.raw.p, (int32_t *)S.nraw.p, (float *)S.out.p,
-                                            (int32_t *)S.nout.p, cap, (const int32_t *)S.redo.p);
+                                            (int32_t *)S.nout.p, cap, (const int32_t *)S.redo.p, d_segx, segx_per_frame, d_klx);
         cs_ctx_count_launches(c, 2);
     }
     /* frames flagged for redo (graph arrays too small; or the A/B switch): routing and fitting on the pixel maps, one thread per frame */
     k_ed_route_fit<<<n_frames, 32, 0, st>>>(w, h, (const int16_t *)S.dx.p, (const int16_t *)S.dy.p, (const int16_t *)S.g.p, (const uint8_t *)S.dir.p,
                                             (uint8_t *)S.edge.p, (const int32_t *)S.anchors.p, (const int32_t *)S.nanch.p, anchor_cap,
                                             (uint32_t *)S.scratch.p, scratch_per_frame, logNT, line_length_thres, (float *)S.raw.p, (int32_t *)S.nraw.p,
-                                            (float *)S.out.p, (int32_t *)S.nout.p, cap, (int32_t *)S.err.p, (const int32_t *)S.redo.p);
+                                            (float *)S.out.p, (int32_t *)S.nout.p, cap, (int32_t *)S.err.p, (const int32_t *)S.redo.p, d_klx);
     cs_ctx_count_launches(c, 6);
     S.node_cap = node_cap;
     if (cudaGetLastError() != cudaSuccess) return cs_ctx_fail(c, CS_ERR_CUDA, "EDLines kernel launch failed");
@@ -1596,6 +1620,63 @@ int cs_edl_run(cs_ctx *c, const uint8_t *imgs, bool imgs_on_device, int n_frames
     S.anchor_cap = anchor_cap;
     if (d_lines) *d_lines = (const float *)S.out.p;
     if (d_counts) *d_counts = (const int32_t *)S.nout.p;
+    return CS_OK;
+}
+
+int cs_edl_run(cs_ctx *c, const uint8_t *imgs, bool imgs_on_device, int n_frames, int w, int h, int stride, int channels, float line_length_thres,
+               int cap, const float **d_lines, const int32_t **d_counts)
+{
+    return ed_run(c, imgs, imgs_on_device, n_frames, w, h, stride, channels, line_length_thres, cap, d_lines, d_counts, false);
+}
+
+int cs_edl_run_keylines(cs_ctx *c, const uint8_t *imgs, bool imgs_on_device, int n_frames, int w, int h, int stride, int channels,
+                        float line_length_thres, int cap, const float **d_lines, const int32_t **d_counts, const float **d_extra,
+                        const int16_t **d_dx, const int16_t **d_dy)
+{
+    const int rc = ed_run(c, imgs, imgs_on_device, n_frames, w, h, stride, channels, line_length_thres, cap, d_lines, d_counts, true);
+    if (rc) return rc;
+    EdState *S = ed_state_of(c);
+    *d_extra = (const float *)S->klx.p;
+    *d_dx = (const int16_t *)S->dx.p;
+    *d_dy = (const int16_t *)S->dy.p;
+    return CS_OK;
+}
+
+/* The Sobel maps BinaryDescriptor::computeSobel builds for the descriptor (binary_descriptor.cpp:352-398, octave 0: GaussianBlur 5 x 5
+ * sigma 1, then Sobel 3 x 3 into CV_16SC1) are the maps EDLineDetector::EdgeDrawing builds from OctaveKeyLines' blurred image (:811-814,
+ * 1617-1622): the same front-end kernel produces them, into the EDLines workspace. */
+int cs_edl_sobel_maps(cs_ctx *c, const uint8_t *imgs, bool imgs_on_device, int n_frames, int w, int h, int stride, int channels,
+                      const int16_t **d_dx, const int16_t **d_dy)
+{
+    EdState &S = *ed_state_of(c);
+    cudaStream_t st = cs_ctx_stream(c);
+    if (w < 8 || h < 8 || w > 32767 || h > 32767) return cs_ctx_fail(c, CS_ERR_INVALID_ARG, "image size unsupported by the line descriptor");
+    const size_t px = (size_t)n_frames * w * h;
+    int rc;
+    const uint8_t *d_img = imgs;
+    if (!imgs_on_device) {
+        if ((rc = ed_ensure(c, S.img, (size_t)n_frames * h * stride))) return rc;
+        if (cudaMemcpyAsync(S.img.p, imgs, (size_t)n_frames * h * stride, cudaMemcpyHostToDevice, st) != cudaSuccess)
+            return cs_ctx_fail(c, CS_ERR_CUDA, "H2D copy of frames failed");
+        d_img = (const uint8_t *)S.img.p;
+    }
+    if ((rc = ed_ensure(c, S.blur, px)) || (rc = ed_ensure(c, S.dx, px * 2)) || (rc = ed_ensure(c, S.dy, px * 2)) || (rc = ed_ensure(c, S.g, px * 2)) ||
+        (rc = ed_ensure(c, S.dir, px)) || (rc = ed_ensure(c, S.err, 16)))
+        return rc;
+    cudaMemsetAsync(S.err.p, 0, 16, st);
+    const dim3 g_tile((w + EDF_TW - 1) / EDF_TW, (h + EDF_TH - 1) / EDF_TH, n_frames);
+    CUtensorMap tm;
+    if (cs_ctx_use_tma(c) && channels == 3 && stride == 3 * w && cs_make_tmap_bytes(&tm, d_img, 3 * (int64_t)w, (int64_t)n_frames * h, stride, EDF_BOXW, EDF_TH + 6))
+        k_ed_front<true><<<g_tile, 256, 0, st>>>(tm, d_img, w, h, stride, channels, (uint8_t *)S.blur.p, (int16_t *)S.dx.p, (int16_t *)S.dy.p, (int16_t *)S.g.p,
+                                                (uint8_t *)S.dir.p, (int32_t *)S.err.p);
+    else
+        k_ed_front<false><<<g_tile, 256, 0, st>>>(tm, d_img, w, h, stride, channels, (uint8_t *)S.blur.p, (int16_t *)S.dx.p, (int16_t *)S.dy.p, (int16_t *)S.g.p,
+                                                 (uint8_t *)S.dir.p, (int32_t *)S.err.p);
+    cs_ctx_count_launches(c, 1);
+    if (cudaGetLastError() != cudaSuccess) return cs_ctx_fail(c, CS_ERR_CUDA, "Sobel-map kernel launch failed");
+    S.last_frames = 0; /* the detector's debug views no longer describe these buffers */
+    *d_dx = (const int16_t *)S.dx.p;
+    *d_dy = (const int16_t *)S.dy.p;
     return CS_OK;
 }
 

@@ -83,4 +83,19 @@ void cs_edl_destroy(void *state);           /* called from cs_destroy */
 int cs_edl_run(cs_ctx *c, const uint8_t *imgs, bool imgs_on_device, int n_frames, int w, int h, int stride, int channels, float line_length_thres,
                int cap, const float **d_lines, const int32_t **d_counts);
 
+/* the same run, also keeping per kept segment what the descriptor needs of its key line (binary_descriptor.cpp:526-540): d_extra holds
+ * cap x 2 floats per frame, {KeyLine::angle (lineDirection_), KeyLine::numOfPixels as an integer's bits}, parallel to d_lines */
+int cs_edl_run_keylines(cs_ctx *c, const uint8_t *imgs, bool imgs_on_device, int n_frames, int w, int h, int stride, int channels,
+                        float line_length_thres, int cap, const float **d_lines, const int32_t **d_counts, const float **d_extra,
+                        const int16_t **d_dx, const int16_t **d_dy /* the detector's own Sobel maps, the ones the descriptor reads */);
+/* BinaryDescriptor::computeSobel for octave 0 (binary_descriptor.cpp:352-398: GaussianBlur 5 x 5 sigma 1, Sobel 3 x 3 to 16S) = the front
+ * end of the EDLines detector: the two int16 maps of every frame, in HBM, owned by the EDLines workspace */
+int cs_edl_sobel_maps(cs_ctx *c, const uint8_t *imgs, bool imgs_on_device, int n_frames, int w, int h, int stride, int channels,
+                      const int16_t **d_dx, const int16_t **d_dy);
+/* LSD flavour of detect_filter_lines from host frames (the body of cs_detect_lines_batch's LSD branch): filtered segments + counts in HBM */
+int cs_lsd_run_host(cs_ctx *c, const uint8_t *imgs, int n_frames, int w, int h, int stride, int channels, float line_length_thres, int cap,
+                    const float **d_lines, const int32_t **d_counts, const uint8_t **d_frames);
+void **cs_ctx_lbd_slot(cs_ctx *c);          /* owned by cs_lbd.cu */
+void cs_lbd_destroy(void *state);           /* called from cs_destroy */
+
 #endif

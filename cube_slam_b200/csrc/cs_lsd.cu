@@ -1628,6 +1628,19 @@ int cs_lsd_run_device(cs_ctx *c, const uint8_t *d_imgs, int n_frames, int w, int
     return CS_OK;
 }
 
+/* host frames in, results stay in HBM (the descriptor path, cs_lbd.cu) */
+int cs_lsd_run_host(cs_ctx *c, const uint8_t *imgs, int n_frames, int w, int h, int stride, int channels, float line_length_thres, int cap,
+                    const float **d_lines, const int32_t **d_counts, const uint8_t **d_frames)
+{
+    LsdState *S = state_of(c);
+    const int rc = lsd_run(c, imgs, false, n_frames, w, h, stride, channels, line_length_thres, cap, *S);
+    if (rc) return rc;
+    *d_lines = (const float *)S->out.p;
+    *d_counts = (const int32_t *)S->nout.p;
+    *d_frames = (const uint8_t *)S->img.p; /* the frames as uploaded (same stride), still in HBM */
+    return CS_OK;
+}
+
 void cs_lsd_destroy(void *state)
 {
     LsdState *S = (LsdState *)state;

@@ -225,6 +225,67 @@ int cs_debug_lsd_prof(cs_ctx *ctx, uint64_t *out16, int reset);
 int cs_debug_edlines(cs_ctx *ctx, int frame, uint8_t *blur, int16_t *dx, int16_t *dy, int16_t *g, uint8_t *dir, int32_t *anchors,
                      int32_t *n_anchors, uint8_t *edge, float *raw_lines, int32_t *n_raw, int cap_raw);
 
+/* ---- line descriptors and matching (the rest of class line_lbd_detect) -------------------------------------- */
+/* The KeyLine fields callers and the descriptor read (line_lbd/include/line_lbd/line_descriptor/descriptor.hpp:104-172) for octave 0, where
+ * startPoint == sPointInOctave; KeyLine::pt is the mid point of the two ends, KeyLine::octave is 0. */
+typedef struct cs_keyline {
+    float start_x, start_y, end_x, end_y; /* startPointX / Y, endPointX / Y */
+    float angle;                          /* KeyLine::angle: EDLines' lineDirection_, LSD's atan2(dy, dx) (LSDDetector.cpp:244) */
+    float line_length;                    /* KeyLine::lineLength */
+    float response;                       /* lineLength / max(width, height) */
+    float size;                           /* (endX - startX) * (endY - startY) */
+    int32_t num_pixels;                   /* KeyLine::numOfPixels: the length of the descriptor's support region */
+    int32_t class_id;                     /* position in the list this call returns (0 .. n-1) */
+} cs_keyline;
+/* cv::DMatch as match_line_descrip returns it */
+typedef struct cs_dmatch {
+    int32_t query_idx, train_idx, img_idx;
+    float distance;
+} cs_dmatch;
+
+/* KeyLine fields of the LSD flavour from n x 4 segment rows, e.g. cs_detect_lines' output (LSDDetector::detectImpl,
+ * line_lbd/libs/LSDDetector.cpp:226-250: length, cv::LineIterator pixel count, angle, size, response).  Host-only, needs no context.
+ * (line_lbd_detect::get_line_descriptors goes through mat_to_keylines, line_lbd_allclass.cpp:68-108, which reads KeyLine fields before it
+ * sets them and leaves class_id / octave unset in what it returns: undefined in the reference.  This is the defined equivalent.) */
+int cs_keylines_from_lines(const float *lines_xyxy, int n, int width, int height, cs_keyline *out);
+
+/* BinaryDescriptor::compute(image, keylines, descriptors[, returnFloatDescr]) (line_lbd/libs/binary_descriptor.cpp:587-592, computeImpl
+ * :603-790, computeSobel :352-398, computeLBD :1146-1509) as line_lbd_detect calls it: row i of desc32 (n x 32 bytes) is the binary LBD
+ * descriptor of key line i; desc72 (optional, n x 72 floats) the float descriptor it is made from.  Reads start / end point, angle and
+ * num_pixels of each key line.  The batch form takes frames laid out back to back and a CSR of key lines per frame. */
+int cs_lbd_compute(cs_ctx *ctx, const uint8_t *img, int width, int height, int stride, int channels, const cs_keyline *keylines, int n,
+                   uint8_t *desc32, float *desc72);
+int cs_lbd_compute_batch(cs_ctx *ctx, const uint8_t *imgs, int n_frames, int width, int height, int stride, int channels,
+                         const cs_keyline *keylines, const int32_t *keyline_offsets /* n_frames + 1 */, uint8_t *desc32, float *desc72);
+
+/* line_lbd_detect::detect_descrip_lines(gray_img, keylines_out, line_descrips) (line_lbd/class/line_lbd_allclass.cpp:253-272): detect
+ * (LSD or EDLines), describe, keep octave 0 and lineLength > line_length_thres.  keylines / desc32 have room for *n_inout lines (batch:
+ * max_lines_per_frame per frame, frame f at f * max_lines_per_frame); on return *n_inout (n_lines[f]) is the number kept.  The Mat
+ * overload (:224-250, no length filter) is the same call with line_length_thres = -1; detect_descrip_lines_octaves (:285-339) for one
+ * octave is this call followed by the start / end swap of :321-330 on the host (shim/line_lbd_b200.cpp, cube_slam_b200/line_lbd.py). */
+int cs_detect_descrip_lines(cs_ctx *ctx, const uint8_t *img, int width, int height, int stride, int channels, const cs_line_params *params,
+                            cs_keyline *keylines, uint8_t *desc32, int32_t *n_inout);
+int cs_detect_descrip_lines_batch(cs_ctx *ctx, const uint8_t *imgs, int n_frames, int width, int height, int stride, int channels,
+                                  const cs_line_params *params, cs_keyline *keylines, uint8_t *desc32, int32_t max_lines_per_frame,
+                                  int32_t *n_lines /* n_frames */);
+
+/* line_lbd_detect::match_line_descrip(query, train, good_matches, matching_dist_thres) (line_lbd_allclass.cpp:341-356) over
+ * BinaryDescriptorMatcher::match (line_lbd/libs/binary_descriptor_matcher.cpp:196-262): for every query descriptor the train descriptor
+ * at the smallest Hamming distance -- of several, the one the reference's multi-index hash meets first -- kept when distance < thres.
+ * matches has room for n_query entries; they come in query order.  Two cases the reference leaves undefined are defined here: a nearest
+ * code further than 128 bits away (its trainIdx is never written there) reports train_idx -1, and a query none of whose bytes is within 4
+ * bits of any train code's (the hash never visits anything) yields no match, as in the reference.
+ * The batch form matches n_pairs independent (query set, train set) pairs given as CSRs of 32-byte rows: pair p's matches start at
+ * matches[query_offsets[p]], n_matches[p] of them. */
+int cs_match_line_descrip(cs_ctx *ctx, const uint8_t *query32, int n_query, const uint8_t *train32, int n_train, float matching_dist_thres,
+                          cs_dmatch *matches, int32_t *n_matches);
+int cs_match_line_descrip_batch(cs_ctx *ctx, const uint8_t *query32, const int32_t *query_offsets, const uint8_t *train32,
+                                const int32_t *train_offsets, int n_pairs, float matching_dist_thres, cs_dmatch *matches, int32_t *n_matches);
+
+/* tests: what the host side hands the descriptor kernel -- per key line {mid x, mid y, cos, sin, length, frame} (6 x 4 bytes) -- and the
+ * two Gaussian weight tables F_g (63) and F_l (21) as floats (binary_descriptor.cpp:140-179).  Host-only, needs no context. */
+int cs_lbd_debug_prepare(const cs_keyline *keylines, int n, void *lines24, float *coef_g63, float *coef_l21);
+
 /* How the reference draws a detected cuboid (plot_image_with_cuboid, detect_3d_cuboid/src/object_3d_util.cpp:54-131, called with
  * whether_save_final_images / whether_plot_final_images, box_proposal_detail.cpp:541-556): its 12 edges in the reference's order, each
  * {x1, y1, x2, y2, B, G, R, thickness}; the caller rasterises them with cv::line(..., CV_AA) exactly as the reference does

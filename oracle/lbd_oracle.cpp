@@ -314,17 +314,16 @@ extern "C" int lbd_orc_detect_keylines(const uint8_t *img, int w, int h, int str
 /* detect_descrip_lines_octaves' reordering (line_lbd_allclass.cpp:321-330), one octave: start x <= end x, angle folded into [-pi/2, pi/2] */
 extern "C" void lbd_orc_order_keylines(lbd_keyline *kl, int n)
 {
-    const float PI = 3.14159265f; /* line_lbd_allclass.h */
+    const double PI = 3.14159265; /* line_lbd_allclass.cpp:19, a double: the comparison and the fold are done in double (:272-281) */
     for (int i = 0; i < n; i++)
         if (kl[i].sx > kl[i].ex) {
             std::swap(kl[i].sx, kl[i].ex);
             std::swap(kl[i].sy, kl[i].ey);
-            float a = kl[i].angle;
+            const float a = kl[i].angle;
             if (a > PI / 2)
-                a = a - PI;
+                kl[i].angle = (float)(a - PI);
             else if (a < -PI / 2)
-                a = a + PI;
-            kl[i].angle = a;
+                kl[i].angle = (float)(a + PI);
         }
 }
 

@@ -514,7 +514,7 @@ def _ref_all():
     if _REF_ALL is None:
         _REF_ALL = C.CDLL(_REF_ALL_PATH)
         _REF_ALL.ref_detect_filter_lines.restype = C.c_int
-    for name in ("ref_detect_descrip_lines", "ref_lbd_compute", "ref_match_line_descrip"):
+    for name in ("ref_detect_descrip_lines", "ref_detect_descrip_lines_octaves", "ref_lbd_compute", "ref_match_line_descrip"):
         getattr(_REF_ALL, name).restype = C.c_int
     return _REF_ALL
 
@@ -528,6 +528,18 @@ def ref_detect_descrip_lines(img, use_LSD=True, line_length_thres=15.0, cap=8192
                                             _p(desc, C.c_uint8), cap)
     if n < 0 or n > cap:
         raise RuntimeError("ref_detect_descrip_lines failed (%d)" % n)
+    return kl[:n].copy(), desc[:n].copy()
+
+
+def ref_detect_descrip_lines_octaves(img, use_LSD=True, line_length_thres=15.0, cap=8192):
+    """The reference's OWN detect_descrip_lines_octaves, octave 0 -> (key lines with start x <= end x, n x 32 descriptors)."""
+    img, w, h, ch = _img_args(img)
+    kl = np.zeros(cap, KEYLINE_DTYPE)
+    desc = np.zeros((cap, 32), np.uint8)
+    n = _ref_all().ref_detect_descrip_lines_octaves(_p(img, C.c_uint8), w, h, ch, int(bool(use_LSD)), C.c_float(line_length_thres),
+                                                    kl.ctypes.data_as(C.c_void_p), _p(desc, C.c_uint8), cap)
+    if n < 0 or n > cap:
+        raise RuntimeError("ref_detect_descrip_lines_octaves failed (%d)" % n)
     return kl[:n].copy(), desc[:n].copy()
 
 

@@ -118,6 +118,43 @@ extern "C" int ref_detect_descrip_lines(const uint8_t *img, int w, int h, int ch
     }
 }
 
+/* detect_descrip_lines_octaves(gray_img, keylines_out, line_descrips) (line_lbd_allclass.cpp:285-339), octave 0 of the one-octave detector */
+extern "C" int ref_detect_descrip_lines_octaves(const uint8_t *img, int w, int h, int channels, int use_LSD, float line_length_thres, ref_keyline *kl_out,
+                                                uint8_t *desc_out, int cap)
+{
+    try {
+        line_lbd_detect &det = ref_detector(use_LSD, line_length_thres);
+        cv::Mat image(h, w, channels == 3 ? CV_8UC3 : CV_8UC1);
+        std::memcpy(image.data, img, (size_t)w * h * channels);
+        std::vector<std::vector<KeyLine>> keylines;
+        std::vector<cv::Mat> descrips;
+        det.detect_descrip_lines_octaves(image, keylines, descrips);
+        if (keylines.size() != 1 || descrips.size() != 1) return -2;
+        const int n = (int)keylines[0].size();
+        if (n > 0 && (descrips[0].rows != n || descrips[0].cols != 32)) return -3;
+        for (int i = 0; i < n && i < cap; i++) {
+            const KeyLine &k = keylines[0][i];
+            ref_keyline &o = kl_out[i];
+            o.sx = k.startPointX;
+            o.sy = k.startPointY;
+            o.ex = k.endPointX;
+            o.ey = k.endPointY;
+            if (o.sx != k.sPointInOctaveX || o.sy != k.sPointInOctaveY || o.ex != k.ePointInOctaveX || o.ey != k.ePointInOctaveY) return -5;
+            o.angle = k.angle;
+            o.line_length = k.lineLength;
+            o.response = k.response;
+            o.size = k.size;
+            o.num_pixels = k.numOfPixels;
+            o.class_id = k.class_id;
+            std::memcpy(desc_out + (size_t)i * 32, descrips[0].ptr(i), 32);
+        }
+        return n;
+    } catch (const std::exception &e) {
+        fprintf(stderr, "ref_detect_descrip_lines_octaves: %s\n", e.what());
+        return -1;
+    }
+}
+
 /* BinaryDescriptor::compute on caller-given key lines (octave 0, class_id as given): desc n x 32 bytes and / or fdesc n x 72 floats */
 extern "C" int ref_lbd_compute(const uint8_t *img, int w, int h, int channels, const ref_keyline *kl, int n, uint8_t *desc, float *fdesc)
 {

@@ -67,6 +67,21 @@ def test_sequence_frames_and_matches_between_neighbours(ref, fixture_b):
     assert len(ref.lbd_match(d0, d1, 40.0)[0]) >= 3
 
 
+@pytest.mark.parametrize("use_lsd", [True, False])
+def test_octaves_variant_orders_the_ends(ref, fixture_a, use_lsd):
+    """detect_descrip_lines_octaves (line_lbd_allclass.cpp:285-339): start x <= end x, the angle folded by normalize_to_PI in double."""
+    img = fixture_a["img"]
+    kr, dr = ref.ref_detect_descrip_lines_octaves(img, use_lsd, 15.0)
+    ko = ref.lbd_detect_keylines(img, use_lsd, 15.0)
+    do = ref.lbd_compute(img, ko)
+    kz = ref.lbd_order_keylines(ko)
+    assert len(kr) == len(kz) and (kz["sx"] != ko["sx"]).any()
+    for f in FIELDS:
+        np.testing.assert_array_equal(kr[f], kz[f], err_msg=f)
+    np.testing.assert_array_equal(kr["class_id"], np.arange(len(kr)))
+    np.testing.assert_array_equal(dr, do)                       # descriptors are computed before the swap
+
+
 @pytest.mark.parametrize("seed,w,h,kind", [(7, 640, 480, "indoor"), (8, 1242, 375, "kitti")])
 def test_synthetic_frames(ref, seed, w, h, kind):
     from cube_slam_b200 import synthetic as S
