@@ -169,3 +169,64 @@ def test_against_the_committed_goldens(det):
     (k0, d0), (k1, d1) = det.detect_descrip_lines_batch(np.stack(imgs))
     m = det.match_line_descrip(d0, d1, g["match"]["thres"])
     assert [list(map(int, x)) for x in zip(m["query_idx"], m["train_idx"], m["distance"])] == g["match"]["triples"]
+
+
+SHIM = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle", "_ref", "libshim_line.so")
+
+
+@pytest.mark.parametrize("use_lsd", [1, 0])
+def test_cpp_shim_descriptor_and_matcher_members(oracle, fixture_a, fixture_b, use_lsd):
+    """shim/line_lbd_b200.cpp's descriptor / matcher members, compiled against the reference's own class header and called as a user of
+    class line_lbd_detect calls them (shim/test/line_shim_driver.cpp -> oracle/_ref/libshim_line.so): detect_descrip_lines (both
+    overloads), detect_descrip_lines_octaves, get_line_descriptors, match_line_descrip."""
+    import ctypes as C
+    if not os.path.exists(SHIM):
+        pytest.skip("oracle/_ref/libshim_line.so not built (needs the reference's headers at build time)")
+    import cube_slam_b200  # noqa: F401
+    L = C.CDLL(SHIM)
+    for name in ("shim_line_detect_descrip", "shim_line_descriptors_of", "shim_line_match"):
+        getattr(L, name).restype = C.c_int
+    img = np.ascontiguousarray(fixture_a["img"], np.uint8)
+    h, w, ch = img.shape
+    u8 = C.POINTER(C.c_uint8)
+    cap = 8192
+    res = {}
+    for mode in (0, 1, 2):
+        kl = np.zeros(cap, oracle.KEYLINE_DTYPE)
+        desc = np.zeros((cap, 32), np.uint8)
+        n = L.shim_line_detect_descrip(img.ctypes.data_as(u8), w, h, ch, use_lsd, C.c_float(15.0), mode, kl.ctypes.data_as(C.c_void_p),
+                                       desc.ctypes.data_as(u8), cap)
+        assert n >= 0
+        res[mode] = (kl[:n], desc[:n])
+    want = oracle.lbd_detect_keylines(img, bool(use_lsd), 15.0)
+    wdesc = oracle.lbd_compute(img, want)
+    for mode, wk in ((0, want), (1, oracle.lbd_order_keylines(want))):
+        kl, desc = res[mode]
+        assert len(kl) == len(wk)
+        for f in ("sx", "sy", "ex", "ey", "angle", "line_length", "response", "size", "num_pixels"):
+            np.testing.assert_array_equal(kl[f], wk[f], err_msg="mode %d %s" % (mode, f))
+        np.testing.assert_array_equal(kl["class_id"], np.arange(len(kl)))
+        np.testing.assert_array_equal(desc, wdesc)
+    wall = oracle.lbd_detect_keylines(img, bool(use_lsd), -1.0)
+    kl, desc = res[2]
+    assert len(kl) == len(wall)
+    for f in ("sx", "sy", "ex", "ey"):
+        np.testing.assert_array_equal(kl[f], wall[f])
+    np.testing.assert_array_equal(desc, oracle.lbd_compute(img, wall))
+    # get_line_descriptors on the rows detect_filter_lines returned
+    rows = np.ascontiguousarray(np.stack([want["sx"], want["sy"], want["ex"], want["ey"]], 1), np.float32)
+    d2 = np.zeros((len(rows), 32), np.uint8)
+    assert L.shim_line_descriptors_of(img.ctypes.data_as(u8), w, h, ch, rows.ctypes.data_as(C.POINTER(C.c_float)), len(rows), d2.ctypes.data_as(u8)) == len(rows)
+    np.testing.assert_array_equal(d2, oracle.lbd_compute(img, oracle.lbd_keylines_from_lsd(rows, w, h)))
+    # match_line_descrip between two frames of the sequence
+    f0, f1 = fixture_b["frames"][0][0], fixture_b["frames"][1][0]
+    d0 = oracle.lbd_compute(f0, oracle.lbd_detect_keylines(f0, True, 15.0))
+    d1 = oracle.lbd_compute(f1, oracle.lbd_detect_keylines(f1, True, 15.0))
+    qi, ti, di = np.zeros(len(d0), np.int32), np.zeros(len(d0), np.int32), np.zeros(len(d0), np.float32)
+    n = L.shim_line_match(d0.ctypes.data_as(u8), len(d0), d1.ctypes.data_as(u8), len(d1), C.c_float(40.0), qi.ctypes.data_as(C.POINTER(C.c_int32)),
+                          ti.ctypes.data_as(C.POINTER(C.c_int32)), di.ctypes.data_as(C.POINTER(C.c_float)))
+    wq, wt, wd = oracle.lbd_match(d0, d1, 40.0)
+    assert n == len(wq) >= 3
+    np.testing.assert_array_equal(qi[:n], wq)
+    np.testing.assert_array_equal(ti[:n], wt)
+    np.testing.assert_array_equal(di[:n], wd)
