@@ -163,6 +163,18 @@ class ClockSampler(threading.Thread):
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": reasons, "samples": len(self.rows)}
 
 
+def time_lbd_subprocess():
+    """The descriptor / matcher half of line_lbd_detect, timed by tools/time_lbd.py in a process of its own after
+    the timed region (whatever happens there cannot touch the numbers above); its JSON object, or why there is none."""
+    try:
+        r = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "time_lbd.py")], capture_output=True, text=True, timeout=240)
+        if r.returncode != 0:
+            return {"error": (r.stderr or r.stdout).strip().splitlines()[-1][:300] if (r.stderr or r.stdout).strip() else "exit %d" % r.returncode}
+        return json.loads(r.stdout.strip().splitlines()[-1])
+    except Exception as e:  # noqa: BLE001 -- an extra key must never cost the bench line
+        return {"error": "%s: %s" % (type(e).__name__, str(e)[:300])}
+
+
 def make_workload(name, rank, seed_base=20260922, frames=None):
     from cube_slam_b200 import synthetic as S
     F, w, h, nb, kind, poisson, over, desc = WORKLOADS[name]
@@ -693,6 +705,8 @@ def run_ours(args, rank, world, local_rank):
     line.update(other)
     if per_rank:
         line["per_rank"] = per_rank
+    if world == 1 and not args.no_extra:
+        line["lbd"] = time_lbd_subprocess()
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
