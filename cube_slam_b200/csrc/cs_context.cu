@@ -547,7 +547,7 @@ int store_batch(cs_ctx *c, const uint8_t *imgs, int n_frames, int width, int hei
     c->prepared = false;
     c->online_lines = online != nullptr;
     if (online) {
-        if (online->numoctaves != 1) return fail(c, CS_ERR_UNSUPPORTED, "only one octave is supported");
+        if (online->numoctaves < 1) return fail(c, CS_ERR_INVALID_ARG, "numoctaves must be at least 1"); /* > 1: same lines, see cs_detect_lines_batch */
         c->line_prm = *online;
         c->online_cap = std::max(64, std::min(c->max_lines > 0 ? c->max_lines : 1024, 4096));
     }

@@ -287,7 +287,8 @@ int cs_detect_descrip_lines_batch(cs_ctx *c, const uint8_t *imgs, int n_frames, 
     int rc = check_image_args(c, imgs, n_frames, width, height, stride, channels);
     if (rc) return rc;
     if (!params || !keylines || !desc32 || !n_lines || max_lines_per_frame <= 0) return cs_ctx_fail(c, CS_ERR_INVALID_ARG, "null or empty argument");
-    if (params->numoctaves != 1) return cs_ctx_fail(c, CS_ERR_UNSUPPORTED, "only one octave is supported (detect_descrip_lines keeps octave 0 only)");
+    /* more octaves: both overloads of detect_descrip_lines keep octave 0 only (:239,266), whose lines and Sobel maps do not depend on the others */
+    if (params->numoctaves < 1) return cs_ctx_fail(c, CS_ERR_INVALID_ARG, "numoctaves must be at least 1");
     cudaSetDevice(cs_ctx_device(c));
     cudaStream_t st = cs_ctx_stream(c);
     const int cap = max_lines_per_frame;

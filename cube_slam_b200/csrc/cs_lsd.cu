@@ -1660,7 +1660,10 @@ int cs_detect_lines_batch(cs_ctx *c, const uint8_t *imgs, int n_frames, int widt
         return cs_ctx_fail(c, CS_ERR_INVALID_ARG, "null or empty argument");
     if (channels != 1 && channels != 3) return cs_ctx_fail(c, CS_ERR_INVALID_ARG, "channels must be 1 or 3"); /* LSDDetector.cpp:163-164 throws on depth != 0 */
     if (stride < width * channels) return cs_ctx_fail(c, CS_ERR_INVALID_ARG, "stride smaller than a row");
-    if (params->numoctaves != 1) return cs_ctx_fail(c, CS_ERR_UNSUPPORTED, "only one octave is supported (filter_lines keeps octave 0 only)");
+    /* More octaves change nothing here: filter_lines keeps octave 0 only (line_lbd_allclass.cpp:200-207) and octave 0 is detected first and
+     * independently of the others in both detectors, so the matrix is the one-octave one (checked against the compiled reference with 2 and
+     * 3 octaves, tests/test_oracle_ref_octaves.py). */
+    if (params->numoctaves < 1) return cs_ctx_fail(c, CS_ERR_INVALID_ARG, "numoctaves must be at least 1");
     cudaSetDevice(cs_ctx_device(c));
     const float *d_out = nullptr;
     const int32_t *d_nout = nullptr;

@@ -120,6 +120,8 @@ class line_lbd_detect(object):
     def detect_descrip_lines_octaves(self, gray_img, cap=8192):
         """detect_descrip_lines_octaves (:285-339) for the one octave the class is built with: the kept key lines with start x <= end x
         (ends swapped and the angle folded into [-pi/2, pi/2] where needed, :321-330) -> ([key lines], [descriptors]), one entry per octave."""
+        if self.numoctaves_ != 1:
+            raise CubeSlamError("detect_descrip_lines_octaves is provided for one octave (the library detects octave 0)")
         kl, desc = self.detect_descrip_lines(gray_img, cap)
         kl = kl.copy()
         PI = 3.14159265                     # line_lbd_allclass.cpp:19, a double: normalize_to_PI compares and folds in double (:272-281)

@@ -90,7 +90,8 @@ typedef struct cs_cuboid_rec {
  * line_lbd/libs/binary_descriptor.cpp:1511-1522). */
 typedef struct cs_line_params {
     int32_t use_LSD;            /* line_lbd_allclass.h:29; class default 0, object_slam sets 1 (main_obj.cpp:365) */
-    int32_t numoctaves;         /* :26, default 1 (only octave 0 survives filter_lines) */
+    int32_t numoctaves;         /* :26, default 1.  Any value >= 1 gives the same result: only octave 0 survives filter_lines (:200-207) and
+                                   detect_descrip_lines (:239,266), and octave 0 does not depend on the higher ones */
     float octaveratio;          /* :27, default 1 */
     float line_length_thres;    /* :30, class default 50, object_slam uses 15 */
 } cs_line_params;

@@ -615,3 +615,33 @@ def detect_frames_batch(imgs, K, Ts, boxes_list, lines_list=None, params=None, l
     if want_records:
         res["records"], res["counts"], res["box_off"] = out, counts, box_off
     return res
+
+
+def ref_detect_filter_lines_octaves(img, use_LSD=True, line_length_thres=15.0, numoctaves=2, cap=8192):
+    """The reference's OWN detect_filter_lines from a detector built with `numoctaves` octaves (ratio 2) -> (n x 4 float32, number of raw key
+    lines over all octaves)."""
+    img, w, h, ch = _img_args(img)
+    L = _ref_all()
+    L.ref_detect_filter_lines_octaves.restype = C.c_int
+    out = np.zeros((cap, 4), np.float32)
+    n_raw = C.c_int(0)
+    n = L.ref_detect_filter_lines_octaves(_p(img, C.c_uint8), w, h, ch, int(bool(use_LSD)), C.c_float(line_length_thres), int(numoctaves), _p(out, C.c_float), cap,
+                                          C.byref(n_raw))
+    if n < 0 or n > cap:
+        raise RuntimeError("ref_detect_filter_lines_octaves failed (%d)" % n)
+    return out[:n].copy(), n_raw.value
+
+
+def ref_minicv_pyrdown(gray, dw, dh):
+    gray = np.ascontiguousarray(gray, np.uint8)
+    out = np.zeros((dh, dw), np.uint8)
+    _ref_all().ref_minicv_pyrdown(_p(gray, C.c_uint8), gray.shape[1], gray.shape[0], _p(out, C.c_uint8), dw, dh)
+    return out
+
+
+def ref_minicv_resize_half(gray):
+    gray = np.ascontiguousarray(gray, np.uint8)
+    h, w = gray.shape
+    out = np.zeros((int(np.rint(h * 0.5)), int(np.rint(w * 0.5))), np.uint8)
+    _ref_all().ref_minicv_resize_half(_p(gray, C.c_uint8), w, h, _p(out, C.c_uint8))
+    return out

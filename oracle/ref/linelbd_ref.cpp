@@ -67,6 +67,48 @@ extern "C" int ref_detect_filter_lines(const uint8_t *img, int w, int h, int cha
     }
 }
 
+/* detect_filter_lines of a detector built with MORE THAN ONE octave (line_lbd_detect(numoctaves, 2.0f), as line_lbd/src/detect_lines.cpp:57-60
+ * parameterises it): filter_lines keeps octave 0 only (:200-207), so the matrix must be the one-octave one -- the claim the product's
+ * acceptance of numoctaves > 1 rests on (tests/test_oracle_ref_octaves.py) */
+extern "C" int ref_detect_filter_lines_octaves(const uint8_t *img, int w, int h, int channels, int use_LSD, float line_length_thres, int numoctaves,
+                                               float *out, int cap, int *n_raw_all_octaves)
+{
+    try {
+        line_lbd_detect det(numoctaves, 2.0f);
+        det.use_LSD = use_LSD != 0;
+        det.line_length_thres = line_length_thres;
+        cv::Mat image(h, w, channels == 3 ? CV_8UC3 : CV_8UC1);
+        std::memcpy(image.data, img, (size_t)w * h * channels);
+        std::vector<KeyLine> raw;
+        det.detect_raw_lines(image, raw);
+        if (n_raw_all_octaves) *n_raw_all_octaves = (int)raw.size();
+        cv::Mat lines;
+        det.detect_filter_lines(image, lines);
+        const int n = lines.rows < cap ? lines.rows : cap;
+        if (n) std::memcpy(out, lines.data, sizeof(float) * 4 * (size_t)n);
+        return lines.rows;
+    } catch (const std::exception &e) {
+        fprintf(stderr, "ref_detect_filter_lines_octaves: %s\n", e.what());
+        return -1;
+    }
+}
+
+/* the stand-in's pyrDown, for pinning against cv2 */
+extern "C" void ref_minicv_pyrdown(const uint8_t *src, int w, int h, uint8_t *dst, int dw, int dh)
+{
+    cv::Mat a(h, w, CV_8UC1), b;
+    std::memcpy(a.data, src, (size_t)w * h);
+    cv::pyrDown(a, b, cv::Size(dw, dh));
+    std::memcpy(dst, b.data, (size_t)dw * dh);
+}
+extern "C" void ref_minicv_resize_half(const uint8_t *src, int w, int h, uint8_t *dst)
+{
+    cv::Mat a(h, w, CV_8UC1), b;
+    std::memcpy(a.data, src, (size_t)w * h);
+    cv::resize(a, b, cv::Size(), 0.5, 0.5);
+    std::memcpy(dst, b.data, (size_t)b.cols * b.rows);
+}
+
 /* the KeyLine fields anything downstream reads, octave 0 (same layout as oracle/lbd_oracle.cpp's lbd_keyline) */
 struct ref_keyline {
     float sx, sy, ex, ey, angle, line_length, response, size;

@@ -473,11 +473,30 @@ inline void resize(InputArray src_, OutputArray dst, Size dsize, double fx, doub
     const Mat src = src_.getMat();
     if (src.type() == CV_8UC1 && dsize.area() == 0) {
         /* OctaveKeyLines shrinks the image for the NEXT octave after every octave, also after the last one (binary_descriptor.cpp:838):
-         * with numOfOctave_ = 1 the result is never read.  Sizes as cv::resize computes them, contents a plain 2 x 2 pick. */
+         * with numOfOctave_ = 1 the result is never read; with more octaves it feeds the detection of the higher ones, whose lines
+         * filter_lines drops again (tests/test_oracle_ref_octaves.py).  Sizes as cv::resize computes them.  Halving an image of even size
+         * is the exact 2 x 2 mean with rounding, (a + b + c + d + 2) >> 2, as cv2 computes INTER_LINEAR there (checked against cv2 4.13);
+         * any other case is plain bilinear interpolation at pixel centres, not pinned. */
         const int dw = (int)std::lrint(src.cols * fx), dh = (int)std::lrint(src.rows * fy);
         Mat out(dh, dw, CV_8UC1);
-        for (int y = 0; y < dh; y++)
-            for (int x = 0; x < dw; x++) out.data[(size_t)y * dw + x] = src.data[(size_t)std::min(src.rows - 1, (int)(y / fy)) * src.cols + std::min(src.cols - 1, (int)(x / fx))];
+        if (fx == 0.5 && fy == 0.5 && src.cols % 2 == 0 && src.rows % 2 == 0) {
+            for (int y = 0; y < dh; y++)
+                for (int x = 0; x < dw; x++) {
+                    const uchar *p = src.data + (size_t)(2 * y) * src.cols + 2 * x;
+                    out.data[(size_t)y * dw + x] = (uchar)((p[0] + p[1] + p[src.cols] + p[src.cols + 1] + 2) >> 2);
+                }
+        } else {
+            for (int y = 0; y < dh; y++)
+                for (int x = 0; x < dw; x++) {
+                    const double sx = std::max(0.0, (x + 0.5) / fx - 0.5), sy = std::max(0.0, (y + 0.5) / fy - 0.5);
+                    const int x0 = std::min((int)sx, src.cols - 1), y0 = std::min((int)sy, src.rows - 1);
+                    const int x1 = std::min(x0 + 1, src.cols - 1), y1 = std::min(y0 + 1, src.rows - 1);
+                    const double ax = sx - x0, ay = sy - y0;
+                    const double v = (1 - ay) * ((1 - ax) * src.data[(size_t)y0 * src.cols + x0] + ax * src.data[(size_t)y0 * src.cols + x1]) +
+                                     ay * ((1 - ax) * src.data[(size_t)y1 * src.cols + x0] + ax * src.data[(size_t)y1 * src.cols + x1]);
+                    out.data[(size_t)y * dw + x] = (uchar)std::lrint(v);
+                }
+        }
         dst.assign(out);
         return;
     }
@@ -637,7 +656,37 @@ inline void merge(const std::vector<Mat> &, OutputArray) { minicv_unreachable("m
 template <typename P, typename... A> inline void line(InputOutputArray, P, P, const Scalar &, A...) { minicv_unreachable("line"); }
 inline void bitwise_xor(InputArray, InputArray, OutputArray) { minicv_unreachable("bitwise_xor"); }
 inline int countNonZero(InputArray) { minicv_unreachable("countNonZero"); }
-template <typename... A> inline void pyrDown(InputArray, OutputArray, A...) { minicv_unreachable("pyrDown"); } /* BinaryDescriptor::computeGaussianPyramid: the descriptor side */
+/* cv::pyrDown on an 8-bit image (LSDDetector::computeGaussianPyramid, LSDDetector.cpp:66-72, and BinaryDescriptor::computeGaussianPyramid
+ * for octaves above 0): the separable 5-tap kernel (1 4 6 4 1) / 16 in both directions at the even source positions, BORDER_REFLECT_101,
+ * one rounding (sum + 128) >> 8.  Equal to cv2.pyrDown bit for bit (tests/test_oracle_ref_octaves.py). */
+inline void pyrDown(InputArray src_, OutputArray dst, Size dsize)
+{
+    const Mat src = src_.getMat();
+    if (src.type() != CV_8UC1) minicv_unreachable("pyrDown other than 8-bit single channel");
+    const int w = src.cols, h = src.rows, dw = dsize.width, dh = dsize.height;
+    if (dw <= 0 || dh <= 0 || std::abs(dw * 2 - w) > 2 || std::abs(dh * 2 - h) > 2) throw std::runtime_error("minicv: pyrDown destination size");
+    auto r101 = [](int p, int n) {
+        if (n == 1) return 0;
+        while (p < 0 || p >= n) p = (p < 0) ? -p : 2 * n - 2 - p;
+        return p;
+    };
+    static const int k[5] = {1, 4, 6, 4, 1};
+    std::vector<int> t((size_t)h * dw);
+    for (int y = 0; y < h; y++)
+        for (int x = 0; x < dw; x++) {
+            int a = 0;
+            for (int i = 0; i < 5; i++) a += k[i] * src.data[(size_t)y * w + r101(2 * x + i - 2, w)];
+            t[(size_t)y * dw + x] = a;
+        }
+    Mat out(dh, dw, CV_8UC1);
+    for (int y = 0; y < dh; y++)
+        for (int x = 0; x < dw; x++) {
+            int a = 0;
+            for (int i = 0; i < 5; i++) a += k[i] * t[(size_t)r101(2 * y + i - 2, h) * dw + x];
+            out.data[(size_t)y * dw + x] = (uchar)((a + 128) >> 8);
+        }
+    dst.assign(out);
+}
 
 }  // namespace cv
 #endif /* ORC_MINICV_HPP */

@@ -88,6 +88,9 @@ void to_keylines(const std::vector<float> &seg, int n, std::vector<cv::line_desc
 /* line_lbd_allclass.cpp:125-135 (one octave) */
 void line_lbd_detect::detect_raw_lines(const cv::Mat &gray_img, std::vector<cv::line_descriptor::KeyLine> &keylines_out)
 {
+    /* with more octaves the reference also returns the key lines of the higher ones here; the library detects octave 0 (all that
+     * filter_lines / detect_filter_lines / detect_descrip_lines keep) */
+    if (numoctaves_ > 1) throw std::runtime_error("cube_slam_b200: detect_raw_lines returns octave 0 only; build the detector with one octave or call detect_filter_lines");
     std::vector<float> seg;
     int32_t n = 0;
     run(this, gray_img, -1.f, seg, n); /* lineLength > -1: every segment */
@@ -206,6 +209,7 @@ void line_lbd_detect::detect_descrip_lines(const cv::Mat &gray_img, std::vector<
 void line_lbd_detect::detect_descrip_lines_octaves(const cv::Mat &gray_img, std::vector<std::vector<cv::line_descriptor::KeyLine>> &keylines_out,
                                                    std::vector<cv::Mat> &line_descrips)
 {
+    if (numoctaves_ > 1) throw std::runtime_error("cube_slam_b200: detect_descrip_lines_octaves is provided for one octave");
     keylines_out.assign((size_t)numoctaves_, std::vector<cv::line_descriptor::KeyLine>());
     line_descrips.assign((size_t)numoctaves_, cv::Mat());
     if (numoctaves_ < 1) return;

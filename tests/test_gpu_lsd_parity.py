@@ -62,12 +62,19 @@ def test_synthetic_and_gray_input(det, oracle):
     assert len(det.detect_filter_lines_batch(flat)[0]) == 0
 
 
-def test_unsupported_modes_fail_loudly(det):
+def test_more_octaves_give_the_same_lines_and_bad_counts_fail_loudly(det, oracle, fixture_a):
+    """filter_lines keeps octave 0 only (line_lbd_allclass.cpp:200-207) and octave 0 does not depend on the higher octaves: a detector built
+    with 2 or 3 octaves returns the one-octave matrix (the compiled reference does: tests/test_oracle_ref_octaves.py)."""
     import cube_slam_b200 as cs
     d = cs.line_lbd_detect(context=det._ctx)
     d.use_LSD = True
-    d.numoctaves_ = 2             # filter_lines keeps octave 0 only; other octaves are never produced here
-    with pytest.raises(cs.CubeSlamError, match="UNSUPPORTED"):
+    d.line_length_thres = 15
+    want = oracle.lsd_detect(fixture_a["img"], 15.0)["lines"]
+    for n in (2, 3):
+        d.numoctaves_ = n
+        np.testing.assert_array_equal(d.detect_filter_lines(fixture_a["img"]), want)
+    d.numoctaves_ = 0
+    with pytest.raises(cs.CubeSlamError, match="INVALID_ARG"):
         d.detect_filter_lines(np.zeros((64, 64), np.uint8))
 
 
