@@ -183,6 +183,25 @@ void keyline_from_lsd_row(const float *e, int w, int h, int class_id, cs_keyline
     kl.class_id = class_id;
 }
 
+/* BinaryDescriptor::detectImpl's KeyLine fill (binary_descriptor.cpp:526-545) for one EDLines segment: e = the ordered end points
+ * (OctaveKeyLines :1083-1139), x = {lineDirection_, numOfPixels as an integer's bits} as the detector kernels leave them */
+void keyline_from_edl_row(const float *e, const float *x, int w, int h, int class_id, cs_keyline &kl)
+{
+    int32_t npx;
+    memcpy(&npx, x + 1, 4);
+    kl.start_x = e[0];
+    kl.start_y = e[1];
+    kl.end_x = e[2];
+    kl.end_y = e[3];
+    kl.angle = x[0];
+    const float ddx = fabsf(e[0] - e[2]), ddy = fabsf(e[1] - e[3]);
+    kl.line_length = sqrtf(ddx * ddx + ddy * ddy); /* OctaveKeyLines :880-886, symmetric in the two ends */
+    kl.num_pixels = npx;
+    kl.size = (e[2] - e[0]) * (e[3] - e[1]);
+    kl.response = kl.line_length / std::max(w, h);
+    kl.class_id = class_id;
+}
+
 /* descriptors of `n` prepared lines over Sobel maps already in HBM; results to the host */
 int describe(cs_ctx *c, LbdState &S, const std::vector<CsLbdLine> &lines, const int16_t *d_dx, const int16_t *d_dy, int w, int h, uint8_t *desc32, float *desc72)
 {
@@ -238,6 +257,13 @@ int cs_keylines_from_lines(const float *lines_xyxy, int n, int width, int height
 {
     if (n < 0 || width <= 0 || height <= 0 || (n > 0 && (!lines_xyxy || !out))) return CS_ERR_INVALID_ARG;
     for (int k = 0; k < n; k++) keyline_from_lsd_row(lines_xyxy + 4 * (size_t)k, width, height, k, out[k]);
+    return CS_OK;
+}
+
+int cs_lbd_debug_keylines_edl(const float *lines_xyxy, const float *extra2, int n, int width, int height, cs_keyline *out)
+{
+    if (n < 0 || width <= 0 || height <= 0 || (n > 0 && (!lines_xyxy || !extra2 || !out))) return CS_ERR_INVALID_ARG;
+    for (int k = 0; k < n; k++) keyline_from_edl_row(lines_xyxy + 4 * (size_t)k, extra2 + 2 * (size_t)k, width, height, k, out[k]);
     return CS_OK;
 }
 
@@ -321,22 +347,8 @@ int cs_detect_descrip_lines_batch(cs_ctx *c, const uint8_t *imgs, int n_frames, 
             cs_keyline &kl = keylines[(size_t)f * cap + k];
             if (params->use_LSD)
                 keyline_from_lsd_row(e, width, height, k, kl);
-            else {
-                const float *x = &extra[((size_t)f * cap + k) * 2];
-                int32_t npx;
-                memcpy(&npx, x + 1, 4);
-                kl.start_x = e[0];
-                kl.start_y = e[1];
-                kl.end_x = e[2];
-                kl.end_y = e[3];
-                kl.angle = x[0];
-                float ddx = fabsf(e[0] - e[2]), ddy = fabsf(e[1] - e[3]);
-                kl.line_length = sqrtf(ddx * ddx + ddy * ddy); /* OctaveKeyLines :880-886, symmetric in the two ends */
-                kl.num_pixels = npx;
-                kl.size = (e[2] - e[0]) * (e[3] - e[1]);
-                kl.response = kl.line_length / std::max(width, height);
-                kl.class_id = k;
-            }
+            else
+                keyline_from_edl_row(e, &extra[((size_t)f * cap + k) * 2], width, height, k, kl);
             CsLbdLine L;
             lbd_prepare(kl, f, L);
             lines.push_back(L);

@@ -286,6 +286,9 @@ int cs_match_line_descrip_batch(cs_ctx *ctx, const uint8_t *query32, const int32
 /* tests: what the host side hands the descriptor kernel -- per key line {mid x, mid y, cos, sin, length, frame} (6 x 4 bytes) -- and the
  * two Gaussian weight tables F_g (63) and F_l (21) as floats (binary_descriptor.cpp:140-179).  Host-only, needs no context. */
 int cs_lbd_debug_prepare(const cs_keyline *keylines, int n, void *lines24, float *coef_g63, float *coef_l21);
+/* tests: the key lines cs_detect_descrip_lines assembles for the EDLines flavour from what the detector kernels leave per kept segment --
+ * the ordered end points and extra2 = {lineDirection_, numOfPixels as an integer's bits} (binary_descriptor.cpp:526-545).  Host-only. */
+int cs_lbd_debug_keylines_edl(const float *lines_xyxy, const float *extra2, int n, int width, int height, cs_keyline *out);
 
 /* How the reference draws a detected cuboid (plot_image_with_cuboid, detect_3d_cuboid/src/object_3d_util.cpp:54-131, called with
  * whether_save_final_images / whether_plot_final_images, box_proposal_detail.cpp:541-556): its 12 edges in the reference's order, each

@@ -110,6 +110,22 @@ def test_border_lines_short_lines_and_gray_input(core, product, oracle):
     assert np.isnan(fwant).any()                       # zero, sqrt gives NaN and the normalisation spreads it -- in the reference as well
 
 
+def test_edlines_key_lines_assembled_on_the_host(product, oracle, fixture_a, fixture_b):
+    """cs_detect_descrip_lines' host step for the EDLines flavour: end points + {direction, numOfPixels} from the kernels -> KeyLine fields."""
+    _lib, L = product
+    for img in (fixture_a["img"], fixture_b["frames"][12][0]):
+        h, w = img.shape[:2]
+        want = oracle.lbd_detect_keylines(img, False, 15.0)
+        rows = np.ascontiguousarray(np.stack([want["sx"], want["sy"], want["ex"], want["ey"]], 1), np.float32)
+        extra = np.zeros((len(want), 2), np.float32)
+        extra[:, 0] = want["angle"]
+        extra[:, 1] = want["num_pixels"].astype(np.int32).view(np.float32)
+        got = np.zeros(len(want), _lib.KEYLINE_DTYPE)
+        assert L.cs_lbd_debug_keylines_edl(_p(rows, C.c_float), _p(extra, C.c_float), len(want), w, h, got.ctypes.data) == 0
+        for a, b in zip(("sx", "sy", "ex", "ey", "angle", "line_length", "response", "size", "num_pixels", "class_id"), _lib.KEYLINE_DTYPE.names):
+            np.testing.assert_array_equal(got[b], want[a], err_msg=b)
+
+
 def test_round_is_half_away_from_zero(core):
     rng = np.random.default_rng(0)
     xs = np.concatenate([rng.uniform(-2000, 2000, 200000), np.arange(-50, 50) + 0.5, np.arange(-50, 50) - 0.5,
