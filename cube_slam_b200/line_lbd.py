@@ -49,6 +49,23 @@ class line_lbd_detect(object):
             raise CubeSlamError("%s: %s" % (_lib.STATUS_NAMES.get(rc, rc), self._ctx.L.cs_last_error(self._ctx.h).decode()))
         return [out[f, :n[f]].copy() for f in range(F)]
 
+    def detect_raw_lines(self, gray_img, downsample_img=False, cap=8192):
+        """detect_raw_lines(gray_img, lines_mat, downsample_img) (line_lbd_allclass.cpp:174-189): every octave-0 segment, no length filter ->
+        n x 4 float32; with downsample_img the image is halved first (cv::resize, as the reference does) and the lines scaled by 2."""
+        if self.numoctaves_ != 1:
+            raise CubeSlamError("detect_raw_lines returns octave 0 only: build the detector with one octave")
+        img = np.asarray(gray_img)
+        if downsample_img:
+            import cv2
+            img = cv2.resize(img, None, fx=0.5, fy=0.5)
+        keep = self.line_length_thres
+        try:
+            self.line_length_thres = -1.0     # lineLength > -1: everything
+            lines = self.detect_filter_lines(img, cap)
+        finally:
+            self.line_length_thres = keep
+        return lines * np.float32(2) if downsample_img else lines
+
     def debug_frame(self, frame=0, cap=8192):
         L = self._ctx.L
         wh = np.zeros(2, np.int32)

@@ -97,6 +97,15 @@ void line_lbd_detect::detect_raw_lines(const cv::Mat &gray_img, std::vector<cv::
     to_keylines(seg, n, keylines_out);
 }
 
+/* line_lbd_allclass.cpp:150-172: the per-octave form, for the one octave this library detects.  (The third overload, :174-189 --
+ * detect_raw_lines(gray, lines_mat, downsample_img) -- is written in terms of the first one and stays the reference's source.) */
+void line_lbd_detect::detect_raw_lines(const cv::Mat &gray_img, std::vector<std::vector<cv::line_descriptor::KeyLine>> &keyline_octaves)
+{
+    if (numoctaves_ > 1) throw std::runtime_error("cube_slam_b200: detect_raw_lines returns octave 0 only; build the detector with one octave or call detect_filter_lines");
+    keyline_octaves.assign(1, std::vector<cv::line_descriptor::KeyLine>());
+    detect_raw_lines(gray_img, keyline_octaves[0]);
+}
+
 /* line_lbd_allclass.cpp:216-221 */
 void line_lbd_detect::detect_filter_lines(const cv::Mat &gray_img, cv::Mat &linesmat_out)
 {

@@ -230,3 +230,15 @@ def test_cpp_shim_descriptor_and_matcher_members(oracle, fixture_a, fixture_b, u
     np.testing.assert_array_equal(qi[:n], wq)
     np.testing.assert_array_equal(ti[:n], wt)
     np.testing.assert_array_equal(di[:n], wd)
+
+
+def test_detect_raw_lines_with_and_without_downsampling(det, oracle, fixture_a):
+    """detect_raw_lines(gray, lines_mat, downsample_img) (line_lbd_allclass.cpp:174-189) through the Python mirror."""
+    import cv2
+    img = fixture_a["img"]
+    half = cv2.resize(img, None, fx=0.5, fy=0.5)
+    for use_lsd, fn in ((True, oracle.lsd_detect), (False, oracle.edl_detect)):
+        det.use_LSD = use_lsd
+        np.testing.assert_array_equal(det.detect_raw_lines(img), fn(img, -1.0)["lines"])
+        np.testing.assert_array_equal(det.detect_raw_lines(img, downsample_img=True), fn(half, -1.0)["lines"] * np.float32(2))
+    assert det.line_length_thres == 15
