@@ -68,7 +68,7 @@ EXPORTS = [
     "cs_debug_candidates", "cs_detect_lines", "cs_detect_lines_batch", "cs_debug_lsd", "cs_debug_lsd_stats", "cs_debug_lsd_prof", "cs_debug_atan2", "cs_atan2_host", "cs_cuboid_draw_edges", "cs_debug_edlines", "cs_debug_stage_offsets", "cs_comm_unique_id", "cs_comm_init",
     "cs_allgather_topk", "cs_allgather_wait", "cs_fetch_gathered",
     "cs_keylines_from_lines", "cs_lbd_compute", "cs_lbd_compute_batch", "cs_detect_descrip_lines", "cs_detect_descrip_lines_batch",
-    "cs_match_line_descrip", "cs_match_line_descrip_batch", "cs_lbd_debug_prepare", "cs_lbd_debug_keylines_edl",
+    "cs_match_line_descrip", "cs_match_line_descrip_batch", "cs_lbd_debug_prepare", "cs_lbd_debug_keylines_edl", "cs_debug_last_set_pose",
 ]
 
 
@@ -137,6 +137,7 @@ def load():
     L.cs_match_line_descrip_batch.argtypes = [vp, u8_p, i32_p, u8_p, i32_p, i, C.c_float, vp, i32_p]
     L.cs_lbd_debug_prepare.argtypes = [vp, i, vp, f_p, f_p]
     L.cs_lbd_debug_keylines_edl.argtypes = [f_p, f_p, i, i, i, vp]
+    L.cs_debug_last_set_pose.argtypes = [u8_p, d_p, d_p, i, i, i32_p]
     for name in EXPORTS:
         fn = getattr(L, name)
         if fn.restype is C.c_int and name not in ("cs_abi_version",):

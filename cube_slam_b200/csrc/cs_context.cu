@@ -101,6 +101,10 @@ struct cs_ctx {
     void *lsd_state = nullptr; /* line-detector workspace (cs_lsd.cu) */
     void *edl_state = nullptr; /* EDLines workspace (cs_edlines.cu) */
     void *lbd_state = nullptr; /* descriptor / matcher workspace (cs_lbd.cu) */
+    /* cs_set_profiling bit 10: later boxes of a roll / pitch-sampled frame start from the camera pose the reference leaves behind
+     * (detect_batch_carried); yaw_override[f] is the cam_pose.camera_yaw a pass derives its yaw samples from (NaN: the raw pose's) */
+    bool carry_cam_pose = false;
+    std::vector<double> yaw_override;
     int64_t line_launches = 0;
 
     /* NCCL (loaded at run time) */
@@ -232,7 +236,8 @@ int build_tables(cs_ctx *c)
         }
         fr.n_pose = (int32_t)c->poses.size() - fr.pose_off;
         /* :126-128 */
-        const double yaw_init = raw.camera_yaw - 90.0 / 180.0 * M_PI;
+        const double cam_yaw = ((size_t)f < c->yaw_override.size() && !std::isnan(c->yaw_override[f])) ? c->yaw_override[f] : raw.camera_yaw;
+        const double yaw_init = cam_yaw - 90.0 / 180.0 * M_PI;
         std::vector<double> ys;
         cshost::linespace_d(yaw_init - p.yaw_half_range_deg / 180.0 * M_PI, yaw_init + p.yaw_half_range_deg / 180.0 * M_PI,
                             p.yaw_step_deg / 180.0 * M_PI, ys);
@@ -595,6 +600,128 @@ int fetch(cs_ctx *c, cs_cuboid_rec *out, int32_t *out_counts)
     return CS_OK;
 }
 
+/* Which camera pose hypothesis the reference's cam_pose holds when it is done with one height sample of a box in roll / pitch-sampling
+ * mode: the sampling loop leaves the last hypothesis (box_proposal_detail.cpp:230-239), then the loop over the kept proposals
+ * (:479-487) sets the pose of each one in turn and so leaves the LAST kept proposal's -- last in good_proposal_ids, which
+ * fuse_normalize_scores_v2 (object_3d_util.cpp:495-527) fills either with the ascending intersection of the two "best 2/3" sets or, when
+ * the angle errors saturate at the cut, with the distance-sorted prefix.  valid / dist / angle: the candidate records of the job in
+ * enumeration order (pose-major), as the sweep kernels leave them; ties rank by index, NaN last (the rule the selection kernels use). */
+int last_set_pose(const uint8_t *valid, const double *dist, const double *angle, int n_cand, int n_pose)
+{
+    if (n_pose <= 0) return 0;
+    std::vector<int> vidx;
+    for (int i = 0; i < n_cand; i++)
+        if (valid[i]) vidx.push_back(i);
+    const int n = (int)vidx.size();
+    if (n == 0 || n_cand % n_pose != 0) return n_pose - 1;
+    const int per_pose = n_cand / n_pose;
+    auto prefix = [&](const double *v, std::vector<int> &idx, int top_k) {
+        std::partial_sort(idx.begin(), idx.begin() + top_k, idx.end(), [&](int a, int b) {
+            const double va = v[vidx[a]], vb = v[vidx[b]];
+            const bool na = std::isnan(va), nb = std::isnan(vb);
+            if (na || nb) return (!na && nb) || (na == nb && a < b);
+            return va < vb || (va == vb && a < b);
+        });
+    };
+    int last; /* position in the valid list of the last kept proposal */
+    if (n > 4) {
+        const int breaking_num = (int)std::round(float(n) / 3.0 * 2.0);
+        std::vector<int> ds(n), as;
+        for (int i = 0; i < n; i++) ds[i] = i;
+        as = ds;
+        prefix(dist, ds, breaking_num);
+        prefix(angle, as, breaking_num);
+        if (angle[vidx[as[breaking_num - 1]]] > angle[vidx[as[breaking_num - 2]]]) {
+            std::vector<char> in_d(n, 0);
+            for (int i = 0; i < breaking_num - 1; i++) in_d[ds[i]] = 1;
+            last = -1;
+            for (int i = 0; i < breaking_num - 1; i++)
+                if (in_d[as[i]]) last = std::max(last, as[i]);
+            if (last < 0) return n_pose - 1; /* empty intersection: no kept proposal, the sampling loop's last pose stands */
+        } else
+            last = ds[breaking_num - 2];
+    } else
+        last = n - 1;
+    return vidx[last] / per_pose;
+}
+
+/* cs_detect_cuboids_batch when cs_set_profiling bit 10 is set, roll / pitch sampling is on and some frame carries more than one box.
+ * The reference works through the boxes of a frame in order and derives box k + 1's yaw samples from the cam_pose box k left behind
+ * (box_proposal_detail.cpp:126-128 after :237,485): the re-derived camera yaw is the raw one give or take an ulp, and because
+ * linespace(yaw - 45 deg, yaw + 45 deg, 6 deg) spans exactly 15 steps, that ulp decides between 15 and 16 yaw samples
+ * (tests/test_sampling_deviation.py).  So: one pass per box rank.  Pass r runs the rank-r box of every frame that has one through the
+ * ordinary kernels, with the frame's yaw samples derived from the pose pass r - 1 left; then the candidate records of each box's last
+ * height sample come back and the host works out which hypothesis the reference's cam_pose would hold (last_set_pose).  Boxes of one
+ * frame are sequential by definition here; frames (and the boxes of one rank) still run side by side. */
+int detect_batch_carried(cs_ctx *c, const uint8_t *imgs, int n_frames, int width, int height, int stride, int channels, const double *T_wc,
+                         const double *boxes, const int32_t *box_offsets, const double *lines, const int32_t *line_offsets,
+                         const cs_cuboid_params *params, cs_cuboid_rec *out, int32_t *out_counts)
+{
+    int max_rank = 0;
+    for (int f = 0; f < n_frames; f++) max_rank = std::max(max_rank, box_offsets[f + 1] - box_offsets[f]);
+    const int topk = params->max_cuboid_num;
+    std::vector<double> next_yaw((size_t)n_frames, std::nan(""));
+    std::vector<double> sub_boxes;
+    std::vector<int32_t> sub_off((size_t)n_frames + 1);
+    std::vector<cs_cuboid_rec> tmp_out;
+    std::vector<int32_t> tmp_cnt;
+    std::vector<uint8_t> h_valid;
+    std::vector<double> h_dist, h_angle;
+    int rc = CS_OK;
+    for (int r = 0; r < max_rank && rc == CS_OK; r++) {
+        sub_boxes.clear();
+        sub_off[0] = 0;
+        for (int f = 0; f < n_frames; f++) {
+            const bool has = box_offsets[f + 1] - box_offsets[f] > r;
+            if (has) sub_boxes.insert(sub_boxes.end(), boxes + (size_t)(box_offsets[f] + r) * 5, boxes + (size_t)(box_offsets[f] + r) * 5 + 5);
+            sub_off[f + 1] = sub_off[f] + (has ? 1 : 0);
+        }
+        const int n_sub = sub_off[n_frames];
+        c->yaw_override = next_yaw; /* rank 0: all NaN, the raw pose */
+        rc = store_batch(c, imgs, n_frames, width, height, stride, channels, T_wc, sub_boxes.data(), sub_off.data(), lines, line_offsets, params);
+        c->yaw_override.clear(); /* the override belongs to this pass only */
+        if (rc) break;
+        if ((rc = run_batch(c, false))) break;
+        tmp_out.assign((size_t)n_sub * topk, cs_cuboid_rec());
+        tmp_cnt.assign((size_t)n_sub, 0);
+        if ((rc = fetch(c, tmp_out.data(), tmp_cnt.data()))) break;
+        for (int f = 0; f < n_frames; f++)
+            if (sub_off[f + 1] > sub_off[f]) {
+                const size_t dst = (size_t)(box_offsets[f] + r), src = (size_t)sub_off[f];
+                std::memcpy(&out[dst * topk], &tmp_out[src * topk], sizeof(cs_cuboid_rec) * topk);
+                out_counts[dst] = tmp_cnt[src];
+            }
+        if (r + 1 == max_rank) break;
+        /* the pose each of these boxes leaves behind: its last height sample decides (every height sample starts with the sampling loop) */
+        const size_t nc = (size_t)c->total_cand;
+        h_valid.resize(std::max<size_t>(nc, 1));
+        h_dist.resize(std::max<size_t>(nc, 1));
+        h_angle.resize(std::max<size_t>(nc, 1));
+        if (nc) {
+            if (cudaMemcpyAsync(h_valid.data(), c->d_cvalid.p, nc, cudaMemcpyDeviceToHost, c->stream) != cudaSuccess ||
+                cudaMemcpyAsync(h_dist.data(), c->d_cdist.p, nc * 8, cudaMemcpyDeviceToHost, c->stream) != cudaSuccess ||
+                cudaMemcpyAsync(h_angle.data(), c->d_cangle.p, nc * 8, cudaMemcpyDeviceToHost, c->stream) != cudaSuccess ||
+                cudaStreamSynchronize(c->stream) != cudaSuccess) {
+                rc = fail(c, CS_ERR_CUDA, "candidate record copy failed: %s", cudaGetErrorString(cudaGetLastError()));
+                break;
+            }
+        }
+        std::fill(next_yaw.begin(), next_yaw.end(), std::nan(""));
+        for (size_t o = 0; o < c->objs.size(); o++) {
+            const CsObj &ob = c->objs[o];
+            const CsFrame &fr = c->frames[ob.frame];
+            int hyp = fr.n_pose - 1;
+            if (ob.n_jobs > 0) {
+                const CsJob &jb = c->jobs[(size_t)ob.job_off + ob.n_jobs - 1];
+                hyp = last_set_pose(&h_valid[jb.cand_off], &h_dist[jb.cand_off], &h_angle[jb.cand_off], jb.n_cand, fr.n_pose);
+            }
+            next_yaw[ob.frame] = c->poses[(size_t)fr.pose_off + hyp].camera_yaw;
+        }
+    }
+    c->yaw_override.clear();
+    return rc;
+}
+
 }  // namespace
 
 /* ============================================================================================ C ABI */
@@ -837,10 +964,23 @@ int cs_detect_cuboids_batch(cs_ctx *c, const uint8_t *imgs, int n_frames, int wi
 {
     if (!c) return CS_ERR_INVALID_ARG;
     cudaSetDevice(c->device);
+    if (c->carry_cam_pose && params && params->whether_sample_cam_roll_pitch && box_offsets && out && out_counts && n_frames > 0) {
+        bool several = false;
+        for (int f = 0; f < n_frames && !several; f++) several = box_offsets[f + 1] - box_offsets[f] > 1;
+        if (several) return detect_batch_carried(c, imgs, n_frames, width, height, stride, channels, T_wc, boxes, box_offsets, lines, line_offsets, params, out, out_counts);
+    }
     int rc = store_batch(c, imgs, n_frames, width, height, stride, channels, T_wc, boxes, box_offsets, lines, line_offsets, params);
     if (rc) return rc;
     if ((rc = run_batch(c, false))) return rc;
     return fetch(c, out, out_counts);
+}
+
+/* tests: last_set_pose on caller-given candidate records (host-only, needs no context) */
+int cs_debug_last_set_pose(const uint8_t *valid, const double *dist_err, const double *angle_err, int n_cand, int n_pose, int32_t *pose_out)
+{
+    if (!valid || !dist_err || !angle_err || n_cand < 0 || n_pose <= 0 || !pose_out) return CS_ERR_INVALID_ARG;
+    *pose_out = last_set_pose(valid, dist_err, angle_err, n_cand, n_pose);
+    return CS_OK;
 }
 
 int cs_detect_cuboids(cs_ctx *c, const uint8_t *img, int width, int height, int stride, int channels, const double T_wc[16], const double *boxes,
@@ -907,6 +1047,7 @@ int cs_set_profiling(cs_ctx *c, int enable)
     c->use_tma = (enable & 256) == 0;      /* bit 8: the line detectors' tile kernels stage every tile with byte loads (A/B of the TMA path) */
     c->use_tma_canny = (enable & 512) != 0; /* bit 9: k_canny_nms stages interior gray tiles by TMA as well */
     c->use_cta_select = (enable & 8) != 0; /* bit 3: CTA-wide sweep / selection kernels (the general path) instead of the warp ones */
+    c->carry_cam_pose = (enable & 1024) != 0; /* bit 10: cs_detect_cuboids[_batch] carries the reference's cam_pose from box to box of a sampled frame */
     return CS_OK;
 }
 

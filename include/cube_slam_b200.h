@@ -187,8 +187,16 @@ int cs_stage_ms(cs_ctx *ctx, const char *stage, float *ms);
  * bit 2 fused hysteresis + wavefront distance transform, bit 3 CTA-wide sweep / selection kernels, bit 4 no high-priority
  * stream for the distance transform -> sweep -> selection tail, bit 5 raster-scan distance transform (one kernel) instead of the cone form,
  * bit 6 cone-form distance transform reading the edge bits from global memory (the path of ROIs whose bit plane exceeds 96 KB),
- * bit 7 the line detectors' plain sequential kernels (one warp per frame) instead of the ordered-speculation kernels */
+ * bit 7 the line detectors' plain sequential kernels (one warp per frame) instead of the ordered-speculation kernels,
+ * bit 8 byte-load staging in the line detectors' tile kernels (A/B of TMA), bit 9 TMA staging in the Canny kernel.
+ * Mode switch, bit 10: with whether_sample_cam_roll_pitch the reference derives the yaw samples of box k + 1 of a frame from the
+ * cam_pose box k left behind (box_proposal_detail.cpp:126-128 after :237,485) -- an ulp away from the raw pose's, which decides between 15
+ * and 16 yaw samples.  By default every box starts from the raw pose (boxes independent, one pass); with bit 10
+ * cs_detect_cuboids[_batch] runs one pass per box rank and carries the pose exactly as the reference does. */
 int cs_set_profiling(cs_ctx *ctx, int enable);
+/* tests: which pose hypothesis the reference's cam_pose holds after one height sample of a box in roll / pitch-sampling mode, from the
+ * candidate records of that job (valid flag, distance error, angle error, enumeration order, pose-major).  Host-only, needs no context. */
+int cs_debug_last_set_pose(const uint8_t *valid, const double *dist_err, const double *angle_err, int n_cand, int n_pose, int32_t *pose_out);
 
 /* debug: when several contexts run concurrently with profiling on, the offsets (ms) of the 8 stage starts and the end of ctx's last run
  * from the start of ref's last run -- a timeline of how the batches in flight overlap (tools/timeline.py) */

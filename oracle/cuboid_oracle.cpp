@@ -427,6 +427,14 @@ static thread_local int g_cut_flip = -1, g_cur_box = -1;
 extern "C" double orc_last_cut_margin(int box) { return (box >= 0 && box < 64) ? g_box_margin[box] : 1e300; }
 extern "C" void orc_set_cut_flip(int box) { g_cut_flip = box; } /* -1: none */
 
+/* Analysis switch, off by default.  With whether_sample_cam_roll_pitch the reference leaves cam_pose at the last pose it set while working
+ * on a box and derives the NEXT box's yaw_init from it (box_proposal_detail.cpp:126,237,485): the re-derived yaw is the raw yaw give or
+ * take an ulp.  By default the CUDA path starts every box from the raw pose (boxes stay independent; DESIGN.md section 2, "Several boxes
+ * in a roll / pitch-sampled frame"; cs_set_profiling bit 10 carries the pose like the reference).  With this switch on the oracle does what
+ * the default does, so that tests/test_sampling_deviation.py can count how often the two ways differ and the GPU test can pin the default. */
+static thread_local int g_independent_boxes = 0;
+extern "C" void orc_set_independent_boxes(int on) { g_independent_boxes = on; }
+
 /* object_3d_util.cpp:495-565 */
 void fuse_normalize_scores_v2(const std::vector<double> &dist_error, const std::vector<double> &angle_error,
                               std::vector<double> &combined, std::vector<int> &keep, double weight_vp_angle, bool normalize)
@@ -832,6 +840,10 @@ extern "C" int orc_detect_cuboid(const uint8_t *img, int w, int h, int stride, i
             down_expand_sample_all.push_back(r);
         }
 
+        if (g_independent_boxes && object_id > 0) { /* analysis only: what the CUDA path does */
+            cam = cam_raw;
+            plane_to_sensor(cam.T, ground_plane_world, ground_plane_sensor);
+        }
         const double yaw_init = cam.yaw - 90.0 / 180.0 * M_PI;
         std::vector<double> obj_yaw_samples;
         linespace<double>(yaw_init - p.yaw_half_range_deg / 180.0 * M_PI, yaw_init + p.yaw_half_range_deg / 180.0 * M_PI,

@@ -1,0 +1,125 @@
+"""Host half of the reference-exact handling of several boxes in a roll / pitch-sampled frame (cs_set_profiling bit 10).
+
+cs_debug_last_set_pose is the function detect_batch_carried (cs_context.cu) runs on the candidate records a pass brings back: which pose
+hypothesis the reference's cam_pose holds after a height sample -- that of the LAST proposal fuse_normalize_scores_v2 keeps
+(box_proposal_detail.cpp:479-487 over object_3d_util.cpp:495-527), or the last sampled one when nothing is kept.  Checked here against the
+oracle's trace of the same height sample (valid rows, their candidate indices, the kept ids in the order the reference visits them), on
+real jobs and on synthetic records that hit every branch (n <= 4, the saturated-angle branch, an empty intersection, NaNs, ties)."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+
+@pytest.fixture(scope="module")
+def L():
+    from cube_slam_b200 import _lib
+    return _lib.load()
+
+
+def _p(a, t):
+    return a.ctypes.data_as(C.POINTER(t))
+
+
+def _last_pose(L, valid, dist, angle, n_pose):
+    out = C.c_int32(-1)
+    valid, dist, angle = np.ascontiguousarray(valid, np.uint8), np.ascontiguousarray(dist, np.float64), np.ascontiguousarray(angle, np.float64)
+    assert L.cs_debug_last_set_pose(_p(valid, C.c_uint8), _p(dist, C.c_double), _p(angle, C.c_double), len(valid), n_pose, C.byref(out)) == 0
+    return out.value
+
+
+def _linespace(start, end, step):
+    """matrix_utils.cpp:350-363: for (i = start; i <= end; i += step)"""
+    out, v = [], start
+    while v <= end:
+        out.append(v)
+        v = v + step
+    return np.array(out)
+
+
+def test_against_the_oracles_trace_of_sampled_jobs(L, oracle):
+    from cube_slam_b200 import synthetic as S
+    p = oracle.default_params(whether_sample_cam_roll_pitch=1)
+    seen = 0
+    for seed in (101, 102):
+        imgs, Ts, boxes, lines, K = S.make_batch(seed, 6, 640, 480, 3, poisson=True)
+        for f in range(len(imgs)):
+            for b in range(len(boxes[f])):
+                tr = oracle.detect_cuboid(imgs[f], K, Ts[f], boxes[f], np.asarray(lines[f], float), p, trace_object=b, trace_caps=(4096, 1 << 21, 1 << 17))["trace"]
+                n_cand, n_valid = tr["n_candidates"], tr["n_valid"]
+                if n_valid < 200:
+                    continue
+                # the sampled roll / pitch grids (4 or 5 values each: linespace(-6 deg, +6 deg, 3 deg) sits on a rounding edge, like the yaw
+                # one; box_proposal_detail.cpp:215-226); candidates are enumerated roll-major, then pitch (:230-232)
+                euler = oracle.cam_pose(K, Ts[f])["euler"]
+                d6, d3 = 6.0 / 180.0 * np.pi, 3.0 / 180.0 * np.pi          # as the reference writes them: (6 / 180) * pi, not 6 * (pi / 180)
+                rolls, pitches = _linespace(euler[0] - d6, euler[0] + d6, d3), _linespace(euler[1] - d6, euler[1] + d6, d3)
+                n_pose = len(rolls) * len(pitches)
+                assert n_pose in (16, 20, 25) and n_cand % n_pose == 0
+                assert set(np.unique(tr["rows"][:, 7])) <= set(rolls) and set(np.unique(tr["rows"][:, 8])) <= set(pitches)
+                valid = np.zeros(n_cand, np.uint8)
+                dist, angle = np.zeros(n_cand), np.zeros(n_cand)
+                valid[tr["cand_index"]] = 1
+                dist[tr["cand_index"]] = tr["rows"][:, 4]
+                angle[tr["cand_index"]] = tr["rows"][:, 5]
+                if tr["n_kept"] == 0:
+                    want = n_pose - 1
+                else:
+                    last = tr["kept_ids"][-1]
+                    want = int(tr["cand_index"][last]) // (n_cand // n_pose)
+                    # ... and that index is the pose the reference sets last: the (roll, pitch) recorded in the kept row (:453,484)
+                    assert want == int(np.searchsorted(rolls, tr["rows"][last, 7])) * len(pitches) + int(np.searchsorted(pitches, tr["rows"][last, 8]))
+                assert _last_pose(L, valid, dist, angle, n_pose) == want
+                seen += n_valid > 4
+    assert seen >= 20
+
+
+def _reference_last(dist, angle):
+    """fuse_normalize_scores_v2's final_keep_inds[-1] (object_3d_util.cpp:495-527) with ties by index, NaN last; None when nothing is kept."""
+    n = len(dist)
+    if n <= 4:
+        return n - 1 if n else None
+    bn = int(round(float(np.float32(n)) / 3.0 * 2.0))
+    key = lambda v: sorted(range(n), key=lambda i: (np.isnan(v[i]), v[i] if not np.isnan(v[i]) else 0.0, i))
+    ds, as_ = key(dist), key(angle)
+    dk = ds[:bn - 1]
+    if angle[as_[bn - 1]] > angle[as_[bn - 2]]:
+        inter = sorted(set(dk) & set(as_[:bn - 1]))
+        return inter[-1] if inter else None
+    return dk[-1]
+
+
+def test_every_branch_on_synthetic_records(L):
+    rng = np.random.default_rng(9)
+    n_pose, per_pose = 5, 40
+    hit = {"small": 0, "saturated": 0, "intersection": 0, "empty": 0, "nan": 0}
+    for trial in range(400):
+        n_cand = n_pose * per_pose
+        valid = (rng.random(n_cand) < rng.choice([0.02, 0.2, 0.6])).astype(np.uint8)
+        dist = np.round(rng.random(n_cand) * rng.choice([4, 1000]), 0 if trial % 3 else 6)      # coarse values: plenty of ties
+        angle = np.round(rng.random(n_cand) * 8, 0 if trial % 2 else 6)
+        mode = trial % 5
+        if mode == 1:
+            angle[:] = np.minimum(angle, 3.0)                                                    # saturates at the cut
+        if mode == 2 and valid.sum() > 6:                                                        # best by distance == worst by angle: empty intersection
+            v = np.flatnonzero(valid)
+            dist[v] = np.arange(len(v), dtype=float)
+            angle[v] = np.arange(len(v), 0, -1, dtype=float)
+        if mode == 3:
+            angle[rng.random(n_cand) < 0.3] = np.nan
+            hit["nan"] += 1
+        v = np.flatnonzero(valid)
+        last = _reference_last(dist[v], angle[v])
+        want = n_pose - 1 if last is None else int(v[last]) // per_pose
+        assert _last_pose(L, valid, dist, angle, n_pose) == want, trial
+        n = len(v)
+        if n <= 4:
+            hit["small"] += 1
+        elif last is None:
+            hit["empty"] += 1
+        else:
+            bn = int(round(float(np.float32(n)) / 3.0 * 2.0))
+            srt = sorted(range(n), key=lambda i: (np.isnan(angle[v][i]), angle[v][i] if not np.isnan(angle[v][i]) else 0.0, i))
+            hit["intersection" if angle[v][srt[bn - 1]] > angle[v][srt[bn - 2]] else "saturated"] += 1
+    assert all(c > 5 for c in hit.values()), hit
+    assert _last_pose(L, np.zeros(50, np.uint8), np.zeros(50), np.zeros(50), 25) == 24      # no valid proposal at all

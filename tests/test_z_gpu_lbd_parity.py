@@ -242,3 +242,46 @@ def test_detect_raw_lines_with_and_without_downsampling(det, oracle, fixture_a):
         np.testing.assert_array_equal(det.detect_raw_lines(img), fn(img, -1.0)["lines"])
         np.testing.assert_array_equal(det.detect_raw_lines(img, downsample_img=True), fn(half, -1.0)["lines"] * np.float32(2))
     assert det.line_length_thres == 15
+
+
+# ---------------------------------------------------------------------------------------------------------------------------------------
+# Not LBD, but new this session and not yet run on a GPU either, so it lives in the file that sorts last: several boxes in a roll / pitch-sampled
+# frame (cs_set_profiling bit 10).
+def test_sampled_frames_with_several_boxes_default_and_carried_pose(oracle):
+    """Frames picked on the CPU (tests/test_sampling_deviation.py): in (seed 102, frame 10) and (seed 104, frame 1) the pose the reference
+    carries from box to box gives the third box 16 yaw samples where the raw pose gives 15 (or the other way round), and a different best
+    proposal.  Default mode: every box starts from the raw pose == the oracle with orc_set_independent_boxes(1).  Bit 10: the library carries
+    the pose == the oracle as it is (== the compiled reference).  Both strictly, every box, every kept cuboid."""
+    import cube_slam_b200 as cs
+    from cube_slam_b200 import synthetic as S
+    from test_gpu_cuboid_parity import _compare_cuboid
+    L = oracle.lib()
+    for seed, pick in ((102, (10, 3)), (104, (1, 0))):
+        imgs, Ts, boxes, lines, K = S.make_batch(seed, 12, 640, 480, 3, poisson=True)
+        sel = list(pick)
+        imgs, Ts = imgs[sel], Ts[sel]
+        boxes, lines = [boxes[i] for i in sel], [lines[i] for i in sel]
+        for kw in (dict(whether_sample_cam_roll_pitch=1, max_cuboid_num=3), dict(whether_sample_cam_roll_pitch=1, whether_sample_bbox_height=1, max_cuboid_num=2)):
+            differs = False
+            for carried in (0, 1):
+                ctx = cs.Context(0, 640, 480, 2, 16, 4096)
+                ctx.set_calibration(K)
+                ctx.L.cs_set_profiling(ctx.h, 1024 if carried else 0)
+                out, counts = ctx.detect_batch_host(imgs, Ts, boxes, lines, cs.default_params(**kw))
+                ctx.close()
+                o = 0
+                try:
+                    L.orc_set_independent_boxes(0 if carried else 1)
+                    for f in range(len(sel)):
+                        ref = oracle.detect_cuboid(imgs[f], K, Ts[f], boxes[f], np.asarray(lines[f], float), oracle.default_params(**kw))
+                        for b in range(len(boxes[f])):
+                            assert counts[o] == len(ref["cuboids"][b]), (seed, f, b, carried)
+                            for k in range(counts[o]):
+                                _compare_cuboid(out[o, k], ref["cuboids"][b][k])
+                            o += 1
+                finally:
+                    L.orc_set_independent_boxes(0)
+                if carried:
+                    differs = differs or out.tobytes() != prev
+                prev = out.tobytes()
+            assert differs, "the two modes returned the same records on frames chosen because they differ"
