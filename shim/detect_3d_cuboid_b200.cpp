@@ -42,6 +42,10 @@ struct CtxTable {
         if (it != map.end()) return it->second;
         cs_ctx *c = cs_create(/*device*/ 0, /*max_width*/ 2048, /*max_height*/ 2048, /*max_frames*/ 1, /*max_boxes*/ 64, /*max_lines*/ 8192);
         if (!c) throw std::runtime_error("cube_slam_b200: cs_create failed (no CUDA device?)");
+        /* a drop-in has the reference's semantics to the letter: with whether_sample_cam_roll_pitch, later boxes of a frame start from the
+         * cam_pose the earlier ones left (box_proposal_detail.cpp:126-128 after :237,485) -- bit 10, one pass per box rank; a frame with a
+         * single box (all object_slam ever passes) takes the ordinary one-pass path either way */
+        cs_set_profiling(c, 1024);
         map.emplace(self, c);
         return c;
     }
