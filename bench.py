@@ -175,6 +175,29 @@ def time_lbd_subprocess():
         return {"error": "%s: %s" % (type(e).__name__, str(e)[:300])}
 
 
+def lbd_cpu_one_core(wl, n=4):
+    """The descriptor half on one host core, for the `lbd` key: the oracle port of detect_descrip_lines (LSD flavour) and of
+    match_line_descrip on n frames of the workload (cpu_baseline leg: the one place bench.py runs oracle code)."""
+    try:
+        from oracle import pyoracle as O
+        imgs = wl["imgs"][:n]
+        t0 = time.perf_counter()
+        kls = [O.lbd_detect_keylines(im, True, 15.0) for im in imgs]
+        t1 = time.perf_counter()
+        descs = [O.lbd_compute(im, k) for im, k in zip(imgs, kls)]
+        t2 = time.perf_counter()
+        pairs = 0
+        for q, t in zip(descs[:-1], descs[1:]):
+            O.lbd_match(q, t, 40.0)
+            pairs += len(q) * len(t)
+        t3 = time.perf_counter()
+        lines = sum(len(k) for k in kls)
+        return {"kind": "port", "cores": 1, "frames": len(imgs), "lines": lines, "describe_lines_per_s": lines / max(t2 - t1, 1e-9),
+                "detect_descrip_frames_per_s": len(imgs) / max(t2 - t0, 1e-9), "match_code_pairs_per_s": pairs / max(t3 - t2, 1e-9)}
+    except Exception as e:  # noqa: BLE001
+        return {"error": "%s: %s" % (type(e).__name__, str(e)[:200])}
+
+
 def make_workload(name, rank, seed_base=20260922, frames=None):
     from cube_slam_b200 import synthetic as S
     F, w, h, nb, kind, poisson, over, desc = WORKLOADS[name]
@@ -707,6 +730,8 @@ def run_ours(args, rank, world, local_rank):
         line["per_rank"] = per_rank
     if world == 1 and not args.no_extra:
         line["lbd"] = time_lbd_subprocess()
+        if not args.no_cpu:
+            line["lbd"]["cpu_one_core"] = lbd_cpu_one_core(wl)
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
