@@ -187,7 +187,8 @@ int cs_stage_ms(cs_ctx *ctx, const char *stage, float *ms);
  * bit 2 fused hysteresis + wavefront distance transform, bit 3 CTA-wide sweep / selection kernels, bit 4 no high-priority
  * stream for the distance transform -> sweep -> selection tail, bit 5 raster-scan distance transform (one kernel) instead of the cone form,
  * bit 6 cone-form distance transform reading the edge bits from global memory (the path of ROIs whose bit plane exceeds 96 KB),
- * bit 7 the line detectors' plain sequential kernels (one warp per frame) instead of the ordered-speculation kernels,
+ * bit 7 the line detectors' round-1 kernels (EDLines: routing and fitting on the pixel maps, one thread per frame) instead of the walk-graph
+ * / warp-per-chain ones (the LSD seed loop has one form since the ordered-speculation kernel was measured and removed),
  * bit 8 byte-load staging in the line detectors' tile kernels (A/B of TMA), bit 9 TMA staging in the Canny kernel.
  * Mode switch, bit 10: with whether_sample_cam_roll_pitch the reference derives the yaw samples of box k + 1 of a frame from the
  * cam_pose box k left behind (box_proposal_detail.cpp:126-128 after :237,485) -- an ulp away from the raw pose's, which decides between 15
