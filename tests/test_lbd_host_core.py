@@ -4,8 +4,11 @@ cube_slam_b200/csrc/cs_lbd_core.h holds every formula of k_lbd_describe and k_lb
 the host.  tests/host_core/lbd_core_host.cpp builds them with g++ (-ffp-contract=off) and drives them exactly as the kernels do -- thread
 index by thread index, phase after phase -- and the product library's own host side (cs_lbd_debug_prepare, cs_keylines_from_lines: host-only
 entry points of libcubeslam_b200.so) prepares the inputs.  The results must equal the oracle (which tests/test_oracle_ref_lbd.py pins to
-the compiled reference) bit for bit.  What this cannot see is the launch itself (grid, barriers, copies): tests/test_z_gpu_lbd_parity.py does
-that on the GPU box."""
+the compiled reference) bit for bit.  A second harness (tests/host_core/lbd_kernels_emu.cpp) compiles the kernels' own source,
+cs_lbd_kernels.cuh, against an emulation of the CUDA execution model -- a std::thread per CUDA thread, a std::barrier for __syncthreads,
+function-local statics for __shared__, shuffles through a block-wide array -- and runs whole launches: the kernels' index arithmetic,
+phase split and barrier placement give the oracle's bytes too.  What is left for the GPU box (tests/test_z_gpu_lbd_parity.py) is the
+host-side launch code: allocations, copies, grid sizes."""
 import ctypes as C
 import os
 import subprocess
@@ -33,6 +36,18 @@ def core():
 
 
 @pytest.fixture(scope="module")
+def emu():
+    """cs_lbd_kernels.cuh itself, compiled against an emulation of the CUDA execution model (tests/host_core/lbd_kernels_emu.cpp)."""
+    src = os.path.join(HERE, "host_core", "lbd_kernels_emu.cpp")
+    deps = [src] + [os.path.join(HERE, "..", "cube_slam_b200", "csrc", f) for f in ("cs_lbd_core.h", "cs_lbd_kernels.cuh")]
+    out = os.path.join(HERE, "host_core", "_build", "liblbdemu.so")
+    os.makedirs(os.path.dirname(out), exist_ok=True)
+    if not os.path.exists(out) or os.path.getmtime(out) < max(os.path.getmtime(d) for d in deps):
+        subprocess.check_call(["g++", "-std=c++20", "-O2", "-fPIC", "-shared", "-pthread", "-ffp-contract=off", "-fno-fast-math", "-o", out, src])
+    return C.CDLL(out)
+
+
+@pytest.fixture(scope="module")
 def product():
     from cube_slam_b200 import _lib
     return _lib, _lib.load()
@@ -42,7 +57,7 @@ def _p(a, t):
     return a.ctypes.data_as(C.POINTER(t))
 
 
-def _describe(core, product, oracle, img, kl):
+def _describe(core, product, oracle, img, kl, entry="host_lbd_describe"):
     """prepare on the product's host side, run the kernel arithmetic on the host, return (desc32, desc72)."""
     _lib, L = product
     n = len(kl)
@@ -55,7 +70,7 @@ def _describe(core, product, oracle, img, kl):
     h, w = dx.shape
     desc, fdesc = np.zeros((n, 32), np.uint8), np.zeros((n, 72), np.float32)
     coef = np.concatenate([g, l]).astype(np.float32)
-    core.host_lbd_describe(lines.ctypes.data, n, _p(dx, C.c_int16), _p(dy, C.c_int16), w, h, _p(coef, C.c_float), _p(desc, C.c_uint8), _p(fdesc, C.c_float))
+    getattr(core, entry)(lines.ctypes.data, n, _p(dx, C.c_int16), _p(dy, C.c_int16), w, h, _p(coef, C.c_float), _p(desc, C.c_uint8), _p(fdesc, C.c_float))
     return desc, fdesc
 
 
@@ -190,6 +205,47 @@ def test_matcher_keys_reproduce_the_hash_order(core, oracle):
             np.testing.assert_array_equal(a, wa)
             np.testing.assert_array_equal(b, wb)
             np.testing.assert_array_equal(c, wc)
+
+
+@pytest.mark.parametrize("use_lsd", [True, False])
+def test_kernel_source_under_the_cuda_model_emulation_describe(emu, product, oracle, fixture_a, use_lsd):
+    """k_lbd_describe as written (blockIdx / threadIdx indexing, shared arrays, four barriers), one std::thread per CUDA thread."""
+    img = fixture_a["img"]
+    kl = oracle.lbd_detect_keylines(img, use_lsd, 30.0 if use_lsd else 15.0)
+    want, fwant = oracle.lbd_compute(img, kl, want_float=True)
+    got, fgot = _describe(emu, product, oracle, img, kl, entry="emu_lbd_describe")
+    assert len(kl) > 60
+    np.testing.assert_array_equal(got, want)
+    np.testing.assert_array_equal(fgot, fwant)
+
+
+def test_kernel_source_under_the_cuda_model_emulation_match(emu, core, oracle):
+    """k_lbd_match as written (strided train loop, shuffle reduction, per-warp shared slots), several pairs in one launch."""
+    rng = np.random.default_rng(4)
+    qs, ts = [], []
+    for nq, nt in ((5, 300), (3, 7), (4, 129), (2, 128)):
+        t = rng.integers(0, 256, (nt, 32), dtype=np.uint8)
+        q = t[rng.integers(0, nt, nq)].copy()
+        for i in range(nq):
+            for b in rng.integers(0, 256, int(rng.integers(0, 30))):
+                q[i, b // 8] ^= np.uint8(1 << (b % 8))
+        t[nt - 1] = t[0]
+        qs.append(q)
+        ts.append(t)
+    qo = np.concatenate([[0], np.cumsum([len(q) for q in qs])]).astype(np.int32)
+    to = np.concatenate([[0], np.cumsum([len(t) for t in ts])]).astype(np.int32)
+    q, t = np.ascontiguousarray(np.concatenate(qs)), np.ascontiguousarray(np.concatenate(ts))
+    assert q.ctypes.data % 16 == 0 and t.ctypes.data % 16 == 0
+    pq = np.concatenate([np.full(len(x), p, np.int32) for p, x in enumerate(qs)])
+    keys_emu, keys_core = np.zeros(len(q), np.uint64), np.zeros(len(q), np.uint64)
+    emu.emu_lbd_match(q.ctypes.data, t.ctypes.data, _p(pq, C.c_int32), _p(to, C.c_int32), len(q), _p(keys_emu, C.c_uint64))
+    core.host_lbd_match(_p(q, C.c_uint8), _p(t, C.c_uint8), _p(pq, C.c_int32), _p(to, C.c_int32), len(q), _p(keys_core, C.c_uint64))
+    np.testing.assert_array_equal(keys_emu, keys_core)
+    for p_, (qq, tt) in enumerate(zip(qs, ts)):              # and the keys mean what the oracle says
+        wq, wt, wd = oracle.lbd_match(qq, tt, 300.0)
+        k = keys_emu[qo[p_]:qo[p_ + 1]]
+        np.testing.assert_array_equal((k >> np.uint64(48)).astype(np.int64)[wq], wd.astype(np.int64))
+        np.testing.assert_array_equal((k & np.uint64(0xFFFFFFFF)).astype(np.int64)[wq][wd <= 128], wt[wd <= 128])
 
 
 def test_pattern_order_is_numeric_order(oracle):
