@@ -160,8 +160,8 @@ int describe(cs_ctx *c, LbdState &S, const std::vector<CsLbdLine> &lines, const 
     }
     if (cudaMemcpyAsync(S.lines.p, lines.data(), n * sizeof(CsLbdLine), cudaMemcpyHostToDevice, st) != cudaSuccess)
         return cs_ctx_fail(c, CS_ERR_CUDA, "upload of the key lines failed");
-    k_lbd_describe<<<(unsigned)n, 64, 0, st>>>((const CsLbdLine *)S.lines.p, (int)n, d_dx, d_dy, w, h, (const float *)S.coef.p, (uint8_t *)S.desc.p,
-                                              desc72 ? (float *)S.fdesc.p : nullptr);
+    launch_lbd_describe((unsigned)n, st, (const CsLbdLine *)S.lines.p, (int)n, d_dx, d_dy, w, h, (const float *)S.coef.p, (uint8_t *)S.desc.p,
+                        desc72 ? (float *)S.fdesc.p : nullptr);
     cs_ctx_count_launches(c, 1);
     if (cudaGetLastError() != cudaSuccess) return cs_ctx_fail(c, CS_ERR_CUDA, "descriptor kernel launch failed: %s", cudaGetErrorString(cudaGetLastError()));
     if (cudaMemcpyAsync(desc32, S.desc.p, n * CS_LBD_BYTES, cudaMemcpyDeviceToHost, st) != cudaSuccess ||
@@ -340,8 +340,8 @@ int cs_match_line_descrip_batch(cs_ctx *c, const uint8_t *query32, const int32_t
         cudaMemcpyAsync(S.pairq.p, pair_of_query.data(), (size_t)nq * 4, cudaMemcpyHostToDevice, st) != cudaSuccess ||
         cudaMemcpyAsync(S.toff.p, train_offsets, (size_t)(n_pairs + 1) * 4, cudaMemcpyHostToDevice, st) != cudaSuccess)
         return cs_ctx_fail(c, CS_ERR_CUDA, "upload of the descriptors failed");
-    k_lbd_match<<<(unsigned)nq, 128, 0, st>>>((const uint4 *)S.q.p, (const uint4 *)S.t.p, (const int32_t *)S.pairq.p, (const int32_t *)S.toff.p, nq,
-                                             (unsigned long long *)S.keys.p);
+    launch_lbd_match((unsigned)nq, st, (const uint4 *)S.q.p, (const uint4 *)S.t.p, (const int32_t *)S.pairq.p, (const int32_t *)S.toff.p, nq,
+                     (unsigned long long *)S.keys.p);
     cs_ctx_count_launches(c, 1);
     if (cudaGetLastError() != cudaSuccess) return cs_ctx_fail(c, CS_ERR_CUDA, "matcher kernel launch failed: %s", cudaGetErrorString(cudaGetLastError()));
     std::vector<unsigned long long> keys((size_t)nq);

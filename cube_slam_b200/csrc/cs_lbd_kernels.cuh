@@ -65,3 +65,29 @@ __global__ void __launch_bounds__(128) k_lbd_match(const uint4 *__restrict__ q_a
         keys[qi] = b;
     }
 }
+
+/* the two launches: a CTA of 64 threads per key line, a CTA of 128 threads per query.  Under the CPU emulation of the test suite
+ * (CS_LBD_EMU_LAUNCH defined by tests/host_core/*.cpp) the same grids run as threads of the host. */
+#if defined(__CUDACC__)
+inline void launch_lbd_describe(unsigned grid, cudaStream_t st, const CsLbdLine *lines, int n_lines, const int16_t *dx_all, const int16_t *dy_all, int w, int h,
+                                const float *coef, uint8_t *desc, float *fdesc)
+{
+    k_lbd_describe<<<grid, 64, 0, st>>>(lines, n_lines, dx_all, dy_all, w, h, coef, desc, fdesc);
+}
+inline void launch_lbd_match(unsigned grid, cudaStream_t st, const uint4 *q_all, const uint4 *t_all, const int32_t *pair_of_query, const int32_t *t_off, int n_queries,
+                             unsigned long long *keys)
+{
+    k_lbd_match<<<grid, 128, 0, st>>>(q_all, t_all, pair_of_query, t_off, n_queries, keys);
+}
+#elif defined(CS_LBD_EMU_LAUNCH)
+inline void launch_lbd_describe(unsigned grid, cudaStream_t, const CsLbdLine *lines, int n_lines, const int16_t *dx_all, const int16_t *dy_all, int w, int h,
+                                const float *coef, uint8_t *desc, float *fdesc)
+{
+    CS_LBD_EMU_LAUNCH(grid, 64, [&] { k_lbd_describe(lines, n_lines, dx_all, dy_all, w, h, coef, desc, fdesc); });
+}
+inline void launch_lbd_match(unsigned grid, cudaStream_t, const uint4 *q_all, const uint4 *t_all, const int32_t *pair_of_query, const int32_t *t_off, int n_queries,
+                             unsigned long long *keys)
+{
+    CS_LBD_EMU_LAUNCH(grid, 128, [&] { k_lbd_match(q_all, t_all, pair_of_query, t_off, n_queries, keys); });
+}
+#endif
