@@ -15,6 +15,7 @@
 #include <string>
 #include <vector>
 
+#include "cs_carried.h"
 #include "cs_host_pose.h"
 #include "cs_internal.h"
 #include "cs_kernels.h"
@@ -657,57 +658,29 @@ int detect_batch_carried(cs_ctx *c, const uint8_t *imgs, int n_frames, int width
                          const double *boxes, const int32_t *box_offsets, const double *lines, const int32_t *line_offsets,
                          const cs_cuboid_params *params, cs_cuboid_rec *out, int32_t *out_counts)
 {
-    int max_rank = 0;
-    for (int f = 0; f < n_frames; f++) max_rank = std::max(max_rank, box_offsets[f + 1] - box_offsets[f]);
-    const int topk = params->max_cuboid_num;
-    std::vector<double> next_yaw((size_t)n_frames, std::nan(""));
-    std::vector<double> sub_boxes;
-    std::vector<int32_t> sub_off((size_t)n_frames + 1);
-    std::vector<cs_cuboid_rec> tmp_out;
-    std::vector<int32_t> tmp_cnt;
     std::vector<uint8_t> h_valid;
     std::vector<double> h_dist, h_angle;
-    int rc = CS_OK;
-    for (int r = 0; r < max_rank && rc == CS_OK; r++) {
-        sub_boxes.clear();
-        sub_off[0] = 0;
-        for (int f = 0; f < n_frames; f++) {
-            const bool has = box_offsets[f + 1] - box_offsets[f] > r;
-            if (has) sub_boxes.insert(sub_boxes.end(), boxes + (size_t)(box_offsets[f] + r) * 5, boxes + (size_t)(box_offsets[f] + r) * 5 + 5);
-            sub_off[f + 1] = sub_off[f] + (has ? 1 : 0);
-        }
-        const int n_sub = sub_off[n_frames];
-        c->yaw_override = next_yaw; /* rank 0: all NaN, the raw pose */
-        rc = store_batch(c, imgs, n_frames, width, height, stride, channels, T_wc, sub_boxes.data(), sub_off.data(), lines, line_offsets, params);
+    /* one pass (cs_carried.h): the ordinary kernels over the rank-r boxes, then -- unless it is the last pass -- the candidate records of
+     * each box's last height sample come back and the host works out which hypothesis the reference's cam_pose would hold */
+    auto run_pass = [&](const double *sub_boxes, const int32_t *sub_off, const std::vector<double> &cam_yaw, cs_cuboid_rec *recs, int32_t *counts,
+                        std::vector<double> *yaw_left) -> int {
+        c->yaw_override = cam_yaw;
+        int rc = store_batch(c, imgs, n_frames, width, height, stride, channels, T_wc, sub_boxes, sub_off, lines, line_offsets, params);
         c->yaw_override.clear(); /* the override belongs to this pass only */
-        if (rc) break;
-        if ((rc = run_batch(c, false))) break;
-        tmp_out.assign((size_t)n_sub * topk, cs_cuboid_rec());
-        tmp_cnt.assign((size_t)n_sub, 0);
-        if ((rc = fetch(c, tmp_out.data(), tmp_cnt.data()))) break;
-        for (int f = 0; f < n_frames; f++)
-            if (sub_off[f + 1] > sub_off[f]) {
-                const size_t dst = (size_t)(box_offsets[f] + r), src = (size_t)sub_off[f];
-                std::memcpy(&out[dst * topk], &tmp_out[src * topk], sizeof(cs_cuboid_rec) * topk);
-                out_counts[dst] = tmp_cnt[src];
-            }
-        if (r + 1 == max_rank) break;
-        /* the pose each of these boxes leaves behind: its last height sample decides (every height sample starts with the sampling loop) */
+        if (rc) return rc;
+        if ((rc = run_batch(c, false))) return rc;
+        if ((rc = fetch(c, recs, counts))) return rc;
+        if (!yaw_left) return CS_OK;
         const size_t nc = (size_t)c->total_cand;
         h_valid.resize(std::max<size_t>(nc, 1));
         h_dist.resize(std::max<size_t>(nc, 1));
         h_angle.resize(std::max<size_t>(nc, 1));
-        if (nc) {
-            if (cudaMemcpyAsync(h_valid.data(), c->d_cvalid.p, nc, cudaMemcpyDeviceToHost, c->stream) != cudaSuccess ||
-                cudaMemcpyAsync(h_dist.data(), c->d_cdist.p, nc * 8, cudaMemcpyDeviceToHost, c->stream) != cudaSuccess ||
-                cudaMemcpyAsync(h_angle.data(), c->d_cangle.p, nc * 8, cudaMemcpyDeviceToHost, c->stream) != cudaSuccess ||
-                cudaStreamSynchronize(c->stream) != cudaSuccess) {
-                rc = fail(c, CS_ERR_CUDA, "candidate record copy failed: %s", cudaGetErrorString(cudaGetLastError()));
-                break;
-            }
-        }
-        std::fill(next_yaw.begin(), next_yaw.end(), std::nan(""));
-        for (size_t o = 0; o < c->objs.size(); o++) {
+        if (nc && (cudaMemcpyAsync(h_valid.data(), c->d_cvalid.p, nc, cudaMemcpyDeviceToHost, c->stream) != cudaSuccess ||
+                   cudaMemcpyAsync(h_dist.data(), c->d_cdist.p, nc * 8, cudaMemcpyDeviceToHost, c->stream) != cudaSuccess ||
+                   cudaMemcpyAsync(h_angle.data(), c->d_cangle.p, nc * 8, cudaMemcpyDeviceToHost, c->stream) != cudaSuccess ||
+                   cudaStreamSynchronize(c->stream) != cudaSuccess))
+            return fail(c, CS_ERR_CUDA, "candidate record copy failed: %s", cudaGetErrorString(cudaGetLastError()));
+        for (size_t o = 0; o < c->objs.size(); o++) { /* every height sample starts with the sampling loop: the last one decides */
             const CsObj &ob = c->objs[o];
             const CsFrame &fr = c->frames[ob.frame];
             int hyp = fr.n_pose - 1;
@@ -715,9 +688,11 @@ int detect_batch_carried(cs_ctx *c, const uint8_t *imgs, int n_frames, int width
                 const CsJob &jb = c->jobs[(size_t)ob.job_off + ob.n_jobs - 1];
                 hyp = last_set_pose(&h_valid[jb.cand_off], &h_dist[jb.cand_off], &h_angle[jb.cand_off], jb.n_cand, fr.n_pose);
             }
-            next_yaw[ob.frame] = c->poses[(size_t)fr.pose_off + hyp].camera_yaw;
+            (*yaw_left)[ob.frame] = c->poses[(size_t)fr.pose_off + hyp].camera_yaw;
         }
-    }
+        return CS_OK;
+    };
+    const int rc = cs_carried_passes(n_frames, boxes, box_offsets, params->max_cuboid_num, out, out_counts, run_pass);
     c->yaw_override.clear();
     return rc;
 }

@@ -434,6 +434,12 @@ extern "C" void orc_set_cut_flip(int box) { g_cut_flip = box; } /* -1: none */
  * the default does, so that tests/test_sampling_deviation.py can count how often the two ways differ and the GPU test can pin the default. */
 static thread_local int g_independent_boxes = 0;
 extern "C" void orc_set_independent_boxes(int on) { g_independent_boxes = on; }
+/* Two more test hooks for the same subject (tests/host_core/carried_emu.cpp lets the oracle stand in for the device under the product's
+ * pass structure): the camera yaw the FIRST box of the next call derives its yaw samples from, as if an earlier box had left it (NaN, the
+ * default: the pose's own), and the camera yaw the last call left behind after its last box. */
+static thread_local double g_first_box_cam_yaw = NAN, g_cam_yaw_left = NAN;
+extern "C" void orc_set_first_box_cam_yaw(double yaw) { g_first_box_cam_yaw = yaw; }
+extern "C" double orc_cam_yaw_left(void) { return g_cam_yaw_left; }
 
 /* object_3d_util.cpp:495-565 */
 void fuse_normalize_scores_v2(const std::vector<double> &dist_error, const std::vector<double> &angle_error,
@@ -844,7 +850,8 @@ extern "C" int orc_detect_cuboid(const uint8_t *img, int w, int h, int stride, i
             cam = cam_raw;
             plane_to_sensor(cam.T, ground_plane_world, ground_plane_sensor);
         }
-        const double yaw_init = cam.yaw - 90.0 / 180.0 * M_PI;
+        const double cam_yaw_now = (object_id == 0 && !std::isnan(g_first_box_cam_yaw)) ? g_first_box_cam_yaw : cam.yaw;
+        const double yaw_init = cam_yaw_now - 90.0 / 180.0 * M_PI;
         std::vector<double> obj_yaw_samples;
         linespace<double>(yaw_init - p.yaw_half_range_deg / 180.0 * M_PI, yaw_init + p.yaw_half_range_deg / 180.0 * M_PI,
                           p.yaw_step_deg / 180.0 * M_PI, obj_yaw_samples);
@@ -1122,5 +1129,6 @@ extern "C" int orc_detect_cuboid(const uint8_t *img, int w, int h, int stride, i
         for (int i = 0; i < actual; i++) out[(size_t)object_id * topk_cap + i] = raw_obj_proposals[order[i]];
         out_counts[object_id] = actual;
     }
+    g_cam_yaw_left = cam.yaw;
     return 0;
 }

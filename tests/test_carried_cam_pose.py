@@ -123,3 +123,65 @@ def test_every_branch_on_synthetic_records(L):
             hit["intersection" if angle[v][srt[bn - 1]] > angle[v][srt[bn - 2]] else "saturated"] += 1
     assert all(c > 5 for c in hit.values()), hit
     assert _last_pose(L, np.zeros(50, np.uint8), np.zeros(50), np.zeros(50), 25) == 24      # no valid proposal at all
+
+
+def test_pass_structure_with_the_oracle_as_the_device(oracle):
+    """cs_carried_passes (cube_slam_b200/csrc/cs_carried.h: what bit 10 runs) with the oracle standing in for the device
+    (tests/host_core/carried_emu.cpp): one-box calls chained by the camera yaw alone reproduce the reference's loop over the boxes of a frame
+    -- on frames where that chaining changes the number of yaw samples, on ordinary ones, on frames with one box or none, with height sampling."""
+    import os
+    import subprocess
+    from cube_slam_b200 import _lib, synthetic as S
+    here = os.path.dirname(os.path.abspath(__file__))
+    src = os.path.join(here, "host_core", "carried_emu.cpp")
+    out = os.path.join(here, "host_core", "_build", "libcarriedemu.so")
+    orc = os.path.abspath(os.path.join(here, "..", "oracle", "_build"))
+    oracle.build()
+    deps = [src, os.path.join(here, "..", "cube_slam_b200", "csrc", "cs_carried.h"), os.path.join(orc, "liboracle.so")]
+    os.makedirs(os.path.dirname(out), exist_ok=True)
+    if not os.path.exists(out) or os.path.getmtime(out) < max(os.path.getmtime(d) for d in deps):
+        subprocess.check_call(["g++", "-std=c++17", "-O2", "-fPIC", "-shared", "-ffp-contract=off", "-o", out, src, "-L", orc, "-loracle", "-Wl,-rpath," + orc])
+    E = C.CDLL(out)
+    OL = oracle.lib()
+    differed = 0
+    for seed, pick in ((102, (10, 3, 0)), (104, (1, 0, 5))):
+        imgs, Ts, boxes, lines, K = S.make_batch(seed, 12, 640, 480, 3, poisson=True)
+        sel = list(pick)
+        imgs = np.ascontiguousarray(imgs[sel])
+        Ts = np.ascontiguousarray(np.asarray(Ts)[sel], np.float64)
+        boxes = [np.asarray(boxes[i], np.float64).reshape(-1, 5) for i in sel] + [np.zeros((0, 5))]       # ... and a frame without boxes
+        lines = [np.asarray(lines[i], np.float64).reshape(-1, 4) for i in sel]
+        imgs = np.ascontiguousarray(np.concatenate([imgs, imgs[:1]]))
+        Ts = np.ascontiguousarray(np.concatenate([Ts, Ts[:1]]))
+        lines.append(lines[0])
+        F, H, W = imgs.shape[:3]
+        box_off = np.concatenate([[0], np.cumsum([len(b) for b in boxes])]).astype(np.int32)
+        line_off = np.concatenate([[0], np.cumsum([len(l) for l in lines])]).astype(np.int32)
+        all_boxes = np.ascontiguousarray(np.concatenate(boxes))
+        all_lines = np.ascontiguousarray(np.concatenate(lines))
+        for kw in (dict(whether_sample_cam_roll_pitch=1, max_cuboid_num=3), dict(whether_sample_cam_roll_pitch=1, whether_sample_bbox_height=1, max_cuboid_num=2)):
+            p = oracle.default_params(**kw)
+            topk = int(p.max_cuboid_num)
+            out_recs = np.zeros((int(box_off[-1]), topk), _lib.CUBOID_DTYPE)
+            counts = np.zeros(int(box_off[-1]), np.int32)
+            n_passes = C.c_int32(0)
+            Kc = np.ascontiguousarray(K, np.float64)
+            rc = E.emu_carried(imgs.ctypes.data_as(C.POINTER(C.c_uint8)), F, W, H, W * 3, 3, _p(Kc, C.c_double), _p(Ts, C.c_double), _p(all_boxes, C.c_double),
+                               _p(box_off, C.c_int32), _p(all_lines, C.c_double), _p(line_off, C.c_int32), C.byref(p), out_recs.ctypes.data_as(C.c_void_p),
+                               _p(counts, C.c_int32), C.byref(n_passes))
+            assert rc == 0 and n_passes.value == max(len(b) for b in boxes) == 3
+            o = 0
+            for f in range(F):
+                if len(boxes[f]) == 0:
+                    continue
+                ref = oracle.detect_cuboid(imgs[f], K, Ts[f], boxes[f], lines[f], p)                    # the reference's loop over the boxes
+                OL.orc_set_independent_boxes(1)
+                ind = oracle.detect_cuboid(imgs[f], K, Ts[f], boxes[f], lines[f], p)
+                OL.orc_set_independent_boxes(0)
+                for b in range(len(boxes[f])):
+                    assert counts[o] == len(ref["cuboids"][b])
+                    got = out_recs[o, :counts[o]]
+                    assert got.tobytes() == ref["cuboids"][b].view(_lib.CUBOID_DTYPE).tobytes() if got.dtype != ref["cuboids"][b].dtype else got.tobytes() == ref["cuboids"][b].tobytes()
+                    differed += int(got.tobytes() != ind["cuboids"][b].tobytes())
+                    o += 1
+    assert differed >= 4        # the chosen frames are ones where starting every box from the raw pose gives other records
