@@ -288,6 +288,10 @@ class detect_3d_cuboid(object):
         self.nominal_skew_ratio = 1.0
         self.max_cut_skew = 3.0
         self._ctx = Context(device, max_width, max_height, 1, max_boxes, max_lines)
+        # the class mirror keeps the reference's semantics to the letter: with whether_sample_cam_roll_pitch, later boxes of a frame start
+        # from the cam_pose the earlier ones left (cs_set_profiling bit 10, one pass per box rank).  A frame with a
+        # single box -- all object_slam ever passes -- takes the ordinary one-pass path either way.
+        self._ctx.check(self._ctx.L.cs_set_profiling(self._ctx.h, 1024))
         self._K = None
 
     def params(self):

@@ -285,3 +285,24 @@ def test_sampled_frames_with_several_boxes_default_and_carried_pose(oracle):
                     differs = differs or out.tobytes() != prev
                 prev = out.tobytes()
             assert differs, "the two modes returned the same records on frames chosen because they differ"
+
+
+def test_class_mirror_carries_the_pose_like_the_reference(oracle):
+    """cs.detect_3d_cuboid (the Python mirror of the class, like the C++ shim) turns bit 10 on: a sampled frame with three boxes gives the
+    oracle's -- the reference's -- cuboids for every box, on a frame where starting from the raw pose would not."""
+    import cube_slam_b200 as cs
+    from cube_slam_b200 import synthetic as S
+    from test_gpu_cuboid_parity import _compare_cuboid
+    imgs, Ts, boxes, lines, K = S.make_batch(102, 12, 640, 480, 3, poisson=True)
+    f = 10
+    det = cs.detect_3d_cuboid()
+    det.set_calibration(K)
+    det.whether_sample_cam_roll_pitch = True
+    det.max_cuboid_num = 3
+    got = det.detect_cuboid(imgs[f], Ts[f], boxes[f], lines[f])
+    ref = oracle.detect_cuboid(imgs[f], K, Ts[f], boxes[f], np.asarray(lines[f], float), oracle.default_params(whether_sample_cam_roll_pitch=1, max_cuboid_num=3))
+    assert len(got) == len(boxes[f]) == 3
+    for b in range(3):
+        assert len(got[b]) == len(ref["cuboids"][b])
+        for k in range(len(got[b])):
+            _compare_cuboid({name: getattr(got[b][k], name) for name in got[b][k].__slots__}, ref["cuboids"][b][k])
