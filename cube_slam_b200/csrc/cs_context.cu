@@ -686,7 +686,7 @@ int detect_batch_carried(cs_ctx *c, const uint8_t *imgs, int n_frames, int width
             int hyp = fr.n_pose - 1;
             if (ob.n_jobs > 0) {
                 const CsJob &jb = c->jobs[(size_t)ob.job_off + ob.n_jobs - 1];
-                hyp = last_set_pose(&h_valid[jb.cand_off], &h_dist[jb.cand_off], &h_angle[jb.cand_off], jb.n_cand, fr.n_pose);
+                hyp = last_set_pose(h_valid.data() + jb.cand_off, h_dist.data() + jb.cand_off, h_angle.data() + jb.cand_off, jb.n_cand, fr.n_pose);
             }
             (*yaw_left)[ob.frame] = c->poses[(size_t)fr.pose_off + hyp].camera_yaw;
         }
