@@ -10,7 +10,6 @@ import ctypes as C
 import os
 import subprocess
 
-import numpy as np
 import pytest
 
 HERE = os.path.dirname(os.path.abspath(__file__))
