@@ -113,3 +113,34 @@ extern "C" void emu_ctx_free(cs_ctx *c)
 }
 extern "C" const char *emu_last_error(cs_ctx *c) { return c->err; }
 extern "C" long long emu_launches(cs_ctx *c) { return c->launches; }
+
+#ifdef CS_EMU_WITH_SHIM_GLUE
+/* The rest of the C ABI that shim/line_lbd_b200.cpp binds, so that the C++ shim and its driver (shim/test/line_shim_driver.cpp) can be
+ * linked against this emulated build and run on the CPU (tests/test_lbd_host_emu.py): context management as trivial stand-ins, cs_detect_lines
+ * answered from the oracle like the detector entry points above. */
+extern "C" int edl_orc_detect(const uint8_t *img, int w, int h, int stride, int channels, float line_length_thres, float *lines_out, int cap, float *raw_lines,
+                              int cap_raw, int *n_raw_out, uint8_t *blur_out, int16_t *dx_out, int16_t *dy_out, int16_t *g_out, uint8_t *dir_out,
+                              int32_t *anchors_out, int *n_anchors_out, uint8_t *edge_out);
+extern "C" cs_ctx *cs_create(int, int, int, int, int, int) { return new cs_ctx(); }
+extern "C" void cs_destroy(cs_ctx *c) { emu_ctx_free(c); }
+extern "C" const char *cs_last_error(const cs_ctx *c) { return c ? c->err : "null context"; }
+extern "C" void cs_default_line_params(cs_line_params *p)
+{
+    p->use_LSD = 0;
+    p->numoctaves = 1;
+    p->octaveratio = 1.f;
+    p->line_length_thres = 50;
+}
+extern "C" int cs_detect_lines(cs_ctx *c, const uint8_t *img, int width, int height, int stride, int channels, const cs_line_params *params, float *lines_xyxy,
+                               int32_t *n_inout)
+{
+    const int cap = *n_inout;
+    const int n = params->use_LSD ? lsd_orc_detect(img, width, height, stride, channels, params->line_length_thres, lines_xyxy, cap, nullptr, 0, nullptr, nullptr,
+                                                   nullptr, nullptr, nullptr, nullptr, 2)
+                                  : edl_orc_detect(img, width, height, stride, channels, params->line_length_thres, lines_xyxy, cap, nullptr, 0, nullptr, nullptr,
+                                                   nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr);
+    if (n < 0 || n > cap) return cs_ctx_fail(c, CS_ERR_CAPACITY, "line detection failed (%d)", n);
+    *n_inout = n;
+    return CS_OK;
+}
+#endif

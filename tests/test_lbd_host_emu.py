@@ -93,6 +93,28 @@ def test_against_the_committed_goldens(det):
     G.test_against_the_committed_goldens(det)
 
 
+def test_cpp_shim_members_linked_against_the_emulated_library(oracle, fixture_a, fixture_b, monkeypatch):
+    """shim/line_lbd_b200.cpp + shim/test/line_shim_driver.cpp -- the C++ a maintainer compiles into the reference's line_lbd package -- built
+    against the reference's own class header as always, but linked against the emulated build of the library instead of libcubeslam_b200.so:
+    the GPU test of the shim's descriptor / matcher members, run on the CPU.  Needs the reference checkout (its headers), like oracle/_ref."""
+    ref_inc = "/root/reference/line_lbd/include"
+    if not os.path.isdir(ref_inc):
+        pytest.skip("the reference's headers are not on this machine")
+    root = os.path.join(HERE, "..")
+    out = os.path.join(HERE, "host_core", "_build", "libshim_line_emu.so")
+    orc = os.path.abspath(os.path.join(root, "oracle", "_build"))
+    srcs = [os.path.join(root, "shim", "line_lbd_b200.cpp"), os.path.join(root, "shim", "test", "line_shim_driver.cpp"), os.path.join(HERE, "host_core", "lbd_host_emu.cpp")]
+    deps = srcs + [os.path.join(root, "cube_slam_b200", "csrc", f) for f in ("cs_lbd.cu", "cs_lbd_core.h", "cs_lbd_kernels.cuh")] + [os.path.join(root, "include", "cube_slam_b200.h")]
+    os.makedirs(os.path.dirname(out), exist_ok=True)
+    if not os.path.exists(out) or os.path.getmtime(out) < max(os.path.getmtime(d) for d in deps):
+        subprocess.check_call(["g++", "-std=c++20", "-O2", "-fPIC", "-shared", "-pthread", "-w", "-ffp-contract=off", "-fno-fast-math", "-DCS_EMU_WITH_SHIM_GLUE",
+                               "-I", os.path.join(root, "include"), "-I", os.path.join(root, "oracle", "ref", "fakecv"), "-I", ref_inc, "-o", out] + srcs +
+                              ["-L", orc, "-loracle", "-Wl,-rpath," + orc])
+    monkeypatch.setattr(G, "SHIM", out)
+    for use_lsd in (1, 0):
+        G.test_cpp_shim_descriptor_and_matcher_members(oracle, fixture_a, fixture_b, use_lsd)
+
+
 def test_detect_raw_lines_is_not_part_of_this_rehearsal(det):
     """detect_raw_lines goes through cs_detect_lines_batch (cs_lsd.cu / cs_edlines.cu, verified on the GPU since round 1), not cs_lbd.cu."""
     assert "cs_detect_lines_batch" not in DEVICE_ENTRY_POINTS
