@@ -63,7 +63,7 @@ template <typename F> static void emu_launch(unsigned grid, unsigned block, F &&
 typedef int cudaError_t;
 typedef void *cudaStream_t;
 enum { cudaSuccess = 0 };
-enum cudaMemcpyKind { cudaMemcpyHostToDevice = 1, cudaMemcpyDeviceToHost = 2 };
+enum cudaMemcpyKind { cudaMemcpyHostToDevice = 1, cudaMemcpyDeviceToHost = 2, cudaMemcpyDeviceToDevice = 3 };
 static inline cudaError_t cudaMalloc(void **p, size_t n)
 {
     *p = std::aligned_alloc(256, (n + 255) / 256 * 256);

@@ -185,3 +185,74 @@ def test_pass_structure_with_the_oracle_as_the_device(oracle):
                     differed += int(got.tobytes() != ind["cuboids"][b].tobytes())
                     o += 1
     assert differed >= 4        # the chosen frames are ones where starting every box from the raw pose gives other records
+
+
+def test_the_librarys_own_host_code_with_the_oracle_as_the_device(oracle):
+    """cs_context.cu itself compiled for the host (tests/host_core/context_emu.cpp: CUDA runtime calls inert, every kernel launcher a no-op
+    except the last stage's, which fills records and candidate records from the oracle using the camera yaw the library's own yaw table
+    was derived from).  cs_detect_cuboids_batch with bit 10 on sampled multi-box frames then returns the reference's cuboids byte for byte --
+    and without bit 10 the independent-boxes ones: the real pass loop, the yaw override reaching build_tables, job / candidate offsets,
+    last_set_pose, the pose-table lookup and the scatter, all exercised without a GPU."""
+    import os
+    import subprocess
+    from cube_slam_b200 import _lib, synthetic as S
+    here = os.path.dirname(os.path.abspath(__file__))
+    root = os.path.join(here, "..")
+    src = os.path.join(here, "host_core", "context_emu.cpp")
+    out = os.path.join(here, "host_core", "_build", "libcontextemu.so")
+    orc = os.path.abspath(os.path.join(root, "oracle", "_build"))
+    csrc = os.path.join(root, "cube_slam_b200", "csrc")
+    oracle.build()
+    deps = [src, os.path.join(here, "host_core", "cuda_emu.h"), os.path.join(here, "host_core", "fake_cuda", "cuda_runtime.h"), os.path.join(orc, "liboracle.so")]
+    deps += [os.path.join(csrc, f) for f in ("cs_context.cu", "cs_carried.h", "cs_internal.h", "cs_kernels.h", "cs_host_pose.cpp", "cs_host_pose.h", "cs_nccl_impl.inc")]
+    os.makedirs(os.path.dirname(out), exist_ok=True)
+    if not os.path.exists(out) or os.path.getmtime(out) < max(os.path.getmtime(d) for d in deps):
+        subprocess.check_call(["g++", "-std=c++20", "-O1", "-fPIC", "-shared", "-pthread", "-ffp-contract=off", "-fno-fast-math", "-I", os.path.join(here, "host_core", "fake_cuda"),
+                               "-x", "c++", "-o", out, src, os.path.join(csrc, "cs_host_pose.cpp"), "-L", orc, "-loracle", "-ldl", "-Wl,-rpath," + orc])
+    E = C.CDLL(out)
+    E.cs_create.restype = C.c_void_p
+    E.cs_last_error.restype = C.c_char_p
+    OL = oracle.lib()
+    for seed, pick in ((102, (10, 3, 0)), (104, (1, 0, 5))):
+        imgs, Ts, boxes, lines, K = S.make_batch(seed, 12, 640, 480, 3, poisson=True)
+        sel = list(pick)
+        imgs = np.ascontiguousarray(imgs[sel])
+        Ts = np.ascontiguousarray(np.asarray(Ts)[sel], np.float64)
+        boxes = [np.asarray(boxes[i], np.float64).reshape(-1, 5) for i in sel]
+        lines = [np.asarray(lines[i], np.float64).reshape(-1, 4) for i in sel]
+        F, H, W = imgs.shape[:3]
+        box_off = np.concatenate([[0], np.cumsum([len(b) for b in boxes])]).astype(np.int32)
+        line_off = np.concatenate([[0], np.cumsum([len(l) for l in lines])]).astype(np.int32)
+        all_boxes, all_lines = np.ascontiguousarray(np.concatenate(boxes)), np.ascontiguousarray(np.concatenate(lines))
+        Kc = np.ascontiguousarray(K, np.float64)
+        for kw in (dict(whether_sample_cam_roll_pitch=1, max_cuboid_num=3), dict(whether_sample_cam_roll_pitch=1, whether_sample_bbox_height=1, max_cuboid_num=2)):
+            prm = _lib.CuboidParams()
+            _lib.load().cs_default_cuboid_params(C.byref(prm))
+            for k, v in kw.items():
+                setattr(prm, k, v)
+            topk = kw["max_cuboid_num"]
+            outs = {}
+            for carried in (1, 0):
+                ctx = C.c_void_p(E.cs_create(0, 640, 480, F, 16, 4096))
+                assert E.cs_set_calibration(ctx, _p(Kc, C.c_double)) == 0
+                assert E.cs_set_profiling(ctx, 1024 if carried else 0) == 0
+                rec = np.zeros((int(box_off[-1]), topk), _lib.CUBOID_DTYPE)
+                cnt = np.zeros(int(box_off[-1]), np.int32)
+                rc = E.emu_detect_cuboids_batch(ctx, imgs.ctypes.data_as(C.POINTER(C.c_uint8)), F, W, H, W * 3, 3, _p(Ts, C.c_double), _p(all_boxes, C.c_double), _p(box_off, C.c_int32),
+                                                _p(all_lines, C.c_double), _p(line_off, C.c_int32), C.byref(prm), rec.ctypes.data_as(C.c_void_p), _p(cnt, C.c_int32))
+                assert rc == 0, E.cs_last_error(ctx)
+                assert E.emu_mismatch() == 0
+                E.cs_destroy(ctx)
+                outs[carried] = rec.tobytes()
+                o = 0
+                OL.orc_set_independent_boxes(0 if carried else 1)
+                try:
+                    for f in range(F):
+                        ref = oracle.detect_cuboid(imgs[f], K, Ts[f], boxes[f], lines[f], oracle.default_params(**kw))
+                        for b in range(len(boxes[f])):
+                            assert cnt[o] == len(ref["cuboids"][b])
+                            assert rec[o, :cnt[o]].tobytes() == ref["cuboids"][b].tobytes(), (seed, f, b, carried)
+                            o += 1
+                finally:
+                    OL.orc_set_independent_boxes(0)
+            assert outs[0] != outs[1]
