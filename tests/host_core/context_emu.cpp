@@ -9,7 +9,9 @@
  * never shipped.  g++ -std=c++20 -I tests/host_core/fake_cuda ... cs_host_pose.cpp, linked against oracle/_build/liboracle.so. */
 #include <cuda_runtime.h> /* tests/host_core/fake_cuda */
 
+#define cs_create cs_create_in_library /* wrapped below: the stand-in launchers need to know which context is running */
 #include "../../cube_slam_b200/csrc/cs_context.cu"
+#undef cs_create
 
 #include "../../oracle/orc_api.h"
 
@@ -155,3 +157,11 @@ extern "C" int emu_detect_cuboids_batch(cs_ctx *c, const uint8_t *imgs, int n_fr
     return cs_detect_cuboids_batch(c, imgs, n_frames, width, height, stride, channels, T_wc, boxes, box_offsets, lines, line_offsets, params, out, out_counts);
 }
 extern "C" int emu_mismatch(void) { return g_mismatch; }
+
+/* cs_create as the Python mirror calls it: the library's own, plus a note of the context for the stand-in launchers (one context at a time) */
+extern "C" cs_ctx *cs_create(int device, int max_width, int max_height, int max_frames, int max_boxes_per_frame, int max_lines_per_frame)
+{
+    g_cur = cs_create_in_library(device, max_width, max_height, max_frames, max_boxes_per_frame, max_lines_per_frame);
+    g_mismatch = 0;
+    return g_cur;
+}

@@ -187,28 +187,33 @@ def test_pass_structure_with_the_oracle_as_the_device(oracle):
     assert differed >= 4        # the chosen frames are ones where starting every box from the raw pose gives other records
 
 
+def _build_context_emu(oracle):
+    import os
+    import subprocess
+    here = os.path.dirname(os.path.abspath(__file__))
+    root = os.path.join(here, "..")
+    srcs = [os.path.join(here, "host_core", "context_emu.cpp"), os.path.join(here, "host_core", "context_emu_absent.cpp")]
+    out = os.path.join(here, "host_core", "_build", "libcontextemu.so")
+    orc = os.path.abspath(os.path.join(root, "oracle", "_build"))
+    csrc = os.path.join(root, "cube_slam_b200", "csrc")
+    oracle.build()
+    deps = srcs + [os.path.join(here, "host_core", "cuda_emu.h"), os.path.join(here, "host_core", "fake_cuda", "cuda_runtime.h"), os.path.join(orc, "liboracle.so")]
+    deps += [os.path.join(csrc, f) for f in ("cs_context.cu", "cs_carried.h", "cs_internal.h", "cs_kernels.h", "cs_host_pose.cpp", "cs_host_pose.h", "cs_nccl_impl.inc")]
+    os.makedirs(os.path.dirname(out), exist_ok=True)
+    if not os.path.exists(out) or os.path.getmtime(out) < max(os.path.getmtime(d) for d in deps):
+        subprocess.check_call(["g++", "-std=c++20", "-O1", "-fPIC", "-shared", "-pthread", "-ffp-contract=off", "-fno-fast-math", "-I", os.path.join(here, "host_core", "fake_cuda"),
+                               "-x", "c++", "-o", out] + srcs + [os.path.join(csrc, "cs_host_pose.cpp"), "-L", orc, "-loracle", "-ldl", "-Wl,-rpath," + orc])
+    return out
+
+
 def test_the_librarys_own_host_code_with_the_oracle_as_the_device(oracle):
     """cs_context.cu itself compiled for the host (tests/host_core/context_emu.cpp: CUDA runtime calls inert, every kernel launcher a no-op
     except the last stage's, which fills records and candidate records from the oracle using the camera yaw the library's own yaw table
     was derived from).  cs_detect_cuboids_batch with bit 10 on sampled multi-box frames then returns the reference's cuboids byte for byte --
     and without bit 10 the independent-boxes ones: the real pass loop, the yaw override reaching build_tables, job / candidate offsets,
     last_set_pose, the pose-table lookup and the scatter, all exercised without a GPU."""
-    import os
-    import subprocess
     from cube_slam_b200 import _lib, synthetic as S
-    here = os.path.dirname(os.path.abspath(__file__))
-    root = os.path.join(here, "..")
-    src = os.path.join(here, "host_core", "context_emu.cpp")
-    out = os.path.join(here, "host_core", "_build", "libcontextemu.so")
-    orc = os.path.abspath(os.path.join(root, "oracle", "_build"))
-    csrc = os.path.join(root, "cube_slam_b200", "csrc")
-    oracle.build()
-    deps = [src, os.path.join(here, "host_core", "cuda_emu.h"), os.path.join(here, "host_core", "fake_cuda", "cuda_runtime.h"), os.path.join(orc, "liboracle.so")]
-    deps += [os.path.join(csrc, f) for f in ("cs_context.cu", "cs_carried.h", "cs_internal.h", "cs_kernels.h", "cs_host_pose.cpp", "cs_host_pose.h", "cs_nccl_impl.inc")]
-    os.makedirs(os.path.dirname(out), exist_ok=True)
-    if not os.path.exists(out) or os.path.getmtime(out) < max(os.path.getmtime(d) for d in deps):
-        subprocess.check_call(["g++", "-std=c++20", "-O1", "-fPIC", "-shared", "-pthread", "-ffp-contract=off", "-fno-fast-math", "-I", os.path.join(here, "host_core", "fake_cuda"),
-                               "-x", "c++", "-o", out, src, os.path.join(csrc, "cs_host_pose.cpp"), "-L", orc, "-loracle", "-ldl", "-Wl,-rpath," + orc])
+    out = _build_context_emu(oracle)
     E = C.CDLL(out)
     E.cs_create.restype = C.c_void_p
     E.cs_last_error.restype = C.c_char_p
@@ -256,3 +261,18 @@ def test_the_librarys_own_host_code_with_the_oracle_as_the_device(oracle):
                 finally:
                     OL.orc_set_independent_boxes(0)
             assert outs[0] != outs[1]
+
+
+def test_gpu_tests_of_the_carried_pose_rehearsed_through_the_python_package(oracle, monkeypatch):
+    """The Python package bound to the emulated build instead of libcubeslam_b200.so (cube_slam_b200/_lib.py's loader pointed at it), and the two
+    GPU tests of this subject run as they are: Context / detect_batch_host with and without bit 10, and the class mirror cs.detect_3d_cuboid."""
+    import sys
+    from cube_slam_b200 import _lib
+    import test_z_gpu_lbd_parity as G
+    monkeypatch.setattr(_lib, "LIB_PATH", _build_context_emu(oracle))
+    monkeypatch.setattr(_lib, "_lib", None)
+    try:
+        G.test_sampled_frames_with_several_boxes_default_and_carried_pose(oracle)
+        G.test_class_mirror_carries_the_pose_like_the_reference(oracle)
+    finally:
+        _lib._lib = None       # the next user gets the real library again
