@@ -15,6 +15,23 @@ def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
 
 
+def pytest_collection_modifyitems(config, items):
+    """tests/test_z_gpu_lbd_parity.py holds the GPU tests of code that has not run on a GPU yet.  Within it, the cases that depend on the one
+    change made to kernels that HAVE been verified -- the EDLines kernels' two extra stores per kept segment (direction, numOfPixels; parameter
+    values False / 0 / "edlines") -- go last, so that with -x a problem there cannot hide the results of everything else."""
+    z = [i for i, it in enumerate(items) if it.fspath.basename == "test_z_gpu_lbd_parity.py"]
+    if not z:
+        return
+
+    def late(it):
+        cs = getattr(it, "callspec", None)
+        return cs is not None and any(v is False or v == "edlines" or (v == 0 and not isinstance(v, bool)) for v in cs.params.values())
+    block = [items[i] for i in z]
+    block = [it for it in block if not late(it)] + [it for it in block if late(it)]
+    for i, it in zip(z, block):
+        items[i] = it
+
+
 def _imread(path):
     import cv2
     img = cv2.imread(path, 1)

@@ -77,8 +77,9 @@ def test_batches(det, oracle, fixture_b, use_lsd):
     G.test_batches_of_sequence_and_synthetic_frames(det, oracle, fixture_b, use_lsd)
 
 
-def test_mat_overload_octaves_variant_and_gray_input(det, oracle, fixture_a):
-    G.test_mat_overload_octaves_variant_and_gray_input(det, oracle, fixture_a)
+@pytest.mark.parametrize("use_lsd", [True, False])
+def test_mat_overload_octaves_variant_and_gray_input(det, oracle, fixture_a, use_lsd):
+    G.test_mat_overload_octaves_variant_and_gray_input(det, oracle, fixture_a, use_lsd)
 
 
 def test_given_keylines_border_and_degenerate_lines(det, oracle):
@@ -89,8 +90,9 @@ def test_match_line_descrip(det, oracle, fixture_b):
     G.test_match_line_descrip(det, oracle, fixture_b)
 
 
-def test_against_the_committed_goldens(det):
-    G.test_against_the_committed_goldens(det)
+@pytest.mark.parametrize("flavour", ["lsd", "edlines"])
+def test_against_the_committed_goldens(det, flavour):
+    G.test_against_the_committed_goldens(det, flavour)
 
 
 def test_cpp_shim_members_linked_against_the_emulated_library(oracle, fixture_a, fixture_b, monkeypatch):

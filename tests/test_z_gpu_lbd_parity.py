@@ -65,11 +65,12 @@ def test_batches_of_sequence_and_synthetic_frames(det, oracle, fixture_b, use_ls
             np.testing.assert_array_equal(desc, oracle.lbd_compute(imgs[f], want))
 
 
-def test_mat_overload_octaves_variant_and_gray_input(det, oracle, fixture_a):
+@pytest.mark.parametrize("use_lsd", [True, False])
+def test_mat_overload_octaves_variant_and_gray_input(det, oracle, fixture_a, use_lsd):
     import cv2
     img = fixture_a["img"]
     gray = cv2.cvtColor(img, cv2.COLOR_BGR2GRAY)
-    for use_lsd in (True, False):
+    for use_lsd in (use_lsd,):
         det.use_LSD = use_lsd
         # detect_descrip_lines(gray, lines_mat, descrips): every octave-0 line, no length filter (line_lbd_allclass.cpp:224-250)
         lines, desc = det.detect_descrip_lines(img, as_mat=True)
@@ -151,19 +152,22 @@ def test_match_line_descrip(det, oracle, fixture_b):
     assert len(m) >= 3
 
 
-def test_against_the_committed_goldens(det):
+@pytest.mark.parametrize("flavour", ["lsd", "edlines"])
+def test_against_the_committed_goldens(det, flavour):
     """No oracle in the loop: counts and checksums recorded by tools/make_golden_lbd.py after oracle == compiled reference held."""
     import cv2
     g = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "expected_lbd.json")))
     for case in g["frames"]:
         img = cv2.imread(os.path.join(os.path.dirname(__file__), "golden", case["image"]), 1)
-        for flav in ("lsd", "edlines"):
+        for flav in (flavour,):
             det.use_LSD = flav == "lsd"
             kl, desc = det.detect_descrip_lines(img)
             assert len(kl) == case[flav]["n"]
             assert zlib.crc32(np.ascontiguousarray(desc).tobytes()) == case[flav]["desc_crc32"]
             assert zlib.crc32(np.ascontiguousarray(kl["angle"]).tobytes()) == case[flav]["angle_crc32"]
             assert int(kl["num_pixels"].sum()) == case[flav]["num_pixels_sum"]
+    if flavour != "lsd":
+        return
     det.use_LSD = True
     imgs = [cv2.imread(os.path.join(os.path.dirname(__file__), "golden", p), 1) for p in g["match"]["images"]]
     (k0, d0), (k1, d1) = det.detect_descrip_lines_batch(np.stack(imgs))
@@ -232,7 +236,7 @@ def test_cpp_shim_descriptor_and_matcher_members(oracle, fixture_a, fixture_b, u
     np.testing.assert_array_equal(di[:n], wd)
 
 
-def test_detect_raw_lines_with_and_without_downsampling(det, oracle, fixture_a):
+def test_detect_raw_lines_with_and_without_downsampling(det, oracle, fixture_a):  # verified kernels only (cs_detect_lines_batch), both flavours
     """detect_raw_lines(gray, lines_mat, downsample_img) (line_lbd_allclass.cpp:174-189) through the Python mirror."""
     import cv2
     img = fixture_a["img"]
