@@ -26,7 +26,18 @@ static thread_local EmuDim3 threadIdx, blockIdx;
 static std::barrier<> *g_block_barrier = nullptr;
 static unsigned long long g_shfl[1024];
 
+#ifdef CS_EMU_DROP_BARRIER
+/* negative control for the racecheck build: every thread skips its CS_EMU_DROP_BARRIER-th __syncthreads (1-based) -- ThreadSanitizer must
+ * then report the accesses that barrier was ordering */
+static thread_local int g_sync_count = 0;
+static inline void __syncthreads()
+{
+    if (++g_sync_count == CS_EMU_DROP_BARRIER) return;
+    g_block_barrier->arrive_and_wait();
+}
+#else
 static inline void __syncthreads() { g_block_barrier->arrive_and_wait(); }
+#endif
 static inline unsigned long long __shfl_xor_sync(unsigned, unsigned long long v, int lane_mask)
 {
     g_shfl[threadIdx.x] = v;
@@ -51,6 +62,9 @@ template <typename F> static void emu_launch(unsigned grid, unsigned block, F &&
             th.emplace_back([&, t, b] {
                 threadIdx.x = t;
                 blockIdx.x = b;
+#ifdef CS_EMU_DROP_BARRIER
+                g_sync_count = 0;
+#endif
                 kernel();
                 bar.arrive_and_drop(); /* a thread that is done must not hold up the barriers the others still reach */
             });

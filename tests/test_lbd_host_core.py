@@ -248,6 +248,30 @@ def test_kernel_source_under_the_cuda_model_emulation_match(emu, core, oracle):
         np.testing.assert_array_equal((k & np.uint64(0xFFFFFFFF)).astype(np.int64)[wq][wd <= 128], wt[wd <= 128])
 
 
+def test_racecheck_of_the_kernels_under_threadsanitizer():
+    """compute-sanitizer's racecheck, without a GPU: the kernels' source under the thread-per-CUDA-thread emulation, built with
+    -fsanitize=thread.  No report as the kernels are; and -- the control that shows the check can see anything -- a report whenever any one of
+    k_lbd_describe's four barriers (k_lbd_match's one) is skipped."""
+    src = os.path.join(HERE, "host_core", "lbd_racecheck_main.cpp")
+    bdir = os.path.join(HERE, "host_core", "_build")
+    os.makedirs(bdir, exist_ok=True)
+
+    def build_and_run(extra, name):
+        exe = os.path.join(bdir, name)
+        subprocess.check_call(["g++", "-std=c++20", "-O1", "-g", "-fsanitize=thread", "-pthread", "-ffp-contract=off", "-o", exe, src] + extra)
+        r = subprocess.run([exe], capture_output=True, text=True, timeout=300)
+        return r.stdout + r.stderr
+
+    probe = subprocess.run(["g++", "-fsanitize=thread", "-x", "c++", "-", "-o", os.path.join(bdir, "tsan_probe")], input="int main(){return 0;}", text=True, capture_output=True)
+    if probe.returncode != 0:
+        pytest.skip("this g++ cannot link ThreadSanitizer")
+    out = build_and_run([], "lbd_racecheck")
+    assert "racecheck done" in out and "ThreadSanitizer" not in out, out[-2000:]
+    for n in (1, 2, 3, 4):
+        out = build_and_run(["-DCS_EMU_DROP_BARRIER=%d" % n], "lbd_racecheck_neg")
+        assert "WARNING: ThreadSanitizer: data race" in out, "dropping barrier %d went unnoticed" % n
+
+
 def test_pattern_order_is_numeric_order(oracle):
     """cs_lbd_match_key orders the s-bit xor patterns of a byte by their value; Mihasher::query's enumeration (restated in the oracle, which
     is pinned to the reference's matches) visits them in exactly that order."""
